@@ -1,0 +1,162 @@
+"""Generate tests/golden/*.npz from the REFERENCE ITSELF (run in the build container only).
+
+    python oracle/make_golden.py            # needs /root/reference (read-only mount)
+
+The reference (the diffusers 0.27 fork under /root/reference/MirrorFusion/src) is imported
+read-only; its `UNet2DConditionModel`, `BrushNetModel`, `DDIMScheduler` and
+`UniPCMultistepScheduler` are instantiated, loaded (strict) with the seeded synthetic
+state_dicts from `mirrorfusion_b200.synth`, and run on CPU in fp32.  The vectors it writes
+are what `tests/test_oracle_golden.py` pins `oracle/mf_oracle.py` against, and what the
+GPU parity tests compare the CUDA path with (the GPU box has no /root/reference).
+TEST INFRASTRUCTURE ONLY.
+"""
+from __future__ import annotations
+
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "reflecting-reality_b200"))
+REF_SRC = "/root/reference/MirrorFusion/src"
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def import_reference():
+    import transformers.utils as tu  # shim: symbol removed in transformers 5, imported by pipeline_loading_utils.py:44
+    if not hasattr(tu, "FLAX_WEIGHTS_NAME"):
+        tu.FLAX_WEIGHTS_NAME = "flax_model.msgpack"
+    sys.path.insert(0, REF_SRC)
+    import diffusers  # noqa
+    return diffusers
+
+
+def build_reference_nets(diffusers, cfg, seed=0):
+    from mirrorfusion_b200.synth import make_state_dict
+    n = len(cfg.block_out_channels)
+    down = tuple("CrossAttnDownBlock2D" if a else "DownBlock2D" for a in cfg.down_has_attn)
+    up = tuple("CrossAttnUpBlock2D" if a else "UpBlock2D" for a in cfg.up_has_attn)
+    unet = diffusers.UNet2DConditionModel(
+        sample_size=cfg.sample_size, in_channels=cfg.in_channels, out_channels=cfg.out_channels,
+        block_out_channels=cfg.block_out_channels, layers_per_block=cfg.layers_per_block,
+        down_block_types=down, up_block_types=up, cross_attention_dim=cfg.cross_attention_dim,
+        attention_head_dim=cfg.heads, norm_num_groups=cfg.norm_num_groups).eval()
+    bn = diffusers.BrushNetModel.from_unet(unet, conditioning_channels=cfg.conditioning_channels).eval()
+    # from_unet ALIASES the bias Parameter (`brushnet.conv_in_condition.bias = unet.conv_in.bias`,
+    # S/models/brushnet.py:518): loading one net's state_dict would silently overwrite the other's.
+    # Un-share it so both nets carry exactly the seeded tensors.
+    bn.conv_in_condition.bias = torch.nn.Parameter(bn.conv_in_condition.bias.detach().clone())
+    usd = make_state_dict(cfg, "unet", seed)
+    bsd = make_state_dict(cfg, "brushnet", seed)
+    unet.load_state_dict(usd, strict=True)
+    bn.load_state_dict(bsd, strict=True)
+    assert torch.equal(unet.conv_in.bias.detach(), usd["conv_in.bias"])
+    return unet, bn, usd, bsd
+
+
+@torch.no_grad()
+def ref_step(unet, bn, x, t, ehs, cond, scale=1.0):
+    d, m, u = bn(x, t, encoder_hidden_states=ehs, brushnet_cond=cond, conditioning_scale=scale, return_dict=False)
+    eps = unet(x, t, encoder_hidden_states=ehs, down_block_add_samples=[a.clone() for a in d],
+               mid_block_add_sample=m, up_block_add_samples=[a.clone() for a in u], return_dict=False)[0]
+    return eps, d, m, u
+
+
+def golden_step(diffusers, cfg, name, images=1, t=500, full_taps=True, seed=0, scale=1.0):
+    from mirrorfusion_b200.synth import make_inputs
+    unet, bn, _, _ = build_reference_nets(diffusers, cfg, seed)
+    inp = make_inputs(cfg, images)
+    x = torch.cat([inp["latents"]] * 2)
+    t0 = time.time()
+    eps, d, m, u = ref_step(unet, bn, x, torch.tensor(t), inp["prompt_embeds"], inp["conditioning_latents"], scale)
+    dt = time.time() - t0
+    plain = unet(x, torch.tensor(t), encoder_hidden_states=inp["prompt_embeds"], return_dict=False)[0]
+    out = {"noise_pred": eps.numpy(), "noise_pred_no_taps": plain.detach().numpy(), "t": np.int64(t),
+           "images": np.int64(images), "seed": np.int64(seed), "scale": np.float64(scale)}
+    taps = list(d) + [m] + list(u)
+    if full_taps:
+        for k, a in enumerate(taps):
+            out[f"tap{k:02d}"] = a.numpy()
+    else:  # full-size config: keep the fixtures small -> per-tap statistics + a strided sample
+        for k, a in enumerate(taps):
+            out[f"tap{k:02d}_l2"] = np.float64(a.double().norm().item())
+            out[f"tap{k:02d}_sample"] = a.flatten()[:: max(1, a.numel() // 4096)][:4096].numpy()
+    np.savez_compressed(os.path.join(GOLD, name), **out)
+    print(f"{name}: ref step {dt:.2f}s  |eps|={eps.norm():.4f} rel(taps effect)={(eps - plain).norm() / plain.norm():.3f}")
+
+
+def golden_loop(diffusers, cfg, name, sched_kind, steps, images=1, seed=0):
+    from mirrorfusion_b200.synth import make_inputs
+    unet, bn, _, _ = build_reference_nets(diffusers, cfg, seed)
+    inp = make_inputs(cfg, images)
+    base = diffusers.DDIMScheduler(beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear",
+                                   clip_sample=False, set_alpha_to_one=False, steps_offset=1)
+    sched = base if sched_kind == "ddim" else diffusers.UniPCMultistepScheduler.from_config(base.config)
+    sched.set_timesteps(steps)
+    lat = inp["latents"] * sched.init_noise_sigma
+    lats, epss = [], []
+    for t in sched.timesteps:                                      # pipeline_brushnet.py:1250-1315
+        x = sched.scale_model_input(torch.cat([lat] * 2), t)
+        eps, *_ = ref_step(unet, bn, x, t, inp["prompt_embeds"], inp["conditioning_latents"])
+        u_, c_ = eps.chunk(2)
+        guided = u_ + 7.5 * (c_ - u_)
+        lat = sched.step(guided, t, lat, return_dict=False)[0]
+        lats.append(lat.numpy().copy())
+        epss.append(eps.numpy().copy())
+    np.savez_compressed(os.path.join(GOLD, name), latents=np.stack(lats), noise_pred=np.stack(epss),
+                        timesteps=sched.timesteps.numpy(), steps=np.int64(steps), guidance=np.float64(7.5))
+    print(f"{name}: {steps} {sched_kind} steps, final |lat|={lat.norm():.4f}")
+
+
+def golden_sched_only(diffusers, name):
+    """Scheduler-only known-answer loops on a fixed pseudo-model (in the spirit of
+    T/schedulers/test_schedulers.py:326-368 dummy_model / dummy_sample_deter)."""
+    g = torch.Generator().manual_seed(3)
+    x0 = torch.randn(2, 4, 8, 8, generator=g)
+    out = {"x0": x0.numpy()}
+    base = diffusers.DDIMScheduler(beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear",
+                                   clip_sample=False, set_alpha_to_one=False, steps_offset=1)
+    for kind, n in (("ddim", 4), ("ddim", 10), ("unipc", 5), ("unipc", 10), ("unipc", 50)):
+        s = base if kind == "ddim" else diffusers.UniPCMultistepScheduler.from_config(base.config)
+        s.set_timesteps(n)
+        x = x0.clone()
+        traj = []
+        for i, t in enumerate(s.timesteps):
+            eps = torch.sin(3.0 * x + 0.01 * float(t)) * 0.9 + 0.1 * x      # deterministic pseudo-model
+            x = s.step(eps, t, x, return_dict=False)[0]
+            traj.append(x.numpy().copy())
+        out[f"{kind}{n}_traj"] = np.stack(traj)
+        out[f"{kind}{n}_timesteps"] = s.timesteps.numpy()
+        if kind == "unipc":
+            out[f"{kind}{n}_sigmas"] = s.sigmas.numpy()
+    np.savez_compressed(os.path.join(GOLD, name), **out)
+    print(f"{name}: scheduler trajectories written")
+
+
+def main():
+    if not os.path.isdir(REF_SRC):
+        raise SystemExit("reference not mounted at /root/reference; golden vectors can only be made in the build container")
+    torch.manual_seed(0)
+    torch.set_num_threads(os.cpu_count())
+    os.makedirs(GOLD, exist_ok=True)
+    diffusers = import_reference()
+    from mirrorfusion_b200.config import MICRO, TINY, SD15
+    which = sys.argv[1:] or ["sched", "micro", "tiny", "sd15"]
+    if "sched" in which:
+        golden_sched_only(diffusers, "sched_traj.npz")
+    if "micro" in which:
+        golden_step(diffusers, MICRO, "micro_step.npz", images=2, t=321, scale=0.8)
+        golden_loop(diffusers, MICRO, "micro_loop_ddim4.npz", "ddim", 4)
+        golden_loop(diffusers, MICRO, "micro_loop_unipc6.npz", "unipc", 6)
+    if "tiny" in which:
+        golden_step(diffusers, TINY, "tiny_step.npz", images=1, t=500)
+        golden_loop(diffusers, TINY, "tiny_loop_unipc8.npz", "unipc", 8)
+    if "sd15" in which:
+        golden_step(diffusers, SD15, "sd15_step.npz", images=1, t=500, full_taps=False)
+
+
+if __name__ == "__main__":
+    main()
