@@ -1,0 +1,147 @@
+/* mfb200.h — C ABI of libmfb200.so: the B200 (sm_100a) kernels of the MirrorFusion denoising hot path.
+ *
+ * The reference (val-iisc/Reflecting-Reality, a diffusers 0.27 fork) has no FFI: its "backend" is
+ * torch.nn.functional.  Each entry point below therefore names the reference call site(s) it replaces
+ * (S/ = MirrorFusion/src/diffusers/).  Conventions:
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless stated; the caller owns all buffers
+ *     and the stream (a cudaStream_t passed as void*); the library owns only plans it returns;
+ *   - activations are NHWC (channels-last) bf16, i.e. [B, H*W, C] row-major token matrices;
+ *   - every function returns MFB_OK (0) or a negative MFB_E* code; mfb_last_error() gives the message;
+ *   - there is NO CPU fallback: mfb_init() fails on anything but compute capability 10.x.
+ */
+#ifndef MFB200_H
+#define MFB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MFB_ABI_VERSION 1
+#define MFB_OK 0
+#define MFB_EINVAL (-1)       /* bad argument / unsupported shape */
+#define MFB_ECUDA (-2)        /* a CUDA runtime/driver call failed */
+#define MFB_EUNSUPPORTED (-3) /* device is not sm_100 */
+
+int mfb_abi_version(void);
+/* Select + validate the device, resolve cuTensorMapEncodeTiled. Idempotent. */
+int mfb_init(int device);
+const char* mfb_last_error(void);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Implicit-GEMM convolution / linear (tcgen05.mma + TMEM accumulators + TMA operand tiles).
+ * Replaces F.conv2d / F.linear behind LoRACompatibleConv/Linear (S/models/lora.py:363-377,445-451) for:
+ *   ResnetBlock2D conv1/conv2/conv_shortcut (S/models/resnet.py:367,396,398-401), Downsample2D
+ *   (S/models/downsampling.py:146-152), Upsample2D.conv (S/models/upsampling.py:179-184), Transformer2DModel
+ *   proj_in/proj_out (S/models/transformers/transformer_2d.py:340-344,417-421), Attention to_q/k/v/out
+ *   (S/models/attention_processor.py:1246-1274), FeedForward/GEGLU (S/models/attention.py:668-675,
+ *   S/models/activations.py:100-103), BrushNet zero-convs (S/models/brushnet.py:832-834,851,891-893).
+ *
+ *   out[b,oh,ow,:] = ( sum_taps x[b, oh*s+kh-pad, ow*s+kw-pad, :] . w_tap  +  sum_e extra_x[e][b,oh,ow,:] . w_e
+ *                      + bias + rowbias[b,:] ) * alpha  + res1[b,oh,ow,:] + res2[b,oh,ow,:]
+ *
+ * w is the packed weight [Cout, Ktot] bf16, K order = (kh, kw, cin) then the extra segments in order.
+ * A linear layer over an [M, K] token matrix is ksize=1, B=1, H=1, W=M, Cin=K.
+ * With geglu=1 the packed rows are interleaved per 128: 64 value rows then the 64 matching gate rows, and
+ * out is [M, Cout/2] = value * gelu_erf(gate).
+ */
+typedef struct mfb_conv_desc {
+    int B, H, W;          /* input geometry (NHWC) */
+    int Cin, Cout;        /* Cin % 64 == 0, Cout % 8 == 0 */
+    int ksize;            /* 1 or 3 (padding = ksize/2) */
+    int stride;           /* 1 or 2 (2 only with ksize 3) */
+    const void* x;        /* [B,H,W,Cin] bf16 */
+    int n_extra;          /* 0..3 extra 1x1 K-segments at OUTPUT resolution (shortcut over concat halves, ...) */
+    const void* extra_x[3];
+    int extra_C[3];
+    const void* w;        /* [Cout, Ktot] bf16 */
+    const float* bias;    /* [Cout] fp32 or NULL */
+    const float* rowbias; /* [B, rowbias_ld] fp32 or NULL: time_emb_proj(silu(emb)) (S/models/resnet.py:369-379) */
+    int rowbias_ld;
+    const float* alpha;   /* device scalar or NULL (=1): BrushNet conditioning_scale (S/models/brushnet.py:904-906) */
+    const void* res1;     /* [B,Ho,Wo,Cout] bf16 or NULL: residual / identity shortcut */
+    const void* res2;     /* second residual: the BrushNet tap (S/models/unets/unet_2d_blocks.py:1388-1398 ...) */
+    void* out;            /* [B,Ho,Wo,Cout] bf16 ([.., Cout/2] with geglu) */
+    int geglu;
+    int block_n;          /* 0 = auto, else 128 or 160 */
+} mfb_conv_desc;
+
+typedef struct mfb_plan mfb_plan;
+int mfb_conv_plan_create(const mfb_conv_desc* desc, mfb_plan** out);
+int mfb_plan_run(mfb_plan* plan, void* stream);
+int mfb_plan_destroy(mfb_plan* plan);
+double mfb_plan_flops(const mfb_plan* plan); /* 2*M*N*Ktot */
+int mfb_plan_ktotal(const mfb_plan* plan);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * GroupNorm (+SiLU) over NHWC bf16, fp32 statistics.  Replaces F.group_norm + F.silu in ResnetBlock2D
+ * (S/models/resnet.py:337-338,381,393), conv_norm_out (S/models/unets/unet_2d_condition.py:1337-1338) and the
+ * GroupNorm of Transformer2DModel (transformer_2d.py:338, eps 1e-6, silu=0).  x2 (optional) is a second tensor
+ * concatenated after x1 along channels — the skip concat of the up blocks (unet_2d_blocks.py:2586,2728) — so the
+ * concatenated tensor is only ever materialised normalised.  stats_ws: >= B*groups*2 floats of scratch.
+ */
+int mfb_groupnorm(const void* x1, int C1, const void* x2, int C2, int B, int HW, int groups, float eps,
+                  const float* gamma, const float* beta, int silu, float* stats_ws, void* out, void* stream);
+
+/* LayerNorm over the last dim of [rows, C] bf16 (S/models/attention.py:313,360,386). */
+int mfb_layernorm(const void* x, int rows, int C, float eps, const float* gamma, const float* beta, void* out,
+                  void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Scaled-dot-product attention, flash style on tcgen05 (S in TMEM, online softmax, P through shared memory).
+ * Replaces F.scaled_dot_product_attention in AttnProcessor2_0.__call__
+ * (S/models/attention_processor.py:1266-1268): no mask, non-causal, scale = head_dim^-0.5.
+ *   q  : [B, Tq, ldq]  bf16, head h occupies columns [h*d, (h+1)*d)
+ *   k  : [B, Tk, ldk]  bf16, same column convention
+ *   vt : [B, heads*d, ldvt] bf16 — V TRANSPOSED (keys contiguous), ldvt >= Tk and ldvt % 8 == 0
+ *   out: [B, Tq, ldo]  bf16
+ * head_dim in {40, 80, 160} (SD1.5: 320/640/1280 channels over 8 heads) or any multiple of 16 <= 160.
+ */
+int mfb_attention(const void* q, int ldq, const void* k, int ldk, const void* vt, int ldvt, void* out, int ldo, int B,
+                  int heads, int head_dim, int Tq, int Tk, void* stream);
+/* [B, T, ld] column block [col0, col0+C) -> transposed [B, C, ldt] (ldt >= T); pads [T, ldt) with zeros. */
+int mfb_transpose_tokens(const void* x, int ld, int col0, int C, int B, int T, void* out, int ldt, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Boundary / small layers.
+ */
+/* conv_in (S/models/unets/unet_2d_condition.py:1182) and conv_in_condition over cat([sample, brushnet_cond])
+ * (S/models/brushnet.py:810-811): NCHW fp32 inputs (sample [B,Ca,H,W], cond [B,Cb,H,W] or NULL) -> NHWC bf16
+ * [B,H,W,Cout].  w: [3,3,Ca+Cb,Cout] fp32.  If tap != NULL also writes out_post = out + tap
+ * (the pre-tap tensor stays the first skip: unet_2d_condition.py:1215-1218). */
+int mfb_conv_in(const float* sample, int Ca, const float* cond, int Cb, int B, int H, int W, const float* w,
+                const float* bias, int Cout, void* out, const void* tap, void* out_post, void* stream);
+/* conv_out (unet_2d_condition.py:1339): NHWC bf16 [B,H,W,Cin] -> NCHW fp32 [B,Cout<=4,H,W]; w [Cout,3,3,Cin] fp32. */
+int mfb_conv_out(const void* x, int Cin, int B, int H, int W, const float* w, const float* bias, int Cout, float* out,
+                 void* stream);
+/* nearest x2 upsample of NHWC bf16 (S/models/upsampling.py:167-173). */
+int mfb_upsample2x(const void* x, int B, int H, int W, int C, void* out, void* stream);
+/* layout conversion at the API boundary */
+int mfb_nchw_f32_to_nhwc_bf16(const float* x, int B, int C, int H, int W, void* out, void* stream);
+int mfb_nhwc_bf16_to_nchw_f32(const void* x, int B, int C, int H, int W, float* out, void* stream);
+int mfb_f32_to_bf16(const float* x, long long n, void* out, void* stream);
+
+/* Timestep path (S/models/embeddings.py:27-67,226-237; S/models/resnet.py:369-376): all in fp32.
+ * sinusoid: t [M] (fp32) -> [M, dim] = [cos | sin] (flip_sin_to_cos=True, shift 0). */
+int mfb_timestep_sinusoid(const float* t, int M, int dim, float* out, void* stream);
+/* y[M,N] = act_out( W[N,K](bf16) . act_in(x[M,K]) + b[N] ), fp32 in/out, M small. act: 0 none, 1 SiLU. */
+int mfb_linear_small(const float* x, int M, int K, const void* w, const float* b, int N, int act_in, int act_out,
+                     float* y, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * CFG combine + scheduler step fused (S/pipelines/brushnet/pipeline_brushnet.py:1310-1315 with
+ * S/schedulers/scheduling_unipc_multistep.py:425,567-572,703-709 / S/schedulers/scheduling_ddim.py:404-450).
+ * eps: [2*Bimg, n] fp32 (uncond half first).  All tensors fp32 [Bimg, n].  coef: device array of 12 floats:
+ *   g, c_x, c_eps                      : m_t   = c_x*x + c_eps*eps_guided           (x0-prediction)
+ *   a_last, a_m0, a_m1, a_mt, use_corr : x_c   = a_last*last + a_m0*m0 + a_m1*m1 + a_mt*m_t   (UniC; skipped if use_corr==0)
+ *   b_x, b_mt, b_m0, b_eps             : x_new = b_x*x_c + b_mt*m_t + b_m0*m0 + b_eps*eps_guided  (UniP / DDIM)
+ * Writes x_new -> x (in place), x_c -> last, shifts m0 -> m1 and m_t -> m0.
+ */
+int mfb_cfg_sched_step(const float* eps, float* x, float* last, float* m0, float* m1, const float* coef, int Bimg,
+                       long long n, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MFB200_H */

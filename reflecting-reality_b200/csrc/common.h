@@ -1,0 +1,36 @@
+// Host-side helpers shared by the translation units of libmfb200.so.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/mfb200.h"
+
+namespace mfb {
+
+void set_error(const char* fmt, ...);
+int device_sm_count();
+
+#define MFB_CUDA_OK(expr)                                                                           \
+    do {                                                                                            \
+        cudaError_t _e = (expr);                                                                    \
+        if (_e != cudaSuccess) {                                                                    \
+            ::mfb::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+            return MFB_ECUDA;                                                                       \
+        }                                                                                           \
+    } while (0)
+
+#define MFB_REQUIRE(cond, ...)                \
+    do {                                      \
+        if (!(cond)) {                        \
+            ::mfb::set_error(__VA_ARGS__);    \
+            return MFB_EINVAL;                \
+        }                                     \
+    } while (0)
+
+// Encode a tiled bf16 tensor map (rank <= 5).  dims/box are innermost-first; strides_bytes has rank-1 entries
+// (stride of dims 1..rank-1).  swizzle128: CU_TENSOR_MAP_SWIZZLE_128B (inner box extent must be 64 elements).
+int encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                     const uint32_t* box, bool swizzle128);
+
+}  // namespace mfb

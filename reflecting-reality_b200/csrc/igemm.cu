@@ -1,0 +1,440 @@
+// Implicit-GEMM convolution / linear layer on tcgen05 tensor cores.
+//
+// Replaces every F.conv2d (3x3 s1/s2, 1x1) and F.linear the reference issues on the hot path
+// (S/models/lora.py:363-377,445-451 called from S/models/resnet.py:367,396-401, downsampling.py:146-152,
+// upsampling.py:179-184, transformer_2d.py:340-344,417-421, attention_processor.py:1246-1274, attention.py:668-675,
+// brushnet.py:832-834,851,891-893).
+//
+//   D[M = B*Ho*Wo pixels, N = Cout] = sum over K-segments  A_seg[M, 64*cblocks] * W[N, kofs_seg ...]^T
+//
+// Activations are NHWC bf16.  A K-segment is (tensor map, dh, dw, channel range): the TMA producer fetches the
+// 128-pixel x 64-channel A tile for filter tap (dh,dw) as ONE 4-D box {64, tw, th, tn} at coordinates
+// (c, w0+dw, h0+dh, n0); out-of-bounds rows/columns are zero-filled by TMA, which is exactly the conv padding.
+// A box lands in shared memory as 128 dense 128-byte rows with the 128B swizzle = the canonical K-major UMMA
+// operand layout, so no im2col buffer and no register staging exists anywhere.  Extra 1x1 segments let one
+// accumulator also absorb the ResnetBlock2D 1x1 shortcut over the (concatenated) block input — the skip concat
+// (unet_2d_blocks.py:2586,2728) is just two segments — and stride-2 convs read four parity views of the input.
+// Warp roles: warp0 = TMA producer, warp1 = TMEM allocator + single-thread tcgen05.mma issuer, warps 2-5 =
+// epilogue (tcgen05.ld -> +bias +timestep-embedding row bias, xalpha, +residual(s) / GEGLU -> bf16 NHWC store).
+// Two CTAs are co-resident per SM (<=113 KB smem, <=256 TMEM columns each), so one CTA's epilogue overlaps the
+// other's main loop.
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <vector>
+
+#include "common.h"
+#include "ptx.cuh"
+
+namespace mfb {
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int MAX_SEG = 16;
+constexpr int IGEMM_THREADS = 192;
+
+struct IgemmSeg {
+    int map;      // which A tensor map
+    int dh, dw;   // spatial offset of this filter tap (in the coordinates of that map)
+    int c0;       // first channel inside that source
+    int cblocks;  // number of 64-channel K blocks
+};
+
+struct IgemmParams {
+    CUtensorMap tmA[4];
+    CUtensorMap tmB;
+    IgemmSeg seg[MAX_SEG];
+    int nseg;
+    int M, N;              // GEMM rows (valid output pixels) and columns (rows of the packed weight)
+    int Wo, Ho, Bn;        // output geometry
+    int tw, th, tn;        // tile box (tw*th*tn == 128)
+    int tiles_w, tiles_h;  // tiles per row / column
+    const float* bias;     // [N] (packed order) or null
+    const float* rowbias;  // [Bn, rowbias_ld] or null (timestep-embedding projection)
+    int rowbias_ld;
+    const float* alpha;    // device scalar or null (1.0)
+    const __nv_bfloat16* res1;  // [M, out_ld] or null
+    const __nv_bfloat16* res2;
+    __nv_bfloat16* out;    // [M, out_ld]
+    int out_ld;
+    int geglu;             // BN == 128 only: cols [0,64) value, [64,128) gate -> out[:, nt*64 + j]
+};
+
+template <int BN>
+struct IgemmCfg {
+    static constexpr int STAGES = 3;
+    static constexpr int A_BYTES = BM * BK * 2;
+    static constexpr int B_BYTES = BN * BK * 2;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int TMEM_COLS = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(IGEMM_THREADS) igemm_kernel(const __grid_constant__ IgemmParams p) {
+    using Cfg = IgemmCfg<BN>;
+    constexpr int STAGES = Cfg::STAGES;
+    extern __shared__ uint8_t smem_raw[];
+    // 1024-byte alignment is required by the 128B swizzle atoms
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bar_base = smem_base + STAGES * Cfg::STAGE_BYTES;
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+    const uint32_t tmem_full_bar = bar_base + 8u * (2 * STAGES);
+    const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 1);
+    uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    // tile coordinates
+    const int mt = blockIdx.x;
+    const int n_tile0 = blockIdx.y * BN;
+    const int t_w = mt % p.tiles_w;
+    const int t_h = (mt / p.tiles_w) % p.tiles_h;
+    const int t_n = mt / (p.tiles_w * p.tiles_h);
+    const int w0 = t_w * p.tw, h0 = t_h * p.th, n0 = t_n * p.tn;
+
+    int total_kb = 0;
+    for (int s = 0; s < p.nseg; ++s) total_kb += p.seg[s].cblocks;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&p.tmB);
+        prefetch_tmap(&p.tmA[0]);
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(full_bar(s), 1);
+            mbar_init(empty_bar(s), 1);
+        }
+        mbar_init(tmem_full_bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ===== TMA producer =====
+            int it = 0, kcol = 0;
+            for (int s = 0; s < p.nseg; ++s) {
+                const IgemmSeg sg = p.seg[s];
+                const void* tm = &p.tmA[sg.map];
+                for (int cb = 0; cb < sg.cblocks; ++cb, ++it, kcol += BK) {
+                    const int stage = it % STAGES;
+                    const uint32_t phase = (it / STAGES) & 1;
+                    mbar_wait(empty_bar(stage), phase ^ 1);
+                    mbar_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
+                    const uint32_t a_dst = smem_base + stage * Cfg::STAGE_BYTES;
+                    tma_load_4d(a_dst, tm, full_bar(stage), sg.c0 + cb * BK, w0 + sg.dw, h0 + sg.dh, n0);
+                    tma_load_2d(a_dst + Cfg::A_BYTES, &p.tmB, full_bar(stage), kcol, n_tile0);
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // ===== MMA issuer =====
+            constexpr uint32_t idesc = make_idesc_bf16(BM, BN);
+            for (int it = 0; it < total_kb; ++it) {
+                const int stage = it % STAGES;
+                const uint32_t phase = (it / STAGES) & 1;
+                mbar_wait(full_bar(stage), phase);
+                tc_fence_after();
+                const uint32_t a_addr = smem_base + stage * Cfg::STAGE_BYTES;
+                const uint64_t adesc = make_desc_k_sw128(a_addr);
+                const uint64_t bdesc = make_desc_k_sw128(a_addr + Cfg::A_BYTES);
+#pragma unroll
+                for (int k = 0; k < BK / 16; ++k) {
+                    // advancing 16 bf16 (32 B) along K inside the 128B swizzle row: +2 in the (addr >> 4) field
+                    umma_bf16(tmem_base, adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), idesc, (it | k) != 0);
+                }
+                umma_commit(empty_bar(stage));  // smem slot reusable once these MMAs have read it
+            }
+            umma_commit(tmem_full_bar);         // accumulator complete
+        }
+        __syncwarp();
+    } else {
+        // ===== epilogue: warps 2..5; TMEM lane quarter = warp % 4 =====
+        const int q = warp & 3;
+        const int r = q * 32 + lane;  // row of the tile == TMEM lane
+        const int rw = r % p.tw;
+        const int rh = (r / p.tw) % p.th;
+        const int rn = r / (p.tw * p.th);
+        const int ow = w0 + rw, oh = h0 + rh, on = n0 + rn;
+        const bool valid = (ow < p.Wo) && (oh < p.Ho) && (on < p.Bn);
+        const long long m = (static_cast<long long>(on) * p.Ho + oh) * p.Wo + ow;
+        const float alpha = p.alpha ? __ldg(p.alpha) : 1.0f;
+        const float* rb = p.rowbias ? p.rowbias + static_cast<long long>(valid ? on : 0) * p.rowbias_ld : nullptr;
+
+        mbar_wait(tmem_full_bar, 0);
+        tc_fence_after();
+        const uint32_t trow = tmem_base + (uint32_t(q * 32) << 16);
+
+        if (!p.geglu) {
+#pragma unroll 1
+            for (int c = 0; c < BN / 32; ++c) {
+                uint32_t v[32];
+                tmem_ld32(trow + c * 32, v);
+                tmem_wait_ld();
+                const int nb = n_tile0 + c * 32;
+                if (valid) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 8) {
+                        const int n = nb + j;
+                        if (n < p.N) {
+                            float f[8];
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[j + e]);
+                            if (p.bias) {
+                                const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+                                const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + n + 4));
+                                f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
+                                f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+                            }
+                            if (rb) {
+                                const float4 b0 = __ldg(reinterpret_cast<const float4*>(rb + n));
+                                const float4 b1 = __ldg(reinterpret_cast<const float4*>(rb + n + 4));
+                                f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
+                                f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+                            }
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) f[e] *= alpha;
+                            if (p.res1) {
+                                const uint4 rv = __ldg(reinterpret_cast<const uint4*>(p.res1 + m * p.out_ld + n));
+                                float2 t;
+                                t = unpack_bf16x2(rv.x); f[0] += t.x; f[1] += t.y;
+                                t = unpack_bf16x2(rv.y); f[2] += t.x; f[3] += t.y;
+                                t = unpack_bf16x2(rv.z); f[4] += t.x; f[5] += t.y;
+                                t = unpack_bf16x2(rv.w); f[6] += t.x; f[7] += t.y;
+                            }
+                            if (p.res2) {
+                                const uint4 rv = __ldg(reinterpret_cast<const uint4*>(p.res2 + m * p.out_ld + n));
+                                float2 t;
+                                t = unpack_bf16x2(rv.x); f[0] += t.x; f[1] += t.y;
+                                t = unpack_bf16x2(rv.y); f[2] += t.x; f[3] += t.y;
+                                t = unpack_bf16x2(rv.z); f[4] += t.x; f[5] += t.y;
+                                t = unpack_bf16x2(rv.w); f[6] += t.x; f[7] += t.y;
+                            }
+                            uint4 o;
+                            o.x = pack_bf16x2(f[0], f[1]);
+                            o.y = pack_bf16x2(f[2], f[3]);
+                            o.z = pack_bf16x2(f[4], f[5]);
+                            o.w = pack_bf16x2(f[6], f[7]);
+                            *reinterpret_cast<uint4*>(p.out + m * p.out_ld + n) = o;
+                        }
+                    }
+                }
+            }
+        } else {
+            // GEGLU (S/models/activations.py:100-103): out = value * gelu_erf(gate); tile = [64 value | 64 gate]
+            if constexpr (BN == 128) {
+#pragma unroll 1
+                for (int c = 0; c < 2; ++c) {
+                    uint32_t v[32], g[32];
+                    tmem_ld32(trow + c * 32, v);
+                    tmem_ld32(trow + 64 + c * 32, g);
+                    tmem_wait_ld();
+                    if (valid) {
+                        const int ncol = blockIdx.y * 64 + c * 32;  // output column
+                        const int pv = n_tile0 + c * 32;            // packed column of the value
+#pragma unroll
+                        for (int j = 0; j < 32; j += 8) {
+                            if (pv + j < p.N) {
+                                float f[8];
+#pragma unroll
+                                for (int e = 0; e < 8; ++e) {
+                                    float val = __uint_as_float(v[j + e]);
+                                    float gat = __uint_as_float(g[j + e]);
+                                    if (p.bias) {
+                                        val += __ldg(p.bias + pv + j + e);
+                                        gat += __ldg(p.bias + pv + 64 + j + e);
+                                    }
+                                    f[e] = val * gelu_erf_f(gat);
+                                }
+                                uint4 o;
+                                o.x = pack_bf16x2(f[0], f[1]);
+                                o.y = pack_bf16x2(f[2], f[3]);
+                                o.z = pack_bf16x2(f[4], f[5]);
+                                o.w = pack_bf16x2(f[6], f[7]);
+                                *reinterpret_cast<uint4*>(p.out + m * p.out_ld + ncol + j) = o;
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        tc_fence_before();
+    }
+
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+struct Plan {
+    IgemmParams p;
+    dim3 grid;
+    int bn;
+    double flops;
+};
+
+static void pick_tile(int W, int H, int B, int* tw, int* th, int* tn) {
+    long best = -1;
+    for (int a = 128; a >= 1; a >>= 1) {
+        for (int b = 128 / a; b >= 1; b >>= 1) {
+            const int c = 128 / (a * b);
+            if (a * b * c != 128) continue;
+            const long tiles = long((W + a - 1) / a) * ((H + b - 1) / b) * ((B + c - 1) / c);
+            // fewest tiles wins; ties prefer wide boxes (longer contiguous runs)
+            if (best < 0 || tiles < best) {
+                best = tiles;
+                *tw = a; *th = b; *tn = c;
+            }
+        }
+    }
+}
+
+template <int BN>
+static int launch_igemm(const Plan& pl, cudaStream_t st) {
+    using Cfg = IgemmCfg<BN>;
+    static bool configured = false;
+    if (!configured) {
+        MFB_CUDA_OK(cudaFuncSetAttribute(igemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        configured = true;
+    }
+    igemm_kernel<BN><<<pl.grid, IGEMM_THREADS, Cfg::SMEM_BYTES, st>>>(pl.p);
+    MFB_CUDA_OK(cudaGetLastError());
+    return MFB_OK;
+}
+
+}  // namespace mfb
+
+using namespace mfb;
+
+extern "C" int mfb_conv_plan_create(const mfb_conv_desc* d, mfb_plan** out) {
+    MFB_REQUIRE(d && out, "null argument");
+    MFB_REQUIRE(d->ksize == 3 || d->ksize == 1, "ksize must be 1 or 3 (got %d)", d->ksize);
+    MFB_REQUIRE(d->stride == 1 || d->stride == 2, "stride must be 1 or 2");
+    MFB_REQUIRE(d->stride == 1 || d->ksize == 3, "stride 2 is only supported for 3x3");
+    MFB_REQUIRE(d->Cin > 0 && d->Cin % 64 == 0, "Cin must be a positive multiple of 64 (got %d)", d->Cin);
+    MFB_REQUIRE(d->Cout > 0 && d->Cout % 8 == 0, "Cout must be a multiple of 8 (got %d)", d->Cout);
+    MFB_REQUIRE(d->n_extra >= 0 && d->n_extra <= 3, "at most 3 extra 1x1 segments");
+    MFB_REQUIRE(d->stride == 1 || d->n_extra == 0, "extra segments are not supported with stride 2");
+    MFB_REQUIRE(d->x && d->w && d->out, "x / w / out must be device pointers");
+    MFB_REQUIRE(!d->geglu || (d->Cout % 128 == 0 && !d->res1 && !d->res2 && !d->rowbias), "geglu needs Cout %% 128 == 0 and no residuals");
+
+    Plan* pl = new Plan();
+    IgemmParams& p = pl->p;
+    memset(&p, 0, sizeof(p));
+    const int B = d->B, H = d->H, W = d->W;
+    const int Ho = d->stride == 1 ? H : (H - 1) / 2 + 1;
+    const int Wo = d->stride == 1 ? W : (W - 1) / 2 + 1;
+    p.Wo = Wo; p.Ho = Ho; p.Bn = B;
+    p.M = B * Ho * Wo;
+    p.N = d->Cout;
+    pick_tile(Wo, Ho, B, &p.tw, &p.th, &p.tn);
+    p.tiles_w = (Wo + p.tw - 1) / p.tw;
+    p.tiles_h = (Ho + p.th - 1) / p.th;
+    const int tiles_n = (B + p.tn - 1) / p.tn;
+    const uint32_t box[4] = {64u, uint32_t(p.tw), uint32_t(p.th), uint32_t(p.tn)};
+
+    int ktot = 0, nseg = 0;
+    int rc = MFB_OK;
+    if (d->stride == 1) {
+        const uint64_t dims[4] = {uint64_t(d->Cin), uint64_t(W), uint64_t(H), uint64_t(B)};
+        const uint64_t str[3] = {uint64_t(d->Cin) * 2, uint64_t(W) * d->Cin * 2, uint64_t(H) * W * d->Cin * 2};
+        rc = encode_tmap_bf16(&p.tmA[0], d->x, 4, dims, str, box, true);
+        if (rc) { delete pl; return rc; }
+        const int r = d->ksize / 2;
+        for (int kh = -r; kh <= r; ++kh)
+            for (int kw = -r; kw <= r; ++kw) {
+                p.seg[nseg++] = IgemmSeg{0, kh, kw, 0, d->Cin / 64};
+                ktot += d->Cin;
+            }
+    } else {
+        // four parity views (ph, pw) of the input: element (h2, w2) of view = x[2*h2 + ph, 2*w2 + pw]
+        for (int ph = 0; ph < 2; ++ph)
+            for (int pw = 0; pw < 2; ++pw) {
+                const uint64_t dims[4] = {uint64_t(d->Cin), uint64_t((W - pw + 1) / 2), uint64_t((H - ph + 1) / 2), uint64_t(B)};
+                const uint64_t str[3] = {uint64_t(d->Cin) * 4, uint64_t(W) * d->Cin * 4, uint64_t(H) * W * d->Cin * 2};
+                const char* base = static_cast<const char*>(d->x) + (size_t(ph) * W + pw) * d->Cin * 2;
+                rc = encode_tmap_bf16(&p.tmA[ph * 2 + pw], base, 4, dims, str, box, true);
+                if (rc) { delete pl; return rc; }
+            }
+        // input row = 2*oh + kh - 1:  kh=0 -> (parity 1, h2 = oh-1); kh=1 -> (0, oh); kh=2 -> (1, oh)
+        const int par[3] = {1, 0, 1}, off[3] = {-1, 0, 0};
+        for (int kh = 0; kh < 3; ++kh)
+            for (int kw = 0; kw < 3; ++kw) {
+                p.seg[nseg++] = IgemmSeg{par[kh] * 2 + par[kw], off[kh], off[kw], 0, d->Cin / 64};
+                ktot += d->Cin;
+            }
+    }
+    for (int e = 0; e < d->n_extra; ++e) {
+        MFB_REQUIRE(d->extra_x[e] && d->extra_C[e] % 64 == 0, "extra segment %d: channels must be a multiple of 64", e);
+        const int C = d->extra_C[e];
+        const uint64_t dims[4] = {uint64_t(C), uint64_t(Wo), uint64_t(Ho), uint64_t(B)};
+        const uint64_t str[3] = {uint64_t(C) * 2, uint64_t(Wo) * C * 2, uint64_t(Ho) * Wo * C * 2};
+        rc = encode_tmap_bf16(&p.tmA[1 + e], d->extra_x[e], 4, dims, str, box, true);
+        if (rc) { delete pl; return rc; }
+        p.seg[nseg++] = IgemmSeg{1 + e, 0, 0, 0, C / 64};
+        ktot += C;
+    }
+    p.nseg = nseg;
+
+    // BN: 160 divides every conv width of the SD1.5 family (320/640/1280/960); GEGLU needs the 64|64 split.
+    int bn = d->geglu ? 128 : (d->Cout % 160 == 0 ? 160 : 128);
+    if (d->block_n == 128 || d->block_n == 160) bn = d->block_n;
+    MFB_REQUIRE(!d->geglu || bn == 128, "geglu requires block_n 128");
+    pl->bn = bn;
+    {
+        const uint64_t dims[2] = {uint64_t(ktot), uint64_t(d->Cout)};
+        const uint64_t str[1] = {uint64_t(ktot) * 2};
+        const uint32_t bbox[2] = {64u, uint32_t(bn)};
+        rc = encode_tmap_bf16(&p.tmB, d->w, 2, dims, str, bbox, true);
+        if (rc) { delete pl; return rc; }
+    }
+    p.bias = d->bias;
+    p.rowbias = d->rowbias;
+    p.rowbias_ld = d->rowbias_ld;
+    p.alpha = d->alpha;
+    p.res1 = static_cast<const __nv_bfloat16*>(d->res1);
+    p.res2 = static_cast<const __nv_bfloat16*>(d->res2);
+    p.out = static_cast<__nv_bfloat16*>(d->out);
+    p.geglu = d->geglu;
+    p.out_ld = d->geglu ? d->Cout / 2 : d->Cout;
+    pl->grid = dim3(p.tiles_w * p.tiles_h * tiles_n, (d->Cout + bn - 1) / bn, 1);
+    pl->flops = 2.0 * double(p.M) * d->Cout * ktot;
+    *out = reinterpret_cast<mfb_plan*>(pl);
+    return MFB_OK;
+}
+
+extern "C" int mfb_plan_run(mfb_plan* plan, void* stream) {
+    MFB_REQUIRE(plan, "null plan");
+    Plan* pl = reinterpret_cast<Plan*>(plan);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    return pl->bn == 160 ? launch_igemm<160>(*pl, st) : launch_igemm<128>(*pl, st);
+}
+
+extern "C" int mfb_plan_destroy(mfb_plan* plan) {
+    delete reinterpret_cast<Plan*>(plan);
+    return MFB_OK;
+}
+
+extern "C" double mfb_plan_flops(const mfb_plan* plan) { return plan ? reinterpret_cast<const Plan*>(plan)->flops : 0.0; }
+
+extern "C" int mfb_plan_ktotal(const mfb_plan* plan) {
+    if (!plan) return 0;
+    const Plan* pl = reinterpret_cast<const Plan*>(plan);
+    int k = 0;
+    for (int s = 0; s < pl->p.nseg; ++s) k += pl->p.seg[s].cblocks * 64;
+    return k;
+}

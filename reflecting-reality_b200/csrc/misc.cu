@@ -1,0 +1,368 @@
+// Boundary and small layers of the denoise step: conv_in / conv_out (4..10 and 4 channels: CUDA-core direct
+// convolutions, <0.1 % of the FLOPs), nearest upsample, layout conversion, the timestep path and the fused
+// CFG + scheduler update.  All are bandwidth/latency bound; accesses are coalesced and vectorised where the
+// shapes allow.
+#include "common.h"
+#include "ptx.cuh"
+
+namespace mfb {
+
+// ---------------------------------------------------------------------------------------------- conv_in
+// grid (ceil(W/8), ceil(H/8), B), block 256.  Input patch (10x10xCin fp32) staged in smem; each thread computes
+// 8 output channels of one pixel at a time; weights [3][3][Cin][Cout] fp32 are read through L1 (coalesced over
+// the 8-channel groups of consecutive threads).
+__global__ void conv_in_kernel(const float* __restrict__ xa, int Ca, const float* __restrict__ xb, int Cb, int H, int W,
+                               const float* __restrict__ w, const float* __restrict__ bias, int Cout,
+                               __nv_bfloat16* __restrict__ out, const __nv_bfloat16* __restrict__ tap,
+                               __nv_bfloat16* __restrict__ out_post) {
+    extern __shared__ float patch[];  // [Cin][10][10]
+    const int Cin = Ca + Cb;
+    const int b = blockIdx.z;
+    const int h0 = blockIdx.y * 8, w0 = blockIdx.x * 8;
+    for (int i = threadIdx.x; i < Cin * 100; i += blockDim.x) {
+        const int c = i / 100, r = i % 100;
+        const int hh = h0 + r / 10 - 1, ww = w0 + r % 10 - 1;
+        float v = 0.f;
+        if (hh >= 0 && hh < H && ww >= 0 && ww < W) {
+            v = c < Ca ? xa[((static_cast<size_t>(b) * Ca + c) * H + hh) * W + ww]
+                       : xb[((static_cast<size_t>(b) * Cb + (c - Ca)) * H + hh) * W + ww];
+        }
+        patch[i] = v;
+    }
+    __syncthreads();
+    const int ngroups = Cout / 8;
+    for (int item = threadIdx.x; item < 64 * ngroups; item += blockDim.x) {
+        const int cg = item % ngroups, pix = item / ngroups;
+        const int ph = pix / 8, pw = pix % 8;
+        const int oh = h0 + ph, ow = w0 + pw;
+        if (oh >= H || ow >= W) continue;
+        float acc[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] = __ldg(&bias[cg * 8 + e]);
+        for (int kh = 0; kh < 3; ++kh)
+            for (int kw = 0; kw < 3; ++kw)
+                for (int c = 0; c < Cin; ++c) {
+                    const float xv = patch[c * 100 + (ph + kh) * 10 + (pw + kw)];
+                    const float* wp = w + ((static_cast<size_t>(kh * 3 + kw) * Cin + c) * Cout + cg * 8);
+                    const float4 w0v = __ldg(reinterpret_cast<const float4*>(wp));
+                    const float4 w1v = __ldg(reinterpret_cast<const float4*>(wp + 4));
+                    acc[0] = fmaf(xv, w0v.x, acc[0]); acc[1] = fmaf(xv, w0v.y, acc[1]);
+                    acc[2] = fmaf(xv, w0v.z, acc[2]); acc[3] = fmaf(xv, w0v.w, acc[3]);
+                    acc[4] = fmaf(xv, w1v.x, acc[4]); acc[5] = fmaf(xv, w1v.y, acc[5]);
+                    acc[6] = fmaf(xv, w1v.z, acc[6]); acc[7] = fmaf(xv, w1v.w, acc[7]);
+                }
+        const size_t o = ((static_cast<size_t>(b) * H + oh) * W + ow) * Cout + cg * 8;
+        uint4 pk;
+        pk.x = pack_bf16x2(acc[0], acc[1]); pk.y = pack_bf16x2(acc[2], acc[3]);
+        pk.z = pack_bf16x2(acc[4], acc[5]); pk.w = pack_bf16x2(acc[6], acc[7]);
+        *reinterpret_cast<uint4*>(out + o) = pk;
+        if (tap) {
+            const uint4 tv = __ldg(reinterpret_cast<const uint4*>(tap + o));
+            float2 t;
+            t = unpack_bf16x2(tv.x); acc[0] += t.x; acc[1] += t.y;
+            t = unpack_bf16x2(tv.y); acc[2] += t.x; acc[3] += t.y;
+            t = unpack_bf16x2(tv.z); acc[4] += t.x; acc[5] += t.y;
+            t = unpack_bf16x2(tv.w); acc[6] += t.x; acc[7] += t.y;
+            pk.x = pack_bf16x2(acc[0], acc[1]); pk.y = pack_bf16x2(acc[2], acc[3]);
+            pk.z = pack_bf16x2(acc[4], acc[5]); pk.w = pack_bf16x2(acc[6], acc[7]);
+            *reinterpret_cast<uint4*>(out_post + o) = pk;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- conv_out
+// One warp per output pixel; K = 9*Cin reduced across lanes with 16-byte activation loads; weights
+// [Cout<=4][3][3][Cin] fp32 staged in shared memory as bf16-free fp32 (<= 46 KB for Cin = 320).
+__global__ void conv_out_kernel(const __nv_bfloat16* __restrict__ x, int Cin, int B, int H, int W,
+                                const float* __restrict__ w, const float* __restrict__ bias, int Cout,
+                                float* __restrict__ out) {
+    extern __shared__ float ws[];  // [Cout][9*Cin]
+    const int K = 9 * Cin;
+    for (int i = threadIdx.x; i < Cout * K; i += blockDim.x) ws[i] = w[i];
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int warps = blockDim.x >> 5;
+    const long long npix = static_cast<long long>(B) * H * W;
+    const int nvec_c = Cin / 8;
+    for (long long pix = static_cast<long long>(blockIdx.x) * warps + (threadIdx.x >> 5); pix < npix;
+         pix += static_cast<long long>(gridDim.x) * warps) {
+        const int ow = pix % W;
+        const int oh = (pix / W) % H;
+        const int b = pix / (static_cast<long long>(W) * H);
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int v = lane; v < 9 * nvec_c; v += 32) {
+            const int tapi = v / nvec_c, cv = v % nvec_c;
+            const int hh = oh + tapi / 3 - 1, ww = ow + tapi % 3 - 1;
+            if (hh < 0 || hh >= H || ww < 0 || ww >= W) continue;
+            const uint4 u = __ldg(reinterpret_cast<const uint4*>(x + ((static_cast<size_t>(b) * H + hh) * W + ww) * Cin + cv * 8));
+            float f[8];
+            float2 t;
+            t = unpack_bf16x2(u.x); f[0] = t.x; f[1] = t.y;
+            t = unpack_bf16x2(u.y); f[2] = t.x; f[3] = t.y;
+            t = unpack_bf16x2(u.z); f[4] = t.x; f[5] = t.y;
+            t = unpack_bf16x2(u.w); f[6] = t.x; f[7] = t.y;
+            for (int co = 0; co < Cout; ++co) {
+                const float* wp = ws + co * K + tapi * Cin + cv * 8;
+#pragma unroll
+                for (int e = 0; e < 8; ++e) acc[co] = fmaf(f[e], wp[e], acc[co]);
+            }
+        }
+        for (int co = 0; co < Cout; ++co) {
+            float a = acc[co];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+            if (lane == 0) out[((static_cast<size_t>(b) * Cout + co) * H + oh) * W + ow] = a + bias[co];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- upsample / layout
+__global__ void upsample2x_kernel(const uint4* __restrict__ x, int H, int W, int CV, uint4* __restrict__ out, long long total) {
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int cv = i % CV;
+        long long r = i / CV;
+        const int ow = r % (2 * W); r /= (2 * W);
+        const int oh = r % (2 * H);
+        const long long b = r / (2 * H);
+        out[i] = __ldg(&x[((b * H + (oh >> 1)) * W + (ow >> 1)) * CV + cv]);
+    }
+}
+
+// NCHW fp32 -> NHWC bf16 via a 32x32 smem transpose over (C, HW)
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, int C, int HW, __nv_bfloat16* __restrict__ out) {
+    __shared__ float tile[32][33];
+    const int b = blockIdx.z;
+    const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int c = c0 + i, p = p0 + threadIdx.x;
+        tile[i][threadIdx.x] = (c < C && p < HW) ? x[(static_cast<size_t>(b) * C + c) * HW + p] : 0.f;
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int p = p0 + i, c = c0 + threadIdx.x;
+        if (c < C && p < HW) out[(static_cast<size_t>(b) * HW + p) * C + c] = __float2bfloat16(tile[threadIdx.x][i]);
+    }
+}
+__global__ void nhwc_to_nchw_kernel(const __nv_bfloat16* __restrict__ x, int C, int HW, float* __restrict__ out) {
+    __shared__ float tile[32][33];
+    const int b = blockIdx.z;
+    const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int p = p0 + i, c = c0 + threadIdx.x;
+        tile[i][threadIdx.x] = (c < C && p < HW) ? __bfloat162float(x[(static_cast<size_t>(b) * HW + p) * C + c]) : 0.f;
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int c = c0 + i, p = p0 + threadIdx.x;
+        if (c < C && p < HW) out[(static_cast<size_t>(b) * C + c) * HW + p] = tile[threadIdx.x][i];
+    }
+}
+__global__ void f32_to_bf16_kernel(const float* __restrict__ x, long long n, __nv_bfloat16* __restrict__ out) {
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+         i += static_cast<long long>(gridDim.x) * blockDim.x)
+        out[i] = __float2bfloat16(x[i]);
+}
+
+// [B, T, ld] columns [col0, col0+C) -> [B, C, ldt] (token index contiguous), zero padding for t in [T, ldt)
+__global__ void transpose_tokens_kernel(const __nv_bfloat16* __restrict__ x, int ld, int col0, int C, int T,
+                                        __nv_bfloat16* __restrict__ out, int ldt) {
+    __shared__ __nv_bfloat16 tile[32][34];
+    const int b = blockIdx.z;
+    const int t0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int t = t0 + i, c = c0 + threadIdx.x;
+        tile[i][threadIdx.x] = (t < T && c < C) ? x[(static_cast<size_t>(b) * T + t) * ld + col0 + c] : __float2bfloat16(0.f);
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int c = c0 + i, t = t0 + threadIdx.x;
+        if (c < C && t < ldt) out[(static_cast<size_t>(b) * C + c) * ldt + t] = tile[threadIdx.x][i];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- timestep path
+__global__ void sinusoid_kernel(const float* __restrict__ t, int M, int dim, float* __restrict__ out) {
+    const int half = dim / 2;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= M * half) return;
+    const int m = i / half, j = i % half;
+    // exponent = -ln(10000) * j / half   (embeddings.py:45-49, downscale_freq_shift = 0)
+    const float freq = expf(-9.210340371976184f * static_cast<float>(j) / static_cast<float>(half));
+    const float a = t[m] * freq;
+    out[static_cast<size_t>(m) * dim + j] = cosf(a);          // flip_sin_to_cos: cos first
+    out[static_cast<size_t>(m) * dim + half + j] = sinf(a);
+}
+
+// y[m, n] = act_out(b[n] + sum_k W[n,k] * act_in(x[m,k]));  one warp per n, rows in groups of 8
+__global__ void linear_small_kernel(const float* __restrict__ x, int M, int K, const __nv_bfloat16* __restrict__ w,
+                                    const float* __restrict__ b, int N, int act_in, int act_out, float* __restrict__ y) {
+    const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (n >= N) return;
+    const int m0 = blockIdx.y * 8;
+    float acc[8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) acc[r] = 0.f;
+    const __nv_bfloat16* wr = w + static_cast<size_t>(n) * K;
+    for (int k = lane * 2; k < K; k += 64) {
+        const float2 wv = unpack_bf16x2(__ldg(reinterpret_cast<const uint32_t*>(wr + k)));
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            if (m0 + r < M) {
+                float2 xv = *reinterpret_cast<const float2*>(x + static_cast<size_t>(m0 + r) * K + k);
+                if (act_in) { xv.x = xv.x / (1.f + expf(-xv.x)); xv.y = xv.y / (1.f + expf(-xv.y)); }
+                acc[r] = fmaf(wv.x, xv.x, fmaf(wv.y, xv.y, acc[r]));
+            }
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+        float a = acc[r];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+        if (lane == 0 && m0 + r < M) {
+            a += b ? b[n] : 0.f;
+            if (act_out) a = a / (1.f + expf(-a));
+            y[static_cast<size_t>(m0 + r) * N + n] = a;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- CFG + scheduler
+__global__ void cfg_sched_kernel(const float* __restrict__ eps, float* __restrict__ x, float* __restrict__ last,
+                                 float* __restrict__ m0, float* __restrict__ m1, const float* __restrict__ coef,
+                                 long long total /* Bimg*n */) {
+    const float g = coef[0], c_x = coef[1], c_eps = coef[2];
+    const float a_last = coef[3], a_m0 = coef[4], a_m1 = coef[5], a_mt = coef[6], use_corr = coef[7];
+    const float b_x = coef[8], b_mt = coef[9], b_m0 = coef[10], b_eps = coef[11];
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const float eu = eps[i], ec = eps[total + i];
+        const float e = eu + g * (ec - eu);                    // pipeline_brushnet.py:1311-1312
+        const float xv = x[i];
+        const float mt = c_x * xv + c_eps * e;                 // convert_model_output (x0 prediction)
+        const float m0v = m0[i], m1v = m1[i];
+        float xc = xv;
+        if (use_corr != 0.f) xc = a_last * last[i] + a_m0 * m0v + a_m1 * m1v + a_mt * mt;   // UniC
+        const float xn = b_x * xc + b_mt * mt + b_m0 * m0v + b_eps * e;                      // UniP / DDIM
+        x[i] = xn;
+        last[i] = xc;
+        m1[i] = m0v;
+        m0[i] = mt;
+    }
+}
+
+}  // namespace mfb
+
+using namespace mfb;
+
+static inline int grid_for(long long n, int block, int cap = 148 * 8) {
+    long long g = (n + block - 1) / block;
+    if (g > cap) g = cap;
+    if (g < 1) g = 1;
+    return static_cast<int>(g);
+}
+
+extern "C" int mfb_conv_in(const float* sample, int Ca, const float* cond, int Cb, int B, int H, int W, const float* w,
+                           const float* bias, int Cout, void* out, const void* tap, void* out_post, void* stream) {
+    MFB_REQUIRE(sample && w && bias && out, "null pointer");
+    if (!cond) Cb = 0;
+    MFB_REQUIRE(Cout % 8 == 0, "Cout must be a multiple of 8");
+    MFB_REQUIRE(!tap || out_post, "tap given without out_post");
+    const int Cin = Ca + Cb;
+    MFB_REQUIRE(Cin <= 64, "conv_in supports at most 64 input channels");
+    dim3 grid((W + 7) / 8, (H + 7) / 8, B);
+    conv_in_kernel<<<grid, 256, Cin * 100 * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
+        sample, Ca, cond, Cb, H, W, w, bias, Cout, static_cast<__nv_bfloat16*>(out), static_cast<const __nv_bfloat16*>(tap),
+        static_cast<__nv_bfloat16*>(out_post));
+    MFB_CUDA_OK(cudaGetLastError());
+    return MFB_OK;
+}
+
+extern "C" int mfb_conv_out(const void* x, int Cin, int B, int H, int W, const float* w, const float* bias, int Cout,
+                            float* out, void* stream) {
+    MFB_REQUIRE(x && w && bias && out, "null pointer");
+    MFB_REQUIRE(Cout >= 1 && Cout <= 4 && Cin % 8 == 0, "conv_out supports Cout <= 4, Cin %% 8 == 0");
+    const size_t smem = static_cast<size_t>(Cout) * 9 * Cin * sizeof(float);
+    MFB_REQUIRE(smem <= 200 * 1024, "conv_out weights do not fit shared memory");
+    static bool configured = false;
+    if (!configured) {
+        MFB_CUDA_OK(cudaFuncSetAttribute(conv_out_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        configured = true;
+    }
+    const long long npix = static_cast<long long>(B) * H * W;
+    const int grid = grid_for(npix, 8, 148 * 2);
+    conv_out_kernel<<<grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(static_cast<const __nv_bfloat16*>(x), Cin, B, H, W, w,
+                                                                           bias, Cout, out);
+    MFB_CUDA_OK(cudaGetLastError());
+    return MFB_OK;
+}
+
+extern "C" int mfb_upsample2x(const void* x, int B, int H, int W, int C, void* out, void* stream) {
+    MFB_REQUIRE(x && out && C % 8 == 0, "bad arguments");
+    const long long total = static_cast<long long>(B) * 4 * H * W * (C / 8);
+    upsample2x_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const uint4*>(x), H, W, C / 8, static_cast<uint4*>(out), total);
+    MFB_CUDA_OK(cudaGetLastError());
+    return MFB_OK;
+}
+
+extern "C" int mfb_nchw_f32_to_nhwc_bf16(const float* x, int B, int C, int H, int W, void* out, void* stream) {
+    MFB_REQUIRE(x && out, "null pointer");
+    dim3 grid((H * W + 31) / 32, (C + 31) / 32, B), block(32, 8);
+    nchw_to_nhwc_kernel<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(x, C, H * W, static_cast<__nv_bfloat16*>(out));
+    MFB_CUDA_OK(cudaGetLastError());
+    return MFB_OK;
+}
+
+extern "C" int mfb_nhwc_bf16_to_nchw_f32(const void* x, int B, int C, int H, int W, float* out, void* stream) {
+    MFB_REQUIRE(x && out, "null pointer");
+    dim3 grid((H * W + 31) / 32, (C + 31) / 32, B), block(32, 8);
+    nhwc_to_nchw_kernel<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const __nv_bfloat16*>(x), C, H * W, out);
+    MFB_CUDA_OK(cudaGetLastError());
+    return MFB_OK;
+}
+
+extern "C" int mfb_f32_to_bf16(const float* x, long long n, void* out, void* stream) {
+    MFB_REQUIRE(x && out, "null pointer");
+    f32_to_bf16_kernel<<<grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, n, static_cast<__nv_bfloat16*>(out));
+    MFB_CUDA_OK(cudaGetLastError());
+    return MFB_OK;
+}
+
+extern "C" int mfb_transpose_tokens(const void* x, int ld, int col0, int C, int B, int T, void* out, int ldt, void* stream) {
+    MFB_REQUIRE(x && out && ldt >= T, "bad arguments");
+    dim3 grid((ldt + 31) / 32, (C + 31) / 32, B), block(32, 8);
+    transpose_tokens_kernel<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const __nv_bfloat16*>(x), ld, col0, C,
+                                                                                  T, static_cast<__nv_bfloat16*>(out), ldt);
+    MFB_CUDA_OK(cudaGetLastError());
+    return MFB_OK;
+}
+
+extern "C" int mfb_timestep_sinusoid(const float* t, int M, int dim, float* out, void* stream) {
+    MFB_REQUIRE(t && out && dim % 2 == 0, "bad arguments");
+    const int n = M * dim / 2;
+    sinusoid_kernel<<<(n + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(t, M, dim, out);
+    MFB_CUDA_OK(cudaGetLastError());
+    return MFB_OK;
+}
+
+extern "C" int mfb_linear_small(const float* x, int M, int K, const void* w, const float* b, int N, int act_in, int act_out,
+                                float* y, void* stream) {
+    MFB_REQUIRE(x && w && y && K % 2 == 0, "bad arguments");
+    dim3 grid((N + 7) / 8, (M + 7) / 8), block(256);
+    linear_small_kernel<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(x, M, K, static_cast<const __nv_bfloat16*>(w), b, N,
+                                                                             act_in, act_out, y);
+    MFB_CUDA_OK(cudaGetLastError());
+    return MFB_OK;
+}
+
+extern "C" int mfb_cfg_sched_step(const float* eps, float* x, float* last, float* m0, float* m1, const float* coef, int Bimg,
+                                  long long n, void* stream) {
+    MFB_REQUIRE(eps && x && last && m0 && m1 && coef, "null pointer");
+    const long long total = static_cast<long long>(Bimg) * n;
+    cfg_sched_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(eps, x, last, m0, m1, coef, total);
+    MFB_CUDA_OK(cudaGetLastError());
+    return MFB_OK;
+}

@@ -1,0 +1,221 @@
+// GroupNorm(+SiLU) and LayerNorm over channels-last bf16 activations, fp32 statistics.  HBM-bound kernels:
+// every access is a 16-byte vector, a thread keeps a fixed 8-channel slice so per-channel scale/shift live in
+// registers, and the up-block skip concat is read from its two source tensors directly.
+#include "common.h"
+#include "ptx.cuh"
+
+namespace mfb {
+
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+    float2 t;
+    t = unpack_bf16x2(u.x); f[0] = t.x; f[1] = t.y;
+    t = unpack_bf16x2(u.y); f[2] = t.x; f[3] = t.y;
+    t = unpack_bf16x2(u.z); f[4] = t.x; f[5] = t.y;
+    t = unpack_bf16x2(u.w); f[6] = t.x; f[7] = t.y;
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+    uint4 o;
+    o.x = pack_bf16x2(f[0], f[1]);
+    o.y = pack_bf16x2(f[2], f[3]);
+    o.z = pack_bf16x2(f[4], f[5]);
+    o.w = pack_bf16x2(f[6], f[7]);
+    return o;
+}
+
+// grid (chunks, B), block (CV = C/8, PY).  stats[b][g] = {sum, sumsq}
+__global__ void gn_stats_kernel(const __nv_bfloat16* __restrict__ x1, int C1, const __nv_bfloat16* __restrict__ x2, int C2,
+                                int HW, int groups, int pix_per_cta, float* __restrict__ stats) {
+    __shared__ float gs[64], gq[64];
+    const int C = C1 + C2;
+    const int cpg = C / groups;
+    const int b = blockIdx.y;
+    const int c0 = threadIdx.x * 8;
+    const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+    if (tid < 64) { gs[tid] = 0.f; gq[tid] = 0.f; }
+    __syncthreads();
+    const __nv_bfloat16* src;
+    int ld, cc;
+    if (c0 < C1) { src = x1; ld = C1; cc = c0; } else { src = x2; ld = C2; cc = c0 - C1; }
+    src += static_cast<size_t>(b) * HW * ld + cc;
+    const int p0 = blockIdx.x * pix_per_cta;
+    const int p1 = min(HW, p0 + pix_per_cta);
+    float s[8], q[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { s[e] = 0.f; q[e] = 0.f; }
+    for (int p = p0 + threadIdx.y; p < p1; p += blockDim.y) {
+        const uint4 u = __ldg(reinterpret_cast<const uint4*>(src + static_cast<size_t>(p) * ld));
+        float f[8];
+        unpack8(u, f);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { s[e] += f[e]; q[e] = fmaf(f[e], f[e], q[e]); }
+    }
+    // 8 consecutive channels touch at most two groups (cpg >= 8)
+    const int g0 = c0 / cpg;
+    float sa = 0.f, qa = 0.f, sb = 0.f, qb = 0.f;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        if ((c0 + e) / cpg == g0) { sa += s[e]; qa += q[e]; } else { sb += s[e]; qb += q[e]; }
+    }
+    atomicAdd(&gs[g0], sa);
+    atomicAdd(&gq[g0], qa);
+    if ((c0 + 7) / cpg != g0) {
+        atomicAdd(&gs[g0 + 1], sb);
+        atomicAdd(&gq[g0 + 1], qb);
+    }
+    __syncthreads();
+    if (tid < groups) {
+        atomicAdd(&stats[(static_cast<size_t>(b) * groups + tid) * 2 + 0], gs[tid]);
+        atomicAdd(&stats[(static_cast<size_t>(b) * groups + tid) * 2 + 1], gq[tid]);
+    }
+}
+
+__global__ void gn_apply_kernel(const __nv_bfloat16* __restrict__ x1, int C1, const __nv_bfloat16* __restrict__ x2, int C2,
+                                int HW, int groups, int pix_per_cta, const float* __restrict__ stats, float eps,
+                                const float* __restrict__ gamma, const float* __restrict__ beta, int silu,
+                                __nv_bfloat16* __restrict__ out) {
+    const int C = C1 + C2;
+    const int cpg = C / groups;
+    const int b = blockIdx.y;
+    const int c0 = threadIdx.x * 8;
+    const float inv_cnt = 1.0f / (static_cast<float>(HW) * cpg);
+    float sc[8], sh[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        const int c = c0 + e;
+        const int g = c / cpg;
+        const float sum = __ldg(&stats[(static_cast<size_t>(b) * groups + g) * 2 + 0]);
+        const float sq = __ldg(&stats[(static_cast<size_t>(b) * groups + g) * 2 + 1]);
+        const float mean = sum * inv_cnt;
+        const float var = fmaxf(sq * inv_cnt - mean * mean, 0.f);
+        const float rstd = rsqrtf(var + eps);
+        sc[e] = rstd * __ldg(&gamma[c]);
+        sh[e] = __ldg(&beta[c]) - mean * sc[e];
+    }
+    const __nv_bfloat16* src;
+    int ld, cc;
+    if (c0 < C1) { src = x1; ld = C1; cc = c0; } else { src = x2; ld = C2; cc = c0 - C1; }
+    src += static_cast<size_t>(b) * HW * ld + cc;
+    __nv_bfloat16* dst = out + static_cast<size_t>(b) * HW * C + c0;
+    const int p0 = blockIdx.x * pix_per_cta;
+    const int p1 = min(HW, p0 + pix_per_cta);
+    for (int p = p0 + threadIdx.y; p < p1; p += blockDim.y) {
+        const uint4 u = __ldg(reinterpret_cast<const uint4*>(src + static_cast<size_t>(p) * ld));
+        float f[8];
+        unpack8(u, f);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            float y = fmaf(f[e], sc[e], sh[e]);
+            f[e] = silu ? silu_f(y) : y;
+        }
+        *reinterpret_cast<uint4*>(dst + static_cast<size_t>(p) * C) = pack8(f);
+    }
+}
+
+// one warp per row, two-pass (mean, then centred variance) on register-resident data
+template <int NV>
+__global__ void layernorm_kernel(const __nv_bfloat16* __restrict__ x, int rows, int C, float eps,
+                                 const float* __restrict__ gamma, const float* __restrict__ beta,
+                                 __nv_bfloat16* __restrict__ out) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const int nvec = C >> 3;
+    const __nv_bfloat16* src = x + static_cast<size_t>(row) * C;
+    float f[NV][8];
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const int v = lane + i * 32;
+        if (v < nvec) {
+            unpack8(__ldg(reinterpret_cast<const uint4*>(src + v * 8)), f[i]);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) sum += f[i][e];
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float mean = sum / C;
+    float var = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const int v = lane + i * 32;
+        if (v < nvec) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) { const float d = f[i][e] - mean; var = fmaf(d, d, var); }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) var += __shfl_xor_sync(0xffffffffu, var, o);
+    const float rstd = rsqrtf(var / C + eps);
+    __nv_bfloat16* dst = out + static_cast<size_t>(row) * C;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const int v = lane + i * 32;
+        if (v < nvec) {
+            const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + v * 8));
+            const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + v * 8 + 4));
+            const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + v * 8));
+            const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta + v * 8 + 4));
+            float y[8];
+            y[0] = (f[i][0] - mean) * rstd * g0.x + b0.x;
+            y[1] = (f[i][1] - mean) * rstd * g0.y + b0.y;
+            y[2] = (f[i][2] - mean) * rstd * g0.z + b0.z;
+            y[3] = (f[i][3] - mean) * rstd * g0.w + b0.w;
+            y[4] = (f[i][4] - mean) * rstd * g1.x + b1.x;
+            y[5] = (f[i][5] - mean) * rstd * g1.y + b1.y;
+            y[6] = (f[i][6] - mean) * rstd * g1.z + b1.z;
+            y[7] = (f[i][7] - mean) * rstd * g1.w + b1.w;
+            *reinterpret_cast<uint4*>(dst + v * 8) = pack8(y);
+        }
+    }
+}
+
+}  // namespace mfb
+
+using namespace mfb;
+
+extern "C" int mfb_groupnorm(const void* x1, int C1, const void* x2, int C2, int B, int HW, int groups, float eps,
+                             const float* gamma, const float* beta, int silu, float* stats_ws, void* out, void* stream) {
+    MFB_REQUIRE(x1 && out && gamma && beta && stats_ws, "null pointer");
+    if (!x2) C2 = 0;
+    const int C = C1 + C2;
+    MFB_REQUIRE(C1 % 8 == 0 && C2 % 8 == 0, "channel counts must be multiples of 8");
+    MFB_REQUIRE(groups > 0 && groups <= 64 && C % groups == 0 && C / groups >= 8, "unsupported group size (C=%d groups=%d)", C, groups);
+    const int CV = C / 8;
+    MFB_REQUIRE(CV <= 1024, "C too large");
+    const int PY = CV >= 256 ? 1 : 256 / CV;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    // enough CTAs to cover the machine a few times, but at least 4*PY pixels each
+    int chunks = (4 * 148 + B - 1) / B;
+    const int max_chunks = (HW + 4 * PY - 1) / (4 * PY);
+    if (chunks > max_chunks) chunks = max_chunks;
+    if (chunks < 1) chunks = 1;
+    const int ppc = (HW + chunks - 1) / chunks;
+    chunks = (HW + ppc - 1) / ppc;
+    MFB_CUDA_OK(cudaMemsetAsync(stats_ws, 0, sizeof(float) * 2 * B * groups, st));
+    dim3 grid(chunks, B), block(CV, PY);
+    gn_stats_kernel<<<grid, block, 0, st>>>(static_cast<const __nv_bfloat16*>(x1), C1, static_cast<const __nv_bfloat16*>(x2), C2,
+                                            HW, groups, ppc, stats_ws);
+    gn_apply_kernel<<<grid, block, 0, st>>>(static_cast<const __nv_bfloat16*>(x1), C1, static_cast<const __nv_bfloat16*>(x2), C2,
+                                            HW, groups, ppc, stats_ws, eps, gamma, beta, silu,
+                                            static_cast<__nv_bfloat16*>(out));
+    MFB_CUDA_OK(cudaGetLastError());
+    return MFB_OK;
+}
+
+extern "C" int mfb_layernorm(const void* x, int rows, int C, float eps, const float* gamma, const float* beta, void* out,
+                             void* stream) {
+    MFB_REQUIRE(x && out && gamma && beta, "null pointer");
+    MFB_REQUIRE(C % 8 == 0 && C <= 2048, "C must be a multiple of 8 and <= 2048 (got %d)", C);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int warps = 8;
+    dim3 grid((rows + warps - 1) / warps), block(warps * 32);
+    const int nv = (C / 8 + 31) / 32;
+    auto X = static_cast<const __nv_bfloat16*>(x);
+    auto O = static_cast<__nv_bfloat16*>(out);
+    if (nv <= 2) layernorm_kernel<2><<<grid, block, 0, st>>>(X, rows, C, eps, gamma, beta, O);
+    else if (nv <= 5) layernorm_kernel<5><<<grid, block, 0, st>>>(X, rows, C, eps, gamma, beta, O);
+    else layernorm_kernel<8><<<grid, block, 0, st>>>(X, rows, C, eps, gamma, beta, O);
+    MFB_CUDA_OK(cudaGetLastError());
+    return MFB_OK;
+}

@@ -1,0 +1,82 @@
+"""ctypes binding of libmfb200.so (the C ABI declared in include/mfb200.h).
+
+There is no fallback: if the shared library is missing or the device is not sm_100 every
+entry point raises.  Build it with `python __graft_entry__.py build` (nvcc, in-tree).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libmfb200.so")
+
+_lib = None
+_inited_device = None
+
+vp, i32, i64, f32, f64 = C.c_void_p, C.c_int, C.c_longlong, C.c_float, C.c_double
+
+
+class ConvDesc(C.Structure):
+    _fields_ = [
+        ("B", i32), ("H", i32), ("W", i32), ("Cin", i32), ("Cout", i32), ("ksize", i32), ("stride", i32),
+        ("x", vp), ("n_extra", i32), ("extra_x", vp * 3), ("extra_C", i32 * 3), ("w", vp), ("bias", vp),
+        ("rowbias", vp), ("rowbias_ld", i32), ("alpha", vp), ("res1", vp), ("res2", vp), ("out", vp),
+        ("geglu", i32), ("block_n", i32),
+    ]
+
+
+_SIGS = {
+    "mfb_abi_version": (i32, []),
+    "mfb_init": (i32, [i32]),
+    "mfb_last_error": (C.c_char_p, []),
+    "mfb_conv_plan_create": (i32, [C.POINTER(ConvDesc), C.POINTER(vp)]),
+    "mfb_plan_run": (i32, [vp, vp]),
+    "mfb_plan_destroy": (i32, [vp]),
+    "mfb_plan_flops": (f64, [vp]),
+    "mfb_plan_ktotal": (i32, [vp]),
+    "mfb_groupnorm": (i32, [vp, i32, vp, i32, i32, i32, i32, f32, vp, vp, i32, vp, vp, vp]),
+    "mfb_layernorm": (i32, [vp, i32, i32, f32, vp, vp, vp, vp]),
+    "mfb_attention": (i32, [vp, i32, vp, i32, vp, i32, vp, i32, i32, i32, i32, i32, i32, vp]),
+    "mfb_transpose_tokens": (i32, [vp, i32, i32, i32, i32, i32, vp, i32, vp]),
+    "mfb_conv_in": (i32, [vp, i32, vp, i32, i32, i32, i32, vp, vp, i32, vp, vp, vp, vp]),
+    "mfb_conv_out": (i32, [vp, i32, i32, i32, i32, vp, vp, i32, vp, vp]),
+    "mfb_upsample2x": (i32, [vp, i32, i32, i32, i32, vp, vp]),
+    "mfb_nchw_f32_to_nhwc_bf16": (i32, [vp, i32, i32, i32, i32, vp, vp]),
+    "mfb_nhwc_bf16_to_nchw_f32": (i32, [vp, i32, i32, i32, i32, vp, vp]),
+    "mfb_f32_to_bf16": (i32, [vp, i64, vp, vp]),
+    "mfb_timestep_sinusoid": (i32, [vp, i32, i32, vp, vp]),
+    "mfb_linear_small": (i32, [vp, i32, i32, vp, vp, i32, i32, i32, vp, vp]),
+    "mfb_cfg_sched_step": (i32, [vp, vp, vp, vp, vp, vp, i32, i64, vp]),
+}
+EXPORTS = tuple(_SIGS)
+
+
+class MfbError(RuntimeError):
+    pass
+
+
+def load(init_device: int | None = None):
+    """Load the library (no GPU needed) and optionally bind it to a device (GPU needed)."""
+    global _lib, _inited_device
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise MfbError(f"{LIB_PATH} not built; run `python __graft_entry__.py build`. There is no CPU fallback.")
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGS.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        if lib.mfb_abi_version() != 1:
+            raise MfbError("libmfb200.so ABI version mismatch")
+        _lib = lib
+    if init_device is not None and _inited_device != init_device:
+        check(_lib.mfb_init(init_device))
+        _inited_device = init_device
+    return _lib
+
+
+def check(rc: int):
+    if rc != 0:
+        msg = _lib.mfb_last_error().decode() if _lib is not None else "?"
+        raise MfbError(f"libmfb200 error {rc}: {msg}")

@@ -1,0 +1,183 @@
+"""Torch-tensor front ends of the C-ABI kernels.  PyTorch only supplies device memory and the stream;
+all math runs in libmfb200.so.  Every function requires CUDA tensors on an sm_100 device."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import torch
+
+from . import _lib
+from ._lib import ConvDesc, check
+
+bf16 = torch.bfloat16
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def lib():
+    if not torch.cuda.is_available():
+        raise _lib.MfbError("mirrorfusion_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+    return _lib.load(torch.cuda.current_device())
+
+
+def _req(t: torch.Tensor, dtype, name: str):
+    if t.dtype != dtype or not t.is_cuda or not t.is_contiguous():
+        raise ValueError(f"{name}: expected contiguous CUDA {dtype} tensor, got {t.dtype} {t.device} contiguous={t.is_contiguous()}")
+
+
+# --------------------------------------------------------------------------------------------- weight packing
+def pack_conv_weight(w: torch.Tensor, extras: Sequence[torch.Tensor] = ()) -> torch.Tensor:
+    """OIHW conv weight (or [out,in] linear weight) -> [Cout, kh*kw*Cin (+ extra 1x1 segments)] bf16,
+    K ordered (kh, kw, cin) to match the tap-major K loop of the implicit GEMM."""
+    if w.dim() == 2:
+        w = w[:, :, None, None]
+    parts = [w.permute(0, 2, 3, 1).reshape(w.shape[0], -1)]
+    for e in extras:
+        parts.append(e.reshape(e.shape[0], -1))
+    return torch.cat(parts, 1).to(bf16).contiguous()
+
+
+def pack_geglu(w: torch.Tensor, b: torch.Tensor):
+    """GEGLU proj [8C, C]: rows [0,4C) value, [4C,8C) gate (activations.py:100-103) -> interleave per 128:
+    64 value rows then the 64 matching gate rows."""
+    half = w.shape[0] // 2
+    wv, wg = w[:half].reshape(half // 64, 64, -1), w[half:].reshape(half // 64, 64, -1)
+    wp = torch.stack([wv, wg], 1).reshape(2 * half, -1)
+    bp = torch.stack([b[:half].reshape(-1, 64), b[half:].reshape(-1, 64)], 1).reshape(-1)
+    return wp.to(bf16).contiguous(), bp.float().contiguous()
+
+
+# --------------------------------------------------------------------------------------------- implicit GEMM
+class ConvPlan:
+    """A prepared implicit-GEMM launch (tensor maps encoded once; all buffers at fixed addresses)."""
+
+    def __init__(self, x: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, B: int, H: int, W: int, Cin: int,
+                 Cout: int, ksize: int = 1, stride: int = 1, extras: Sequence[torch.Tensor] = (),
+                 bias: Optional[torch.Tensor] = None, rowbias: Optional[torch.Tensor] = None, rowbias_ld: int = 0,
+                 alpha: Optional[torch.Tensor] = None, res1: Optional[torch.Tensor] = None,
+                 res2: Optional[torch.Tensor] = None, geglu: bool = False, block_n: int = 0):
+        L = lib()
+        _req(x, bf16, "x"); _req(w, bf16, "w"); _req(out, bf16, "out")
+        d = ConvDesc()
+        d.B, d.H, d.W, d.Cin, d.Cout, d.ksize, d.stride = B, H, W, Cin, Cout, ksize, stride
+        d.x, d.w, d.out = x.data_ptr(), w.data_ptr(), out.data_ptr()
+        d.n_extra = len(extras)
+        for i, e in enumerate(extras):
+            _req(e, bf16, f"extra{i}")
+            d.extra_x[i] = e.data_ptr()
+            d.extra_C[i] = e.shape[-1]
+        for name, t in (("bias", bias), ("rowbias", rowbias), ("alpha", alpha)):
+            if t is not None:
+                _req(t, torch.float32, name)
+                setattr(d, name, t.data_ptr())
+        d.rowbias_ld = rowbias_ld
+        for name, t in (("res1", res1), ("res2", res2)):
+            if t is not None:
+                _req(t, bf16, name)
+                setattr(d, name, t.data_ptr())
+        d.geglu = int(geglu)
+        d.block_n = block_n
+        ktot = ksize * ksize * Cin + sum(e.shape[-1] for e in extras)
+        if tuple(w.shape) != (Cout, ktot):
+            raise ValueError(f"packed weight shape {tuple(w.shape)} != ({Cout}, {ktot})")
+        h = C.c_void_p()
+        check(L.mfb_conv_plan_create(C.byref(d), C.byref(h)))
+        self._h = h
+        self._L = L
+        self._keep = (x, w, out, extras, bias, rowbias, alpha, res1, res2)
+        self.flops = L.mfb_plan_flops(h)
+
+    def run(self):
+        check(self._L.mfb_plan_run(self._h, _stream()))
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                self._L.mfb_plan_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+
+def linear_plan(x: torch.Tensor, w: torch.Tensor, out: torch.Tensor, **kw) -> ConvPlan:
+    """x [M, K] bf16, w [N, K] packed bf16 -> out [M, N] (or [M, N/2] with geglu)."""
+    M, K = x.shape
+    return ConvPlan(x, w, out, B=1, H=1, W=M, Cin=K, Cout=w.shape[0], ksize=1, **kw)
+
+
+# --------------------------------------------------------------------------------------------- norms
+def groupnorm(x1, x2, gamma, beta, out, stats_ws, *, B, HW, groups, eps, silu):
+    L = lib()
+    C1 = x1.shape[-1]
+    C2 = 0 if x2 is None else x2.shape[-1]
+    check(L.mfb_groupnorm(_ptr(x1), C1, _ptr(x2), C2, B, HW, groups, eps, _ptr(gamma), _ptr(beta), int(silu),
+                          _ptr(stats_ws), _ptr(out), _stream()))
+
+
+def layernorm(x, gamma, beta, out, eps=1e-5):
+    L = lib()
+    rows, Cc = x.numel() // x.shape[-1], x.shape[-1]
+    check(L.mfb_layernorm(_ptr(x), rows, Cc, eps, _ptr(gamma), _ptr(beta), _ptr(out), _stream()))
+
+
+# --------------------------------------------------------------------------------------------- attention
+def attention(q, k, vt, out, *, B, heads, head_dim, Tq, Tk, ldq=None, ldk=None, ldvt=None, ldo=None):
+    L = lib()
+    check(L.mfb_attention(_ptr(q), ldq or q.shape[-1], _ptr(k), ldk or k.shape[-1], _ptr(vt), ldvt or vt.shape[-1],
+                          _ptr(out), ldo or out.shape[-1], B, heads, head_dim, Tq, Tk, _stream()))
+
+
+def transpose_tokens(x, out, *, ld, col0, Cc, B, T, ldt):
+    check(lib().mfb_transpose_tokens(_ptr(x), ld, col0, Cc, B, T, _ptr(out), ldt, _stream()))
+
+
+# --------------------------------------------------------------------------------------------- boundary / misc
+def conv_in(sample, cond, w, bias, out, tap=None, out_post=None):
+    B, Ca, H, W = sample.shape
+    Cb = 0 if cond is None else cond.shape[1]
+    check(lib().mfb_conv_in(_ptr(sample), Ca, _ptr(cond), Cb, B, H, W, _ptr(w), _ptr(bias), out.shape[-1], _ptr(out),
+                            _ptr(tap), _ptr(out_post), _stream()))
+
+
+def conv_out(x, w, bias, out, *, B, H, W):
+    check(lib().mfb_conv_out(_ptr(x), x.shape[-1], B, H, W, _ptr(w), _ptr(bias), out.shape[1], _ptr(out), _stream()))
+
+
+def upsample2x(x, out, *, B, H, W):
+    check(lib().mfb_upsample2x(_ptr(x), B, H, W, x.shape[-1], _ptr(out), _stream()))
+
+
+def nchw_to_nhwc(x, out):
+    B, Cc, H, W = x.shape
+    check(lib().mfb_nchw_f32_to_nhwc_bf16(_ptr(x), B, Cc, H, W, _ptr(out), _stream()))
+
+
+def nhwc_to_nchw(x, out):
+    B, Cc, H, W = out.shape
+    check(lib().mfb_nhwc_bf16_to_nchw_f32(_ptr(x), B, Cc, H, W, _ptr(out), _stream()))
+
+
+def f32_to_bf16(x, out):
+    check(lib().mfb_f32_to_bf16(_ptr(x), x.numel(), _ptr(out), _stream()))
+
+
+def timestep_sinusoid(t, out):
+    check(lib().mfb_timestep_sinusoid(_ptr(t), t.numel(), out.shape[-1], _ptr(out), _stream()))
+
+
+def linear_small(x, w, b, y, act_in=False, act_out=False):
+    M, K = x.shape
+    check(lib().mfb_linear_small(_ptr(x), M, K, _ptr(w), _ptr(b), w.shape[0], int(act_in), int(act_out), _ptr(y), _stream()))
+
+
+def cfg_sched_step(eps, x, last, m0, m1, coef):
+    Bimg = x.shape[0]
+    n = x.numel() // Bimg
+    check(lib().mfb_cfg_sched_step(_ptr(eps), _ptr(x), _ptr(last), _ptr(m0), _ptr(m1), _ptr(coef), Bimg, n, _stream()))

@@ -1,0 +1,271 @@
+"""Kernel-level parity: every C-ABI kernel against a plain PyTorch fp32 evaluation of the same op on the same
+(bf16-rounded) inputs.  Tolerances are rel-L2 in fp32: bf16 output rounding alone is ~1.5e-3."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+bf16 = torch.bfloat16
+
+
+def rel(a, b):
+    a, b = a.double(), b.double()
+    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from mirrorfusion_b200 import ops as o
+    o.lib()
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    return o
+
+
+def _g(seed):
+    return torch.Generator(device="cuda").manual_seed(seed)
+
+
+def randn(*shape, seed=0, scale=1.0, dtype=bf16):
+    return (torch.randn(*shape, generator=_g(seed), device="cuda") * scale).to(dtype)
+
+
+def nhwc_to_nchw(x):
+    return x.float().permute(0, 3, 1, 2).contiguous()
+
+
+# ------------------------------------------------------------------------------------------------ implicit GEMM
+@pytest.mark.parametrize("M,K,N", [(512, 320, 320), (154, 768, 320), (8192, 320, 960), (100, 64, 8), (128, 1280, 1280)])
+def test_linear(ops, M, K, N):
+    x = randn(M, K, seed=1)
+    w = randn(N, K, seed=2, scale=K ** -0.5)
+    b = randn(N, seed=3, dtype=torch.float32)
+    out = torch.full((M, N), float("nan"), device="cuda", dtype=bf16)
+    ops.linear_plan(x, w, out, bias=b).run()
+    ref = x.float() @ w.float().t() + b
+    assert rel(out.float(), ref) < 4e-3
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout", [(2, 16, 16, 128, 320), (4, 8, 8, 64, 128), (2, 64, 64, 320, 320),
+                                            (3, 8, 8, 64, 160), (1, 24, 24, 64, 160), (2, 12, 12, 128, 128)])
+def test_conv3x3_full_epilogue(ops, B, H, W, Cin, Cout):
+    x = randn(B, H, W, Cin, seed=1)
+    w = randn(Cout, Cin, 3, 3, seed=2, scale=(9 * Cin) ** -0.5)
+    bias = randn(Cout, seed=3, dtype=torch.float32)
+    rowbias = randn(B, Cout + 64, seed=4, dtype=torch.float32)   # a slice of a wider table
+    alpha = torch.tensor([0.75], device="cuda")
+    r1 = randn(B, H, W, Cout, seed=5)
+    r2 = randn(B, H, W, Cout, seed=6)
+    out = torch.full((B, H, W, Cout), float("nan"), device="cuda", dtype=bf16)
+    wp = ops.pack_conv_weight(w.float())
+    # rowbias is a [B, ld] table with ld > Cout: the kernel reads the first Cout columns of each row
+    plan = ops.ConvPlan(x, wp, out, B=B, H=H, W=W, Cin=Cin, Cout=Cout, ksize=3, bias=bias,
+                        rowbias=rowbias, rowbias_ld=Cout + 64, alpha=alpha, res1=r1, res2=r2)
+    plan.run()
+    ref = F.conv2d(nhwc_to_nchw(x), w.float(), None, padding=1)
+    ref = (ref + bias.view(1, -1, 1, 1) + rowbias[:, :Cout, None, None]) * 0.75 + nhwc_to_nchw(r1) + nhwc_to_nchw(r2)
+    assert rel(nhwc_to_nchw(out), ref) < 4e-3
+
+
+@pytest.mark.parametrize("B,H,W,C", [(2, 32, 32, 64), (2, 16, 16, 128), (1, 64, 64, 320), (2, 24, 24, 64)])
+def test_conv3x3_stride2(ops, B, H, W, C):
+    x = randn(B, H, W, C, seed=1)
+    w = randn(C, C, 3, 3, seed=2, scale=(9 * C) ** -0.5)
+    bias = randn(C, seed=3, dtype=torch.float32)
+    tap = randn(B, H // 2, W // 2, C, seed=4)
+    out = torch.full((B, H // 2, W // 2, C), float("nan"), device="cuda", dtype=bf16)
+    ops.ConvPlan(x, ops.pack_conv_weight(w.float()), out, B=B, H=H, W=W, Cin=C, Cout=C, ksize=3, stride=2, bias=bias,
+                 res2=tap).run()
+    ref = F.conv2d(nhwc_to_nchw(x), w.float(), bias, stride=2, padding=1) + nhwc_to_nchw(tap)
+    assert rel(nhwc_to_nchw(out), ref) < 4e-3
+
+
+def test_conv3x3_with_shortcut_segments(ops):
+    # ResnetBlock2D tail on an up block: conv2(h) + conv_shortcut(cat([x, skip])) fused in one accumulator
+    B, H, W, Cmid, Ca, Cb = 2, 16, 16, 128, 128, 64
+    h = randn(B, H, W, Cmid, seed=1)
+    xa = randn(B, H, W, Ca, seed=2)
+    xb = randn(B, H, W, Cb, seed=3)
+    w2 = randn(Cmid, Cmid, 3, 3, seed=4, scale=(9 * Cmid) ** -0.5)
+    ws = randn(Cmid, Ca + Cb, 1, 1, seed=5, scale=(Ca + Cb) ** -0.5)
+    bias = randn(Cmid, seed=6, dtype=torch.float32)
+    out = torch.full((B, H, W, Cmid), float("nan"), device="cuda", dtype=bf16)
+    wp = ops.pack_conv_weight(w2.float(), extras=[ws.float()[:, :Ca, 0, 0], ws.float()[:, Ca:, 0, 0]])
+    ops.ConvPlan(h, wp, out, B=B, H=H, W=W, Cin=Cmid, Cout=Cmid, ksize=3, extras=[xa, xb], bias=bias).run()
+    ref = F.conv2d(nhwc_to_nchw(h), w2.float(), bias, padding=1) + F.conv2d(
+        torch.cat([nhwc_to_nchw(xa), nhwc_to_nchw(xb)], 1), ws.float())
+    assert rel(nhwc_to_nchw(out), ref) < 4e-3
+
+
+def test_geglu_linear(ops):
+    M, Cc = 384, 320
+    x = randn(M, Cc, seed=1)
+    w = randn(8 * Cc, Cc, seed=2, scale=Cc ** -0.5)
+    b = randn(8 * Cc, seed=3, dtype=torch.float32)
+    wp, bp = ops.pack_geglu(w.float(), b)
+    out = torch.full((M, 4 * Cc), float("nan"), device="cuda", dtype=bf16)
+    ops.linear_plan(x, wp, out, bias=bp, geglu=True).run()
+    y = x.float() @ w.float().t() + b
+    val, gate = y.chunk(2, -1)
+    assert rel(out.float(), val * F.gelu(gate)) < 4e-3
+
+
+def test_conv_block_n_variants_agree(ops):
+    B, H, W, Cin, Cout = 2, 16, 16, 64, 640
+    x = randn(B, H, W, Cin, seed=1)
+    wp = ops.pack_conv_weight(randn(Cout, Cin, 3, 3, seed=2, scale=0.05).float())
+    o1 = torch.empty(B, H, W, Cout, device="cuda", dtype=bf16)
+    o2 = torch.empty_like(o1)
+    ops.ConvPlan(x, wp, o1, B=B, H=H, W=W, Cin=Cin, Cout=Cout, ksize=3, block_n=128).run()
+    ops.ConvPlan(x, wp, o2, B=B, H=H, W=W, Cin=Cin, Cout=Cout, ksize=3, block_n=160).run()
+    assert torch.equal(o1, o2)    # same K order, same fp32 accumulation -> bit identical
+
+
+# ------------------------------------------------------------------------------------------------ norms
+@pytest.mark.parametrize("B,HW,C1,C2,groups,eps,silu", [
+    (2, 4096, 320, 0, 32, 1e-5, True), (2, 256, 1280, 640, 32, 1e-5, True), (2, 1024, 640, 320, 32, 1e-5, True),
+    (3, 64, 1280, 1280, 32, 1e-5, True), (2, 1024, 640, 0, 32, 1e-6, False), (2, 256, 64, 0, 8, 1e-5, True)])
+def test_groupnorm(ops, B, HW, C1, C2, groups, eps, silu):
+    x1 = randn(B, HW, C1, seed=1) + 0.5
+    x2 = randn(B, HW, C2, seed=2, scale=2.0) if C2 else None
+    Cc = C1 + C2
+    gamma = 1 + 0.1 * randn(Cc, seed=3, dtype=torch.float32)
+    beta = 0.1 * randn(Cc, seed=4, dtype=torch.float32)
+    out = torch.full((B, HW, Cc), float("nan"), device="cuda", dtype=bf16)
+    ws = torch.empty(B * groups * 2, device="cuda")
+    ops.groupnorm(x1, x2, gamma, beta, out, ws, B=B, HW=HW, groups=groups, eps=eps, silu=silu)
+    xin = x1.float() if x2 is None else torch.cat([x1.float(), x2.float()], -1)
+    ref = F.group_norm(xin.transpose(1, 2), groups, gamma, beta, eps)
+    if silu:
+        ref = F.silu(ref)
+    assert rel(out.float(), ref.transpose(1, 2)) < 4e-3
+
+
+@pytest.mark.parametrize("rows,C", [(8192, 320), (2048, 640), (513, 1280), (64, 64), (100, 128)])
+def test_layernorm(ops, rows, C):
+    x = randn(rows, C, seed=1) * 2 + 0.3
+    gamma = 1 + 0.1 * randn(C, seed=2, dtype=torch.float32)
+    beta = 0.1 * randn(C, seed=3, dtype=torch.float32)
+    out = torch.full((rows, C), float("nan"), device="cuda", dtype=bf16)
+    ops.layernorm(x, gamma, beta, out)
+    assert rel(out.float(), F.layer_norm(x.float(), (C,), gamma, beta, 1e-5)) < 4e-3
+
+
+# ------------------------------------------------------------------------------------------------ attention
+@pytest.mark.parametrize("B,heads,d,Tq,Tk", [
+    (2, 8, 40, 4096, 4096), (2, 8, 80, 1024, 1024), (2, 8, 160, 256, 256), (2, 8, 160, 64, 64),
+    (2, 8, 40, 4096, 77), (2, 8, 80, 1024, 77), (2, 8, 160, 256, 77), (2, 8, 160, 64, 77),
+    (2, 2, 32, 256, 256), (2, 2, 64, 64, 64), (2, 2, 64, 16, 77), (1, 8, 40, 200, 333)])
+def test_attention(ops, B, heads, d, Tq, Tk):
+    Cc = heads * d
+    q = randn(B, Tq, Cc, seed=1)
+    k = randn(B, Tk, Cc, seed=2)
+    v = randn(B, Tk, Cc, seed=3)
+    ldt = (Tk + 7) // 8 * 8
+    vt = torch.full((B, Cc, ldt), float("nan"), device="cuda", dtype=bf16)
+    ops.transpose_tokens(v, vt, ld=Cc, col0=0, Cc=Cc, B=B, T=Tk, ldt=ldt)
+    assert torch.equal(vt[:, :, :Tk], v.transpose(1, 2))
+    out = torch.full((B, Tq, Cc), float("nan"), device="cuda", dtype=bf16)
+    ops.attention(q, k, vt, out, B=B, heads=heads, head_dim=d, Tq=Tq, Tk=Tk)
+    qh = q.float().view(B, Tq, heads, d).transpose(1, 2)
+    kh = k.float().view(B, Tk, heads, d).transpose(1, 2)
+    vh = v.float().view(B, Tk, heads, d).transpose(1, 2)
+    s = (qh @ kh.transpose(-1, -2)) * d ** -0.5
+    ref = (torch.softmax(s, -1) @ vh).transpose(1, 2).reshape(B, Tq, Cc)
+    assert rel(out.float(), ref) < 6e-3
+
+
+def test_attention_fused_qkv_layout(ops):
+    # q/k read straight out of a fused [B, T, 3C] projection buffer via leading dimensions
+    B, heads, d, T = 2, 8, 40, 512
+    Cc = heads * d
+    qkv = randn(B, T, 3 * Cc, seed=7)
+    vt = torch.empty(B, Cc, T, device="cuda", dtype=bf16)
+    ops.transpose_tokens(qkv, vt, ld=3 * Cc, col0=2 * Cc, Cc=Cc, B=B, T=T, ldt=T)
+    out = torch.empty(B, T, Cc, device="cuda", dtype=bf16)
+    ops.attention(qkv, qkv[:, :, Cc:], vt, out, B=B, heads=heads, head_dim=d, Tq=T, Tk=T, ldq=3 * Cc, ldk=3 * Cc)
+    q, k, v = [t.float().view(B, T, heads, d).transpose(1, 2) for t in qkv.split(Cc, -1)]
+    ref = (torch.softmax(q @ k.transpose(-1, -2) * d ** -0.5, -1) @ v).transpose(1, 2).reshape(B, T, Cc)
+    assert rel(out.float(), ref) < 6e-3
+
+
+# ------------------------------------------------------------------------------------------------ boundary / misc
+@pytest.mark.parametrize("Ca,Cb,H,W", [(4, 0, 64, 64), (4, 6, 64, 64), (4, 6, 20, 12)])
+def test_conv_in(ops, Ca, Cb, H, W):
+    B, Cout = 2, 320
+    xa = randn(B, Ca, H, W, seed=1, dtype=torch.float32)
+    xb = randn(B, Cb, H, W, seed=2, dtype=torch.float32) if Cb else None
+    w = randn(Cout, Ca + Cb, 3, 3, seed=3, scale=0.1, dtype=torch.float32)
+    b = randn(Cout, seed=4, dtype=torch.float32)
+    tap = randn(B, H, W, Cout, seed=5)
+    out = torch.empty(B, H, W, Cout, device="cuda", dtype=bf16)
+    post = torch.empty_like(out)
+    ops.conv_in(xa, xb, w.permute(2, 3, 1, 0).contiguous(), b, out, tap, post)
+    xin = xa if xb is None else torch.cat([xa, xb], 1)
+    ref = F.conv2d(xin, w, b, padding=1)
+    assert rel(nhwc_to_nchw(out), ref) < 4e-3
+    assert rel(nhwc_to_nchw(post), ref + nhwc_to_nchw(tap)) < 4e-3
+
+
+def test_conv_out(ops):
+    B, H, W, Cin = 2, 64, 64, 320
+    x = randn(B, H, W, Cin, seed=1)
+    w = randn(4, Cin, 3, 3, seed=2, scale=0.02, dtype=torch.float32)
+    b = randn(4, seed=3, dtype=torch.float32)
+    out = torch.empty(B, 4, H, W, device="cuda")
+    ops.conv_out(x, w.permute(0, 2, 3, 1).contiguous(), b, out, B=B, H=H, W=W)
+    assert rel(out, F.conv2d(nhwc_to_nchw(x), w, b, padding=1)) < 1e-4
+
+
+def test_upsample_and_layout(ops):
+    B, H, W, Cc = 2, 8, 8, 128
+    x = randn(B, H, W, Cc, seed=1)
+    up = torch.empty(B, 2 * H, 2 * W, Cc, device="cuda", dtype=bf16)
+    ops.upsample2x(x, up, B=B, H=H, W=W)
+    ref = F.interpolate(nhwc_to_nchw(x), scale_factor=2.0, mode="nearest")
+    assert torch.equal(nhwc_to_nchw(up), ref)
+    f = randn(B, 5, 7, 9, seed=2, dtype=torch.float32)
+    nh = torch.empty(B, 7, 9, 5, device="cuda", dtype=bf16)
+    ops.nchw_to_nhwc(f, nh)
+    assert torch.equal(nh, f.permute(0, 2, 3, 1).to(bf16))
+    back = torch.empty(B, 5, 7, 9, device="cuda")
+    ops.nhwc_to_nchw(nh, back)
+    assert torch.equal(back, nh.float().permute(0, 3, 1, 2))
+
+
+def test_timestep_path(ops):
+    t = torch.tensor([999.0, 500.0, 1.0], device="cuda")
+    emb = torch.empty(3, 320, device="cuda")
+    ops.timestep_sinusoid(t, emb)
+    half = 160
+    freq = torch.exp(-math.log(10000.0) * torch.arange(half, device="cuda", dtype=torch.float32) / half)
+    a = t[:, None] * freq[None]
+    assert torch.allclose(emb, torch.cat([a.cos(), a.sin()], -1), atol=2e-4)
+    w = randn(1280, 320, seed=1, scale=0.05)
+    b = randn(1280, seed=2, dtype=torch.float32)
+    y = torch.empty(3, 1280, device="cuda")
+    ops.linear_small(emb, w, b, y, act_in=False, act_out=True)
+    assert rel(y, F.silu(emb @ w.float().t() + b)) < 1e-5
+    y2 = torch.empty(3, 1280, device="cuda")
+    ops.linear_small(emb, w, b, y2, act_in=True, act_out=False)
+    assert rel(y2, F.silu(emb) @ w.float().t() + b) < 1e-5
+
+
+def test_cfg_sched_kernel(ops):
+    Bi, n = 3, 4 * 64 * 64
+    eps = randn(2 * Bi, n, seed=1, dtype=torch.float32)
+    x = randn(Bi, n, seed=2, dtype=torch.float32)
+    last = randn(Bi, n, seed=3, dtype=torch.float32)
+    m0 = randn(Bi, n, seed=4, dtype=torch.float32)
+    m1 = randn(Bi, n, seed=5, dtype=torch.float32)
+    coef = torch.tensor([7.5, 1.1, -0.4, 0.9, 0.2, -0.05, 0.3, 1.0, 0.8, 0.15, -0.07, 0.0], device="cuda")
+    e = eps[:Bi] + 7.5 * (eps[Bi:] - eps[:Bi])
+    mt = 1.1 * x - 0.4 * e
+    xc = 0.9 * last + 0.2 * m0 - 0.05 * m1 + 0.3 * mt
+    xn = 0.8 * xc + 0.15 * mt - 0.07 * m0
+    m0_old = m0.clone()
+    ops.cfg_sched_step(eps, x, last, m0, m1, coef)
+    assert rel(x, xn) < 1e-6 and rel(last, xc) < 1e-6 and rel(m0, mt) < 1e-6 and torch.equal(m1, m0_old)
