@@ -132,14 +132,16 @@ int mfb_linear_small(const float* x, int M, int K, const void* w, const float* b
 /* ------------------------------------------------------------------------------------------------------------
  * CFG combine + scheduler step fused (S/pipelines/brushnet/pipeline_brushnet.py:1310-1315 with
  * S/schedulers/scheduling_unipc_multistep.py:425,567-572,703-709 / S/schedulers/scheduling_ddim.py:404-450).
- * eps: [2*Bimg, n] fp32 (uncond half first).  All tensors fp32 [Bimg, n].  coef: device array of 12 floats:
+ * eps_uncond / eps_cond: the two halves of the [2*Bimg, n] fp32 noise prediction (uncond half first in the
+ * reference batch; pass the same pointer twice with g = 0 for an already-guided prediction).  All tensors fp32
+ * [Bimg, n].  coef: device array of 12 floats:
  *   g, c_x, c_eps                      : m_t   = c_x*x + c_eps*eps_guided           (x0-prediction)
  *   a_last, a_m0, a_m1, a_mt, use_corr : x_c   = a_last*last + a_m0*m0 + a_m1*m1 + a_mt*m_t   (UniC; skipped if use_corr==0)
  *   b_x, b_mt, b_m0, b_eps             : x_new = b_x*x_c + b_mt*m_t + b_m0*m0 + b_eps*eps_guided  (UniP / DDIM)
  * Writes x_new -> x (in place), x_c -> last, shifts m0 -> m1 and m_t -> m0.
  */
-int mfb_cfg_sched_step(const float* eps, float* x, float* last, float* m0, float* m1, const float* coef, int Bimg,
-                       long long n, void* stream);
+int mfb_cfg_sched_step(const float* eps_uncond, const float* eps_cond, float* x, float* last, float* m0, float* m1,
+                       const float* coef, int Bimg, long long n, void* stream);
 
 #ifdef __cplusplus
 }

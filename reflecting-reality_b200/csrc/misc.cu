@@ -230,7 +230,7 @@ __global__ void linear_small_kernel(const float* __restrict__ x, int M, int K, c
 }
 
 // ---------------------------------------------------------------------------------------------- CFG + scheduler
-__global__ void cfg_sched_kernel(const float* __restrict__ eps, float* __restrict__ x, float* __restrict__ last,
+__global__ void cfg_sched_kernel(const float* __restrict__ eps_u, const float* __restrict__ eps_c, float* __restrict__ x, float* __restrict__ last,
                                  float* __restrict__ m0, float* __restrict__ m1, const float* __restrict__ coef,
                                  long long total /* Bimg*n */) {
     const float g = coef[0], c_x = coef[1], c_eps = coef[2];
@@ -238,7 +238,7 @@ __global__ void cfg_sched_kernel(const float* __restrict__ eps, float* __restric
     const float b_x = coef[8], b_mt = coef[9], b_m0 = coef[10], b_eps = coef[11];
     for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
          i += static_cast<long long>(gridDim.x) * blockDim.x) {
-        const float eu = eps[i], ec = eps[total + i];
+        const float eu = eps_u[i], ec = eps_c[i];
         const float e = eu + g * (ec - eu);                    // pipeline_brushnet.py:1311-1312
         const float xv = x[i];
         const float mt = c_x * xv + c_eps * e;                 // convert_model_output (x0 prediction)
@@ -358,11 +358,11 @@ extern "C" int mfb_linear_small(const float* x, int M, int K, const void* w, con
     return MFB_OK;
 }
 
-extern "C" int mfb_cfg_sched_step(const float* eps, float* x, float* last, float* m0, float* m1, const float* coef, int Bimg,
-                                  long long n, void* stream) {
-    MFB_REQUIRE(eps && x && last && m0 && m1 && coef, "null pointer");
+extern "C" int mfb_cfg_sched_step(const float* eps_uncond, const float* eps_cond, float* x, float* last, float* m0, float* m1,
+                                  const float* coef, int Bimg, long long n, void* stream) {
+    MFB_REQUIRE(eps_uncond && eps_cond && x && last && m0 && m1 && coef, "null pointer");
     const long long total = static_cast<long long>(Bimg) * n;
-    cfg_sched_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(eps, x, last, m0, m1, coef, total);
+    cfg_sched_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(eps_uncond, eps_cond, x, last, m0, m1, coef, total);
     MFB_CUDA_OK(cudaGetLastError());
     return MFB_OK;
 }

@@ -47,7 +47,7 @@ _SIGS = {
     "mfb_f32_to_bf16": (i32, [vp, i64, vp, vp]),
     "mfb_timestep_sinusoid": (i32, [vp, i32, i32, vp, vp]),
     "mfb_linear_small": (i32, [vp, i32, i32, vp, vp, i32, i32, i32, vp, vp]),
-    "mfb_cfg_sched_step": (i32, [vp, vp, vp, vp, vp, vp, i32, i64, vp]),
+    "mfb_cfg_sched_step": (i32, [vp, vp, vp, vp, vp, vp, vp, i32, i64, vp]),
 }
 EXPORTS = tuple(_SIGS)
 

@@ -37,7 +37,8 @@ SD15 = NetConfig()
 
 # A small member of the same family (channel counts stay multiples of 64 so the
 # tcgen05 path applies); used by fast parity tests.
-TINY = NetConfig(block_out_channels=(64, 128, 128, 128), heads=2, cross_attention_dim=64, sample_size=16)
+TINY = NetConfig(block_out_channels=(64, 128, 128, 128), heads=2, cross_attention_dim=64, sample_size=16,
+                  norm_num_groups=8)
 # An even smaller one for CPU-only oracle pins against the reference (any channel count).
 MICRO = NetConfig(block_out_channels=(32, 64, 64, 64), heads=2, cross_attention_dim=32, sample_size=8)
 

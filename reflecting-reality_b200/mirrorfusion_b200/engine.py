@@ -1,0 +1,393 @@
+"""Host-side sequencing of one denoise step on the libmfb200 kernels.
+
+`StepEngine` owns the two networks of the MirrorFusion hot path for a FIXED problem geometry
+(net batch B = 2 x images with CFG, latent H x W): every activation lives in a buffer allocated once, every
+GEMM/conv is a prepared plan (TMA descriptors encoded once), so a whole step is a static list of kernel
+launches that can be captured into one CUDA graph.  Layer order follows
+BrushNetModel.forward (S/models/brushnet.py:678-925) and UNet2DConditionModel.forward
+(S/models/unets/unet_2d_condition.py:1039-1348) with the tap sites of SURVEY.md §3.3.
+
+Fusions relative to the reference's op list:
+  * skip concat + GroupNorm + SiLU: one kernel reading both sources (no torch.cat tensor);
+  * ResnetBlock2D conv2 + 1x1 conv_shortcut (over both concat halves) + identity residual + BrushNet tap:
+    one implicit GEMM (shortcut = extra K-segments, residual/tap in the epilogue);
+  * conv1 + bias + time_emb_proj(silu(emb)) broadcast: epilogue row-bias, the 22 projections of a net are one GEMV;
+  * q/k/v projections: one GEMM (N = 3C); attention out-proj / FF-out / proj_out + residual (+tap): epilogue;
+  * GEGLU: epilogue of the FF-in GEMM; zero-conv x conditioning_scale: epilogue alpha;
+  * cross-attention K/V of the 77-token context: computed once per prompt, not per step.
+"""
+from __future__ import annotations
+
+from typing import Callable, Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import ops
+from .config import NetConfig, tap_channels, up_block_channels
+
+bf16 = torch.bfloat16
+f32 = torch.float32
+
+
+class _Net:
+    def __init__(self, cfg: NetConfig, sd: Dict[str, torch.Tensor], B: int, H: int, W: int, device, name: str):
+        self.cfg, self.B, self.H, self.W, self.dev, self.name = cfg, B, H, W, device, name
+        self.sd = {k: v.detach().to(device=device, dtype=f32) for k, v in sd.items()}
+        self.prog: List[Callable[[], None]] = []
+        self.keep: List[object] = []
+        self._scratch: Dict[Tuple, torch.Tensor] = {}
+        self.flops = 0.0
+        self.launches = 0
+        G = cfg.norm_num_groups
+        self.gn_ws = torch.zeros(B * G * 2, device=device, dtype=f32)
+        ops.lib()
+
+    # ---- memory
+    def buf(self, *shape, dtype=bf16) -> torch.Tensor:
+        t = torch.zeros(*shape, device=self.dev, dtype=dtype)
+        self.keep.append(t)
+        return t
+
+    def scratch(self, role: str, *shape) -> torch.Tensor:
+        key = (role,) + tuple(shape)
+        if key not in self._scratch:
+            self._scratch[key] = torch.zeros(*shape, device=self.dev, dtype=bf16)
+        return self._scratch[key]
+
+    def wf(self, name: str) -> torch.Tensor:
+        return self.sd[name].contiguous()
+
+    # ---- op emitters
+    def emit(self, fn: Callable[[], None], n_launch: int = 1):
+        self.prog.append(fn)
+        self.launches += n_launch
+
+    def emit_plan(self, plan: ops.ConvPlan):
+        self.keep.append(plan)
+        self.flops += plan.flops
+        self.emit(plan.run)
+
+    def groupnorm(self, x1, x2, prefix: str, out, HW: int, eps: float, silu: bool):
+        g, b = self.wf(prefix + ".weight"), self.wf(prefix + ".bias")
+        G = self.cfg.norm_num_groups
+        self.keep += [g, b]
+        self.emit(lambda: ops.groupnorm(x1, x2, g, b, out, self.gn_ws, B=self.B, HW=HW, groups=G, eps=eps, silu=silu), 2)
+
+    def layernorm(self, x, prefix: str, out):
+        g, b = self.wf(prefix + ".weight"), self.wf(prefix + ".bias")
+        self.keep += [g, b]
+        self.emit(lambda: ops.layernorm(x, g, b, out, 1e-5))
+
+    # ---- timestep path (embeddings.py:27-67,226-237; resnet.py:369-376), fp32
+    def build_time_path(self, resnet_prefixes: Sequence[str]):
+        c0, temb = self.cfg.block_out_channels[0], self.cfg.time_embed_dim
+        self.t_dev = torch.zeros(self.B, device=self.dev, dtype=f32)
+        sin = self.buf(self.B, c0, dtype=f32)
+        e1 = self.buf(self.B, temb, dtype=f32)
+        emb = self.buf(self.B, temb, dtype=f32)
+        w1, b1 = self.wf("time_embedding.linear_1.weight").to(bf16), self.wf("time_embedding.linear_1.bias")
+        w2, b2 = self.wf("time_embedding.linear_2.weight").to(bf16), self.wf("time_embedding.linear_2.bias")
+        wcat = torch.cat([self.sd[p + ".time_emb_proj.weight"] for p in resnet_prefixes], 0).to(bf16).contiguous()
+        bcat = torch.cat([self.sd[p + ".time_emb_proj.bias"] for p in resnet_prefixes], 0).contiguous()
+        self.rowbias = self.buf(self.B, wcat.shape[0], dtype=f32)
+        self.rowbias_off = {}
+        off = 0
+        for p in resnet_prefixes:
+            self.rowbias_off[p] = off
+            off += self.sd[p + ".time_emb_proj.weight"].shape[0]
+        self.keep += [w1, b1, w2, b2, wcat, bcat]
+        self.emit(lambda: ops.timestep_sinusoid(self.t_dev, sin))
+        self.emit(lambda: ops.linear_small(sin, w1, b1, e1, act_out=True))
+        self.emit(lambda: ops.linear_small(e1, w2, b2, emb))
+        self.emit(lambda: ops.linear_small(emb, wcat, bcat, self.rowbias, act_in=True))
+
+    # ---- ResnetBlock2D (resnet.py:329-405)
+    def resnet(self, p: str, xa, xb, HW_hw: Tuple[int, int], cout: int, tap=None):
+        h, w = HW_hw
+        HW = h * w
+        B = self.B
+        ca = xa.shape[-1]
+        cb = 0 if xb is None else xb.shape[-1]
+        cin = ca + cb
+        eps = self.cfg.norm_eps
+        n1 = self.scratch("n1", B, HW, cin)
+        self.groupnorm(xa, xb, p + ".norm1", n1, HW, eps, True)
+        h1 = self.scratch("h1", B, HW, cout)
+        w1 = ops.pack_conv_weight(self.sd[p + ".conv1.weight"])
+        off = self.rowbias_off[p]
+        rb = self.rowbias[:, off:]
+        self.emit_plan(ops.ConvPlan(n1, w1, h1, B=B, H=h, W=w, Cin=cin, Cout=cout, ksize=3, bias=self.wf(p + ".conv1.bias"),
+                                    rowbias=rb, rowbias_ld=self.rowbias.shape[1]))
+        n2 = self.scratch("n2", B, HW, cout)
+        self.groupnorm(h1, None, p + ".norm2", n2, HW, eps, True)
+        out = self.buf(B, HW, cout)
+        bias = self.sd[p + ".conv2.bias"].clone()
+        if p + ".conv_shortcut.weight" in self.sd:
+            ws = self.sd[p + ".conv_shortcut.weight"][:, :, 0, 0]
+            extras_w = [ws[:, :ca]] + ([ws[:, ca:]] if cb else [])
+            extras_x = [xa] + ([xb] if cb else [])
+            w2 = ops.pack_conv_weight(self.sd[p + ".conv2.weight"], extras=extras_w)
+            bias = bias + self.sd[p + ".conv_shortcut.bias"]
+            res1 = None
+        else:
+            assert cb == 0 and ca == cout
+            w2 = ops.pack_conv_weight(self.sd[p + ".conv2.weight"])
+            extras_x = []
+            res1 = xa
+        self.emit_plan(ops.ConvPlan(n2, w2, out, B=B, H=h, W=w, Cin=cout, Cout=cout, ksize=3, extras=extras_x,
+                                    bias=bias.contiguous(), res1=res1, res2=tap))
+        return out
+
+    def downsample(self, p: str, x, hw, tap=None):
+        h, w = hw
+        c = x.shape[-1]
+        out = self.buf(self.B, (h // 2) * (w // 2), c)
+        wp = ops.pack_conv_weight(self.sd[p + ".conv.weight"])
+        self.emit_plan(ops.ConvPlan(x, wp, out, B=self.B, H=h, W=w, Cin=c, Cout=c, ksize=3, stride=2,
+                                    bias=self.wf(p + ".conv.bias"), res2=tap))
+        return out
+
+    def upsample(self, p: str, x, hw, tap=None):
+        h, w = hw
+        c = x.shape[-1]
+        up = self.scratch("up", self.B, 4 * h * w, c)
+        self.emit(lambda: ops.upsample2x(x, up, B=self.B, H=h, W=w))
+        out = self.buf(self.B, 4 * h * w, c)
+        wp = ops.pack_conv_weight(self.sd[p + ".conv.weight"])
+        self.emit_plan(ops.ConvPlan(up, wp, out, B=self.B, H=2 * h, W=2 * w, Cin=c, Cout=c, ksize=3,
+                                    bias=self.wf(p + ".conv.bias"), res2=tap))
+        return out
+
+    def run(self):
+        for f in self.prog:
+            f()
+
+
+def _resnet_prefixes(cfg: NetConfig) -> List[str]:
+    out = []
+    n = len(cfg.block_out_channels)
+    for i in range(n):
+        out += [f"down_blocks.{i}.resnets.{j}" for j in range(cfg.layers_per_block)]
+    out += ["mid_block.resnets.0", "mid_block.resnets.1"]
+    for i in range(n):
+        out += [f"up_blocks.{i}.resnets.{j}" for j in range(cfg.layers_per_block + 1)]
+    return out
+
+
+class BrushNetEngine(_Net):
+    """BrushNetModel.forward on the kernels: conv_in_condition over [latent || cond], resnet-only down/mid/up,
+    28 zero-conv taps scaled by conditioning_scale (a device scalar, so the captured graph serves any scale)."""
+
+    def __init__(self, cfg, sd, B, H, W, device, tap_bufs: Optional[List[torch.Tensor]] = None):
+        super().__init__(cfg, sd, B, H, W, device, "brushnet")
+        boc = cfg.block_out_channels
+        n = len(boc)
+        self.sample_in = torch.zeros(B, cfg.in_channels, H, W, device=device, dtype=f32)
+        self.cond_in = torch.zeros(B, cfg.conditioning_channels, H, W, device=device, dtype=f32)
+        self.scale = torch.ones(1, device=device, dtype=f32)
+        self.build_time_path(_resnet_prefixes(cfg))
+        # conv_in_condition (brushnet.py:810-811)
+        wci = self.sd["conv_in_condition.weight"].permute(2, 3, 1, 0).contiguous()
+        bci = self.wf("conv_in_condition.bias")
+        x = self.buf(B, H * W, boc[0])
+        self.keep += [wci, bci]
+        self.emit(lambda: ops.conv_in(self.sample_in, self.cond_in, wci, bci, x))
+        hw = (H, W)
+        feats: List[Tuple[torch.Tensor, Tuple[int, int]]] = [(x, hw)]
+        for i in range(n):
+            for j in range(cfg.layers_per_block):
+                x = self.resnet(f"down_blocks.{i}.resnets.{j}", x, None, hw, boc[i])
+                feats.append((x, hw))
+            if i != n - 1:
+                x = self.downsample(f"down_blocks.{i}.downsamplers.0", x, hw)
+                hw = (hw[0] // 2, hw[1] // 2)
+                feats.append((x, hw))
+        down_feats = list(feats)
+        x = self.resnet("mid_block.resnets.0", x, None, hw, boc[-1])
+        x = self.resnet("mid_block.resnets.1", x, None, hw, boc[-1])
+        mid_feat = (x, hw)
+        up_feats = []
+        skips = list(feats)
+        for i, layers in enumerate(up_block_channels(cfg)):
+            for j, (_cin, _hid, _skip, cout) in enumerate(layers):
+                s, shw = skips.pop()
+                assert shw == hw
+                x = self.resnet(f"up_blocks.{i}.resnets.{j}", x, s, hw, cout)
+                up_feats.append((x, hw))
+            if i != n - 1:
+                x = self.upsample(f"up_blocks.{i}.upsamplers.0", x, hw)
+                hw = (hw[0] * 2, hw[1] * 2)
+                up_feats.append((x, hw))
+        # zero-convs (brushnet.py:831-834,851,890-893) with the conditioning scale (:904-906) as epilogue alpha
+        srcs = down_feats + [mid_feat] + up_feats
+        names = [f"brushnet_down_blocks.{k}" for k in range(len(down_feats))] + ["brushnet_mid_block"] + \
+                [f"brushnet_up_blocks.{k}" for k in range(len(up_feats))]
+        self.taps: List[torch.Tensor] = []
+        self.tap_hw: List[Tuple[int, int]] = []
+        for k, ((src, shw), nm) in enumerate(zip(srcs, names)):
+            c = src.shape[-1]
+            t = tap_bufs[k] if tap_bufs is not None else self.buf(B, shw[0] * shw[1], c)
+            wz = ops.pack_conv_weight(self.sd[nm + ".weight"])
+            self.emit_plan(ops.ConvPlan(src, wz, t, B=B, H=shw[0], W=shw[1], Cin=c, Cout=c, ksize=1,
+                                        bias=self.wf(nm + ".bias"), alpha=self.scale))
+            self.taps.append(t)
+            self.tap_hw.append(shw)
+        self.n_down = len(down_feats)
+
+
+class UNetEngine(_Net):
+    """UNet2DConditionModel.forward (SD1.5 family) with the BrushNet taps consumed in the producing epilogues."""
+
+    def __init__(self, cfg, sd, B, H, W, device, ctx_len: int = 77):
+        super().__init__(cfg, sd, B, H, W, device, "unet")
+        boc = cfg.block_out_channels
+        n = len(boc)
+        self.ctx_len = ctx_len
+        self.ctx_pad = (ctx_len + 7) // 8 * 8
+        self.sample_in = torch.zeros(B, cfg.in_channels, H, W, device=device, dtype=f32)
+        self.ehs_in = torch.zeros(B, ctx_len, cfg.cross_attention_dim, device=device, dtype=f32)
+        self.ehs_bf = torch.zeros(B * ctx_len, cfg.cross_attention_dim, device=device, dtype=bf16)
+        self.out = torch.zeros(B, cfg.out_channels, H, W, device=device, dtype=f32)
+        self.ctx_prog: List[Callable[[], None]] = []
+        # tap input buffers (zero == "no taps"); shapes in pop order
+        dch, mch, uch = tap_channels(cfg)
+        self.tap_hw: List[Tuple[int, int]] = []
+        hw = (H, W)
+        self.tap_hw.append(hw)
+        for i in range(n):
+            self.tap_hw += [hw] * cfg.layers_per_block
+            if i != n - 1:
+                hw = (hw[0] // 2, hw[1] // 2)
+                self.tap_hw.append(hw)
+        self.tap_hw.append(hw)
+        for i in range(n):
+            self.tap_hw += [hw] * (cfg.layers_per_block + 1)
+            if i != n - 1:
+                hw = (hw[0] * 2, hw[1] * 2)
+                self.tap_hw.append(hw)
+        chans = dch + [mch] + uch
+        self.taps = [self.buf(B, h_ * w_, c) for (h_, w_), c in zip(self.tap_hw, chans)]
+        self.n_down = len(dch)
+        tap_it = iter(self.taps)
+
+        self.build_time_path(_resnet_prefixes(cfg))
+        wci = self.sd["conv_in.weight"].permute(2, 3, 1, 0).contiguous()
+        bci = self.wf("conv_in.bias")
+        self.keep += [wci, bci]
+        hw = (H, W)
+        pre = self.buf(B, H * W, boc[0])      # first skip keeps the PRE-tap conv_in output (unet_2d_condition.py:1215-1218)
+        x = self.buf(B, H * W, boc[0])
+        tap0 = next(tap_it)
+        self.emit(lambda: ops.conv_in(self.sample_in, None, wci, bci, pre, tap0, x))
+        skips = [(pre, hw)]
+        for i in range(n):
+            for j in range(cfg.layers_per_block):
+                tap = next(tap_it)
+                if cfg.down_has_attn[i]:
+                    x = self.resnet(f"down_blocks.{i}.resnets.{j}", x, None, hw, boc[i])
+                    x = self.transformer(f"down_blocks.{i}.attentions.{j}", x, hw, tap)
+                else:
+                    x = self.resnet(f"down_blocks.{i}.resnets.{j}", x, None, hw, boc[i], tap=tap)
+                skips.append((x, hw))
+            if i != n - 1:
+                x = self.downsample(f"down_blocks.{i}.downsamplers.0", x, hw, tap=next(tap_it))
+                hw = (hw[0] // 2, hw[1] // 2)
+                skips.append((x, hw))
+        # mid (UNetMidBlock2DCrossAttn unet_2d_blocks.py:850-899) + mid tap (unet_2d_condition.py:1288-1289)
+        x = self.resnet("mid_block.resnets.0", x, None, hw, boc[-1])
+        x = self.transformer("mid_block.attentions.0", x, hw, None)
+        x = self.resnet("mid_block.resnets.1", x, None, hw, boc[-1], tap=next(tap_it))
+        for i, layers in enumerate(up_block_channels(cfg)):
+            for j, (_cin, _hid, _skip, cout) in enumerate(layers):
+                s, shw = skips.pop()
+                assert shw == hw
+                tap = next(tap_it)
+                if cfg.up_has_attn[i]:
+                    x = self.resnet(f"up_blocks.{i}.resnets.{j}", x, s, hw, cout)
+                    x = self.transformer(f"up_blocks.{i}.attentions.{j}", x, hw, tap)
+                else:
+                    x = self.resnet(f"up_blocks.{i}.resnets.{j}", x, s, hw, cout, tap=tap)
+            if i != n - 1:
+                x = self.upsample(f"up_blocks.{i}.upsamplers.0", x, hw, tap=next(tap_it))
+                hw = (hw[0] * 2, hw[1] * 2)
+        # conv_norm_out -> SiLU -> conv_out (unet_2d_condition.py:1336-1339)
+        nout = self.scratch("n1", B, H * W, boc[0])
+        self.groupnorm(x, None, "conv_norm_out", nout, H * W, cfg.norm_eps, True)
+        wco = self.sd["conv_out.weight"].permute(0, 2, 3, 1).contiguous()
+        bco = self.wf("conv_out.bias")
+        self.keep += [wco, bco]
+        self.emit(lambda: ops.conv_out(nout, wco, bco, self.out, B=B, H=H, W=W))
+
+    # Transformer2DModel + BasicTransformerBlock (transformer_2d.py:334-430, attention.py:291-412)
+    def transformer(self, p: str, x, hw, tap):
+        B, cfg = self.B, self.cfg
+        h, w = hw
+        T = h * w
+        M = B * T
+        C = x.shape[-1]
+        heads = cfg.heads
+        d = C // heads
+        t = p + ".transformer_blocks.0"
+        g = self.scratch("tg", B, T, C)
+        self.groupnorm(x, None, p + ".norm", g, T, 1e-6, False)
+        h0 = self.scratch("th0", M, C)
+        self.emit_plan(ops.linear_plan(g.view(M, C), ops.pack_conv_weight(self.sd[p + ".proj_in.weight"]), h0,
+                                       bias=self.wf(p + ".proj_in.bias")))
+        # --- self attention
+        nrm = self.scratch("tn", M, C)
+        self.layernorm(h0, t + ".norm1", nrm)
+        qkv = self.scratch("tqkv", M, 3 * C)
+        wqkv = torch.cat([self.sd[t + ".attn1.to_q.weight"], self.sd[t + ".attn1.to_k.weight"],
+                          self.sd[t + ".attn1.to_v.weight"]], 0).to(bf16).contiguous()
+        self.emit_plan(ops.linear_plan(nrm, wqkv, qkv))
+        Tp = (T + 7) // 8 * 8
+        vt = self.scratch("tvt", B, C, Tp)
+        self.emit(lambda: ops.transpose_tokens(qkv, vt, ld=3 * C, col0=2 * C, Cc=C, B=B, T=T, ldt=Tp))
+        att = self.scratch("tatt", M, C)
+        kview = qkv.view(-1)[C:]
+        self.emit(lambda: ops.attention(qkv, kview, vt, att, B=B, heads=heads, head_dim=d, Tq=T, Tk=T, ldq=3 * C,
+                                        ldk=3 * C, ldvt=Tp, ldo=C))
+        self.flops += 4.0 * B * T * T * C
+        h1 = self.scratch("th1", M, C)
+        self.emit_plan(ops.linear_plan(att, self.sd[t + ".attn1.to_out.0.weight"].to(bf16).contiguous(), h1,
+                                       bias=self.wf(t + ".attn1.to_out.0.bias"), res1=h0))
+        # --- cross attention (K/V of the context are prepared once per prompt: ctx_prog)
+        Lc, Lp = self.ctx_len, self.ctx_pad
+        k2 = self.buf(B * Lc, C)
+        v2 = self.scratch("tv2", B * Lc, C)
+        v2t = self.buf(B, C, Lp)
+        pk = ops.linear_plan(self.ehs_bf, self.sd[t + ".attn2.to_k.weight"].to(bf16).contiguous(), k2)
+        pv = ops.linear_plan(self.ehs_bf, self.sd[t + ".attn2.to_v.weight"].to(bf16).contiguous(), v2)
+        self.keep += [pk, pv]
+        self.ctx_prog += [pk.run, pv.run,
+                          lambda: ops.transpose_tokens(v2, v2t, ld=C, col0=0, Cc=C, B=B, T=Lc, ldt=Lp)]
+        self.layernorm(h1, t + ".norm2", nrm)
+        q2 = self.scratch("tq2", M, C)
+        self.emit_plan(ops.linear_plan(nrm, self.sd[t + ".attn2.to_q.weight"].to(bf16).contiguous(), q2))
+        self.emit(lambda: ops.attention(q2, k2, v2t, att, B=B, heads=heads, head_dim=d, Tq=T, Tk=Lc, ldq=C, ldk=C,
+                                        ldvt=Lp, ldo=C))
+        self.flops += 4.0 * B * T * Lc * C
+        h2 = self.scratch("th2", M, C)
+        self.emit_plan(ops.linear_plan(att, self.sd[t + ".attn2.to_out.0.weight"].to(bf16).contiguous(), h2,
+                                       bias=self.wf(t + ".attn2.to_out.0.bias"), res1=h1))
+        # --- GEGLU feed-forward
+        self.layernorm(h2, t + ".norm3", nrm)
+        wg, bg = ops.pack_geglu(self.sd[t + ".ff.net.0.proj.weight"], self.sd[t + ".ff.net.0.proj.bias"])
+        gg = self.scratch("tgg", M, 4 * C)
+        self.emit_plan(ops.linear_plan(nrm, wg, gg, bias=bg, geglu=True))
+        h3 = self.scratch("th3", M, C)
+        self.emit_plan(ops.linear_plan(gg, self.sd[t + ".ff.net.2.weight"].to(bf16).contiguous(), h3,
+                                       bias=self.wf(t + ".ff.net.2.bias"), res1=h2))
+        # --- proj_out + transformer residual (+ BrushNet tap, added after the attention: unet_2d_blocks.py:1374-1389)
+        out = self.buf(B, T, C)
+        self.emit_plan(ops.linear_plan(h3, ops.pack_conv_weight(self.sd[p + ".proj_out.weight"]), out.view(M, C),
+                                       bias=self.wf(p + ".proj_out.bias"), res1=x.view(M, C),
+                                       res2=None if tap is None else tap.view(M, C)))
+        return out
+
+    def set_context(self, ehs: torch.Tensor):
+        """encoder_hidden_states [B, 77, ctx] -> cached cross-attention K / V^T of all 16 layers."""
+        self.ehs_in.copy_(ehs.to(device=self.dev, dtype=f32))
+        ops.f32_to_bf16(self.ehs_in, self.ehs_bf)
+        for f in self.ctx_prog:
+            f()

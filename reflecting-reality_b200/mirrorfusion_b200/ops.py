@@ -75,7 +75,11 @@ class ConvPlan:
             d.extra_C[i] = e.shape[-1]
         for name, t in (("bias", bias), ("rowbias", rowbias), ("alpha", alpha)):
             if t is not None:
-                _req(t, torch.float32, name)
+                if name == "rowbias":   # may be a column slice of a wider [B, ld] table
+                    if t.dtype != torch.float32 or not t.is_cuda or t.stride(-1) != 1:
+                        raise ValueError("rowbias: expected CUDA float32 with unit inner stride")
+                else:
+                    _req(t, torch.float32, name)
                 setattr(d, name, t.data_ptr())
         d.rowbias_ld = rowbias_ld
         for name, t in (("res1", res1), ("res2", res2)):
@@ -177,7 +181,8 @@ def linear_small(x, w, b, y, act_in=False, act_out=False):
     check(lib().mfb_linear_small(_ptr(x), M, K, _ptr(w), _ptr(b), w.shape[0], int(act_in), int(act_out), _ptr(y), _stream()))
 
 
-def cfg_sched_step(eps, x, last, m0, m1, coef):
+def cfg_sched_step(eps_u, eps_c, x, last, m0, m1, coef):
     Bimg = x.shape[0]
     n = x.numel() // Bimg
-    check(lib().mfb_cfg_sched_step(_ptr(eps), _ptr(x), _ptr(last), _ptr(m0), _ptr(m1), _ptr(coef), Bimg, n, _stream()))
+    check(lib().mfb_cfg_sched_step(_ptr(eps_u), _ptr(eps_c), _ptr(x), _ptr(last), _ptr(m0), _ptr(m1), _ptr(coef), Bimg, n,
+                                   _stream()))

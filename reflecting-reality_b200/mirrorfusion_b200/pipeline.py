@@ -1,0 +1,337 @@
+"""Drop-in surface for the hot path: the reference's call signatures over the B200 engines.
+
+  * `B200BrushNetModel.forward`      <- BrushNetModel.forward          (S/models/brushnet.py:678-692)
+  * `B200UNet2DConditionModel.forward` <- UNet2DConditionModel.forward (S/models/unets/unet_2d_condition.py:1039-1057)
+  * `MirrorFusionB200Pipeline.__call__` <- the denoise loop of StableDiffusionBrushNetPipeline.__call__
+                                         (S/pipelines/brushnet/pipeline_brushnet.py:848-880, 1219-1332)
+  * `StepEngine`: the fused form the pipeline actually runs: BrushNet + UNet + CFG + scheduler step as one
+    CUDA graph per geometry, taps handed over in HBM buffers shared between the two engines.
+
+Tensors cross this boundary in the reference's layout (NCHW, any float dtype); inside everything is NHWC bf16.
+VAE / CLIP / image preprocessing stay outside: the pipeline takes `prompt_embeds` and
+`conditioning_latents` (or a `vae_encode` callable) like the parity recipe of SURVEY.md Appendix A.
+"""
+from __future__ import annotations
+
+import inspect
+from types import SimpleNamespace
+from typing import Any, Callable, Dict, List, Optional, Tuple, Union
+
+import torch
+
+from . import ops
+from .config import NetConfig, SD15, tap_channels
+from .engine import BrushNetEngine, UNetEngine
+from .schedulers import B200DDIMScheduler, B200UniPCScheduler
+
+f32 = torch.float32
+
+
+def _as_timestep_vector(timestep, batch: int, device) -> torch.Tensor:
+    """Scalar / 0-dim / [B] timestep -> fp32 [B] on device (unet_2d_condition.py:1141-1152)."""
+    if not torch.is_tensor(timestep):
+        timestep = torch.tensor([float(timestep)], dtype=f32)
+    t = timestep.to(device=device, dtype=f32).reshape(-1)
+    if t.numel() == 1:
+        t = t.expand(batch)
+    if t.numel() != batch:
+        raise ValueError(f"timestep has {t.numel()} entries for a batch of {batch}")
+    return t.contiguous()
+
+
+class _GeomCache:
+    def __init__(self, factory):
+        self._factory = factory
+        self._engines: Dict[Tuple[int, int, int], Any] = {}
+
+    def get(self, B, H, W):
+        key = (B, H, W)
+        if key not in self._engines:
+            self._engines[key] = self._factory(B, H, W)
+        return self._engines[key]
+
+
+class B200BrushNetModel:
+    """BrushNetModel on sm_100a kernels.  `forward` keeps the reference signature and return convention:
+    `(down_block_res_samples: list[12], mid_block_res_sample, up_block_res_samples: list[15])`, fresh lists each call
+    (the UNet pops them), NCHW in the dtype of `sample`."""
+
+    def __init__(self, state_dict: Dict[str, torch.Tensor], cfg: NetConfig = SD15, device="cuda", dtype=torch.bfloat16):
+        self.cfg = cfg
+        self.device = torch.device(device)
+        self.dtype = dtype
+        self.config = SimpleNamespace(global_pool_conditions=False, in_channels=cfg.in_channels,
+                                      conditioning_channels=cfg.conditioning_channels,
+                                      block_out_channels=cfg.block_out_channels)
+        self._sd = state_dict
+        self._cache = _GeomCache(lambda B, H, W: BrushNetEngine(cfg, state_dict, B, H, W, self.device))
+
+    def engine(self, B, H, W) -> BrushNetEngine:
+        return self._cache.get(B, H, W)
+
+    def forward(self, sample, timestep, encoder_hidden_states=None, brushnet_cond=None, conditioning_scale: float = 1.0,
+                class_labels=None, timestep_cond=None, attention_mask=None, added_cond_kwargs=None,
+                cross_attention_kwargs=None, guess_mode: bool = False, return_dict: bool = True):
+        if brushnet_cond is None:
+            raise ValueError("brushnet_cond is required")
+        if guess_mode or class_labels is not None or timestep_cond is not None or added_cond_kwargs:
+            raise NotImplementedError("guess_mode / class / additional embeddings are not on the MirrorFusion path")
+        B, _, H, W = sample.shape
+        if brushnet_cond.shape[1] != self.cfg.conditioning_channels:
+            raise ValueError(f"brushnet_cond has {brushnet_cond.shape[1]} channels, expected {self.cfg.conditioning_channels}")
+        e = self.engine(B, H, W)
+        e.sample_in.copy_(sample)
+        e.cond_in.copy_(brushnet_cond)
+        e.t_dev.copy_(_as_timestep_vector(timestep, B, self.device))
+        e.scale.fill_(float(conditioning_scale))
+        e.run()
+        outs = []
+        for t, (h, w) in zip(e.taps, e.tap_hw):
+            o = torch.empty(B, t.shape[-1], h, w, device=self.device, dtype=f32)
+            ops.nhwc_to_nchw(t, o)
+            outs.append(o.to(sample.dtype))
+        down, mid, up = outs[: e.n_down], outs[e.n_down], outs[e.n_down + 1:]
+        if not return_dict:
+            return down, mid, up
+        return SimpleNamespace(down_block_res_samples=down, mid_block_res_sample=mid, up_block_res_samples=up)
+
+    __call__ = forward
+
+
+class B200UNet2DConditionModel:
+    """UNet2DConditionModel (SD1.5 family) on sm_100a kernels with the three BrushNet kwargs of the fork
+    (unet_2d_condition.py:1054-1056).  Tap lists are consumed with pop(0) like the reference (:1218,1228,1306)."""
+
+    def __init__(self, state_dict: Dict[str, torch.Tensor], cfg: NetConfig = SD15, device="cuda", dtype=torch.bfloat16):
+        self.cfg = cfg
+        self.device = torch.device(device)
+        self.dtype = dtype
+        self.config = SimpleNamespace(in_channels=cfg.in_channels, time_cond_proj_dim=None, sample_size=cfg.sample_size,
+                                      block_out_channels=cfg.block_out_channels)
+        self._sd = state_dict
+        self._cache = _GeomCache(lambda B, H, W: UNetEngine(cfg, state_dict, B, H, W, self.device))
+        self._ctx_key = None
+
+    def engine(self, B, H, W) -> UNetEngine:
+        return self._cache.get(B, H, W)
+
+    def forward(self, sample, timestep, encoder_hidden_states, class_labels=None, timestep_cond=None, attention_mask=None,
+                cross_attention_kwargs=None, added_cond_kwargs=None, down_block_additional_residuals=None,
+                mid_block_additional_residual=None, down_intrablock_additional_residuals=None,
+                encoder_attention_mask=None, return_dict: bool = True, down_block_add_samples=None,
+                mid_block_add_sample=None, up_block_add_samples=None):
+        if any(a is not None for a in (class_labels, timestep_cond, attention_mask, added_cond_kwargs,
+                                       down_block_additional_residuals, mid_block_additional_residual,
+                                       down_intrablock_additional_residuals, encoder_attention_mask)):
+            raise NotImplementedError("ControlNet / adapter / mask arguments are not on the MirrorFusion path")
+        B, _, H, W = sample.shape
+        e = self.engine(B, H, W)
+        key = (encoder_hidden_states.data_ptr(), encoder_hidden_states._version, tuple(encoder_hidden_states.shape), id(e))
+        if key != self._ctx_key:
+            if encoder_hidden_states.shape[1] != e.ctx_len:
+                raise ValueError(f"encoder_hidden_states must have {e.ctx_len} tokens")
+            e.set_context(encoder_hidden_states)
+            self._ctx_key = key
+        is_brushnet = down_block_add_samples is not None and mid_block_add_sample is not None \
+            and up_block_add_samples is not None                                          # :1202
+        if is_brushnet:
+            n_up = len(e.taps) - e.n_down - 1
+            if len(down_block_add_samples) != e.n_down or len(up_block_add_samples) != n_up:
+                raise ValueError("wrong number of BrushNet residuals")
+            srcs = [down_block_add_samples.pop(0) for _ in range(e.n_down)] + [mid_block_add_sample] + \
+                   [up_block_add_samples.pop(0) for _ in range(n_up)]
+            for dst, s in zip(e.taps, srcs):
+                ops.nchw_to_nhwc(s.to(f32).contiguous(), dst)
+        else:
+            for dst in e.taps:
+                dst.zero_()
+        e.sample_in.copy_(sample)
+        e.t_dev.copy_(_as_timestep_vector(timestep, B, self.device))
+        e.run()
+        out = e.out.to(sample.dtype).clone()
+        if not return_dict:
+            return (out,)
+        return SimpleNamespace(sample=out)
+
+    __call__ = forward
+
+
+class StepEngine:
+    """One fused denoise step for `images` images (net batch 2*images, [uncond, cond] halves):
+    latents -> BrushNet -> UNet (+taps) -> CFG -> scheduler, all state resident on the device."""
+
+    def __init__(self, cfg: NetConfig, unet_sd, brushnet_sd, images: int, H: int, W: int, device="cuda",
+                 use_graph: bool = True):
+        self.cfg, self.images, self.H, self.W = cfg, images, H, W
+        self.dev = torch.device(device)
+        B = 2 * images
+        self.unet = UNetEngine(cfg, unet_sd, B, H, W, self.dev)
+        self.bn = BrushNetEngine(cfg, brushnet_sd, B, H, W, self.dev, tap_bufs=self.unet.taps)
+        z = lambda: torch.zeros(images, cfg.in_channels, H, W, device=self.dev, dtype=f32)
+        self.x, self.last, self.m0, self.m1 = z(), z(), z(), z()
+        self.coef = torch.zeros(12, device=self.dev, dtype=f32)
+        self.use_graph = use_graph
+        self.graph: Optional[torch.cuda.CUDAGraph] = None
+        self.launches_per_step = self.unet.launches + self.bn.launches + 1
+        self.flops_per_step = self.unet.flops + self.bn.flops
+
+    def set_conditioning(self, prompt_embeds: torch.Tensor, conditioning_latents: torch.Tensor):
+        self.unet.set_context(prompt_embeds)
+        self.bn.cond_in.copy_(conditioning_latents)
+
+    def _enqueue(self):
+        n = self.images
+        for e in (self.bn, self.unet):                    # latent_model_input = cat([latents] * 2) (:1256)
+            e.sample_in[:n].copy_(self.x)
+            e.sample_in[n:].copy_(self.x)
+        self.bn.run()
+        self.unet.run()
+        eps = self.unet.out
+        ops.cfg_sched_step(eps[:n], eps[n:], self.x, self.last, self.m0, self.m1, self.coef)
+
+    def step(self, t: float, coef_row: torch.Tensor, scale: float = 1.0):
+        self.bn.t_dev.fill_(float(t))
+        self.unet.t_dev.fill_(float(t))
+        self.bn.scale.fill_(float(scale))
+        self.coef.copy_(coef_row, non_blocking=True)
+        if not self.use_graph:
+            self._enqueue()
+            return
+        if self.graph is None:
+            self._capture()
+        self.graph.replay()
+
+    def _capture(self):
+        # one eager pass first (lazy cudaFuncSetAttribute calls, allocator warm-up), on saved state
+        saved = [t.clone() for t in (self.x, self.last, self.m0, self.m1)]
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            self._enqueue()
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self._enqueue()
+        for dst, src in zip((self.x, self.last, self.m0, self.m1), saved):
+            dst.copy_(src)
+        self.graph = g
+
+    def denoise(self, latents: torch.Tensor, scheduler, num_inference_steps: int, guidance_scale: float = 7.5,
+                conditioning_scales: Optional[List[float]] = None,
+                callback: Optional[Callable[[int, int, torch.Tensor], Optional[torch.Tensor]]] = None) -> torch.Tensor:
+        scheduler.set_timesteps(num_inference_steps, device="cpu")
+        table = scheduler.coefficient_table(guidance_scale).to(self.dev)
+        self.x.copy_(latents.to(device=self.dev, dtype=f32) * scheduler.init_noise_sigma)
+        for t_ in (self.last, self.m0, self.m1):
+            t_.zero_()
+        ts = scheduler.timesteps.tolist()
+        for i, t in enumerate(ts):
+            sc = 1.0 if conditioning_scales is None else conditioning_scales[i]
+            self.step(float(t), table[i], sc)
+            if callback is not None:
+                new = callback(i, int(t), self.x)
+                if new is not None:
+                    self.x.copy_(new)
+        return self.x
+
+
+class MirrorFusionB200Pipeline:
+    """The denoise loop of StableDiffusionBrushNetPipeline behind its `__call__` argument names."""
+
+    def __init__(self, unet_state_dict, brushnet_state_dict, scheduler=None, cfg: NetConfig = SD15, device="cuda",
+                 depth_conditioning_mode: str = "concat", normals_conditioning_mode: Optional[str] = None,
+                 vae_encode: Optional[Callable[[torch.Tensor], torch.Tensor]] = None,
+                 vae_decode: Optional[Callable[[torch.Tensor], torch.Tensor]] = None, vae_scale_factor: int = 8):
+        if depth_conditioning_mode != "concat" or normals_conditioning_mode is not None:
+            raise NotImplementedError("only depth_conditioning_mode='concat' (the released MirrorFusion checkpoint) is implemented")
+        self.cfg, self.device = cfg, torch.device(device)
+        self.unet_sd, self.brushnet_sd = unet_state_dict, brushnet_state_dict
+        self.scheduler = scheduler or B200UniPCScheduler()
+        self.vae_encode, self.vae_decode, self.vae_scale_factor = vae_encode, vae_decode, vae_scale_factor
+        self._engines: Dict[Tuple[int, int, int], StepEngine] = {}
+
+    def engine(self, images, H, W) -> StepEngine:
+        key = (images, H, W)
+        if key not in self._engines:
+            self._engines[key] = StepEngine(self.cfg, self.unet_sd, self.brushnet_sd, images, H, W, self.device)
+        return self._engines[key]
+
+    def check_inputs(self, prompt_embeds, negative_prompt_embeds, brushnet_conditioning_scale, control_guidance_start,
+                     control_guidance_end, callback_on_step_end_tensor_inputs):
+        # the subset of pipeline_brushnet.py:573-693 that applies without tokenizer / PIL inputs
+        if prompt_embeds is None:
+            raise ValueError("Provide `prompt_embeds` (the text encoder stays outside this package).")
+        if negative_prompt_embeds is not None and prompt_embeds.shape != negative_prompt_embeds.shape:
+            raise ValueError("`prompt_embeds` and `negative_prompt_embeds` must have the same shape when passed directly, but"
+                             f" got: `prompt_embeds` {prompt_embeds.shape} != `negative_prompt_embeds` {negative_prompt_embeds.shape}.")
+        if not isinstance(brushnet_conditioning_scale, float):
+            raise TypeError("For single brushnet: `brushnet_conditioning_scale` must be type `float`.")   # :649-650
+        if control_guidance_start >= control_guidance_end:
+            raise ValueError(f"control guidance start: {control_guidance_start} cannot be larger or equal to control guidance end: {control_guidance_end}.")
+        if control_guidance_start < 0.0:
+            raise ValueError(f"control guidance start: {control_guidance_start} can't be smaller than 0.")
+        if control_guidance_end > 1.0:
+            raise ValueError(f"control guidance end: {control_guidance_end} can't be larger than 1.0.")
+        if callback_on_step_end_tensor_inputs is not None and any(k != "latents" for k in callback_on_step_end_tensor_inputs):
+            raise ValueError("`callback_on_step_end_tensor_inputs` has to be in ['latents']")
+
+    @torch.no_grad()
+    def __call__(self, prompt=None, image=None, mask=None, depth=None, normals=None, height=None, width=None,
+                 num_inference_steps: int = 50, timesteps=None, guidance_scale: float = 7.5, negative_prompt=None,
+                 num_images_per_prompt: int = 1, eta: float = 0.0, generator=None, latents=None, prompt_embeds=None,
+                 negative_prompt_embeds=None, output_type: str = "latent", return_dict: bool = True,
+                 cross_attention_kwargs=None, brushnet_conditioning_scale: float = 1.0, guess_mode: bool = False,
+                 control_guidance_start: float = 0.0, control_guidance_end: float = 1.0, clip_skip=None,
+                 callback_on_step_end=None, callback_on_step_end_tensor_inputs=("latents",),
+                 conditioning_latents: Optional[torch.Tensor] = None):
+        if prompt is not None or negative_prompt is not None:
+            raise NotImplementedError("tokenizer / CLIP are outside the hot path: pass prompt_embeds / negative_prompt_embeds")
+        if timesteps is not None or eta != 0.0 or guess_mode or num_images_per_prompt != 1:
+            raise NotImplementedError("custom timesteps / eta / guess_mode / num_images_per_prompt are not implemented")
+        self.check_inputs(prompt_embeds, negative_prompt_embeds, brushnet_conditioning_scale, control_guidance_start,
+                          control_guidance_end, callback_on_step_end_tensor_inputs)
+        do_cfg = guidance_scale > 1.0                                                      # :835-836
+        if not do_cfg:
+            raise NotImplementedError("the fused step is built for classifier-free guidance (guidance_scale > 1)")
+        if negative_prompt_embeds is None:
+            negative_prompt_embeds = torch.zeros_like(prompt_embeds)
+        b = prompt_embeds.shape[0]
+        ehs = torch.cat([negative_prompt_embeds, prompt_embeds])                           # uncond first (:1102-1103)
+        if conditioning_latents is None:
+            conditioning_latents = self._prepare_conditioning(image, mask, depth, b)
+        if conditioning_latents.shape[0] == b:
+            conditioning_latents = torch.cat([conditioning_latents] * 2)                   # CFG duplicate (:771-772)
+        H, W = conditioning_latents.shape[-2:]
+        if latents is None:
+            latents = torch.randn(b, self.cfg.in_channels, H, W, generator=generator,
+                                  device=generator.device if generator is not None else "cpu")   # randn_tensor semantics
+        eng = self.engine(b, H, W)
+        eng.set_conditioning(ehs, conditioning_latents)
+        n = num_inference_steps
+        keep = [1.0 - float(i / n < control_guidance_start or (i + 1) / n > control_guidance_end) for i in range(n)]   # :1236-1242
+        scales = [brushnet_conditioning_scale * k for k in keep]                            # :1269-1275
+        cb = None
+        if callback_on_step_end is not None:
+            def cb(i, t, x):
+                out = callback_on_step_end(self, i, t, {"latents": x})
+                return None if out is None else out.pop("latents", None)
+        x = eng.denoise(latents, self.scheduler, n, guidance_scale, scales, cb)
+        result = x.clone()
+        if output_type != "latent":
+            if self.vae_decode is None:
+                raise ValueError("output_type != 'latent' needs a vae_decode callable")
+            result = self.vae_decode(result / 0.18215)                                      # :1342
+        if not return_dict:
+            return (result, None)
+        return SimpleNamespace(images=result, nsfw_content_detected=None)
+
+    def _prepare_conditioning(self, image, mask, depth, b):
+        """pipeline_brushnet.py:1188-1202 given already preprocessed tensors: image [-1,1] masked RGB, mask 1-ch {0,1},
+        depth [b,1,h,w] in [-1,1]; needs `vae_encode` returning the latent sample."""
+        if self.vae_encode is None or image is None or mask is None or depth is None:
+            raise ValueError("pass `conditioning_latents`, or `image`/`mask`/`depth` together with a `vae_encode` callable")
+        lat = self.vae_encode(image) * 0.18215
+        m = torch.nn.functional.interpolate(mask, size=lat.shape[-2:])
+        d = torch.nn.functional.interpolate(depth, size=lat.shape[-2:])
+        return torch.cat([lat, m.to(lat), d.to(lat)], 1)

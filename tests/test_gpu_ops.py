@@ -267,5 +267,5 @@ def test_cfg_sched_kernel(ops):
     xc = 0.9 * last + 0.2 * m0 - 0.05 * m1 + 0.3 * mt
     xn = 0.8 * xc + 0.15 * mt - 0.07 * m0
     m0_old = m0.clone()
-    ops.cfg_sched_step(eps, x, last, m0, m1, coef)
+    ops.cfg_sched_step(eps[:Bi], eps[Bi:], x, last, m0, m1, coef)
     assert rel(x, xn) < 1e-6 and rel(last, xc) < 1e-6 and rel(m0, mt) < 1e-6 and torch.equal(m1, m0_old)
