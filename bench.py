@@ -1,0 +1,326 @@
+#!/usr/bin/env python
+"""bench.py — MirrorFusion denoising hot path on B200: images/s at 512x512, 50 UniPC steps, CFG 7.5.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--images 8] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+A "step" is one pass of the hot path over one batch: BrushNet + UNet (with the 28 taps) on net batch 2*images,
+CFG combine and the UniPC update, for `images` 512x512 images per GPU (BASELINE.json configs[1]: batch 8).
+    value = N * images / (50 * seconds_per_step)      [images/s, whole job, inputs resident in HBM]
+    e2e   = the same through the public API with host buffers: every timed step copies the step's latents from
+            pinned host memory to the device and reads the updated latents back.
+`--impl reference` times the reference algorithm on the host CPU cores (the fp32 oracle port of the reference's
+BrushNetModel/UNet2DConditionModel/UniPC step — the reference itself is not present on the GPU box).
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "reflecting-reality_b200")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import torch  # noqa: E402
+
+STEPS_PER_IMAGE = 50
+METRIC = "images_per_s_512x512_50_unipc_steps_cfg7.5"
+FLOP_PER_SAMPLE_STEP = 1.2446e12          # BrushNet 4.413e11 + UNet 8.033e11 at 64x64 latents
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return {"bf16_burst": d.get("bf16_tflops"), "bf16_sustained": d.get("bf16_tflops_sustained"),
+                "hbm_gbs": d.get("hbm_gbs"), "source": "measured (MEASURED_PEAKS.json)"}
+    return {"bf16_burst": 1590.0, "bf16_sustained": 1400.0, "hbm_gbs": 6650.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out = ""
+        sm, mx, reasons, pw = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        busy = [s for s, w in zip(sm, pw) if w > 0.5 * max(pw)] or sm
+        return {"sm_mhz": statistics.median(busy), "sm_max_mhz": max(mx), "power_w_max": max(pw), "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+# ----------------------------------------------------------------------------------------------------- reference arm
+def cpu_reference_run(steps: int, warmup: int, images: int = 1):
+    """The reference's algorithm on the host cores: fp32 oracle port, SD1.5 config, `images` image(s) + CFG per step."""
+    from oracle import mf_oracle as O           # the one place bench.py executes oracle/: as the CPU baseline
+    from mirrorfusion_b200.config import SD15
+    from mirrorfusion_b200.synth import make_inputs, make_state_dict
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg = SD15
+    usd, bsd = make_state_dict(cfg, "unet"), make_state_dict(cfg, "brushnet")
+    inp = make_inputs(cfg, images)
+    sched = O.UniPCOracle()
+    sched.set_timesteps(STEPS_PER_IMAGE)
+    lat = inp["latents"]
+    ts = sched.timesteps
+    times = []
+    with torch.no_grad():
+        for i in range(warmup + steps):
+            t = ts[i % len(ts)]
+            if i % len(ts) == 0 and i > 0:
+                sched.set_timesteps(STEPS_PER_IMAGE)
+            t0 = time.perf_counter()
+            eps, _ = O.noise_pred_step(usd, bsd, cfg, torch.cat([lat] * 2), t, inp["prompt_embeds"],
+                                       inp["conditioning_latents"], 1.0)
+            lat = sched.step(O.cfg_combine(eps, 7.5), t, lat)
+            dt = time.perf_counter() - t0
+            if i >= warmup:
+                times.append(dt)
+    sec = sum(times) / len(times)
+    return {"sec_per_step": sec, "images_per_s": images / (STEPS_PER_IMAGE * sec), "cores": cores,
+            "sample": f"{images} image(s) (net batch {2 * images}) x {len(times)} denoise step(s), SD1.5 config, 64x64 latents, fp32, "
+                      f"torch CPU with {cores} threads"}
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    r = cpu_reference_run(args.steps, min(args.warmup, 1), images=1)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": r["images_per_s"], "unit": "images/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": r["sec_per_step"] * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "MirrorFusion 512x512, 50 UniPC steps, CFG 7.5 (reference algorithm on host CPU; bounded sample: "
+                               "1 image per step instead of 8)", "images_per_step": 1, "latent": "64x64", "steps_per_image": 50},
+        "cpu_baseline": {"value": r["images_per_s"], "unit": "images/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]},
+        "e2e": {"value": r["images_per_s"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------------- our arm
+def run_ours(args, rank, world, local_rank):
+    import torch.distributed as dist
+    from mirrorfusion_b200.config import SD15
+    from mirrorfusion_b200.pipeline import StepEngine
+    from mirrorfusion_b200.schedulers import B200UniPCScheduler
+    from mirrorfusion_b200.synth import make_inputs, make_state_dict
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; mirrorfusion_b200 has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    cfg = SD15
+    images = args.images
+    H = W = args.latent
+    usd, bsd = make_state_dict(cfg, "unet"), make_state_dict(cfg, "brushnet")
+    # image indices are global: rank r owns images [r*images, (r+1)*images) -> any GPU count reproduces the same per-image inputs
+    inp_all = make_inputs(cfg, images * world, height=H, width=W)
+    sl = slice(rank * images, (rank + 1) * images)
+    n_all = images * world
+    lat0 = inp_all["latents"][sl]
+    cond = torch.cat([inp_all["conditioning_latents"][:n_all][sl], inp_all["conditioning_latents"][n_all:][sl]])
+    ehs = torch.cat([inp_all["prompt_embeds"][:n_all][sl], inp_all["prompt_embeds"][n_all:][sl]])
+
+    eng = StepEngine(cfg, usd, bsd, images, H, W, dev, use_graph=not args.no_graph)
+    del usd, bsd
+    eng.set_conditioning(ehs.to(dev), cond.to(dev))
+    sched = B200UniPCScheduler()
+    sched.set_timesteps(STEPS_PER_IMAGE)
+    table = sched.coefficient_table(7.5).to(dev)
+    ts = sched.timesteps.tolist()
+    eng.x.copy_(lat0.to(dev))
+
+    def one_step(i):
+        j = i % STEPS_PER_IMAGE
+        if j == 0:                        # new image batch: reset the multistep state
+            eng.x.copy_(lat0_dev)
+            eng.last.zero_(); eng.m0.zero_(); eng.m1.zero_()
+        eng.step(float(ts[j]), table[j], 1.0)
+
+    lat0_dev = lat0.to(dev)
+    stream = torch.cuda.current_stream()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- device-resident timing
+    for i in range(args.warmup):
+        one_step(i)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for i in range(args.steps):
+        one_step(args.warmup + i)
+    if world > 1:                         # the path's only collective: the final gather of the latents
+        gathered = torch.empty(world * images, cfg.in_channels, H, W, device=dev, dtype=torch.float32)
+        dist.all_gather_into_tensor(gathered, eng.x)
+    e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    if world > 1:
+        tmax = torch.tensor([ms], device=dev)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        ms = tmax.item()
+    ms_per_step = ms / args.steps
+    value = world * images / (STEPS_PER_IMAGE * ms_per_step * 1e-3)
+
+    # ---------------- end to end through the public API with host buffers
+    host_in = lat0.clone().pin_memory()
+    host_out = torch.empty_like(host_in).pin_memory()
+    h2d = host_in.numel() * 4 + 12 * 4
+    d2h = host_out.numel() * 4
+    table_host = table.cpu().pin_memory()
+
+    def e2e_step(i):
+        j = i % STEPS_PER_IMAGE
+        eng.x.copy_(host_in, non_blocking=True)                     # this step's latents from pinned host memory
+        eng.step(float(ts[j]), table_host[j], 1.0)                  # coefficients also come from the host
+        host_out.copy_(eng.x, non_blocking=True)                    # read the step's result back
+        torch.cuda.current_stream().synchronize()
+        host_in.copy_(host_out)
+
+    for i in range(min(args.warmup, 3)):
+        e2e_step(i)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        e2e_step(i)
+    barrier()
+    e2e_ms = (time.perf_counter() - t0) * 1e3
+    if world > 1:
+        tmax = torch.tensor([e2e_ms], device=dev)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        e2e_ms = tmax.item()
+    e2e_value = world * images / (STEPS_PER_IMAGE * (e2e_ms / args.steps) * 1e-3)
+
+    if rank != 0:
+        return
+    # ---------------- live per-kernel-family timing (CUDA events around every launch of one step)
+    peaks = load_peaks()
+    fam = {}
+    for e in (eng.bn, eng.unet):
+        for k, (t_ms, fl, n) in e.run_timed().items():
+            r = fam.setdefault(k, [0.0, 0.0, 0])
+            r[0] += t_ms; r[1] += fl; r[2] += n
+    ig = fam.get("igemm", [1e-9, 0.0, 1])
+    achieved = ig[1] / (ig[0] * 1e-3) / 1e12
+    peak = peaks["bf16_sustained"]
+    step_flops = FLOP_PER_SAMPLE_STEP * 2 * images
+    roofline = {
+        "bound": "tensor", "kernel": "mfb::igemm_kernel<160|128> (tcgen05 implicit-GEMM conv/linear)",
+        "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+        "peak_source": peaks["source"] + ", sustained bf16 (kernel timed inside a long step)", "traffic": None,
+        "launches_per_step": ig[2], "avg_launch_ms": ig[0] / max(ig[2], 1),
+        "algorithmic_flops_per_step": ig[1],
+        "share_of_step_time": ig[0] / sum(v[0] for v in fam.values()),
+        "families_ms_per_step": {k: round(v[0], 4) for k, v in sorted(fam.items())},
+        "whole_step_tflops": step_flops / (ms_per_step * 1e-3) / 1e12,
+        "whole_step_frac_of_peak": step_flops / (ms_per_step * 1e-3) / 1e12 / peak,
+    }
+    # ---------------- CPU baseline (bounded sample) on this box's host cores
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        r = cpu_reference_run(steps=2, warmup=1, images=1)
+        cpu = {"value": r["images_per_s"], "unit": "images/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]}
+    line = {
+        "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+        "data": "synthetic",
+        "config": {"workload": f"MirrorFusion (SD1.5 UNet + BrushNet, depth-concat cond) {8 * H}x{8 * W}, batch {images} images/GPU "
+                               f"(net batch {2 * images}), 50 UniPC steps, CFG 7.5, random-init weights",
+                   "images_per_gpu": images, "latent": f"{H}x{W}", "steps_per_image": STEPS_PER_IMAGE,
+                   "steps_per_s": 1e3 / ms_per_step, "cuda_graph": not args.no_graph, "parallelism": f"dp{world} (images sharded, no per-step collective)",
+                   "l2": "inputs larger than L2: 2.96 GB of bf16 weights + >1 GB of activations stream per step (L2 = 126 MB)"},
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": e2e_ms / args.steps},
+        "gpu_launches": eng.launches_per_step * args.steps,
+        "roofline": roofline,
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--images", type=int, default=8, help="images per GPU per step (BASELINE.json configs[1]: 8)")
+    ap.add_argument("--latent", type=int, default=64, help="latent side (64 = 512x512 pixels)")
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    try:
+        run_ours(args, rank, world, local_rank)
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -34,6 +34,7 @@ class _Net:
         self.cfg, self.B, self.H, self.W, self.dev, self.name = cfg, B, H, W, device, name
         self.sd = {k: v.detach().to(device=device, dtype=f32) for k, v in sd.items()}
         self.prog: List[Callable[[], None]] = []
+        self.tags: List[Tuple[str, float]] = []       # (kernel family, algorithmic FLOPs) per program entry
         self.keep: List[object] = []
         self._scratch: Dict[Tuple, torch.Tensor] = {}
         self.flops = 0.0
@@ -58,25 +59,26 @@ class _Net:
         return self.sd[name].contiguous()
 
     # ---- op emitters
-    def emit(self, fn: Callable[[], None], n_launch: int = 1):
+    def emit(self, fn: Callable[[], None], n_launch: int = 1, tag: str = "misc", flops: float = 0.0):
         self.prog.append(fn)
+        self.tags.append((tag, flops))
         self.launches += n_launch
 
     def emit_plan(self, plan: ops.ConvPlan):
         self.keep.append(plan)
         self.flops += plan.flops
-        self.emit(plan.run)
+        self.emit(plan.run, 1, "igemm", plan.flops)
 
     def groupnorm(self, x1, x2, prefix: str, out, HW: int, eps: float, silu: bool):
         g, b = self.wf(prefix + ".weight"), self.wf(prefix + ".bias")
         G = self.cfg.norm_num_groups
         self.keep += [g, b]
-        self.emit(lambda: ops.groupnorm(x1, x2, g, b, out, self.gn_ws, B=self.B, HW=HW, groups=G, eps=eps, silu=silu), 2)
+        self.emit(lambda: ops.groupnorm(x1, x2, g, b, out, self.gn_ws, B=self.B, HW=HW, groups=G, eps=eps, silu=silu), 2, "groupnorm")
 
     def layernorm(self, x, prefix: str, out):
         g, b = self.wf(prefix + ".weight"), self.wf(prefix + ".bias")
         self.keep += [g, b]
-        self.emit(lambda: ops.layernorm(x, g, b, out, 1e-5))
+        self.emit(lambda: ops.layernorm(x, g, b, out, 1e-5), 1, "layernorm")
 
     # ---- timestep path (embeddings.py:27-67,226-237; resnet.py:369-376), fp32
     def build_time_path(self, resnet_prefixes: Sequence[str]):
@@ -162,6 +164,25 @@ class _Net:
         for f in self.prog:
             f()
 
+    def run_timed(self):
+        """Run the program once with a CUDA-event pair around every entry (on the current stream) and return
+        {family: (milliseconds, algorithmic FLOPs, entries)} — the live per-kernel timing bench.py reports."""
+        evs = []
+        for f in self.prog:
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            f()
+            b.record()
+            evs.append((a, b))
+        torch.cuda.synchronize()
+        out: Dict[str, List[float]] = {}
+        for (a, b), (tag, fl) in zip(evs, self.tags):
+            r = out.setdefault(tag, [0.0, 0.0, 0])
+            r[0] += a.elapsed_time(b)
+            r[1] += fl
+            r[2] += 1
+        return out
+
 
 def _resnet_prefixes(cfg: NetConfig) -> List[str]:
     out = []
@@ -191,7 +212,7 @@ class BrushNetEngine(_Net):
         bci = self.wf("conv_in_condition.bias")
         x = self.buf(B, H * W, boc[0])
         self.keep += [wci, bci]
-        self.emit(lambda: ops.conv_in(self.sample_in, self.cond_in, wci, bci, x))
+        self.emit(lambda x0=x: ops.conv_in(self.sample_in, self.cond_in, wci, bci, x0))   # bind now: `x` is reassigned below
         hw = (H, W)
         feats: List[Tuple[torch.Tensor, Tuple[int, int]]] = [(x, hw)]
         for i in range(n):
@@ -278,7 +299,7 @@ class UNetEngine(_Net):
         pre = self.buf(B, H * W, boc[0])      # first skip keeps the PRE-tap conv_in output (unet_2d_condition.py:1215-1218)
         x = self.buf(B, H * W, boc[0])
         tap0 = next(tap_it)
-        self.emit(lambda: ops.conv_in(self.sample_in, None, wci, bci, pre, tap0, x))
+        self.emit(lambda x0=x: ops.conv_in(self.sample_in, None, wci, bci, pre, tap0, x0))  # bind now: `x` is reassigned below
         skips = [(pre, hw)]
         for i in range(n):
             for j in range(cfg.layers_per_block):
@@ -316,7 +337,7 @@ class UNetEngine(_Net):
         wco = self.sd["conv_out.weight"].permute(0, 2, 3, 1).contiguous()
         bco = self.wf("conv_out.bias")
         self.keep += [wco, bco]
-        self.emit(lambda: ops.conv_out(nout, wco, bco, self.out, B=B, H=H, W=W))
+        self.emit(lambda: ops.conv_out(nout, wco, bco, self.out, B=B, H=H, W=W))  # nout/wco/bco are not rebound
 
     # Transformer2DModel + BasicTransformerBlock (transformer_2d.py:334-430, attention.py:291-412)
     def transformer(self, p: str, x, hw, tap):
@@ -346,7 +367,7 @@ class UNetEngine(_Net):
         att = self.scratch("tatt", M, C)
         kview = qkv.view(-1)[C:]
         self.emit(lambda: ops.attention(qkv, kview, vt, att, B=B, heads=heads, head_dim=d, Tq=T, Tk=T, ldq=3 * C,
-                                        ldk=3 * C, ldvt=Tp, ldo=C))
+                                        ldk=3 * C, ldvt=Tp, ldo=C), 1, "attention", 4.0 * B * T * T * C)
         self.flops += 4.0 * B * T * T * C
         h1 = self.scratch("th1", M, C)
         self.emit_plan(ops.linear_plan(att, self.sd[t + ".attn1.to_out.0.weight"].to(bf16).contiguous(), h1,
@@ -365,7 +386,7 @@ class UNetEngine(_Net):
         q2 = self.scratch("tq2", M, C)
         self.emit_plan(ops.linear_plan(nrm, self.sd[t + ".attn2.to_q.weight"].to(bf16).contiguous(), q2))
         self.emit(lambda: ops.attention(q2, k2, v2t, att, B=B, heads=heads, head_dim=d, Tq=T, Tk=Lc, ldq=C, ldk=C,
-                                        ldvt=Lp, ldo=C))
+                                        ldvt=Lp, ldo=C), 1, "attention", 4.0 * B * T * Lc * C)
         self.flops += 4.0 * B * T * Lc * C
         h2 = self.scratch("th2", M, C)
         self.emit_plan(ops.linear_plan(att, self.sd[t + ".attn2.to_out.0.weight"].to(bf16).contiguous(), h2,
