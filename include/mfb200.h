@@ -64,7 +64,7 @@ typedef struct mfb_conv_desc {
     const void* res2;     /* second residual: the BrushNet tap (S/models/unets/unet_2d_blocks.py:1388-1398 ...) */
     void* out;            /* [B,Ho,Wo,Cout] bf16 ([.., Cout/2] with geglu) */
     int geglu;
-    int block_n;          /* 0 = auto, else 128 or 160 */
+    int block_n;          /* 0 = auto, else 64, 80, 128 or 160 */
 } mfb_conv_desc;
 
 typedef struct mfb_plan mfb_plan;

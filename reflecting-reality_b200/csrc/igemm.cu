@@ -32,7 +32,8 @@ namespace mfb {
 constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int MAX_SEG = 16;
-constexpr int IGEMM_THREADS = 192;
+constexpr int IGEMM_EPI_WARPS = 8;
+constexpr int IGEMM_THREADS = 64 + 32 * IGEMM_EPI_WARPS;
 
 struct IgemmSeg {
     int map;      // which A tensor map
@@ -50,6 +51,7 @@ struct IgemmParams {
     int Wo, Ho, Bn;        // output geometry
     int tw, th, tn;        // tile box (tw*th*tn == 128)
     int tiles_w, tiles_h;  // tiles per row / column
+    int tiles_m, tiles_nn; // total M tiles, N tiles
     const float* bias;     // [N] (packed order) or null
     const float* rowbias;  // [Bn, rowbias_ld] or null (timestep-embedding projection)
     int rowbias_ld;
@@ -63,16 +65,44 @@ struct IgemmParams {
 
 template <int BN>
 struct IgemmCfg {
-    static constexpr int STAGES = 3;
     static constexpr int A_BYTES = BM * BK * 2;
     static constexpr int B_BYTES = BN * BK * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int TMEM_COLS = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
+    // persistent CTA, one per SM: as many operand stages as fit under the 227 KB limit (operand fetch is
+    // L2-latency/bandwidth bound, so depth matters more than anything else here)
+    static constexpr int STAGES = (224 * 1024) / STAGE_BYTES > 8 ? 8 : (224 * 1024) / STAGE_BYTES;
+    static constexpr int ACC_COLS = BN <= 64 ? 64 : BN <= 128 ? 128 : 256;  // TMEM columns per accumulator slot
+    static constexpr int TMEM_COLS = 2 * ACC_COLS;                           // double-buffered accumulator
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
+__device__ __forceinline__ void add_bf16x8(float (&f)[8], const uint4& rv) {
+    float2 t;
+    t = unpack_bf16x2(rv.x); f[0] += t.x; f[1] += t.y;
+    t = unpack_bf16x2(rv.y); f[2] += t.x; f[3] += t.y;
+    t = unpack_bf16x2(rv.z); f[4] += t.x; f[5] += t.y;
+    t = unpack_bf16x2(rv.w); f[6] += t.x; f[7] += t.y;
+}
+__device__ __forceinline__ void add_f32x8(float (&f)[8], const float* __restrict__ p) {
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(p));
+    const float4 b1 = __ldg(reinterpret_cast<const float4*>(p + 4));
+    f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
+    f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+}
+__device__ __forceinline__ uint4 pack_bf16x8(const float (&f)[8]) {
+    uint4 o;
+    o.x = pack_bf16x2(f[0], f[1]);
+    o.y = pack_bf16x2(f[2], f[3]);
+    o.z = pack_bf16x2(f[4], f[5]);
+    o.w = pack_bf16x2(f[6], f[7]);
+    return o;
+}
+
+// Persistent kernel: grid = min(#tiles, #SMs); CTA c processes tiles c, c+grid, ... (N-tile fastest, so the CTAs
+// running at the same time share A tiles through L2).  The accumulator is double-buffered in TMEM: while the 8
+// epilogue warps drain tile i, the MMA warp already accumulates tile i+1.
 template <int BN>
-__global__ void __launch_bounds__(IGEMM_THREADS) igemm_kernel(const __grid_constant__ IgemmParams p) {
+__global__ void __launch_bounds__(IGEMM_THREADS, 1) igemm_kernel(const __grid_constant__ IgemmParams p) {
     using Cfg = IgemmCfg<BN>;
     constexpr int STAGES = Cfg::STAGES;
     extern __shared__ uint8_t smem_raw[];
@@ -81,20 +111,15 @@ __global__ void __launch_bounds__(IGEMM_THREADS) igemm_kernel(const __grid_const
     const uint32_t bar_base = smem_base + STAGES * Cfg::STAGE_BYTES;
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
     auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
-    const uint32_t tmem_full_bar = bar_base + 8u * (2 * STAGES);
-    const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 1);
+    auto tmem_full_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
+    auto tmem_empty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
+    const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
     uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-
-    // tile coordinates
-    const int mt = blockIdx.x;
-    const int n_tile0 = blockIdx.y * BN;
-    const int t_w = mt % p.tiles_w;
-    const int t_h = (mt / p.tiles_w) % p.tiles_h;
-    const int t_n = mt / (p.tiles_w * p.tiles_h);
-    const int w0 = t_w * p.tw, h0 = t_h * p.th, n0 = t_n * p.tn;
+    const int tiles_n = p.tiles_nn;
+    const int num_tiles = p.tiles_m * tiles_n;
 
     int total_kb = 0;
     for (int s = 0; s < p.nseg; ++s) total_kb += p.seg[s].cblocks;
@@ -106,7 +131,10 @@ __global__ void __launch_bounds__(IGEMM_THREADS) igemm_kernel(const __grid_const
             mbar_init(full_bar(s), 1);
             mbar_init(empty_bar(s), 1);
         }
-        mbar_init(tmem_full_bar, 1);
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(tmem_full_bar(a), 1);
+            mbar_init(tmem_empty_bar(a), IGEMM_EPI_WARPS);
+        }
         fence_barrier_init();
     }
     if (warp == 1) {
@@ -121,18 +149,25 @@ __global__ void __launch_bounds__(IGEMM_THREADS) igemm_kernel(const __grid_const
     if (warp == 0) {
         if (lane == 0) {
             // ===== TMA producer =====
-            int it = 0, kcol = 0;
-            for (int s = 0; s < p.nseg; ++s) {
-                const IgemmSeg sg = p.seg[s];
-                const void* tm = &p.tmA[sg.map];
-                for (int cb = 0; cb < sg.cblocks; ++cb, ++it, kcol += BK) {
-                    const int stage = it % STAGES;
-                    const uint32_t phase = (it / STAGES) & 1;
-                    mbar_wait(empty_bar(stage), phase ^ 1);
-                    mbar_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
-                    const uint32_t a_dst = smem_base + stage * Cfg::STAGE_BYTES;
-                    tma_load_4d(a_dst, tm, full_bar(stage), sg.c0 + cb * BK, w0 + sg.dw, h0 + sg.dh, n0);
-                    tma_load_2d(a_dst + Cfg::A_BYTES, &p.tmB, full_bar(stage), kcol, n_tile0);
+            int it = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int nt = tile % tiles_n, mt = tile / tiles_n;
+                const int w0 = (mt % p.tiles_w) * p.tw;
+                const int h0 = ((mt / p.tiles_w) % p.tiles_h) * p.th;
+                const int n0 = (mt / (p.tiles_w * p.tiles_h)) * p.tn;
+                int kcol = 0;
+                for (int s = 0; s < p.nseg; ++s) {
+                    const IgemmSeg sg = p.seg[s];
+                    const void* tm = &p.tmA[sg.map];
+                    for (int cb = 0; cb < sg.cblocks; ++cb, ++it, kcol += BK) {
+                        const int stage = it % STAGES;
+                        const uint32_t phase = (it / STAGES) & 1;
+                        mbar_wait(empty_bar(stage), phase ^ 1);
+                        mbar_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
+                        const uint32_t a_dst = smem_base + stage * Cfg::STAGE_BYTES;
+                        tma_load_4d(a_dst, tm, full_bar(stage), sg.c0 + cb * BK, w0 + sg.dw, h0 + sg.dh, n0);
+                        tma_load_2d(a_dst + Cfg::A_BYTES, &p.tmB, full_bar(stage), kcol, nt * BN);
+                    }
                 }
             }
         }
@@ -141,137 +176,134 @@ __global__ void __launch_bounds__(IGEMM_THREADS) igemm_kernel(const __grid_const
         if (lane == 0) {
             // ===== MMA issuer =====
             constexpr uint32_t idesc = make_idesc_bf16(BM, BN);
-            for (int it = 0; it < total_kb; ++it) {
-                const int stage = it % STAGES;
-                const uint32_t phase = (it / STAGES) & 1;
-                mbar_wait(full_bar(stage), phase);
+            int it = 0, li = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++li) {
+                const int as = li & 1;
+                mbar_wait(tmem_empty_bar(as), ((li >> 1) & 1) ^ 1);   // epilogue has drained this accumulator slot
                 tc_fence_after();
-                const uint32_t a_addr = smem_base + stage * Cfg::STAGE_BYTES;
-                const uint64_t adesc = make_desc_k_sw128(a_addr);
-                const uint64_t bdesc = make_desc_k_sw128(a_addr + Cfg::A_BYTES);
+                const uint32_t tacc = tmem_base + as * Cfg::ACC_COLS;
+                for (int kb = 0; kb < total_kb; ++kb, ++it) {
+                    const int stage = it % STAGES;
+                    const uint32_t phase = (it / STAGES) & 1;
+                    mbar_wait(full_bar(stage), phase);
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_base + stage * Cfg::STAGE_BYTES;
+                    const uint64_t adesc = make_desc_k_sw128(a_addr);
+                    const uint64_t bdesc = make_desc_k_sw128(a_addr + Cfg::A_BYTES);
 #pragma unroll
-                for (int k = 0; k < BK / 16; ++k) {
-                    // advancing 16 bf16 (32 B) along K inside the 128B swizzle row: +2 in the (addr >> 4) field
-                    umma_bf16(tmem_base, adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), idesc, (it | k) != 0);
+                    for (int k = 0; k < BK / 16; ++k) {
+                        // advancing 16 bf16 (32 B) along K inside the 128B swizzle row: +2 in the (addr >> 4) field
+                        umma_bf16(tacc, adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), idesc, (kb | k) != 0);
+                    }
+                    umma_commit(empty_bar(stage));  // smem slot reusable once these MMAs have read it
                 }
-                umma_commit(empty_bar(stage));  // smem slot reusable once these MMAs have read it
+                umma_commit(tmem_full_bar(as));     // accumulator complete
             }
-            umma_commit(tmem_full_bar);         // accumulator complete
         }
         __syncwarp();
     } else {
-        // ===== epilogue: warps 2..5; TMEM lane quarter = warp % 4 =====
+        // ===== epilogue: warps 2..9.  TMEM lane quarter = warp % 4; the two warps of a quarter split the columns =====
         const int q = warp & 3;
+        const int half = (warp - 2) >> 2;
         const int r = q * 32 + lane;  // row of the tile == TMEM lane
         const int rw = r % p.tw;
         const int rh = (r / p.tw) % p.th;
         const int rn = r / (p.tw * p.th);
-        const int ow = w0 + rw, oh = h0 + rh, on = n0 + rn;
-        const bool valid = (ow < p.Wo) && (oh < p.Ho) && (on < p.Bn);
-        const long long m = (static_cast<long long>(on) * p.Ho + oh) * p.Wo + ow;
         const float alpha = p.alpha ? __ldg(p.alpha) : 1.0f;
-        const float* rb = p.rowbias ? p.rowbias + static_cast<long long>(valid ? on : 0) * p.rowbias_ld : nullptr;
+        int li = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++li) {
+            const int nt = tile % tiles_n, mt = tile / tiles_n;
+            const int ow = (mt % p.tiles_w) * p.tw + rw;
+            const int oh = ((mt / p.tiles_w) % p.tiles_h) * p.th + rh;
+            const int on = (mt / (p.tiles_w * p.tiles_h)) * p.tn + rn;
+            const bool valid = (ow < p.Wo) && (oh < p.Ho) && (on < p.Bn);
+            const long long m = (static_cast<long long>(on) * p.Ho + oh) * p.Wo + ow;
+            const float* rb = p.rowbias ? p.rowbias + static_cast<long long>(valid ? on : 0) * p.rowbias_ld : nullptr;
+            const int as = li & 1;
+            mbar_wait(tmem_full_bar(as), (li >> 1) & 1);
+            tc_fence_after();
+            const uint32_t trow = tmem_base + as * Cfg::ACC_COLS + (uint32_t(q * 32) << 16);
 
-        mbar_wait(tmem_full_bar, 0);
-        tc_fence_after();
-        const uint32_t trow = tmem_base + (uint32_t(q * 32) << 16);
-
-        if (!p.geglu) {
+            if (!p.geglu) {
+                constexpr int NCH = BN / 16;                 // 16-column chunks; warp `half` 0 takes the first ceil(NCH/2)
+                const int c_begin = half ? (NCH + 1) / 2 : 0;
+                const int c_end = half ? NCH : (NCH + 1) / 2;
 #pragma unroll 1
-            for (int c = 0; c < BN / 32; ++c) {
-                uint32_t v[32];
-                tmem_ld32(trow + c * 32, v);
-                tmem_wait_ld();
-                const int nb = n_tile0 + c * 32;
-                if (valid) {
+                for (int c = c_begin; c < c_end; ++c) {
+                    const int col = c * 16;
+                    const int n = nt * BN + col;
+                    const bool do0 = valid && (n < p.N), do1 = valid && (n + 8 < p.N);
+                    // issue the residual loads first so they are in flight while the accumulator is fetched
+                    uint4 r1a = make_uint4(0, 0, 0, 0), r1b = r1a, r2a = r1a, r2b = r1a;
+                    if (p.res1) {
+                        if (do0) r1a = __ldg(reinterpret_cast<const uint4*>(p.res1 + m * p.out_ld + n));
+                        if (do1) r1b = __ldg(reinterpret_cast<const uint4*>(p.res1 + m * p.out_ld + n + 8));
+                    }
+                    if (p.res2) {
+                        if (do0) r2a = __ldg(reinterpret_cast<const uint4*>(p.res2 + m * p.out_ld + n));
+                        if (do1) r2b = __ldg(reinterpret_cast<const uint4*>(p.res2 + m * p.out_ld + n + 8));
+                    }
+                    uint32_t v[16];
+                    tmem_ld16(trow + col, v);
+                    tmem_wait_ld();
 #pragma unroll
-                    for (int j = 0; j < 32; j += 8) {
-                        const int n = nb + j;
-                        if (n < p.N) {
+                    for (int j = 0; j < 2; ++j) {
+                        if (j == 0 ? do0 : do1) {
+                            const int nn = n + j * 8;
                             float f[8];
 #pragma unroll
-                            for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[j + e]);
-                            if (p.bias) {
-                                const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
-                                const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + n + 4));
-                                f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
-                                f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
-                            }
-                            if (rb) {
-                                const float4 b0 = __ldg(reinterpret_cast<const float4*>(rb + n));
-                                const float4 b1 = __ldg(reinterpret_cast<const float4*>(rb + n + 4));
-                                f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
-                                f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
-                            }
+                            for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[j * 8 + e]);
+                            if (p.bias) add_f32x8(f, p.bias + nn);
+                            if (rb) add_f32x8(f, rb + nn);
 #pragma unroll
                             for (int e = 0; e < 8; ++e) f[e] *= alpha;
-                            if (p.res1) {
-                                const uint4 rv = __ldg(reinterpret_cast<const uint4*>(p.res1 + m * p.out_ld + n));
-                                float2 t;
-                                t = unpack_bf16x2(rv.x); f[0] += t.x; f[1] += t.y;
-                                t = unpack_bf16x2(rv.y); f[2] += t.x; f[3] += t.y;
-                                t = unpack_bf16x2(rv.z); f[4] += t.x; f[5] += t.y;
-                                t = unpack_bf16x2(rv.w); f[6] += t.x; f[7] += t.y;
-                            }
-                            if (p.res2) {
-                                const uint4 rv = __ldg(reinterpret_cast<const uint4*>(p.res2 + m * p.out_ld + n));
-                                float2 t;
-                                t = unpack_bf16x2(rv.x); f[0] += t.x; f[1] += t.y;
-                                t = unpack_bf16x2(rv.y); f[2] += t.x; f[3] += t.y;
-                                t = unpack_bf16x2(rv.z); f[4] += t.x; f[5] += t.y;
-                                t = unpack_bf16x2(rv.w); f[6] += t.x; f[7] += t.y;
-                            }
-                            uint4 o;
-                            o.x = pack_bf16x2(f[0], f[1]);
-                            o.y = pack_bf16x2(f[2], f[3]);
-                            o.z = pack_bf16x2(f[4], f[5]);
-                            o.w = pack_bf16x2(f[6], f[7]);
-                            *reinterpret_cast<uint4*>(p.out + m * p.out_ld + n) = o;
+                            if (p.res1) add_bf16x8(f, j == 0 ? r1a : r1b);
+                            if (p.res2) add_bf16x8(f, j == 0 ? r2a : r2b);
+                            *reinterpret_cast<uint4*>(p.out + m * p.out_ld + nn) = pack_bf16x8(f);
                         }
                     }
                 }
-            }
-        } else {
-            // GEGLU (S/models/activations.py:100-103): out = value * gelu_erf(gate); tile = [64 value | 64 gate]
-            if constexpr (BN == 128) {
+            } else {
+                // GEGLU (S/models/activations.py:100-103): out = value * gelu_erf(gate); tile = [64 value | 64 gate]
+                if constexpr (BN == 128) {
 #pragma unroll 1
-                for (int c = 0; c < 2; ++c) {
-                    uint32_t v[32], g[32];
-                    tmem_ld32(trow + c * 32, v);
-                    tmem_ld32(trow + 64 + c * 32, g);
-                    tmem_wait_ld();
-                    if (valid) {
-                        const int ncol = blockIdx.y * 64 + c * 32;  // output column
-                        const int pv = n_tile0 + c * 32;            // packed column of the value
+                    for (int c = 0; c < 2; ++c) {
+                        const int col = half * 32 + c * 16;   // value column inside the tile; gate = col + 64
+                        uint32_t v[16], g[16];
+                        tmem_ld16(trow + col, v);
+                        tmem_ld16(trow + 64 + col, g);
+                        tmem_wait_ld();
+                        const int pv = nt * BN + col;          // packed column of the value
+                        const int ncol = nt * 64 + col;        // output column
 #pragma unroll
-                        for (int j = 0; j < 32; j += 8) {
-                            if (pv + j < p.N) {
-                                float f[8];
+                        for (int j = 0; j < 2; ++j) {
+                            if (valid && pv + j * 8 < p.N) {
+                                float f[8], gt[8];
 #pragma unroll
                                 for (int e = 0; e < 8; ++e) {
-                                    float val = __uint_as_float(v[j + e]);
-                                    float gat = __uint_as_float(g[j + e]);
-                                    if (p.bias) {
-                                        val += __ldg(p.bias + pv + j + e);
-                                        gat += __ldg(p.bias + pv + 64 + j + e);
-                                    }
-                                    f[e] = val * gelu_erf_f(gat);
+                                    f[e] = __uint_as_float(v[j * 8 + e]);
+                                    gt[e] = __uint_as_float(g[j * 8 + e]);
                                 }
-                                uint4 o;
-                                o.x = pack_bf16x2(f[0], f[1]);
-                                o.y = pack_bf16x2(f[2], f[3]);
-                                o.z = pack_bf16x2(f[4], f[5]);
-                                o.w = pack_bf16x2(f[6], f[7]);
-                                *reinterpret_cast<uint4*>(p.out + m * p.out_ld + ncol + j) = o;
+                                if (p.bias) {
+                                    add_f32x8(f, p.bias + pv + j * 8);
+                                    add_f32x8(gt, p.bias + pv + 64 + j * 8);
+                                }
+#pragma unroll
+                                for (int e = 0; e < 8; ++e) f[e] *= gelu_erf_f(gt[e]);
+                                *reinterpret_cast<uint4*>(p.out + m * p.out_ld + ncol + j * 8) = pack_bf16x8(f);
                             }
                         }
                     }
                 }
             }
+            // all tcgen05.ld of this warp have completed (wait::ld above): hand the accumulator slot back
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tmem_empty_bar(as));
         }
-        tc_fence_before();
     }
 
+    tc_fence_before();
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
@@ -391,10 +423,19 @@ extern "C" int mfb_conv_plan_create(const mfb_conv_desc* d, mfb_plan** out) {
     p.nseg = nseg;
 
     // BN: 160 divides every conv width of the SD1.5 family (320/640/1280/960); GEGLU needs the 64|64 split.
+    // When the wide tile leaves most SMs without work (8x8 latents: M = 64*B), halve it.
+    const int tiles_m = p.tiles_w * p.tiles_h * tiles_n;
     int bn = d->geglu ? 128 : (d->Cout % 160 == 0 ? 160 : 128);
-    if (d->block_n == 128 || d->block_n == 160) bn = d->block_n;
+    if (!d->geglu) {
+        const int sms = device_sm_count() > 0 ? device_sm_count() : 148;
+        const long t_wide = long(tiles_m) * ((d->Cout + bn - 1) / bn);
+        if (t_wide * 10 < long(sms) * 7 && d->Cout > bn / 2) bn /= 2;
+    }
+    if (d->block_n == 64 || d->block_n == 80 || d->block_n == 128 || d->block_n == 160) bn = d->block_n;
     MFB_REQUIRE(!d->geglu || bn == 128, "geglu requires block_n 128");
     pl->bn = bn;
+    p.tiles_m = tiles_m;
+    p.tiles_nn = (d->Cout + bn - 1) / bn;
     {
         const uint64_t dims[2] = {uint64_t(ktot), uint64_t(d->Cout)};
         const uint64_t str[1] = {uint64_t(ktot) * 2};
@@ -411,7 +452,11 @@ extern "C" int mfb_conv_plan_create(const mfb_conv_desc* d, mfb_plan** out) {
     p.out = static_cast<__nv_bfloat16*>(d->out);
     p.geglu = d->geglu;
     p.out_ld = d->geglu ? d->Cout / 2 : d->Cout;
-    pl->grid = dim3(p.tiles_w * p.tiles_h * tiles_n, (d->Cout + bn - 1) / bn, 1);
+    {
+        const int sms = device_sm_count() > 0 ? device_sm_count() : 148;
+        const long total = long(p.tiles_m) * p.tiles_nn;
+        pl->grid = dim3(unsigned(total < sms ? total : sms), 1, 1);
+    }
     pl->flops = 2.0 * double(p.M) * d->Cout * ktot;
     *out = reinterpret_cast<mfb_plan*>(pl);
     return MFB_OK;
@@ -421,7 +466,12 @@ extern "C" int mfb_plan_run(mfb_plan* plan, void* stream) {
     MFB_REQUIRE(plan, "null plan");
     Plan* pl = reinterpret_cast<Plan*>(plan);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    return pl->bn == 160 ? launch_igemm<160>(*pl, st) : launch_igemm<128>(*pl, st);
+    switch (pl->bn) {
+        case 160: return launch_igemm<160>(*pl, st);
+        case 128: return launch_igemm<128>(*pl, st);
+        case 80: return launch_igemm<80>(*pl, st);
+        default: return launch_igemm<64>(*pl, st);
+    }
 }
 
 extern "C" int mfb_plan_destroy(mfb_plan* plan) {

@@ -8,9 +8,9 @@
 namespace mfb {
 
 // ---------------------------------------------------------------------------------------------- conv_in
-// grid (ceil(W/8), ceil(H/8), B), block 256.  Input patch (10x10xCin fp32) staged in smem; each thread computes
-// 8 output channels of one pixel at a time; weights [3][3][Cin][Cout] fp32 are read through L1 (coalesced over
-// the 8-channel groups of consecutive threads).
+// grid (ceil(W/8), ceil(H/8), B), block = 8 * Cout/8 threads (320 for Cout = 320).  Input patch (10x10xCin fp32)
+// staged in smem; a thread owns an 8-channel group and one 8-pixel row of the tile, so each weight vector
+// ([3][3][Cin][Cout] fp32, coalesced over the channel groups of consecutive threads) is loaded once per 8 pixels.
 __global__ void conv_in_kernel(const float* __restrict__ xa, int Ca, const float* __restrict__ xb, int Cb, int H, int W,
                                const float* __restrict__ w, const float* __restrict__ bias, int Cout,
                                __nv_bfloat16* __restrict__ out, const __nv_bfloat16* __restrict__ tap,
@@ -31,41 +31,54 @@ __global__ void conv_in_kernel(const float* __restrict__ xa, int Ca, const float
     }
     __syncthreads();
     const int ngroups = Cout / 8;
-    for (int item = threadIdx.x; item < 64 * ngroups; item += blockDim.x) {
-        const int cg = item % ngroups, pix = item / ngroups;
-        const int ph = pix / 8, pw = pix % 8;
-        const int oh = h0 + ph, ow = w0 + pw;
-        if (oh >= H || ow >= W) continue;
-        float acc[8];
+    for (int item = threadIdx.x; item < 8 * ngroups; item += blockDim.x) {
+        const int cg = item % ngroups, ph = item / ngroups;
+        const int oh = h0 + ph;
+        if (oh >= H) continue;
+        float acc[8][8];  // [pixel in row][channel]
 #pragma unroll
-        for (int e = 0; e < 8; ++e) acc[e] = __ldg(&bias[cg * 8 + e]);
+        for (int e = 0; e < 8; ++e) {
+            const float bv = __ldg(&bias[cg * 8 + e]);
+#pragma unroll
+            for (int px = 0; px < 8; ++px) acc[px][e] = bv;
+        }
         for (int kh = 0; kh < 3; ++kh)
             for (int kw = 0; kw < 3; ++kw)
                 for (int c = 0; c < Cin; ++c) {
-                    const float xv = patch[c * 100 + (ph + kh) * 10 + (pw + kw)];
                     const float* wp = w + ((static_cast<size_t>(kh * 3 + kw) * Cin + c) * Cout + cg * 8);
                     const float4 w0v = __ldg(reinterpret_cast<const float4*>(wp));
                     const float4 w1v = __ldg(reinterpret_cast<const float4*>(wp + 4));
-                    acc[0] = fmaf(xv, w0v.x, acc[0]); acc[1] = fmaf(xv, w0v.y, acc[1]);
-                    acc[2] = fmaf(xv, w0v.z, acc[2]); acc[3] = fmaf(xv, w0v.w, acc[3]);
-                    acc[4] = fmaf(xv, w1v.x, acc[4]); acc[5] = fmaf(xv, w1v.y, acc[5]);
-                    acc[6] = fmaf(xv, w1v.z, acc[6]); acc[7] = fmaf(xv, w1v.w, acc[7]);
+                    const float* prow = patch + c * 100 + (ph + kh) * 10 + kw;
+#pragma unroll
+                    for (int px = 0; px < 8; ++px) {
+                        const float xv = prow[px];
+                        acc[px][0] = fmaf(xv, w0v.x, acc[px][0]); acc[px][1] = fmaf(xv, w0v.y, acc[px][1]);
+                        acc[px][2] = fmaf(xv, w0v.z, acc[px][2]); acc[px][3] = fmaf(xv, w0v.w, acc[px][3]);
+                        acc[px][4] = fmaf(xv, w1v.x, acc[px][4]); acc[px][5] = fmaf(xv, w1v.y, acc[px][5]);
+                        acc[px][6] = fmaf(xv, w1v.z, acc[px][6]); acc[px][7] = fmaf(xv, w1v.w, acc[px][7]);
+                    }
                 }
-        const size_t o = ((static_cast<size_t>(b) * H + oh) * W + ow) * Cout + cg * 8;
-        uint4 pk;
-        pk.x = pack_bf16x2(acc[0], acc[1]); pk.y = pack_bf16x2(acc[2], acc[3]);
-        pk.z = pack_bf16x2(acc[4], acc[5]); pk.w = pack_bf16x2(acc[6], acc[7]);
-        *reinterpret_cast<uint4*>(out + o) = pk;
-        if (tap) {
-            const uint4 tv = __ldg(reinterpret_cast<const uint4*>(tap + o));
-            float2 t;
-            t = unpack_bf16x2(tv.x); acc[0] += t.x; acc[1] += t.y;
-            t = unpack_bf16x2(tv.y); acc[2] += t.x; acc[3] += t.y;
-            t = unpack_bf16x2(tv.z); acc[4] += t.x; acc[5] += t.y;
-            t = unpack_bf16x2(tv.w); acc[6] += t.x; acc[7] += t.y;
-            pk.x = pack_bf16x2(acc[0], acc[1]); pk.y = pack_bf16x2(acc[2], acc[3]);
-            pk.z = pack_bf16x2(acc[4], acc[5]); pk.w = pack_bf16x2(acc[6], acc[7]);
-            *reinterpret_cast<uint4*>(out_post + o) = pk;
+#pragma unroll
+        for (int px = 0; px < 8; ++px) {
+            const int ow = w0 + px;
+            if (ow >= W) continue;
+            const size_t o = ((static_cast<size_t>(b) * H + oh) * W + ow) * Cout + cg * 8;
+            uint4 pk;
+            pk.x = pack_bf16x2(acc[px][0], acc[px][1]); pk.y = pack_bf16x2(acc[px][2], acc[px][3]);
+            pk.z = pack_bf16x2(acc[px][4], acc[px][5]); pk.w = pack_bf16x2(acc[px][6], acc[px][7]);
+            *reinterpret_cast<uint4*>(out + o) = pk;
+            if (tap) {
+                const uint4 tv = __ldg(reinterpret_cast<const uint4*>(tap + o));
+                float2 t;
+                float f[8];
+                t = unpack_bf16x2(tv.x); f[0] = acc[px][0] + t.x; f[1] = acc[px][1] + t.y;
+                t = unpack_bf16x2(tv.y); f[2] = acc[px][2] + t.x; f[3] = acc[px][3] + t.y;
+                t = unpack_bf16x2(tv.z); f[4] = acc[px][4] + t.x; f[5] = acc[px][5] + t.y;
+                t = unpack_bf16x2(tv.w); f[6] = acc[px][6] + t.x; f[7] = acc[px][7] + t.y;
+                pk.x = pack_bf16x2(f[0], f[1]); pk.y = pack_bf16x2(f[2], f[3]);
+                pk.z = pack_bf16x2(f[4], f[5]); pk.w = pack_bf16x2(f[6], f[7]);
+                *reinterpret_cast<uint4*>(out_post + o) = pk;
+            }
         }
     }
 }
@@ -90,11 +103,26 @@ __global__ void conv_out_kernel(const __nv_bfloat16* __restrict__ x, int Cin, in
         const int oh = (pix / W) % H;
         const int b = pix / (static_cast<long long>(W) * H);
         float acc[4] = {0.f, 0.f, 0.f, 0.f};
-        for (int v = lane; v < 9 * nvec_c; v += 32) {
+        constexpr int MAXV = 12;                      // 9 * (Cin/8) / 32 rounded up for Cin <= 320
+        uint4 ubuf[MAXV];
+        const int nv = 9 * nvec_c;
+#pragma unroll
+        for (int i = 0; i < MAXV; ++i) {              // all loads of this pixel in flight at once
+            const int v = lane + i * 32;
+            ubuf[i] = make_uint4(0, 0, 0, 0);
+            if (v < nv) {
+                const int tapi = v / nvec_c, cv = v % nvec_c;
+                const int hh = oh + tapi / 3 - 1, ww = ow + tapi % 3 - 1;
+                if (hh >= 0 && hh < H && ww >= 0 && ww < W)
+                    ubuf[i] = __ldg(reinterpret_cast<const uint4*>(x + ((static_cast<size_t>(b) * H + hh) * W + ww) * Cin + cv * 8));
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < MAXV; ++i) {
+            const int v = lane + i * 32;
+            if (v >= nv) break;
             const int tapi = v / nvec_c, cv = v % nvec_c;
-            const int hh = oh + tapi / 3 - 1, ww = ow + tapi % 3 - 1;
-            if (hh < 0 || hh >= H || ww < 0 || ww >= W) continue;
-            const uint4 u = __ldg(reinterpret_cast<const uint4*>(x + ((static_cast<size_t>(b) * H + hh) * W + ww) * Cin + cv * 8));
+            const uint4 u = ubuf[i];
             float f[8];
             float2 t;
             t = unpack_bf16x2(u.x); f[0] = t.x; f[1] = t.y;
@@ -194,37 +222,54 @@ __global__ void sinusoid_kernel(const float* __restrict__ t, int M, int dim, flo
     out[static_cast<size_t>(m) * dim + half + j] = sinf(a);
 }
 
-// y[m, n] = act_out(b[n] + sum_k W[n,k] * act_in(x[m,k]));  one warp per n, rows in groups of 8
+// y[m, n] = act_out(b[n] + sum_k W[n,k] * act_in(x[m,k])).  grid (ceil(N/64), ceil(M/8)), block 256:
+// the 8 activation rows of the block are staged once in shared memory (with act_in applied) and reused by
+// the 64 output columns of the block (8 warps x 8 columns); weights stream through as 16-byte bf16 vectors.
 __global__ void linear_small_kernel(const float* __restrict__ x, int M, int K, const __nv_bfloat16* __restrict__ w,
                                     const float* __restrict__ b, int N, int act_in, int act_out, float* __restrict__ y) {
-    const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const int lane = threadIdx.x & 31;
-    if (n >= N) return;
+    extern __shared__ float xs[];  // [8][K]
     const int m0 = blockIdx.y * 8;
-    float acc[8];
+    for (int i = threadIdx.x; i < 8 * K; i += blockDim.x) {
+        const int r = i / K, k = i % K;
+        float v = (m0 + r < M) ? x[static_cast<size_t>(m0 + r) * K + k] : 0.f;
+        if (act_in) v = v / (1.f + expf(-v));
+        xs[i] = v;
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int j = 0; j < 8; ++j) {
+        const int n = blockIdx.x * 64 + warp * 8 + j;
+        if (n >= N) break;
+        float acc[8];
 #pragma unroll
-    for (int r = 0; r < 8; ++r) acc[r] = 0.f;
-    const __nv_bfloat16* wr = w + static_cast<size_t>(n) * K;
-    for (int k = lane * 2; k < K; k += 64) {
-        const float2 wv = unpack_bf16x2(__ldg(reinterpret_cast<const uint32_t*>(wr + k)));
+        for (int r = 0; r < 8; ++r) acc[r] = 0.f;
+        const __nv_bfloat16* wr = w + static_cast<size_t>(n) * K;
+        for (int k = lane * 8; k < K; k += 256) {
+            const uint4 u = __ldg(reinterpret_cast<const uint4*>(wr + k));
+            float wv[8];
+            float2 t;
+            t = unpack_bf16x2(u.x); wv[0] = t.x; wv[1] = t.y;
+            t = unpack_bf16x2(u.y); wv[2] = t.x; wv[3] = t.y;
+            t = unpack_bf16x2(u.z); wv[4] = t.x; wv[5] = t.y;
+            t = unpack_bf16x2(u.w); wv[6] = t.x; wv[7] = t.y;
 #pragma unroll
-        for (int r = 0; r < 8; ++r) {
-            if (m0 + r < M) {
-                float2 xv = *reinterpret_cast<const float2*>(x + static_cast<size_t>(m0 + r) * K + k);
-                if (act_in) { xv.x = xv.x / (1.f + expf(-xv.x)); xv.y = xv.y / (1.f + expf(-xv.y)); }
-                acc[r] = fmaf(wv.x, xv.x, fmaf(wv.y, xv.y, acc[r]));
+            for (int r = 0; r < 8; ++r) {
+                const float4 x0 = *reinterpret_cast<const float4*>(xs + r * K + k);
+                const float4 x1 = *reinterpret_cast<const float4*>(xs + r * K + k + 4);
+                acc[r] += wv[0] * x0.x + wv[1] * x0.y + wv[2] * x0.z + wv[3] * x0.w + wv[4] * x1.x + wv[5] * x1.y +
+                          wv[6] * x1.z + wv[7] * x1.w;
             }
         }
-    }
 #pragma unroll
-    for (int r = 0; r < 8; ++r) {
-        float a = acc[r];
+        for (int r = 0; r < 8; ++r) {
+            float a = acc[r];
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-        if (lane == 0 && m0 + r < M) {
-            a += b ? b[n] : 0.f;
-            if (act_out) a = a / (1.f + expf(-a));
-            y[static_cast<size_t>(m0 + r) * N + n] = a;
+            for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+            if (lane == 0 && m0 + r < M) {
+                a += b ? b[n] : 0.f;
+                if (act_out) a = a / (1.f + expf(-a));
+                y[static_cast<size_t>(m0 + r) * N + n] = a;
+            }
         }
     }
 }
@@ -273,7 +318,10 @@ extern "C" int mfb_conv_in(const float* sample, int Ca, const float* cond, int C
     const int Cin = Ca + Cb;
     MFB_REQUIRE(Cin <= 64, "conv_in supports at most 64 input channels");
     dim3 grid((W + 7) / 8, (H + 7) / 8, B);
-    conv_in_kernel<<<grid, 256, Cin * 100 * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
+    int threads = 8 * (Cout / 8);
+    if (threads > 640) threads = 640;
+    threads = (threads + 31) / 32 * 32;
+    conv_in_kernel<<<grid, threads, Cin * 100 * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
         sample, Ca, cond, Cb, H, W, w, bias, Cout, static_cast<__nv_bfloat16*>(out), static_cast<const __nv_bfloat16*>(tap),
         static_cast<__nv_bfloat16*>(out_post));
     MFB_CUDA_OK(cudaGetLastError());
@@ -283,7 +331,7 @@ extern "C" int mfb_conv_in(const float* sample, int Ca, const float* cond, int C
 extern "C" int mfb_conv_out(const void* x, int Cin, int B, int H, int W, const float* w, const float* bias, int Cout,
                             float* out, void* stream) {
     MFB_REQUIRE(x && w && bias && out, "null pointer");
-    MFB_REQUIRE(Cout >= 1 && Cout <= 4 && Cin % 8 == 0, "conv_out supports Cout <= 4, Cin %% 8 == 0");
+    MFB_REQUIRE(Cout >= 1 && Cout <= 4 && Cin % 8 == 0 && 9 * (Cin / 8) <= 12 * 32, "conv_out supports Cout <= 4, Cin %% 8 == 0, Cin <= 336");
     const size_t smem = static_cast<size_t>(Cout) * 9 * Cin * sizeof(float);
     MFB_REQUIRE(smem <= 200 * 1024, "conv_out weights do not fit shared memory");
     static bool configured = false;
@@ -292,7 +340,7 @@ extern "C" int mfb_conv_out(const void* x, int Cin, int B, int H, int W, const f
         configured = true;
     }
     const long long npix = static_cast<long long>(B) * H * W;
-    const int grid = grid_for(npix, 8, 148 * 2);
+    const int grid = grid_for(npix, 8, 148 * 4);
     conv_out_kernel<<<grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(static_cast<const __nv_bfloat16*>(x), Cin, B, H, W, w,
                                                                            bias, Cout, out);
     MFB_CUDA_OK(cudaGetLastError());
@@ -350,9 +398,15 @@ extern "C" int mfb_timestep_sinusoid(const float* t, int M, int dim, float* out,
 
 extern "C" int mfb_linear_small(const float* x, int M, int K, const void* w, const float* b, int N, int act_in, int act_out,
                                 float* y, void* stream) {
-    MFB_REQUIRE(x && w && y && K % 2 == 0, "bad arguments");
-    dim3 grid((N + 7) / 8, (M + 7) / 8), block(256);
-    linear_small_kernel<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(x, M, K, static_cast<const __nv_bfloat16*>(w), b, N,
+    MFB_REQUIRE(x && w && y && K % 8 == 0 && K <= 4096, "linear_small needs K %% 8 == 0 and K <= 4096");
+    const size_t smem = static_cast<size_t>(8) * K * sizeof(float);
+    static bool configured = false;
+    if (!configured) {
+        MFB_CUDA_OK(cudaFuncSetAttribute(linear_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 4096 * 4));
+        configured = true;
+    }
+    dim3 grid((N + 63) / 64, (M + 7) / 8), block(256);
+    linear_small_kernel<<<grid, block, smem, static_cast<cudaStream_t>(stream)>>>(x, M, K, static_cast<const __nv_bfloat16*>(w), b, N,
                                                                              act_in, act_out, y);
     MFB_CUDA_OK(cudaGetLastError());
     return MFB_OK;

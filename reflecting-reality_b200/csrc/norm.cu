@@ -42,7 +42,22 @@ __global__ void gn_stats_kernel(const __nv_bfloat16* __restrict__ x1, int C1, co
     float s[8], q[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) { s[e] = 0.f; q[e] = 0.f; }
-    for (int p = p0 + threadIdx.y; p < p1; p += blockDim.y) {
+    // 4 independent 16-byte loads in flight per thread (HBM-bound: memory-level parallelism is what matters)
+    const int step = blockDim.y;
+    int p = p0 + threadIdx.y;
+    for (; p + 3 * step < p1; p += 4 * step) {
+        uint4 u[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) u[k] = __ldg(reinterpret_cast<const uint4*>(src + static_cast<size_t>(p + k * step) * ld));
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            float f[8];
+            unpack8(u[k], f);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) { s[e] += f[e]; q[e] = fmaf(f[e], f[e], q[e]); }
+        }
+    }
+    for (; p < p1; p += step) {
         const uint4 u = __ldg(reinterpret_cast<const uint4*>(src + static_cast<size_t>(p) * ld));
         float f[8];
         unpack8(u, f);
@@ -98,13 +113,31 @@ __global__ void gn_apply_kernel(const __nv_bfloat16* __restrict__ x1, int C1, co
     __nv_bfloat16* dst = out + static_cast<size_t>(b) * HW * C + c0;
     const int p0 = blockIdx.x * pix_per_cta;
     const int p1 = min(HW, p0 + pix_per_cta);
-    for (int p = p0 + threadIdx.y; p < p1; p += blockDim.y) {
+    const int step = blockDim.y;
+    int p = p0 + threadIdx.y;
+    for (; p + 3 * step < p1; p += 4 * step) {
+        uint4 u[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) u[k] = __ldg(reinterpret_cast<const uint4*>(src + static_cast<size_t>(p + k * step) * ld));
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            float f[8];
+            unpack8(u[k], f);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const float y = fmaf(f[e], sc[e], sh[e]);
+                f[e] = silu ? silu_f(y) : y;
+            }
+            *reinterpret_cast<uint4*>(dst + static_cast<size_t>(p + k * step) * C) = pack8(f);
+        }
+    }
+    for (; p < p1; p += step) {
         const uint4 u = __ldg(reinterpret_cast<const uint4*>(src + static_cast<size_t>(p) * ld));
         float f[8];
         unpack8(u, f);
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
-            float y = fmaf(f[e], sc[e], sh[e]);
+            const float y = fmaf(f[e], sc[e], sh[e]);
             f[e] = silu ? silu_f(y) : y;
         }
         *reinterpret_cast<uint4*>(dst + static_cast<size_t>(p) * C) = pack8(f);

@@ -117,11 +117,24 @@ def test_conv_block_n_variants_agree(ops):
     B, H, W, Cin, Cout = 2, 16, 16, 64, 640
     x = randn(B, H, W, Cin, seed=1)
     wp = ops.pack_conv_weight(randn(Cout, Cin, 3, 3, seed=2, scale=0.05).float())
-    o1 = torch.empty(B, H, W, Cout, device="cuda", dtype=bf16)
-    o2 = torch.empty_like(o1)
-    ops.ConvPlan(x, wp, o1, B=B, H=H, W=W, Cin=Cin, Cout=Cout, ksize=3, block_n=128).run()
-    ops.ConvPlan(x, wp, o2, B=B, H=H, W=W, Cin=Cin, Cout=Cout, ksize=3, block_n=160).run()
-    assert torch.equal(o1, o2)    # same K order, same fp32 accumulation -> bit identical
+    outs = []
+    for bn in (64, 80, 128, 160):
+        o = torch.full((B, H, W, Cout), float("nan"), device="cuda", dtype=bf16)
+        ops.ConvPlan(x, wp, o, B=B, H=H, W=W, Cin=Cin, Cout=Cout, ksize=3, block_n=bn).run()
+        outs.append(o)
+    for o in outs[1:]:
+        assert torch.equal(outs[0], o)    # same K order, same fp32 accumulation -> bit identical
+
+
+def test_persistent_tile_loop_many_tiles(ops):
+    # far more tiles than SMs: every CTA walks several tiles through both TMEM accumulator slots
+    M, K, N = 40000, 128, 640
+    x = randn(M, K, seed=1)
+    w = randn(N, K, seed=2, scale=K ** -0.5)
+    r1 = randn(M, N, seed=3)
+    out = torch.full((M, N), float("nan"), device="cuda", dtype=bf16)
+    ops.linear_plan(x, w, out, res1=r1).run()
+    assert rel(out.float(), x.float() @ w.float().t() + r1.float()) < 4e-3
 
 
 # ------------------------------------------------------------------------------------------------ norms

@@ -30,6 +30,8 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--batch", type=int, default=16)
     ap.add_argument("--block-n", type=int, default=0)
+    ap.add_argument("--only", type=str, default="", help="substring filter on the shape name")
+    ap.add_argument("--iters", type=int, default=20)
     args = ap.parse_args()
     ops.lib()
     B = args.batch
@@ -46,6 +48,8 @@ def main():
     ]
     rows = []
     for name, H, cin, cout, ks in shapes:
+        if args.only and args.only not in name:
+            continue
         x = torch.randn(B, H, H, cin, device="cuda").to(bf16)
         w = (torch.randn(cout, ks * ks * cin, device="cuda") * 0.02).to(bf16)
         geglu = "geglu" in name
@@ -53,11 +57,13 @@ def main():
         bias = torch.zeros(cout, device="cuda")
         plan = ops.ConvPlan(x, w, out, B=B, H=H, W=H, Cin=cin, Cout=cout, ksize=ks, bias=bias, geglu=geglu,
                             block_n=0 if geglu else args.block_n)
-        ms = time_plan(plan)
+        ms = time_plan(plan, args.iters)
         tf = plan.flops / ms / 1e9
         rows.append({"shape": name, "M": B * H * H, "N": cout, "K": ks * ks * cin, "ms": round(ms, 4), "tflops": round(tf, 1)})
         print(f"{name:40s} M={B*H*H:6d} N={cout:5d} K={ks*ks*cin:6d}  {ms:8.4f} ms  {tf:7.1f} TFLOP/s", flush=True)
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    if args.only:
+        return
     with open(os.path.join(ROOT, "gpurun_out", f"igemm_shapes_b{B}.json"), "w") as f:
         json.dump(rows, f, indent=1)
 
