@@ -24,7 +24,7 @@ void set_error(const char* fmt, ...) {
 int device_sm_count() { return g_sms; }
 
 int encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                     const uint32_t* box, bool swizzle128) {
+                     const uint32_t* box, int swizzle_bytes) {
     if (!g_encode) {
         set_error("mfb_init() has not been called (cuTensorMapEncodeTiled unresolved)");
         return MFB_EINVAL;
@@ -44,7 +44,9 @@ int encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_
         return MFB_EINVAL;
     }
     CUresult r = g_encode(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(base), gdim, gstr, bdim, estr,
-                          CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                          : swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE,
                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         set_error("cuTensorMapEncodeTiled failed (CUresult %d) rank %d dims [%llu,%llu,%llu,%llu] box [%u,%u,%u,%u]", int(r), rank,

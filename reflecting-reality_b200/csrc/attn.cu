@@ -305,14 +305,14 @@ extern "C" int mfb_attention(const void* q, int ldq, const void* k, int ldk, con
         const uint64_t dims[3] = {uint64_t(ldq), uint64_t(Tq), uint64_t(B)};
         const uint64_t str[2] = {uint64_t(ldq) * 2, uint64_t(Tq) * ldq * 2};
         const uint32_t box[3] = {64, BQ, 1};
-        int rc = encode_tmap_bf16(&p.tmQ, q, 3, dims, str, box, true);
+        int rc = encode_tmap_bf16(&p.tmQ, q, 3, dims, str, box, 128);
         if (rc) return rc;
     }
     {
         const uint64_t dims[3] = {uint64_t(ldk), uint64_t(Tk), uint64_t(B)};
         const uint64_t str[2] = {uint64_t(ldk) * 2, uint64_t(Tk) * ldk * 2};
         const uint32_t box[3] = {64, BKV, 1};
-        int rc = encode_tmap_bf16(&p.tmK, k, 3, dims, str, box, true);
+        int rc = encode_tmap_bf16(&p.tmK, k, 3, dims, str, box, 128);
         if (rc) return rc;
     }
     {
@@ -320,7 +320,7 @@ extern "C" int mfb_attention(const void* q, int ldq, const void* k, int ldk, con
         const uint64_t dims[3] = {uint64_t(ldvt), rows, uint64_t(B)};
         const uint64_t str[2] = {uint64_t(ldvt) * 2, rows * ldvt * 2};
         const uint32_t box[3] = {64, uint32_t(dpad), 1};
-        int rc = encode_tmap_bf16(&p.tmV, vt, 3, dims, str, box, true);
+        int rc = encode_tmap_bf16(&p.tmV, vt, 3, dims, str, box, 128);
         if (rc) return rc;
     }
     p.out = static_cast<__nv_bfloat16*>(out);

@@ -29,8 +29,9 @@ int device_sm_count();
     } while (0)
 
 // Encode a tiled bf16 tensor map (rank <= 5).  dims/box are innermost-first; strides_bytes has rank-1 entries
-// (stride of dims 1..rank-1).  swizzle128: CU_TENSOR_MAP_SWIZZLE_128B (inner box extent must be 64 elements).
+// (stride of dims 1..rank-1).  swizzle_bytes: 0 (none), 32, 64 or 128 — the inner box extent must span exactly
+// that many bytes (16 / 32 / 64 bf16 elements).
 int encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                     const uint32_t* box, bool swizzle128);
+                     const uint32_t* box, int swizzle_bytes);
 
 }  // namespace mfb

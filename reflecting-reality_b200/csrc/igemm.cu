@@ -45,6 +45,8 @@ struct IgemmSeg {
 struct IgemmParams {
     CUtensorMap tmA[4];
     CUtensorMap tmB;
+    CUtensorMap tmOut;     // output tile store  (box {EPI box cols, tw, th, tn}, 64B / 32B swizzle)
+    CUtensorMap tmRes;     // res1 tile load, same geometry
     IgemmSeg seg[MAX_SEG];
     int nseg;
     int M, N;              // GEMM rows (valid output pixels) and columns (rows of the packed weight)
@@ -68,13 +70,26 @@ struct IgemmCfg {
     static constexpr int A_BYTES = BM * BK * 2;
     static constexpr int B_BYTES = BN * BK * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    // epilogue staging tile: the bf16 output tile (and, before that, the res1 tile) as column blocks of BOXC
+    // columns x 128 rows, each block written/read by one TMA box with the 64B (BOXC 32) or 32B (BOXC 16) swizzle
+    static constexpr int BOXC = (BN % 32 == 0) ? 32 : 16;
+    static constexpr int STG_BYTES = BM * BN * 2;
     // persistent CTA, one per SM: as many operand stages as fit under the 227 KB limit (operand fetch is
     // L2-latency/bandwidth bound, so depth matters more than anything else here)
-    static constexpr int STAGES = (224 * 1024) / STAGE_BYTES > 8 ? 8 : (224 * 1024) / STAGE_BYTES;
+    static constexpr int STAGES = (224 * 1024 - STG_BYTES) / STAGE_BYTES > 8 ? 8 : (224 * 1024 - STG_BYTES) / STAGE_BYTES;
     static constexpr int ACC_COLS = BN <= 64 ? 64 : BN <= 128 ? 128 : 256;  // TMEM columns per accumulator slot
     static constexpr int TMEM_COLS = 2 * ACC_COLS;                           // double-buffered accumulator
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STG_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
+
+// byte offset of the 16-byte chunk holding columns [col, col+8) of row r inside the swizzled staging tile
+template <int BOXC>
+__device__ __forceinline__ uint32_t stg_off(int r, int col) {
+    const int blk = col / BOXC;
+    const int j = (col % BOXC) >> 3;
+    const int sw = BOXC == 32 ? ((r >> 1) & 3) : ((r >> 2) & 1);
+    return uint32_t(blk * (BM * BOXC * 2) + r * (BOXC * 2) + ((j ^ sw) << 4));
+}
 
 __device__ __forceinline__ void add_bf16x8(float (&f)[8], const uint4& rv) {
     float2 t;
@@ -108,12 +123,15 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 1) igemm_kernel(const __grid_co
     extern __shared__ uint8_t smem_raw[];
     // 1024-byte alignment is required by the 128B swizzle atoms
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    const uint32_t bar_base = smem_base + STAGES * Cfg::STAGE_BYTES;
+    const uint32_t stg_base = smem_base + STAGES * Cfg::STAGE_BYTES;
+    const uint32_t bar_base = stg_base + Cfg::STG_BYTES;
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
     auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
     auto tmem_full_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
     auto tmem_empty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
-    const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
+    const uint32_t res_full_bar = bar_base + 8u * (2 * STAGES + 4);
+    const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 5);
+    uint8_t* stg_gen = smem_raw + (stg_base - smem_u32(smem_raw));   // generic pointer to the staging tile
     uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
     const int warp = threadIdx.x >> 5;
@@ -127,6 +145,7 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 1) igemm_kernel(const __grid_co
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&p.tmB);
         prefetch_tmap(&p.tmA[0]);
+        prefetch_tmap(&p.tmOut);
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(full_bar(s), 1);
             mbar_init(empty_bar(s), 1);
@@ -135,6 +154,7 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 1) igemm_kernel(const __grid_co
             mbar_init(tmem_full_bar(a), 1);
             mbar_init(tmem_empty_bar(a), IGEMM_EPI_WARPS);
         }
+        mbar_init(res_full_bar, 1);
         fence_barrier_init();
     }
     if (warp == 1) {
@@ -202,64 +222,81 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 1) igemm_kernel(const __grid_co
         }
         __syncwarp();
     } else {
-        // ===== epilogue: warps 2..9.  TMEM lane quarter = warp % 4; the two warps of a quarter split the columns =====
+        // ===== epilogue: warps 2..9.  TMEM lane quarter = warp % 4; the two warps of a quarter split the columns.
+        // Per tile: (leader) wait until the previous tile's TMA store has drained the staging tile, TMA-load the res1
+        // tile into it -> every thread: accumulator row chunk from TMEM, + bias / row bias, x alpha, + res1 (read from
+        // the staging tile) + res2 -> bf16 back into the staging tile -> (leader) TMA store.  All global traffic of
+        // the epilogue except the rare res2 is therefore full-line TMA traffic, and M/N tails are clipped by TMA.
+        constexpr int BOXC = Cfg::BOXC;
         const int q = warp & 3;
         const int half = (warp - 2) >> 2;
+        const bool leader = (warp == 2 && lane == 0);
         const int r = q * 32 + lane;  // row of the tile == TMEM lane
         const int rw = r % p.tw;
         const int rh = (r / p.tw) % p.th;
         const int rn = r / (p.tw * p.th);
         const float alpha = p.alpha ? __ldg(p.alpha) : 1.0f;
+        const int bn_out = p.geglu ? BN / 2 : BN;      // output columns per tile
+        const int nbox = bn_out / BOXC;
         int li = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++li) {
             const int nt = tile % tiles_n, mt = tile / tiles_n;
-            const int ow = (mt % p.tiles_w) * p.tw + rw;
-            const int oh = ((mt / p.tiles_w) % p.tiles_h) * p.th + rh;
-            const int on = (mt / (p.tiles_w * p.tiles_h)) * p.tn + rn;
+            const int w0 = (mt % p.tiles_w) * p.tw;
+            const int h0 = ((mt / p.tiles_w) % p.tiles_h) * p.th;
+            const int n0 = (mt / (p.tiles_w * p.tiles_h)) * p.tn;
+            const int ow = w0 + rw, oh = h0 + rh, on = n0 + rn;
             const bool valid = (ow < p.Wo) && (oh < p.Ho) && (on < p.Bn);
             const long long m = (static_cast<long long>(on) * p.Ho + oh) * p.Wo + ow;
             const float* rb = p.rowbias ? p.rowbias + static_cast<long long>(valid ? on : 0) * p.rowbias_ld : nullptr;
+            if (leader) {
+                tma_store_wait_read();                 // previous tile's store no longer reads the staging tile
+                if (p.res1) {
+                    mbar_expect_tx(res_full_bar, uint32_t(nbox) * BM * BOXC * 2);
+                    for (int bx = 0; bx < nbox; ++bx)
+                        tma_load_4d(stg_base + bx * (BM * BOXC * 2), &p.tmRes, res_full_bar, nt * bn_out + bx * BOXC, w0, h0, n0);
+                }
+            }
+            __syncwarp();
+            named_bar_sync(1, IGEMM_EPI_WARPS * 32);   // staging tile is free (or being filled with res1)
             const int as = li & 1;
             mbar_wait(tmem_full_bar(as), (li >> 1) & 1);
+            if (p.res1) mbar_wait(res_full_bar, li & 1);
             tc_fence_after();
             const uint32_t trow = tmem_base + as * Cfg::ACC_COLS + (uint32_t(q * 32) << 16);
 
             if (!p.geglu) {
                 constexpr int NCH = BN / 16;                 // 16-column chunks; warp `half` 0 takes the first ceil(NCH/2)
-                const int c_begin = half ? (NCH + 1) / 2 : 0;
-                const int c_end = half ? NCH : (NCH + 1) / 2;
-#pragma unroll 1
-                for (int c = c_begin; c < c_end; ++c) {
-                    const int col = c * 16;
-                    const int n = nt * BN + col;
-                    const bool do0 = valid && (n < p.N), do1 = valid && (n + 8 < p.N);
-                    // issue the residual loads first so they are in flight while the accumulator is fetched
-                    uint4 r1a = make_uint4(0, 0, 0, 0), r1b = r1a, r2a = r1a, r2b = r1a;
-                    if (p.res1) {
-                        if (do0) r1a = __ldg(reinterpret_cast<const uint4*>(p.res1 + m * p.out_ld + n));
-                        if (do1) r1b = __ldg(reinterpret_cast<const uint4*>(p.res1 + m * p.out_ld + n + 8));
-                    }
-                    if (p.res2) {
-                        if (do0) r2a = __ldg(reinterpret_cast<const uint4*>(p.res2 + m * p.out_ld + n));
-                        if (do1) r2b = __ldg(reinterpret_cast<const uint4*>(p.res2 + m * p.out_ld + n + 8));
-                    }
-                    uint32_t v[16];
-                    tmem_ld16(trow + col, v);
-                    tmem_wait_ld();
+                constexpr int MAXC = (NCH + 1) / 2;
+                const int c_begin = half ? MAXC : 0;
+                const int c_cnt = half ? NCH - MAXC : MAXC;
+                // fetch this warp's whole accumulator slice with back-to-back tcgen05.ld and ONE wait
+                uint32_t v[MAXC][16];
 #pragma unroll
-                    for (int j = 0; j < 2; ++j) {
-                        if (j == 0 ? do0 : do1) {
+                for (int i = 0; i < MAXC; ++i)
+                    if (i < c_cnt) tmem_ld16(trow + (c_begin + i) * 16, v[i]);
+                tmem_wait_ld();
+#pragma unroll
+                for (int i = 0; i < MAXC; ++i) {
+                    if (i < c_cnt) {
+                        const int col = (c_begin + i) * 16;
+                        const int n = nt * BN + col;
+#pragma unroll
+                        for (int j = 0; j < 2; ++j) {
                             const int nn = n + j * 8;
+                            uint4* sp = reinterpret_cast<uint4*>(stg_gen + stg_off<BOXC>(r, col + j * 8));
                             float f[8];
 #pragma unroll
-                            for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[j * 8 + e]);
-                            if (p.bias) add_f32x8(f, p.bias + nn);
-                            if (rb) add_f32x8(f, rb + nn);
+                            for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[i][j * 8 + e]);
+                            if (nn < p.N) {
+                                if (p.bias) add_f32x8(f, p.bias + nn);
+                                if (rb) add_f32x8(f, rb + nn);
+                            }
 #pragma unroll
                             for (int e = 0; e < 8; ++e) f[e] *= alpha;
-                            if (p.res1) add_bf16x8(f, j == 0 ? r1a : r1b);
-                            if (p.res2) add_bf16x8(f, j == 0 ? r2a : r2b);
-                            *reinterpret_cast<uint4*>(p.out + m * p.out_ld + nn) = pack_bf16x8(f);
+                            if (p.res1) add_bf16x8(f, *sp);
+                            if (p.res2 && valid && nn < p.N)   // rare (tap sites): straight from global
+                                add_bf16x8(f, __ldg(reinterpret_cast<const uint4*>(p.res2 + m * p.out_ld + nn)));
+                            *sp = pack_bf16x8(f);
                         }
                     }
                 }
@@ -274,24 +311,21 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 1) igemm_kernel(const __grid_co
                         tmem_ld16(trow + 64 + col, g);
                         tmem_wait_ld();
                         const int pv = nt * BN + col;          // packed column of the value
-                        const int ncol = nt * 64 + col;        // output column
 #pragma unroll
                         for (int j = 0; j < 2; ++j) {
-                            if (valid && pv + j * 8 < p.N) {
-                                float f[8], gt[8];
+                            float f[8], gt[8];
 #pragma unroll
-                                for (int e = 0; e < 8; ++e) {
-                                    f[e] = __uint_as_float(v[j * 8 + e]);
-                                    gt[e] = __uint_as_float(g[j * 8 + e]);
-                                }
-                                if (p.bias) {
-                                    add_f32x8(f, p.bias + pv + j * 8);
-                                    add_f32x8(gt, p.bias + pv + 64 + j * 8);
-                                }
-#pragma unroll
-                                for (int e = 0; e < 8; ++e) f[e] *= gelu_erf_f(gt[e]);
-                                *reinterpret_cast<uint4*>(p.out + m * p.out_ld + ncol + j * 8) = pack_bf16x8(f);
+                            for (int e = 0; e < 8; ++e) {
+                                f[e] = __uint_as_float(v[j * 8 + e]);
+                                gt[e] = __uint_as_float(g[j * 8 + e]);
                             }
+                            if (p.bias && pv + j * 8 < p.N) {
+                                add_f32x8(f, p.bias + pv + j * 8);
+                                add_f32x8(gt, p.bias + pv + 64 + j * 8);
+                            }
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) f[e] *= gelu_erf_f(gt[e]);
+                            *reinterpret_cast<uint4*>(stg_gen + stg_off<BOXC>(r, col + j * 8)) = pack_bf16x8(f);
                         }
                     }
                 }
@@ -300,7 +334,16 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 1) igemm_kernel(const __grid_co
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tmem_empty_bar(as));
+            fence_proxy_async_smem();                  // generic-proxy writes of the staging tile -> visible to TMA
+            named_bar_sync(1, IGEMM_EPI_WARPS * 32);
+            if (leader) {
+                for (int bx = 0; bx < nbox; ++bx)
+                    tma_store_4d(&p.tmOut, stg_base + bx * (BM * BOXC * 2), nt * bn_out + bx * BOXC, w0, h0, n0);
+                tma_store_commit();
+            }
+            __syncwarp();
         }
+        if (leader) tma_store_wait_all();              // the stores must have landed before the kernel ends
     }
 
     tc_fence_before();
@@ -384,7 +427,7 @@ extern "C" int mfb_conv_plan_create(const mfb_conv_desc* d, mfb_plan** out) {
     if (d->stride == 1) {
         const uint64_t dims[4] = {uint64_t(d->Cin), uint64_t(W), uint64_t(H), uint64_t(B)};
         const uint64_t str[3] = {uint64_t(d->Cin) * 2, uint64_t(W) * d->Cin * 2, uint64_t(H) * W * d->Cin * 2};
-        rc = encode_tmap_bf16(&p.tmA[0], d->x, 4, dims, str, box, true);
+        rc = encode_tmap_bf16(&p.tmA[0], d->x, 4, dims, str, box, 128);
         if (rc) { delete pl; return rc; }
         const int r = d->ksize / 2;
         for (int kh = -r; kh <= r; ++kh)
@@ -399,7 +442,7 @@ extern "C" int mfb_conv_plan_create(const mfb_conv_desc* d, mfb_plan** out) {
                 const uint64_t dims[4] = {uint64_t(d->Cin), uint64_t((W - pw + 1) / 2), uint64_t((H - ph + 1) / 2), uint64_t(B)};
                 const uint64_t str[3] = {uint64_t(d->Cin) * 4, uint64_t(W) * d->Cin * 4, uint64_t(H) * W * d->Cin * 2};
                 const char* base = static_cast<const char*>(d->x) + (size_t(ph) * W + pw) * d->Cin * 2;
-                rc = encode_tmap_bf16(&p.tmA[ph * 2 + pw], base, 4, dims, str, box, true);
+                rc = encode_tmap_bf16(&p.tmA[ph * 2 + pw], base, 4, dims, str, box, 128);
                 if (rc) { delete pl; return rc; }
             }
         // input row = 2*oh + kh - 1:  kh=0 -> (parity 1, h2 = oh-1); kh=1 -> (0, oh); kh=2 -> (1, oh)
@@ -415,7 +458,7 @@ extern "C" int mfb_conv_plan_create(const mfb_conv_desc* d, mfb_plan** out) {
         const int C = d->extra_C[e];
         const uint64_t dims[4] = {uint64_t(C), uint64_t(Wo), uint64_t(Ho), uint64_t(B)};
         const uint64_t str[3] = {uint64_t(C) * 2, uint64_t(Wo) * C * 2, uint64_t(Ho) * Wo * C * 2};
-        rc = encode_tmap_bf16(&p.tmA[1 + e], d->extra_x[e], 4, dims, str, box, true);
+        rc = encode_tmap_bf16(&p.tmA[1 + e], d->extra_x[e], 4, dims, str, box, 128);
         if (rc) { delete pl; return rc; }
         p.seg[nseg++] = IgemmSeg{1 + e, 0, 0, 0, C / 64};
         ktot += C;
@@ -440,8 +483,21 @@ extern "C" int mfb_conv_plan_create(const mfb_conv_desc* d, mfb_plan** out) {
         const uint64_t dims[2] = {uint64_t(ktot), uint64_t(d->Cout)};
         const uint64_t str[1] = {uint64_t(ktot) * 2};
         const uint32_t bbox[2] = {64u, uint32_t(bn)};
-        rc = encode_tmap_bf16(&p.tmB, d->w, 2, dims, str, bbox, true);
+        rc = encode_tmap_bf16(&p.tmB, d->w, 2, dims, str, bbox, 128);
         if (rc) { delete pl; return rc; }
+    }
+    {
+        const int boxc = (bn % 32 == 0) ? 32 : 16;
+        const int out_ld = d->geglu ? d->Cout / 2 : d->Cout;
+        const uint64_t dims[4] = {uint64_t(out_ld), uint64_t(Wo), uint64_t(Ho), uint64_t(B)};
+        const uint64_t str[3] = {uint64_t(out_ld) * 2, uint64_t(Wo) * out_ld * 2, uint64_t(Ho) * Wo * out_ld * 2};
+        const uint32_t obox[4] = {uint32_t(boxc), uint32_t(p.tw), uint32_t(p.th), uint32_t(p.tn)};
+        rc = encode_tmap_bf16(&p.tmOut, d->out, 4, dims, str, obox, boxc * 2);
+        if (rc) { delete pl; return rc; }
+        if (d->res1) {
+            rc = encode_tmap_bf16(&p.tmRes, d->res1, 4, dims, str, obox, boxc * 2);
+            if (rc) { delete pl; return rc; }
+        }
     }
     p.bias = d->bias;
     p.rowbias = d->rowbias;
