@@ -2,10 +2,10 @@
 // AttnProcessor2_0.__call__, S/models/attention_processor.py:1266-1268; no mask, non-causal).
 //
 // One CTA = one 128-query tile of one (batch, head).  Per 128-key tile:
-//   warp0 (TMA)     : K tile [128 keys x d] and V^T tile [d x 128 keys] -> swizzled smem ring
-//   warp1 (MMA)     : S = Q K^T  (M128 N128, K = d in 16-steps)  -> TMEM cols [0,128)
+//   warp4 (TMA)     : K tile [128 keys x d] and V^T tile [d x 128 keys] -> swizzled smem ring
+//   warp5 (MMA)     : S = Q K^T  (M128 N128, K = d in 16-steps)  -> TMEM cols [0,128)
 //                     O += P V   (M128 N=dpad, K = 128 keys)     -> TMEM cols [128,128+dpad)
-//   warps2-5 (128 t): thread = query row: tcgen05.ld S row, online softmax in the exp2 domain with lazy
+//   warps0-3 (128 t): thread = query row: tcgen05.ld S row, online softmax in the exp2 domain with lazy
 //                     (threshold 2^8) rescaling of O in TMEM, P -> bf16 -> smem in the K-major 128B-swizzled
 //                     layout the PV MMA reads, final O / l -> bf16 global.
 // Head dims 40/80/160 are not multiples of 64: Q/K boxes are 64 columns wide starting at h*d, the MMA K extent
@@ -77,7 +77,7 @@ __global__ void __launch_bounds__(ATT_THREADS, (D <= 40) ? 2 : 1) attention_kern
     const int ntiles = (p.Tk + BKV - 1) / BKV;
     constexpr bool kZeroPad = (D % 16) != 0;
 
-    if (warp == 0 && lane == 0) {
+    if (warp == 4 && lane == 0) {
         prefetch_tmap(&p.tmQ);
         prefetch_tmap(&p.tmK);
         prefetch_tmap(&p.tmV);
@@ -89,7 +89,7 @@ __global__ void __launch_bounds__(ATT_THREADS, (D <= 40) ? 2 : 1) attention_kern
         for (int s = 0; s < STAGES; ++s) { mbar_init(kv_full(s), 1); mbar_init(kv_empty(s), 1); }
         fence_barrier_init();
     }
-    if (warp == 1) {
+    if (warp == 5) {
         tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
         tmem_relinquish();
     }
@@ -98,7 +98,9 @@ __global__ void __launch_bounds__(ATT_THREADS, (D <= 40) ? 2 : 1) attention_kern
     tc_fence_after();
     const uint32_t tmem_base = *reinterpret_cast<uint32_t*>(gen_base + (tmem_slot - base));
 
-    if (warp == 0) {
+    // warps 0-3 = softmax (TMEM lane quarter = warp), warp 4 = TMA, warp 5 = MMA: the single-thread issuers get the
+    // highest warp ids so the arbiter never lets softmax warps starve them
+    if (warp == 4) {
         if (lane == 0) {
             // ===== TMA producer =====
             mbar_expect_tx(q_full, Cfg::Q_BYTES);
@@ -116,7 +118,7 @@ __global__ void __launch_bounds__(ATT_THREADS, (D <= 40) ? 2 : 1) attention_kern
             }
         }
         __syncwarp();
-    } else if (warp == 1) {
+    } else if (warp == 5) {
         if (lane == 0) {
             // ===== MMA issuer =====
             constexpr uint32_t idesc_qk = make_idesc_bf16(128, BKV);
@@ -172,7 +174,7 @@ __global__ void __launch_bounds__(ATT_THREADS, (D <= 40) ? 2 : 1) attention_kern
         }
         float m_used = -INFINITY, l = 0.f;
         for (int j = 0; j < ntiles; ++j) {
-            mbar_wait(s_full, j & 1);
+            mbar_wait_relaxed(s_full, j & 1);
             tc_fence_after();
             uint32_t sv[4][32];
             tmem_ld32(tS + 0, sv[0]);
@@ -198,7 +200,7 @@ __global__ void __launch_bounds__(ATT_THREADS, (D <= 40) ? 2 : 1) attention_kern
                 m_used = mx;
             }
             if (j > 0) {
-                mbar_wait(o_full, (j - 1) & 1);  // PV(j-1) finished: P buffer free, O stable
+                mbar_wait_relaxed(o_full, (j - 1) & 1);  // PV(j-1) finished: P buffer free, O stable
                 tc_fence_after();
                 if (__any_sync(0xffffffffu, alpha != 1.f)) {
 #pragma unroll
@@ -269,7 +271,7 @@ __global__ void __launch_bounds__(ATT_THREADS, (D <= 40) ? 2 : 1) attention_kern
         tc_fence_before();
     }
     __syncthreads();
-    if (warp == 1) {
+    if (warp == 5) {
         tc_fence_after();
         tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
     }

@@ -14,8 +14,8 @@
 // operand layout, so no im2col buffer and no register staging exists anywhere.  Extra 1x1 segments let one
 // accumulator also absorb the ResnetBlock2D 1x1 shortcut over the (concatenated) block input — the skip concat
 // (unet_2d_blocks.py:2586,2728) is just two segments — and stride-2 convs read four parity views of the input.
-// Warp roles: warp0 = TMA producer, warp1 = TMEM allocator + single-thread tcgen05.mma issuer, warps 2-5 =
-// epilogue (tcgen05.ld -> +bias +timestep-embedding row bias, xalpha, +residual(s) / GEGLU -> bf16 NHWC store).
+// Warp roles: warps 0-7 = epilogue, warp 8 = TMA producer, warp 9 = TMEM allocator + single-thread tcgen05.mma issuer
+// (epilogue (tcgen05.ld -> +bias +timestep-embedding row bias, xalpha, +residual(s) / GEGLU -> bf16 NHWC store).
 // Two CTAs are co-resident per SM (<=113 KB smem, <=256 TMEM columns each), so one CTA's epilogue overlaps the
 // other's main loop.
 #include <stdarg.h>
@@ -43,7 +43,7 @@ struct IgemmSeg {
 };
 
 struct IgemmParams {
-    CUtensorMap tmA[4];
+    CUtensorMap tmA[7];    // stride 1: [0] = conv input, [1..3] = extra 1x1 sources; stride 2: [0..3] = parity views, [4..6] = extras
     CUtensorMap tmB;
     CUtensorMap tmOut;     // output tile store  (box {EPI box cols, tw, th, tn}, 64B / 32B swizzle)
     CUtensorMap tmRes;     // res1 tile load, same geometry
@@ -142,7 +142,7 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 1) igemm_kernel(const __grid_co
     int total_kb = 0;
     for (int s = 0; s < p.nseg; ++s) total_kb += p.seg[s].cblocks;
 
-    if (warp == 0 && lane == 0) {
+    if (warp == IGEMM_EPI_WARPS && lane == 0) {
         prefetch_tmap(&p.tmB);
         prefetch_tmap(&p.tmA[0]);
         prefetch_tmap(&p.tmOut);
@@ -157,7 +157,7 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 1) igemm_kernel(const __grid_co
         mbar_init(res_full_bar, 1);
         fence_barrier_init();
     }
-    if (warp == 1) {
+    if (warp == IGEMM_EPI_WARPS + 1) {
         tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
         tmem_relinquish();
     }
@@ -166,7 +166,9 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 1) igemm_kernel(const __grid_co
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
 
-    if (warp == 0) {
+    // Warp roles: the two single-thread issuers sit in the HIGHEST warp ids (8 = TMA, 9 = MMA): the sub-partition
+    // arbiter favours higher warp ids, so epilogue warps can never starve them.
+    if (warp == IGEMM_EPI_WARPS) {
         if (lane == 0) {
             // ===== TMA producer =====
             int it = 0;
@@ -192,7 +194,7 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 1) igemm_kernel(const __grid_co
             }
         }
         __syncwarp();
-    } else if (warp == 1) {
+    } else if (warp == IGEMM_EPI_WARPS + 1) {
         if (lane == 0) {
             // ===== MMA issuer =====
             constexpr uint32_t idesc = make_idesc_bf16(BM, BN);
@@ -222,15 +224,15 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 1) igemm_kernel(const __grid_co
         }
         __syncwarp();
     } else {
-        // ===== epilogue: warps 2..9.  TMEM lane quarter = warp % 4; the two warps of a quarter split the columns.
+        // ===== epilogue: warps 0..7.  TMEM lane quarter = warp % 4; the two warps of a quarter split the columns.
         // Per tile: (leader) wait until the previous tile's TMA store has drained the staging tile, TMA-load the res1
         // tile into it -> every thread: accumulator row chunk from TMEM, + bias / row bias, x alpha, + res1 (read from
         // the staging tile) + res2 -> bf16 back into the staging tile -> (leader) TMA store.  All global traffic of
         // the epilogue except the rare res2 is therefore full-line TMA traffic, and M/N tails are clipped by TMA.
         constexpr int BOXC = Cfg::BOXC;
         const int q = warp & 3;
-        const int half = (warp - 2) >> 2;
-        const bool leader = (warp == 2 && lane == 0);
+        const int half = warp >> 2;
+        const bool leader = (warp == 0 && lane == 0);
         const int r = q * 32 + lane;  // row of the tile == TMEM lane
         const int rw = r % p.tw;
         const int rh = (r / p.tw) % p.th;
@@ -259,8 +261,8 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 1) igemm_kernel(const __grid_co
             __syncwarp();
             named_bar_sync(1, IGEMM_EPI_WARPS * 32);   // staging tile is free (or being filled with res1)
             const int as = li & 1;
-            mbar_wait(tmem_full_bar(as), (li >> 1) & 1);
-            if (p.res1) mbar_wait(res_full_bar, li & 1);
+            mbar_wait_relaxed(tmem_full_bar(as), (li >> 1) & 1);
+            if (p.res1) mbar_wait_relaxed(res_full_bar, li & 1);
             tc_fence_after();
             const uint32_t trow = tmem_base + as * Cfg::ACC_COLS + (uint32_t(q * 32) << 16);
 
@@ -348,7 +350,7 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 1) igemm_kernel(const __grid_co
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) {
+    if (warp == IGEMM_EPI_WARPS + 1) {
         tc_fence_after();
         tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
     }
@@ -403,7 +405,6 @@ extern "C" int mfb_conv_plan_create(const mfb_conv_desc* d, mfb_plan** out) {
     MFB_REQUIRE(d->Cin > 0 && d->Cin % 64 == 0, "Cin must be a positive multiple of 64 (got %d)", d->Cin);
     MFB_REQUIRE(d->Cout > 0 && d->Cout % 8 == 0, "Cout must be a multiple of 8 (got %d)", d->Cout);
     MFB_REQUIRE(d->n_extra >= 0 && d->n_extra <= 3, "at most 3 extra 1x1 segments");
-    MFB_REQUIRE(d->stride == 1 || d->n_extra == 0, "extra segments are not supported with stride 2");
     MFB_REQUIRE(d->x && d->w && d->out, "x / w / out must be device pointers");
     MFB_REQUIRE(!d->geglu || (d->Cout % 128 == 0 && !d->res1 && !d->res2 && !d->rowbias), "geglu needs Cout %% 128 == 0 and no residuals");
 
@@ -458,9 +459,10 @@ extern "C" int mfb_conv_plan_create(const mfb_conv_desc* d, mfb_plan** out) {
         const int C = d->extra_C[e];
         const uint64_t dims[4] = {uint64_t(C), uint64_t(Wo), uint64_t(Ho), uint64_t(B)};
         const uint64_t str[3] = {uint64_t(C) * 2, uint64_t(Wo) * C * 2, uint64_t(Ho) * Wo * C * 2};
-        rc = encode_tmap_bf16(&p.tmA[1 + e], d->extra_x[e], 4, dims, str, box, 128);
+        const int mi = (d->stride == 1 ? 1 : 4) + e;
+        rc = encode_tmap_bf16(&p.tmA[mi], d->extra_x[e], 4, dims, str, box, 128);
         if (rc) { delete pl; return rc; }
-        p.seg[nseg++] = IgemmSeg{1 + e, 0, 0, 0, C / 64};
+        p.seg[nseg++] = IgemmSeg{mi, 0, 0, 0, C / 64};
         ktot += C;
     }
     p.nseg = nseg;

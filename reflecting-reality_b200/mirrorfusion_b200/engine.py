@@ -39,6 +39,8 @@ class _Net:
         self._scratch: Dict[Tuple, torch.Tensor] = {}
         self.flops = 0.0
         self.launches = 0
+        # fused BrushNet taps: (packed weight, column offset, C, zero-conv weight [C,C] f32, bias buffer, base bias, zero-conv bias)
+        self.fused_taps: List[Tuple] = []
         G = cfg.norm_num_groups
         self.gn_ws = torch.zeros(B * G * 2, device=device, dtype=f32)
         ops.lib()
@@ -57,6 +59,17 @@ class _Net:
 
     def wf(self, name: str) -> torch.Tensor:
         return self.sd[name].contiguous()
+
+    # ---- BrushNet tap folded into the consuming GEMM as one more K-segment:
+    #      out += s * (Wz . h_brushnet + bz)   (brushnet.py:832-834,904-906 + the tap add sites)
+    def _register_fused(self, wp, koff, wz, bias_buf, base_bias, bz):
+        self.fused_taps.append((wp, koff, wz.shape[1], wz, bias_buf, base_bias, bz))
+
+    def set_tap_scale(self, s: float):
+        """Re-scale the fused zero-conv K-segments in place (descriptors keep pointing at the same buffers)."""
+        for wp, koff, c, wz, bias_buf, base_bias, bz in self.fused_taps:
+            wp[:, koff:koff + c].copy_((wz * s).to(bf16))
+            bias_buf.copy_(base_bias + s * bz)
 
     # ---- op emitters
     def emit(self, fn: Callable[[], None], n_launch: int = 1, tag: str = "misc", flops: float = 0.0):
@@ -104,7 +117,7 @@ class _Net:
         self.emit(lambda: ops.linear_small(emb, wcat, bcat, self.rowbias, act_in=True))
 
     # ---- ResnetBlock2D (resnet.py:329-405)
-    def resnet(self, p: str, xa, xb, HW_hw: Tuple[int, int], cout: int, tap=None):
+    def resnet(self, p: str, xa, xb, HW_hw: Tuple[int, int], cout: int, tap=None, tap_src=None):
         h, w = HW_hw
         HW = h * w
         B = self.B
@@ -124,40 +137,59 @@ class _Net:
         self.groupnorm(h1, None, p + ".norm2", n2, HW, eps, True)
         out = self.buf(B, HW, cout)
         bias = self.sd[p + ".conv2.bias"].clone()
+        wmain = self.sd[p + ".conv2.weight"]
+        extras_w: list = []
+        extras_x: list = []
+        res1 = None
         if p + ".conv_shortcut.weight" in self.sd:
             ws = self.sd[p + ".conv_shortcut.weight"][:, :, 0, 0]
-            extras_w = [ws[:, :ca]] + ([ws[:, ca:]] if cb else [])
-            extras_x = [xa] + ([xb] if cb else [])
-            w2 = ops.pack_conv_weight(self.sd[p + ".conv2.weight"], extras=extras_w)
+            extras_w += [ws[:, :ca]] + ([ws[:, ca:]] if cb else [])
+            extras_x += [xa] + ([xb] if cb else [])
             bias = bias + self.sd[p + ".conv_shortcut.bias"]
-            res1 = None
         else:
             assert cb == 0 and ca == cout
-            w2 = ops.pack_conv_weight(self.sd[p + ".conv2.weight"])
-            extras_x = []
             res1 = xa
+        fused = None
+        if tap_src is not None:
+            koff = 9 * cout + sum(e.shape[1] for e in extras_w)
+            extras_w.append(tap_src[1]); extras_x.append(tap_src[0])
+            fused = (koff, tap_src[1], tap_src[2])
+        w2 = ops.pack_conv_weight(wmain, extras=extras_w)
+        base_bias = bias.contiguous()
+        bias_buf = base_bias.clone()
+        if fused is not None:
+            self._register_fused(w2, fused[0], fused[1], bias_buf, base_bias, fused[2])
         self.emit_plan(ops.ConvPlan(n2, w2, out, B=B, H=h, W=w, Cin=cout, Cout=cout, ksize=3, extras=extras_x,
-                                    bias=bias.contiguous(), res1=res1, res2=tap))
+                                    bias=bias_buf, res1=res1, res2=tap))
         return out
 
-    def downsample(self, p: str, x, hw, tap=None):
+    def _sampler_conv(self, p: str, x, out, h, w, stride, tap, tap_src):
+        c = x.shape[-1]
+        extras_w, extras_x = [], []
+        if tap_src is not None:
+            extras_w.append(tap_src[1]); extras_x.append(tap_src[0])
+        wp = ops.pack_conv_weight(self.sd[p + ".conv.weight"], extras=extras_w)
+        base_bias = self.wf(p + ".conv.bias")
+        bias_buf = base_bias.clone()
+        if tap_src is not None:
+            self._register_fused(wp, 9 * c, tap_src[1], bias_buf, base_bias, tap_src[2])
+        self.emit_plan(ops.ConvPlan(x, wp, out, B=self.B, H=h, W=w, Cin=c, Cout=c, ksize=3, stride=stride, extras=extras_x,
+                                    bias=bias_buf, res2=tap))
+
+    def downsample(self, p: str, x, hw, tap=None, tap_src=None):
         h, w = hw
         c = x.shape[-1]
         out = self.buf(self.B, (h // 2) * (w // 2), c)
-        wp = ops.pack_conv_weight(self.sd[p + ".conv.weight"])
-        self.emit_plan(ops.ConvPlan(x, wp, out, B=self.B, H=h, W=w, Cin=c, Cout=c, ksize=3, stride=2,
-                                    bias=self.wf(p + ".conv.bias"), res2=tap))
+        self._sampler_conv(p, x, out, h, w, 2, tap, tap_src)
         return out
 
-    def upsample(self, p: str, x, hw, tap=None):
+    def upsample(self, p: str, x, hw, tap=None, tap_src=None):
         h, w = hw
         c = x.shape[-1]
         up = self.scratch("up", self.B, 4 * h * w, c)
         self.emit(lambda: ops.upsample2x(x, up, B=self.B, H=h, W=w))
         out = self.buf(self.B, 4 * h * w, c)
-        wp = ops.pack_conv_weight(self.sd[p + ".conv.weight"])
-        self.emit_plan(ops.ConvPlan(up, wp, out, B=self.B, H=2 * h, W=2 * w, Cin=c, Cout=c, ksize=3,
-                                    bias=self.wf(p + ".conv.bias"), res2=tap))
+        self._sampler_conv(p, up, out, 2 * h, 2 * w, 1, tap, tap_src)
         return out
 
     def run(self):
@@ -199,7 +231,10 @@ class BrushNetEngine(_Net):
     """BrushNetModel.forward on the kernels: conv_in_condition over [latent || cond], resnet-only down/mid/up,
     28 zero-conv taps scaled by conditioning_scale (a device scalar, so the captured graph serves any scale)."""
 
-    def __init__(self, cfg, sd, B, H, W, device, tap_bufs: Optional[List[torch.Tensor]] = None):
+    def __init__(self, cfg, sd, B, H, W, device, tap_bufs: Optional[List[torch.Tensor]] = None,
+                 only_first_tap: bool = False):
+        """only_first_tap: fused pipeline mode — only the conv_in-site tap is materialised; the other 27 zero-convs
+        are handed to the UNet engine as (feature, weight, bias) and run there as K-segments of the consuming GEMM."""
         super().__init__(cfg, sd, B, H, W, device, "brushnet")
         boc = cfg.block_out_channels
         n = len(boc)
@@ -245,7 +280,11 @@ class BrushNetEngine(_Net):
                 [f"brushnet_up_blocks.{k}" for k in range(len(up_feats))]
         self.taps: List[torch.Tensor] = []
         self.tap_hw: List[Tuple[int, int]] = []
+        self.tap_sources = [(src, self.sd[nm + ".weight"][:, :, 0, 0].contiguous(), self.wf(nm + ".bias"))
+                            for (src, _), nm in zip(srcs, names)]
         for k, ((src, shw), nm) in enumerate(zip(srcs, names)):
+            if only_first_tap and k > 0:
+                break
             c = src.shape[-1]
             t = tap_bufs[k] if tap_bufs is not None else self.buf(B, shw[0] * shw[1], c)
             wz = ops.pack_conv_weight(self.sd[nm + ".weight"])
@@ -259,7 +298,10 @@ class BrushNetEngine(_Net):
 class UNetEngine(_Net):
     """UNet2DConditionModel.forward (SD1.5 family) with the BrushNet taps consumed in the producing epilogues."""
 
-    def __init__(self, cfg, sd, B, H, W, device, ctx_len: int = 77):
+    def __init__(self, cfg, sd, B, H, W, device, ctx_len: int = 77, tap_sources: Optional[List[Tuple]] = None,
+                 tap0: Optional[torch.Tensor] = None):
+        """tap_sources (fused pipeline mode): the BrushNet engine's 28 (feature, zero-conv weight, bias) triples; taps
+        1..27 then run as K-segments of the consuming GEMMs and only tap 0 (conv_in site) is read as a tensor."""
         super().__init__(cfg, sd, B, H, W, device, "unet")
         boc = cfg.block_out_channels
         n = len(boc)
@@ -287,9 +329,14 @@ class UNetEngine(_Net):
                 hw = (hw[0] * 2, hw[1] * 2)
                 self.tap_hw.append(hw)
         chans = dch + [mch] + uch
-        self.taps = [self.buf(B, h_ * w_, c) for (h_, w_), c in zip(self.tap_hw, chans)]
         self.n_down = len(dch)
-        tap_it = iter(self.taps)
+        if tap_sources is None:
+            self.taps = [self.buf(B, h_ * w_, c) for (h_, w_), c in zip(self.tap_hw, chans)]
+            tap_it = iter([(t, None) for t in self.taps])
+        else:
+            assert tap0 is not None and len(tap_sources) == len(chans)
+            self.taps = [tap0]
+            tap_it = iter([(tap0, None)] + [(None, src) for src in tap_sources[1:]])
 
         self.build_time_path(_resnet_prefixes(cfg))
         wci = self.sd["conv_in.weight"].permute(2, 3, 1, 0).contiguous()
@@ -298,38 +345,41 @@ class UNetEngine(_Net):
         hw = (H, W)
         pre = self.buf(B, H * W, boc[0])      # first skip keeps the PRE-tap conv_in output (unet_2d_condition.py:1215-1218)
         x = self.buf(B, H * W, boc[0])
-        tap0 = next(tap_it)
+        tap0, _ = next(tap_it)
         self.emit(lambda x0=x: ops.conv_in(self.sample_in, None, wci, bci, pre, tap0, x0))  # bind now: `x` is reassigned below
         skips = [(pre, hw)]
         for i in range(n):
             for j in range(cfg.layers_per_block):
-                tap = next(tap_it)
+                tap, tsrc = next(tap_it)
                 if cfg.down_has_attn[i]:
                     x = self.resnet(f"down_blocks.{i}.resnets.{j}", x, None, hw, boc[i])
-                    x = self.transformer(f"down_blocks.{i}.attentions.{j}", x, hw, tap)
+                    x = self.transformer(f"down_blocks.{i}.attentions.{j}", x, hw, tap, tsrc)
                 else:
-                    x = self.resnet(f"down_blocks.{i}.resnets.{j}", x, None, hw, boc[i], tap=tap)
+                    x = self.resnet(f"down_blocks.{i}.resnets.{j}", x, None, hw, boc[i], tap=tap, tap_src=tsrc)
                 skips.append((x, hw))
             if i != n - 1:
-                x = self.downsample(f"down_blocks.{i}.downsamplers.0", x, hw, tap=next(tap_it))
+                tap, tsrc = next(tap_it)
+                x = self.downsample(f"down_blocks.{i}.downsamplers.0", x, hw, tap=tap, tap_src=tsrc)
                 hw = (hw[0] // 2, hw[1] // 2)
                 skips.append((x, hw))
         # mid (UNetMidBlock2DCrossAttn unet_2d_blocks.py:850-899) + mid tap (unet_2d_condition.py:1288-1289)
         x = self.resnet("mid_block.resnets.0", x, None, hw, boc[-1])
-        x = self.transformer("mid_block.attentions.0", x, hw, None)
-        x = self.resnet("mid_block.resnets.1", x, None, hw, boc[-1], tap=next(tap_it))
+        x = self.transformer("mid_block.attentions.0", x, hw, None, None)
+        tap, tsrc = next(tap_it)
+        x = self.resnet("mid_block.resnets.1", x, None, hw, boc[-1], tap=tap, tap_src=tsrc)
         for i, layers in enumerate(up_block_channels(cfg)):
             for j, (_cin, _hid, _skip, cout) in enumerate(layers):
                 s, shw = skips.pop()
                 assert shw == hw
-                tap = next(tap_it)
+                tap, tsrc = next(tap_it)
                 if cfg.up_has_attn[i]:
                     x = self.resnet(f"up_blocks.{i}.resnets.{j}", x, s, hw, cout)
-                    x = self.transformer(f"up_blocks.{i}.attentions.{j}", x, hw, tap)
+                    x = self.transformer(f"up_blocks.{i}.attentions.{j}", x, hw, tap, tsrc)
                 else:
-                    x = self.resnet(f"up_blocks.{i}.resnets.{j}", x, s, hw, cout, tap=tap)
+                    x = self.resnet(f"up_blocks.{i}.resnets.{j}", x, s, hw, cout, tap=tap, tap_src=tsrc)
             if i != n - 1:
-                x = self.upsample(f"up_blocks.{i}.upsamplers.0", x, hw, tap=next(tap_it))
+                tap, tsrc = next(tap_it)
+                x = self.upsample(f"up_blocks.{i}.upsamplers.0", x, hw, tap=tap, tap_src=tsrc)
                 hw = (hw[0] * 2, hw[1] * 2)
         # conv_norm_out -> SiLU -> conv_out (unet_2d_condition.py:1336-1339)
         nout = self.scratch("n1", B, H * W, boc[0])
@@ -340,7 +390,7 @@ class UNetEngine(_Net):
         self.emit(lambda: ops.conv_out(nout, wco, bco, self.out, B=B, H=H, W=W))  # nout/wco/bco are not rebound
 
     # Transformer2DModel + BasicTransformerBlock (transformer_2d.py:334-430, attention.py:291-412)
-    def transformer(self, p: str, x, hw, tap):
+    def transformer(self, p: str, x, hw, tap, tap_src=None):
         B, cfg = self.B, self.cfg
         h, w = hw
         T = h * w
@@ -401,8 +451,15 @@ class UNetEngine(_Net):
                                        bias=self.wf(t + ".ff.net.2.bias"), res1=h2))
         # --- proj_out + transformer residual (+ BrushNet tap, added after the attention: unet_2d_blocks.py:1374-1389)
         out = self.buf(B, T, C)
-        self.emit_plan(ops.linear_plan(h3, ops.pack_conv_weight(self.sd[p + ".proj_out.weight"]), out.view(M, C),
-                                       bias=self.wf(p + ".proj_out.bias"), res1=x.view(M, C),
+        extras_w, extras_x = [], []
+        if tap_src is not None:
+            extras_w.append(tap_src[1]); extras_x.append(tap_src[0].view(M, C))
+        wpo = ops.pack_conv_weight(self.sd[p + ".proj_out.weight"], extras=extras_w)
+        base_bias = self.wf(p + ".proj_out.bias")
+        bias_buf = base_bias.clone()
+        if tap_src is not None:
+            self._register_fused(wpo, C, tap_src[1], bias_buf, base_bias, tap_src[2])
+        self.emit_plan(ops.linear_plan(h3, wpo, out.view(M, C), extras=extras_x, bias=bias_buf, res1=x.view(M, C),
                                        res2=None if tap is None else tap.view(M, C)))
         return out
 

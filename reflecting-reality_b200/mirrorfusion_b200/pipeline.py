@@ -161,12 +161,20 @@ class StepEngine:
     latents -> BrushNet -> UNet (+taps) -> CFG -> scheduler, all state resident on the device."""
 
     def __init__(self, cfg: NetConfig, unet_sd, brushnet_sd, images: int, H: int, W: int, device="cuda",
-                 use_graph: bool = True):
+                 use_graph: bool = True, fuse_taps: bool = True):
         self.cfg, self.images, self.H, self.W = cfg, images, H, W
         self.dev = torch.device(device)
         B = 2 * images
-        self.unet = UNetEngine(cfg, unet_sd, B, H, W, self.dev)
-        self.bn = BrushNetEngine(cfg, brushnet_sd, B, H, W, self.dev, tap_bufs=self.unet.taps)
+        self.fuse_taps = fuse_taps
+        if fuse_taps:
+            # 27 of the 28 zero-convs run inside the UNet GEMM that consumes the tap (extra K-segment); only the
+            # conv_in-site tap is a tensor
+            self.bn = BrushNetEngine(cfg, brushnet_sd, B, H, W, self.dev, only_first_tap=True)
+            self.unet = UNetEngine(cfg, unet_sd, B, H, W, self.dev, tap_sources=self.bn.tap_sources, tap0=self.bn.taps[0])
+        else:
+            self.unet = UNetEngine(cfg, unet_sd, B, H, W, self.dev)
+            self.bn = BrushNetEngine(cfg, brushnet_sd, B, H, W, self.dev, tap_bufs=self.unet.taps)
+        self._tap_scale = 1.0
         z = lambda: torch.zeros(images, cfg.in_channels, H, W, device=self.dev, dtype=f32)
         self.x, self.last, self.m0, self.m1 = z(), z(), z(), z()
         self.coef = torch.zeros(12, device=self.dev, dtype=f32)
@@ -193,6 +201,9 @@ class StepEngine:
         self.bn.t_dev.fill_(float(t))
         self.unet.t_dev.fill_(float(t))
         self.bn.scale.fill_(float(scale))
+        if self.fuse_taps and float(scale) != self._tap_scale:      # rare: only at control-guidance window edges
+            self.unet.set_tap_scale(float(scale))
+            self._tap_scale = float(scale)
         self.coef.copy_(coef_row, non_blocking=True)
         if not self.use_graph:
             self._enqueue()

@@ -74,6 +74,22 @@ def test_sd15_program_flop_census(stub_ops):
         assert sum(1 for p in plans if p.kind[1] == 2) == 3
 
 
+def test_fused_tap_program(stub_ops):
+    """Fused pipeline mode: 27 zero-convs become K-segments of the consuming UNet GEMMs; FLOPs are unchanged."""
+    from mirrorfusion_b200.engine import BrushNetEngine, UNetEngine
+    B = 2
+    bn = BrushNetEngine(SD15, _meta_sd(SD15, "brushnet"), B, 64, 64, "cpu", only_first_tap=True)
+    un = UNetEngine(SD15, _meta_sd(SD15, "unet"), B, 64, 64, "cpu", tap_sources=bn.tap_sources, tap0=bn.taps[0])
+    assert len(bn.taps) == 1 and len(un.fused_taps) == 27
+    total = (bn.flops + un.flops) / B
+    assert abs(total - 1.2446e12) / 1.2446e12 < 4e-3
+    bn0 = BrushNetEngine(SD15, _meta_sd(SD15, "brushnet"), B, 64, 64, "cpu")
+    assert bn0.launches - bn.launches == 27
+    un.set_tap_scale(0.5)      # in-place rescale of the fused segments keeps every buffer address
+    wp, koff, c, wz, bias_buf, base_bias, bz = un.fused_taps[0]
+    assert wp.shape[1] >= koff + c and bias_buf.shape == base_bias.shape
+
+
 def test_tiny_program_builds_for_odd_batches(stub_ops):
     from mirrorfusion_b200.engine import BrushNetEngine, UNetEngine
     for B in (2, 6):

@@ -113,6 +113,47 @@ def test_tiny_unipc_loop_vs_reference_golden(P, golden_dir):
         assert rel(out, g["latents"][-1]) == errs[-1]
 
 
+def test_fused_taps_match_unfused_and_oracle(P):
+    """The fused pipeline mode (27 zero-convs as K-segments of the consuming UNet GEMMs) against the unfused mode
+    (tap tensors) and the fp32 oracle, with a conditioning scale != 1 (in-place rescale of the fused segments)."""
+    from oracle import mf_oracle as O
+    cfg = TINY
+    usd, bsd = make_state_dict(cfg, "unet"), make_state_dict(cfg, "brushnet")
+    inp = make_inputs(cfg, 2, seed=5)
+    sched = P.B200DDIMScheduler()
+    sched.set_timesteps(4)
+    table = sched.coefficient_table(7.5).cuda()
+    outs = {}
+    for fuse in (False, True):
+        eng = P.StepEngine(cfg, usd, bsd, 2, cfg.sample_size, cfg.sample_size, use_graph=False, fuse_taps=fuse)
+        eng.set_conditioning(inp["prompt_embeds"].cuda(), inp["conditioning_latents"].cuda())
+        eng.x.copy_(inp["latents"].cuda())
+        eng.step(float(sched.timesteps[0]), table[0], 0.6)
+        outs[fuse] = (eng.unet.out.clone(), eng.x.clone())
+    assert rel(outs[True][0], outs[False][0]) < 6e-3
+    with torch.no_grad():
+        ref, _ = O.noise_pred_step(usd, bsd, cfg, torch.cat([inp["latents"]] * 2), sched.timesteps[0], inp["prompt_embeds"],
+                                   inp["conditioning_latents"], 0.6)
+    e_f, e_u = rel(outs[True][0], ref), rel(outs[False][0], ref)
+    record("tiny_fused_vs_unfused", fused_vs_oracle=e_f, unfused_vs_oracle=e_u, fused_vs_unfused=rel(outs[True][0], outs[False][0]))
+    assert e_f < TINY_TOL and e_u < TINY_TOL
+
+
+def test_sd15_fused_step_vs_reference_golden(P, golden_dir):
+    """Full SD1.5-shaped nets through the fused StepEngine (what bench.py runs): raw noise prediction vs the reference."""
+    g = np.load(os.path.join(golden_dir, "sd15_step.npz"))
+    cfg = SD15
+    usd, bsd = make_state_dict(cfg, "unet"), make_state_dict(cfg, "brushnet")
+    inp = make_inputs(cfg, 1)
+    eng = P.StepEngine(cfg, usd, bsd, 1, 64, 64, use_graph=False, fuse_taps=True)
+    eng.set_conditioning(inp["prompt_embeds"].cuda(), inp["conditioning_latents"].cuda())
+    eng.x.copy_(inp["latents"].cuda())
+    eng.step(float(g["t"]), torch.zeros(12, device="cuda"), float(g["scale"]))
+    e = rel(eng.unet.out, g["noise_pred"])
+    record("sd15_fused_step_vs_reference", noise_pred=e)
+    assert e < BF16_TOL
+
+
 def test_batched_step_vs_oracle_on_gpu(P):
     """4 images (net batch 8) on TINY: CUDA path vs the fp32 oracle evaluated on the GPU with TF32 disabled."""
     from oracle import mf_oracle as O
