@@ -79,8 +79,11 @@ int mfb_plan_ktotal(const mfb_plan* plan);
  * (S/models/resnet.py:337-338,381,393), conv_norm_out (S/models/unets/unet_2d_condition.py:1337-1338) and the
  * GroupNorm of Transformer2DModel (transformer_2d.py:338, eps 1e-6, silu=0).  x2 (optional) is a second tensor
  * concatenated after x1 along channels — the skip concat of the up blocks (unet_2d_blocks.py:2586,2728) — so the
- * concatenated tensor is only ever materialised normalised.  stats_ws: >= B*groups*2 floats of scratch.
+ * concatenated tensor is only ever materialised normalised.  stats_ws: MFB_GN_WS_FLOATS(B, groups) floats of scratch,
+ * ZERO-INITIALISED once by the caller (it holds self-resetting ticket counters); the reduction is deterministic.
  */
+#define MFB_GN_MAX_CHUNKS 64
+#define MFB_GN_WS_FLOATS(B, groups) (2 * (B) * (groups) * (1 + MFB_GN_MAX_CHUNKS) + (B))
 int mfb_groupnorm(const void* x1, int C1, const void* x2, int C2, int B, int HW, int groups, float eps,
                   const float* gamma, const float* beta, int silu, float* stats_ws, void* out, void* stream);
 

@@ -22,17 +22,21 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
     return o;
 }
 
-// grid (chunks, B), block (CV = C/8, PY).  stats[b][g] = {sum, sumsq}
+// grid (chunks, B), block (CV = C/8, PY).  Deterministic: every CTA writes its per-group partial {sum, sumsq} to
+// part[b][chunk][g], the last CTA of a batch image to finish (ticket counter) adds the partials in chunk order into
+// stats[b][g] and re-arms the counter — no floating-point atomics on global memory, no memset between calls.
 __global__ void gn_stats_kernel(const __nv_bfloat16* __restrict__ x1, int C1, const __nv_bfloat16* __restrict__ x2, int C2,
-                                int HW, int groups, int pix_per_cta, float* __restrict__ stats) {
+                                int HW, int groups, int pix_per_cta, float* __restrict__ stats, float* __restrict__ part,
+                                unsigned int* __restrict__ counters) {
     __shared__ float gs[64], gq[64];
+    __shared__ float4 ps[1024];
+    __shared__ int pg[1024];
+    __shared__ unsigned int s_ticket;
     const int C = C1 + C2;
     const int cpg = C / groups;
     const int b = blockIdx.y;
     const int c0 = threadIdx.x * 8;
     const int tid = threadIdx.y * blockDim.x + threadIdx.x;
-    if (tid < 64) { gs[tid] = 0.f; gq[tid] = 0.f; }
-    __syncthreads();
     const __nv_bfloat16* src;
     int ld, cc;
     if (c0 < C1) { src = x1; ld = C1; cc = c0; } else { src = x2; ld = C2; cc = c0 - C1; }
@@ -64,23 +68,52 @@ __global__ void gn_stats_kernel(const __nv_bfloat16* __restrict__ x1, int C1, co
 #pragma unroll
         for (int e = 0; e < 8; ++e) { s[e] += f[e]; q[e] = fmaf(f[e], f[e], q[e]); }
     }
-    // 8 consecutive channels touch at most two groups (cpg >= 8)
+    // 8 consecutive channels touch at most two groups (cpg >= 8).  Fixed-order (deterministic) CTA reduction:
+    // every thread parks its two partial pairs in shared memory, then thread g sums group g over all threads.
     const int g0 = c0 / cpg;
     float sa = 0.f, qa = 0.f, sb = 0.f, qb = 0.f;
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
         if ((c0 + e) / cpg == g0) { sa += s[e]; qa += q[e]; } else { sb += s[e]; qb += q[e]; }
     }
-    atomicAdd(&gs[g0], sa);
-    atomicAdd(&gq[g0], qa);
-    if ((c0 + 7) / cpg != g0) {
-        atomicAdd(&gs[g0 + 1], sb);
-        atomicAdd(&gq[g0 + 1], qb);
-    }
+    ps[tid] = make_float4(sa, qa, sb, qb);
+    pg[tid] = g0;
     __syncthreads();
     if (tid < groups) {
-        atomicAdd(&stats[(static_cast<size_t>(b) * groups + tid) * 2 + 0], gs[tid]);
-        atomicAdd(&stats[(static_cast<size_t>(b) * groups + tid) * 2 + 1], gq[tid]);
+        float a = 0.f, q2 = 0.f;
+        const int nthreads = blockDim.x * blockDim.y;
+        for (int t = 0; t < nthreads; ++t) {
+            const int gt = pg[t];
+            if (gt == tid) { a += ps[t].x; q2 += ps[t].y; }
+            else if (gt + 1 == tid) { a += ps[t].z; q2 += ps[t].w; }
+        }
+        gs[tid] = a;
+        gq[tid] = q2;
+    }
+    __syncthreads();
+    const int chunks = gridDim.x;
+    float* mypart = part + (static_cast<size_t>(b) * chunks + blockIdx.x) * groups * 2;
+    if (tid < groups) {
+        mypart[tid * 2 + 0] = gs[tid];
+        mypart[tid * 2 + 1] = gq[tid];
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_ticket = atomicAdd(&counters[b], 1u);
+    __syncthreads();
+    if (s_ticket == static_cast<unsigned int>(chunks - 1)) {   // last CTA of this image: fixed-order final reduction
+        __threadfence();
+        if (tid < groups) {
+            float a = 0.f, q2 = 0.f;
+            const float* pb = part + static_cast<size_t>(b) * chunks * groups * 2;
+            for (int c = 0; c < chunks; ++c) {
+                a += __ldcg(&pb[(static_cast<size_t>(c) * groups + tid) * 2 + 0]);
+                q2 += __ldcg(&pb[(static_cast<size_t>(c) * groups + tid) * 2 + 1]);
+            }
+            stats[(static_cast<size_t>(b) * groups + tid) * 2 + 0] = a;
+            stats[(static_cast<size_t>(b) * groups + tid) * 2 + 1] = q2;
+        }
+        if (tid == 0) counters[b] = 0u;
     }
 }
 
@@ -222,13 +255,16 @@ extern "C" int mfb_groupnorm(const void* x1, int C1, const void* x2, int C2, int
     int chunks = (4 * 148 + B - 1) / B;
     const int max_chunks = (HW + 4 * PY - 1) / (4 * PY);
     if (chunks > max_chunks) chunks = max_chunks;
+    if (chunks > MFB_GN_MAX_CHUNKS) chunks = MFB_GN_MAX_CHUNKS;
     if (chunks < 1) chunks = 1;
     const int ppc = (HW + chunks - 1) / chunks;
     chunks = (HW + ppc - 1) / ppc;
-    MFB_CUDA_OK(cudaMemsetAsync(stats_ws, 0, sizeof(float) * 2 * B * groups, st));
+    // workspace layout: stats [B*groups*2] | partials [B*MAX_CHUNKS*groups*2] | ticket counters [B] (zero on first use)
+    float* part = stats_ws + static_cast<size_t>(2) * B * groups;
+    unsigned int* counters = reinterpret_cast<unsigned int*>(part + static_cast<size_t>(2) * B * groups * MFB_GN_MAX_CHUNKS);
     dim3 grid(chunks, B), block(CV, PY);
     gn_stats_kernel<<<grid, block, 0, st>>>(static_cast<const __nv_bfloat16*>(x1), C1, static_cast<const __nv_bfloat16*>(x2), C2,
-                                            HW, groups, ppc, stats_ws);
+                                            HW, groups, ppc, stats_ws, part, counters);
     gn_apply_kernel<<<grid, block, 0, st>>>(static_cast<const __nv_bfloat16*>(x1), C1, static_cast<const __nv_bfloat16*>(x2), C2,
                                             HW, groups, ppc, stats_ws, eps, gamma, beta, silu,
                                             static_cast<__nv_bfloat16*>(out));

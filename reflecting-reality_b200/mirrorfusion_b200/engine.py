@@ -42,7 +42,7 @@ class _Net:
         # fused BrushNet taps: (packed weight, column offset, C, zero-conv weight [C,C] f32, bias buffer, base bias, zero-conv bias)
         self.fused_taps: List[Tuple] = []
         G = cfg.norm_num_groups
-        self.gn_ws = torch.zeros(B * G * 2, device=device, dtype=f32)
+        self.gn_ws = torch.zeros(ops.gn_ws_floats(B, G), device=device, dtype=f32)   # zeroed once: holds ticket counters
         ops.lib()
 
     # ---- memory
@@ -63,6 +63,7 @@ class _Net:
     # ---- BrushNet tap folded into the consuming GEMM as one more K-segment:
     #      out += s * (Wz . h_brushnet + bz)   (brushnet.py:832-834,904-906 + the tap add sites)
     def _register_fused(self, wp, koff, wz, bias_buf, base_bias, bz):
+        bias_buf.copy_(base_bias + bz)          # conditioning scale 1.0 until set_tap_scale() says otherwise
         self.fused_taps.append((wp, koff, wz.shape[1], wz, bias_buf, base_bias, bz))
 
     def set_tap_scale(self, s: float):

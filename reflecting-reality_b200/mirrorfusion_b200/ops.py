@@ -117,6 +117,14 @@ def linear_plan(x: torch.Tensor, w: torch.Tensor, out: torch.Tensor, **kw) -> Co
 
 
 # --------------------------------------------------------------------------------------------- norms
+GN_MAX_CHUNKS = 64
+
+
+def gn_ws_floats(B: int, groups: int) -> int:
+    """MFB_GN_WS_FLOATS of include/mfb200.h: stats + per-chunk partials + ticket counters."""
+    return 2 * B * groups * (1 + GN_MAX_CHUNKS) + B
+
+
 def groupnorm(x1, x2, gamma, beta, out, stats_ws, *, B, HW, groups, eps, silu):
     L = lib()
     C1 = x1.shape[-1]

@@ -39,6 +39,7 @@ class FakePlan:
 def stub_ops(monkeypatch):
     calls = []
     monkeypatch.setattr(real_ops, "lib", lambda: None)
+    assert real_ops.gn_ws_floats(2, 32) == 2 * 2 * 32 * 65 + 2
     monkeypatch.setattr(real_ops, "ConvPlan", FakePlan)
     monkeypatch.setattr(real_ops, "linear_plan",
                         lambda x, w, out, **kw: FakePlan(x, w, out, B=1, H=1, W=x.shape[0], Cin=x.shape[1], Cout=w.shape[0], **kw))
@@ -88,6 +89,7 @@ def test_fused_tap_program(stub_ops):
     un.set_tap_scale(0.5)      # in-place rescale of the fused segments keeps every buffer address
     wp, koff, c, wz, bias_buf, base_bias, bz = un.fused_taps[0]
     assert wp.shape[1] >= koff + c and bias_buf.shape == base_bias.shape
+    assert torch.equal(bias_buf, base_bias + 0.5 * bz)
 
 
 def test_tiny_program_builds_for_odd_batches(stub_ops):
