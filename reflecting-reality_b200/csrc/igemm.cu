@@ -20,6 +20,7 @@
 // other's main loop.
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <vector>
@@ -45,6 +46,7 @@ struct IgemmSeg {
 struct IgemmParams {
     CUtensorMap tmA[7];    // stride 1: [0] = conv input, [1..3] = extra 1x1 sources; stride 2: [0..3] = parity views, [4..6] = extras
     CUtensorMap tmB;
+    CUtensorMap tmBh;      // weights with a BN/2-row box (pair mode: each CTA fetches half and multicasts it)
     CUtensorMap tmOut;     // output tile store  (box {EPI box cols, tw, th, tn}, 64B / 32B swizzle)
     CUtensorMap tmRes;     // res1 tile load, same geometry
     IgemmSeg seg[MAX_SEG];
@@ -116,7 +118,11 @@ __device__ __forceinline__ uint4 pack_bf16x8(const float (&f)[8]) {
 // Persistent kernel: grid = min(#tiles, #SMs); CTA c processes tiles c, c+grid, ... (N-tile fastest, so the CTAs
 // running at the same time share A tiles through L2).  The accumulator is double-buffered in TMEM: while the 8
 // epilogue warps drain tile i, the MMA warp already accumulates tile i+1.
-template <int BN>
+// PAIR = true: launched as clusters of 2 CTAs that work on two consecutive M tiles of the same N tile.  The weight
+// tile is the same for both, so each CTA fetches half of it and TMA-multicasts it into both shared memories: the
+// L2 -> SM operand traffic per CTA drops from 16+20 KB to 16+10 KB per K block (the kernel is bound by that
+// traffic, not by the tensor pipe).  A slot is recycled only after BOTH CTAs' MMAs have read it (multicast commit).
+template <int BN, bool PAIR>
 __global__ void __launch_bounds__(IGEMM_THREADS, 1) igemm_kernel(const __grid_constant__ IgemmParams p) {
     using Cfg = IgemmCfg<BN>;
     constexpr int STAGES = Cfg::STAGES;
@@ -137,7 +143,12 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 1) igemm_kernel(const __grid_co
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int tiles_n = p.tiles_nn;
-    const int num_tiles = p.tiles_m * tiles_n;
+    // work items: PAIR -> (pair of M tiles, N tile); this CTA takes M tile 2*mp + rank (a tile past the end is all
+    // out-of-bounds: zero-filled loads, clipped stores)
+    const uint32_t crank = PAIR ? cluster_ctarank() : 0u;
+    const int num_tiles = (PAIR ? (p.tiles_m + 1) / 2 : p.tiles_m) * tiles_n;
+    const int wi0 = PAIR ? int(blockIdx.x >> 1) : int(blockIdx.x);
+    const int wstep = PAIR ? int(gridDim.x >> 1) : int(gridDim.x);
 
     int total_kb = 0;
     for (int s = 0; s < p.nseg; ++s) total_kb += p.seg[s].cblocks;
@@ -148,7 +159,7 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 1) igemm_kernel(const __grid_co
         prefetch_tmap(&p.tmOut);
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(full_bar(s), 1);
-            mbar_init(empty_bar(s), 1);
+            mbar_init(empty_bar(s), PAIR ? 2 : 1);
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(tmem_full_bar(a), 1);
@@ -163,6 +174,7 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 1) igemm_kernel(const __grid_co
     }
     tc_fence_before();
     __syncthreads();
+    if constexpr (PAIR) cluster_sync_all();     // the peer's barriers must exist before anything is multicast at them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
 
@@ -172,8 +184,9 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 1) igemm_kernel(const __grid_co
         if (lane == 0) {
             // ===== TMA producer =====
             int it = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                const int nt = tile % tiles_n, mt = tile / tiles_n;
+            for (int tile = wi0; tile < num_tiles; tile += wstep) {
+                const int nt = tile % tiles_n;
+                const int mt = PAIR ? 2 * (tile / tiles_n) + int(crank) : tile / tiles_n;
                 const int w0 = (mt % p.tiles_w) * p.tw;
                 const int h0 = ((mt / p.tiles_w) % p.tiles_h) * p.th;
                 const int n0 = (mt / (p.tiles_w * p.tiles_h)) * p.tn;
@@ -188,7 +201,13 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 1) igemm_kernel(const __grid_co
                         mbar_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
                         const uint32_t a_dst = smem_base + stage * Cfg::STAGE_BYTES;
                         tma_load_4d(a_dst, tm, full_bar(stage), sg.c0 + cb * BK, w0 + sg.dw, h0 + sg.dh, n0);
-                        tma_load_2d(a_dst + Cfg::A_BYTES, &p.tmB, full_bar(stage), kcol, nt * BN);
+                        if constexpr (PAIR) {
+                            constexpr int HB = (BN / 2) * BK * 2;    // bytes of half a weight tile
+                            tma_load_2d_mc(a_dst + Cfg::A_BYTES + crank * HB, &p.tmBh, full_bar(stage), kcol,
+                                           nt * BN + int(crank) * (BN / 2), uint16_t(3));
+                        } else {
+                            tma_load_2d(a_dst + Cfg::A_BYTES, &p.tmB, full_bar(stage), kcol, nt * BN);
+                        }
                     }
                 }
             }
@@ -199,7 +218,7 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 1) igemm_kernel(const __grid_co
             // ===== MMA issuer =====
             constexpr uint32_t idesc = make_idesc_bf16(BM, BN);
             int it = 0, li = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++li) {
+            for (int tile = wi0; tile < num_tiles; tile += wstep, ++li) {
                 const int as = li & 1;
                 mbar_wait(tmem_empty_bar(as), ((li >> 1) & 1) ^ 1);   // epilogue has drained this accumulator slot
                 tc_fence_after();
@@ -217,7 +236,10 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 1) igemm_kernel(const __grid_co
                         // advancing 16 bf16 (32 B) along K inside the 128B swizzle row: +2 in the (addr >> 4) field
                         umma_bf16(tacc, adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), idesc, (kb | k) != 0);
                     }
-                    umma_commit(empty_bar(stage));  // smem slot reusable once these MMAs have read it
+                    // smem slot reusable once these MMAs have read it (PAIR: tell the peer too — it writes half of
+                    // the weight tile into this CTA's slot)
+                    if constexpr (PAIR) umma_commit_mc(empty_bar(stage), uint16_t(3));
+                    else umma_commit(empty_bar(stage));
                 }
                 umma_commit(tmem_full_bar(as));     // accumulator complete
             }
@@ -241,8 +263,9 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 1) igemm_kernel(const __grid_co
         const int bn_out = p.geglu ? BN / 2 : BN;      // output columns per tile
         const int nbox = bn_out / BOXC;
         int li = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++li) {
-            const int nt = tile % tiles_n, mt = tile / tiles_n;
+        for (int tile = wi0; tile < num_tiles; tile += wstep, ++li) {
+            const int nt = tile % tiles_n;
+            const int mt = PAIR ? 2 * (tile / tiles_n) + int(crank) : tile / tiles_n;
             const int w0 = (mt % p.tiles_w) * p.tw;
             const int h0 = ((mt / p.tiles_w) % p.tiles_h) * p.th;
             const int n0 = (mt / (p.tiles_w * p.tiles_h)) * p.tn;
@@ -350,6 +373,7 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 1) igemm_kernel(const __grid_co
 
     tc_fence_before();
     __syncthreads();
+    if constexpr (PAIR) cluster_sync_all();     // no CTA may exit while its peer can still multicast into it
     if (warp == IGEMM_EPI_WARPS + 1) {
         tc_fence_after();
         tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
@@ -361,6 +385,7 @@ struct Plan {
     IgemmParams p;
     dim3 grid;
     int bn;
+    bool pair;
     double flops;
 };
 
@@ -380,16 +405,28 @@ static void pick_tile(int W, int H, int B, int* tw, int* th, int* tn) {
     }
 }
 
-template <int BN>
+template <int BN, bool PAIR>
 static int launch_igemm(const Plan& pl, cudaStream_t st) {
     using Cfg = IgemmCfg<BN>;
     static bool configured = false;
     if (!configured) {
-        MFB_CUDA_OK(cudaFuncSetAttribute(igemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        MFB_CUDA_OK(cudaFuncSetAttribute(igemm_kernel<BN, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
         configured = true;
     }
-    igemm_kernel<BN><<<pl.grid, IGEMM_THREADS, Cfg::SMEM_BYTES, st>>>(pl.p);
-    MFB_CUDA_OK(cudaGetLastError());
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = pl.grid;
+    cfg.blockDim = dim3(IGEMM_THREADS);
+    cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = PAIR ? 2 : 1;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    MFB_CUDA_OK(cudaLaunchKernelEx(&cfg, igemm_kernel<BN, PAIR>, pl.p));
     return MFB_OK;
 }
 
@@ -487,6 +524,16 @@ extern "C" int mfb_conv_plan_create(const mfb_conv_desc* d, mfb_plan** out) {
         const uint32_t bbox[2] = {64u, uint32_t(bn)};
         rc = encode_tmap_bf16(&p.tmB, d->w, 2, dims, str, bbox, 128);
         if (rc) { delete pl; return rc; }
+        const uint32_t hbox[2] = {64u, uint32_t(bn / 2)};
+        rc = encode_tmap_bf16(&p.tmBh, d->w, 2, dims, str, hbox, 128);
+        if (rc) { delete pl; return rc; }
+    }
+    // pair (weight-multicast) mode is opt-in (MFB_PAIR=1): measured 3-8 % SLOWER than independent CTAs on B200
+    // (profiles/r01d_pair_multicast_ab.md) — the kernel is bound by shared-memory operand bandwidth, which multicast
+    // does not reduce, and the lock-step coupling costs.  Kept as the base for the cta_group::2 variant.
+    {
+        const char* np = getenv("MFB_PAIR");
+        pl->pair = tiles_m >= 2 && (np && np[0] == '1');
     }
     {
         const int boxc = (bn % 32 == 0) ? 32 : 16;
@@ -512,8 +559,14 @@ extern "C" int mfb_conv_plan_create(const mfb_conv_desc* d, mfb_plan** out) {
     p.out_ld = d->geglu ? d->Cout / 2 : d->Cout;
     {
         const int sms = device_sm_count() > 0 ? device_sm_count() : 148;
-        const long total = long(p.tiles_m) * p.tiles_nn;
-        pl->grid = dim3(unsigned(total < sms ? total : sms), 1, 1);
+        if (pl->pair) {
+            const long pairs = long((p.tiles_m + 1) / 2) * p.tiles_nn;
+            const long maxp = sms / 2;
+            pl->grid = dim3(unsigned(2 * (pairs < maxp ? pairs : maxp)), 1, 1);
+        } else {
+            const long total = long(p.tiles_m) * p.tiles_nn;
+            pl->grid = dim3(unsigned(total < sms ? total : sms), 1, 1);
+        }
     }
     pl->flops = 2.0 * double(p.M) * d->Cout * ktot;
     *out = reinterpret_cast<mfb_plan*>(pl);
@@ -524,11 +577,19 @@ extern "C" int mfb_plan_run(mfb_plan* plan, void* stream) {
     MFB_REQUIRE(plan, "null plan");
     Plan* pl = reinterpret_cast<Plan*>(plan);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (pl->pair) {
+        switch (pl->bn) {
+            case 160: return launch_igemm<160, true>(*pl, st);
+            case 128: return launch_igemm<128, true>(*pl, st);
+            case 80: return launch_igemm<80, true>(*pl, st);
+            default: return launch_igemm<64, true>(*pl, st);
+        }
+    }
     switch (pl->bn) {
-        case 160: return launch_igemm<160>(*pl, st);
-        case 128: return launch_igemm<128>(*pl, st);
-        case 80: return launch_igemm<80>(*pl, st);
-        default: return launch_igemm<64>(*pl, st);
+        case 160: return launch_igemm<160, false>(*pl, st);
+        case 128: return launch_igemm<128, false>(*pl, st);
+        case 80: return launch_igemm<80, false>(*pl, st);
+        default: return launch_igemm<64, false>(*pl, st);
     }
 }
 

@@ -30,7 +30,6 @@ __global__ void gn_stats_kernel(const __nv_bfloat16* __restrict__ x1, int C1, co
                                 unsigned int* __restrict__ counters) {
     __shared__ float gs[64], gq[64];
     __shared__ float4 ps[1024];
-    __shared__ int pg[1024];
     __shared__ unsigned int s_ticket;
     const int C = C1 + C2;
     const int cpg = C / groups;
@@ -76,16 +75,31 @@ __global__ void gn_stats_kernel(const __nv_bfloat16* __restrict__ x1, int C1, co
     for (int e = 0; e < 8; ++e) {
         if ((c0 + e) / cpg == g0) { sa += s[e]; qa += q[e]; } else { sb += s[e]; qb += q[e]; }
     }
+    // level 1: over the pixel lanes (ty) of each channel vector, in ty order
     ps[tid] = make_float4(sa, qa, sb, qb);
-    pg[tid] = g0;
     __syncthreads();
+    const int CV = blockDim.x;
+    if (tid < CV) {
+        float4 acc = ps[tid];
+        for (int y = 1; y < blockDim.y; ++y) {
+            const float4 v = ps[y * CV + tid];
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+        ps[tid] = acc;
+    }
+    __syncthreads();
+    // level 2: thread g sums the (few) channel vectors that touch group g, in channel order
     if (tid < groups) {
         float a = 0.f, q2 = 0.f;
-        const int nthreads = blockDim.x * blockDim.y;
-        for (int t = 0; t < nthreads; ++t) {
-            const int gt = pg[t];
-            if (gt == tid) { a += ps[t].x; q2 += ps[t].y; }
-            else if (gt + 1 == tid) { a += ps[t].z; q2 += ps[t].w; }
+        int v0 = (tid * cpg) / 8 - 1;
+        if (v0 < 0) v0 = 0;
+        int v1 = ((tid + 1) * cpg - 1) / 8;
+        if (v1 > CV - 1) v1 = CV - 1;
+        for (int v = v0; v <= v1; ++v) {
+            const int gv = (v * 8) / cpg;
+            const float4 pv = ps[v];
+            if (gv == tid) { a += pv.x; q2 += pv.y; }
+            else if (gv + 1 == tid) { a += pv.z; q2 += pv.w; }
         }
         gs[tid] = a;
         gq[tid] = q2;
@@ -104,14 +118,23 @@ __global__ void gn_stats_kernel(const __nv_bfloat16* __restrict__ x1, int C1, co
     if (s_ticket == static_cast<unsigned int>(chunks - 1)) {   // last CTA of this image: fixed-order final reduction
         __threadfence();
         if (tid < groups) {
-            float a = 0.f, q2 = 0.f;
-            const float* pb = part + static_cast<size_t>(b) * chunks * groups * 2;
-            for (int c = 0; c < chunks; ++c) {
-                a += __ldcg(&pb[(static_cast<size_t>(c) * groups + tid) * 2 + 0]);
-                q2 += __ldcg(&pb[(static_cast<size_t>(c) * groups + tid) * 2 + 1]);
+            // four independent partial chains (loads in flight), combined in a fixed order
+            float a[4] = {0.f, 0.f, 0.f, 0.f}, q2[4] = {0.f, 0.f, 0.f, 0.f};
+            const float2* pb = reinterpret_cast<const float2*>(part + static_cast<size_t>(b) * chunks * groups * 2);
+            int c = 0;
+            for (; c + 3 < chunks; c += 4) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const float2 v = __ldcg(&pb[static_cast<size_t>(c + k) * groups + tid]);
+                    a[k] += v.x; q2[k] += v.y;
+                }
             }
-            stats[(static_cast<size_t>(b) * groups + tid) * 2 + 0] = a;
-            stats[(static_cast<size_t>(b) * groups + tid) * 2 + 1] = q2;
+            for (; c < chunks; ++c) {
+                const float2 v = __ldcg(&pb[static_cast<size_t>(c) * groups + tid]);
+                a[0] += v.x; q2[0] += v.y;
+            }
+            stats[(static_cast<size_t>(b) * groups + tid) * 2 + 0] = (a[0] + a[1]) + (a[2] + a[3]);
+            stats[(static_cast<size_t>(b) * groups + tid) * 2 + 1] = (q2[0] + q2[1]) + (q2[2] + q2[3]);
         }
         if (tid == 0) counters[b] = 0u;
     }
