@@ -65,6 +65,8 @@ typedef struct mfb_conv_desc {
     void* out;            /* [B,Ho,Wo,Cout] bf16 ([.., Cout/2] with geglu) */
     int geglu;
     int block_n;          /* 0 = auto, else 64, 80, 128 or 160 */
+    int igemm_mode;       /* 0 = auto (env MFB_IGEMM_MODE or independent CTAs); 1 independent CTAs, 2 CTA pair + weight multicast,
+                             3 CTA pair + cta_group::2 UMMA (256-row tile) */
 } mfb_conv_desc;
 
 typedef struct mfb_plan mfb_plan;

@@ -122,14 +122,23 @@ __device__ __forceinline__ uint4 pack_bf16x8(const float (&f)[8]) {
 // tile is the same for both, so each CTA fetches half of it and TMA-multicasts it into both shared memories: the
 // L2 -> SM operand traffic per CTA drops from 16+20 KB to 16+10 KB per K block (the kernel is bound by that
 // traffic, not by the tensor pipe).  A slot is recycled only after BOTH CTAs' MMAs have read it (multicast commit).
-template <int BN, bool PAIR>
+// MODE 2 (cta_group::2): the pair computes ONE 256 x BN tile per step: each CTA stages its own 128 activation rows and
+// HALF of the weight tile (BN/2 rows); the leader CTA's single MMA thread issues tcgen05.mma.cta_group::2 (M = 256), which
+// reads A from each CTA's own shared memory and the two halves of B from both, and accumulates into both CTAs' TMEM.
+// Shared-memory operand traffic per SM per K step drops from (128 + BN) to (128 + BN/2) rows — the resource this
+// kernel is bound by.  TMA completions of both CTAs are counted on the LEADER's full barrier; the leader's commits are
+// multicast to both CTAs' empty / accumulator-full barriers; both epilogues arrive on the leader's accumulator-empty one.
+template <int BN, int MODE>
 __global__ void __launch_bounds__(IGEMM_THREADS, 1) igemm_kernel(const __grid_constant__ IgemmParams p) {
     using Cfg = IgemmCfg<BN>;
+    constexpr bool PAIR = MODE != 0;
+    constexpr bool TWOSM = MODE == 2;
+    constexpr int STAGE_BYTES = TWOSM ? Cfg::A_BYTES + Cfg::B_BYTES / 2 : Cfg::STAGE_BYTES;
     constexpr int STAGES = Cfg::STAGES;
     extern __shared__ uint8_t smem_raw[];
     // 1024-byte alignment is required by the 128B swizzle atoms
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    const uint32_t stg_base = smem_base + STAGES * Cfg::STAGE_BYTES;
+    const uint32_t stg_base = smem_base + STAGES * Cfg::STAGE_BYTES;   // (MODE 2 uses smaller stages inside the same budget)
     const uint32_t bar_base = stg_base + Cfg::STG_BYTES;
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
     auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
@@ -159,18 +168,23 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 1) igemm_kernel(const __grid_co
         prefetch_tmap(&p.tmOut);
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(full_bar(s), 1);
-            mbar_init(empty_bar(s), PAIR ? 2 : 1);
+            mbar_init(empty_bar(s), MODE == 1 ? 2 : 1);
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(tmem_full_bar(a), 1);
-            mbar_init(tmem_empty_bar(a), IGEMM_EPI_WARPS);
+            mbar_init(tmem_empty_bar(a), TWOSM ? 2 * IGEMM_EPI_WARPS : IGEMM_EPI_WARPS);
         }
         mbar_init(res_full_bar, 1);
         fence_barrier_init();
     }
     if (warp == IGEMM_EPI_WARPS + 1) {
-        tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
-        tmem_relinquish();
+        if constexpr (TWOSM) {
+            tmem_alloc_2sm(tmem_slot, Cfg::TMEM_COLS);
+            tmem_relinquish_2sm();
+        } else {
+            tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+            tmem_relinquish();
+        }
     }
     tc_fence_before();
     __syncthreads();
@@ -198,10 +212,18 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 1) igemm_kernel(const __grid_co
                         const int stage = it % STAGES;
                         const uint32_t phase = (it / STAGES) & 1;
                         mbar_wait(empty_bar(stage), phase ^ 1);
+                        const uint32_t a_dst = smem_base + stage * STAGE_BYTES;
+                        if constexpr (TWOSM) {
+                            // both CTAs' bytes are counted on the leader's barrier
+                            if (crank == 0) mbar_expect_tx(full_bar(stage), 2 * STAGE_BYTES);
+                            const uint32_t lbar = mapa_shared(full_bar(stage), 0);
+                            tma_load_4d_2sm(a_dst, tm, lbar, sg.c0 + cb * BK, w0 + sg.dw, h0 + sg.dh, n0);
+                            tma_load_2d_2sm(a_dst + Cfg::A_BYTES, &p.tmBh, lbar, kcol, nt * BN + int(crank) * (BN / 2));
+                            continue;
+                        }
                         mbar_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
-                        const uint32_t a_dst = smem_base + stage * Cfg::STAGE_BYTES;
                         tma_load_4d(a_dst, tm, full_bar(stage), sg.c0 + cb * BK, w0 + sg.dw, h0 + sg.dh, n0);
-                        if constexpr (PAIR) {
+                        if constexpr (MODE == 1) {
                             constexpr int HB = (BN / 2) * BK * 2;    // bytes of half a weight tile
                             tma_load_2d_mc(a_dst + Cfg::A_BYTES + crank * HB, &p.tmBh, full_bar(stage), kcol,
                                            nt * BN + int(crank) * (BN / 2), uint16_t(3));
@@ -214,9 +236,9 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 1) igemm_kernel(const __grid_co
         }
         __syncwarp();
     } else if (warp == IGEMM_EPI_WARPS + 1) {
-        if (lane == 0) {
-            // ===== MMA issuer =====
-            constexpr uint32_t idesc = make_idesc_bf16(BM, BN);
+        if (lane == 0 && (!TWOSM || crank == 0)) {
+            // ===== MMA issuer (MODE 2: leader CTA only) =====
+            constexpr uint32_t idesc = make_idesc_bf16(TWOSM ? 2 * BM : BM, BN);
             int it = 0, li = 0;
             for (int tile = wi0; tile < num_tiles; tile += wstep, ++li) {
                 const int as = li & 1;
@@ -228,20 +250,23 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 1) igemm_kernel(const __grid_co
                     const uint32_t phase = (it / STAGES) & 1;
                     mbar_wait(full_bar(stage), phase);
                     tc_fence_after();
-                    const uint32_t a_addr = smem_base + stage * Cfg::STAGE_BYTES;
+                    const uint32_t a_addr = smem_base + stage * STAGE_BYTES;
                     const uint64_t adesc = make_desc_k_sw128(a_addr);
                     const uint64_t bdesc = make_desc_k_sw128(a_addr + Cfg::A_BYTES);
 #pragma unroll
                     for (int k = 0; k < BK / 16; ++k) {
                         // advancing 16 bf16 (32 B) along K inside the 128B swizzle row: +2 in the (addr >> 4) field
-                        umma_bf16(tacc, adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), idesc, (kb | k) != 0);
+                        if constexpr (TWOSM) umma_bf16_2sm(tacc, adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), idesc, (kb | k) != 0);
+                        else umma_bf16(tacc, adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), idesc, (kb | k) != 0);
                     }
-                    // smem slot reusable once these MMAs have read it (PAIR: tell the peer too — it writes half of
-                    // the weight tile into this CTA's slot)
-                    if constexpr (PAIR) umma_commit_mc(empty_bar(stage), uint16_t(3));
+                    // smem slot reusable once these MMAs have read it (pair modes: tell the peer too)
+                    if constexpr (TWOSM) umma_commit_2sm_mc(empty_bar(stage), uint16_t(3));
+                    else if constexpr (MODE == 1) umma_commit_mc(empty_bar(stage), uint16_t(3));
                     else umma_commit(empty_bar(stage));
                 }
-                umma_commit(tmem_full_bar(as));     // accumulator complete
+                // accumulator complete
+                if constexpr (TWOSM) umma_commit_2sm_mc(tmem_full_bar(as), uint16_t(3));
+                else umma_commit(tmem_full_bar(as));
             }
         }
         __syncwarp();
@@ -358,7 +383,10 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 1) igemm_kernel(const __grid_co
             // all tcgen05.ld of this warp have completed (wait::ld above): hand the accumulator slot back
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(tmem_empty_bar(as));
+            if (lane == 0) {
+                if constexpr (TWOSM) mbar_arrive_cluster(mapa_shared(tmem_empty_bar(as), 0));   // the leader issues the MMAs
+                else mbar_arrive(tmem_empty_bar(as));
+            }
             fence_proxy_async_smem();                  // generic-proxy writes of the staging tile -> visible to TMA
             named_bar_sync(1, IGEMM_EPI_WARPS * 32);
             if (leader) {
@@ -376,7 +404,8 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 1) igemm_kernel(const __grid_co
     if constexpr (PAIR) cluster_sync_all();     // no CTA may exit while its peer can still multicast into it
     if (warp == IGEMM_EPI_WARPS + 1) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+        if constexpr (TWOSM) tmem_dealloc_2sm(tmem_base, Cfg::TMEM_COLS);
+        else tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
     }
 }
 
@@ -385,7 +414,7 @@ struct Plan {
     IgemmParams p;
     dim3 grid;
     int bn;
-    bool pair;
+    int mode;   // 0 independent CTAs, 1 pair + weight multicast, 2 pair + cta_group::2 UMMA
     double flops;
 };
 
@@ -405,12 +434,12 @@ static void pick_tile(int W, int H, int B, int* tw, int* th, int* tn) {
     }
 }
 
-template <int BN, bool PAIR>
+template <int BN, int MODE>
 static int launch_igemm(const Plan& pl, cudaStream_t st) {
     using Cfg = IgemmCfg<BN>;
     static bool configured = false;
     if (!configured) {
-        MFB_CUDA_OK(cudaFuncSetAttribute(igemm_kernel<BN, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        MFB_CUDA_OK(cudaFuncSetAttribute(igemm_kernel<BN, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
         configured = true;
     }
     cudaLaunchConfig_t cfg;
@@ -421,12 +450,12 @@ static int launch_igemm(const Plan& pl, cudaStream_t st) {
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = PAIR ? 2 : 1;
+    attr[0].val.clusterDim.x = MODE != 0 ? 2 : 1;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    MFB_CUDA_OK(cudaLaunchKernelEx(&cfg, igemm_kernel<BN, PAIR>, pl.p));
+    MFB_CUDA_OK(cudaLaunchKernelEx(&cfg, igemm_kernel<BN, MODE>, pl.p));
     return MFB_OK;
 }
 
@@ -532,8 +561,10 @@ extern "C" int mfb_conv_plan_create(const mfb_conv_desc* d, mfb_plan** out) {
     // (profiles/r01d_pair_multicast_ab.md) — the kernel is bound by shared-memory operand bandwidth, which multicast
     // does not reduce, and the lock-step coupling costs.  Kept as the base for the cta_group::2 variant.
     {
-        const char* np = getenv("MFB_PAIR");
-        pl->pair = tiles_m >= 2 && (np && np[0] == '1');
+        const char* np = getenv("MFB_IGEMM_MODE");   // 0 / 1 / 2, default 0
+        pl->mode = (tiles_m >= 2 && np) ? atoi(np) : 0;
+        if (pl->mode < 0 || pl->mode > 2) pl->mode = 0;
+        if (d->igemm_mode >= 1 && d->igemm_mode <= 3) pl->mode = tiles_m >= 2 ? d->igemm_mode - 1 : 0;
     }
     {
         const int boxc = (bn % 32 == 0) ? 32 : 16;
@@ -559,7 +590,7 @@ extern "C" int mfb_conv_plan_create(const mfb_conv_desc* d, mfb_plan** out) {
     p.out_ld = d->geglu ? d->Cout / 2 : d->Cout;
     {
         const int sms = device_sm_count() > 0 ? device_sm_count() : 148;
-        if (pl->pair) {
+        if (pl->mode != 0) {
             const long pairs = long((p.tiles_m + 1) / 2) * p.tiles_nn;
             const long maxp = sms / 2;
             pl->grid = dim3(unsigned(2 * (pairs < maxp ? pairs : maxp)), 1, 1);
@@ -577,19 +608,27 @@ extern "C" int mfb_plan_run(mfb_plan* plan, void* stream) {
     MFB_REQUIRE(plan, "null plan");
     Plan* pl = reinterpret_cast<Plan*>(plan);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (pl->pair) {
+    if (pl->mode == 2) {
         switch (pl->bn) {
-            case 160: return launch_igemm<160, true>(*pl, st);
-            case 128: return launch_igemm<128, true>(*pl, st);
-            case 80: return launch_igemm<80, true>(*pl, st);
-            default: return launch_igemm<64, true>(*pl, st);
+            case 160: return launch_igemm<160, 2>(*pl, st);
+            case 128: return launch_igemm<128, 2>(*pl, st);
+            case 80: return launch_igemm<80, 2>(*pl, st);
+            default: return launch_igemm<64, 2>(*pl, st);
+        }
+    }
+    if (pl->mode == 1) {
+        switch (pl->bn) {
+            case 160: return launch_igemm<160, 1>(*pl, st);
+            case 128: return launch_igemm<128, 1>(*pl, st);
+            case 80: return launch_igemm<80, 1>(*pl, st);
+            default: return launch_igemm<64, 1>(*pl, st);
         }
     }
     switch (pl->bn) {
-        case 160: return launch_igemm<160, false>(*pl, st);
-        case 128: return launch_igemm<128, false>(*pl, st);
-        case 80: return launch_igemm<80, false>(*pl, st);
-        default: return launch_igemm<64, false>(*pl, st);
+        case 160: return launch_igemm<160, 0>(*pl, st);
+        case 128: return launch_igemm<128, 0>(*pl, st);
+        case 80: return launch_igemm<80, 0>(*pl, st);
+        default: return launch_igemm<64, 0>(*pl, st);
     }
 }
 

@@ -62,7 +62,7 @@ class ConvPlan:
                  Cout: int, ksize: int = 1, stride: int = 1, extras: Sequence[torch.Tensor] = (),
                  bias: Optional[torch.Tensor] = None, rowbias: Optional[torch.Tensor] = None, rowbias_ld: int = 0,
                  alpha: Optional[torch.Tensor] = None, res1: Optional[torch.Tensor] = None,
-                 res2: Optional[torch.Tensor] = None, geglu: bool = False, block_n: int = 0):
+                 res2: Optional[torch.Tensor] = None, geglu: bool = False, block_n: int = 0, igemm_mode: int = 0):
         L = lib()
         _req(x, bf16, "x"); _req(w, bf16, "w"); _req(out, bf16, "out")
         d = ConvDesc()
@@ -88,6 +88,7 @@ class ConvPlan:
                 setattr(d, name, t.data_ptr())
         d.geglu = int(geglu)
         d.block_n = block_n
+        d.igemm_mode = igemm_mode
         ktot = ksize * ksize * Cin + sum(e.shape[-1] for e in extras)
         if tuple(w.shape) != (Cout, ktot):
             raise ValueError(f"packed weight shape {tuple(w.shape)} != ({Cout}, {ktot})")

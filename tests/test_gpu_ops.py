@@ -126,6 +126,23 @@ def test_conv_block_n_variants_agree(ops):
         assert torch.equal(outs[0], o)    # same K order, same fp32 accumulation -> bit identical
 
 
+@pytest.mark.parametrize("B,H,W,Cin,Cout", [(2, 32, 32, 128, 320), (3, 16, 16, 64, 128), (2, 64, 64, 320, 640)])
+def test_igemm_cluster_modes_agree(ops, B, H, W, Cin, Cout):
+    """igemm_mode 1 = independent CTAs, 2 = CTA pair + TMA-multicast weight tile, 3 = CTA pair + tcgen05.mma.cta_group::2
+    (256-row UMMA tile, accumulators in both SMs' TMEM).  Same K order and fp32 accumulation -> bit-identical outputs
+    (odd M-tile counts exercise the all-out-of-bounds partner tile)."""
+    x = randn(B, H, W, Cin, seed=1)
+    wp = ops.pack_conv_weight(randn(Cout, Cin, 3, 3, seed=2, scale=0.05).float())
+    bias = randn(Cout, seed=3, dtype=torch.float32)
+    r1 = randn(B, H, W, Cout, seed=4)
+    outs = []
+    for mode in (1, 2, 3):
+        o = torch.full((B, H, W, Cout), float("nan"), device="cuda", dtype=bf16)
+        ops.ConvPlan(x, wp, o, B=B, H=H, W=W, Cin=Cin, Cout=Cout, ksize=3, bias=bias, res1=r1, igemm_mode=mode).run()
+        outs.append(o)
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+
+
 def test_persistent_tile_loop_many_tiles(ops):
     # far more tiles than SMs: every CTA walks several tiles through both TMEM accumulator slots
     M, K, N = 40000, 128, 640
