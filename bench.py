@@ -174,6 +174,7 @@ def run_ours(args, rank, world, local_rank):
     table = sched.coefficient_table(7.5).to(dev)
     ts = sched.timesteps.tolist()
     eng.x.copy_(lat0.to(dev))
+    eng.prepare_timesteps(ts)      # timestep-embedding tables for the whole schedule (depends only on t)
 
     def one_step(i):
         j = i % STEPS_PER_IMAGE

@@ -38,6 +38,8 @@ const char* mfb_last_error(void);
  *   (S/models/attention_processor.py:1246-1274), FeedForward/GEGLU (S/models/attention.py:668-675,
  *   S/models/activations.py:100-103), BrushNet zero-convs (S/models/brushnet.py:832-834,851,891-893).
  *
+ * (mfb_plan_flops reports ALGORITHMIC work: 2*M*N*Ktot of the convolution as the reference computes it.)
+ *
  *   out[b,oh,ow,:] = ( sum_taps x[b, oh*s+kh-pad, ow*s+kw-pad, :] . w_tap  +  sum_e extra_x[e][b,oh,ow,:] . w_e
  *                      + bias + rowbias[b,:] ) * alpha  + res1[b,oh,ow,:] + res2[b,oh,ow,:]
  *
@@ -65,6 +67,10 @@ typedef struct mfb_conv_desc {
     void* out;            /* [B,Ho,Wo,Cout] bf16 ([.., Cout/2] with geglu) */
     int geglu;
     int block_n;          /* 0 = auto, else 64, 80, 128 or 160 */
+    int up2x;             /* 1: the conv runs over the nearest-2x upsample of x (Upsample2D, S/models/upsampling.py:167-184).
+                             B,H,W are the LOW-resolution input dims, out/res/extras are [B,2H,2W,.]; w holds the four
+                             sub-pixel phases [4][Cout][4*Cin + extras] (phase = py*2+px, taps that hit the same source
+                             pixel pre-summed); the plan issues 4 launches and never materialises the upsampled tensor */
     int igemm_mode;       /* 0 = auto (env MFB_IGEMM_MODE or independent CTAs); 1 independent CTAs, 2 CTA pair + weight multicast,
                              3 CTA pair + cta_group::2 UMMA (256-row tile) */
 } mfb_conv_desc;
@@ -75,6 +81,7 @@ int mfb_plan_run(mfb_plan* plan, void* stream);
 int mfb_plan_destroy(mfb_plan* plan);
 double mfb_plan_flops(const mfb_plan* plan); /* 2*M*N*Ktot */
 int mfb_plan_ktotal(const mfb_plan* plan);
+int mfb_plan_launches(const mfb_plan* plan); /* kernel launches per mfb_plan_run (4 for up2x plans) */
 
 /* ------------------------------------------------------------------------------------------------------------
  * GroupNorm (+SiLU) over NHWC bf16, fp32 statistics.  Replaces F.group_norm + F.silu in ResnetBlock2D

@@ -65,6 +65,7 @@ struct IgemmParams {
     __nv_bfloat16* out;    // [M, out_ld]
     int out_ld;
     int geglu;             // BN == 128 only: cols [0,64) value, [64,128) gate -> out[:, nt*64 + j]
+    int o_step, o_py, o_px, o_Hf, o_Wf;   // rows map to output pixel (o_step*oh + o_py, o_step*ow + o_px) of [Bn, o_Hf, o_Wf]
 };
 
 template <int BN>
@@ -296,7 +297,8 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 1) igemm_kernel(const __grid_co
             const int n0 = (mt / (p.tiles_w * p.tiles_h)) * p.tn;
             const int ow = w0 + rw, oh = h0 + rh, on = n0 + rn;
             const bool valid = (ow < p.Wo) && (oh < p.Ho) && (on < p.Bn);
-            const long long m = (static_cast<long long>(on) * p.Ho + oh) * p.Wo + ow;
+            // linear pixel index inside the full output tensor (only used for the directly-read res2)
+            const long long m = (static_cast<long long>(on) * p.o_Hf + oh * p.o_step + p.o_py) * p.o_Wf + ow * p.o_step + p.o_px;
             const float* rb = p.rowbias ? p.rowbias + static_cast<long long>(valid ? on : 0) * p.rowbias_ld : nullptr;
             if (leader) {
                 tma_store_wait_read();                 // previous tile's store no longer reads the staging tile
@@ -411,10 +413,12 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 1) igemm_kernel(const __grid_co
 
 // ------------------------------------------------------------------------------------------------ host side
 struct Plan {
-    IgemmParams p;
+    IgemmParams p[4];   // 1 launch, or the 4 sub-pixel phases of an upsample-fused conv
+    int nlaunch;
     dim3 grid;
     int bn;
     int mode;   // 0 independent CTAs, 1 pair + weight multicast, 2 pair + cta_group::2 UMMA
+    int ktot;
     double flops;
 };
 
@@ -435,7 +439,7 @@ static void pick_tile(int W, int H, int B, int* tw, int* th, int* tn) {
 }
 
 template <int BN, int MODE>
-static int launch_igemm(const Plan& pl, cudaStream_t st) {
+static int launch_igemm(const Plan& pl, const IgemmParams& prm, cudaStream_t st) {
     using Cfg = IgemmCfg<BN>;
     static bool configured = false;
     if (!configured) {
@@ -455,7 +459,7 @@ static int launch_igemm(const Plan& pl, cudaStream_t st) {
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    MFB_CUDA_OK(cudaLaunchKernelEx(&cfg, igemm_kernel<BN, MODE>, pl.p));
+    MFB_CUDA_OK(cudaLaunchKernelEx(&cfg, igemm_kernel<BN, MODE>, prm));
     return MFB_OK;
 }
 
@@ -463,26 +467,35 @@ static int launch_igemm(const Plan& pl, cudaStream_t st) {
 
 using namespace mfb;
 
-extern "C" int mfb_conv_plan_create(const mfb_conv_desc* d, mfb_plan** out) {
-    MFB_REQUIRE(d && out, "null argument");
-    MFB_REQUIRE(d->ksize == 3 || d->ksize == 1, "ksize must be 1 or 3 (got %d)", d->ksize);
-    MFB_REQUIRE(d->stride == 1 || d->stride == 2, "stride must be 1 or 2");
-    MFB_REQUIRE(d->stride == 1 || d->ksize == 3, "stride 2 is only supported for 3x3");
-    MFB_REQUIRE(d->Cin > 0 && d->Cin % 64 == 0, "Cin must be a positive multiple of 64 (got %d)", d->Cin);
-    MFB_REQUIRE(d->Cout > 0 && d->Cout % 8 == 0, "Cout must be a multiple of 8 (got %d)", d->Cout);
-    MFB_REQUIRE(d->n_extra >= 0 && d->n_extra <= 3, "at most 3 extra 1x1 segments");
-    MFB_REQUIRE(d->x && d->w && d->out, "x / w / out must be device pointers");
-    MFB_REQUIRE(!d->geglu || (d->Cout % 128 == 0 && !d->res1 && !d->res2 && !d->rowbias), "geglu needs Cout %% 128 == 0 and no residuals");
+// Tensor map over an NHWC tensor [B, Hf, Wf, C], optionally restricted to the pixels (step*h + py, step*w + px):
+// the view has dims (C, Wv, Hv, B).
+static int encode_nhwc(CUtensorMap* tm, const void* base, int C, int Wf, int Hf, int B, int step, int py, int px,
+                       const uint32_t* box, int swz) {
+    const int Wv = (Wf - px + step - 1) / step, Hv = (Hf - py + step - 1) / step;
+    const uint64_t dims[4] = {uint64_t(C), uint64_t(Wv), uint64_t(Hv), uint64_t(B)};
+    const uint64_t str[3] = {uint64_t(C) * 2 * step, uint64_t(Wf) * C * 2 * step, uint64_t(Hf) * Wf * C * 2};
+    const char* b = static_cast<const char*>(base) + (size_t(py) * Wf + px) * C * 2;
+    return encode_tmap_bf16(tm, b, 4, dims, str, box, swz);
+}
 
-    Plan* pl = new Plan();
-    IgemmParams& p = pl->p;
+// One kernel launch worth of parameters.  up_py/up_px >= 0: sub-pixel phase of a 3x3 conv over the nearest-2x
+// upsample of x (Upsample2D, S/models/upsampling.py:167-184): output pixels (2h+py, 2w+px) only see a 2x2
+// neighbourhood of the low-resolution input, with the 3x3 taps that fall on the same source pixel pre-summed
+// into one weight, so the upsampled tensor never exists and 4/9 of the MMA work remains.
+static int build_params(const mfb_conv_desc* d, int up_py, int up_px, const void* w, Plan* pl, IgemmParams& p) {
     memset(&p, 0, sizeof(p));
+    const bool up = up_py >= 0;
     const int B = d->B, H = d->H, W = d->W;
-    const int Ho = d->stride == 1 ? H : (H - 1) / 2 + 1;
-    const int Wo = d->stride == 1 ? W : (W - 1) / 2 + 1;
+    // GEMM-row geometry (one row per computed output pixel of this launch)
+    const int Ho = up ? H : (d->stride == 1 ? H : (H - 1) / 2 + 1);
+    const int Wo = up ? W : (d->stride == 1 ? W : (W - 1) / 2 + 1);
+    // geometry of the full output tensor and of this launch's view of it
+    const int ostep = up ? 2 : 1, opy = up ? up_py : 0, opx = up ? up_px : 0;
+    const int Hf = Ho * ostep, Wf = Wo * ostep;
     p.Wo = Wo; p.Ho = Ho; p.Bn = B;
     p.M = B * Ho * Wo;
     p.N = d->Cout;
+    p.o_step = ostep; p.o_py = opy; p.o_px = opx; p.o_Hf = Hf; p.o_Wf = Wf;
     pick_tile(Wo, Ho, B, &p.tw, &p.th, &p.tn);
     p.tiles_w = (Wo + p.tw - 1) / p.tw;
     p.tiles_h = (Ho + p.th - 1) / p.th;
@@ -491,11 +504,17 @@ extern "C" int mfb_conv_plan_create(const mfb_conv_desc* d, mfb_plan** out) {
 
     int ktot = 0, nseg = 0;
     int rc = MFB_OK;
-    if (d->stride == 1) {
-        const uint64_t dims[4] = {uint64_t(d->Cin), uint64_t(W), uint64_t(H), uint64_t(B)};
-        const uint64_t str[3] = {uint64_t(d->Cin) * 2, uint64_t(W) * d->Cin * 2, uint64_t(H) * W * d->Cin * 2};
-        rc = encode_tmap_bf16(&p.tmA[0], d->x, 4, dims, str, box, 128);
-        if (rc) { delete pl; return rc; }
+    if (up) {
+        rc = encode_nhwc(&p.tmA[0], d->x, d->Cin, W, H, B, 1, 0, 0, box, 128);
+        if (rc) return rc;
+        for (int ty = 0; ty < 2; ++ty)
+            for (int tx = 0; tx < 2; ++tx) {
+                p.seg[nseg++] = IgemmSeg{0, up_py - 1 + ty, up_px - 1 + tx, 0, d->Cin / 64};
+                ktot += d->Cin;
+            }
+    } else if (d->stride == 1) {
+        rc = encode_nhwc(&p.tmA[0], d->x, d->Cin, W, H, B, 1, 0, 0, box, 128);
+        if (rc) return rc;
         const int r = d->ksize / 2;
         for (int kh = -r; kh <= r; ++kh)
             for (int kw = -r; kw <= r; ++kw) {
@@ -506,11 +525,8 @@ extern "C" int mfb_conv_plan_create(const mfb_conv_desc* d, mfb_plan** out) {
         // four parity views (ph, pw) of the input: element (h2, w2) of view = x[2*h2 + ph, 2*w2 + pw]
         for (int ph = 0; ph < 2; ++ph)
             for (int pw = 0; pw < 2; ++pw) {
-                const uint64_t dims[4] = {uint64_t(d->Cin), uint64_t((W - pw + 1) / 2), uint64_t((H - ph + 1) / 2), uint64_t(B)};
-                const uint64_t str[3] = {uint64_t(d->Cin) * 4, uint64_t(W) * d->Cin * 4, uint64_t(H) * W * d->Cin * 2};
-                const char* base = static_cast<const char*>(d->x) + (size_t(ph) * W + pw) * d->Cin * 2;
-                rc = encode_tmap_bf16(&p.tmA[ph * 2 + pw], base, 4, dims, str, box, 128);
-                if (rc) { delete pl; return rc; }
+                rc = encode_nhwc(&p.tmA[ph * 2 + pw], d->x, d->Cin, W, H, B, 2, ph, pw, box, 128);
+                if (rc) return rc;
             }
         // input row = 2*oh + kh - 1:  kh=0 -> (parity 1, h2 = oh-1); kh=1 -> (0, oh); kh=2 -> (1, oh)
         const int par[3] = {1, 0, 1}, off[3] = {-1, 0, 0};
@@ -523,15 +539,14 @@ extern "C" int mfb_conv_plan_create(const mfb_conv_desc* d, mfb_plan** out) {
     for (int e = 0; e < d->n_extra; ++e) {
         MFB_REQUIRE(d->extra_x[e] && d->extra_C[e] % 64 == 0, "extra segment %d: channels must be a multiple of 64", e);
         const int C = d->extra_C[e];
-        const uint64_t dims[4] = {uint64_t(C), uint64_t(Wo), uint64_t(Ho), uint64_t(B)};
-        const uint64_t str[3] = {uint64_t(C) * 2, uint64_t(Wo) * C * 2, uint64_t(Ho) * Wo * C * 2};
-        const int mi = (d->stride == 1 ? 1 : 4) + e;
-        rc = encode_tmap_bf16(&p.tmA[mi], d->extra_x[e], 4, dims, str, box, 128);
-        if (rc) { delete pl; return rc; }
+        const int mi = ((!up && d->stride == 2) ? 4 : 1) + e;
+        rc = encode_nhwc(&p.tmA[mi], d->extra_x[e], C, Wf, Hf, B, ostep, opy, opx, box, 128);   // extras live at OUTPUT resolution
+        if (rc) return rc;
         p.seg[nseg++] = IgemmSeg{mi, 0, 0, 0, C / 64};
         ktot += C;
     }
     p.nseg = nseg;
+    pl->ktot = ktot;
 
     // BN: 160 divides every conv width of the SD1.5 family (320/640/1280/960); GEGLU needs the 64|64 split.
     // When the wide tile leaves most SMs without work (8x8 latents: M = 64*B), halve it.
@@ -551,17 +566,16 @@ extern "C" int mfb_conv_plan_create(const mfb_conv_desc* d, mfb_plan** out) {
         const uint64_t dims[2] = {uint64_t(ktot), uint64_t(d->Cout)};
         const uint64_t str[1] = {uint64_t(ktot) * 2};
         const uint32_t bbox[2] = {64u, uint32_t(bn)};
-        rc = encode_tmap_bf16(&p.tmB, d->w, 2, dims, str, bbox, 128);
-        if (rc) { delete pl; return rc; }
+        rc = encode_tmap_bf16(&p.tmB, w, 2, dims, str, bbox, 128);
+        if (rc) return rc;
         const uint32_t hbox[2] = {64u, uint32_t(bn / 2)};
-        rc = encode_tmap_bf16(&p.tmBh, d->w, 2, dims, str, hbox, 128);
-        if (rc) { delete pl; return rc; }
+        rc = encode_tmap_bf16(&p.tmBh, w, 2, dims, str, hbox, 128);
+        if (rc) return rc;
     }
-    // pair (weight-multicast) mode is opt-in (MFB_PAIR=1): measured 3-8 % SLOWER than independent CTAs on B200
-    // (profiles/r01d_pair_multicast_ab.md) — the kernel is bound by shared-memory operand bandwidth, which multicast
-    // does not reduce, and the lock-step coupling costs.  Kept as the base for the cta_group::2 variant.
+    // CTA-pair modes are opt-in (env MFB_IGEMM_MODE = 1 | 2 or desc.igemm_mode): measured slightly SLOWER than
+    // independent CTAs on B200 for these tile shapes (profiles/r01d_pair_multicast_ab.md).
     {
-        const char* np = getenv("MFB_IGEMM_MODE");   // 0 / 1 / 2, default 0
+        const char* np = getenv("MFB_IGEMM_MODE");
         pl->mode = (tiles_m >= 2 && np) ? atoi(np) : 0;
         if (pl->mode < 0 || pl->mode > 2) pl->mode = 0;
         if (d->igemm_mode >= 1 && d->igemm_mode <= 3) pl->mode = tiles_m >= 2 ? d->igemm_mode - 1 : 0;
@@ -569,14 +583,12 @@ extern "C" int mfb_conv_plan_create(const mfb_conv_desc* d, mfb_plan** out) {
     {
         const int boxc = (bn % 32 == 0) ? 32 : 16;
         const int out_ld = d->geglu ? d->Cout / 2 : d->Cout;
-        const uint64_t dims[4] = {uint64_t(out_ld), uint64_t(Wo), uint64_t(Ho), uint64_t(B)};
-        const uint64_t str[3] = {uint64_t(out_ld) * 2, uint64_t(Wo) * out_ld * 2, uint64_t(Ho) * Wo * out_ld * 2};
         const uint32_t obox[4] = {uint32_t(boxc), uint32_t(p.tw), uint32_t(p.th), uint32_t(p.tn)};
-        rc = encode_tmap_bf16(&p.tmOut, d->out, 4, dims, str, obox, boxc * 2);
-        if (rc) { delete pl; return rc; }
+        rc = encode_nhwc(&p.tmOut, d->out, out_ld, Wf, Hf, B, ostep, opy, opx, obox, boxc * 2);
+        if (rc) return rc;
         if (d->res1) {
-            rc = encode_tmap_bf16(&p.tmRes, d->res1, 4, dims, str, obox, boxc * 2);
-            if (rc) { delete pl; return rc; }
+            rc = encode_nhwc(&p.tmRes, d->res1, out_ld, Wf, Hf, B, ostep, opy, opx, obox, boxc * 2);
+            if (rc) return rc;
         }
     }
     p.bias = d->bias;
@@ -599,38 +611,69 @@ extern "C" int mfb_conv_plan_create(const mfb_conv_desc* d, mfb_plan** out) {
             pl->grid = dim3(unsigned(total < sms ? total : sms), 1, 1);
         }
     }
-    pl->flops = 2.0 * double(p.M) * d->Cout * ktot;
+    return MFB_OK;
+}
+
+extern "C" int mfb_conv_plan_create(const mfb_conv_desc* d, mfb_plan** out) {
+    MFB_REQUIRE(d && out, "null argument");
+    MFB_REQUIRE(d->ksize == 3 || d->ksize == 1, "ksize must be 1 or 3 (got %d)", d->ksize);
+    MFB_REQUIRE(d->stride == 1 || d->stride == 2, "stride must be 1 or 2");
+    MFB_REQUIRE(d->stride == 1 || d->ksize == 3, "stride 2 is only supported for 3x3");
+    MFB_REQUIRE(d->Cin > 0 && d->Cin % 64 == 0, "Cin must be a positive multiple of 64 (got %d)", d->Cin);
+    MFB_REQUIRE(d->Cout > 0 && d->Cout % 8 == 0, "Cout must be a multiple of 8 (got %d)", d->Cout);
+    MFB_REQUIRE(d->n_extra >= 0 && d->n_extra <= 3, "at most 3 extra 1x1 segments");
+    MFB_REQUIRE(d->x && d->w && d->out, "x / w / out must be device pointers");
+    MFB_REQUIRE(!d->geglu || (d->Cout % 128 == 0 && !d->res1 && !d->res2 && !d->rowbias), "geglu needs Cout %% 128 == 0 and no residuals");
+    MFB_REQUIRE(!d->up2x || (d->ksize == 3 && d->stride == 1 && !d->geglu), "up2x needs a 3x3 stride-1 conv");
+
+    Plan* pl = new Plan();
+    int rc;
+    if (d->up2x) {
+        // w = [4 phases][Cout][4*Cin + extras], phase index = py*2 + px
+        pl->nlaunch = 4;
+        for (int ph = 0; ph < 4; ++ph) {
+            const int kt = 4 * d->Cin + (d->n_extra > 0 ? d->extra_C[0] : 0) + (d->n_extra > 1 ? d->extra_C[1] : 0) +
+                           (d->n_extra > 2 ? d->extra_C[2] : 0);
+            const char* wp = static_cast<const char*>(d->w) + size_t(ph) * d->Cout * kt * 2;
+            rc = build_params(d, ph >> 1, ph & 1, wp, pl, pl->p[ph]);
+            if (rc) { delete pl; return rc; }
+        }
+        int kext = 0;
+        for (int e = 0; e < d->n_extra; ++e) kext += d->extra_C[e];
+        pl->flops = 2.0 * double(d->B) * (2 * d->H) * (2 * d->W) * d->Cout * (9.0 * d->Cin + kext);   // algorithmic
+    } else {
+        pl->nlaunch = 1;
+        rc = build_params(d, -1, -1, d->w, pl, pl->p[0]);
+        if (rc) { delete pl; return rc; }
+        pl->flops = 2.0 * double(pl->p[0].M) * d->Cout * pl->ktot;
+    }
     *out = reinterpret_cast<mfb_plan*>(pl);
     return MFB_OK;
+}
+
+template <int MODE>
+static int run_one(const Plan& pl, const IgemmParams& prm, cudaStream_t st) {
+    switch (pl.bn) {
+        case 160: return launch_igemm<160, MODE>(pl, prm, st);
+        case 128: return launch_igemm<128, MODE>(pl, prm, st);
+        case 80: return launch_igemm<80, MODE>(pl, prm, st);
+        default: return launch_igemm<64, MODE>(pl, prm, st);
+    }
 }
 
 extern "C" int mfb_plan_run(mfb_plan* plan, void* stream) {
     MFB_REQUIRE(plan, "null plan");
     Plan* pl = reinterpret_cast<Plan*>(plan);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (pl->mode == 2) {
-        switch (pl->bn) {
-            case 160: return launch_igemm<160, 2>(*pl, st);
-            case 128: return launch_igemm<128, 2>(*pl, st);
-            case 80: return launch_igemm<80, 2>(*pl, st);
-            default: return launch_igemm<64, 2>(*pl, st);
-        }
+    for (int i = 0; i < pl->nlaunch; ++i) {
+        const int rc = pl->mode == 2 ? run_one<2>(*pl, pl->p[i], st) : pl->mode == 1 ? run_one<1>(*pl, pl->p[i], st)
+                                                                                    : run_one<0>(*pl, pl->p[i], st);
+        if (rc) return rc;
     }
-    if (pl->mode == 1) {
-        switch (pl->bn) {
-            case 160: return launch_igemm<160, 1>(*pl, st);
-            case 128: return launch_igemm<128, 1>(*pl, st);
-            case 80: return launch_igemm<80, 1>(*pl, st);
-            default: return launch_igemm<64, 1>(*pl, st);
-        }
-    }
-    switch (pl->bn) {
-        case 160: return launch_igemm<160, 0>(*pl, st);
-        case 128: return launch_igemm<128, 0>(*pl, st);
-        case 80: return launch_igemm<80, 0>(*pl, st);
-        default: return launch_igemm<64, 0>(*pl, st);
-    }
+    return MFB_OK;
 }
+
+extern "C" int mfb_plan_launches(const mfb_plan* plan) { return plan ? reinterpret_cast<const Plan*>(plan)->nlaunch : 0; }
 
 extern "C" int mfb_plan_destroy(mfb_plan* plan) {
     delete reinterpret_cast<Plan*>(plan);
@@ -641,8 +684,5 @@ extern "C" double mfb_plan_flops(const mfb_plan* plan) { return plan ? reinterpr
 
 extern "C" int mfb_plan_ktotal(const mfb_plan* plan) {
     if (!plan) return 0;
-    const Plan* pl = reinterpret_cast<const Plan*>(plan);
-    int k = 0;
-    for (int s = 0; s < pl->p.nseg; ++s) k += pl->p.seg[s].cblocks * 64;
-    return k;
+    return reinterpret_cast<const Plan*>(plan)->ktot;
 }

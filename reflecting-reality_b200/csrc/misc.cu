@@ -84,64 +84,62 @@ __global__ void conv_in_kernel(const float* __restrict__ xa, int Ca, const float
 }
 
 // ---------------------------------------------------------------------------------------------- conv_out
-// One warp per output pixel; K = 9*Cin reduced across lanes with 16-byte activation loads; weights
-// [Cout<=4][3][3][Cin] fp32 staged in shared memory as bf16-free fp32 (<= 46 KB for Cin = 320).
-__global__ void conv_out_kernel(const __nv_bfloat16* __restrict__ x, int Cin, int B, int H, int W,
-                                const float* __restrict__ w, const float* __restrict__ bias, int Cout,
-                                float* __restrict__ out) {
-    extern __shared__ float ws[];  // [Cout][9*Cin]
+// One thread per output pixel, all Cout (<= 4) outputs in registers.  Weights [3][3][Cin][4] fp32 sit in shared
+// memory and are read as warp-wide BROADCAST float4s (every lane needs the same weight), activations come in as
+// 16-byte vectors through L1 (each pixel is re-read by its 9 neighbours).  ~50 issue slots per 8 channels.
+__global__ void __launch_bounds__(128) conv_out_kernel(const __nv_bfloat16* __restrict__ x, int Cin, int B, int H, int W,
+                                                        const float* __restrict__ w, const float* __restrict__ bias, int Cout,
+                                                        float* __restrict__ out) {
+    extern __shared__ float4 ws4[];  // [9*Cin] : (w[co=0..3]) for (tap, cin)
     const int K = 9 * Cin;
-    for (int i = threadIdx.x; i < Cout * K; i += blockDim.x) ws[i] = w[i];
+    for (int i = threadIdx.x; i < K; i += blockDim.x) {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        v.x = w[i];
+        if (Cout > 1) v.y = w[K + i];
+        if (Cout > 2) v.z = w[2 * K + i];
+        if (Cout > 3) v.w = w[3 * K + i];
+        ws4[i] = v;
+    }
     __syncthreads();
-    const int lane = threadIdx.x & 31;
-    const int warps = blockDim.x >> 5;
     const long long npix = static_cast<long long>(B) * H * W;
-    const int nvec_c = Cin / 8;
-    for (long long pix = static_cast<long long>(blockIdx.x) * warps + (threadIdx.x >> 5); pix < npix;
-         pix += static_cast<long long>(gridDim.x) * warps) {
-        const int ow = pix % W;
-        const int oh = (pix / W) % H;
-        const int b = pix / (static_cast<long long>(W) * H);
-        float acc[4] = {0.f, 0.f, 0.f, 0.f};
-        constexpr int MAXV = 12;                      // 9 * (Cin/8) / 32 rounded up for Cin <= 320
-        uint4 ubuf[MAXV];
-        const int nv = 9 * nvec_c;
-#pragma unroll
-        for (int i = 0; i < MAXV; ++i) {              // all loads of this pixel in flight at once
-            const int v = lane + i * 32;
-            ubuf[i] = make_uint4(0, 0, 0, 0);
-            if (v < nv) {
-                const int tapi = v / nvec_c, cv = v % nvec_c;
-                const int hh = oh + tapi / 3 - 1, ww = ow + tapi % 3 - 1;
-                if (hh >= 0 && hh < H && ww >= 0 && ww < W)
-                    ubuf[i] = __ldg(reinterpret_cast<const uint4*>(x + ((static_cast<size_t>(b) * H + hh) * W + ww) * Cin + cv * 8));
-            }
-        }
-#pragma unroll
-        for (int i = 0; i < MAXV; ++i) {
-            const int v = lane + i * 32;
-            if (v >= nv) break;
-            const int tapi = v / nvec_c, cv = v % nvec_c;
-            const uint4 u = ubuf[i];
+    const long long pix = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (pix >= npix) return;
+    const int ow = pix % W;
+    const int oh = (pix / W) % H;
+    const int b = pix / (static_cast<long long>(W) * H);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int nvec = Cin / 8;
+#pragma unroll 1
+    for (int tap = 0; tap < 9; ++tap) {
+        const int hh = oh + tap / 3 - 1, ww = ow + tap % 3 - 1;
+        if (hh < 0 || hh >= H || ww < 0 || ww >= W) continue;
+        const uint4* src = reinterpret_cast<const uint4*>(x + ((static_cast<size_t>(b) * H + hh) * W + ww) * Cin);
+        const float4* wt = ws4 + tap * Cin;
+#pragma unroll 4
+        for (int v = 0; v < nvec; ++v) {
+            const uint4 u = __ldg(src + v);
             float f[8];
             float2 t;
             t = unpack_bf16x2(u.x); f[0] = t.x; f[1] = t.y;
             t = unpack_bf16x2(u.y); f[2] = t.x; f[3] = t.y;
             t = unpack_bf16x2(u.z); f[4] = t.x; f[5] = t.y;
             t = unpack_bf16x2(u.w); f[6] = t.x; f[7] = t.y;
-            for (int co = 0; co < Cout; ++co) {
-                const float* wp = ws + co * K + tapi * Cin + cv * 8;
 #pragma unroll
-                for (int e = 0; e < 8; ++e) acc[co] = fmaf(f[e], wp[e], acc[co]);
+            for (int e = 0; e < 8; ++e) {
+                const float4 wv = wt[v * 8 + e];
+                acc.x = fmaf(f[e], wv.x, acc.x);
+                acc.y = fmaf(f[e], wv.y, acc.y);
+                acc.z = fmaf(f[e], wv.z, acc.z);
+                acc.w = fmaf(f[e], wv.w, acc.w);
             }
         }
-        for (int co = 0; co < Cout; ++co) {
-            float a = acc[co];
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-            if (lane == 0) out[((static_cast<size_t>(b) * Cout + co) * H + oh) * W + ow] = a + bias[co];
-        }
     }
+    const size_t hw = static_cast<size_t>(H) * W;
+    float* o = out + static_cast<size_t>(b) * Cout * hw + static_cast<size_t>(oh) * W + ow;
+    o[0] = acc.x + bias[0];
+    if (Cout > 1) o[hw] = acc.y + bias[1];
+    if (Cout > 2) o[2 * hw] = acc.z + bias[2];
+    if (Cout > 3) o[3 * hw] = acc.w + bias[3];
 }
 
 // ---------------------------------------------------------------------------------------------- upsample / layout
@@ -331,8 +329,8 @@ extern "C" int mfb_conv_in(const float* sample, int Ca, const float* cond, int C
 extern "C" int mfb_conv_out(const void* x, int Cin, int B, int H, int W, const float* w, const float* bias, int Cout,
                             float* out, void* stream) {
     MFB_REQUIRE(x && w && bias && out, "null pointer");
-    MFB_REQUIRE(Cout >= 1 && Cout <= 4 && Cin % 8 == 0 && 9 * (Cin / 8) <= 12 * 32, "conv_out supports Cout <= 4, Cin %% 8 == 0, Cin <= 336");
-    const size_t smem = static_cast<size_t>(Cout) * 9 * Cin * sizeof(float);
+    MFB_REQUIRE(Cout >= 1 && Cout <= 4 && Cin % 8 == 0, "conv_out supports Cout <= 4, Cin %% 8 == 0");
+    const size_t smem = static_cast<size_t>(9) * Cin * sizeof(float4);
     MFB_REQUIRE(smem <= 200 * 1024, "conv_out weights do not fit shared memory");
     static bool configured = false;
     if (!configured) {
@@ -340,8 +338,8 @@ extern "C" int mfb_conv_out(const void* x, int Cin, int B, int H, int W, const f
         configured = true;
     }
     const long long npix = static_cast<long long>(B) * H * W;
-    const int grid = grid_for(npix, 8, 148 * 4);
-    conv_out_kernel<<<grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(static_cast<const __nv_bfloat16*>(x), Cin, B, H, W, w,
+    const int grid = static_cast<int>((npix + 127) / 128);
+    conv_out_kernel<<<grid, 128, smem, static_cast<cudaStream_t>(stream)>>>(static_cast<const __nv_bfloat16*>(x), Cin, B, H, W, w,
                                                                            bias, Cout, out);
     MFB_CUDA_OK(cudaGetLastError());
     return MFB_OK;

@@ -22,7 +22,7 @@ class ConvDesc(C.Structure):
         ("B", i32), ("H", i32), ("W", i32), ("Cin", i32), ("Cout", i32), ("ksize", i32), ("stride", i32),
         ("x", vp), ("n_extra", i32), ("extra_x", vp * 3), ("extra_C", i32 * 3), ("w", vp), ("bias", vp),
         ("rowbias", vp), ("rowbias_ld", i32), ("alpha", vp), ("res1", vp), ("res2", vp), ("out", vp),
-        ("geglu", i32), ("block_n", i32), ("igemm_mode", i32),
+        ("geglu", i32), ("block_n", i32), ("up2x", i32), ("igemm_mode", i32),
     ]
 
 
@@ -35,6 +35,7 @@ _SIGS = {
     "mfb_plan_destroy": (i32, [vp]),
     "mfb_plan_flops": (f64, [vp]),
     "mfb_plan_ktotal": (i32, [vp]),
+    "mfb_plan_launches": (i32, [vp]),
     "mfb_groupnorm": (i32, [vp, i32, vp, i32, i32, i32, i32, f32, vp, vp, i32, vp, vp, vp]),
     "mfb_layernorm": (i32, [vp, i32, i32, f32, vp, vp, vp, vp]),
     "mfb_attention": (i32, [vp, i32, vp, i32, vp, i32, vp, i32, i32, i32, i32, i32, i32, vp]),

@@ -39,6 +39,7 @@ class _Net:
         self._scratch: Dict[Tuple, torch.Tensor] = {}
         self.flops = 0.0
         self.launches = 0
+        self.n_time_ops = 0
         # fused BrushNet taps: (packed weight, column offset, C, zero-conv weight [C,C] f32, bias buffer, base bias, zero-conv bias)
         self.fused_taps: List[Tuple] = []
         G = cfg.norm_num_groups
@@ -81,7 +82,7 @@ class _Net:
     def emit_plan(self, plan: ops.ConvPlan):
         self.keep.append(plan)
         self.flops += plan.flops
-        self.emit(plan.run, 1, "igemm", plan.flops)
+        self.emit(plan.run, getattr(plan, "launches", 1), "igemm", plan.flops)
 
     def groupnorm(self, x1, x2, prefix: str, out, HW: int, eps: float, silu: bool):
         g, b = self.wf(prefix + ".weight"), self.wf(prefix + ".bias")
@@ -116,6 +117,26 @@ class _Net:
         self.emit(lambda: ops.linear_small(sin, w1, b1, e1, act_out=True))
         self.emit(lambda: ops.linear_small(e1, w2, b2, emb))
         self.emit(lambda: ops.linear_small(emb, wcat, bcat, self.rowbias, act_in=True))
+        self.n_time_ops = len(self.prog)      # the timestep path depends only on t: a denoise loop can hoist it
+
+    def timestep_table(self, timesteps: Sequence[float]) -> torch.Tensor:
+        """Row-bias rows (all time_emb_proj outputs of this net) for a list of timesteps: [len(timesteps), sum Cout].
+        Runs the timestep path B timesteps at a time, outside the step loop."""
+        rows = []
+        ts = [float(t) for t in timesteps]
+        for i in range(0, len(ts), self.B):
+            chunk = ts[i:i + self.B]
+            pad = chunk + [chunk[-1]] * (self.B - len(chunk))
+            self.t_dev.copy_(torch.tensor(pad, dtype=f32))
+            for f in self.prog[: self.n_time_ops]:
+                f()
+            rows.append(self.rowbias[: len(chunk)].clone())
+        return torch.cat(rows, 0)
+
+    def run_main(self):
+        """Everything after the timestep path (row biases must already be in self.rowbias)."""
+        for f in self.prog[self.n_time_ops:]:
+            f()
 
     # ---- ResnetBlock2D (resnet.py:329-405)
     def resnet(self, p: str, xa, xb, HW_hw: Tuple[int, int], cout: int, tap=None, tap_src=None):
@@ -185,12 +206,21 @@ class _Net:
         return out
 
     def upsample(self, p: str, x, hw, tap=None, tap_src=None):
+        """Upsample2D (nearest x2 + conv3x3, upsampling.py:145-186) as four sub-pixel 2x2 convolutions over the
+        low-resolution tensor: no upsampled intermediate, 4/9 of the MMA work."""
         h, w = hw
         c = x.shape[-1]
-        up = self.scratch("up", self.B, 4 * h * w, c)
-        self.emit(lambda: ops.upsample2x(x, up, B=self.B, H=h, W=w))
         out = self.buf(self.B, 4 * h * w, c)
-        self._sampler_conv(p, up, out, 2 * h, 2 * w, 1, tap, tap_src)
+        extras_w, extras_x = [], []
+        if tap_src is not None:
+            extras_w.append(tap_src[1]); extras_x.append(tap_src[0])
+        wp = ops.pack_upconv_weight(self.sd[p + ".conv.weight"], extras=extras_w)      # [4, C, 4C (+C)]
+        base_bias = self.wf(p + ".conv.bias")
+        bias_buf = base_bias.clone()
+        if tap_src is not None:
+            self._register_fused(wp.view(4 * c, -1), 4 * c, tap_src[1].repeat(4, 1), bias_buf, base_bias, tap_src[2])
+        self.emit_plan(ops.ConvPlan(x, wp, out, B=self.B, H=h, W=w, Cin=c, Cout=c, ksize=3, up2x=True, extras=extras_x,
+                                    bias=bias_buf, res2=tap))
         return out
 
     def run(self):

@@ -44,6 +44,29 @@ def pack_conv_weight(w: torch.Tensor, extras: Sequence[torch.Tensor] = ()) -> to
     return torch.cat(parts, 1).to(bf16).contiguous()
 
 
+def pack_upconv_weight(w: torch.Tensor, extras: Sequence[torch.Tensor] = ()) -> torch.Tensor:
+    """3x3 conv applied to a nearest-2x upsampled input == four sub-pixel phases, each a 2x2 conv over the
+    low-resolution input whose taps are sums of the 3x3 taps that land on the same source pixel.
+    OIHW [Cout,Cin,3,3] -> [4 (py*2+px), Cout, 2*2*Cin (+ extra 1x1 segments)] bf16 (sums in fp32, one rounding)."""
+    w = w.float()
+    # rows: phase 0 -> {dy=-1: kh0, dy=0: kh1+kh2}; phase 1 -> {dy=0: kh0+kh1, dy=+1: kh2}   (same for columns)
+    comb = [[(0,), (1, 2)], [(0, 1), (2,)]]
+    out = []
+    for py in range(2):
+        for px in range(2):
+            taps = []
+            for ty in range(2):
+                for tx in range(2):
+                    acc = 0
+                    for kh in comb[py][ty]:
+                        for kw in comb[px][tx]:
+                            acc = acc + w[:, :, kh, kw]
+                    taps.append(acc)                      # [Cout, Cin]
+            parts = [torch.stack(taps, 1).reshape(w.shape[0], -1)] + [e.reshape(e.shape[0], -1).float() for e in extras]
+            out.append(torch.cat(parts, 1))
+    return torch.stack(out, 0).to(bf16).contiguous()
+
+
 def pack_geglu(w: torch.Tensor, b: torch.Tensor):
     """GEGLU proj [8C, C]: rows [0,4C) value, [4C,8C) gate (activations.py:100-103) -> interleave per 128:
     64 value rows then the 64 matching gate rows."""
@@ -62,7 +85,7 @@ class ConvPlan:
                  Cout: int, ksize: int = 1, stride: int = 1, extras: Sequence[torch.Tensor] = (),
                  bias: Optional[torch.Tensor] = None, rowbias: Optional[torch.Tensor] = None, rowbias_ld: int = 0,
                  alpha: Optional[torch.Tensor] = None, res1: Optional[torch.Tensor] = None,
-                 res2: Optional[torch.Tensor] = None, geglu: bool = False, block_n: int = 0, igemm_mode: int = 0):
+                 res2: Optional[torch.Tensor] = None, geglu: bool = False, block_n: int = 0, igemm_mode: int = 0, up2x: bool = False):
         L = lib()
         _req(x, bf16, "x"); _req(w, bf16, "w"); _req(out, bf16, "out")
         d = ConvDesc()
@@ -89,15 +112,18 @@ class ConvPlan:
         d.geglu = int(geglu)
         d.block_n = block_n
         d.igemm_mode = igemm_mode
-        ktot = ksize * ksize * Cin + sum(e.shape[-1] for e in extras)
-        if tuple(w.shape) != (Cout, ktot):
-            raise ValueError(f"packed weight shape {tuple(w.shape)} != ({Cout}, {ktot})")
+        d.up2x = int(up2x)
+        ktot = (4 if up2x else ksize * ksize) * Cin + sum(e.shape[-1] for e in extras)
+        want = (4, Cout, ktot) if up2x else (Cout, ktot)
+        if tuple(w.shape) != want:
+            raise ValueError(f"packed weight shape {tuple(w.shape)} != {want}")
         h = C.c_void_p()
         check(L.mfb_conv_plan_create(C.byref(d), C.byref(h)))
         self._h = h
         self._L = L
         self._keep = (x, w, out, extras, bias, rowbias, alpha, res1, res2)
         self.flops = L.mfb_plan_flops(h)
+        self.launches = L.mfb_plan_launches(h)
 
     def run(self):
         check(self._L.mfb_plan_run(self._h, _stream()))

@@ -175,6 +175,7 @@ class StepEngine:
             self.unet = UNetEngine(cfg, unet_sd, B, H, W, self.dev)
             self.bn = BrushNetEngine(cfg, brushnet_sd, B, H, W, self.dev, tap_bufs=self.unet.taps)
         self._tap_scale = 1.0
+        self.time_tables = None     # (timesteps, brushnet table, unet table) once prepare_timesteps() has run
         z = lambda: torch.zeros(images, cfg.in_channels, H, W, device=self.dev, dtype=f32)
         self.x, self.last, self.m0, self.m1 = z(), z(), z(), z()
         self.coef = torch.zeros(12, device=self.dev, dtype=f32)
@@ -192,14 +193,33 @@ class StepEngine:
         for e in (self.bn, self.unet):                    # latent_model_input = cat([latents] * 2) (:1256)
             e.sample_in[:n].copy_(self.x)
             e.sample_in[n:].copy_(self.x)
-        self.bn.run()
-        self.unet.run()
+        if self.time_tables is None:
+            self.bn.run()
+            self.unet.run()
+        else:                                             # timestep path hoisted: row biases were copied in by step()
+            self.bn.run_main()
+            self.unet.run_main()
         eps = self.unet.out
         ops.cfg_sched_step(eps[:n], eps[n:], self.x, self.last, self.m0, self.m1, self.coef)
 
+    def prepare_timesteps(self, timesteps):
+        """Hoist the timestep path (sinusoid -> MLP -> all 22+22 time_emb_proj, embeddings.py:27-67,226-237,
+        resnet.py:369-376) out of the loop: it depends only on t, so both nets' row-bias tables for the whole
+        schedule are computed once.  Must be called before the step graph is captured."""
+        if self.graph is not None:
+            raise RuntimeError("prepare_timesteps() must run before the first captured step")
+        ts = [float(t) for t in timesteps]
+        self.time_tables = ({t: i for i, t in enumerate(ts)}, self.bn.timestep_table(ts), self.unet.timestep_table(ts))
+        self.launches_per_step = self.unet.launches + self.bn.launches + 1 - 8
+
     def step(self, t: float, coef_row: torch.Tensor, scale: float = 1.0):
-        self.bn.t_dev.fill_(float(t))
-        self.unet.t_dev.fill_(float(t))
+        if self.time_tables is not None:
+            i = self.time_tables[0][float(t)]
+            self.bn.rowbias.copy_(self.time_tables[1][i].expand_as(self.bn.rowbias))
+            self.unet.rowbias.copy_(self.time_tables[2][i].expand_as(self.unet.rowbias))
+        else:
+            self.bn.t_dev.fill_(float(t))
+            self.unet.t_dev.fill_(float(t))
         self.bn.scale.fill_(float(scale))
         if self.fuse_taps and float(scale) != self._tap_scale:      # rare: only at control-guidance window edges
             self.unet.set_tap_scale(float(scale))
@@ -237,6 +257,10 @@ class StepEngine:
         for t_ in (self.last, self.m0, self.m1):
             t_.zero_()
         ts = scheduler.timesteps.tolist()
+        if self.graph is None:
+            self.prepare_timesteps(ts)
+        elif self.time_tables is not None and any(float(t) not in self.time_tables[0] for t in ts):
+            raise RuntimeError("this StepEngine was captured for a different timestep schedule")
         for i, t in enumerate(ts):
             sc = 1.0 if conditioning_scales is None else conditioning_scales[i]
             self.step(float(t), table[i], sc)

@@ -12,12 +12,19 @@ from mirrorfusion_b200.config import SD15, TINY, param_shapes
 
 class FakePlan:
     def __init__(self, x, w, out, *, B, H, W, Cin, Cout, ksize=1, stride=1, extras=(), bias=None, rowbias=None,
-                 rowbias_ld=0, alpha=None, res1=None, res2=None, geglu=False, block_n=0):
+                 rowbias_ld=0, alpha=None, res1=None, res2=None, geglu=False, block_n=0, igemm_mode=0, up2x=False):
         Ho, Wo = (H, W) if stride == 1 else ((H - 1) // 2 + 1, (W - 1) // 2 + 1)
+        if up2x:
+            Ho, Wo = 2 * H, 2 * W
         M = B * Ho * Wo
-        ktot = ksize * ksize * Cin + sum(e.shape[-1] for e in extras)
+        ext = sum(e.shape[-1] for e in extras)
+        ktot = ksize * ksize * Cin + ext
         assert x.numel() == B * H * W * Cin, "input buffer size"
-        assert tuple(w.shape) == (Cout, ktot), (tuple(w.shape), Cout, ktot)
+        if up2x:
+            assert tuple(w.shape) == (4, Cout, 4 * Cin + ext), tuple(w.shape)
+        else:
+            assert tuple(w.shape) == (Cout, ktot), (tuple(w.shape), Cout, ktot)
+        self.launches = 4 if up2x else 1
         assert out.numel() == M * (Cout // 2 if geglu else Cout), "output buffer size"
         for e in extras:
             assert e.numel() == M * e.shape[-1]

@@ -83,6 +83,30 @@ def test_conv3x3_stride2(ops, B, H, W, C):
     assert rel(nhwc_to_nchw(out), ref) < 4e-3
 
 
+@pytest.mark.parametrize("B,H,W,C,with_extra", [(2, 8, 8, 128, False), (2, 16, 16, 64, True), (1, 32, 32, 320, True), (3, 12, 12, 64, False)])
+def test_upsample_fused_conv(ops, B, H, W, C, with_extra):
+    """Upsample2D = nearest x2 + conv3x3 as four sub-pixel 2x2 convs over the low-res input (no upsampled tensor),
+    with the tap add and an extra 1x1 K-segment living at the OUTPUT resolution."""
+    x = randn(B, H, W, C, seed=1)
+    w = randn(C, C, 3, 3, seed=2, scale=(9 * C) ** -0.5)
+    bias = randn(C, seed=3, dtype=torch.float32)
+    tap = randn(B, 2 * H, 2 * W, C, seed=4)
+    ex = randn(B, 2 * H, 2 * W, 64, seed=5) if with_extra else None
+    wz = randn(C, 64, seed=6, scale=0.1) if with_extra else None
+    out = torch.full((B, 2 * H, 2 * W, C), float("nan"), device="cuda", dtype=bf16)
+    wp = ops.pack_upconv_weight(w.float(), extras=[wz.float()] if with_extra else [])
+    plan = ops.ConvPlan(x, wp, out, B=B, H=H, W=W, Cin=C, Cout=C, ksize=3, up2x=True, bias=bias, res2=tap,
+                        extras=[ex] if with_extra else [])
+    assert plan.launches == 4
+    plan.run()
+    up = F.interpolate(nhwc_to_nchw(x), scale_factor=2.0, mode="nearest")
+    ref = F.conv2d(up, w.float(), bias, padding=1) + nhwc_to_nchw(tap)
+    if with_extra:
+        ref = ref + F.conv2d(nhwc_to_nchw(ex), wz.float()[:, :, None, None])
+    assert rel(nhwc_to_nchw(out), ref) < 5e-3
+    assert abs(plan.flops - 2.0 * B * 4 * H * W * C * (9 * C + (64 if with_extra else 0))) < 1.0   # algorithmic FLOPs
+
+
 def test_conv3x3_with_shortcut_segments(ops):
     # ResnetBlock2D tail on an up block: conv2(h) + conv_shortcut(cat([x, skip])) fused in one accumulator
     B, H, W, Cmid, Ca, Cb = 2, 16, 16, 128, 128, 64
