@@ -1,6 +1,7 @@
 // Library-wide host glue: error string, device validation, tensor-map encoding.
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <cudaTypedefs.h>
@@ -22,6 +23,15 @@ void set_error(const char* fmt, ...) {
 }
 
 int device_sm_count() { return g_sms; }
+
+bool pdl_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("MFB_PDL");
+        v = (e && e[0] == '1') ? 1 : 0;   // opt-in: measured neutral-to-slightly-negative inside the CUDA graph (profiles/r01f)
+    }
+    return v == 1;
+}
 
 int encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                      const uint32_t* box, int swizzle_bytes) {

@@ -97,6 +97,8 @@ __global__ void __launch_bounds__(ATT_THREADS, (D <= 40) ? 2 : 1) attention_kern
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *reinterpret_cast<uint32_t*>(gen_base + (tmem_slot - base));
+    pdl_trigger();
+    pdl_wait();
 
     // warps 0-3 = softmax (TMEM lane quarter = warp), warp 4 = TMA, warp 5 = MMA: the single-thread issuers get the
     // highest warp ids so the arbiter never lets softmax warps starve them
@@ -286,8 +288,7 @@ static int launch_attention(const AttParams& p, int B, cudaStream_t st) {
         configured = true;
     }
     dim3 grid((p.Tq + BQ - 1) / BQ, p.heads, B);
-    attention_kernel<D><<<grid, ATT_THREADS, Cfg::SMEM_BYTES, st>>>(p);
-    MFB_CUDA_OK(cudaGetLastError());
+    MFB_CUDA_OK(launch_k(attention_kernel<D>, grid, dim3(ATT_THREADS), Cfg::SMEM_BYTES, st, 1, p));
     return MFB_OK;
 }
 

@@ -19,6 +19,8 @@ __global__ void conv_in_kernel(const float* __restrict__ xa, int Ca, const float
     const int Cin = Ca + Cb;
     const int b = blockIdx.z;
     const int h0 = blockIdx.y * 8, w0 = blockIdx.x * 8;
+    pdl_trigger();
+    pdl_wait();
     for (int i = threadIdx.x; i < Cin * 100; i += blockDim.x) {
         const int c = i / 100, r = i % 100;
         const int hh = h0 + r / 10 - 1, ww = w0 + r % 10 - 1;
@@ -101,6 +103,8 @@ __global__ void __launch_bounds__(128) conv_out_kernel(const __nv_bfloat16* __re
         ws4[i] = v;
     }
     __syncthreads();
+    pdl_trigger();
+    pdl_wait();      // the weights above are static; the activations below come from the previous kernel
     const long long npix = static_cast<long long>(B) * H * W;
     const long long pix = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (pix >= npix) return;
@@ -196,6 +200,8 @@ __global__ void transpose_tokens_kernel(const __nv_bfloat16* __restrict__ x, int
     __shared__ __nv_bfloat16 tile[32][34];
     const int b = blockIdx.z;
     const int t0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    pdl_trigger();
+    pdl_wait();
     for (int i = threadIdx.y; i < 32; i += blockDim.y) {
         const int t = t0 + i, c = c0 + threadIdx.x;
         tile[i][threadIdx.x] = (t < T && c < C) ? x[(static_cast<size_t>(b) * T + t) * ld + col0 + c] : __float2bfloat16(0.f);
@@ -276,6 +282,8 @@ __global__ void linear_small_kernel(const float* __restrict__ x, int M, int K, c
 __global__ void cfg_sched_kernel(const float* __restrict__ eps_u, const float* __restrict__ eps_c, float* __restrict__ x, float* __restrict__ last,
                                  float* __restrict__ m0, float* __restrict__ m1, const float* __restrict__ coef,
                                  long long total /* Bimg*n */) {
+    pdl_trigger();
+    pdl_wait();
     const float g = coef[0], c_x = coef[1], c_eps = coef[2];
     const float a_last = coef[3], a_m0 = coef[4], a_m1 = coef[5], a_mt = coef[6], use_corr = coef[7];
     const float b_x = coef[8], b_mt = coef[9], b_m0 = coef[10], b_eps = coef[11];
@@ -319,10 +327,9 @@ extern "C" int mfb_conv_in(const float* sample, int Ca, const float* cond, int C
     int threads = 8 * (Cout / 8);
     if (threads > 640) threads = 640;
     threads = (threads + 31) / 32 * 32;
-    conv_in_kernel<<<grid, threads, Cin * 100 * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
-        sample, Ca, cond, Cb, H, W, w, bias, Cout, static_cast<__nv_bfloat16*>(out), static_cast<const __nv_bfloat16*>(tap),
-        static_cast<__nv_bfloat16*>(out_post));
-    MFB_CUDA_OK(cudaGetLastError());
+    MFB_CUDA_OK(launch_k(conv_in_kernel, grid, dim3(threads), Cin * 100 * sizeof(float), static_cast<cudaStream_t>(stream), 1,
+                         sample, Ca, cond, Cb, H, W, w, bias, Cout, static_cast<__nv_bfloat16*>(out),
+                         static_cast<const __nv_bfloat16*>(tap), static_cast<__nv_bfloat16*>(out_post)));
     return MFB_OK;
 }
 
@@ -339,9 +346,8 @@ extern "C" int mfb_conv_out(const void* x, int Cin, int B, int H, int W, const f
     }
     const long long npix = static_cast<long long>(B) * H * W;
     const int grid = static_cast<int>((npix + 127) / 128);
-    conv_out_kernel<<<grid, 128, smem, static_cast<cudaStream_t>(stream)>>>(static_cast<const __nv_bfloat16*>(x), Cin, B, H, W, w,
-                                                                           bias, Cout, out);
-    MFB_CUDA_OK(cudaGetLastError());
+    MFB_CUDA_OK(launch_k(conv_out_kernel, dim3(grid), dim3(128), smem, static_cast<cudaStream_t>(stream), 1,
+                         static_cast<const __nv_bfloat16*>(x), Cin, B, H, W, w, bias, Cout, out));
     return MFB_OK;
 }
 
@@ -380,9 +386,8 @@ extern "C" int mfb_f32_to_bf16(const float* x, long long n, void* out, void* str
 extern "C" int mfb_transpose_tokens(const void* x, int ld, int col0, int C, int B, int T, void* out, int ldt, void* stream) {
     MFB_REQUIRE(x && out && ldt >= T, "bad arguments");
     dim3 grid((ldt + 31) / 32, (C + 31) / 32, B), block(32, 8);
-    transpose_tokens_kernel<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const __nv_bfloat16*>(x), ld, col0, C,
-                                                                                  T, static_cast<__nv_bfloat16*>(out), ldt);
-    MFB_CUDA_OK(cudaGetLastError());
+    MFB_CUDA_OK(launch_k(transpose_tokens_kernel, grid, block, 0, static_cast<cudaStream_t>(stream), 1,
+                         static_cast<const __nv_bfloat16*>(x), ld, col0, C, T, static_cast<__nv_bfloat16*>(out), ldt));
     return MFB_OK;
 }
 
@@ -414,7 +419,7 @@ extern "C" int mfb_cfg_sched_step(const float* eps_uncond, const float* eps_cond
                                   const float* coef, int Bimg, long long n, void* stream) {
     MFB_REQUIRE(eps_uncond && eps_cond && x && last && m0 && m1 && coef, "null pointer");
     const long long total = static_cast<long long>(Bimg) * n;
-    cfg_sched_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(eps_uncond, eps_cond, x, last, m0, m1, coef, total);
-    MFB_CUDA_OK(cudaGetLastError());
+    MFB_CUDA_OK(launch_k(cfg_sched_kernel, dim3(grid_for(total, 256)), dim3(256), 0, static_cast<cudaStream_t>(stream), 1,
+                         eps_uncond, eps_cond, x, last, m0, m1, coef, total));
     return MFB_OK;
 }

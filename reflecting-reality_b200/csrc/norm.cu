@@ -36,6 +36,8 @@ __global__ void gn_stats_kernel(const __nv_bfloat16* __restrict__ x1, int C1, co
     const int b = blockIdx.y;
     const int c0 = threadIdx.x * 8;
     const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+    pdl_trigger();
+    pdl_wait();
     const __nv_bfloat16* src;
     int ld, cc;
     if (c0 < C1) { src = x1; ld = C1; cc = c0; } else { src = x2; ld = C2; cc = c0 - C1; }
@@ -149,6 +151,8 @@ __global__ void gn_apply_kernel(const __nv_bfloat16* __restrict__ x1, int C1, co
     const int b = blockIdx.y;
     const int c0 = threadIdx.x * 8;
     const float inv_cnt = 1.0f / (static_cast<float>(HW) * cpg);
+    pdl_trigger();
+    pdl_wait();
     float sc[8], sh[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
@@ -207,6 +211,8 @@ __global__ void layernorm_kernel(const __nv_bfloat16* __restrict__ x, int rows, 
                                  __nv_bfloat16* __restrict__ out) {
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
+    pdl_trigger();
+    pdl_wait();
     if (row >= rows) return;
     const int nvec = C >> 3;
     const __nv_bfloat16* src = x + static_cast<size_t>(row) * C;
@@ -286,12 +292,11 @@ extern "C" int mfb_groupnorm(const void* x1, int C1, const void* x2, int C2, int
     float* part = stats_ws + static_cast<size_t>(2) * B * groups;
     unsigned int* counters = reinterpret_cast<unsigned int*>(part + static_cast<size_t>(2) * B * groups * MFB_GN_MAX_CHUNKS);
     dim3 grid(chunks, B), block(CV, PY);
-    gn_stats_kernel<<<grid, block, 0, st>>>(static_cast<const __nv_bfloat16*>(x1), C1, static_cast<const __nv_bfloat16*>(x2), C2,
-                                            HW, groups, ppc, stats_ws, part, counters);
-    gn_apply_kernel<<<grid, block, 0, st>>>(static_cast<const __nv_bfloat16*>(x1), C1, static_cast<const __nv_bfloat16*>(x2), C2,
-                                            HW, groups, ppc, stats_ws, eps, gamma, beta, silu,
-                                            static_cast<__nv_bfloat16*>(out));
-    MFB_CUDA_OK(cudaGetLastError());
+    MFB_CUDA_OK(launch_k(gn_stats_kernel, grid, block, 0, st, 1, static_cast<const __nv_bfloat16*>(x1), C1,
+                         static_cast<const __nv_bfloat16*>(x2), C2, HW, groups, ppc, stats_ws, part, counters));
+    MFB_CUDA_OK(launch_k(gn_apply_kernel, grid, block, 0, st, 1, static_cast<const __nv_bfloat16*>(x1), C1,
+                         static_cast<const __nv_bfloat16*>(x2), C2, HW, groups, ppc, static_cast<const float*>(stats_ws), eps, gamma,
+                         beta, silu, static_cast<__nv_bfloat16*>(out)));
     return MFB_OK;
 }
 
@@ -305,9 +310,8 @@ extern "C" int mfb_layernorm(const void* x, int rows, int C, float eps, const fl
     const int nv = (C / 8 + 31) / 32;
     auto X = static_cast<const __nv_bfloat16*>(x);
     auto O = static_cast<__nv_bfloat16*>(out);
-    if (nv <= 2) layernorm_kernel<2><<<grid, block, 0, st>>>(X, rows, C, eps, gamma, beta, O);
-    else if (nv <= 5) layernorm_kernel<5><<<grid, block, 0, st>>>(X, rows, C, eps, gamma, beta, O);
-    else layernorm_kernel<8><<<grid, block, 0, st>>>(X, rows, C, eps, gamma, beta, O);
-    MFB_CUDA_OK(cudaGetLastError());
+    if (nv <= 2) MFB_CUDA_OK(launch_k(layernorm_kernel<2>, grid, block, 0, st, 1, X, rows, C, eps, gamma, beta, O));
+    else if (nv <= 5) MFB_CUDA_OK(launch_k(layernorm_kernel<5>, grid, block, 0, st, 1, X, rows, C, eps, gamma, beta, O));
+    else MFB_CUDA_OK(launch_k(layernorm_kernel<8>, grid, block, 0, st, 1, X, rows, C, eps, gamma, beta, O));
     return MFB_OK;
 }
