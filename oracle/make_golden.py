@@ -136,6 +136,31 @@ def golden_sched_only(diffusers, name):
     print(f"{name}: scheduler trajectories written")
 
 
+def golden_signatures(diffusers, name):
+    """Parameter names (in order) of the reference entry points the drop-in classes mirror."""
+    import inspect
+    import json
+    from diffusers.models.attention_processor import AttnProcessor2_0
+    targets = {
+        "BrushNetModel.forward": diffusers.BrushNetModel.forward,
+        "UNet2DConditionModel.forward": diffusers.UNet2DConditionModel.forward,
+        "StableDiffusionBrushNetPipeline.__call__": diffusers.StableDiffusionBrushNetPipeline.__call__,
+        "AttnProcessor2_0.__call__": AttnProcessor2_0.__call__,
+        "UniPCMultistepScheduler.step": diffusers.UniPCMultistepScheduler.step,
+        "DDIMScheduler.step": diffusers.DDIMScheduler.step,
+        "UniPCMultistepScheduler.set_timesteps": diffusers.UniPCMultistepScheduler.set_timesteps,
+        "UniPCMultistepScheduler.scale_model_input": diffusers.UniPCMultistepScheduler.scale_model_input,
+    }
+    out = {}
+    for k, fn in targets.items():
+        sig = inspect.signature(fn)
+        out[k] = [{"name": p.name, "default": None if p.default is inspect._empty else repr(p.default),
+                   "kind": str(p.kind)} for p in sig.parameters.values()]
+    with open(os.path.join(GOLD, name), "w") as f:
+        json.dump(out, f, indent=1)
+    print(f"{name}: {len(out)} reference signatures")
+
+
 def main():
     if not os.path.isdir(REF_SRC):
         raise SystemExit("reference not mounted at /root/reference; golden vectors can only be made in the build container")
@@ -144,7 +169,9 @@ def main():
     os.makedirs(GOLD, exist_ok=True)
     diffusers = import_reference()
     from mirrorfusion_b200.config import MICRO, TINY, SD15
-    which = sys.argv[1:] or ["sched", "micro", "tiny", "sd15"]
+    which = sys.argv[1:] or ["sched", "micro", "tiny", "sd15", "sigs"]
+    if "sigs" in which:
+        golden_signatures(diffusers, "reference_signatures.json")
     if "sched" in which:
         golden_sched_only(diffusers, "sched_traj.npz")
     if "micro" in which:

@@ -156,6 +156,94 @@ class B200UNet2DConditionModel:
     __call__ = forward
 
 
+class B200AttnProcessor:
+    """Attention processor on the sm_100a kernels with the reference's processor call contract
+    `proc(attn, hidden_states, encoder_hidden_states=None, attention_mask=None, temb=None, scale=1.0)`
+    (AttnProcessor2_0.__call__, S/models/attention_processor.py:1213-1286), installable with
+    `Attention.set_processor` / `unet.set_attn_processor` (:380-398, unet_2d_condition.py:716-748).
+    It reads `attn.to_q/to_k/to_v/to_out[0]`, `attn.heads`, `attn.residual_connection`, `attn.rescale_output_factor`;
+    q/k/v run as ONE fused GEMM for self-attention, the softmax(QK^T/sqrt(d))V is the flash tcgen05 kernel.
+    Plans and packed weights are cached per (module, geometry)."""
+
+    def __init__(self):
+        self._cache: Dict[Tuple, Any] = {}
+
+    def _state(self, attn, B, T, Tk, C, Cctx, is_self, dev):
+        key = (id(attn), B, T, Tk, C, Cctx, is_self)
+        st = self._cache.get(key)
+        if st is not None:
+            return st
+        bf = torch.bfloat16
+        heads = attn.heads
+        z = lambda *shape: torch.zeros(*shape, device=dev, dtype=bf)
+        st = SimpleNamespace()
+        st.x = z(B * T, C)
+        st.att = z(B * T, C)
+        st.out = z(B * T, C)
+        Tp = (Tk + 7) // 8 * 8
+        st.vt = z(B, C, Tp)
+        st.Tp = Tp
+        wq, wk, wv = (attn.to_q.weight.detach(), attn.to_k.weight.detach(), attn.to_v.weight.detach())
+        wo = attn.to_out[0].weight.detach().to(device=dev, dtype=bf).contiguous()
+        bo = attn.to_out[0].bias
+        st.bo = None if bo is None else bo.detach().to(device=dev, dtype=f32).contiguous()
+        if is_self:
+            st.qkv = z(B * T, 3 * C)
+            w = torch.cat([wq, wk, wv], 0).to(device=dev, dtype=bf).contiguous()
+            st.plans = [ops.linear_plan(st.x, w, st.qkv)]
+        else:
+            st.ctx = z(B * Tk, Cctx)
+            st.q = z(B * T, C)
+            st.k = z(B * Tk, C)
+            st.v = z(B * Tk, C)
+            st.plans = [ops.linear_plan(st.x, wq.to(device=dev, dtype=bf).contiguous(), st.q),
+                        ops.linear_plan(st.ctx, wk.to(device=dev, dtype=bf).contiguous(), st.k),
+                        ops.linear_plan(st.ctx, wv.to(device=dev, dtype=bf).contiguous(), st.v)]
+        st.out_plan = ops.linear_plan(st.att, wo, st.out, bias=st.bo)
+        st.heads = heads
+        self._cache[key] = st
+        return st
+
+    def __call__(self, attn, hidden_states, encoder_hidden_states=None, attention_mask=None, temb=None, scale: float = 1.0):
+        if attention_mask is not None:
+            raise NotImplementedError("attention_mask is not on the MirrorFusion path (the pipeline never passes one)")
+        if getattr(attn, "spatial_norm", None) is not None or getattr(attn, "group_norm", None) is not None \
+                or getattr(attn, "norm_cross", None):
+            raise NotImplementedError("spatial_norm / group_norm / norm_cross attention variants are not on the MirrorFusion path")
+        residual = hidden_states
+        input_ndim = hidden_states.ndim
+        if input_ndim == 4:
+            b_, c_, h_, w_ = hidden_states.shape
+            hidden_states = hidden_states.view(b_, c_, h_ * w_).transpose(1, 2)
+        B, T, C = hidden_states.shape
+        is_self = encoder_hidden_states is None
+        Tk = T if is_self else encoder_hidden_states.shape[1]
+        Cctx = C if is_self else encoder_hidden_states.shape[2]
+        heads = attn.heads
+        d = C // heads
+        dev = hidden_states.device
+        st = self._state(attn, B, T, Tk, C, Cctx, is_self, dev)
+        st.x.copy_(hidden_states.reshape(B * T, C))
+        if is_self:
+            st.plans[0].run()
+            ops.transpose_tokens(st.qkv, st.vt, ld=3 * C, col0=2 * C, Cc=C, B=B, T=T, ldt=st.Tp)
+            ops.attention(st.qkv, st.qkv.view(-1)[C:], st.vt, st.att, B=B, heads=heads, head_dim=d, Tq=T, Tk=T, ldq=3 * C,
+                          ldk=3 * C, ldvt=st.Tp, ldo=C)
+        else:
+            st.ctx.copy_(encoder_hidden_states.reshape(B * Tk, Cctx))
+            for p in st.plans:
+                p.run()
+            ops.transpose_tokens(st.v, st.vt, ld=C, col0=0, Cc=C, B=B, T=Tk, ldt=st.Tp)
+            ops.attention(st.q, st.k, st.vt, st.att, B=B, heads=heads, head_dim=d, Tq=T, Tk=Tk, ldq=C, ldk=C, ldvt=st.Tp, ldo=C)
+        st.out_plan.run()
+        out = st.out.view(B, T, C).to(hidden_states.dtype)
+        if input_ndim == 4:
+            out = out.transpose(-1, -2).reshape(b_, c_, h_, w_)
+        if getattr(attn, "residual_connection", False):
+            out = out + residual
+        return out / getattr(attn, "rescale_output_factor", 1.0)
+
+
 class StepEngine:
     """One fused denoise step for `images` images (net batch 2*images, [uncond, cond] halves):
     latents -> BrushNet -> UNet (+taps) -> CFG -> scheduler, all state resident on the device."""
@@ -315,11 +403,19 @@ class MirrorFusionB200Pipeline:
     def __call__(self, prompt=None, image=None, mask=None, depth=None, normals=None, height=None, width=None,
                  num_inference_steps: int = 50, timesteps=None, guidance_scale: float = 7.5, negative_prompt=None,
                  num_images_per_prompt: int = 1, eta: float = 0.0, generator=None, latents=None, prompt_embeds=None,
-                 negative_prompt_embeds=None, output_type: str = "latent", return_dict: bool = True,
+                 negative_prompt_embeds=None, ip_adapter_image=None, ip_adapter_image_embeds=None,
+                 output_type: str = "latent", return_dict: bool = True,
                  cross_attention_kwargs=None, brushnet_conditioning_scale: float = 1.0, guess_mode: bool = False,
                  control_guidance_start: float = 0.0, control_guidance_end: float = 1.0, clip_skip=None,
-                 callback_on_step_end=None, callback_on_step_end_tensor_inputs=("latents",),
-                 conditioning_latents: Optional[torch.Tensor] = None):
+                 callback_on_step_end=None, callback_on_step_end_tensor_inputs=("latents",), **kwargs):
+        """Same parameters, in the same order, as StableDiffusionBrushNetPipeline.__call__ (pipeline_brushnet.py:848-880).
+        One extra keyword rides in **kwargs: `conditioning_latents` ([b or 2b, 6, h, w], what :1188-1202 builds) for
+        callers that keep the VAE outside."""
+        conditioning_latents = kwargs.pop("conditioning_latents", None)
+        if kwargs:
+            raise TypeError(f"unexpected keyword arguments: {sorted(kwargs)}")
+        if ip_adapter_image is not None or ip_adapter_image_embeds is not None:
+            raise NotImplementedError("IP-adapter inputs are not on the MirrorFusion depth-concat path")
         if prompt is not None or negative_prompt is not None:
             raise NotImplementedError("tokenizer / CLIP are outside the hot path: pass prompt_embeds / negative_prompt_embeds")
         if timesteps is not None or eta != 0.0 or guess_mode or num_images_per_prompt != 1:

@@ -41,7 +41,7 @@ class _Base:
     order = 1
     init_noise_sigma = 1.0
 
-    def scale_model_input(self, sample, timestep=None):
+    def scale_model_input(self, sample, *args, **kwargs):
         """Identity for both schedulers (scheduling_ddim.py:238-253, scheduling_unipc_multistep.py:835-849)."""
         return sample
 
@@ -62,8 +62,7 @@ class _Base:
             rows.append(c)
         return torch.tensor(np.stack(rows), dtype=torch.float32)
 
-    def step(self, model_output: torch.Tensor, timestep, sample: torch.Tensor, eta: float = 0.0, generator=None,
-             return_dict: bool = True):
+    def _step(self, model_output: torch.Tensor, timestep, sample: torch.Tensor, eta: float = 0.0, return_dict: bool = True):
         """Reference-compatible single step on an already guided `model_output` (same kernel, g = 0)."""
         if self.num_inference_steps is None:
             raise ValueError("Number of inference steps is 'None', you need to run 'set_timesteps' after creating the scheduler")
@@ -134,6 +133,14 @@ class B200DDIMScheduler(_Base):
 
     def _advance(self, i):
         pass
+
+    def step(self, model_output, timestep, sample, eta: float = 0.0, use_clipped_model_output: bool = False, generator=None,
+             variance_noise=None, return_dict: bool = True):
+        """DDIMScheduler.step (scheduling_ddim.py:344-466), same signature (the pipeline picks `eta` / `generator` by
+        signature inspection, pipeline_brushnet.py:556-571)."""
+        if use_clipped_model_output or variance_noise is not None:
+            raise NotImplementedError("use_clipped_model_output / variance_noise are not on the MirrorFusion path")
+        return self._step(model_output, timestep, sample, eta=eta, return_dict=return_dict)
 
     def coefficients(self, i: int) -> np.ndarray:
         t = int(self._ts[i])
@@ -218,6 +225,10 @@ class B200UniPCScheduler(_Base):
     @property
     def step_index(self):
         return self._step_index
+
+    def step(self, model_output, timestep, sample, return_dict: bool = True):
+        """UniPCMultistepScheduler.step (scheduling_unipc_multistep.py:754-833), same signature."""
+        return self._step(model_output, timestep, sample, return_dict=return_dict)
 
     def _lam(self, k):
         s = float(self.sigmas[k])

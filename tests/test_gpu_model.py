@@ -177,6 +177,53 @@ def test_batched_step_vs_oracle_on_gpu(P):
     assert rel(eps, ref) < TINY_TOL
 
 
+class _FakeAttention(torch.nn.Module):
+    """Stand-in with the attributes the processor contract reads from diffusers' `Attention`
+    (S/models/attention_processor.py:40-216): q/k/v without bias, to_out[0] with bias."""
+
+    def __init__(self, C, ctx, heads):
+        super().__init__()
+        self.heads = heads
+        self.to_q = torch.nn.Linear(C, C, bias=False)
+        self.to_k = torch.nn.Linear(ctx, C, bias=False)
+        self.to_v = torch.nn.Linear(ctx, C, bias=False)
+        self.to_out = torch.nn.ModuleList([torch.nn.Linear(C, C), torch.nn.Dropout(0.0)])
+        self.residual_connection = False
+        self.rescale_output_factor = 1.0
+        self.spatial_norm = self.group_norm = None
+        self.norm_cross = None
+
+
+@pytest.mark.parametrize("C,heads,T,ctx,Tk", [(320, 8, 1024, None, None), (640, 8, 256, 768, 77), (320, 8, 4096, 768, 77)])
+def test_attention_processor_contract(P, C, heads, T, ctx, Tk):
+    """B200AttnProcessor against the math of AttnProcessor2_0 (attention_processor.py:1213-1286) on a module with the
+    reference's attribute layout: 3-D and 4-D inputs, self- and cross-attention."""
+    torch.manual_seed(0)
+    attn = _FakeAttention(C, ctx or C, heads).cuda()
+    proc = P.B200AttnProcessor()
+    B = 2
+    hs = torch.randn(B, T, C, device="cuda")
+    ehs = None if ctx is None else torch.randn(B, Tk, ctx, device="cuda")
+    got = proc(attn, hs, encoder_hidden_states=ehs)
+    src = hs if ehs is None else ehs
+    d = C // heads
+    with torch.no_grad():
+        q = attn.to_q(hs).view(B, -1, heads, d).transpose(1, 2)
+        k = attn.to_k(src).view(B, -1, heads, d).transpose(1, 2)
+        v = attn.to_v(src).view(B, -1, heads, d).transpose(1, 2)
+        ref = torch.nn.functional.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(B, T, C)
+        ref = attn.to_out[0](ref)
+    assert got.shape == ref.shape and got.dtype == hs.dtype
+    assert rel(got, ref) < 1.5e-2
+    if ctx is None:      # 4-D (B, C, H, W) entry of the contract
+        side = int(T ** 0.5)
+        got4 = proc(attn, hs.transpose(1, 2).reshape(B, C, side, side).contiguous())
+        assert got4.shape == (B, C, side, side)
+        assert rel(got4.reshape(B, C, T).transpose(1, 2), ref) < 1.5e-2
+    with pytest.raises(NotImplementedError):
+        proc(attn, hs, encoder_hidden_states=ehs, attention_mask=torch.zeros(1, device="cuda"))
+
+
 def test_scheduler_step_api(P):
     from oracle import mf_oracle as O
     g = torch.Generator().manual_seed(5)
