@@ -224,6 +224,42 @@ def test_attention_processor_contract(P, C, heads, T, ctx, Tk):
         proc(attn, hs, encoder_hidden_states=ehs, attention_mask=torch.zeros(1, device="cuda"))
 
 
+@pytest.mark.parametrize("sched_kind,steps", [("ddim", 4), ("unipc", 5)])
+def test_pipeline_call_vs_oracle_loop(P, sched_kind, steps):
+    """MirrorFusionB200Pipeline.__call__ (reference argument names) end to end on TINY: CFG batch order, the
+    brushnet_keep window (control_guidance_end < 1 switches the taps off for the last steps), per-step callback —
+    against the oracle's restatement of the loop body (pipeline_brushnet.py:1250-1315).  BASELINE config 1 is the
+    4-step DDIM case."""
+    from oracle import mf_oracle as O
+    cfg = TINY
+    usd, bsd = make_state_dict(cfg, "unet"), make_state_dict(cfg, "brushnet")
+    inp = make_inputs(cfg, 2, seed=11)
+    sched = P.B200DDIMScheduler() if sched_kind == "ddim" else P.B200UniPCScheduler()
+    pipe = P.MirrorFusionB200Pipeline(usd, bsd, scheduler=sched, cfg=cfg)
+    seen = []
+    def cb(pipe_, i, t, kw):
+        seen.append((i, int(t), tuple(kw["latents"].shape)))
+        return {}
+    end = 0.75
+    out = pipe(prompt_embeds=inp["prompt_embeds"][2:].cuda(), negative_prompt_embeds=inp["prompt_embeds"][:2].cuda(),
+               conditioning_latents=inp["conditioning_latents"][:2].cuda(), latents=inp["latents"].cuda(),
+               num_inference_steps=steps, guidance_scale=7.5, brushnet_conditioning_scale=0.9, control_guidance_end=end,
+               callback_on_step_end=cb, output_type="latent").images
+    assert [s_[0] for s_ in seen] == list(range(steps)) and seen[0][2] == (2, 4, cfg.sample_size, cfg.sample_size)
+    osched = O.DDIMOracle() if sched_kind == "ddim" else O.UniPCOracle()
+    osched.set_timesteps(steps)
+    lat = inp["latents"].clone()
+    with torch.no_grad():
+        for i, t in enumerate(osched.timesteps):
+            keep = 1.0 - float(i / steps < 0.0 or (i + 1) / steps > end)                # pipeline_brushnet.py:1236-1242
+            eps, _ = O.noise_pred_step(usd, bsd, cfg, torch.cat([lat] * 2), t, inp["prompt_embeds"],
+                                       inp["conditioning_latents"], 0.9 * keep)
+            lat = osched.step(O.cfg_combine(eps, 7.5), t, lat)
+    e = rel(out, lat)
+    record("tiny_pipeline_call_vs_oracle", scheduler=sched_kind, steps=steps, latents=e)
+    assert e < 4e-2
+
+
 def test_scheduler_step_api(P):
     from oracle import mf_oracle as O
     g = torch.Generator().manual_seed(5)
