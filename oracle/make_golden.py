@@ -136,6 +136,48 @@ def golden_sched_only(diffusers, name):
     print(f"{name}: scheduler trajectories written")
 
 
+def golden_psnr(diffusers, steps=20):
+    """Final-image protocol of north_star: run the REFERENCE loop (SD1.5-shaped random-init nets, UniPC, CFG 7.5, fp32 CPU),
+    keep the final latents, and trace a small random-init reference AutoencoderKL decoder to TorchScript so that the
+    GPU box (no reference there) can decode both sides with the same VAE and measure PSNR on uint8 images."""
+    from mirrorfusion_b200.config import SD15
+    from mirrorfusion_b200.synth import make_inputs
+    torch.manual_seed(123)
+    vae = diffusers.AutoencoderKL(in_channels=3, out_channels=3, down_block_types=("DownEncoderBlock2D",) * 2,
+                                  up_block_types=("UpDecoderBlock2D",) * 2, block_out_channels=(32, 64), layers_per_block=1,
+                                  latent_channels=4, norm_num_groups=8, sample_size=128, scaling_factor=0.18215).eval()
+
+    class Dec(torch.nn.Module):
+        def __init__(self, v):
+            super().__init__()
+            self.v = v
+
+        def forward(self, z):
+            return self.v.decode(z / 0.18215, return_dict=False)[0]          # pipeline_brushnet.py:1342
+
+    with torch.no_grad():
+        ts = torch.jit.trace(Dec(vae), torch.randn(1, 4, 64, 64), check_trace=False)
+    ts.save(os.path.join(GOLD, "tiny_vae_decoder.pt"))
+    unet, bn, _, _ = build_reference_nets(diffusers, SD15, 0)
+    inp = make_inputs(SD15, 1)
+    base = diffusers.DDIMScheduler(beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear",
+                                   clip_sample=False, set_alpha_to_one=False, steps_offset=1)
+    sched = diffusers.UniPCMultistepScheduler.from_config(base.config)
+    sched.set_timesteps(steps)
+    lat = inp["latents"] * sched.init_noise_sigma
+    t0 = time.time()
+    for t in sched.timesteps:
+        x = torch.cat([lat] * 2)
+        eps, *_ = ref_step(unet, bn, x, t, inp["prompt_embeds"], inp["conditioning_latents"])
+        u_, c_ = eps.chunk(2)
+        lat = sched.step(u_ + 7.5 * (c_ - u_), t, lat, return_dict=False)[0]
+    with torch.no_grad():
+        img = ts(lat)
+    np.savez_compressed(os.path.join(GOLD, "sd15_loop_unipc%d_final.npz" % steps), latents=lat.numpy(), image=img.numpy(),
+                        steps=np.int64(steps), guidance=np.float64(7.5))
+    print(f"sd15 {steps}-step reference loop: {time.time() - t0:.0f}s, |lat|={lat.norm():.3f}, image range [{img.min():.2f},{img.max():.2f}]")
+
+
 def golden_signatures(diffusers, name):
     """Parameter names (in order) of the reference entry points the drop-in classes mirror."""
     import inspect
@@ -170,6 +212,8 @@ def main():
     diffusers = import_reference()
     from mirrorfusion_b200.config import MICRO, TINY, SD15
     which = sys.argv[1:] or ["sched", "micro", "tiny", "sd15", "sigs"]
+    if "psnr" in which:
+        golden_psnr(diffusers)
     if "sigs" in which:
         golden_signatures(diffusers, "reference_signatures.json")
     if "sched" in which:

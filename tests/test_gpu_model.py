@@ -260,6 +260,38 @@ def test_pipeline_call_vs_oracle_loop(P, sched_kind, steps):
     assert e < 4e-2
 
 
+def test_sd15_final_image_psnr_vs_reference(P, golden_dir):
+    """north_star: final decoded images within PSNR >= 40 dB of the reference.  The reference loop (SD1.5-shaped nets,
+    20 UniPC steps, CFG 7.5, fp32 CPU) was run by oracle/make_golden.py; both sides' final latents go through the SAME
+    traced reference AutoencoderKL decoder (tests/golden/tiny_vae_decoder.pt) and PSNR is taken on uint8 images like
+    M/metrics/metrics.py:62-67 (10 log10(255^2 / mse))."""
+    path = os.path.join(golden_dir, "sd15_loop_unipc20_final.npz")
+    if not os.path.exists(path):
+        pytest.skip("sd15_loop_unipc20_final.npz not generated")
+    g = np.load(path)
+    cfg = SD15
+    usd, bsd = make_state_dict(cfg, "unet"), make_state_dict(cfg, "brushnet")
+    inp = make_inputs(cfg, 1)
+    eng = P.StepEngine(cfg, usd, bsd, 1, 64, 64, use_graph=True)
+    eng.set_conditioning(inp["prompt_embeds"].cuda(), inp["conditioning_latents"].cuda())
+    lat = eng.denoise(inp["latents"].cuda(), P.B200UniPCScheduler(), int(g["steps"]), float(g["guidance"])).cpu()
+    dec = torch.jit.load(os.path.join(golden_dir, "tiny_vae_decoder.pt"))
+    with torch.no_grad():
+        img = dec(lat)
+        img_ref = dec(torch.from_numpy(g["latents"]))
+    assert rel(img_ref, g["image"]) < 1e-4                     # the traced decoder reproduces the reference decode here
+
+    def to_u8(x):                                              # VaeImageProcessor.postprocess: (x/2+0.5).clamp(0,1) -> uint8
+        return ((x / 2 + 0.5).clamp(0, 1) * 255).round()
+
+    mse = (to_u8(img) - to_u8(img_ref)).pow(2).mean().item()
+    psnr = 10 * np.log10(255.0 ** 2 / max(mse, 1e-12))
+    e_lat = rel(lat, g["latents"])
+    record("sd15_unipc20_final_image", psnr_db=float(psnr), latents_rel_l2=e_lat)
+    assert e_lat < 3e-2
+    assert psnr >= 40.0, psnr
+
+
 def test_scheduler_step_api(P):
     from oracle import mf_oracle as O
     g = torch.Generator().manual_seed(5)
