@@ -40,6 +40,8 @@ class _Net:
         self.flops = 0.0
         self.launches = 0
         self.n_time_ops = 0
+        self.writer_pos: Dict[int, int] = {}      # data_ptr of a produced tensor -> program position of its writer
+        self.ext_reads: Dict[int, List[int]] = {}  # program position -> data_ptrs it reads (candidates for cross-net deps)
         # fused BrushNet taps: (packed weight, column offset, C, zero-conv weight [C,C] f32, bias buffer, base bias, zero-conv bias)
         self.fused_taps: List[Tuple] = []
         G = cfg.norm_num_groups
@@ -74,15 +76,23 @@ class _Net:
             bias_buf.copy_(base_bias + s * bz)
 
     # ---- op emitters
-    def emit(self, fn: Callable[[], None], n_launch: int = 1, tag: str = "misc", flops: float = 0.0):
+    def emit(self, fn: Callable[[], None], n_launch: int = 1, tag: str = "misc", flops: float = 0.0, out=None, reads=()):
+        """`out` / `reads`: tensors this entry writes / reads that may belong to the OTHER network's engine — the
+        two-stream scheduler of StepEngine turns them into cross-stream events."""
+        pos = len(self.prog)
         self.prog.append(fn)
         self.tags.append((tag, flops))
         self.launches += n_launch
+        if out is not None:
+            self.writer_pos[out.data_ptr()] = pos
+        ext = [t.data_ptr() for t in reads if t is not None]
+        if ext:
+            self.ext_reads[pos] = ext
 
-    def emit_plan(self, plan: ops.ConvPlan):
+    def emit_plan(self, plan: ops.ConvPlan, out=None, reads=()):
         self.keep.append(plan)
         self.flops += plan.flops
-        self.emit(plan.run, getattr(plan, "launches", 1), "igemm", plan.flops)
+        self.emit(plan.run, getattr(plan, "launches", 1), "igemm", plan.flops, out=out, reads=reads)
 
     def groupnorm(self, x1, x2, prefix: str, out, HW: int, eps: float, silu: bool):
         g, b = self.wf(prefix + ".weight"), self.wf(prefix + ".bias")
@@ -182,7 +192,7 @@ class _Net:
         if fused is not None:
             self._register_fused(w2, fused[0], fused[1], bias_buf, base_bias, fused[2])
         self.emit_plan(ops.ConvPlan(n2, w2, out, B=B, H=h, W=w, Cin=cout, Cout=cout, ksize=3, extras=extras_x,
-                                    bias=bias_buf, res1=res1, res2=tap))
+                                    bias=bias_buf, res1=res1, res2=tap), out=out, reads=list(extras_x) + [tap])
         return out
 
     def _sampler_conv(self, p: str, x, out, h, w, stride, tap, tap_src):
@@ -196,7 +206,7 @@ class _Net:
         if tap_src is not None:
             self._register_fused(wp, 9 * c, tap_src[1], bias_buf, base_bias, tap_src[2])
         self.emit_plan(ops.ConvPlan(x, wp, out, B=self.B, H=h, W=w, Cin=c, Cout=c, ksize=3, stride=stride, extras=extras_x,
-                                    bias=bias_buf, res2=tap))
+                                    bias=bias_buf, res2=tap), out=out, reads=list(extras_x) + [tap])
 
     def downsample(self, p: str, x, hw, tap=None, tap_src=None):
         h, w = hw
@@ -220,7 +230,7 @@ class _Net:
         if tap_src is not None:
             self._register_fused(wp.view(4 * c, -1), 4 * c, tap_src[1].repeat(4, 1), bias_buf, base_bias, tap_src[2])
         self.emit_plan(ops.ConvPlan(x, wp, out, B=self.B, H=h, W=w, Cin=c, Cout=c, ksize=3, up2x=True, extras=extras_x,
-                                    bias=bias_buf, res2=tap))
+                                    bias=bias_buf, res2=tap), out=out, reads=list(extras_x) + [tap])
         return out
 
     def run(self):
@@ -278,7 +288,7 @@ class BrushNetEngine(_Net):
         bci = self.wf("conv_in_condition.bias")
         x = self.buf(B, H * W, boc[0])
         self.keep += [wci, bci]
-        self.emit(lambda x0=x: ops.conv_in(self.sample_in, self.cond_in, wci, bci, x0))   # bind now: `x` is reassigned below
+        self.emit(lambda x0=x: ops.conv_in(self.sample_in, self.cond_in, wci, bci, x0), out=x)   # bind now: `x` is reassigned below
         hw = (H, W)
         feats: List[Tuple[torch.Tensor, Tuple[int, int]]] = [(x, hw)]
         for i in range(n):
@@ -320,7 +330,7 @@ class BrushNetEngine(_Net):
             t = tap_bufs[k] if tap_bufs is not None else self.buf(B, shw[0] * shw[1], c)
             wz = ops.pack_conv_weight(self.sd[nm + ".weight"])
             self.emit_plan(ops.ConvPlan(src, wz, t, B=B, H=shw[0], W=shw[1], Cin=c, Cout=c, ksize=1,
-                                        bias=self.wf(nm + ".bias"), alpha=self.scale))
+                                        bias=self.wf(nm + ".bias"), alpha=self.scale), out=t)
             self.taps.append(t)
             self.tap_hw.append(shw)
         self.n_down = len(down_feats)
@@ -377,7 +387,7 @@ class UNetEngine(_Net):
         pre = self.buf(B, H * W, boc[0])      # first skip keeps the PRE-tap conv_in output (unet_2d_condition.py:1215-1218)
         x = self.buf(B, H * W, boc[0])
         tap0, _ = next(tap_it)
-        self.emit(lambda x0=x: ops.conv_in(self.sample_in, None, wci, bci, pre, tap0, x0))  # bind now: `x` is reassigned below
+        self.emit(lambda x0=x: ops.conv_in(self.sample_in, None, wci, bci, pre, tap0, x0), reads=[tap0])  # bind now: `x` is reassigned below
         skips = [(pre, hw)]
         for i in range(n):
             for j in range(cfg.layers_per_block):
@@ -491,7 +501,7 @@ class UNetEngine(_Net):
         if tap_src is not None:
             self._register_fused(wpo, C, tap_src[1], bias_buf, base_bias, tap_src[2])
         self.emit_plan(ops.linear_plan(h3, wpo, out.view(M, C), extras=extras_x, bias=bias_buf, res1=x.view(M, C),
-                                       res2=None if tap is None else tap.view(M, C)))
+                                       res2=None if tap is None else tap.view(M, C)), out=out, reads=list(extras_x) + [tap])
         return out
 
     def set_context(self, ehs: torch.Tensor):

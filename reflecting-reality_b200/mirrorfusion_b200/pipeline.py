@@ -249,7 +249,7 @@ class StepEngine:
     latents -> BrushNet -> UNet (+taps) -> CFG -> scheduler, all state resident on the device."""
 
     def __init__(self, cfg: NetConfig, unet_sd, brushnet_sd, images: int, H: int, W: int, device="cuda",
-                 use_graph: bool = True, fuse_taps: bool = True):
+                 use_graph: bool = True, fuse_taps: bool = True, two_streams: bool = True):
         self.cfg, self.images, self.H, self.W = cfg, images, H, W
         self.dev = torch.device(device)
         B = 2 * images
@@ -263,6 +263,8 @@ class StepEngine:
             self.unet = UNetEngine(cfg, unet_sd, B, H, W, self.dev)
             self.bn = BrushNetEngine(cfg, brushnet_sd, B, H, W, self.dev, tap_bufs=self.unet.taps)
         self._tap_scale = 1.0
+        self.two_streams = two_streams
+        self._side_stream = torch.cuda.Stream(device=self.dev) if two_streams else None
         self.time_tables = None     # (timesteps, brushnet table, unet table) once prepare_timesteps() has run
         z = lambda: torch.zeros(images, cfg.in_channels, H, W, device=self.dev, dtype=f32)
         self.x, self.last, self.m0, self.m1 = z(), z(), z(), z()
@@ -281,12 +283,13 @@ class StepEngine:
         for e in (self.bn, self.unet):                    # latent_model_input = cat([latents] * 2) (:1256)
             e.sample_in[:n].copy_(self.x)
             e.sample_in[n:].copy_(self.x)
-        if self.time_tables is None:
-            self.bn.run()
-            self.unet.run()
-        else:                                             # timestep path hoisted: row biases were copied in by step()
-            self.bn.run_main()
-            self.unet.run_main()
+        skip = 0 if self.time_tables is None else None    # hoisted timestep path: row biases were copied in by step()
+        if self.two_streams:
+            self._run_two_streams(skip)
+        else:
+            for e in (self.bn, self.unet):
+                for f in e.prog[(e.n_time_ops if skip is None else 0):]:
+                    f()
         eps = self.unet.out
         ops.cfg_sched_step(eps[:n], eps[n:], self.x, self.last, self.m0, self.m1, self.coef)
 
@@ -299,6 +302,35 @@ class StepEngine:
         ts = [float(t) for t in timesteps]
         self.time_tables = ({t: i for i, t in enumerate(ts)}, self.bn.timestep_table(ts), self.unet.timestep_table(ts))
         self.launches_per_step = self.unet.launches + self.bn.launches + 1 - 8
+
+    def _run_two_streams(self, skip):
+        """BrushNet on a side stream, UNet on the current one.  The UNet entry that consumes BrushNet tensor k (a fused
+        zero-conv K-segment or the conv_in-site tap) waits on an event recorded right after the BrushNet entry that
+        writes it, so BrushNet runs ahead and its bandwidth-bound kernels (GroupNorm, boundary convs) overlap the UNet's
+        tensor-bound ones and vice versa.  Works eagerly and under CUDA-graph capture (fork/join on the capture stream)."""
+        cur = torch.cuda.current_stream()
+        side = self._side_stream
+        b0 = self.bn.n_time_ops if skip is None else 0
+        u0 = self.unet.n_time_ops if skip is None else 0
+        # UNet position -> BrushNet position it depends on
+        need = {}
+        for pos, ptrs in self.unet.ext_reads.items():
+            deps = [self.bn.writer_pos[p] for p in ptrs if p in self.bn.writer_pos]
+            if deps and pos >= u0:
+                need[pos] = max(deps)
+        wanted = sorted(set(need.values()))
+        events = {bp: torch.cuda.Event() for bp in wanted}
+        side.wait_stream(cur)                                        # fork
+        with torch.cuda.stream(side):
+            for i in range(b0, len(self.bn.prog)):
+                self.bn.prog[i]()
+                if i in events:
+                    events[i].record(side)
+        for i in range(u0, len(self.unet.prog)):
+            if i in need:
+                cur.wait_event(events[need[i]])
+            self.unet.prog[i]()
+        cur.wait_stream(side)                                        # join
 
     def step(self, t: float, coef_row: torch.Tensor, scale: float = 1.0):
         if self.time_tables is not None:
