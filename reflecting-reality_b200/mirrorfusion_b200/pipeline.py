@@ -249,7 +249,7 @@ class StepEngine:
     latents -> BrushNet -> UNet (+taps) -> CFG -> scheduler, all state resident on the device."""
 
     def __init__(self, cfg: NetConfig, unet_sd, brushnet_sd, images: int, H: int, W: int, device="cuda",
-                 use_graph: bool = True, fuse_taps: bool = True, two_streams: bool = True):
+                 use_graph: bool = True, fuse_taps: bool = True, two_streams: bool = False):
         self.cfg, self.images, self.H, self.W = cfg, images, H, W
         self.dev = torch.device(device)
         B = 2 * images
