@@ -82,6 +82,13 @@ int mfb_plan_destroy(mfb_plan* plan);
 double mfb_plan_flops(const mfb_plan* plan); /* 2*M*N*Ktot */
 int mfb_plan_ktotal(const mfb_plan* plan);
 int mfb_plan_launches(const mfb_plan* plan); /* kernel launches per mfb_plan_run (4 for up2x plans) */
+/* Fused GroupNorm statistics: the epilogue can also emit, per (image, tile, output channel), the sum and sum of squares
+ * of the bf16 values it stores — the statistics F.group_norm of the CONSUMER would otherwise re-read the tensor for
+ * (S/models/resnet.py:337,381).  mfb_plan_stats_floats = size of the [B][tiles][Cout][2] fp32 buffer to provide
+ * (0: this plan cannot — GEGLU, or tiles that straddle images); mfb_plan_set_stats installs it (NULL = off). */
+long long mfb_plan_stats_floats(const mfb_plan* plan);
+int mfb_plan_stats_tiles(const mfb_plan* plan);
+int mfb_plan_set_stats(mfb_plan* plan, float* buf);
 
 /* ------------------------------------------------------------------------------------------------------------
  * GroupNorm (+SiLU) over NHWC bf16, fp32 statistics.  Replaces F.group_norm + F.silu in ResnetBlock2D
@@ -95,6 +102,12 @@ int mfb_plan_launches(const mfb_plan* plan); /* kernel launches per mfb_plan_run
 #define MFB_GN_WS_FLOATS(B, groups) (2 * (B) * (groups) * (1 + MFB_GN_MAX_CHUNKS) + (B))
 int mfb_groupnorm(const void* x1, int C1, const void* x2, int C2, int B, int HW, int groups, float eps,
                   const float* gamma, const float* beta, int silu, float* stats_ws, void* out, void* stream);
+
+/* Same, with the statistics of each source already available as igemm partials (mfb_plan_set_stats): the full-tensor
+ * statistics pass is replaced by a tiny fixed-order reduction. */
+int mfb_groupnorm_prestat(const void* x1, int C1, const float* part1, int tiles1, const void* x2, int C2, const float* part2,
+                          int tiles2, int B, int HW, int groups, float eps, const float* gamma, const float* beta, int silu,
+                          float* stats_ws, void* out, void* stream);
 
 /* LayerNorm over the last dim of [rows, C] bf16 (S/models/attention.py:313,360,386). */
 int mfb_layernorm(const void* x, int rows, int C, float eps, const float* gamma, const float* beta, void* out,

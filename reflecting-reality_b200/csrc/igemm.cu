@@ -65,6 +65,9 @@ struct IgemmParams {
     __nv_bfloat16* out;    // [M, out_ld]
     int out_ld;
     int geglu;             // BN == 128 only: cols [0,64) value, [64,128) gate -> out[:, nt*64 + j]
+    float* stats;          // optional per-(image, tile, channel) {sum, sumsq} of the bf16 OUTPUT (GroupNorm statistics of the
+                           // consumer, fused here): [Bn][stats_tiles][out_ld][2]; null = off
+    int stats_tiles, stats_tile_base;
     int o_step, o_py, o_px, o_Hf, o_Wf;   // rows map to output pixel (o_step*oh + o_py, o_step*ow + o_px) of [Bn, o_Hf, o_Wf]
 };
 
@@ -393,6 +396,32 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 1) igemm_kernel(const __grid_co
             }
             fence_proxy_async_smem();                  // generic-proxy writes of the staging tile -> visible to TMA
             named_bar_sync(1, IGEMM_EPI_WARPS * 32);
+            if (p.stats != nullptr && int(threadIdx.x) < bn_out && nt * bn_out + int(threadIdx.x) < p.out_ld) {
+                // Fused GroupNorm statistics: thread = output channel; sum / sum-of-squares of the ROUNDED (bf16) values of
+                // this tile's valid rows, per image, read back from the staging tile.  Written (not accumulated) to a
+                // per-(image, tile) slot, so the consumer's reduction order is fixed -> deterministic.
+                const int c = threadIdx.x;
+                const int vw = min(p.tw, p.Wo - w0), vh = min(p.th, p.Ho - h0), vn = min(p.tn, p.Bn - n0);
+                const int tile_in_img = (p.tn == 1 ? mt % (p.tiles_w * p.tiles_h) : 0) + p.stats_tile_base;
+                const uint8_t* colp = stg_gen + (c & 7) * 2;
+                for (int in_ = 0; in_ < vn; ++in_) {
+                    float sm = 0.f, sq = 0.f;
+                    for (int ih = 0; ih < vh; ++ih) {
+                        const int rbase = (in_ * p.th + ih) * p.tw;
+                        for (int iw = 0; iw < vw; ++iw) {
+                            const float v = __bfloat162float(
+                                *reinterpret_cast<const __nv_bfloat16*>(colp + stg_off<BOXC>(rbase + iw, c & ~7)));
+                            sm += v;
+                            sq = fmaf(v, v, sq);
+                        }
+                    }
+                    float2* dst = reinterpret_cast<float2*>(p.stats) +
+                                  (static_cast<size_t>(n0 + in_) * p.stats_tiles + tile_in_img) * p.out_ld + nt * bn_out + c;
+                    *dst = make_float2(sm, sq);
+                }
+            }
+            // the next tile's res1 TMA load overwrites the staging tile: nobody may still be reading it
+            if (p.stats != nullptr) named_bar_sync(1, IGEMM_EPI_WARPS * 32);
             if (leader) {
                 for (int bx = 0; bx < nbox; ++bx)
                     tma_store_4d(&p.tmOut, stg_base + bx * (BM * BOXC * 2), nt * bn_out + bx * BOXC, w0, h0, n0);
@@ -421,6 +450,9 @@ struct Plan {
     int bn;
     int mode;   // 0 independent CTAs, 1 pair + weight multicast, 2 pair + cta_group::2 UMMA
     int ktot;
+    int stats_tiles;    // per-image tile slots of the fused GroupNorm statistics (0 = not supported for this plan)
+    int stats_C;
+    int stats_B;
     double flops;
 };
 
@@ -580,6 +612,18 @@ static int build_params(const mfb_conv_desc* d, int up_py, int up_px, const void
             if (rc) return rc;
         }
     }
+    {
+        // fused output statistics are available when every tile belongs to ONE image, or one tile covers whole images
+        const int per_img = p.tiles_w * p.tiles_h;
+        const bool ok = !d->geglu && (p.tn == 1 || per_img == 1);
+        const int nphase = up ? 4 : 1;
+        pl->stats_tiles = ok ? per_img * nphase : 0;
+        pl->stats_C = d->Cout;
+        pl->stats_B = B;
+        p.stats = nullptr;
+        p.stats_tiles = pl->stats_tiles;
+        p.stats_tile_base = up ? (up_py * 2 + up_px) * per_img : 0;
+    }
     p.bias = d->bias;
     p.rowbias = d->rowbias;
     p.rowbias_ld = d->rowbias_ld;
@@ -663,6 +707,22 @@ extern "C" int mfb_plan_run(mfb_plan* plan, void* stream) {
 }
 
 extern "C" int mfb_plan_launches(const mfb_plan* plan) { return plan ? reinterpret_cast<const Plan*>(plan)->nlaunch : 0; }
+
+// Fused GroupNorm statistics of the plan's output: number of floats the caller must provide (0 = unsupported)...
+extern "C" long long mfb_plan_stats_floats(const mfb_plan* plan) {
+    if (!plan) return 0;
+    const Plan* pl = reinterpret_cast<const Plan*>(plan);
+    return 2LL * pl->stats_B * pl->stats_tiles * pl->stats_C;
+}
+extern "C" int mfb_plan_stats_tiles(const mfb_plan* plan) { return plan ? reinterpret_cast<const Plan*>(plan)->stats_tiles : 0; }
+// ... and the buffer [B][tiles][C][2] fp32 the epilogue writes them to (NULL switches the fusion off).
+extern "C" int mfb_plan_set_stats(mfb_plan* plan, float* buf) {
+    MFB_REQUIRE(plan, "null plan");
+    Plan* pl = reinterpret_cast<Plan*>(plan);
+    MFB_REQUIRE(pl->stats_tiles > 0 || !buf, "this plan cannot produce output statistics");
+    for (int i = 0; i < pl->nlaunch; ++i) pl->p[i].stats = buf;
+    return MFB_OK;
+}
 
 extern "C" int mfb_plan_destroy(mfb_plan* plan) {
     delete reinterpret_cast<Plan*>(plan);

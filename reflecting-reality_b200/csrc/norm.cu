@@ -142,6 +142,42 @@ __global__ void gn_stats_kernel(const __nv_bfloat16* __restrict__ x1, int C1, co
     }
 }
 
+// Statistics already produced by the igemm epilogue as per-(image, tile, channel) partials: reduce them to
+// stats[b][g] in a fixed order.  grid (B), block (8 lanes x groups): lane j of group g takes every 8th (channel, tile)
+// pair of the group, then the 8 partials are added in lane order.
+__global__ void gn_finalize_kernel(const float2* __restrict__ part1, int C1, int tiles1, const float2* __restrict__ part2, int C2,
+                                   int tiles2, int groups, float* __restrict__ stats) {
+    __shared__ float2 red[64 * 8];
+    pdl_trigger();
+    pdl_wait();
+    const int b = blockIdx.x;
+    const int g = threadIdx.x >> 3, j = threadIdx.x & 7;
+    const int C = C1 + C2, cpg = C / groups;
+    float sm = 0.f, sq = 0.f;
+    if (g < groups) {
+        for (int ci = j; ci < cpg; ci += 8) {
+            const int c = g * cpg + ci;
+            const float2* src;
+            int tiles, Cs, cc;
+            if (c < C1) { src = part1; tiles = tiles1; Cs = C1; cc = c; } else { src = part2; tiles = tiles2; Cs = C2; cc = c - C1; }
+            const float2* pb = src + static_cast<size_t>(b) * tiles * Cs + cc;
+            for (int t = 0; t < tiles; ++t) {
+                const float2 v = __ldcg(pb + static_cast<size_t>(t) * Cs);
+                sm += v.x;
+                sq += v.y;
+            }
+        }
+        red[threadIdx.x] = make_float2(sm, sq);
+    }
+    __syncthreads();
+    if (g < groups && j == 0) {
+        float a = 0.f, q2 = 0.f;
+        for (int k = 0; k < 8; ++k) { a += red[g * 8 + k].x; q2 += red[g * 8 + k].y; }
+        stats[(static_cast<size_t>(b) * groups + g) * 2 + 0] = a;
+        stats[(static_cast<size_t>(b) * groups + g) * 2 + 1] = q2;
+    }
+}
+
 __global__ void gn_apply_kernel(const __nv_bfloat16* __restrict__ x1, int C1, const __nv_bfloat16* __restrict__ x2, int C2,
                                 int HW, int groups, int pix_per_cta, const float* __restrict__ stats, float eps,
                                 const float* __restrict__ gamma, const float* __restrict__ beta, int silu,
@@ -269,8 +305,9 @@ __global__ void layernorm_kernel(const __nv_bfloat16* __restrict__ x, int rows, 
 
 using namespace mfb;
 
-extern "C" int mfb_groupnorm(const void* x1, int C1, const void* x2, int C2, int B, int HW, int groups, float eps,
-                             const float* gamma, const float* beta, int silu, float* stats_ws, void* out, void* stream) {
+static int groupnorm_impl(const void* x1, int C1, const void* x2, int C2, int B, int HW, int groups, float eps, const float* gamma,
+                          const float* beta, int silu, float* stats_ws, void* out, void* stream, const float* part1, int tiles1,
+                          const float* part2, int tiles2) {
     MFB_REQUIRE(x1 && out && gamma && beta && stats_ws, "null pointer");
     if (!x2) C2 = 0;
     const int C = C1 + C2;
@@ -292,12 +329,31 @@ extern "C" int mfb_groupnorm(const void* x1, int C1, const void* x2, int C2, int
     float* part = stats_ws + static_cast<size_t>(2) * B * groups;
     unsigned int* counters = reinterpret_cast<unsigned int*>(part + static_cast<size_t>(2) * B * groups * MFB_GN_MAX_CHUNKS);
     dim3 grid(chunks, B), block(CV, PY);
-    MFB_CUDA_OK(launch_k(gn_stats_kernel, grid, block, 0, st, 1, static_cast<const __nv_bfloat16*>(x1), C1,
-                         static_cast<const __nv_bfloat16*>(x2), C2, HW, groups, ppc, stats_ws, part, counters));
+    if (part1 != nullptr && (C2 == 0 || part2 != nullptr)) {
+        // statistics came with the producing GEMM(s): only the tiny fixed-order reduction is left
+        MFB_CUDA_OK(launch_k(gn_finalize_kernel, dim3(B), dim3(8 * groups), 0, st, 1, reinterpret_cast<const float2*>(part1), C1, tiles1,
+                             reinterpret_cast<const float2*>(part2), C2, tiles2, groups, stats_ws));
+    } else {
+        MFB_CUDA_OK(launch_k(gn_stats_kernel, grid, block, 0, st, 1, static_cast<const __nv_bfloat16*>(x1), C1,
+                             static_cast<const __nv_bfloat16*>(x2), C2, HW, groups, ppc, stats_ws, part, counters));
+    }
     MFB_CUDA_OK(launch_k(gn_apply_kernel, grid, block, 0, st, 1, static_cast<const __nv_bfloat16*>(x1), C1,
                          static_cast<const __nv_bfloat16*>(x2), C2, HW, groups, ppc, static_cast<const float*>(stats_ws), eps, gamma,
                          beta, silu, static_cast<__nv_bfloat16*>(out)));
     return MFB_OK;
+}
+
+extern "C" int mfb_groupnorm(const void* x1, int C1, const void* x2, int C2, int B, int HW, int groups, float eps,
+                             const float* gamma, const float* beta, int silu, float* stats_ws, void* out, void* stream) {
+    return groupnorm_impl(x1, C1, x2, C2, B, HW, groups, eps, gamma, beta, silu, stats_ws, out, stream, nullptr, 0, nullptr, 0);
+}
+
+extern "C" int mfb_groupnorm_prestat(const void* x1, int C1, const float* part1, int tiles1, const void* x2, int C2,
+                                     const float* part2, int tiles2, int B, int HW, int groups, float eps, const float* gamma,
+                                     const float* beta, int silu, float* stats_ws, void* out, void* stream) {
+    MFB_REQUIRE(part1 && tiles1 > 0 && (!x2 || (part2 && tiles2 > 0)), "mfb_groupnorm_prestat needs the partial statistics of every source");
+    MFB_REQUIRE(groups <= 64, "at most 64 groups");
+    return groupnorm_impl(x1, C1, x2, C2, B, HW, groups, eps, gamma, beta, silu, stats_ws, out, stream, part1, tiles1, part2, tiles2);
 }
 
 extern "C" int mfb_layernorm(const void* x, int rows, int C, float eps, const float* gamma, const float* beta, void* out,

@@ -42,6 +42,9 @@ class _Net:
         self.n_time_ops = 0
         self.writer_pos: Dict[int, int] = {}      # data_ptr of a produced tensor -> program position of its writer
         self.ext_reads: Dict[int, List[int]] = {}  # program position -> data_ptrs it reads (candidates for cross-net deps)
+        # GroupNorm statistics produced by the igemm epilogue that wrote a tensor: data_ptr -> (partials buffer, tiles)
+        self.stats_of: Dict[int, Tuple[torch.Tensor, int]] = {}
+        self.fuse_gn_stats = True
         # fused BrushNet taps: (packed weight, column offset, C, zero-conv weight [C,C] f32, bias buffer, base bias, zero-conv bias)
         self.fused_taps: List[Tuple] = []
         G = cfg.norm_num_groups
@@ -89,7 +92,16 @@ class _Net:
         if ext:
             self.ext_reads[pos] = ext
 
-    def emit_plan(self, plan: ops.ConvPlan, out=None, reads=()):
+    def emit_plan(self, plan: ops.ConvPlan, out=None, reads=(), gn_stats: bool = False):
+        """gn_stats: the output will be normalised by a GroupNorm -> let the epilogue emit its statistics."""
+        if gn_stats and self.fuse_gn_stats and out is not None:
+            st = plan.enable_output_stats()
+            if st is not None:
+                self.stats_of[out.data_ptr()] = st
+            else:
+                self.stats_of.pop(out.data_ptr(), None)
+        elif out is not None:
+            self.stats_of.pop(out.data_ptr(), None)      # buffer rewritten by a producer without statistics
         self.keep.append(plan)
         self.flops += plan.flops
         self.emit(plan.run, getattr(plan, "launches", 1), "igemm", plan.flops, out=out, reads=reads)
@@ -98,7 +110,12 @@ class _Net:
         g, b = self.wf(prefix + ".weight"), self.wf(prefix + ".bias")
         G = self.cfg.norm_num_groups
         self.keep += [g, b]
-        self.emit(lambda: ops.groupnorm(x1, x2, g, b, out, self.gn_ws, B=self.B, HW=HW, groups=G, eps=eps, silu=silu), 2, "groupnorm")
+        p1 = self.stats_of.get(x1.data_ptr())
+        p2 = None if x2 is None else self.stats_of.get(x2.data_ptr())
+        if p1 is None or (x2 is not None and p2 is None):
+            p1 = p2 = None
+        self.emit(lambda: ops.groupnorm(x1, x2, g, b, out, self.gn_ws, B=self.B, HW=HW, groups=G, eps=eps, silu=silu,
+                                        part1=p1, part2=p2), 2, "groupnorm")
 
     def layernorm(self, x, prefix: str, out):
         g, b = self.wf(prefix + ".weight"), self.wf(prefix + ".bias")
@@ -164,7 +181,7 @@ class _Net:
         off = self.rowbias_off[p]
         rb = self.rowbias[:, off:]
         self.emit_plan(ops.ConvPlan(n1, w1, h1, B=B, H=h, W=w, Cin=cin, Cout=cout, ksize=3, bias=self.wf(p + ".conv1.bias"),
-                                    rowbias=rb, rowbias_ld=self.rowbias.shape[1]))
+                                    rowbias=rb, rowbias_ld=self.rowbias.shape[1]), out=h1, gn_stats=True)
         n2 = self.scratch("n2", B, HW, cout)
         self.groupnorm(h1, None, p + ".norm2", n2, HW, eps, True)
         out = self.buf(B, HW, cout)
@@ -192,7 +209,7 @@ class _Net:
         if fused is not None:
             self._register_fused(w2, fused[0], fused[1], bias_buf, base_bias, fused[2])
         self.emit_plan(ops.ConvPlan(n2, w2, out, B=B, H=h, W=w, Cin=cout, Cout=cout, ksize=3, extras=extras_x,
-                                    bias=bias_buf, res1=res1, res2=tap), out=out, reads=list(extras_x) + [tap])
+                                    bias=bias_buf, res1=res1, res2=tap), out=out, reads=list(extras_x) + [tap], gn_stats=True)
         return out
 
     def _sampler_conv(self, p: str, x, out, h, w, stride, tap, tap_src):
@@ -206,7 +223,7 @@ class _Net:
         if tap_src is not None:
             self._register_fused(wp, 9 * c, tap_src[1], bias_buf, base_bias, tap_src[2])
         self.emit_plan(ops.ConvPlan(x, wp, out, B=self.B, H=h, W=w, Cin=c, Cout=c, ksize=3, stride=stride, extras=extras_x,
-                                    bias=bias_buf, res2=tap), out=out, reads=list(extras_x) + [tap])
+                                    bias=bias_buf, res2=tap), out=out, reads=list(extras_x) + [tap], gn_stats=True)
 
     def downsample(self, p: str, x, hw, tap=None, tap_src=None):
         h, w = hw
@@ -230,7 +247,7 @@ class _Net:
         if tap_src is not None:
             self._register_fused(wp.view(4 * c, -1), 4 * c, tap_src[1].repeat(4, 1), bias_buf, base_bias, tap_src[2])
         self.emit_plan(ops.ConvPlan(x, wp, out, B=self.B, H=h, W=w, Cin=c, Cout=c, ksize=3, up2x=True, extras=extras_x,
-                                    bias=bias_buf, res2=tap), out=out, reads=list(extras_x) + [tap])
+                                    bias=bias_buf, res2=tap), out=out, reads=list(extras_x) + [tap], gn_stats=True)
         return out
 
     def run(self):
@@ -501,7 +518,8 @@ class UNetEngine(_Net):
         if tap_src is not None:
             self._register_fused(wpo, C, tap_src[1], bias_buf, base_bias, tap_src[2])
         self.emit_plan(ops.linear_plan(h3, wpo, out.view(M, C), extras=extras_x, bias=bias_buf, res1=x.view(M, C),
-                                       res2=None if tap is None else tap.view(M, C)), out=out, reads=list(extras_x) + [tap])
+                                       res2=None if tap is None else tap.view(M, C)), out=out, reads=list(extras_x) + [tap],
+                       gn_stats=True)
         return out
 
     def set_context(self, ehs: torch.Tensor):

@@ -128,6 +128,20 @@ class ConvPlan:
     def run(self):
         check(self._L.mfb_plan_run(self._h, _stream()))
 
+    def enable_output_stats(self, buf: Optional[torch.Tensor] = None):
+        """Let the epilogue also emit the GroupNorm statistics of the output (per image, tile, channel).  Returns
+        (buffer, tiles) or None if this plan cannot (GEGLU / tiles straddling images)."""
+        n = self._L.mfb_plan_stats_floats(self._h)
+        if n <= 0:
+            return None
+        if buf is None:
+            buf = torch.zeros(n, device=self._keep[2].device, dtype=torch.float32)
+        elif buf.numel() < n or buf.dtype != torch.float32:
+            raise ValueError("statistics buffer too small")
+        check(self._L.mfb_plan_set_stats(self._h, C.c_void_p(buf.data_ptr())))
+        self._stats = buf
+        return buf, self._L.mfb_plan_stats_tiles(self._h)
+
     def __del__(self):
         try:
             if getattr(self, "_h", None):
@@ -152,10 +166,16 @@ def gn_ws_floats(B: int, groups: int) -> int:
     return 2 * B * groups * (1 + GN_MAX_CHUNKS) + B
 
 
-def groupnorm(x1, x2, gamma, beta, out, stats_ws, *, B, HW, groups, eps, silu):
+def groupnorm(x1, x2, gamma, beta, out, stats_ws, *, B, HW, groups, eps, silu, part1=None, part2=None):
+    """part1 / part2: (buffer, tiles) from ConvPlan.enable_output_stats of the GEMM that produced x1 / x2."""
     L = lib()
     C1 = x1.shape[-1]
     C2 = 0 if x2 is None else x2.shape[-1]
+    if part1 is not None and (x2 is None or part2 is not None):
+        check(L.mfb_groupnorm_prestat(_ptr(x1), C1, _ptr(part1[0]), part1[1], _ptr(x2), C2,
+                                      _ptr(part2[0]) if part2 else None, part2[1] if part2 else 0, B, HW, groups, eps,
+                                      _ptr(gamma), _ptr(beta), int(silu), _ptr(stats_ws), _ptr(out), _stream()))
+        return
     check(L.mfb_groupnorm(_ptr(x1), C1, _ptr(x2), C2, B, HW, groups, eps, _ptr(gamma), _ptr(beta), int(silu),
                           _ptr(stats_ws), _ptr(out), _stream()))
 

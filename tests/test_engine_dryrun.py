@@ -41,6 +41,9 @@ class FakePlan:
     def run(self):
         pass
 
+    def enable_output_stats(self, buf=None):
+        return None
+
 
 @pytest.fixture
 def stub_ops(monkeypatch):

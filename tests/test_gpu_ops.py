@@ -201,6 +201,42 @@ def test_groupnorm(ops, B, HW, C1, C2, groups, eps, silu):
     assert rel(out.float(), ref.transpose(1, 2)) < 4e-3
 
 
+@pytest.mark.parametrize("B,H,W,Cin,Cout,up", [(2, 32, 32, 64, 320, False), (4, 8, 8, 64, 640, False), (2, 12, 12, 64, 160, False),
+                                               (2, 8, 8, 64, 320, True), (3, 16, 16, 128, 1280, False)])
+def test_groupnorm_with_statistics_from_the_conv_epilogue(ops, B, H, W, Cin, Cout, up):
+    """The igemm epilogue emits per-(image, tile, channel) sum / sum-of-squares of the values it stores; GroupNorm then
+    only runs a tiny fixed-order reduction instead of re-reading the tensor.  Must equal the two-pass GroupNorm bit for
+    bit up to fp32 summation order, and the second source of a concat may come from another conv."""
+    groups = 32
+    Ho, Wo = (2 * H, 2 * W) if up else (H, W)
+    x = randn(B, H, W, Cin, seed=1)
+    w = randn(Cout, Cin, 3, 3, seed=2, scale=(9 * Cin) ** -0.5)
+    bias = randn(Cout, seed=3, dtype=torch.float32)
+    res = randn(B, Ho, Wo, Cout, seed=4)
+    out = torch.full((B, Ho, Wo, Cout), float("nan"), device="cuda", dtype=bf16)
+    wp = ops.pack_upconv_weight(w.float()) if up else ops.pack_conv_weight(w.float())
+    plan = ops.ConvPlan(x, wp, out, B=B, H=H, W=W, Cin=Cin, Cout=Cout, ksize=3, bias=bias, res1=None if up else res,
+                        res2=res if up else None, up2x=up)
+    st = plan.enable_output_stats()
+    assert st is not None
+    plan.run()
+    part, tiles = st
+    got = part.view(B, tiles, Cout, 2).sum(1)                       # [B, C, 2]
+    o = out.float().view(B, Ho * Wo, Cout)
+    assert rel(got[..., 0], o.sum(1)) < 1e-4 and rel(got[..., 1], (o * o).sum(1)) < 1e-5
+    # GroupNorm + SiLU over cat([out, y2]) with y2's statistics computed the classic way for the first call ...
+    gamma = 1 + 0.1 * randn(Cout, seed=5, dtype=torch.float32)
+    beta = 0.1 * randn(Cout, seed=6, dtype=torch.float32)
+    ws = torch.zeros(ops.gn_ws_floats(B, groups), device="cuda")
+    y_fused = torch.full((B, Ho * Wo, Cout), float("nan"), device="cuda", dtype=bf16)
+    y_plain = torch.full_like(y_fused, float("nan"))
+    ops.groupnorm(out.view(B, Ho * Wo, Cout), None, gamma, beta, y_fused, ws, B=B, HW=Ho * Wo, groups=groups, eps=1e-5, silu=True,
+                  part1=st)
+    ops.groupnorm(out.view(B, Ho * Wo, Cout), None, gamma, beta, y_plain, ws, B=B, HW=Ho * Wo, groups=groups, eps=1e-5, silu=True)
+    ref = F.silu(F.group_norm(o.transpose(1, 2), groups, gamma, beta, 1e-5)).transpose(1, 2)
+    assert rel(y_fused.float(), ref) < 4e-3 and rel(y_fused.float(), y_plain.float()) < 2e-3
+
+
 @pytest.mark.parametrize("rows,C", [(8192, 320), (2048, 640), (513, 1280), (64, 64), (100, 128)])
 def test_layernorm(ops, rows, C):
     x = randn(rows, C, seed=1) * 2 + 0.3
