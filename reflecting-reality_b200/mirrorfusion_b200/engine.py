@@ -44,7 +44,7 @@ class _Net:
         self.ext_reads: Dict[int, List[int]] = {}  # program position -> data_ptrs it reads (candidates for cross-net deps)
         # GroupNorm statistics produced by the igemm epilogue that wrote a tensor: data_ptr -> (partials buffer, tiles)
         self.stats_of: Dict[int, Tuple[torch.Tensor, int]] = {}
-        self.fuse_gn_stats = True
+        self.fuse_gn_stats = False    # opt-in: measured performance-neutral at the bench geometry (profiles/r01j)
         # fused BrushNet taps: (packed weight, column offset, C, zero-conv weight [C,C] f32, bias buffer, base bias, zero-conv bias)
         self.fused_taps: List[Tuple] = []
         G = cfg.norm_num_groups
@@ -517,9 +517,11 @@ class UNetEngine(_Net):
         bias_buf = base_bias.clone()
         if tap_src is not None:
             self._register_fused(wpo, C, tap_src[1], bias_buf, base_bias, tap_src[2])
-        self.emit_plan(ops.linear_plan(h3, wpo, out.view(M, C), extras=extras_x, bias=bias_buf, res1=x.view(M, C),
-                                       res2=None if tap is None else tap.view(M, C)), out=out, reads=list(extras_x) + [tap],
-                       gn_stats=True)
+        # a 1x1 conv with the real (B, h, w) geometry rather than a flat token GEMM: the epilogue's fused GroupNorm
+        # statistics are per image
+        self.emit_plan(ops.ConvPlan(h3, wpo, out, B=B, H=h, W=w, Cin=h3.shape[-1], Cout=C, ksize=1,
+                                    extras=[e.view(B, T, -1) for e in extras_x], bias=bias_buf, res1=x, res2=tap),
+                       out=out, reads=list(extras_x) + [tap], gn_stats=True)
         return out
 
     def set_context(self, ehs: torch.Tensor):
