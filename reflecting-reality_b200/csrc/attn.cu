@@ -70,7 +70,9 @@ __global__ void __launch_bounds__(ATT_THREADS, (D <= 40) ? 2 : 1) attention_kern
     const uint32_t tmem_slot = bar + 40u + 8u * (2 * STAGES);
     uint8_t* gen_base = smem_raw + (base - raw_u32);  // generic pointer to `base`
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // warp index broadcast from lane 0: the role branches are provably warp-uniform; the issuing thread of the TMA /
+    // MMA warps is picked with elect.sync so ptxas emits UTMALDG / UTCHMMA / UTCBAR without ELECT waterfall loops
+    const int warp = __shfl_sync(0xffffffffu, int(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
     const int q0 = blockIdx.x * BQ;
     const int h = blockIdx.y;
     const int b = blockIdx.z;
@@ -103,7 +105,7 @@ __global__ void __launch_bounds__(ATT_THREADS, (D <= 40) ? 2 : 1) attention_kern
     // warps 0-3 = softmax (TMEM lane quarter = warp), warp 4 = TMA, warp 5 = MMA: the single-thread issuers get the
     // highest warp ids so the arbiter never lets softmax warps starve them
     if (warp == 4) {
-        if (lane == 0) {
+        if (elect_one()) {
             // ===== TMA producer =====
             mbar_expect_tx(q_full, Cfg::Q_BYTES);
             for (int kb = 0; kb < NKB; ++kb) tma_load_3d(q_smem + kb * BQ * 128, &p.tmQ, q_full, h * D + kb * 64, q0, b);
@@ -121,7 +123,7 @@ __global__ void __launch_bounds__(ATT_THREADS, (D <= 40) ? 2 : 1) attention_kern
         }
         __syncwarp();
     } else if (warp == 5) {
-        if (lane == 0) {
+        if (elect_one()) {
             // ===== MMA issuer =====
             constexpr uint32_t idesc_qk = make_idesc_bf16(128, BKV);
             constexpr uint32_t idesc_pv = make_idesc_bf16(128, DPAD);

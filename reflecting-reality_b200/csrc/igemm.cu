@@ -153,7 +153,8 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 1) igemm_kernel(const __grid_co
     uint8_t* stg_gen = smem_raw + (stg_base - smem_u32(smem_raw));   // generic pointer to the staging tile
     uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
-    const int warp = threadIdx.x >> 5;
+    // warp index broadcast from lane 0 so the compiler knows the role branches below are warp-uniform
+    const int warp = __shfl_sync(0xffffffffu, int(threadIdx.x >> 5), 0);
     const int lane = threadIdx.x & 31;
     const int tiles_n = p.tiles_nn;
     // work items: PAIR -> (pair of M tiles, N tile); this CTA takes M tile 2*mp + rank (a tile past the end is all
@@ -200,10 +201,15 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 1) igemm_kernel(const __grid_co
 
     // Warp roles: the two single-thread issuers sit in the HIGHEST warp ids (8 = TMA, 9 = MMA): the sub-partition
     // arbiter favours higher warp ids, so epilogue warps can never starve them.
+    // The issuing thread of each is chosen with elect.sync, not `lane == 0`: only then does ptxas know that exactly
+    // one thread executes the UTMALDG / UTCHMMA / UTCBAR instructions and emit them straight; behind a lane test
+    // it wraps every one of them in an ELECT / BRA.U.ANY "waterfall" loop (~44 issue cycles per MMA, measured in
+    // tools/microbench/mma_rate.cu), which made the MMA thread, not the tensor pipe, the pace-setter of the main loop.
     if (warp == IGEMM_EPI_WARPS) {
-        if (lane == 0) {
+        if (elect_one()) {
             // ===== TMA producer =====
-            int it = 0;
+            int stage = 0;
+            uint32_t phase = 0;
             for (int tile = wi0; tile < num_tiles; tile += wstep) {
                 const int nt = tile % tiles_n;
                 const int mt = PAIR ? 2 * (tile / tiles_n) + int(crank) : tile / tiles_n;
@@ -214,9 +220,7 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 1) igemm_kernel(const __grid_co
                 for (int s = 0; s < p.nseg; ++s) {
                     const IgemmSeg sg = p.seg[s];
                     const void* tm = &p.tmA[sg.map];
-                    for (int cb = 0; cb < sg.cblocks; ++cb, ++it, kcol += BK) {
-                        const int stage = it % STAGES;
-                        const uint32_t phase = (it / STAGES) & 1;
+                    for (int cb = 0; cb < sg.cblocks; ++cb, kcol += BK) {
                         mbar_wait(empty_bar(stage), phase ^ 1);
                         const uint32_t a_dst = smem_base + stage * STAGE_BYTES;
                         if constexpr (TWOSM) {
@@ -225,35 +229,35 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 1) igemm_kernel(const __grid_co
                             const uint32_t lbar = mapa_shared(full_bar(stage), 0);
                             tma_load_4d_2sm(a_dst, tm, lbar, sg.c0 + cb * BK, w0 + sg.dw, h0 + sg.dh, n0);
                             tma_load_2d_2sm(a_dst + Cfg::A_BYTES, &p.tmBh, lbar, kcol, nt * BN + int(crank) * (BN / 2));
-                            continue;
-                        }
-                        mbar_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
-                        tma_load_4d(a_dst, tm, full_bar(stage), sg.c0 + cb * BK, w0 + sg.dw, h0 + sg.dh, n0);
-                        if constexpr (MODE == 1) {
-                            constexpr int HB = (BN / 2) * BK * 2;    // bytes of half a weight tile
-                            tma_load_2d_mc(a_dst + Cfg::A_BYTES + crank * HB, &p.tmBh, full_bar(stage), kcol,
-                                           nt * BN + int(crank) * (BN / 2), uint16_t(3));
                         } else {
-                            tma_load_2d(a_dst + Cfg::A_BYTES, &p.tmB, full_bar(stage), kcol, nt * BN);
+                            mbar_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
+                            tma_load_4d(a_dst, tm, full_bar(stage), sg.c0 + cb * BK, w0 + sg.dw, h0 + sg.dh, n0);
+                            if constexpr (MODE == 1) {
+                                constexpr int HB = (BN / 2) * BK * 2;    // bytes of half a weight tile
+                                tma_load_2d_mc(a_dst + Cfg::A_BYTES + crank * HB, &p.tmBh, full_bar(stage), kcol,
+                                               nt * BN + int(crank) * (BN / 2), uint16_t(3));
+                            } else {
+                                tma_load_2d(a_dst + Cfg::A_BYTES, &p.tmB, full_bar(stage), kcol, nt * BN);
+                            }
                         }
+                        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
                     }
                 }
             }
         }
         __syncwarp();
     } else if (warp == IGEMM_EPI_WARPS + 1) {
-        if (lane == 0 && (!TWOSM || crank == 0)) {
+        if ((!TWOSM || crank == 0) && elect_one()) {
             // ===== MMA issuer (MODE 2: leader CTA only) =====
             constexpr uint32_t idesc = make_idesc_bf16(TWOSM ? 2 * BM : BM, BN);
-            int it = 0, li = 0;
+            int li = 0, stage = 0;
+            uint32_t phase = 0;
             for (int tile = wi0; tile < num_tiles; tile += wstep, ++li) {
                 const int as = li & 1;
                 mbar_wait(tmem_empty_bar(as), ((li >> 1) & 1) ^ 1);   // epilogue has drained this accumulator slot
                 tc_fence_after();
                 const uint32_t tacc = tmem_base + as * Cfg::ACC_COLS;
-                for (int kb = 0; kb < total_kb; ++kb, ++it) {
-                    const int stage = it % STAGES;
-                    const uint32_t phase = (it / STAGES) & 1;
+                for (int kb = 0; kb < total_kb; ++kb) {
                     mbar_wait(full_bar(stage), phase);
                     tc_fence_after();
                     const uint32_t a_addr = smem_base + stage * STAGE_BYTES;
@@ -269,6 +273,7 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 1) igemm_kernel(const __grid_co
                     if constexpr (TWOSM) umma_commit_2sm_mc(empty_bar(stage), uint16_t(3));
                     else if constexpr (MODE == 1) umma_commit_mc(empty_bar(stage), uint16_t(3));
                     else umma_commit(empty_bar(stage));
+                    if (++stage == STAGES) { stage = 0; phase ^= 1u; }
                 }
                 // accumulator complete
                 if constexpr (TWOSM) umma_commit_2sm_mc(tmem_full_bar(as), uint16_t(3));
