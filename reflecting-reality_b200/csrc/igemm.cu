@@ -85,7 +85,8 @@ struct IgemmCfg {
     static constexpr int STAGES = (224 * 1024 - STG_BYTES) / STAGE_BYTES > 8 ? 8 : (224 * 1024 - STG_BYTES) / STAGE_BYTES;
     static constexpr int ACC_COLS = BN <= 64 ? 64 : BN <= 128 ? 128 : 256;  // TMEM columns per accumulator slot
     static constexpr int TMEM_COLS = 2 * ACC_COLS;                           // double-buffered accumulator
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STG_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STG_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ +
+                                      2 * BN * 4 /*column bias of the current / next tile*/;
 };
 
 // byte offset of the 16-byte chunk holding columns [col, col+8) of row r inside the swizzled staging tile
@@ -152,6 +153,7 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 1) igemm_kernel(const __grid_co
     const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 5);
     uint8_t* stg_gen = smem_raw + (stg_base - smem_u32(smem_raw));   // generic pointer to the staging tile
     uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+    float* sbias = reinterpret_cast<float*>(smem_raw + (bar_base + 256 - smem_u32(smem_raw)));   // [2][BN]
 
     // warp index broadcast from lane 0 so the compiler knows the role branches below are warp-uniform
     const int warp = __shfl_sync(0xffffffffu, int(threadIdx.x >> 5), 0);
@@ -309,7 +311,23 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 1) igemm_kernel(const __grid_co
             const bool valid = (ow < p.Wo) && (oh < p.Ho) && (on < p.Bn);
             // linear pixel index inside the full output tensor (only used for the directly-read res2)
             const long long m = (static_cast<long long>(on) * p.o_Hf + oh * p.o_step + p.o_py) * p.o_Wf + ow * p.o_step + p.o_px;
-            const float* rb = p.rowbias ? p.rowbias + static_cast<long long>(valid ? on : 0) * p.rowbias_ld : nullptr;
+            // Column bias of this tile (bias + the row bias when the whole tile lies in one image), fetched into shared
+            // memory while the MMAs of the tile are still running; the per-element code below then only does
+            // broadcast LDS instead of dependent global loads.  A tile spanning several images (8x8 level) keeps
+            // the per-row global read of the row bias.
+            const int as = li & 1;
+            float* sb = sbias + as * BN;
+            const bool rb_folded = p.rowbias != nullptr && p.tn == 1;
+            const float* rb = (p.rowbias && !rb_folded) ? p.rowbias + static_cast<long long>(valid ? on : 0) * p.rowbias_ld : nullptr;
+            if (int(threadIdx.x) < BN) {
+                const int n = nt * BN + int(threadIdx.x);
+                float bv = 0.f;
+                if (n < p.N) {
+                    if (p.bias) bv = __ldg(p.bias + n);
+                    if (rb_folded) bv += __ldg(p.rowbias + static_cast<long long>(min(n0, p.Bn - 1)) * p.rowbias_ld + n);
+                }
+                sb[threadIdx.x] = bv;
+            }
             if (leader) {
                 tma_store_wait_read();                 // previous tile's store no longer reads the staging tile
                 if (p.res1) {
@@ -319,12 +337,20 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 1) igemm_kernel(const __grid_co
                 }
             }
             __syncwarp();
-            named_bar_sync(1, IGEMM_EPI_WARPS * 32);   // staging tile is free (or being filled with res1)
-            const int as = li & 1;
+            named_bar_sync(1, IGEMM_EPI_WARPS * 32);   // staging tile is free (or being filled with res1); sb is visible
             mbar_wait_relaxed(tmem_full_bar(as), (li >> 1) & 1);
-            if (p.res1) mbar_wait_relaxed(res_full_bar, li & 1);
             tc_fence_after();
             const uint32_t trow = tmem_base + as * Cfg::ACC_COLS + (uint32_t(q * 32) << 16);
+            // once this warp's accumulator slice sits in registers the slot goes back to the MMA warp
+            auto release_acc = [&]() {
+                tmem_wait_ld();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) {
+                    if constexpr (TWOSM) mbar_arrive_cluster(mapa_shared(tmem_empty_bar(as), 0));   // the leader issues the MMAs
+                    else mbar_arrive(tmem_empty_bar(as));
+                }
+            };
 
             if (!p.geglu) {
                 constexpr int NCH = BN / 16;                 // 16-column chunks; warp `half` 0 takes the first ceil(NCH/2)
@@ -336,7 +362,8 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 1) igemm_kernel(const __grid_co
 #pragma unroll
                 for (int i = 0; i < MAXC; ++i)
                     if (i < c_cnt) tmem_ld16(trow + (c_begin + i) * 16, v[i]);
-                tmem_wait_ld();
+                release_acc();
+                if (p.res1) mbar_wait_relaxed(res_full_bar, li & 1);
 #pragma unroll
                 for (int i = 0; i < MAXC; ++i) {
                     if (i < c_cnt) {
@@ -346,15 +373,18 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 1) igemm_kernel(const __grid_co
                         for (int j = 0; j < 2; ++j) {
                             const int nn = n + j * 8;
                             uint4* sp = reinterpret_cast<uint4*>(stg_gen + stg_off<BOXC>(r, col + j * 8));
+                            const float4 b0 = *reinterpret_cast<const float4*>(sb + col + j * 8);
+                            const float4 b1 = *reinterpret_cast<const float4*>(sb + col + j * 8 + 4);
                             float f[8];
+                            f[0] = __uint_as_float(v[i][j * 8 + 0]) + b0.x; f[1] = __uint_as_float(v[i][j * 8 + 1]) + b0.y;
+                            f[2] = __uint_as_float(v[i][j * 8 + 2]) + b0.z; f[3] = __uint_as_float(v[i][j * 8 + 3]) + b0.w;
+                            f[4] = __uint_as_float(v[i][j * 8 + 4]) + b1.x; f[5] = __uint_as_float(v[i][j * 8 + 5]) + b1.y;
+                            f[6] = __uint_as_float(v[i][j * 8 + 6]) + b1.z; f[7] = __uint_as_float(v[i][j * 8 + 7]) + b1.w;
+                            if (rb && nn < p.N) add_f32x8(f, rb + nn);
+                            if (p.alpha) {
 #pragma unroll
-                            for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[i][j * 8 + e]);
-                            if (nn < p.N) {
-                                if (p.bias) add_f32x8(f, p.bias + nn);
-                                if (rb) add_f32x8(f, rb + nn);
+                                for (int e = 0; e < 8; ++e) f[e] *= alpha;
                             }
-#pragma unroll
-                            for (int e = 0; e < 8; ++e) f[e] *= alpha;
                             if (p.res1) add_bf16x8(f, *sp);
                             if (p.res2 && valid && nn < p.N)   // rare (tap sites): straight from global
                                 add_bf16x8(f, __ldg(reinterpret_cast<const uint4*>(p.res2 + m * p.out_ld + nn)));
@@ -365,39 +395,33 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 1) igemm_kernel(const __grid_co
             } else {
                 // GEGLU (S/models/activations.py:100-103): out = value * gelu_erf(gate); tile = [64 value | 64 gate]
                 if constexpr (BN == 128) {
-#pragma unroll 1
+                    uint32_t v[2][16], g[2][16];
+#pragma unroll
                     for (int c = 0; c < 2; ++c) {
-                        const int col = half * 32 + c * 16;   // value column inside the tile; gate = col + 64
-                        uint32_t v[16], g[16];
-                        tmem_ld16(trow + col, v);
-                        tmem_ld16(trow + 64 + col, g);
-                        tmem_wait_ld();
-                        const int pv = nt * BN + col;          // packed column of the value
+                        tmem_ld16(trow + half * 32 + c * 16, v[c]);        // value columns; gate = +64
+                        tmem_ld16(trow + 64 + half * 32 + c * 16, g[c]);
+                    }
+                    release_acc();
+#pragma unroll
+                    for (int c = 0; c < 2; ++c) {
+                        const int col = half * 32 + c * 16;
 #pragma unroll
                         for (int j = 0; j < 2; ++j) {
-                            float f[8], gt[8];
+                            float f[8], bv[8], bg[8];
+                            *reinterpret_cast<float4*>(bv) = *reinterpret_cast<const float4*>(sb + col + j * 8);
+                            *reinterpret_cast<float4*>(bv + 4) = *reinterpret_cast<const float4*>(sb + col + j * 8 + 4);
+                            *reinterpret_cast<float4*>(bg) = *reinterpret_cast<const float4*>(sb + 64 + col + j * 8);
+                            *reinterpret_cast<float4*>(bg + 4) = *reinterpret_cast<const float4*>(sb + 64 + col + j * 8 + 4);
 #pragma unroll
                             for (int e = 0; e < 8; ++e) {
-                                f[e] = __uint_as_float(v[j * 8 + e]);
-                                gt[e] = __uint_as_float(g[j * 8 + e]);
+                                const float val = __uint_as_float(v[c][j * 8 + e]) + bv[e];
+                                const float gate = __uint_as_float(g[c][j * 8 + e]) + bg[e];
+                                f[e] = val * gelu_erf_f(gate);
                             }
-                            if (p.bias && pv + j * 8 < p.N) {
-                                add_f32x8(f, p.bias + pv + j * 8);
-                                add_f32x8(gt, p.bias + pv + 64 + j * 8);
-                            }
-#pragma unroll
-                            for (int e = 0; e < 8; ++e) f[e] *= gelu_erf_f(gt[e]);
                             *reinterpret_cast<uint4*>(stg_gen + stg_off<BOXC>(r, col + j * 8)) = pack_bf16x8(f);
                         }
                     }
                 }
-            }
-            // all tcgen05.ld of this warp have completed (wait::ld above): hand the accumulator slot back
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) {
-                if constexpr (TWOSM) mbar_arrive_cluster(mapa_shared(tmem_empty_bar(as), 0));   // the leader issues the MMAs
-                else mbar_arrive(tmem_empty_bar(as));
             }
             fence_proxy_async_smem();                  // generic-proxy writes of the staging tile -> visible to TMA
             named_bar_sync(1, IGEMM_EPI_WARPS * 32);

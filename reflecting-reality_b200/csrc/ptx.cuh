@@ -309,22 +309,24 @@ __device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
     return __bfloat1622float2(h);
 }
 __device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
-// exact (erf) GELU, F.gelu default (S/models/activations.py:94-98).  erf by Abramowitz-Stegun 7.1.26
-// (|abs err| <= 1.5e-7, far below bf16 resolution): branch-free, one ex2 + one rcp instead of libdevice erff's ~40
-// instructions — the GEGLU epilogue was ALU-bound on erff.
+// exact (erf) GELU, F.gelu default (S/models/activations.py:94-98): gelu(x) = x * Phi(x).  The normal CDF tail is
+// evaluated as Phi(-a) = 2^-L(a), a = min(|x|, 6), with L a degree-7 polynomial (Chebyshev fit of -log2(erfc(a/sqrt2)/2)
+// on [0, 6]; |gelu error| <= 7e-7 over all x, far below bf16 resolution): 7 FMA + one ex2, branch-free.  (libdevice
+// erff is ~40 instructions and the Abramowitz-Stegun form needs a reciprocal as well; the GEGLU epilogue is bound
+// by issue slots, not by the tensor pipe, on the K=320 projections.)
 __device__ __forceinline__ float gelu_erf_f(float x) {
-    const float z = fabsf(x) * 0.70710678118654752f;
-    const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
-    float poly = fmaf(1.061405429f, t, -1.453152027f);
-    poly = fmaf(poly, t, 1.421413741f);
-    poly = fmaf(poly, t, -0.284496736f);
-    poly = fmaf(poly, t, 0.254829592f);
-    poly *= t;
+    const float a = fminf(fabsf(x), 6.0f);
+    float l = fmaf(1.889626219e-06f, a, -6.268139987e-05f);
+    l = fmaf(l, a, 9.388679173e-04f);
+    l = fmaf(l, a, -8.539461531e-03f);
+    l = fmaf(l, a, 5.402068794e-02f);
+    l = fmaf(l, a, 4.584097862e-01f);
+    l = fmaf(l, a, 1.151269197e+00f);
+    l = fmaf(l, a, 9.999943376e-01f);
     float e;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-z * z * 1.4426950408889634f));
-    const float erf_abs = fmaf(-poly, e, 1.0f);          // erf(|x|/sqrt2)
-    const float erf_v = copysignf(erf_abs, x);
-    return 0.5f * x * (1.0f + erf_v);
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-l));
+    const float phi = x < 0.f ? e : 1.0f - e;
+    return x * phi;
 }
 
 }  // namespace mfb
