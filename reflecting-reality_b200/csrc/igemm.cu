@@ -26,6 +26,7 @@
 #include <vector>
 
 #include "common.h"
+#include <type_traits>
 #include "ptx.cuh"
 
 namespace mfb {
@@ -120,6 +121,33 @@ __device__ __forceinline__ uint4 pack_bf16x8(const float (&f)[8]) {
     return o;
 }
 
+// Walks the tile sequence tile0, tile0 + step, ... of one CTA without per-tile integer divisions: the position is kept
+// as mixed-radix digits (N tile, tile column, tile row, image group) and advanced by the pre-decomposed step.  (The
+// K=320 projections have only 5 K blocks per tile: a handful of runtime divisions per tile in every thread showed up
+// as ~14 % of the epilogue's samples.)
+struct TileIter {
+    int nt, iw, ih, ig;          // current digits
+    int dn, dw, dh, dg;          // step digits
+    int rn, rw, rh;              // radices
+    __device__ __forceinline__ void init(int tile0, int step, int tiles_n, int tiles_w, int tiles_h) {
+        rn = tiles_n; rw = tiles_w; rh = tiles_h;
+        nt = tile0 % rn; int m = tile0 / rn;
+        iw = m % rw; m /= rw; ih = m % rh; ig = m / rh;
+        dn = step % rn; m = step / rn;
+        dw = m % rw; m /= rw; dh = m % rh; dg = m / rh;
+    }
+    __device__ __forceinline__ void next() {
+        nt += dn;
+        int c = nt >= rn; nt -= c ? rn : 0;
+        iw += dw + c;
+        c = iw >= rw; iw -= c ? rw : 0;
+        ih += dh + c;
+        c = ih >= rh; ih -= c ? rh : 0;
+        ig += dg + c;
+    }
+    __device__ __forceinline__ int mt() const { return (ig * rh + ih) * rw + iw; }
+};
+
 // Persistent kernel: grid = min(#tiles, #SMs); CTA c processes tiles c, c+grid, ... (N-tile fastest, so the CTAs
 // running at the same time share A tiles through L2).  The accumulator is double-buffered in TMEM: while the 8
 // epilogue warps drain tile i, the MMA warp already accumulates tile i+1.
@@ -212,12 +240,20 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 1) igemm_kernel(const __grid_co
             // ===== TMA producer =====
             int stage = 0;
             uint32_t phase = 0;
+            TileIter ti;
+            if constexpr (!PAIR) ti.init(wi0, wstep, tiles_n, p.tiles_w, p.tiles_h);
             for (int tile = wi0; tile < num_tiles; tile += wstep) {
-                const int nt = tile % tiles_n;
-                const int mt = PAIR ? 2 * (tile / tiles_n) + int(crank) : tile / tiles_n;
-                const int w0 = (mt % p.tiles_w) * p.tw;
-                const int h0 = ((mt / p.tiles_w) % p.tiles_h) * p.th;
-                const int n0 = (mt / (p.tiles_w * p.tiles_h)) * p.tn;
+                int nt, w0, h0, n0;
+                if constexpr (PAIR) {
+                    nt = tile % tiles_n;
+                    const int mt = 2 * (tile / tiles_n) + int(crank);
+                    w0 = (mt % p.tiles_w) * p.tw;
+                    h0 = ((mt / p.tiles_w) % p.tiles_h) * p.th;
+                    n0 = (mt / (p.tiles_w * p.tiles_h)) * p.tn;
+                } else {
+                    nt = ti.nt; w0 = ti.iw * p.tw; h0 = ti.ih * p.th; n0 = ti.ig * p.tn;
+                    ti.next();
+                }
                 int kcol = 0;
                 for (int s = 0; s < p.nseg; ++s) {
                     const IgemmSeg sg = p.seg[s];
@@ -301,16 +337,25 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 1) igemm_kernel(const __grid_co
         const int bn_out = p.geglu ? BN / 2 : BN;      // output columns per tile
         const int nbox = bn_out / BOXC;
         int li = 0;
+        TileIter ti;
+        if constexpr (!PAIR) ti.init(wi0, wstep, tiles_n, p.tiles_w, p.tiles_h);
+        // which per-element extras this launch needs (uniform for the whole launch): 0 = bias only, 1 = + res1 tile,
+        // 2 = anything else (per-row row bias, alpha, res2).  Each flavour gets its own straight-line code.
+        const int flavour = (p.alpha || p.res2 || (p.rowbias && p.tn != 1)) ? 2 : (p.res1 ? 1 : 0);
         for (int tile = wi0; tile < num_tiles; tile += wstep, ++li) {
-            const int nt = tile % tiles_n;
-            const int mt = PAIR ? 2 * (tile / tiles_n) + int(crank) : tile / tiles_n;
-            const int w0 = (mt % p.tiles_w) * p.tw;
-            const int h0 = ((mt / p.tiles_w) % p.tiles_h) * p.th;
-            const int n0 = (mt / (p.tiles_w * p.tiles_h)) * p.tn;
+            int nt, mt, w0, h0, n0;
+            if constexpr (PAIR) {
+                nt = tile % tiles_n;
+                mt = 2 * (tile / tiles_n) + int(crank);
+                w0 = (mt % p.tiles_w) * p.tw;
+                h0 = ((mt / p.tiles_w) % p.tiles_h) * p.th;
+                n0 = (mt / (p.tiles_w * p.tiles_h)) * p.tn;
+            } else {
+                nt = ti.nt; mt = ti.mt(); w0 = ti.iw * p.tw; h0 = ti.ih * p.th; n0 = ti.ig * p.tn;
+                ti.next();
+            }
             const int ow = w0 + rw, oh = h0 + rh, on = n0 + rn;
             const bool valid = (ow < p.Wo) && (oh < p.Ho) && (on < p.Bn);
-            // linear pixel index inside the full output tensor (only used for the directly-read res2)
-            const long long m = (static_cast<long long>(on) * p.o_Hf + oh * p.o_step + p.o_py) * p.o_Wf + ow * p.o_step + p.o_px;
             // Column bias of this tile (bias + the row bias when the whole tile lies in one image), fetched into shared
             // memory while the MMAs of the tile are still running; the per-element code below then only does
             // broadcast LDS instead of dependent global loads.  A tile spanning several images (8x8 level) keeps
@@ -364,34 +409,45 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 1) igemm_kernel(const __grid_co
                     if (i < c_cnt) tmem_ld16(trow + (c_begin + i) * 16, v[i]);
                 release_acc();
                 if (p.res1) mbar_wait_relaxed(res_full_bar, li & 1);
+                auto body = [&](auto res1_c, auto extra_c) {
+                    constexpr bool RES1 = decltype(res1_c)::value, EXTRA = decltype(extra_c)::value;
 #pragma unroll
-                for (int i = 0; i < MAXC; ++i) {
-                    if (i < c_cnt) {
-                        const int col = (c_begin + i) * 16;
-                        const int n = nt * BN + col;
+                    for (int i = 0; i < MAXC; ++i) {
+                        if (i < c_cnt) {
+                            const int col = (c_begin + i) * 16;
 #pragma unroll
-                        for (int j = 0; j < 2; ++j) {
-                            const int nn = n + j * 8;
-                            uint4* sp = reinterpret_cast<uint4*>(stg_gen + stg_off<BOXC>(r, col + j * 8));
-                            const float4 b0 = *reinterpret_cast<const float4*>(sb + col + j * 8);
-                            const float4 b1 = *reinterpret_cast<const float4*>(sb + col + j * 8 + 4);
-                            float f[8];
-                            f[0] = __uint_as_float(v[i][j * 8 + 0]) + b0.x; f[1] = __uint_as_float(v[i][j * 8 + 1]) + b0.y;
-                            f[2] = __uint_as_float(v[i][j * 8 + 2]) + b0.z; f[3] = __uint_as_float(v[i][j * 8 + 3]) + b0.w;
-                            f[4] = __uint_as_float(v[i][j * 8 + 4]) + b1.x; f[5] = __uint_as_float(v[i][j * 8 + 5]) + b1.y;
-                            f[6] = __uint_as_float(v[i][j * 8 + 6]) + b1.z; f[7] = __uint_as_float(v[i][j * 8 + 7]) + b1.w;
-                            if (rb && nn < p.N) add_f32x8(f, rb + nn);
-                            if (p.alpha) {
+                            for (int j = 0; j < 2; ++j) {
+                                uint4* sp = reinterpret_cast<uint4*>(stg_gen + stg_off<BOXC>(r, col + j * 8));
+                                const float4 b0 = *reinterpret_cast<const float4*>(sb + col + j * 8);
+                                const float4 b1 = *reinterpret_cast<const float4*>(sb + col + j * 8 + 4);
+                                float f[8];
+                                f[0] = __uint_as_float(v[i][j * 8 + 0]) + b0.x; f[1] = __uint_as_float(v[i][j * 8 + 1]) + b0.y;
+                                f[2] = __uint_as_float(v[i][j * 8 + 2]) + b0.z; f[3] = __uint_as_float(v[i][j * 8 + 3]) + b0.w;
+                                f[4] = __uint_as_float(v[i][j * 8 + 4]) + b1.x; f[5] = __uint_as_float(v[i][j * 8 + 5]) + b1.y;
+                                f[6] = __uint_as_float(v[i][j * 8 + 6]) + b1.z; f[7] = __uint_as_float(v[i][j * 8 + 7]) + b1.w;
+                                if constexpr (EXTRA) {
+                                    const int nn = nt * BN + col + j * 8;
+                                    if (rb && nn < p.N) add_f32x8(f, rb + nn);
 #pragma unroll
-                                for (int e = 0; e < 8; ++e) f[e] *= alpha;
+                                    for (int e = 0; e < 8; ++e) f[e] *= alpha;
+                                    if (p.res1) add_bf16x8(f, *sp);
+                                    if (p.res2 && valid && nn < p.N) {  // rare (tap sites): straight from global
+                                        // linear pixel index inside the full output tensor
+                                        const long long m = (static_cast<long long>(on) * p.o_Hf + oh * p.o_step + p.o_py) * p.o_Wf +
+                                                            ow * p.o_step + p.o_px;
+                                        add_bf16x8(f, __ldg(reinterpret_cast<const uint4*>(p.res2 + m * p.out_ld + nn)));
+                                    }
+                                } else if constexpr (RES1) {
+                                    add_bf16x8(f, *sp);
+                                }
+                                *sp = pack_bf16x8(f);
                             }
-                            if (p.res1) add_bf16x8(f, *sp);
-                            if (p.res2 && valid && nn < p.N)   // rare (tap sites): straight from global
-                                add_bf16x8(f, __ldg(reinterpret_cast<const uint4*>(p.res2 + m * p.out_ld + nn)));
-                            *sp = pack_bf16x8(f);
                         }
                     }
-                }
+                };
+                if (flavour == 0) body(std::false_type{}, std::false_type{});
+                else if (flavour == 1) body(std::true_type{}, std::false_type{});
+                else body(std::false_type{}, std::true_type{});
             } else {
                 // GEGLU (S/models/activations.py:100-103): out = value * gelu_erf(gate); tile = [64 value | 64 gate]
                 if constexpr (BN == 128) {
