@@ -65,9 +65,10 @@ __global__ void __launch_bounds__(ATT_THREADS, (D <= 40) ? 2 : 1) attention_kern
     const uint32_t p_smem = kv_smem + STAGES * Cfg::KV_BYTES;
     const uint32_t bar = p_smem + Cfg::P_BYTES;
     const uint32_t q_full = bar, q_ready = bar + 8, s_full = bar + 16, p_full = bar + 24, o_full = bar + 32;
-    auto kv_full = [&](int s) { return bar + 40u + 8u * s; };
-    auto kv_empty = [&](int s) { return bar + 40u + 8u * (STAGES + s); };
-    const uint32_t tmem_slot = bar + 40u + 8u * (2 * STAGES);
+    const uint32_t s_free = bar + 40;
+    auto kv_full = [&](int s) { return bar + 48u + 8u * s; };
+    auto kv_empty = [&](int s) { return bar + 48u + 8u * (STAGES + s); };
+    const uint32_t tmem_slot = bar + 48u + 8u * (2 * STAGES);
     uint8_t* gen_base = smem_raw + (base - raw_u32);  // generic pointer to `base`
 
     // warp index broadcast from lane 0: the role branches are provably warp-uniform; the issuing thread of the TMA /
@@ -88,6 +89,7 @@ __global__ void __launch_bounds__(ATT_THREADS, (D <= 40) ? 2 : 1) attention_kern
         mbar_init(s_full, 1);
         mbar_init(p_full, 128);
         mbar_init(o_full, 1);
+        mbar_init(s_free, 4);
         for (int s = 0; s < STAGES; ++s) { mbar_init(kv_full(s), 1); mbar_init(kv_empty(s), 1); }
         fence_barrier_init();
     }
@@ -112,7 +114,7 @@ __global__ void __launch_bounds__(ATT_THREADS, (D <= 40) ? 2 : 1) attention_kern
             for (int j = 0; j < ntiles; ++j) {
                 const int s = j % STAGES;
                 const uint32_t ph = (j / STAGES) & 1;
-                mbar_wait(kv_empty(s), ph ^ 1);
+                mbar_wait_relaxed(kv_empty(s), ph ^ 1);
                 mbar_expect_tx(kv_full(s), Cfg::K_BYTES + Cfg::V_BYTES);
                 const uint32_t kd = kv_smem + s * Cfg::KV_BYTES;
                 for (int kb = 0; kb < NKB; ++kb) tma_load_3d(kd + kb * BKV * 128, &p.tmK, kv_full(s), h * D + kb * 64, j * BKV, b);
@@ -130,7 +132,7 @@ __global__ void __launch_bounds__(ATT_THREADS, (D <= 40) ? 2 : 1) attention_kern
             const uint32_t tS = tmem_base, tO = tmem_base + Cfg::O_COL;
             auto issue_qk = [&](int j) {
                 const int s = j % STAGES;
-                mbar_wait(kv_full(s), (j / STAGES) & 1);
+                mbar_wait_relaxed(kv_full(s), (j / STAGES) & 1);
                 tc_fence_after();
                 const uint32_t kd = kv_smem + s * Cfg::KV_BYTES;
 #pragma unroll
@@ -146,7 +148,15 @@ __global__ void __launch_bounds__(ATT_THREADS, (D <= 40) ? 2 : 1) attention_kern
             issue_qk(0);
             for (int j = 0; j < ntiles; ++j) {
                 const int s = j % STAGES;
-                mbar_wait(p_full, j & 1);  // P(j) in smem, S(j) consumed, O rescaled
+                // The softmax warps copy S(j) into registers and hand the TMEM buffer back at once (s_free), so
+                // S(j+1) = Q K(j+1)^T is computed while they are still exponentiating S(j).  Needs the K/V tile of
+                // j+1 resident next to tile j's, i.e. two operand stages.
+                if (STAGES >= 2 && j + 1 < ntiles) {
+                    mbar_wait_relaxed(s_free, j & 1);
+                    tc_fence_after();
+                    issue_qk(j + 1);
+                }
+                mbar_wait_relaxed(p_full, j & 1);  // P(j) in smem, O rescaled
                 tc_fence_after();
                 const uint32_t vd = kv_smem + s * Cfg::KV_BYTES + Cfg::K_BYTES;
 #pragma unroll
@@ -157,7 +167,7 @@ __global__ void __launch_bounds__(ATT_THREADS, (D <= 40) ? 2 : 1) attention_kern
                 }
                 umma_commit(o_full);
                 umma_commit(kv_empty(s));
-                if (j + 1 < ntiles) issue_qk(j + 1);
+                if (STAGES < 2 && j + 1 < ntiles) issue_qk(j + 1);
             }
         }
         __syncwarp();
@@ -188,16 +198,23 @@ __global__ void __launch_bounds__(ATT_THREADS, (D <= 40) ? 2 : 1) attention_kern
             tmem_wait_ld();
             const int kbase = j * BKV;
             const bool tail = kbase + BKV > p.Tk;
-            float mx = -INFINITY;
+            // S(j) now lives in registers: the MMA warp may overwrite the TMEM buffer with S(j+1)
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(s_free);
+            float mx = -INFINITY;      // row max of the RAW scores (scale > 0 commutes with max)
 #pragma unroll
             for (int c = 0; c < 4; ++c)
 #pragma unroll
                 for (int i = 0; i < 32; ++i) {
-                    float s = __uint_as_float(sv[c][i]) * p.scale_log2;
-                    if (tail && kbase + c * 32 + i >= p.Tk) s = -INFINITY;
-                    sv[c][i] = __float_as_uint(s);
+                    float s = __uint_as_float(sv[c][i]);
+                    if (tail && kbase + c * 32 + i >= p.Tk) {
+                        s = -INFINITY;
+                        sv[c][i] = __float_as_uint(s);
+                    }
                     mx = fmaxf(mx, s);
                 }
+            mx *= p.scale_log2;
             float alpha = 1.f;
             if (mx > m_used + 8.f) {  // lazy rescale: keep a stale max while the row max grew by < 2^8
                 alpha = ex2f(m_used - mx);
@@ -229,7 +246,7 @@ __global__ void __launch_bounds__(ATT_THREADS, (D <= 40) ? 2 : 1) attention_kern
                     float e[8];
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
-                        e[i] = ex2f(__uint_as_float(sv[c][i8 * 8 + i]) - m_used);
+                        e[i] = ex2f(fmaf(__uint_as_float(sv[c][i8 * 8 + i]), p.scale_log2, -m_used));   // one FFMA + one MUFU
                         sum += e[i];
                     }
                     uint4 pk;
