@@ -66,9 +66,13 @@ __global__ void __launch_bounds__(ATT_THREADS, (D <= 40) ? 2 : 1) attention_kern
     const uint32_t bar = p_smem + Cfg::P_BYTES;
     const uint32_t q_full = bar, q_ready = bar + 8, s_full = bar + 16, p_full = bar + 24, o_full = bar + 32;
     const uint32_t s_free = bar + 40;
-    auto kv_full = [&](int s) { return bar + 48u + 8u * s; };
-    auto kv_empty = [&](int s) { return bar + 48u + 8u * (STAGES + s); };
-    const uint32_t tmem_slot = bar + 48u + 8u * (2 * STAGES);
+    // K and V tiles have separate full/empty barriers: a K slot is free as soon as Q K^T has read it, long before
+    // the P V product of the same tile — so the K tile two steps ahead is already in flight
+    auto k_full = [&](int s) { return bar + 48u + 8u * s; };
+    auto k_empty = [&](int s) { return bar + 48u + 8u * (STAGES + s); };
+    auto v_full = [&](int s) { return bar + 48u + 8u * (2 * STAGES + s); };
+    auto v_empty = [&](int s) { return bar + 48u + 8u * (3 * STAGES + s); };
+    const uint32_t tmem_slot = bar + 48u + 8u * (4 * STAGES);
     uint8_t* gen_base = smem_raw + (base - raw_u32);  // generic pointer to `base`
 
     // warp index broadcast from lane 0: the role branches are provably warp-uniform; the issuing thread of the TMA /
@@ -90,7 +94,10 @@ __global__ void __launch_bounds__(ATT_THREADS, (D <= 40) ? 2 : 1) attention_kern
         mbar_init(p_full, 128);
         mbar_init(o_full, 1);
         mbar_init(s_free, 4);
-        for (int s = 0; s < STAGES; ++s) { mbar_init(kv_full(s), 1); mbar_init(kv_empty(s), 1); }
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(k_full(s), 1); mbar_init(k_empty(s), 1);
+            mbar_init(v_full(s), 1); mbar_init(v_empty(s), 1);
+        }
         fence_barrier_init();
     }
     if (warp == 5) {
@@ -111,16 +118,22 @@ __global__ void __launch_bounds__(ATT_THREADS, (D <= 40) ? 2 : 1) attention_kern
             // ===== TMA producer =====
             mbar_expect_tx(q_full, Cfg::Q_BYTES);
             for (int kb = 0; kb < NKB; ++kb) tma_load_3d(q_smem + kb * BQ * 128, &p.tmQ, q_full, h * D + kb * 64, q0, b);
-            for (int j = 0; j < ntiles; ++j) {
+            auto load_k = [&](int j) {
                 const int s = j % STAGES;
-                const uint32_t ph = (j / STAGES) & 1;
-                mbar_wait_relaxed(kv_empty(s), ph ^ 1);
-                mbar_expect_tx(kv_full(s), Cfg::K_BYTES + Cfg::V_BYTES);
+                mbar_wait_relaxed(k_empty(s), ((j / STAGES) & 1) ^ 1);
+                mbar_expect_tx(k_full(s), Cfg::K_BYTES);
                 const uint32_t kd = kv_smem + s * Cfg::KV_BYTES;
-                for (int kb = 0; kb < NKB; ++kb) tma_load_3d(kd + kb * BKV * 128, &p.tmK, kv_full(s), h * D + kb * 64, j * BKV, b);
-                const uint32_t vd = kd + Cfg::K_BYTES;
-                tma_load_3d(vd, &p.tmV, kv_full(s), j * BKV, h * D, b);
-                tma_load_3d(vd + DPAD * 128, &p.tmV, kv_full(s), j * BKV + 64, h * D, b);
+                for (int kb = 0; kb < NKB; ++kb) tma_load_3d(kd + kb * BKV * 128, &p.tmK, k_full(s), h * D + kb * 64, j * BKV, b);
+            };
+            load_k(0);
+            for (int j = 0; j < ntiles; ++j) {
+                if (j + 1 < ntiles) load_k(j + 1);        // K runs one tile ahead of V
+                const int s = j % STAGES;
+                mbar_wait_relaxed(v_empty(s), ((j / STAGES) & 1) ^ 1);
+                mbar_expect_tx(v_full(s), Cfg::V_BYTES);
+                const uint32_t vd = kv_smem + s * Cfg::KV_BYTES + Cfg::K_BYTES;
+                tma_load_3d(vd, &p.tmV, v_full(s), j * BKV, h * D, b);
+                tma_load_3d(vd + DPAD * 128, &p.tmV, v_full(s), j * BKV + 64, h * D, b);
             }
         }
         __syncwarp();
@@ -132,7 +145,7 @@ __global__ void __launch_bounds__(ATT_THREADS, (D <= 40) ? 2 : 1) attention_kern
             const uint32_t tS = tmem_base, tO = tmem_base + Cfg::O_COL;
             auto issue_qk = [&](int j) {
                 const int s = j % STAGES;
-                mbar_wait_relaxed(kv_full(s), (j / STAGES) & 1);
+                mbar_wait_relaxed(k_full(s), (j / STAGES) & 1);
                 tc_fence_after();
                 const uint32_t kd = kv_smem + s * Cfg::KV_BYTES;
 #pragma unroll
@@ -142,6 +155,7 @@ __global__ void __launch_bounds__(ATT_THREADS, (D <= 40) ? 2 : 1) attention_kern
                     umma_bf16(tS, ad, bd, idesc_qk, ks != 0);
                 }
                 umma_commit(s_full);
+                umma_commit(k_empty(s));
             };
             mbar_wait(q_full, 0);
             if (kZeroPad) mbar_wait(q_ready, 0);
@@ -150,12 +164,13 @@ __global__ void __launch_bounds__(ATT_THREADS, (D <= 40) ? 2 : 1) attention_kern
                 const int s = j % STAGES;
                 // The softmax warps copy S(j) into registers and hand the TMEM buffer back at once (s_free), so
                 // S(j+1) = Q K(j+1)^T is computed while they are still exponentiating S(j).  Needs the K/V tile of
-                // j+1 resident next to tile j's, i.e. two operand stages.
-                if (STAGES >= 2 && j + 1 < ntiles) {
+                // j+1 resident next to tile j's (K slots are recycled independently of V slots).
+                if (j + 1 < ntiles) {
                     mbar_wait_relaxed(s_free, j & 1);
                     tc_fence_after();
                     issue_qk(j + 1);
                 }
+                mbar_wait_relaxed(v_full(s), (j / STAGES) & 1);
                 mbar_wait_relaxed(p_full, j & 1);  // P(j) in smem, O rescaled
                 tc_fence_after();
                 const uint32_t vd = kv_smem + s * Cfg::KV_BYTES + Cfg::K_BYTES;
@@ -166,8 +181,7 @@ __global__ void __launch_bounds__(ATT_THREADS, (D <= 40) ? 2 : 1) attention_kern
                     umma_bf16(tO, ad, bd, idesc_pv, (j | ks) != 0);
                 }
                 umma_commit(o_full);
-                umma_commit(kv_empty(s));
-                if (STAGES < 2 && j + 1 < ntiles) issue_qk(j + 1);
+                umma_commit(v_empty(s));
             }
         }
         __syncwarp();
