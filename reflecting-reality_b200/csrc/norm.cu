@@ -1,6 +1,7 @@
 // GroupNorm(+SiLU) and LayerNorm over channels-last bf16 activations, fp32 statistics.  HBM-bound kernels:
 // every access is a 16-byte vector, a thread keeps a fixed 8-channel slice so per-channel scale/shift live in
 // registers, and the up-block skip concat is read from its two source tensors directly.
+#include <stdlib.h>
 #include "common.h"
 #include "ptx.cuh"
 
@@ -50,6 +51,18 @@ __global__ void gn_stats_kernel(const __nv_bfloat16* __restrict__ x1, int C1, co
     // 4 independent 16-byte loads in flight per thread (HBM-bound: memory-level parallelism is what matters)
     const int step = blockDim.y;
     int p = p0 + threadIdx.y;
+    for (; p + 7 * step < p1; p += 8 * step) {
+        uint4 u[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) u[k] = __ldg(reinterpret_cast<const uint4*>(src + static_cast<size_t>(p + k * step) * ld));
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            float f[8];
+            unpack8(u[k], f);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) { s[e] += f[e]; q[e] = fmaf(f[e], f[e], q[e]); }
+        }
+    }
     for (; p + 3 * step < p1; p += 4 * step) {
         uint4 u[4];
 #pragma unroll
@@ -211,6 +224,22 @@ __global__ void gn_apply_kernel(const __nv_bfloat16* __restrict__ x1, int C1, co
     const int p1 = min(HW, p0 + pix_per_cta);
     const int step = blockDim.y;
     int p = p0 + threadIdx.y;
+    for (; p + 7 * step < p1; p += 8 * step) {   // 8 x 16 B in flight per thread
+        uint4 u[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) u[k] = __ldg(reinterpret_cast<const uint4*>(src + static_cast<size_t>(p + k * step) * ld));
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            float f[8];
+            unpack8(u[k], f);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const float y = fmaf(f[e], sc[e], sh[e]);
+                f[e] = silu ? silu_f(y) : y;
+            }
+            *reinterpret_cast<uint4*>(dst + static_cast<size_t>(p + k * step) * C) = pack8(f);
+        }
+    }
     for (; p + 3 * step < p1; p += 4 * step) {
         uint4 u[4];
 #pragma unroll
@@ -237,6 +266,107 @@ __global__ void gn_apply_kernel(const __nv_bfloat16* __restrict__ x1, int C1, co
             f[e] = silu ? silu_f(y) : y;
         }
         *reinterpret_cast<uint4*>(dst + static_cast<size_t>(p) * C) = pack8(f);
+    }
+}
+
+// Small feature maps (8x8 level: a few MB per tensor; measured slower than the two-kernel path from 16x16 up): statistics and normalisation in ONE launch, the
+// data held in registers in between.  A CTA owns (image b, slab of G whole groups) with G*cpg a multiple of 8
+// channels; blockDim = (vectors per slab, pixel lanes); thread (v, ty) keeps pixels ty, ty+PY, ... of channel vector v
+// (<= MAXP of them; up to 1024 threads so that every thread has only a few loads, all in flight at once).  The
+// two-kernel path costs two dependent launches on these sizes.  Reduction order is fixed (tree over pixel lanes, then
+// vectors in channel order), so results are run-to-run deterministic.
+template <int MAXP>
+__global__ void __launch_bounds__(1024) gn_small_kernel(const __nv_bfloat16* __restrict__ x1, int C1, const __nv_bfloat16* __restrict__ x2,
+                                                        int C2, int HW, int groups, int G, float eps,
+                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                        int silu, __nv_bfloat16* __restrict__ out) {
+    __shared__ float4 ps[1024];
+    __shared__ float g_mean[8], g_rstd[8];
+    const int C = C1 + C2;
+    const int cpg = C / groups;
+    const int b = blockIdx.y;
+    const int nvec = blockDim.x, PY = blockDim.y;
+    const int tid = threadIdx.y * nvec + threadIdx.x;
+    const int cs = blockIdx.x * G * cpg;            // first channel of the slab
+    const int c0 = cs + threadIdx.x * 8;
+    pdl_trigger();
+    pdl_wait();
+    const __nv_bfloat16* src;
+    int ld, cc;
+    if (c0 < C1) { src = x1; ld = C1; cc = c0; } else { src = x2; ld = C2; cc = c0 - C1; }
+    src += static_cast<size_t>(b) * HW * ld + cc;
+    uint4 u[MAXP];
+#pragma unroll
+    for (int k = 0; k < MAXP; ++k) {
+        const int p = threadIdx.y + k * PY;
+        u[k] = p < HW ? __ldg(reinterpret_cast<const uint4*>(src + static_cast<size_t>(p) * ld)) : make_uint4(0, 0, 0, 0);
+    }
+    float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, q[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int k = 0; k < MAXP; ++k) {
+        float f[8];
+        unpack8(u[k], f);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { s[e] += f[e]; q[e] = fmaf(f[e], f[e], q[e]); }
+    }
+    // 8 consecutive channels touch at most two groups (cpg >= 8)
+    const int g0 = (c0 - cs) / cpg;                 // slab-local group of the first channel
+    float sa = 0.f, qa = 0.f, sb = 0.f, qb = 0.f;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        if ((c0 - cs + e) / cpg == g0) { sa += s[e]; qa += q[e]; } else { sb += s[e]; qb += q[e]; }
+    }
+    ps[tid] = make_float4(sa, qa, sb, qb);
+    __syncthreads();
+    // level 1: binary tree over the pixel lanes of each channel vector (fixed shape -> deterministic)
+    int stride = 1;
+    while (stride < PY) stride <<= 1;
+    for (stride >>= 1; stride > 0; stride >>= 1) {
+        if (int(threadIdx.y) < stride && int(threadIdx.y) + stride < PY) {
+            float4 a = ps[tid];
+            const float4 v = ps[tid + stride * nvec];
+            a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+            ps[tid] = a;
+        }
+        __syncthreads();
+    }
+    if (tid < G) {                                  // level 2: over the vectors that touch group tid, in channel order
+        float a = 0.f, q2 = 0.f;
+        for (int v = 0; v < nvec; ++v) {
+            const int gv = (v * 8) / cpg;
+            const float4 pv = ps[v];
+            if (gv == tid) { a += pv.x; q2 += pv.y; }
+            else if (gv + 1 == tid) { a += pv.z; q2 += pv.w; }
+        }
+        const float inv_cnt = 1.0f / (static_cast<float>(HW) * cpg);
+        const float mean = a * inv_cnt;
+        const float var = fmaxf(q2 * inv_cnt - mean * mean, 0.f);
+        g_mean[tid] = mean;
+        g_rstd[tid] = rsqrtf(var + eps);
+    }
+    __syncthreads();
+    float sc[8], sh[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        const int c = c0 + e;
+        const int g = (c - cs) / cpg;
+        sc[e] = g_rstd[g] * __ldg(&gamma[c]);
+        sh[e] = __ldg(&beta[c]) - g_mean[g] * sc[e];
+    }
+    __nv_bfloat16* dst = out + static_cast<size_t>(b) * HW * C + c0;
+#pragma unroll
+    for (int k = 0; k < MAXP; ++k) {
+        const int p = threadIdx.y + k * PY;
+        if (p < HW) {
+            float f[8];
+            unpack8(u[k], f);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const float y = fmaf(f[e], sc[e], sh[e]);
+                f[e] = silu ? silu_f(y) : y;
+            }
+            *reinterpret_cast<uint4*>(dst + static_cast<size_t>(p) * C) = pack8(f);
+        }
     }
 }
 
@@ -317,14 +447,48 @@ static int groupnorm_impl(const void* x1, int C1, const void* x2, int C2, int B,
     MFB_REQUIRE(CV <= 1024, "C too large");
     const int PY = CV >= 256 ? 1 : 256 / CV;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    // enough CTAs to cover the machine a few times, but at least 4*PY pixels each
-    int chunks = (4 * 148 + B - 1) / B;
-    const int max_chunks = (HW + 4 * PY - 1) / (4 * PY);
-    if (chunks > max_chunks) chunks = max_chunks;
-    if (chunks > MFB_GN_MAX_CHUNKS) chunks = MFB_GN_MAX_CHUNKS;
-    if (chunks < 1) chunks = 1;
-    const int ppc = (HW + chunks - 1) / chunks;
-    chunks = (HW + ppc - 1) / ppc;
+    static const int small_max_hw = [] { const char* e = getenv("MFB_GN_SMALL_HW"); return e ? atoi(e) : 64; }();
+    if (part1 == nullptr && HW <= small_max_hw) {
+        // single-launch path for the small feature maps
+        const int cpg = C / groups;
+        int G = 1;
+        while (G <= 4 && (G * cpg) % 8 != 0) G *= 2;
+        const int nvec = G * cpg / 8;
+        if (G <= 4 && groups % G == 0 && nvec <= 64) {
+            const int py = 256 / nvec < HW ? 256 / nvec : HW;   // ~256 threads: several CTAs per SM, one wave
+            const int ppt = (HW + py - 1) / py;
+            dim3 g2(groups / G, B), b2(nvec, py);
+            auto X1 = static_cast<const __nv_bfloat16*>(x1);
+            auto X2 = static_cast<const __nv_bfloat16*>(x2);
+            auto O = static_cast<__nv_bfloat16*>(out);
+            if (ppt <= 2) {
+                MFB_CUDA_OK(launch_k(gn_small_kernel<2>, g2, b2, 0, st, 1, X1, C1, X2, C2, HW, groups, G, eps, gamma, beta, silu, O));
+                return MFB_OK;
+            }
+            if (ppt <= 4) {
+                MFB_CUDA_OK(launch_k(gn_small_kernel<4>, g2, b2, 0, st, 1, X1, C1, X2, C2, HW, groups, G, eps, gamma, beta, silu, O));
+                return MFB_OK;
+            }
+        }
+    }
+    // Grid = ONE full wave of resident CTAs (occupancy API x SM count), every CTA an equal pixel chunk: a grid a
+    // third larger than the resident set (the earlier fixed 4 CTAs/SM guess against 3 resident at 80 registers)
+    // costs a whole second wave.  At least 4*PY pixels per CTA.
+    auto pick_chunks = [&](const void* kernel) {
+        int resident = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, kernel, CV * PY, 0) != cudaSuccess || resident < 1) resident = 2;
+        int chunks = (resident * device_sm_count()) / B;
+        const int max_chunks = (HW + 4 * PY - 1) / (4 * PY);
+        if (chunks > max_chunks) chunks = max_chunks;
+        if (chunks > MFB_GN_MAX_CHUNKS) chunks = MFB_GN_MAX_CHUNKS;
+        if (chunks < 1) chunks = 1;
+        const int ppc = (HW + chunks - 1) / chunks;
+        return ppc;
+    };
+    const int ppc = pick_chunks(reinterpret_cast<const void*>(gn_stats_kernel));          // statistics pass
+    const int chunks = (HW + ppc - 1) / ppc;
+    const int ppc_apply = pick_chunks(reinterpret_cast<const void*>(gn_apply_kernel));    // apply pass
+    const int chunks_apply = (HW + ppc_apply - 1) / ppc_apply;
     // workspace layout: stats [B*groups*2] | partials [B*MAX_CHUNKS*groups*2] | ticket counters [B] (zero on first use)
     float* part = stats_ws + static_cast<size_t>(2) * B * groups;
     unsigned int* counters = reinterpret_cast<unsigned int*>(part + static_cast<size_t>(2) * B * groups * MFB_GN_MAX_CHUNKS);
@@ -337,8 +501,8 @@ static int groupnorm_impl(const void* x1, int C1, const void* x2, int C2, int B,
         MFB_CUDA_OK(launch_k(gn_stats_kernel, grid, block, 0, st, 1, static_cast<const __nv_bfloat16*>(x1), C1,
                              static_cast<const __nv_bfloat16*>(x2), C2, HW, groups, ppc, stats_ws, part, counters));
     }
-    MFB_CUDA_OK(launch_k(gn_apply_kernel, grid, block, 0, st, 1, static_cast<const __nv_bfloat16*>(x1), C1,
-                         static_cast<const __nv_bfloat16*>(x2), C2, HW, groups, ppc, static_cast<const float*>(stats_ws), eps, gamma,
+    MFB_CUDA_OK(launch_k(gn_apply_kernel, dim3(chunks_apply, B), block, 0, st, 1, static_cast<const __nv_bfloat16*>(x1), C1,
+                         static_cast<const __nv_bfloat16*>(x2), C2, HW, groups, ppc_apply, static_cast<const float*>(stats_ws), eps, gamma,
                          beta, silu, static_cast<__nv_bfloat16*>(out)));
     return MFB_OK;
 }

@@ -181,7 +181,10 @@ def test_persistent_tile_loop_many_tiles(ops):
 # ------------------------------------------------------------------------------------------------ norms
 @pytest.mark.parametrize("B,HW,C1,C2,groups,eps,silu", [
     (2, 4096, 320, 0, 32, 1e-5, True), (2, 256, 1280, 640, 32, 1e-5, True), (2, 1024, 640, 320, 32, 1e-5, True),
-    (3, 64, 1280, 1280, 32, 1e-5, True), (2, 1024, 640, 0, 32, 1e-6, False), (2, 256, 64, 0, 8, 1e-5, True)])
+    (3, 64, 1280, 1280, 32, 1e-5, True), (2, 1024, 640, 0, 32, 1e-6, False), (2, 256, 64, 0, 8, 1e-5, True),
+    # single-launch path of the small feature maps: group pairs (cpg 20 / 60), one group per CTA (cpg 40 / 80)
+    (2, 256, 640, 0, 32, 1e-5, True), (3, 64, 1280, 0, 32, 1e-5, True), (2, 256, 1280, 1280, 32, 1e-5, False),
+    (16, 4096, 320, 0, 32, 1e-5, True)])
 def test_groupnorm(ops, B, HW, C1, C2, groups, eps, silu):
     x1 = randn(B, HW, C1, seed=1) + 0.5
     x2 = randn(B, HW, C2, seed=2, scale=2.0) if C2 else None

@@ -1,5 +1,5 @@
-"""Per-shape throughput of the flash-attention kernel on the attention shapes of one SD1.5 denoise step
- at net batch B.  Prints ms and TFLOP/s (unpadded head dim) per shape; used to steer tuning."""
+"""Per-shape throughput of GroupNorm(+SiLU) (statistics pass + apply pass) on the shapes of one SD1.5 denoise step
+ at net batch B: ms and effective GB/s (algorithmic traffic = 2 reads + 1 write of the tensor)."""
 import argparse
 import os
 import sys
@@ -16,27 +16,24 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--batch", type=int, default=16)
     ap.add_argument("--only", type=str, default="")
-    ap.add_argument("--iters", type=int, default=10)
+    ap.add_argument("--iters", type=int, default=20)
     args = ap.parse_args()
     ops.lib()
     B = args.batch
-    shapes = [  # (name, Tq, Tk, heads, head_dim)
-        ("self 64x64 d40", 4096, 4096, 8, 40), ("cross 64x64 d40", 4096, 77, 8, 40),
-        ("self 32x32 d80", 1024, 1024, 8, 80), ("cross 32x32 d80", 1024, 77, 8, 80),
-        ("self 16x16 d160", 256, 256, 8, 160), ("cross 16x16 d160", 256, 77, 8, 160),
-        ("self 8x8 d160", 64, 64, 8, 160),
-    ]
-    for name, Tq, Tk, H, D in shapes:
+    shapes = [("64x64 320", 64, 320, 0), ("64x64 640+320", 64, 640, 320), ("64x64 320+320", 64, 320, 320),
+              ("32x32 640", 32, 640, 0), ("32x32 1280+640", 32, 1280, 640), ("16x16 1280", 16, 1280, 0),
+              ("16x16 1280+1280", 16, 1280, 1280), ("8x8 1280", 8, 1280, 0), ("8x8 1280+1280", 8, 1280, 1280)]
+    for name, H, C1, C2 in shapes:
         if args.only and args.only not in name:
             continue
-        C = H * D
-        Tkp = (Tk + 7) // 8 * 8
-        q = torch.randn(B, Tq, C, device="cuda").to(bf16)
-        k = torch.randn(B, Tk, C, device="cuda").to(bf16)
-        vt = torch.zeros(B, C, Tkp, device="cuda", dtype=bf16)
-        vt[:, :, :Tk] = torch.randn(B, C, Tk, device="cuda").to(bf16)
-        out = torch.empty(B, Tq, C, device="cuda", dtype=bf16)
-        run = lambda: ops.attention(q, k, vt, out, B=B, heads=H, head_dim=D, Tq=Tq, Tk=Tk)
+        HW, C = H * H, C1 + C2
+        x1 = torch.randn(B, HW, C1, device="cuda").to(bf16)
+        x2 = torch.randn(B, HW, C2, device="cuda").to(bf16) if C2 else None
+        out = torch.empty(B, HW, C, device="cuda", dtype=bf16)
+        gamma = torch.ones(C, device="cuda")
+        beta = torch.zeros(C, device="cuda")
+        ws = torch.zeros(ops.gn_ws_floats(B, 32), device="cuda")
+        run = lambda: ops.groupnorm(x1, x2, gamma, beta, out, ws, B=B, HW=HW, groups=32, eps=1e-5, silu=True)
         for _ in range(3):
             run()
         torch.cuda.synchronize()
@@ -57,8 +54,8 @@ def main():
         b.record()
         torch.cuda.synchronize()
         ms = a.elapsed_time(b) / args.iters
-        fl = 4.0 * B * H * Tq * Tk * D
-        print(f"{name:20s} Tq={Tq:5d} Tk={Tk:5d} H={H} D={D:3d}  {ms:8.4f} ms  {fl / ms / 1e9:8.1f} TFLOP/s", flush=True)
+        nbytes = 3.0 * B * HW * C * 2
+        print(f"GN+SiLU {name:18s} {B * HW * C * 2 / 1e6:7.1f} MB  {ms * 1e3:8.1f} us  {nbytes / ms / 1e6:8.1f} GB/s", flush=True)
 
 
 if __name__ == "__main__":
