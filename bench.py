@@ -255,7 +255,7 @@ def run_ours(args, rank, world, local_rank):
             r = fam.setdefault(k, [0.0, 0.0, 0])
             r[0] += t_ms; r[1] += fl; r[2] += n
     traffic, traffic_src = None, None
-    tp = os.path.join(ROOT, "profiles", "r01g_igemm_traffic.json")     # from the committed ncu --set full capture
+    tp = os.path.join(ROOT, "profiles", "r01m_igemm_traffic.json")     # from the committed ncu --set full capture
     if os.path.exists(tp):
         with open(tp) as f:
             tj = json.load(f)
@@ -267,7 +267,8 @@ def run_ours(args, rank, world, local_rank):
     roofline = {
         "bound": "tensor", "kernel": "mfb::igemm_kernel<160|128> (tcgen05 implicit-GEMM conv/linear)",
         "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-        "peak_source": peaks["source"] + ", sustained bf16 (kernel timed inside a long step)", "traffic": None,
+        "peak_source": peaks["source"] + ", sustained bf16 (kernel timed inside a long step)",
+        "traffic": traffic, "traffic_unit": "DRAM bytes per launch (read + write)", "traffic_source": traffic_src,
         "launches_per_step": ig[2], "avg_launch_ms": ig[0] / max(ig[2], 1),
         "algorithmic_flops_per_step": ig[1],
         "share_of_step_time": ig[0] / sum(v[0] for v in fam.values()),
