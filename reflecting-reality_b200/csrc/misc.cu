@@ -194,22 +194,38 @@ __global__ void f32_to_bf16_kernel(const float* __restrict__ x, long long n, __n
         out[i] = __float2bfloat16(x[i]);
 }
 
-// [B, T, ld] columns [col0, col0+C) -> [B, C, ldt] (token index contiguous), zero padding for t in [T, ldt)
-__global__ void transpose_tokens_kernel(const __nv_bfloat16* __restrict__ x, int ld, int col0, int C, int T,
-                                        __nv_bfloat16* __restrict__ out, int ldt) {
-    __shared__ __nv_bfloat16 tile[32][34];
+// [B, T, ld] columns [col0, col0+C) -> [B, C, ldt] (token index contiguous), zero padding for t in [T, ldt).
+// 64 x 64 tile per CTA, 16-byte global accesses on both sides (a row of 64 channels / 64 tokens = one 128 B line):
+// thread (tl, cv) loads 8 channels of tokens tl, tl+32, scatters them into a [channel][token] smem tile (pitch 72
+// elements = 144 B keeps the 16-byte rows of the read side aligned), then thread (cl, tv) stores 8 tokens of channels
+// cl, cl+32.  Requires col0 % 8 == 0, C % 8 == 0, ld % 8 == 0, ldt % 8 == 0 (checked on the host).
+__global__ void __launch_bounds__(256) transpose_tokens_kernel(const __nv_bfloat16* __restrict__ x, int ld, int col0, int C, int T,
+                                                                __nv_bfloat16* __restrict__ out, int ldt) {
+    __shared__ __align__(16) __nv_bfloat16 tile[64][72];
     const int b = blockIdx.z;
-    const int t0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    const int t0 = blockIdx.x * 64, c0 = blockIdx.y * 64;
+    const int v = threadIdx.x & 7, l = threadIdx.x >> 3;     // 8 vectors x 32 rows
     pdl_trigger();
     pdl_wait();
-    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
-        const int t = t0 + i, c = c0 + threadIdx.x;
-        tile[i][threadIdx.x] = (t < T && c < C) ? x[(static_cast<size_t>(b) * T + t) * ld + col0 + c] : __float2bfloat16(0.f);
+    uint4 u[2];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        const int t = t0 + l + 32 * k, c = c0 + v * 8;
+        u[k] = (t < T && c < C) ? __ldg(reinterpret_cast<const uint4*>(x + (static_cast<size_t>(b) * T + t) * ld + col0 + c))
+                                : make_uint4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        const __nv_bfloat16* e = reinterpret_cast<const __nv_bfloat16*>(&u[k]);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) tile[v * 8 + i][l + 32 * k] = e[i];
     }
     __syncthreads();
-    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
-        const int c = c0 + i, t = t0 + threadIdx.x;
-        if (c < C && t < ldt) out[(static_cast<size_t>(b) * C + c) * ldt + t] = tile[threadIdx.x][i];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        const int c = c0 + l + 32 * k, t = t0 + v * 8;
+        if (c < C && t < ldt)
+            *reinterpret_cast<uint4*>(out + (static_cast<size_t>(b) * C + c) * ldt + t) = *reinterpret_cast<const uint4*>(&tile[l + 32 * k][v * 8]);
     }
 }
 
@@ -385,7 +401,8 @@ extern "C" int mfb_f32_to_bf16(const float* x, long long n, void* out, void* str
 
 extern "C" int mfb_transpose_tokens(const void* x, int ld, int col0, int C, int B, int T, void* out, int ldt, void* stream) {
     MFB_REQUIRE(x && out && ldt >= T, "bad arguments");
-    dim3 grid((ldt + 31) / 32, (C + 31) / 32, B), block(32, 8);
+    MFB_REQUIRE(ld % 8 == 0 && col0 % 8 == 0 && C % 8 == 0 && ldt % 8 == 0, "transpose_tokens needs ld, col0, C, ldt to be multiples of 8");
+    dim3 grid((ldt + 63) / 64, (C + 63) / 64, B), block(256);
     MFB_CUDA_OK(launch_k(transpose_tokens_kernel, grid, block, 0, static_cast<cudaStream_t>(stream), 1,
                          static_cast<const __nv_bfloat16*>(x), ld, col0, C, T, static_cast<__nv_bfloat16*>(out), ldt));
     return MFB_OK;

@@ -266,6 +266,7 @@ def test_attention(ops, B, heads, d, Tq, Tk):
     vt = torch.full((B, Cc, ldt), float("nan"), device="cuda", dtype=bf16)
     ops.transpose_tokens(v, vt, ld=Cc, col0=0, Cc=Cc, B=B, T=Tk, ldt=ldt)
     assert torch.equal(vt[:, :, :Tk], v.transpose(1, 2))
+    assert bool((vt[:, :, Tk:] == 0).all())          # key padding up to the 16-byte boundary is zero-filled
     out = torch.full((B, Tq, Cc), float("nan"), device="cuda", dtype=bf16)
     ops.attention(q, k, vt, out, B=B, heads=heads, head_dim=d, Tq=Tq, Tk=Tk)
     qh = q.float().view(B, Tq, heads, d).transpose(1, 2)
