@@ -249,12 +249,40 @@ class StepEngine:
     latents -> BrushNet -> UNet (+taps) -> CFG -> scheduler, all state resident on the device."""
 
     def __init__(self, cfg: NetConfig, unet_sd, brushnet_sd, images: int, H: int, W: int, device="cuda",
-                 use_graph: bool = True, fuse_taps: bool = True, two_streams: bool = False):
+                 use_graph: bool = True, fuse_taps: bool = True, two_streams: bool = False,
+                 dedup_brushnet_cfg: bool = False):
+        """dedup_brushnet_cfg (opt-in, exact): BrushNetModel has no attention, so `encoder_hidden_states` is unused
+        (brushnet.py:678-925) and in the pipeline's default mode both CFG halves of its batch are identical by
+        construction (`latent_model_input = torch.cat([latents] * 2)`, doubled `conditioning_latents`,
+        pipeline_brushnet.py:1256,1188-1202).  The branch is then evaluated on `images` samples and its 28 features
+        are broadcast to both halves before the UNet consumes them — bit-identical taps, 18 % fewer FLOPs per step.
+        `set_conditioning` refuses conditioning whose halves differ.  Off by default: the headline numbers of
+        bench.py run the reference's full 2b-sample BrushNet."""
         self.cfg, self.images, self.H, self.W = cfg, images, H, W
         self.dev = torch.device(device)
         B = 2 * images
         self.fuse_taps = fuse_taps
-        if fuse_taps:
+        self.dedup = bool(dedup_brushnet_cfg)
+        if self.dedup and not fuse_taps:
+            raise ValueError("dedup_brushnet_cfg requires fuse_taps=True")
+        if self.dedup:
+            self.bn = BrushNetEngine(cfg, brushnet_sd, images, H, W, self.dev, only_first_tap=True)
+            dup = lambda t: torch.empty(2, *t.shape, device=self.dev, dtype=t.dtype)
+            both = []
+            for k, (src, wz, bz) in enumerate(self.bn.tap_sources):
+                if k == 0:                                   # the conv_in-site tap is consumed as a tensor (tap0)
+                    both.append((src, wz, bz))
+                    continue
+                d = dup(src)
+                self.bn.emit(lambda s0=src, d0=d: d0.copy_(s0.unsqueeze(0).expand_as(d0)), out=d)
+                both.append((d.view(2 * src.shape[0], *src.shape[1:]), wz, bz))
+            t0 = self.bn.taps[0]
+            d0 = dup(t0)
+            self.bn.emit(lambda s0=t0, d1=d0: d1.copy_(s0.unsqueeze(0).expand_as(d1)), out=d0)
+            self._dup_keep = [d0] + [b[0] for b in both]
+            self.unet = UNetEngine(cfg, unet_sd, B, H, W, self.dev, tap_sources=both,
+                                   tap0=d0.view(2 * t0.shape[0], *t0.shape[1:]))
+        elif fuse_taps:
             # 27 of the 28 zero-convs run inside the UNet GEMM that consumes the tap (extra K-segment); only the
             # conv_in-site tap is a tensor
             self.bn = BrushNetEngine(cfg, brushnet_sd, B, H, W, self.dev, only_first_tap=True)
@@ -276,13 +304,20 @@ class StepEngine:
 
     def set_conditioning(self, prompt_embeds: torch.Tensor, conditioning_latents: torch.Tensor):
         self.unet.set_context(prompt_embeds)
-        self.bn.cond_in.copy_(conditioning_latents)
+        if self.dedup:
+            n = self.images
+            if not torch.equal(conditioning_latents[:n], conditioning_latents[n:]):
+                raise ValueError("dedup_brushnet_cfg: the two CFG halves of conditioning_latents differ")
+            self.bn.cond_in.copy_(conditioning_latents[:n])
+        else:
+            self.bn.cond_in.copy_(conditioning_latents)
 
     def _enqueue(self):
         n = self.images
         for e in (self.bn, self.unet):                    # latent_model_input = cat([latents] * 2) (:1256)
             e.sample_in[:n].copy_(self.x)
-            e.sample_in[n:].copy_(self.x)
+            if e.sample_in.shape[0] > n:                  # (the de-duplicated BrushNet sees each latent once)
+                e.sample_in[n:].copy_(self.x)
         skip = 0 if self.time_tables is None else None    # hoisted timestep path: row biases were copied in by step()
         if self.two_streams:
             self._run_two_streams(skip)

@@ -139,6 +139,36 @@ def test_fused_taps_match_unfused_and_oracle(P):
     assert rel(outs[True][0], outs[False][0]) < 2e-2      # two independent bf16 rounding histories
 
 
+def test_brushnet_cfg_dedup_is_exact(P):
+    """Opt-in BrushNet CFG de-duplication: the branch ignores the text, so with identical conditioning halves it is run
+    on `images` samples and broadcast — the noise prediction and the updated latents must be BIT-identical to the full
+    2b-sample evaluation (same kernels, same per-sample arithmetic), eagerly and as a CUDA graph, over several steps
+    and with a conditioning scale != 1; differing halves must be refused."""
+    cfg = TINY
+    usd, bsd = make_state_dict(cfg, "unet"), make_state_dict(cfg, "brushnet")
+    inp = make_inputs(cfg, 3, seed=11)
+    sched = P.B200UniPCScheduler()
+    sched.set_timesteps(4)
+    table = sched.coefficient_table(7.5).cuda()
+    outs = {}
+    for dedup, graph in ((False, False), (True, False), (True, True)):
+        eng = P.StepEngine(cfg, usd, bsd, 3, cfg.sample_size, cfg.sample_size, use_graph=graph, dedup_brushnet_cfg=dedup)
+        eng.set_conditioning(inp["prompt_embeds"].cuda(), inp["conditioning_latents"].cuda())
+        eng.x.copy_(inp["latents"].cuda())
+        for i in range(3):
+            eng.step(float(sched.timesteps[i]), table[i], 0.7)
+        torch.cuda.synchronize()
+        outs[(dedup, graph)] = (eng.unet.out.clone(), eng.x.clone())
+    for key in ((True, False), (True, True)):
+        assert torch.equal(outs[key][0], outs[(False, False)][0])
+        assert torch.equal(outs[key][1], outs[(False, False)][1])
+    eng = P.StepEngine(cfg, usd, bsd, 3, cfg.sample_size, cfg.sample_size, use_graph=False, dedup_brushnet_cfg=True)
+    bad = inp["conditioning_latents"].clone()
+    bad[-1] += 1.0
+    with pytest.raises(ValueError):
+        eng.set_conditioning(inp["prompt_embeds"].cuda(), bad.cuda())
+
+
 def test_sd15_fused_step_vs_reference_golden(P, golden_dir):
     """Full SD1.5-shaped nets through the fused StepEngine (what bench.py runs): raw noise prediction vs the reference."""
     g = np.load(os.path.join(golden_dir, "sd15_step.npz"))
