@@ -373,19 +373,23 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 1) igemm_kernel(const __grid_co
                 }
                 sb[threadIdx.x] = bv;
             }
-            if (leader) {
-                tma_store_wait_read();                 // previous tile's store no longer reads the staging tile
-                if (p.res1) {
+            const uint32_t trow = tmem_base + as * Cfg::ACC_COLS + (uint32_t(q * 32) << 16);
+            // The staging tile is needed (a) for the residual tile, which TMA loads into it as soon as the previous
+            // tile's store has drained it — at the tile start — or (b) without a residual only once the accumulator
+            // slice sits in registers: then the leader's wait for the previous store and the barrier that publishes it
+            // (and the column bias) move behind the TMEM load and the store drains under the accumulator wait.
+            // (Reading the residual straight from global into registers was measured slower: row-strided 16-byte loads.)
+            const bool early_stage = p.res1 != nullptr;
+            if (early_stage) {
+                if (leader) {
+                    tma_store_wait_read();
                     mbar_expect_tx(res_full_bar, uint32_t(nbox) * BM * BOXC * 2);
                     for (int bx = 0; bx < nbox; ++bx)
                         tma_load_4d(stg_base + bx * (BM * BOXC * 2), &p.tmRes, res_full_bar, nt * bn_out + bx * BOXC, w0, h0, n0);
                 }
+                __syncwarp();
+                named_bar_sync(1, IGEMM_EPI_WARPS * 32);   // staging tile is being filled with res1; sb is visible
             }
-            __syncwarp();
-            named_bar_sync(1, IGEMM_EPI_WARPS * 32);   // staging tile is free (or being filled with res1); sb is visible
-            mbar_wait_relaxed(tmem_full_bar(as), (li >> 1) & 1);
-            tc_fence_after();
-            const uint32_t trow = tmem_base + as * Cfg::ACC_COLS + (uint32_t(q * 32) << 16);
             // once this warp's accumulator slice sits in registers the slot goes back to the MMA warp
             auto release_acc = [&]() {
                 tmem_wait_ld();
@@ -395,6 +399,11 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 1) igemm_kernel(const __grid_co
                     if constexpr (TWOSM) mbar_arrive_cluster(mapa_shared(tmem_empty_bar(as), 0));   // the leader issues the MMAs
                     else mbar_arrive(tmem_empty_bar(as));
                 }
+                if (!early_stage) {
+                    if (leader) tma_store_wait_read();     // previous tile's store no longer reads the staging tile
+                    __syncwarp();
+                    named_bar_sync(1, IGEMM_EPI_WARPS * 32);   // staging tile is free; sb is visible
+                }
             };
 
             if (!p.geglu) {
@@ -402,6 +411,8 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 1) igemm_kernel(const __grid_co
                 constexpr int MAXC = (NCH + 1) / 2;
                 const int c_begin = half ? MAXC : 0;
                 const int c_cnt = half ? NCH - MAXC : MAXC;
+                mbar_wait_relaxed(tmem_full_bar(as), (li >> 1) & 1);
+                tc_fence_after();
                 // fetch this warp's whole accumulator slice with back-to-back tcgen05.ld and ONE wait
                 uint32_t v[MAXC][16];
 #pragma unroll
@@ -451,6 +462,8 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 1) igemm_kernel(const __grid_co
             } else {
                 // GEGLU (S/models/activations.py:100-103): out = value * gelu_erf(gate); tile = [64 value | 64 gate]
                 if constexpr (BN == 128) {
+                    mbar_wait_relaxed(tmem_full_bar(as), (li >> 1) & 1);
+                    tc_fence_after();
                     uint32_t v[2][16], g[2][16];
 #pragma unroll
                     for (int c = 0; c < 2; ++c) {

@@ -113,6 +113,13 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const void* tmap, uint
         : "memory");
 }
 
+// L2 prefetch of a 4-D box (no shared-memory destination, no completion tracking)
+__device__ __forceinline__ void tma_prefetch_4d(const void* tmap, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global [%0, {%1, %2, %3, %4}];" ::"l"(reinterpret_cast<uint64_t>(tmap)),
+                 "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+                 : "memory");
+}
+
 // multicast: the box is written at the same CTA-relative smem offset of every CTA in `mask`, and complete_tx is
 // signalled on the mbarrier at the same offset in each of them
 __device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1, uint16_t mask) {

@@ -35,6 +35,7 @@ class _Net:
         self.sd = {k: v.detach().to(device=device, dtype=f32) for k, v in sd.items()}
         self.prog: List[Callable[[], None]] = []
         self.tags: List[Tuple[str, float]] = []       # (kernel family, algorithmic FLOPs) per program entry
+        self.notes: List[Optional[str]] = []          # shape note per program entry (igemm plans only)
         self.keep: List[object] = []
         self._scratch: Dict[Tuple, torch.Tensor] = {}
         self.flops = 0.0
@@ -85,6 +86,7 @@ class _Net:
         pos = len(self.prog)
         self.prog.append(fn)
         self.tags.append((tag, flops))
+        self.notes.append(None)
         self.launches += n_launch
         if out is not None:
             self.writer_pos[out.data_ptr()] = pos
@@ -105,6 +107,7 @@ class _Net:
         self.keep.append(plan)
         self.flops += plan.flops
         self.emit(plan.run, getattr(plan, "launches", 1), "igemm", plan.flops, out=out, reads=reads)
+        self.notes[-1] = getattr(plan, "note", None)
 
     def groupnorm(self, x1, x2, prefix: str, out, HW: int, eps: float, silu: bool):
         g, b = self.wf(prefix + ".weight"), self.wf(prefix + ".bias")
@@ -254,9 +257,10 @@ class _Net:
         for f in self.prog:
             f()
 
-    def run_timed(self):
+    def run_timed(self, per_entry: bool = False):
         """Run the program once with a CUDA-event pair around every entry (on the current stream) and return
-        {family: (milliseconds, algorithmic FLOPs, entries)} — the live per-kernel timing bench.py reports."""
+        {family: (milliseconds, algorithmic FLOPs, entries)} — the live per-kernel timing bench.py reports.
+        per_entry=True returns [(family, note, ms, FLOPs)] per program entry instead (tools/profile_step.py)."""
         evs = []
         for f in self.prog:
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -265,6 +269,8 @@ class _Net:
             b.record()
             evs.append((a, b))
         torch.cuda.synchronize()
+        if per_entry:
+            return [(tag, note, a.elapsed_time(b), fl) for (a, b), (tag, fl), note in zip(evs, self.tags, self.notes)]
         out: Dict[str, List[float]] = {}
         for (a, b), (tag, fl) in zip(evs, self.tags):
             r = out.setdefault(tag, [0.0, 0.0, 0])

@@ -124,6 +124,10 @@ class ConvPlan:
         self._keep = (x, w, out, extras, bias, rowbias, alpha, res1, res2)
         self.flops = L.mfb_plan_flops(h)
         self.launches = L.mfb_plan_launches(h)
+        Ho, Wo = (2 * H, 2 * W) if up2x else ((H + stride - 1) // stride, (W + stride - 1) // stride)
+        self.note = (f"M={B * Ho * Wo} N={Cout} K={ktot} k{ksize}" + (" s2" if stride == 2 else "") + (" up2x" if up2x else "") +
+                     (" geglu" if geglu else "") + (" +res1" if res1 is not None else "") + (" +res2" if res2 is not None else "") +
+                     (f" +{len(extras)}seg" if extras else ""))
 
     def run(self):
         check(self._L.mfb_plan_run(self._h, _stream()))
