@@ -257,12 +257,13 @@ class _Net:
         for f in self.prog:
             f()
 
-    def run_timed(self, per_entry: bool = False):
+    def run_timed(self, per_entry: bool = False, skip: int = 0):
         """Run the program once with a CUDA-event pair around every entry (on the current stream) and return
         {family: (milliseconds, algorithmic FLOPs, entries)} — the live per-kernel timing bench.py reports.
-        per_entry=True returns [(family, note, ms, FLOPs)] per program entry instead (tools/profile_step.py)."""
+        per_entry=True returns [(family, note, ms, FLOPs)] per program entry instead (tools/profile_step.py).
+        skip: leading entries to leave out (the hoisted timestep path: `n_time_ops`)."""
         evs = []
-        for f in self.prog:
+        for f in self.prog[skip:]:
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
             f()
@@ -270,9 +271,9 @@ class _Net:
             evs.append((a, b))
         torch.cuda.synchronize()
         if per_entry:
-            return [(tag, note, a.elapsed_time(b), fl) for (a, b), (tag, fl), note in zip(evs, self.tags, self.notes)]
+            return [(tag, note, a.elapsed_time(b), fl) for (a, b), (tag, fl), note in zip(evs, self.tags[skip:], self.notes[skip:])]
         out: Dict[str, List[float]] = {}
-        for (a, b), (tag, fl) in zip(evs, self.tags):
+        for (a, b), (tag, fl) in zip(evs, self.tags[skip:]):
             r = out.setdefault(tag, [0.0, 0.0, 0])
             r[0] += a.elapsed_time(b)
             r[1] += fl

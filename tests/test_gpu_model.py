@@ -169,6 +169,27 @@ def test_brushnet_cfg_dedup_is_exact(P):
         eng.set_conditioning(inp["prompt_embeds"].cuda(), bad.cuda())
 
 
+@pytest.mark.parametrize("H,W,images", [(24, 40, 3), (8, 8, 1), (40, 16, 2)])
+def test_non_square_latents_vs_oracle(P, H, W, images):
+    """Latent sizes that are not powers of two and not multiples of the 128-row GEMM tile (192x320, 64x64 and 320x128
+    pixel images; the reference accepts any multiple of 8): M / N tails of every tile, clipped TMA stores, odd image
+    counts — one fused step (taps as K-segments) against the fp32 oracle."""
+    from oracle import mf_oracle as O
+    cfg = TINY
+    usd, bsd = make_state_dict(cfg, "unet"), make_state_dict(cfg, "brushnet")
+    inp = make_inputs(cfg, images, seed=21, height=H, width=W)
+    eng = P.StepEngine(cfg, usd, bsd, images, H, W, use_graph=False)
+    eng.set_conditioning(inp["prompt_embeds"].cuda(), inp["conditioning_latents"].cuda())
+    eng.x.copy_(inp["latents"].cuda())
+    eng.step(481.0, torch.zeros(12, device="cuda"), 1.0)
+    with torch.no_grad():
+        ref, _ = O.noise_pred_step(usd, bsd, cfg, torch.cat([inp["latents"]] * 2), 481.0, inp["prompt_embeds"],
+                                   inp["conditioning_latents"], 1.0)
+    e = rel(eng.unet.out, ref)
+    record("tiny_non_square_vs_oracle", H=H, W=W, images=images, noise_pred=e)
+    assert e < TINY_TOL
+
+
 def test_sd15_fused_step_vs_reference_golden(P, golden_dir):
     """Full SD1.5-shaped nets through the fused StepEngine (what bench.py runs): raw noise prediction vs the reference."""
     g = np.load(os.path.join(golden_dir, "sd15_step.npz"))

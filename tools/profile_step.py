@@ -38,7 +38,7 @@ def main():
     for _ in range(3):                          # keep the last of 3 passes (warm)
         rows = []
         for net, e in (("brushnet", eng.bn), ("unet", eng.unet)):
-            rows += [(net,) + r for r in e.run_timed(per_entry=True)]
+            rows += [(net,) + r for r in e.run_timed(per_entry=True, skip=e.n_time_ops)]   # timestep path: hoisted in the real loop
     agg = collections.OrderedDict()
     fam = collections.Counter()
     for net, tag, note, ms, fl in rows:
@@ -48,6 +48,9 @@ def main():
         a = agg.setdefault(note, [0, 0.0, 0.0])
         a[0] += 1; a[1] += ms; a[2] += fl
     print("families (ms, eager events incl. launch gaps):", {k: round(v, 3) for k, v in fam.items()})
+    for tag in ("misc", "attention", "groupnorm", "layernorm"):
+        ent = sorted([(ms, net, i) for i, (net, t, note, ms, fl) in enumerate(rows) if t == tag], reverse=True)
+        print(f"{tag}: {len(ent)} entries; top:", [(round(ms * 1e3, 1), net, i) for ms, net, i in ent[:12]], "(us, net, program index)")
     tot = sum(a[1] for a in agg.values())
     print(f"igemm: {tot:.3f} ms in {sum(a[0] for a in agg.values())} launches; by shape, sorted by headroom (ms above the ideal):")
     out = []
