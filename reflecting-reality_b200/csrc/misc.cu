@@ -86,64 +86,112 @@ __global__ void conv_in_kernel(const float* __restrict__ xa, int Ca, const float
 }
 
 // ---------------------------------------------------------------------------------------------- conv_out
-// One thread per output pixel, all Cout (<= 4) outputs in registers.  Weights [3][3][Cin][4] fp32 sit in shared
-// memory and are read as warp-wide BROADCAST float4s (every lane needs the same weight), activations come in as
-// 16-byte vectors through L1 (each pixel is re-read by its 9 neighbours).  ~50 issue slots per 8 channels.
-__global__ void __launch_bounds__(128) conv_out_kernel(const __nv_bfloat16* __restrict__ x, int Cin, int B, int H, int W,
+// 320 -> 4 channel 3x3 conv at the fp32 NCHW boundary, CUDA cores (fp32 accumulate AND fp32 output: rounding the
+// noise prediction to bf16 would eat the parity margin).  Persistent CTAs of 256 threads = 32 pixel quads x 8 channel
+// slices.  A thread owns 4 consecutive pixels of a row and the 16-byte channel vectors v = 8k + s of its slice s (the 8
+// lanes of a quad read 128 contiguous bytes per pixel); per (k, filter row) it loads the 6 input pixels the quad needs
+// once and reuses every weight float4 (4 outputs per input channel) for all 4 pixels — a weight LDS.128 costs four LSU
+// cycles per warp, so without that reuse the kernel is bound by shared-memory reads (131 us), not by the 755 MFMA.
+// Weights are staged ONCE per CTA as [tap][k][e][s] float4, so the 8 slices of a warp read 128 contiguous bytes
+// (conflict-free) and the 4 quads of the warp share them by broadcast.  Partial sums of the 8 slices are combined with
+// a fixed-order shuffle butterfly.
+__global__ void __launch_bounds__(256) conv_out_kernel(const __nv_bfloat16* __restrict__ x, int Cin, int B, int H, int W,
                                                         const float* __restrict__ w, const float* __restrict__ bias, int Cout,
                                                         float* __restrict__ out) {
-    extern __shared__ float4 ws4[];  // [9*Cin] : (w[co=0..3]) for (tap, cin)
+    extern __shared__ float4 ws4[];  // [9][KV][8][8] : tap, k, element e, slice s  ->  channel c = (8k + s) * 8 + e
     const int K = 9 * Cin;
-    for (int i = threadIdx.x; i < K; i += blockDim.x) {
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        v.x = w[i];
-        if (Cout > 1) v.y = w[K + i];
-        if (Cout > 2) v.z = w[2 * K + i];
-        if (Cout > 3) v.w = w[3 * K + i];
-        ws4[i] = v;
+    const int nvec = Cin / 8;                 // 16-byte vectors per pixel
+    const int KV = (nvec + 7) / 8;            // vectors per slice
+    for (int i = threadIdx.x; i < 9 * KV * 64; i += blockDim.x) {
+        const int s = i & 7, e = (i >> 3) & 7, k = (i >> 6) % KV, tap = i / (64 * KV);
+        const int v = 8 * k + s;
+        float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (v < nvec) {
+            const int src = tap * Cin + v * 8 + e;
+            val.x = w[src];
+            if (Cout > 1) val.y = w[K + src];
+            if (Cout > 2) val.z = w[2 * K + src];
+            if (Cout > 3) val.w = w[3 * K + src];
+        }
+        ws4[i] = val;
     }
     __syncthreads();
     pdl_trigger();
     pdl_wait();      // the weights above are static; the activations below come from the previous kernel
-    const long long npix = static_cast<long long>(B) * H * W;
-    const long long pix = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (pix >= npix) return;
-    const int ow = pix % W;
-    const int oh = (pix / W) % H;
-    const int b = pix / (static_cast<long long>(W) * H);
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    const int nvec = Cin / 8;
-#pragma unroll 1
-    for (int tap = 0; tap < 9; ++tap) {
-        const int hh = oh + tap / 3 - 1, ww = ow + tap % 3 - 1;
-        if (hh < 0 || hh >= H || ww < 0 || ww >= W) continue;
-        const uint4* src = reinterpret_cast<const uint4*>(x + ((static_cast<size_t>(b) * H + hh) * W + ww) * Cin);
-        const float4* wt = ws4 + tap * Cin;
-#pragma unroll 4
-        for (int v = 0; v < nvec; ++v) {
-            const uint4 u = __ldg(src + v);
-            float f[8];
-            float2 t;
-            t = unpack_bf16x2(u.x); f[0] = t.x; f[1] = t.y;
-            t = unpack_bf16x2(u.y); f[2] = t.x; f[3] = t.y;
-            t = unpack_bf16x2(u.z); f[4] = t.x; f[5] = t.y;
-            t = unpack_bf16x2(u.w); f[6] = t.x; f[7] = t.y;
+    const int s = threadIdx.x & 7;
+    const int qpr = (W + 3) / 4;                                   // pixel quads per row
+    const long long nquad = static_cast<long long>(B) * H * qpr;
+    const size_t hw = static_cast<size_t>(H) * W;
+    for (long long q = static_cast<long long>(blockIdx.x) * 32 + (threadIdx.x >> 3); q < ((nquad + 31) / 32) * 32;
+         q += static_cast<long long>(gridDim.x) * 32) {
+        const bool live = q < nquad;           // whole 8-lane groups are live or not; dead ones still join the shuffles
+        const int ow0 = live ? int(q % qpr) * 4 : 0;
+        const int oh = live ? int((q / qpr) % H) : 0;
+        const int b = live ? int(q / (static_cast<long long>(qpr) * H)) : 0;
+        float4 acc[4];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-                const float4 wv = wt[v * 8 + e];
-                acc.x = fmaf(f[e], wv.x, acc.x);
-                acc.y = fmaf(f[e], wv.y, acc.y);
-                acc.z = fmaf(f[e], wv.z, acc.z);
-                acc.w = fmaf(f[e], wv.w, acc.w);
+        for (int px = 0; px < 4; ++px) acc[px] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (live) {
+#pragma unroll 1
+            for (int k = 0; k < KV; ++k) {
+                const int v = 8 * k + s;
+                if (v >= nvec) continue;
+#pragma unroll 1
+                for (int kh = 0; kh < 3; ++kh) {
+                    const int hh = oh + kh - 1;
+                    if (hh < 0 || hh >= H) continue;
+                    const uint4* row = reinterpret_cast<const uint4*>(x + ((static_cast<size_t>(b) * H + hh) * W) * Cin) + v;
+                    float f[6][8];
+#pragma unroll
+                    for (int cc = 0; cc < 6; ++cc) {
+                        const int col = ow0 - 1 + cc;
+                        uint4 u = make_uint4(0, 0, 0, 0);
+                        if (col >= 0 && col < W) u = __ldg(row + static_cast<size_t>(col) * nvec);
+                        float2 t;
+                        t = unpack_bf16x2(u.x); f[cc][0] = t.x; f[cc][1] = t.y;
+                        t = unpack_bf16x2(u.y); f[cc][2] = t.x; f[cc][3] = t.y;
+                        t = unpack_bf16x2(u.z); f[cc][4] = t.x; f[cc][5] = t.y;
+                        t = unpack_bf16x2(u.w); f[cc][6] = t.x; f[cc][7] = t.y;
+                    }
+#pragma unroll
+                    for (int kw = 0; kw < 3; ++kw) {
+                        const float4* wt = ws4 + ((kh * 3 + kw) * KV + k) * 64 + s;
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
+                            const float4 wv = wt[e * 8];
+#pragma unroll
+                            for (int px = 0; px < 4; ++px) {
+                                const float xv = f[px + kw][e];
+                                acc[px].x = fmaf(xv, wv.x, acc[px].x);
+                                acc[px].y = fmaf(xv, wv.y, acc[px].y);
+                                acc[px].z = fmaf(xv, wv.z, acc[px].z);
+                                acc[px].w = fmaf(xv, wv.w, acc[px].w);
+                            }
+                        }
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int px = 0; px < 4; ++px) {
+#pragma unroll
+            for (int d = 1; d < 8; d <<= 1) {      // fixed-order butterfly over the 8 channel slices
+                acc[px].x += __shfl_xor_sync(0xffffffffu, acc[px].x, d);
+                acc[px].y += __shfl_xor_sync(0xffffffffu, acc[px].y, d);
+                acc[px].z += __shfl_xor_sync(0xffffffffu, acc[px].z, d);
+                acc[px].w += __shfl_xor_sync(0xffffffffu, acc[px].w, d);
+            }
+        }
+        if (live && s < Cout) {
+#pragma unroll
+            for (int px = 0; px < 4; ++px) {
+                if (ow0 + px < W) {
+                    const float r = s == 0 ? acc[px].x : s == 1 ? acc[px].y : s == 2 ? acc[px].z : acc[px].w;
+                    out[static_cast<size_t>(b) * Cout * hw + s * hw + static_cast<size_t>(oh) * W + ow0 + px] = r + bias[s];
+                }
             }
         }
     }
-    const size_t hw = static_cast<size_t>(H) * W;
-    float* o = out + static_cast<size_t>(b) * Cout * hw + static_cast<size_t>(oh) * W + ow;
-    o[0] = acc.x + bias[0];
-    if (Cout > 1) o[hw] = acc.y + bias[1];
-    if (Cout > 2) o[2 * hw] = acc.z + bias[2];
-    if (Cout > 3) o[3 * hw] = acc.w + bias[3];
 }
 
 // ---------------------------------------------------------------------------------------------- upsample / layout
@@ -353,16 +401,18 @@ extern "C" int mfb_conv_out(const void* x, int Cin, int B, int H, int W, const f
                             float* out, void* stream) {
     MFB_REQUIRE(x && w && bias && out, "null pointer");
     MFB_REQUIRE(Cout >= 1 && Cout <= 4 && Cin % 8 == 0, "conv_out supports Cout <= 4, Cin %% 8 == 0");
-    const size_t smem = static_cast<size_t>(9) * Cin * sizeof(float4);
+    const size_t smem = static_cast<size_t>(9) * ((Cin / 8 + 7) / 8) * 64 * sizeof(float4);
     MFB_REQUIRE(smem <= 200 * 1024, "conv_out weights do not fit shared memory");
     static bool configured = false;
     if (!configured) {
         MFB_CUDA_OK(cudaFuncSetAttribute(conv_out_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         configured = true;
     }
-    const long long npix = static_cast<long long>(B) * H * W;
-    const int grid = static_cast<int>((npix + 127) / 128);
-    MFB_CUDA_OK(launch_k(conv_out_kernel, dim3(grid), dim3(128), smem, static_cast<cudaStream_t>(stream), 1,
+    const long long nquad = static_cast<long long>(B) * H * ((W + 3) / 4);
+    long long grid = (nquad + 31) / 32;
+    const long long resident = 2LL * device_sm_count();      // persistent: the weight staging is paid once per CTA
+    if (grid > resident) grid = resident;
+    MFB_CUDA_OK(launch_k(conv_out_kernel, dim3(static_cast<unsigned>(grid)), dim3(256), smem, static_cast<cudaStream_t>(stream), 1,
                          static_cast<const __nv_bfloat16*>(x), Cin, B, H, W, w, bias, Cout, out));
     return MFB_OK;
 }

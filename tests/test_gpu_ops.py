@@ -309,12 +309,15 @@ def test_conv_in(ops, Ca, Cb, H, W):
     assert rel(nhwc_to_nchw(post), ref + nhwc_to_nchw(tap)) < 4e-3
 
 
-def test_conv_out(ops):
-    B, H, W, Cin = 2, 64, 64, 320
+@pytest.mark.parametrize("B,H,W,Cin,Cout", [(2, 64, 64, 320, 4), (16, 64, 64, 320, 4), (3, 5, 7, 64, 4), (1, 16, 16, 72, 3),
+                                            (2, 24, 40, 64, 4)])
+def test_conv_out(ops, B, H, W, Cin, Cout):
+    # sizes whose pixel count is / is not a multiple of the 32-pixel CTA step, channel-vector counts that do / do not
+    # fill the 8 lanes of a pixel group (Cin 72 -> 9 vectors), fewer than 4 outputs, more pixel groups than resident CTAs
     x = randn(B, H, W, Cin, seed=1)
-    w = randn(4, Cin, 3, 3, seed=2, scale=0.02, dtype=torch.float32)
-    b = randn(4, seed=3, dtype=torch.float32)
-    out = torch.empty(B, 4, H, W, device="cuda")
+    w = randn(Cout, Cin, 3, 3, seed=2, scale=0.02, dtype=torch.float32)
+    b = randn(Cout, seed=3, dtype=torch.float32)
+    out = torch.full((B, Cout, H, W), float("nan"), device="cuda")
     ops.conv_out(x, w.permute(0, 2, 3, 1).contiguous(), b, out, B=B, H=H, W=W)
     assert rel(out, F.conv2d(nhwc_to_nchw(x), w, b, padding=1)) < 1e-4
 
