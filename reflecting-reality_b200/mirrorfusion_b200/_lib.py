@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libmfb200.so")
+# MFB200_LIB selects another build of the SAME library (kernel A/B variants, tools/ab_build.sh); never a fallback
+LIB_PATH = os.environ.get("MFB200_LIB") or os.path.join(_HERE, "lib", "libmfb200.so")
 
 _lib = None
 _inited_device = None

@@ -277,6 +277,25 @@ def test_attention(ops, B, heads, d, Tq, Tk):
     assert rel(out.float(), ref) < 6e-3
 
 
+@pytest.mark.parametrize("d,T", [(40, 1024), (80, 512), (160, 256)])
+def test_attention_rescale_path(ops, d, T):
+    # keys grow along the sequence, so the running row maximum jumps by more than the lazy-rescale threshold (2^8)
+    # in later key tiles and the O accumulator in TMEM is rescaled many times (randn inputs almost never do that)
+    B, heads = 2, 4
+    Cc = heads * d
+    q = randn(B, T, Cc, seed=11) * 3.0
+    ramp = torch.linspace(0.2, 6.0, T, device="cuda").view(1, T, 1)
+    k = (randn(B, T, Cc, seed=12).float() * ramp).to(bf16)
+    v = randn(B, T, Cc, seed=13)
+    vt = torch.empty(B, Cc, T, device="cuda", dtype=bf16)
+    ops.transpose_tokens(v, vt, ld=Cc, col0=0, Cc=Cc, B=B, T=T, ldt=T)
+    out = torch.full((B, T, Cc), float("nan"), device="cuda", dtype=bf16)
+    ops.attention(q, k, vt, out, B=B, heads=heads, head_dim=d, Tq=T, Tk=T)
+    qh, kh, vh = [t.float().view(B, T, heads, d).transpose(1, 2) for t in (q, k, v)]
+    ref = (torch.softmax(qh @ kh.transpose(-1, -2) * d ** -0.5, -1) @ vh).transpose(1, 2).reshape(B, T, Cc)
+    assert rel(out.float(), ref) < 8e-3
+
+
 def test_attention_fused_qkv_layout(ops):
     # q/k read straight out of a fused [B, T, 3C] projection buffer via leading dimensions
     B, heads, d, T = 2, 8, 40, 512
