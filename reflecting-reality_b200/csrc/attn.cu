@@ -40,6 +40,16 @@ constexpr int BQ = 128;   // query rows per tile (= TMEM lanes)
 #ifndef MFB_ATT_PINGPONG        // 1: the two warpgroups alternate in the exponential phase
 #define MFB_ATT_PINGPONG 1
 #endif
+// same knobs for the middle head dims (40 < d <= 80: the 1024-token layers), one CTA per SM
+#ifndef MFB_ATT_NQ_MID
+#define MFB_ATT_NQ_MID 2
+#endif
+#ifndef MFB_ATT_KV_MID
+#define MFB_ATT_KV_MID 64
+#endif
+#ifndef MFB_ATT_PINGPONG_MID
+#define MFB_ATT_PINGPONG_MID 1
+#endif
 #ifndef MFB_ATT_HANDOFF_EARLY   // the turn is handed over this many 8-column groups before the end of the exponential phase
 #define MFB_ATT_HANDOFF_EARLY 0
 #endif
@@ -52,8 +62,10 @@ struct AttCfg {
     static constexpr bool SMALL = D <= 40;
     static constexpr int DPAD = (D + 15) / 16 * 16;       // MMA K extent of QK^T and N extent of PV
     static constexpr int NKB = (D + 63) / 64;             // 64-column boxes per Q / K tile
-    static constexpr int NQ = SMALL ? MFB_ATT_NQ_SMALL : 1;
-    static constexpr int BKV = SMALL ? MFB_ATT_KV_SMALL : 128;
+    static constexpr bool MID = D > 40 && D <= 80;
+    static constexpr int NQ = SMALL ? MFB_ATT_NQ_SMALL : MID ? MFB_ATT_NQ_MID : 1;
+    static constexpr int BKV = SMALL ? MFB_ATT_KV_SMALL : MID ? MFB_ATT_KV_MID : 128;
+    static constexpr bool PINGPONG = NQ == 2 && (SMALL ? MFB_ATT_PINGPONG : MFB_ATT_PINGPONG_MID);
     static constexpr int CTAS_PER_SM = SMALL ? MFB_ATT_CTAS_SMALL : 1;
     static constexpr int THREADS = (4 * NQ + 2) * 32;     // NQ softmax warpgroups + TMA warp + MMA warp
     static constexpr int STAGES = D > 80 ? 1 : 2;         // K/V ring depth (smem-limited for d = 160)
@@ -240,7 +252,7 @@ __global__ void __launch_bounds__(AttCfg<D>::THREADS, AttCfg<D>::CTAS_PER_SM) at
         const int r = qd * 32 + lane;
         const uint32_t lane_off = uint32_t(qd * 32) << 16;
         const uint32_t tS = tmem_base + t * BKV + lane_off, tO = tmem_base + NQ * BKV + t * DPAD + lane_off;
-        constexpr bool kPingPong = NQ == 2 && MFB_ATT_PINGPONG;
+        constexpr bool kPingPong = Cfg::PINGPONG;
         constexpr int TURN_BAR = 1;                      // named barriers 1, 2: "warpgroup 0 / 1 may exponentiate"
         if (kZeroPad) {
             // zero Q columns [D, DPAD) of this row (one 16-byte chunk: D % 8 == 0) in the swizzled tile
@@ -408,7 +420,7 @@ extern "C" int mfb_attention(const void* q, int ldq, const void* k, int ldk, con
     {
         const uint64_t dims[3] = {uint64_t(ldk), uint64_t(Tk), uint64_t(B)};
         const uint64_t str[2] = {uint64_t(ldk) * 2, uint64_t(Tk) * ldk * 2};
-        const uint32_t box[3] = {64, uint32_t(head_dim <= 40 ? AttCfg<40>::BKV : 128), 1};      // AttCfg<D>::BKV keys per tile
+        const uint32_t box[3] = {64, uint32_t(head_dim <= 40 ? AttCfg<40>::BKV : head_dim <= 80 ? AttCfg<80>::BKV : 128), 1};      // AttCfg<D>::BKV keys per tile
         int rc = encode_tmap_bf16(&p.tmK, k, 3, dims, str, box, 128);
         if (rc) return rc;
     }
