@@ -119,11 +119,11 @@ int mfb_layernorm(const void* x, int rows, int C, float eps, const float* gamma,
  * (S/models/attention_processor.py:1266-1268): no mask, non-causal, scale = head_dim^-0.5.
  *   q  : [B, Tq, ldq]  bf16, head h occupies columns [h*d, (h+1)*d)
  *   k  : [B, Tk, ldk]  bf16, same column convention
- *   vt : [B, heads*d, ldvt] bf16 — V TRANSPOSED (keys contiguous), ldvt >= Tk and ldvt % 8 == 0
+ *   v  : [B, Tk, ldv] bf16 (head h at columns [h*d, (h+1)*d)) — consumed as stored (MN-major tensor-core operand)
  *   out: [B, Tq, ldo]  bf16
  * head_dim in {40, 80, 160} (SD1.5: 320/640/1280 channels over 8 heads) or any multiple of 16 <= 160.
  */
-int mfb_attention(const void* q, int ldq, const void* k, int ldk, const void* vt, int ldvt, void* out, int ldo, int B,
+int mfb_attention(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* out, int ldo, int B,
                   int heads, int head_dim, int Tq, int Tk, void* stream);
 /* [B, T, ld] column block [col0, col0+C) -> transposed [B, C, ldt] (ldt >= T); pads [T, ldt) with zeros. */
 int mfb_transpose_tokens(const void* x, int ld, int col0, int C, int B, int T, void* out, int ldt, void* stream);

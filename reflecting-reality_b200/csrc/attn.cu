@@ -2,7 +2,7 @@
 // AttnProcessor2_0.__call__, S/models/attention_processor.py:1266-1268; no mask, non-causal).
 //
 // One CTA = NQ 128-query tiles of one (batch, head) sharing the K/V stream.  Per key tile of BKV keys:
-//   TMA warp        : K tile [BKV keys x d] and V^T tile [d x BKV keys] -> swizzled smem ring
+//   TMA warp        : K tile [BKV keys x d] and V tile [BKV keys x d] -> swizzled smem ring
 //   MMA warp        : S_t = Q_t K^T  (M128 N=BKV, K = d in 16-steps)  -> TMEM, one S buffer per query tile
 //                     O_t += P_t V   (M128 N=dpad, K = BKV keys)      -> TMEM
 //   softmax warpgroup t (128 threads, thread = query row): tcgen05.ld S row, online softmax in the exp2 domain with
@@ -16,8 +16,10 @@
 // (profiles/r01k, profiles/r01n).
 // Head dims 40/80/160 are not multiples of 64: Q/K boxes are 64 columns wide starting at h*d, the MMA K extent
 // is d rounded up to 16, and for d % 16 != 0 the softmax threads zero the Q columns [d, dpad) in smem once, so
-// the neighbouring head's K columns that ride along contribute nothing.  V is consumed transposed
-// ([B, heads*d, keys]) so that both MMAs use the same K-major operand form as the GEMM kernel.
+// the neighbouring head's K columns that ride along contribute nothing.  V is consumed as stored ([B, keys, heads*d],
+// e.g. straight out of the fused q|k|v projection): its tile is the MN-major B operand of the P V product, so no
+// transposed copy of V exists anywhere (the neighbouring head's columns [d, dpad) only feed accumulator columns that
+// are never stored).
 #include <math.h>
 #include <string.h>
 
@@ -72,8 +74,8 @@ struct AttCfg {
     static constexpr int QT_BYTES = NKB * BQ * 128;       // one query tile
     static constexpr int Q_BYTES = NQ * QT_BYTES;
     static constexpr int K_BYTES = NKB * BKV * 128;
-    static constexpr int V_BYTES = (BKV / 64) * DPAD * 128;   // 64-key boxes of DPAD rows
-    static constexpr int KV_BYTES = K_BYTES + ((V_BYTES + 1023) / 1024) * 1024;
+    static constexpr int V_BYTES = K_BYTES;                   // same box shape: BKV key rows x 64-column blocks
+    static constexpr int KV_BYTES = K_BYTES + V_BYTES;
     static constexpr int P_BYTES = (BKV / 64) * BQ * 128;     // 128 x BKV bf16 as 64-key blocks, per query tile
     static constexpr int TMEM_USED = NQ * (BKV + DPAD);       // S_0..S_{NQ-1} | O_0..O_{NQ-1}
     static constexpr int TMEM_COLS = TMEM_USED <= 128 ? 128 : TMEM_USED <= 256 ? 256 : 512;
@@ -190,8 +192,7 @@ __global__ void __launch_bounds__(AttCfg<D>::THREADS, AttCfg<D>::CTAS_PER_SM) at
                 mbar_wait_relaxed(v_empty(s), ((j / STAGES) & 1) ^ 1);
                 mbar_expect_tx(v_full(s), Cfg::V_BYTES);
                 const uint32_t vd = kv_smem + s * Cfg::KV_BYTES + Cfg::K_BYTES;
-                for (int kb2 = 0; kb2 < BKV / 64; ++kb2)
-                    tma_load_3d(vd + kb2 * DPAD * 128, &p.tmV, v_full(s), j * BKV + 64 * kb2, h * D, b);
+                for (int kb = 0; kb < NKB; ++kb) tma_load_3d(vd + kb * BKV * 128, &p.tmV, v_full(s), h * D + kb * 64, j * BKV, b);
             }
         }
         __syncwarp();
@@ -199,7 +200,7 @@ __global__ void __launch_bounds__(AttCfg<D>::THREADS, AttCfg<D>::CTAS_PER_SM) at
         if (elect_one()) {
             // ===== MMA issuer =====
             constexpr uint32_t idesc_qk = make_idesc_bf16(128, BKV);
-            constexpr uint32_t idesc_pv = make_idesc_bf16(128, DPAD);
+            constexpr uint32_t idesc_pv = make_idesc_bf16(128, DPAD, 0, 1);     // B = V tile, MN-major
             // S_t(j) = Q_t K(j)^T for every query tile; the K slot is released after the last one
             auto issue_qk = [&](int j, bool wait_free) {
                 const int s = j % STAGES;
@@ -236,7 +237,7 @@ __global__ void __launch_bounds__(AttCfg<D>::THREADS, AttCfg<D>::CTAS_PER_SM) at
 #pragma unroll
                     for (int ks = 0; ks < BKV / 16; ++ks) {
                         const uint64_t ad = make_desc_k_sw128(p_smem + t * Cfg::P_BYTES + (ks / 4) * BQ * 128) + uint64_t(2 * (ks % 4));
-                        const uint64_t bd = make_desc_k_sw128(vd + (ks / 4) * DPAD * 128) + uint64_t(2 * (ks % 4));
+                        const uint64_t bd = make_desc_mn_sw128(vd + ks * 16 * 128, BKV * 128);      // 16 key rows per K step
                         umma_bf16(tmem_base + NQ * BKV + t * DPAD, ad, bd, idesc_pv, (j | ks) != 0);
                     }
                     umma_commit(pv_done(t));
@@ -402,14 +403,14 @@ static int launch_attention(const AttParams& p, int B, cudaStream_t st) {
 
 using namespace mfb;
 
-extern "C" int mfb_attention(const void* q, int ldq, const void* k, int ldk, const void* vt, int ldvt, void* out, int ldo,
+extern "C" int mfb_attention(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* out, int ldo,
                              int B, int heads, int head_dim, int Tq, int Tk, void* stream) {
-    MFB_REQUIRE(q && k && vt && out, "null pointer");
-    MFB_REQUIRE(ldq % 8 == 0 && ldk % 8 == 0 && ldvt % 8 == 0 && ldo % 8 == 0, "leading dimensions must be multiples of 8");
-    MFB_REQUIRE(Tq > 0 && Tk > 0 && ldvt >= Tk, "bad sequence lengths");
+    MFB_REQUIRE(q && k && v && out, "null pointer");
+    MFB_REQUIRE(ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 && ldo % 8 == 0, "leading dimensions must be multiples of 8");
+    MFB_REQUIRE(Tq > 0 && Tk > 0, "bad sequence lengths");
     AttParams p;
     memset(&p, 0, sizeof(p));
-    int dpad = (head_dim + 15) / 16 * 16;
+    const uint32_t kv_box = uint32_t(head_dim <= 40 ? AttCfg<40>::BKV : head_dim <= 80 ? AttCfg<80>::BKV : 128);   // AttCfg<D>::BKV keys per tile
     {
         const uint64_t dims[3] = {uint64_t(ldq), uint64_t(Tq), uint64_t(B)};
         const uint64_t str[2] = {uint64_t(ldq) * 2, uint64_t(Tq) * ldq * 2};
@@ -420,16 +421,15 @@ extern "C" int mfb_attention(const void* q, int ldq, const void* k, int ldk, con
     {
         const uint64_t dims[3] = {uint64_t(ldk), uint64_t(Tk), uint64_t(B)};
         const uint64_t str[2] = {uint64_t(ldk) * 2, uint64_t(Tk) * ldk * 2};
-        const uint32_t box[3] = {64, uint32_t(head_dim <= 40 ? AttCfg<40>::BKV : head_dim <= 80 ? AttCfg<80>::BKV : 128), 1};      // AttCfg<D>::BKV keys per tile
+        const uint32_t box[3] = {64, kv_box, 1};
         int rc = encode_tmap_bf16(&p.tmK, k, 3, dims, str, box, 128);
         if (rc) return rc;
     }
     {
-        const uint64_t rows = uint64_t(heads) * head_dim;
-        const uint64_t dims[3] = {uint64_t(ldvt), rows, uint64_t(B)};
-        const uint64_t str[2] = {uint64_t(ldvt) * 2, rows * ldvt * 2};
-        const uint32_t box[3] = {64, uint32_t(dpad), 1};
-        int rc = encode_tmap_bf16(&p.tmV, vt, 3, dims, str, box, 128);
+        const uint64_t dims[3] = {uint64_t(ldv), uint64_t(Tk), uint64_t(B)};
+        const uint64_t str[2] = {uint64_t(ldv) * 2, uint64_t(Tk) * ldv * 2};
+        const uint32_t box[3] = {64, kv_box, 1};
+        int rc = encode_tmap_bf16(&p.tmV, v, 3, dims, str, box, 128);
         if (rc) return rc;
     }
     p.out = static_cast<__nv_bfloat16*>(out);

@@ -255,6 +255,19 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, int a_mn_ma
 // Shared-memory matrix descriptor for a K-major operand tile stored as dense 128-byte rows with the
 // 128B swizzle (exactly what a TMA box with inner extent 64 bf16 and CU_TENSOR_MAP_SWIZZLE_128B writes):
 // start>>4 | LBO(enc 1, unused for swizzled K-major) | SBO = 1024 B (8 rows x 128 B) | version 1 | layout SWIZZLE_128B (2).
+// Same physical tile (dense 128-byte rows, 128B swizzle) read as an MN-major operand: a row is one K index holding 64
+// contiguous M/N elements.  Canonical form ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units (cute/atom/mma_traits_sm100.hpp
+// make_umma_desc<Major::MN>): SBO = 1024 B between groups of 8 K rows, LBO = bytes between 64-element M/N blocks.  A K step
+// of 16 advances the start address by 16 rows = 2048 B.  Used for V in attention (P V needs V[key][d] with d contiguous).
+__device__ __forceinline__ uint64_t make_desc_mn_sw128(uint32_t smem_addr, uint32_t lbo_bytes) {
+    uint64_t d = 0;
+    d |= uint64_t((smem_addr & 0x3FFFF) >> 4);
+    d |= uint64_t((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= uint64_t(1024 >> 4) << 32;
+    d |= uint64_t(1) << 46;
+    d |= uint64_t(2) << 61;
+    return d;
+}
 __device__ __forceinline__ uint64_t make_desc_k_sw128(uint32_t smem_addr) {
     uint64_t d = 0;
     d |= uint64_t((smem_addr & 0x3FFFF) >> 4);

@@ -371,7 +371,6 @@ class UNetEngine(_Net):
         boc = cfg.block_out_channels
         n = len(boc)
         self.ctx_len = ctx_len
-        self.ctx_pad = (ctx_len + 7) // 8 * 8
         self.sample_in = torch.zeros(B, cfg.in_channels, H, W, device=device, dtype=f32)
         self.ehs_in = torch.zeros(B, ctx_len, cfg.cross_attention_dim, device=device, dtype=f32)
         self.ehs_bf = torch.zeros(B * ctx_len, cfg.cross_attention_dim, device=device, dtype=bf16)
@@ -476,32 +475,27 @@ class UNetEngine(_Net):
         wqkv = torch.cat([self.sd[t + ".attn1.to_q.weight"], self.sd[t + ".attn1.to_k.weight"],
                           self.sd[t + ".attn1.to_v.weight"]], 0).to(bf16).contiguous()
         self.emit_plan(ops.linear_plan(nrm, wqkv, qkv))
-        Tp = (T + 7) // 8 * 8
-        vt = self.scratch("tvt", B, C, Tp)
-        self.emit(lambda: ops.transpose_tokens(qkv, vt, ld=3 * C, col0=2 * C, Cc=C, B=B, T=T, ldt=Tp))
         att = self.scratch("tatt", M, C)
-        kview = qkv.view(-1)[C:]
-        self.emit(lambda: ops.attention(qkv, kview, vt, att, B=B, heads=heads, head_dim=d, Tq=T, Tk=T, ldq=3 * C,
-                                        ldk=3 * C, ldvt=Tp, ldo=C), 1, "attention", 4.0 * B * T * T * C)
+        kview, vview = qkv.view(-1)[C:], qkv.view(-1)[2 * C:]      # q | k | v column blocks of the fused projection
+        self.emit(lambda: ops.attention(qkv, kview, vview, att, B=B, heads=heads, head_dim=d, Tq=T, Tk=T, ldq=3 * C,
+                                        ldk=3 * C, ldv=3 * C, ldo=C), 1, "attention", 4.0 * B * T * T * C)
         self.flops += 4.0 * B * T * T * C
         h1 = self.scratch("th1", M, C)
         self.emit_plan(ops.linear_plan(att, self.sd[t + ".attn1.to_out.0.weight"].to(bf16).contiguous(), h1,
                                        bias=self.wf(t + ".attn1.to_out.0.bias"), res1=h0))
         # --- cross attention (K/V of the context are prepared once per prompt: ctx_prog)
-        Lc, Lp = self.ctx_len, self.ctx_pad
+        Lc = self.ctx_len
         k2 = self.buf(B * Lc, C)
-        v2 = self.scratch("tv2", B * Lc, C)
-        v2t = self.buf(B, C, Lp)
+        v2 = self.buf(B * Lc, C)
         pk = ops.linear_plan(self.ehs_bf, self.sd[t + ".attn2.to_k.weight"].to(bf16).contiguous(), k2)
         pv = ops.linear_plan(self.ehs_bf, self.sd[t + ".attn2.to_v.weight"].to(bf16).contiguous(), v2)
         self.keep += [pk, pv]
-        self.ctx_prog += [pk.run, pv.run,
-                          lambda: ops.transpose_tokens(v2, v2t, ld=C, col0=0, Cc=C, B=B, T=Lc, ldt=Lp)]
+        self.ctx_prog += [pk.run, pv.run]
         self.layernorm(h1, t + ".norm2", nrm)
         q2 = self.scratch("tq2", M, C)
         self.emit_plan(ops.linear_plan(nrm, self.sd[t + ".attn2.to_q.weight"].to(bf16).contiguous(), q2))
-        self.emit(lambda: ops.attention(q2, k2, v2t, att, B=B, heads=heads, head_dim=d, Tq=T, Tk=Lc, ldq=C, ldk=C,
-                                        ldvt=Lp, ldo=C), 1, "attention", 4.0 * B * T * Lc * C)
+        self.emit(lambda: ops.attention(q2, k2, v2, att, B=B, heads=heads, head_dim=d, Tq=T, Tk=Lc, ldq=C, ldk=C,
+                                        ldv=C, ldo=C), 1, "attention", 4.0 * B * T * Lc * C)
         self.flops += 4.0 * B * T * Lc * C
         h2 = self.scratch("th2", M, C)
         self.emit_plan(ops.linear_plan(att, self.sd[t + ".attn2.to_out.0.weight"].to(bf16).contiguous(), h2,

@@ -191,9 +191,10 @@ def layernorm(x, gamma, beta, out, eps=1e-5):
 
 
 # --------------------------------------------------------------------------------------------- attention
-def attention(q, k, vt, out, *, B, heads, head_dim, Tq, Tk, ldq=None, ldk=None, ldvt=None, ldo=None):
+def attention(q, k, v, out, *, B, heads, head_dim, Tq, Tk, ldq=None, ldk=None, ldv=None, ldo=None):
+    """q [B,Tq,ldq], k / v [B,Tk,ld] (views into a fused q|k|v buffer are fine: pass the leading dimension)."""
     L = lib()
-    check(L.mfb_attention(_ptr(q), ldq or q.shape[-1], _ptr(k), ldk or k.shape[-1], _ptr(vt), ldvt or vt.shape[-1],
+    check(L.mfb_attention(_ptr(q), ldq or q.shape[-1], _ptr(k), ldk or k.shape[-1], _ptr(v), ldv or v.shape[-1],
                           _ptr(out), ldo or out.shape[-1], B, heads, head_dim, Tq, Tk, _stream()))
 
 

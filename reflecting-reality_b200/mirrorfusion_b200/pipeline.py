@@ -180,9 +180,6 @@ class B200AttnProcessor:
         st.x = z(B * T, C)
         st.att = z(B * T, C)
         st.out = z(B * T, C)
-        Tp = (Tk + 7) // 8 * 8
-        st.vt = z(B, C, Tp)
-        st.Tp = Tp
         wq, wk, wv = (attn.to_q.weight.detach(), attn.to_k.weight.detach(), attn.to_v.weight.detach())
         wo = attn.to_out[0].weight.detach().to(device=dev, dtype=bf).contiguous()
         bo = attn.to_out[0].bias
@@ -226,15 +223,13 @@ class B200AttnProcessor:
         st.x.copy_(hidden_states.reshape(B * T, C))
         if is_self:
             st.plans[0].run()
-            ops.transpose_tokens(st.qkv, st.vt, ld=3 * C, col0=2 * C, Cc=C, B=B, T=T, ldt=st.Tp)
-            ops.attention(st.qkv, st.qkv.view(-1)[C:], st.vt, st.att, B=B, heads=heads, head_dim=d, Tq=T, Tk=T, ldq=3 * C,
-                          ldk=3 * C, ldvt=st.Tp, ldo=C)
+            ops.attention(st.qkv, st.qkv.view(-1)[C:], st.qkv.view(-1)[2 * C:], st.att, B=B, heads=heads, head_dim=d, Tq=T, Tk=T,
+                          ldq=3 * C, ldk=3 * C, ldv=3 * C, ldo=C)
         else:
             st.ctx.copy_(encoder_hidden_states.reshape(B * Tk, Cctx))
             for p in st.plans:
                 p.run()
-            ops.transpose_tokens(st.v, st.vt, ld=C, col0=0, Cc=C, B=B, T=Tk, ldt=st.Tp)
-            ops.attention(st.q, st.k, st.vt, st.att, B=B, heads=heads, head_dim=d, Tq=T, Tk=Tk, ldq=C, ldk=C, ldvt=st.Tp, ldo=C)
+            ops.attention(st.q, st.k, st.v, st.att, B=B, heads=heads, head_dim=d, Tq=T, Tk=Tk, ldq=C, ldk=C, ldv=C, ldo=C)
         st.out_plan.run()
         out = st.out.view(B, T, C).to(hidden_states.dtype)
         if input_ndim == 4:

@@ -30,13 +30,11 @@ def main():
         if args.only and args.only not in name:
             continue
         C = H * D
-        Tkp = (Tk + 7) // 8 * 8
         q = torch.randn(B, Tq, C, device="cuda").to(bf16)
         k = torch.randn(B, Tk, C, device="cuda").to(bf16)
-        vt = torch.zeros(B, C, Tkp, device="cuda", dtype=bf16)
-        vt[:, :, :Tk] = torch.randn(B, C, Tk, device="cuda").to(bf16)
+        v = torch.randn(B, Tk, C, device="cuda").to(bf16)
         out = torch.empty(B, Tq, C, device="cuda", dtype=bf16)
-        run = lambda: ops.attention(q, k, vt, out, B=B, heads=H, head_dim=D, Tq=Tq, Tk=Tk)
+        run = lambda: ops.attention(q, k, v, out, B=B, heads=H, head_dim=D, Tq=Tq, Tk=Tk)
         for _ in range(3):
             run()
         torch.cuda.synchronize()
