@@ -408,25 +408,31 @@ extern "C" int mfb_attention(const void* q, int ldq, const void* k, int ldk, con
     MFB_REQUIRE(q && k && v && out, "null pointer");
     MFB_REQUIRE(ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 && ldo % 8 == 0, "leading dimensions must be multiples of 8");
     MFB_REQUIRE(Tq > 0 && Tk > 0, "bad sequence lengths");
+    MFB_REQUIRE(ldq >= heads * head_dim && ldk >= heads * head_dim && ldv >= heads * head_dim && ldo >= heads * head_dim,
+                "leading dimensions must cover heads * head_dim columns");
     AttParams p;
     memset(&p, 0, sizeof(p));
+    // the maps expose exactly the heads*d columns of each tensor (row stride = ld): the 64-column boxes of the last
+    // heads reach past them, and those columns must come back as TMA zero fill, not as whatever follows in memory
+    // (for a v view into a fused q|k|v buffer that would be the next row — and past the allocation on the last row)
+    const uint64_t width = uint64_t(heads) * head_dim;
     const uint32_t kv_box = uint32_t(head_dim <= 40 ? AttCfg<40>::BKV : head_dim <= 80 ? AttCfg<80>::BKV : 128);   // AttCfg<D>::BKV keys per tile
     {
-        const uint64_t dims[3] = {uint64_t(ldq), uint64_t(Tq), uint64_t(B)};
+        const uint64_t dims[3] = {width, uint64_t(Tq), uint64_t(B)};
         const uint64_t str[2] = {uint64_t(ldq) * 2, uint64_t(Tq) * ldq * 2};
         const uint32_t box[3] = {64, BQ, 1};
         int rc = encode_tmap_bf16(&p.tmQ, q, 3, dims, str, box, 128);
         if (rc) return rc;
     }
     {
-        const uint64_t dims[3] = {uint64_t(ldk), uint64_t(Tk), uint64_t(B)};
+        const uint64_t dims[3] = {width, uint64_t(Tk), uint64_t(B)};
         const uint64_t str[2] = {uint64_t(ldk) * 2, uint64_t(Tk) * ldk * 2};
         const uint32_t box[3] = {64, kv_box, 1};
         int rc = encode_tmap_bf16(&p.tmK, k, 3, dims, str, box, 128);
         if (rc) return rc;
     }
     {
-        const uint64_t dims[3] = {uint64_t(ldv), uint64_t(Tk), uint64_t(B)};
+        const uint64_t dims[3] = {width, uint64_t(Tk), uint64_t(B)};
         const uint64_t str[2] = {uint64_t(ldv) * 2, uint64_t(Tk) * ldv * 2};
         const uint32_t box[3] = {64, kv_box, 1};
         int rc = encode_tmap_bf16(&p.tmV, v, 3, dims, str, box, 128);
