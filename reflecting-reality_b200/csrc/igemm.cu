@@ -70,6 +70,8 @@ struct IgemmParams {
                            // consumer, fused here): [Bn][stats_tiles][out_ld][2]; null = off
     int stats_tiles, stats_tile_base;
     int o_step, o_py, o_px, o_Hf, o_Wf;   // rows map to output pixel (o_step*oh + o_py, o_step*ow + o_px) of [Bn, o_Hf, o_Wf]
+    int stages;            // operand ring depth actually used (<= IgemmCfg::STAGES)
+    int nstg;              // staging tiles: 1, or 2 = double-buffered epilogue (short-K launches, see igemm_kernel)
 };
 
 template <int BN>
@@ -83,11 +85,15 @@ struct IgemmCfg {
     static constexpr int STG_BYTES = BM * BN * 2;
     // persistent CTA, one per SM: as many operand stages as fit under the 227 KB limit (operand fetch is
     // L2-latency/bandwidth bound, so depth matters more than anything else here)
-    static constexpr int STAGES = (224 * 1024 - STG_BYTES) / STAGE_BYTES > 8 ? 8 : (224 * 1024 - STG_BYTES) / STAGE_BYTES;
+    static constexpr int MAX_STAGES = 8;
+    static constexpr int STAGES = (224 * 1024 - STG_BYTES) / STAGE_BYTES > MAX_STAGES ? MAX_STAGES : (224 * 1024 - STG_BYTES) / STAGE_BYTES;
+    // with a second staging tile (double-buffered epilogue) the ring gives up STG_BYTES
+    static constexpr int STAGES_2STG = (224 * 1024 - 2 * STG_BYTES) / STAGE_BYTES > MAX_STAGES ? MAX_STAGES : (224 * 1024 - 2 * STG_BYTES) / STAGE_BYTES;
     static constexpr int ACC_COLS = BN <= 64 ? 64 : BN <= 128 ? 128 : 256;  // TMEM columns per accumulator slot
     static constexpr int TMEM_COLS = 2 * ACC_COLS;                           // double-buffered accumulator
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STG_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ +
+    static constexpr int SMEM_BYTES = 224 * 1024 /*ring + staging tile(s)*/ + 1024 /*align slack*/ + 256 /*barriers*/ +
                                       2 * BN * 4 /*column bias of the current / next tile*/;
+    static_assert(STAGES >= 2 && STAGES_2STG >= 2 && SMEM_BYTES <= 227 * 1024, "shared memory budget");
 };
 
 // byte offset of the 16-byte chunk holding columns [col, col+8) of row r inside the swizzled staging tile
@@ -161,24 +167,30 @@ struct TileIter {
 // Shared-memory operand traffic per SM per K step drops from (128 + BN) to (128 + BN/2) rows — the resource this
 // kernel is bound by.  TMA completions of both CTAs are counted on the LEADER's full barrier; the leader's commits are
 // multicast to both CTAs' empty / accumulator-full barriers; both epilogues arrive on the leader's accumulator-empty one.
+// p.nstg == 2 (opt-in) double-buffers the epilogue's staging tile: the TMA store of tile i drains while tile i+1 is
+// assembled in the other buffer, and the residual tile of tile i+1 is prefetched into that buffer one whole tile ahead, so
+// the per-tile chain "previous store drained -> residual loaded -> TMEM load -> math -> store" loses its two TMA latencies.
+// The ring gives up one staging tile's worth of stages for it.
 template <int BN, int MODE>
 __global__ void __launch_bounds__(IGEMM_THREADS, 1) igemm_kernel(const __grid_constant__ IgemmParams p) {
     using Cfg = IgemmCfg<BN>;
     constexpr bool PAIR = MODE != 0;
     constexpr bool TWOSM = MODE == 2;
     constexpr int STAGE_BYTES = TWOSM ? Cfg::A_BYTES + Cfg::B_BYTES / 2 : Cfg::STAGE_BYTES;
-    constexpr int STAGES = Cfg::STAGES;
+    constexpr int MAXS = Cfg::MAX_STAGES;
+    const int STAGES = p.stages;
+    const int nstg = PAIR ? 1 : p.nstg;
     extern __shared__ uint8_t smem_raw[];
     // 1024-byte alignment is required by the 128B swizzle atoms
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t stg_base = smem_base + STAGES * Cfg::STAGE_BYTES;   // (MODE 2 uses smaller stages inside the same budget)
-    const uint32_t bar_base = stg_base + Cfg::STG_BYTES;
+    const uint32_t bar_base = stg_base + nstg * Cfg::STG_BYTES;
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
-    auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
-    auto tmem_full_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
-    auto tmem_empty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
-    const uint32_t res_full_bar = bar_base + 8u * (2 * STAGES + 4);
-    const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 5);
+    auto empty_bar = [&](int s) { return bar_base + 8u * (MAXS + s); };
+    auto tmem_full_bar = [&](int a) { return bar_base + 8u * (2 * MAXS + a); };
+    auto tmem_empty_bar = [&](int a) { return bar_base + 8u * (2 * MAXS + 2 + a); };
+    const uint32_t res_full_bar = bar_base + 8u * (2 * MAXS + 4);
+    const uint32_t tmem_slot = bar_base + 8u * (2 * MAXS + 5);
     uint8_t* stg_gen = smem_raw + (stg_base - smem_u32(smem_raw));   // generic pointer to the staging tile
     uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
     float* sbias = reinterpret_cast<float*>(smem_raw + (bar_base + 256 - smem_u32(smem_raw)));   // [2][BN]
@@ -342,6 +354,17 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 1) igemm_kernel(const __grid_co
         // which per-element extras this launch needs (uniform for the whole launch): 0 = bias only, 1 = + res1 tile,
         // 2 = anything else (per-row row bias, alpha, res2).  Each flavour gets its own straight-line code.
         const int flavour = (p.alpha || p.res2 || (p.rowbias && p.tn != 1)) ? 2 : (p.res1 ? 1 : 0);
+        // residual tile of (nt, w0, h0, n0) -> staging buffer `buf` (leader only)
+        auto load_res = [&](int buf, int nt_, int w0_, int h0_, int n0_) {
+            mbar_expect_tx(res_full_bar, uint32_t(nbox) * BM * BOXC * 2);
+            for (int bx = 0; bx < nbox; ++bx)
+                tma_load_4d(stg_base + buf * Cfg::STG_BYTES + bx * (BM * BOXC * 2), &p.tmRes, res_full_bar, nt_ * bn_out + bx * BOXC,
+                            w0_, h0_, n0_);
+        };
+        if constexpr (!PAIR) {
+            if (nstg == 2 && p.res1 != nullptr && leader && wi0 < num_tiles)
+                load_res(0, ti.nt, ti.iw * p.tw, ti.ih * p.th, ti.ig * p.tn);      // first tile; later ones are prefetched
+        }
         for (int tile = wi0; tile < num_tiles; tile += wstep, ++li) {
             int nt, mt, w0, h0, n0;
             if constexpr (PAIR) {
@@ -361,6 +384,9 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 1) igemm_kernel(const __grid_co
             // broadcast LDS instead of dependent global loads.  A tile spanning several images (8x8 level) keeps
             // the per-row global read of the row bias.
             const int as = li & 1;
+            const int sbuf = nstg == 2 ? as : 0;                       // staging buffer of this tile
+            const uint32_t stg_b = stg_base + sbuf * Cfg::STG_BYTES;
+            uint8_t* const stg_g = stg_gen + sbuf * Cfg::STG_BYTES;
             float* sb = sbias + as * BN;
             const bool rb_folded = p.rowbias != nullptr && p.tn == 1;
             const float* rb = (p.rowbias && !rb_folded) ? p.rowbias + static_cast<long long>(valid ? on : 0) * p.rowbias_ld : nullptr;
@@ -381,11 +407,9 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 1) igemm_kernel(const __grid_co
             // (Reading the residual straight from global into registers was measured slower: row-strided 16-byte loads.)
             const bool early_stage = p.res1 != nullptr;
             if (early_stage) {
-                if (leader) {
+                if (leader && nstg == 1) {
                     tma_store_wait_read();
-                    mbar_expect_tx(res_full_bar, uint32_t(nbox) * BM * BOXC * 2);
-                    for (int bx = 0; bx < nbox; ++bx)
-                        tma_load_4d(stg_base + bx * (BM * BOXC * 2), &p.tmRes, res_full_bar, nt * bn_out + bx * BOXC, w0, h0, n0);
+                    load_res(0, nt, w0, h0, n0);
                 }
                 __syncwarp();
                 named_bar_sync(1, IGEMM_EPI_WARPS * 32);   // staging tile is being filled with res1; sb is visible
@@ -400,7 +424,10 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 1) igemm_kernel(const __grid_co
                     else mbar_arrive(tmem_empty_bar(as));
                 }
                 if (!early_stage) {
-                    if (leader) tma_store_wait_read();     // previous tile's store no longer reads the staging tile
+                    if (leader) {                          // the last store out of THIS staging buffer no longer reads it
+                        if (nstg == 2) tma_store_wait_read_but1();
+                        else tma_store_wait_read();
+                    }
                     __syncwarp();
                     named_bar_sync(1, IGEMM_EPI_WARPS * 32);   // staging tile is free; sb is visible
                 }
@@ -428,7 +455,7 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 1) igemm_kernel(const __grid_co
                             const int col = (c_begin + i) * 16;
 #pragma unroll
                             for (int j = 0; j < 2; ++j) {
-                                uint4* sp = reinterpret_cast<uint4*>(stg_gen + stg_off<BOXC>(r, col + j * 8));
+                                uint4* sp = reinterpret_cast<uint4*>(stg_g + stg_off<BOXC>(r, col + j * 8));
                                 const float4 b0 = *reinterpret_cast<const float4*>(sb + col + j * 8);
                                 const float4 b1 = *reinterpret_cast<const float4*>(sb + col + j * 8 + 4);
                                 float f[8];
@@ -487,7 +514,7 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 1) igemm_kernel(const __grid_co
                                 const float gate = __uint_as_float(g[c][j * 8 + e]) + bg[e];
                                 f[e] = val * gelu_erf_f(gate);
                             }
-                            *reinterpret_cast<uint4*>(stg_gen + stg_off<BOXC>(r, col + j * 8)) = pack_bf16x8(f);
+                            *reinterpret_cast<uint4*>(stg_g + stg_off<BOXC>(r, col + j * 8)) = pack_bf16x8(f);
                         }
                     }
                 }
@@ -501,7 +528,7 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 1) igemm_kernel(const __grid_co
                 const int c = threadIdx.x;
                 const int vw = min(p.tw, p.Wo - w0), vh = min(p.th, p.Ho - h0), vn = min(p.tn, p.Bn - n0);
                 const int tile_in_img = (p.tn == 1 ? mt % (p.tiles_w * p.tiles_h) : 0) + p.stats_tile_base;
-                const uint8_t* colp = stg_gen + (c & 7) * 2;
+                const uint8_t* colp = stg_g + (c & 7) * 2;
                 for (int in_ = 0; in_ < vn; ++in_) {
                     float sm = 0.f, sq = 0.f;
                     for (int ih = 0; ih < vh; ++ih) {
@@ -522,8 +549,16 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 1) igemm_kernel(const __grid_co
             if (p.stats != nullptr) named_bar_sync(1, IGEMM_EPI_WARPS * 32);
             if (leader) {
                 for (int bx = 0; bx < nbox; ++bx)
-                    tma_store_4d(&p.tmOut, stg_base + bx * (BM * BOXC * 2), nt * bn_out + bx * BOXC, w0, h0, n0);
+                    tma_store_4d(&p.tmOut, stg_b + bx * (BM * BOXC * 2), nt * bn_out + bx * BOXC, w0, h0, n0);
                 tma_store_commit();
+                if constexpr (!PAIR) {
+                    if (nstg == 2 && p.res1 != nullptr && tile + wstep < num_tiles) {
+                        // prefetch the NEXT tile's residual into the other buffer (ti already points at that tile) as
+                        // soon as the store issued one tile ago has finished reading it
+                        tma_store_wait_read_but1();
+                        load_res(sbuf ^ 1, ti.nt, ti.iw * p.tw, ti.ih * p.th, ti.ig * p.tn);
+                    }
+                }
             }
             __syncwarp();
         }
@@ -731,6 +766,22 @@ static int build_params(const mfb_conv_desc* d, int up_py, int up_px, const void
     p.out = static_cast<__nv_bfloat16*>(d->out);
     p.geglu = d->geglu;
     p.out_ld = d->geglu ? d->Cout / 2 : d->Cout;
+    {
+        // double-buffered epilogue: opt-in (env MFB_IGEMM_NSTG = 2, or MFB_IGEMM_NSTG_KMAX = largest K that gets it).
+        // Measured neutral-to-slower on B200 (profiles/r01o_igemm_double_staging.md): these launches are paced by operand
+        // fetch and, for N = K = 320, by HBM bytes — not by the epilogue chain — and the ring stage it costs hurts.
+        const int sms = device_sm_count() > 0 ? device_sm_count() : 148;
+        const char* e1 = getenv("MFB_IGEMM_NSTG");
+        const char* e2 = getenv("MFB_IGEMM_NSTG_KMAX");
+        const int kmax = e2 ? atoi(e2) : 0;
+        const long total = long(p.tiles_m) * p.tiles_nn;
+        int nstg = (pl->mode == 0 && ktot <= kmax && total > sms) ? 2 : 1;
+        if (e1 && pl->mode == 0) nstg = atoi(e1) == 2 ? 2 : 1;
+        const int stg_bytes = BM * bn * 2, stage_bytes = BM * BK * 2 + bn * BK * 2;
+        int stages = (224 * 1024 - nstg * stg_bytes) / stage_bytes;
+        p.nstg = nstg;
+        p.stages = stages > 8 ? 8 : stages;
+    }
     {
         const int sms = device_sm_count() > 0 ? device_sm_count() : 148;
         if (pl->mode != 0) {

@@ -45,6 +45,9 @@ def main():
         ("linear 64x64 320->960 (qkv)", 64, 320, 960, 1), ("linear 64x64 320->2560 (geglu)", 64, 320, 2560, 1),
         ("linear 64x64 1280->320 (ff out)", 64, 1280, 320, 1), ("linear 32x32 640->5120 (geglu)", 32, 640, 5120, 1),
         ("linear 16x16 1280->10240 (geglu)", 16, 1280, 10240, 1), ("zero-conv 64x64 320->320", 64, 320, 320, 1),
+        ("linear 64x64 320->320 +res (attn out)", 64, 320, 320, 1), ("linear 32x32 640->640 +res (attn out)", 32, 640, 640, 1),
+        ("linear 16x16 1280->1280 +res (attn out)", 16, 1280, 1280, 1), ("linear 64x64 1280->320 +res (ff out)", 64, 1280, 320, 1),
+        ("linear 32x32 2560->640 +res (ff out)", 32, 2560, 640, 1), ("linear 32x32 640->1920 (qkv)", 32, 640, 1920, 1),
     ]
     rows = []
     for name, H, cin, cout, ks in shapes:
@@ -55,7 +58,8 @@ def main():
         geglu = "geglu" in name
         out = torch.empty(B, H, H, cout // 2 if geglu else cout, device="cuda", dtype=bf16)
         bias = torch.zeros(cout, device="cuda")
-        plan = ops.ConvPlan(x, w, out, B=B, H=H, W=H, Cin=cin, Cout=cout, ksize=ks, bias=bias, geglu=geglu,
+        res1 = torch.randn(B, H, H, cout, device="cuda").to(bf16) if "+res" in name else None
+        plan = ops.ConvPlan(x, w, out, B=B, H=H, W=H, Cin=cin, Cout=cout, ksize=ks, bias=bias, geglu=geglu, res1=res1,
                             block_n=0 if geglu else args.block_n)
         ms = time_plan(plan, args.iters)
         tf = plan.flops / ms / 1e9
