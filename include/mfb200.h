@@ -73,6 +73,8 @@ typedef struct mfb_conv_desc {
                              pixel pre-summed); the plan issues 4 launches and never materialises the upsampled tensor */
     int igemm_mode;       /* 0 = auto (env MFB_IGEMM_MODE or independent CTAs); 1 independent CTAs, 2 CTA pair + weight multicast,
                              3 CTA pair + cta_group::2 UMMA (256-row tile) */
+    int dtype;            /* 0 = bf16 tensors, tcgen05 path (the product).  1 = fp32 PARITY MODE: x / extras / w / res / out
+                             are fp32, CUDA-core FFMA accumulation (csrc/fp32mode.cu) — same descriptor semantics */
 } mfb_conv_desc;
 
 typedef struct mfb_plan mfb_plan;
@@ -167,6 +169,25 @@ int mfb_linear_small(const float* x, int M, int K, const void* w, const float* b
  */
 int mfb_cfg_sched_step(const float* eps_uncond, const float* eps_cond, float* x, float* last, float* m0, float* m1,
                        const float* coef, int Bimg, long long n, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * fp32 parity mode (BASELINE.json configs[0]; north_star: per-step noise prediction within rel-L2 1e-4 in fp32 mode).
+ * Same argument meaning as the bf16 entry points above with every bf16 tensor replaced by fp32 (conv / linear: set
+ * mfb_conv_desc.dtype = 1).  Plain CUDA-core kernels: a correctness instrument for the shared host program, not a
+ * performance path.
+ */
+int mfb_groupnorm_f32(const float* x1, int C1, const float* x2, int C2, int B, int HW, int groups, float eps,
+                      const float* gamma, const float* beta, int silu, float* out, void* stream);
+int mfb_layernorm_f32(const float* x, int rows, int C, float eps, const float* gamma, const float* beta, float* out,
+                      void* stream);
+int mfb_attention_f32(const float* q, int ldq, const float* k, int ldk, const float* v, int ldv, float* out, int ldo,
+                      int B, int heads, int head_dim, int Tq, int Tk, void* stream);
+int mfb_conv_in_f32(const float* sample, int Ca, const float* cond, int Cb, int B, int H, int W, const float* w,
+                    const float* bias, int Cout, float* out, const float* tap, float* out_post, void* stream);
+int mfb_conv_out_f32(const float* x, int Cin, int B, int H, int W, const float* w, const float* bias, int Cout, float* out,
+                     void* stream);
+int mfb_linear_small_f32(const float* x, int M, int K, const float* w, const float* b, int N, int act_in, int act_out,
+                         float* y, void* stream);
 
 #ifdef __cplusplus
 }

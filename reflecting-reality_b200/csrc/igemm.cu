@@ -27,6 +27,7 @@
 
 #include "common.h"
 #include <type_traits>
+#include "fp32mode.h"
 #include "ptx.cuh"
 
 namespace mfb {
@@ -587,6 +588,8 @@ struct Plan {
     int stats_C;
     int stats_B;
     double flops;
+    bool f32;           // fp32 parity mode (mfb_conv_desc.dtype == 1): CUDA-core launches described by q[]
+    Conv32Params q[4];
 };
 
 static void pick_tile(int W, int H, int B, int* tw, int* th, int* tn) {
@@ -810,6 +813,25 @@ extern "C" int mfb_conv_plan_create(const mfb_conv_desc* d, mfb_plan** out) {
 
     Plan* pl = new Plan();
     int rc;
+    pl->f32 = d->dtype == 1;
+    if (pl->f32) {
+        pl->mode = 0; pl->bn = 0; pl->stats_tiles = 0; pl->stats_C = d->Cout; pl->stats_B = d->B;
+        int kext = 0;
+        for (int e = 0; e < d->n_extra; ++e) kext += d->extra_C[e];
+        pl->nlaunch = d->up2x ? 4 : 1;
+        for (int ph = 0; ph < pl->nlaunch; ++ph) {
+            const size_t kt = size_t(d->up2x ? 4 : d->ksize * d->ksize) * d->Cin + kext;
+            const char* wp = static_cast<const char*>(d->w) + size_t(ph) * d->Cout * kt * 4;
+            rc = conv32_build(d, d->up2x ? ph >> 1 : -1, d->up2x ? ph & 1 : -1, wp, pl->q[ph]);
+            if (rc) { delete pl; return rc; }
+        }
+        pl->ktot = pl->q[0].ktot;
+        const double Ho = d->up2x ? 2.0 * d->H : double((d->H + d->stride - 1) / d->stride);
+        const double Wo = d->up2x ? 2.0 * d->W : double((d->W + d->stride - 1) / d->stride);
+        pl->flops = 2.0 * d->B * Ho * Wo * d->Cout * (double(d->ksize) * d->ksize * d->Cin + kext);
+        *out = reinterpret_cast<mfb_plan*>(pl);
+        return MFB_OK;
+    }
     if (d->up2x) {
         // w = [4 phases][Cout][4*Cin + extras], phase index = py*2 + px
         pl->nlaunch = 4;
@@ -847,6 +869,13 @@ extern "C" int mfb_plan_run(mfb_plan* plan, void* stream) {
     MFB_REQUIRE(plan, "null plan");
     Plan* pl = reinterpret_cast<Plan*>(plan);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (pl->f32) {
+        for (int i = 0; i < pl->nlaunch; ++i) {
+            const int rc = conv32_launch(pl->q[i], st);
+            if (rc) return rc;
+        }
+        return MFB_OK;
+    }
     for (int i = 0; i < pl->nlaunch; ++i) {
         const int rc = pl->mode == 2 ? run_one<2>(*pl, pl->p[i], st) : pl->mode == 1 ? run_one<1>(*pl, pl->p[i], st)
                                                                                     : run_one<0>(*pl, pl->p[i], st);

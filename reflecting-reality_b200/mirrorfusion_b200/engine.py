@@ -25,13 +25,13 @@ import torch
 from . import ops
 from .config import NetConfig, tap_channels, up_block_channels
 
-bf16 = torch.bfloat16
 f32 = torch.float32
 
 
 class _Net:
     def __init__(self, cfg: NetConfig, sd: Dict[str, torch.Tensor], B: int, H: int, W: int, device, name: str):
         self.cfg, self.B, self.H, self.W, self.dev, self.name = cfg, B, H, W, device, name
+        self.act = ops.act_dtype()     # storage dtype: self.act (product) or fp32 (parity mode, `with ops.precision('fp32')`)
         self.sd = {k: v.detach().to(device=device, dtype=f32) for k, v in sd.items()}
         self.prog: List[Callable[[], None]] = []
         self.tags: List[Tuple[str, float]] = []       # (kernel family, algorithmic FLOPs) per program entry
@@ -53,15 +53,15 @@ class _Net:
         ops.lib()
 
     # ---- memory
-    def buf(self, *shape, dtype=bf16) -> torch.Tensor:
-        t = torch.zeros(*shape, device=self.dev, dtype=dtype)
+    def buf(self, *shape, dtype=None) -> torch.Tensor:
+        t = torch.zeros(*shape, device=self.dev, dtype=dtype or self.act)
         self.keep.append(t)
         return t
 
     def scratch(self, role: str, *shape) -> torch.Tensor:
         key = (role,) + tuple(shape)
         if key not in self._scratch:
-            self._scratch[key] = torch.zeros(*shape, device=self.dev, dtype=bf16)
+            self._scratch[key] = torch.zeros(*shape, device=self.dev, dtype=self.act)
         return self._scratch[key]
 
     def wf(self, name: str) -> torch.Tensor:
@@ -76,7 +76,7 @@ class _Net:
     def set_tap_scale(self, s: float):
         """Re-scale the fused zero-conv K-segments in place (descriptors keep pointing at the same buffers)."""
         for wp, koff, c, wz, bias_buf, base_bias, bz in self.fused_taps:
-            wp[:, koff:koff + c].copy_((wz * s).to(bf16))
+            wp[:, koff:koff + c].copy_((wz * s).to(self.act))
             bias_buf.copy_(base_bias + s * bz)
 
     # ---- op emitters
@@ -132,9 +132,9 @@ class _Net:
         sin = self.buf(self.B, c0, dtype=f32)
         e1 = self.buf(self.B, temb, dtype=f32)
         emb = self.buf(self.B, temb, dtype=f32)
-        w1, b1 = self.wf("time_embedding.linear_1.weight").to(bf16), self.wf("time_embedding.linear_1.bias")
-        w2, b2 = self.wf("time_embedding.linear_2.weight").to(bf16), self.wf("time_embedding.linear_2.bias")
-        wcat = torch.cat([self.sd[p + ".time_emb_proj.weight"] for p in resnet_prefixes], 0).to(bf16).contiguous()
+        w1, b1 = self.wf("time_embedding.linear_1.weight").to(self.act), self.wf("time_embedding.linear_1.bias")
+        w2, b2 = self.wf("time_embedding.linear_2.weight").to(self.act), self.wf("time_embedding.linear_2.bias")
+        wcat = torch.cat([self.sd[p + ".time_emb_proj.weight"] for p in resnet_prefixes], 0).to(self.act).contiguous()
         bcat = torch.cat([self.sd[p + ".time_emb_proj.bias"] for p in resnet_prefixes], 0).contiguous()
         self.rowbias = self.buf(self.B, wcat.shape[0], dtype=f32)
         self.rowbias_off = {}
@@ -373,7 +373,7 @@ class UNetEngine(_Net):
         self.ctx_len = ctx_len
         self.sample_in = torch.zeros(B, cfg.in_channels, H, W, device=device, dtype=f32)
         self.ehs_in = torch.zeros(B, ctx_len, cfg.cross_attention_dim, device=device, dtype=f32)
-        self.ehs_bf = torch.zeros(B * ctx_len, cfg.cross_attention_dim, device=device, dtype=bf16)
+        self.ehs_bf = torch.zeros(B * ctx_len, cfg.cross_attention_dim, device=device, dtype=self.act)
         self.out = torch.zeros(B, cfg.out_channels, H, W, device=device, dtype=f32)
         self.ctx_prog: List[Callable[[], None]] = []
         # tap input buffers (zero == "no taps"); shapes in pop order
@@ -473,7 +473,7 @@ class UNetEngine(_Net):
         self.layernorm(h0, t + ".norm1", nrm)
         qkv = self.scratch("tqkv", M, 3 * C)
         wqkv = torch.cat([self.sd[t + ".attn1.to_q.weight"], self.sd[t + ".attn1.to_k.weight"],
-                          self.sd[t + ".attn1.to_v.weight"]], 0).to(bf16).contiguous()
+                          self.sd[t + ".attn1.to_v.weight"]], 0).to(self.act).contiguous()
         self.emit_plan(ops.linear_plan(nrm, wqkv, qkv))
         att = self.scratch("tatt", M, C)
         kview, vview = qkv.view(-1)[C:], qkv.view(-1)[2 * C:]      # q | k | v column blocks of the fused projection
@@ -481,24 +481,24 @@ class UNetEngine(_Net):
                                         ldk=3 * C, ldv=3 * C, ldo=C), 1, "attention", 4.0 * B * T * T * C)
         self.flops += 4.0 * B * T * T * C
         h1 = self.scratch("th1", M, C)
-        self.emit_plan(ops.linear_plan(att, self.sd[t + ".attn1.to_out.0.weight"].to(bf16).contiguous(), h1,
+        self.emit_plan(ops.linear_plan(att, self.sd[t + ".attn1.to_out.0.weight"].to(self.act).contiguous(), h1,
                                        bias=self.wf(t + ".attn1.to_out.0.bias"), res1=h0))
         # --- cross attention (K/V of the context are prepared once per prompt: ctx_prog)
         Lc = self.ctx_len
         k2 = self.buf(B * Lc, C)
         v2 = self.buf(B * Lc, C)
-        pk = ops.linear_plan(self.ehs_bf, self.sd[t + ".attn2.to_k.weight"].to(bf16).contiguous(), k2)
-        pv = ops.linear_plan(self.ehs_bf, self.sd[t + ".attn2.to_v.weight"].to(bf16).contiguous(), v2)
+        pk = ops.linear_plan(self.ehs_bf, self.sd[t + ".attn2.to_k.weight"].to(self.act).contiguous(), k2)
+        pv = ops.linear_plan(self.ehs_bf, self.sd[t + ".attn2.to_v.weight"].to(self.act).contiguous(), v2)
         self.keep += [pk, pv]
         self.ctx_prog += [pk.run, pv.run]
         self.layernorm(h1, t + ".norm2", nrm)
         q2 = self.scratch("tq2", M, C)
-        self.emit_plan(ops.linear_plan(nrm, self.sd[t + ".attn2.to_q.weight"].to(bf16).contiguous(), q2))
+        self.emit_plan(ops.linear_plan(nrm, self.sd[t + ".attn2.to_q.weight"].to(self.act).contiguous(), q2))
         self.emit(lambda: ops.attention(q2, k2, v2, att, B=B, heads=heads, head_dim=d, Tq=T, Tk=Lc, ldq=C, ldk=C,
                                         ldv=C, ldo=C), 1, "attention", 4.0 * B * T * Lc * C)
         self.flops += 4.0 * B * T * Lc * C
         h2 = self.scratch("th2", M, C)
-        self.emit_plan(ops.linear_plan(att, self.sd[t + ".attn2.to_out.0.weight"].to(bf16).contiguous(), h2,
+        self.emit_plan(ops.linear_plan(att, self.sd[t + ".attn2.to_out.0.weight"].to(self.act).contiguous(), h2,
                                        bias=self.wf(t + ".attn2.to_out.0.bias"), res1=h1))
         # --- GEGLU feed-forward
         self.layernorm(h2, t + ".norm3", nrm)
@@ -506,7 +506,7 @@ class UNetEngine(_Net):
         gg = self.scratch("tgg", M, 4 * C)
         self.emit_plan(ops.linear_plan(nrm, wg, gg, bias=bg, geglu=True))
         h3 = self.scratch("th3", M, C)
-        self.emit_plan(ops.linear_plan(gg, self.sd[t + ".ff.net.2.weight"].to(bf16).contiguous(), h3,
+        self.emit_plan(ops.linear_plan(gg, self.sd[t + ".ff.net.2.weight"].to(self.act).contiguous(), h3,
                                        bias=self.wf(t + ".ff.net.2.bias"), res1=h2))
         # --- proj_out + transformer residual (+ BrushNet tap, added after the attention: unet_2d_blocks.py:1374-1389)
         out = self.buf(B, T, C)

@@ -2,6 +2,7 @@
 all math runs in libmfb200.so.  Every function requires CUDA tensors on an sm_100 device."""
 from __future__ import annotations
 
+import contextlib
 import ctypes as C
 from typing import Optional, Sequence
 
@@ -11,6 +12,35 @@ from . import _lib
 from ._lib import ConvDesc, check
 
 bf16 = torch.bfloat16
+f32 = torch.float32
+
+# Storage dtype of activations and packed weights.  bf16 = the product path (tcgen05 kernels).  float32 = the fp32
+# PARITY MODE (BASELINE config 1, rel-L2 1e-4 bar): the same host program on the CUDA-core kernels of csrc/fp32mode.cu.
+# Engines read it while they are BUILT (buffers, packed weights); at run time every op dispatches on its tensors' dtype.
+_ACT = [bf16]
+
+
+def act_dtype():
+    return _ACT[0]
+
+
+@contextlib.contextmanager
+def precision(mode: str):
+    """`with ops.precision("fp32"): eng = StepEngine(...)` builds an engine in fp32 parity mode ("bf16" = default)."""
+    if mode not in ("bf16", "fp32"):
+        raise ValueError(f"precision must be 'bf16' or 'fp32', got {mode!r}")
+    old = _ACT[0]
+    _ACT[0] = f32 if mode == "fp32" else bf16
+    try:
+        yield
+    finally:
+        _ACT[0] = old
+
+
+def _is32(t: torch.Tensor) -> bool:
+    if t.dtype not in (bf16, f32):
+        raise ValueError(f"activation tensors must be bfloat16 (product path) or float32 (parity mode), got {t.dtype}")
+    return t.dtype == f32
 
 
 def _ptr(t: Optional[torch.Tensor]):
@@ -41,7 +71,7 @@ def pack_conv_weight(w: torch.Tensor, extras: Sequence[torch.Tensor] = ()) -> to
     parts = [w.permute(0, 2, 3, 1).reshape(w.shape[0], -1)]
     for e in extras:
         parts.append(e.reshape(e.shape[0], -1))
-    return torch.cat(parts, 1).to(bf16).contiguous()
+    return torch.cat(parts, 1).to(act_dtype()).contiguous()
 
 
 def pack_upconv_weight(w: torch.Tensor, extras: Sequence[torch.Tensor] = ()) -> torch.Tensor:
@@ -64,7 +94,7 @@ def pack_upconv_weight(w: torch.Tensor, extras: Sequence[torch.Tensor] = ()) -> 
                     taps.append(acc)                      # [Cout, Cin]
             parts = [torch.stack(taps, 1).reshape(w.shape[0], -1)] + [e.reshape(e.shape[0], -1).float() for e in extras]
             out.append(torch.cat(parts, 1))
-    return torch.stack(out, 0).to(bf16).contiguous()
+    return torch.stack(out, 0).to(act_dtype()).contiguous()
 
 
 def pack_geglu(w: torch.Tensor, b: torch.Tensor):
@@ -74,7 +104,7 @@ def pack_geglu(w: torch.Tensor, b: torch.Tensor):
     wv, wg = w[:half].reshape(half // 64, 64, -1), w[half:].reshape(half // 64, 64, -1)
     wp = torch.stack([wv, wg], 1).reshape(2 * half, -1)
     bp = torch.stack([b[:half].reshape(-1, 64), b[half:].reshape(-1, 64)], 1).reshape(-1)
-    return wp.to(bf16).contiguous(), bp.float().contiguous()
+    return wp.to(act_dtype()).contiguous(), bp.float().contiguous()
 
 
 # --------------------------------------------------------------------------------------------- implicit GEMM
@@ -87,13 +117,15 @@ class ConvPlan:
                  alpha: Optional[torch.Tensor] = None, res1: Optional[torch.Tensor] = None,
                  res2: Optional[torch.Tensor] = None, geglu: bool = False, block_n: int = 0, igemm_mode: int = 0, up2x: bool = False):
         L = lib()
-        _req(x, bf16, "x"); _req(w, bf16, "w"); _req(out, bf16, "out")
+        dt = f32 if _is32(x) else bf16      # fp32 tensors select the parity-mode plan (mfb_conv_desc.dtype = 1)
+        _req(x, dt, "x"); _req(w, dt, "w"); _req(out, dt, "out")
         d = ConvDesc()
+        d.dtype = 1 if dt == f32 else 0
         d.B, d.H, d.W, d.Cin, d.Cout, d.ksize, d.stride = B, H, W, Cin, Cout, ksize, stride
         d.x, d.w, d.out = x.data_ptr(), w.data_ptr(), out.data_ptr()
         d.n_extra = len(extras)
         for i, e in enumerate(extras):
-            _req(e, bf16, f"extra{i}")
+            _req(e, dt, f"extra{i}")
             d.extra_x[i] = e.data_ptr()
             d.extra_C[i] = e.shape[-1]
         for name, t in (("bias", bias), ("rowbias", rowbias), ("alpha", alpha)):
@@ -107,7 +139,7 @@ class ConvPlan:
         d.rowbias_ld = rowbias_ld
         for name, t in (("res1", res1), ("res2", res2)):
             if t is not None:
-                _req(t, bf16, name)
+                _req(t, dt, name)
                 setattr(d, name, t.data_ptr())
         d.geglu = int(geglu)
         d.block_n = block_n
@@ -175,6 +207,10 @@ def groupnorm(x1, x2, gamma, beta, out, stats_ws, *, B, HW, groups, eps, silu, p
     L = lib()
     C1 = x1.shape[-1]
     C2 = 0 if x2 is None else x2.shape[-1]
+    if _is32(x1):
+        check(L.mfb_groupnorm_f32(_ptr(x1), C1, _ptr(x2), C2, B, HW, groups, eps, _ptr(gamma), _ptr(beta), int(silu), _ptr(out),
+                                  _stream()))
+        return
     if part1 is not None and (x2 is None or part2 is not None):
         check(L.mfb_groupnorm_prestat(_ptr(x1), C1, _ptr(part1[0]), part1[1], _ptr(x2), C2,
                                       _ptr(part2[0]) if part2 else None, part2[1] if part2 else 0, B, HW, groups, eps,
@@ -187,15 +223,17 @@ def groupnorm(x1, x2, gamma, beta, out, stats_ws, *, B, HW, groups, eps, silu, p
 def layernorm(x, gamma, beta, out, eps=1e-5):
     L = lib()
     rows, Cc = x.numel() // x.shape[-1], x.shape[-1]
-    check(L.mfb_layernorm(_ptr(x), rows, Cc, eps, _ptr(gamma), _ptr(beta), _ptr(out), _stream()))
+    fn = L.mfb_layernorm_f32 if _is32(x) else L.mfb_layernorm
+    check(fn(_ptr(x), rows, Cc, eps, _ptr(gamma), _ptr(beta), _ptr(out), _stream()))
 
 
 # --------------------------------------------------------------------------------------------- attention
 def attention(q, k, v, out, *, B, heads, head_dim, Tq, Tk, ldq=None, ldk=None, ldv=None, ldo=None):
     """q [B,Tq,ldq], k / v [B,Tk,ld] (views into a fused q|k|v buffer are fine: pass the leading dimension)."""
     L = lib()
-    check(L.mfb_attention(_ptr(q), ldq or q.shape[-1], _ptr(k), ldk or k.shape[-1], _ptr(v), ldv or v.shape[-1],
-                          _ptr(out), ldo or out.shape[-1], B, heads, head_dim, Tq, Tk, _stream()))
+    fn = L.mfb_attention_f32 if _is32(q) else L.mfb_attention
+    check(fn(_ptr(q), ldq or q.shape[-1], _ptr(k), ldk or k.shape[-1], _ptr(v), ldv or v.shape[-1],
+             _ptr(out), ldo or out.shape[-1], B, heads, head_dim, Tq, Tk, _stream()))
 
 
 def transpose_tokens(x, out, *, ld, col0, Cc, B, T, ldt):
@@ -206,12 +244,14 @@ def transpose_tokens(x, out, *, ld, col0, Cc, B, T, ldt):
 def conv_in(sample, cond, w, bias, out, tap=None, out_post=None):
     B, Ca, H, W = sample.shape
     Cb = 0 if cond is None else cond.shape[1]
-    check(lib().mfb_conv_in(_ptr(sample), Ca, _ptr(cond), Cb, B, H, W, _ptr(w), _ptr(bias), out.shape[-1], _ptr(out),
-                            _ptr(tap), _ptr(out_post), _stream()))
+    fn = lib().mfb_conv_in_f32 if _is32(out) else lib().mfb_conv_in
+    check(fn(_ptr(sample), Ca, _ptr(cond), Cb, B, H, W, _ptr(w), _ptr(bias), out.shape[-1], _ptr(out), _ptr(tap), _ptr(out_post),
+             _stream()))
 
 
 def conv_out(x, w, bias, out, *, B, H, W):
-    check(lib().mfb_conv_out(_ptr(x), x.shape[-1], B, H, W, _ptr(w), _ptr(bias), out.shape[1], _ptr(out), _stream()))
+    fn = lib().mfb_conv_out_f32 if _is32(x) else lib().mfb_conv_out
+    check(fn(_ptr(x), x.shape[-1], B, H, W, _ptr(w), _ptr(bias), out.shape[1], _ptr(out), _stream()))
 
 
 def upsample2x(x, out, *, B, H, W):
@@ -229,6 +269,10 @@ def nhwc_to_nchw(x, out):
 
 
 def f32_to_bf16(x, out):
+    """fp32 -> activation storage dtype (a plain copy in fp32 parity mode)."""
+    if out.dtype == f32:
+        out.copy_(x.view_as(out))
+        return
     check(lib().mfb_f32_to_bf16(_ptr(x), x.numel(), _ptr(out), _stream()))
 
 
@@ -238,7 +282,8 @@ def timestep_sinusoid(t, out):
 
 def linear_small(x, w, b, y, act_in=False, act_out=False):
     M, K = x.shape
-    check(lib().mfb_linear_small(_ptr(x), M, K, _ptr(w), _ptr(b), w.shape[0], int(act_in), int(act_out), _ptr(y), _stream()))
+    fn = lib().mfb_linear_small_f32 if _is32(w) else lib().mfb_linear_small
+    check(fn(_ptr(x), M, K, _ptr(w), _ptr(b), w.shape[0], int(act_in), int(act_out), _ptr(y), _stream()))
 
 
 def cfg_sched_step(eps_u, eps_c, x, last, m0, m1, coef):

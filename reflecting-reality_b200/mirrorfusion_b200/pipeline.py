@@ -245,14 +245,22 @@ class StepEngine:
 
     def __init__(self, cfg: NetConfig, unet_sd, brushnet_sd, images: int, H: int, W: int, device="cuda",
                  use_graph: bool = True, fuse_taps: bool = True, two_streams: bool = False,
-                 dedup_brushnet_cfg: bool = False):
-        """dedup_brushnet_cfg (opt-in, exact): BrushNetModel has no attention, so `encoder_hidden_states` is unused
+                 dedup_brushnet_cfg: bool = False, precision: str = "bf16"):
+        """precision: "bf16" = the product path (tcgen05 kernels); "fp32" = the PARITY MODE of BASELINE config 1 — the
+        same program (fusions, K-segments, tap folding, buffers) with fp32 storage on the CUDA-core kernels of
+        csrc/fp32mode.cu, for the rel-L2 1e-4 bar against the fp32 reference.
+        dedup_brushnet_cfg (opt-in, exact): BrushNetModel has no attention, so `encoder_hidden_states` is unused
         (brushnet.py:678-925) and in the pipeline's default mode both CFG halves of its batch are identical by
         construction (`latent_model_input = torch.cat([latents] * 2)`, doubled `conditioning_latents`,
         pipeline_brushnet.py:1256,1188-1202).  The branch is then evaluated on `images` samples and its 28 features
         are broadcast to both halves before the UNet consumes them — bit-identical taps, 18 % fewer FLOPs per step.
         `set_conditioning` refuses conditioning whose halves differ.  Off by default: the headline numbers of
         bench.py run the reference's full 2b-sample BrushNet."""
+        self.precision = precision
+        with ops.precision(precision):      # engines read the storage dtype while they are built
+            self._build(cfg, unet_sd, brushnet_sd, images, H, W, device, use_graph, fuse_taps, two_streams, dedup_brushnet_cfg)
+
+    def _build(self, cfg, unet_sd, brushnet_sd, images, H, W, device, use_graph, fuse_taps, two_streams, dedup_brushnet_cfg):
         self.cfg, self.images, self.H, self.W = cfg, images, H, W
         self.dev = torch.device(device)
         B = 2 * images
