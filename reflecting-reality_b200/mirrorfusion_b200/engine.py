@@ -118,7 +118,7 @@ class _Net:
         if p1 is None or (x2 is not None and p2 is None):
             p1 = p2 = None
         self.emit(lambda: ops.groupnorm(x1, x2, g, b, out, self.gn_ws, B=self.B, HW=HW, groups=G, eps=eps, silu=silu,
-                                        part1=p1, part2=p2), 2, "groupnorm")
+                                        part1=p1, part2=p2), 1 if HW <= 64 else 2, "groupnorm")   # <= 8x8 maps: single-launch kernel
 
     def layernorm(self, x, prefix: str, out):
         g, b = self.wf(prefix + ".weight"), self.wf(prefix + ".bias")

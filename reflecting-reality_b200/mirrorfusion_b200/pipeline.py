@@ -435,7 +435,9 @@ class MirrorFusionB200Pipeline:
     def __init__(self, unet_state_dict, brushnet_state_dict, scheduler=None, cfg: NetConfig = SD15, device="cuda",
                  depth_conditioning_mode: str = "concat", normals_conditioning_mode: Optional[str] = None,
                  vae_encode: Optional[Callable[[torch.Tensor], torch.Tensor]] = None,
-                 vae_decode: Optional[Callable[[torch.Tensor], torch.Tensor]] = None, vae_scale_factor: int = 8):
+                 vae_decode: Optional[Callable[[torch.Tensor], torch.Tensor]] = None, vae_scale_factor: int = 8,
+                 precision: str = "bf16"):
+        """precision="fp32": the fp32 parity mode of StepEngine (BASELINE config 1), otherwise the bf16 product path."""
         if depth_conditioning_mode != "concat" or normals_conditioning_mode is not None:
             raise NotImplementedError("only depth_conditioning_mode='concat' (the released MirrorFusion checkpoint) is implemented")
         self.cfg, self.device = cfg, torch.device(device)
@@ -443,11 +445,13 @@ class MirrorFusionB200Pipeline:
         self.scheduler = scheduler or B200UniPCScheduler()
         self.vae_encode, self.vae_decode, self.vae_scale_factor = vae_encode, vae_decode, vae_scale_factor
         self._engines: Dict[Tuple[int, int, int], StepEngine] = {}
+        self.precision = precision
 
     def engine(self, images, H, W) -> StepEngine:
         key = (images, H, W)
         if key not in self._engines:
-            self._engines[key] = StepEngine(self.cfg, self.unet_sd, self.brushnet_sd, images, H, W, self.device)
+            self._engines[key] = StepEngine(self.cfg, self.unet_sd, self.brushnet_sd, images, H, W, self.device,
+                                            precision=self.precision)
         return self._engines[key]
 
     def check_inputs(self, prompt_embeds, negative_prompt_embeds, brushnet_conditioning_scale, control_guidance_start,

@@ -89,3 +89,24 @@ def test_fp32_and_bf16_engines_share_the_program(P):
         assert [t for t, _ in ea.tags] == [t for t, _ in eb.tags]
         assert ea.notes == eb.notes
         assert ea.flops == eb.flops
+
+
+@pytest.mark.parametrize("cfg_name", ["tiny", "sd15"])
+def test_config1_ddim4_pipeline_call_fp32_vs_oracle(P, cfg_name):
+    """BASELINE.json configs[0] end to end: 1 image, 4 DDIM steps, CFG 7.5, fp32 — MirrorFusionB200Pipeline.__call__ in
+    fp32 mode against the oracle's restatement of the reference loop (pinned to the reference by tests/test_oracle_golden.py),
+    run on the host cores in fp32.  "sd15" is the config's real geometry (SD1.5 nets, 512x512 -> 64x64 latents)."""
+    from oracle import mf_oracle as O
+    cfg = TINY if cfg_name == "tiny" else SD15
+    size = cfg.sample_size if cfg_name == "tiny" else 64
+    usd, bsd = make_state_dict(cfg, "unet"), make_state_dict(cfg, "brushnet")
+    inp = make_inputs(cfg, 1, height=size, width=size)
+    pipe = P.MirrorFusionB200Pipeline(usd, bsd, scheduler=P.B200DDIMScheduler(), cfg=cfg, precision="fp32")
+    out = pipe(prompt_embeds=inp["prompt_embeds"][1:].cuda(), negative_prompt_embeds=inp["prompt_embeds"][:1].cuda(),
+               conditioning_latents=inp["conditioning_latents"][:1].cuda(), latents=inp["latents"].cuda(),
+               num_inference_steps=4, guidance_scale=7.5, output_type="latent").images
+    with torch.no_grad():
+        ref = O.denoise_loop(usd, bsd, cfg, O.DDIMOracle(), inp["latents"], inp["prompt_embeds"], inp["conditioning_latents"], 4, 7.5)
+    e = rel(out, ref)
+    record("fp32_mode_config1_ddim4_pipeline_vs_oracle", cfg=cfg_name, latents=e)
+    assert e < 1e-3          # 4 steps with CFG 7.5 amplify the 1e-4 per-step bar; measured ~1e-5

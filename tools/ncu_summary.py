@@ -1,5 +1,6 @@
 """Summarise ncu outputs into small text files for profiles/:
-   python tools/ncu_summary.py launches <launches.csv> <out.md>      (from --metrics gpu__time_duration.sum --csv)
+   python tools/ncu_summary.py launches <launches.csv> <out.md> [N]  (from --metrics gpu__time_duration.sum --csv; N = keep only
+                                                                      the last N launches of our kernels; -1 = one step)
    python tools/ncu_summary.py full <report.ncu-rep> <out.md>        (from --set full)"""
 import collections
 import csv
@@ -14,12 +15,21 @@ KEEP = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "sm__ops_path_tensor_op_hmma_src_bf16_dst_fp32_sparsity_off.avg.pct_of_peak_sustained_elapsed"]
 
 
-def launches(path, out):
+OURS = ("igemm_kernel", "attention_kernel", "gn_", "layernorm_kernel", "conv_in_kernel", "conv_out_kernel", "cfg_sched_kernel",
+        "transpose_tokens_kernel", "linear_small", "timestep_sinusoid", "f32_to_bf16")
+
+
+def launches(path, out, last=0):
+    """last > 0: keep only the last `last` launches of this library's kernels (one step out of a longer capture)."""
     lines = [l for l in open(path) if not l.startswith("==")]
     agg = collections.defaultdict(lambda: [0, 0.0])
-    for row in csv.DictReader(lines):
-        if row.get("Metric Name") != "gpu__time_duration.sum":
-            continue
+    rows = [r for r in csv.DictReader(lines) if r.get("Metric Name") == "gpu__time_duration.sum"]
+    if last == -1:      # exactly one denoise step: the launches between two consecutive cfg_sched kernels (the step's last kernel)
+        ends = [i for i, r in enumerate(rows) if "cfg_sched_kernel" in r["Kernel Name"]]
+        rows = [r for r in rows[ends[-2] + 1: ends[-1] + 1] if any(k in r["Kernel Name"] for k in OURS)]
+    elif last:
+        rows = [r for r in rows if any(k in r["Kernel Name"] for k in OURS)][-last:]
+    for row in rows:
         v = float(row["Metric Value"].replace(",", ""))
         u = row["Metric Unit"]
         v = v / 1e3 if u == "ns" else v * 1e3 if u == "ms" else v
@@ -49,4 +59,7 @@ def full(path, out):
 
 
 if __name__ == "__main__":
-    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2], sys.argv[3])
+    if sys.argv[1] == "launches":
+        launches(sys.argv[2], sys.argv[3], int(sys.argv[4]) if len(sys.argv) > 4 else 0)
+    else:
+        full(sys.argv[2], sys.argv[3])
