@@ -36,6 +36,29 @@ METRIC = "images_per_s_512x512_50_unipc_steps_cfg7.5"
 FLOP_PER_SAMPLE_STEP = 1.2446e12          # BrushNet 4.413e11 + UNet 8.033e11 at 64x64 latents
 
 
+
+# The driver reads ONE JSON line from stdout.  Libraries write banners there too (NCCL prints its version line to
+# stdout when NCCL_DEBUG is set), so file descriptor 1 is pointed at stderr for the whole run and the result line goes
+# to the saved real stdout.
+_REAL_STDOUT = None
+
+
+def capture_stdout():
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit_json(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -139,7 +162,7 @@ def run_reference(args, rank):
         "e2e": {"value": r["images_per_s"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit_json(line)
 
 
 # ----------------------------------------------------------------------------------------------------- our arm
@@ -336,7 +359,7 @@ def run_ours(args, rank, world, local_rank):
         line["config"]["brushnet_cfg_dedup"] = True
     if dedup_line is not None:
         line["brushnet_cfg_dedup"] = dedup_line
-    print(json.dumps(line), flush=True)
+    emit_json(line)
 
 
 def main():
@@ -359,6 +382,7 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    capture_stdout()
     if args.impl == "reference":
         run_reference(args, rank)
         return
