@@ -115,6 +115,10 @@ int mfb_groupnorm_prestat(const void* x1, int C1, const float* part1, int tiles1
 int mfb_layernorm(const void* x, int rows, int C, float eps, const float* gamma, const float* beta, void* out,
                   void* stream);
 
+/* Row softmax over [rows, cols] bf16 (in place allowed): the VAE mid block's single-head d = 512 attention runs as two
+ * GEMMs around it (S/models/attention_processor.py:1266-1268). */
+int mfb_softmax_rows(const void* x, int rows, int cols, void* out, void* stream);
+
 /* ------------------------------------------------------------------------------------------------------------
  * Scaled-dot-product attention, flash style on tcgen05 (S in TMEM, online softmax, P through shared memory).
  * Replaces F.scaled_dot_product_attention in AttnProcessor2_0.__call__

@@ -178,6 +178,26 @@ def golden_psnr(diffusers, steps=20):
     print(f"sd15 {steps}-step reference loop: {time.time() - t0:.0f}s, |lat|={lat.norm():.3f}, image range [{img.min():.2f},{img.max():.2f}]")
 
 
+@torch.no_grad()
+def golden_vae_decode(diffusers, name="tiny_vae_decode.npz", seed=0):
+    """AutoencoderKL.decode of the reference on the seeded TINY_VAE decoder weights (vae.make_vae_state_dict)."""
+    from mirrorfusion_b200.vae import TINY_VAE, make_vae_state_dict
+    cfg = TINY_VAE
+    n = len(cfg.block_out_channels)
+    vae = diffusers.AutoencoderKL(in_channels=3, out_channels=cfg.out_channels, down_block_types=("DownEncoderBlock2D",) * n,
+                                  up_block_types=("UpDecoderBlock2D",) * n, block_out_channels=cfg.block_out_channels,
+                                  layers_per_block=cfg.layers_per_block, latent_channels=cfg.latent_channels,
+                                  norm_num_groups=cfg.norm_num_groups, sample_size=32, scaling_factor=cfg.scaling_factor).eval()
+    sd = make_vae_state_dict(cfg, seed)
+    res = vae.load_state_dict(sd, strict=False)
+    assert not res.unexpected_keys, res.unexpected_keys
+    assert all(k.startswith(("encoder.", "quant_conv.")) for k in res.missing_keys), res.missing_keys   # decoder fully covered
+    z = torch.randn(2, cfg.latent_channels, 16, 16, generator=torch.Generator().manual_seed(4321)) * 3.0
+    img = vae.decode(z).sample
+    np.savez_compressed(os.path.join(GOLD, name), z=z.numpy(), image=img.numpy(), seed=seed)
+    print(f"{name}: z {tuple(z.shape)} -> image {tuple(img.shape)}, |image| = {img.norm().item():.4f}")
+
+
 def golden_signatures(diffusers, name):
     """Parameter names (in order) of the reference entry points the drop-in classes mirror."""
     import inspect
@@ -214,6 +234,8 @@ def main():
     which = sys.argv[1:] or ["sched", "micro", "tiny", "sd15", "sigs"]
     if "psnr" in which:
         golden_psnr(diffusers)
+    if "vae" in which:
+        golden_vae_decode(diffusers)
     if "sigs" in which:
         golden_signatures(diffusers, "reference_signatures.json")
     if "sched" in which:

@@ -233,7 +233,7 @@ __global__ void __launch_bounds__(256) ln32_kernel(const float* __restrict__ x, 
 // ------------------------------------------------------------------------------------------------ attention
 // one warp per (batch, head, query row); keys in chunks of 32: lane = key for the scores (online softmax across
 // chunks), lane = output dims {lane, lane+32, ...} for the P V accumulation
-constexpr int A32_MAXD = 160;
+constexpr int A32_MAXD = 512;       // 512 = the VAE mid block's single head
 __global__ void __launch_bounds__(128) attn32_kernel(const float* __restrict__ q, int ldq, const float* __restrict__ k, int ldk,
                                                      const float* __restrict__ v, int ldv, float* __restrict__ out, int ldo, int heads,
                                                      int d, int Tq, int Tk, float scale) {

@@ -442,7 +442,9 @@ static int groupnorm_impl(const void* x1, int C1, const void* x2, int C2, int B,
     if (!x2) C2 = 0;
     const int C = C1 + C2;
     MFB_REQUIRE(C1 % 8 == 0 && C2 % 8 == 0, "channel counts must be multiples of 8");
-    MFB_REQUIRE(groups > 0 && groups <= 64 && C % groups == 0 && C / groups >= 8, "unsupported group size (C=%d groups=%d)", C, groups);
+    // an 8-channel vector may straddle at most two groups: 4 channels per group (the VAE's 128-channel level) is the minimum
+    MFB_REQUIRE(groups > 0 && groups <= 64 && C % groups == 0 && C / groups >= 4 && (C / groups) % 4 == 0,
+                "unsupported group size (C=%d groups=%d)", C, groups);
     const int CV = C / 8;
     MFB_REQUIRE(CV <= 1024, "C too large");
     const int PY = CV >= 256 ? 1 : 256 / CV;
@@ -518,6 +520,65 @@ extern "C" int mfb_groupnorm_prestat(const void* x1, int C1, const float* part1,
     MFB_REQUIRE(part1 && tiles1 > 0 && (!x2 || (part2 && tiles2 > 0)), "mfb_groupnorm_prestat needs the partial statistics of every source");
     MFB_REQUIRE(groups <= 64, "at most 64 groups");
     return groupnorm_impl(x1, C1, x2, C2, B, HW, groups, eps, gamma, beta, silu, stats_ws, out, stream, part1, tiles1, part2, tiles2);
+}
+
+// Row softmax over [rows, cols] bf16 (fp32 math), one CTA of 256 threads per row, 16-byte accesses; in place allowed.
+// Used by the single-head (d = 512) attention of the VAE mid block, whose scores come out of a GEMM already scaled
+// (S/models/attention_processor.py:1266-1268 — softmax(Q K^T * d^-0.5) as two GEMMs around this kernel).
+namespace mfb {
+__global__ void __launch_bounds__(256) softmax_rows_kernel(const __nv_bfloat16* __restrict__ x, int cols, __nv_bfloat16* __restrict__ out) {
+    __shared__ float red[8];
+    pdl_trigger();
+    pdl_wait();
+    const __nv_bfloat16* xr = x + static_cast<size_t>(blockIdx.x) * cols;
+    __nv_bfloat16* orow = out + static_cast<size_t>(blockIdx.x) * cols;
+    const int nv = cols / 8;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    auto block_reduce = [&](float v, bool is_max) {
+        for (int o = 16; o > 0; o >>= 1) {
+            const float t = __shfl_xor_sync(0xffffffffu, v, o);
+            v = is_max ? fmaxf(v, t) : v + t;
+        }
+        __syncthreads();
+        if (lane == 0) red[wid] = v;
+        __syncthreads();
+        float r = red[0];
+        for (int i = 1; i < 8; ++i) r = is_max ? fmaxf(r, red[i]) : r + red[i];      // fixed order: deterministic
+        return r;
+    };
+    float mx = -INFINITY;
+    for (int v = threadIdx.x; v < nv; v += 256) {
+        float f[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(xr) + v), f);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) mx = fmaxf(mx, f[e]);
+    }
+    mx = block_reduce(mx, true);
+    float sum = 0.f;
+    for (int v = threadIdx.x; v < nv; v += 256) {
+        float f[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(xr) + v), f);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) sum += __expf(f[e] - mx);
+    }
+    sum = block_reduce(sum, false);
+    const float inv = 1.0f / sum;
+    for (int v = threadIdx.x; v < nv; v += 256) {
+        float f[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(xr) + v), f);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) f[e] = __expf(f[e] - mx) * inv;
+        reinterpret_cast<uint4*>(orow)[v] = pack8(f);
+    }
+}
+}  // namespace mfb
+
+extern "C" int mfb_softmax_rows(const void* x, int rows, int cols, void* out, void* stream) {
+    MFB_REQUIRE(x && out && rows > 0, "null pointer");
+    MFB_REQUIRE(cols > 0 && cols % 8 == 0, "cols must be a positive multiple of 8 (got %d)", cols);
+    MFB_CUDA_OK(launch_k(softmax_rows_kernel, dim3(rows), dim3(256), 0, static_cast<cudaStream_t>(stream), 1,
+                         static_cast<const __nv_bfloat16*>(x), cols, static_cast<__nv_bfloat16*>(out)));
+    return MFB_OK;
 }
 
 extern "C" int mfb_layernorm(const void* x, int rows, int C, float eps, const float* gamma, const float* beta, void* out,

@@ -43,6 +43,7 @@ _SIGS = {
     "mfb_groupnorm_prestat": (i32, [vp, i32, vp, i32, vp, i32, vp, i32, i32, i32, i32, f32, vp, vp, i32, vp, vp, vp]),
     "mfb_groupnorm": (i32, [vp, i32, vp, i32, i32, i32, i32, f32, vp, vp, i32, vp, vp, vp]),
     "mfb_layernorm": (i32, [vp, i32, i32, f32, vp, vp, vp, vp]),
+    "mfb_softmax_rows": (i32, [vp, i32, i32, vp, vp]),
     "mfb_attention": (i32, [vp, i32, vp, i32, vp, i32, vp, i32, i32, i32, i32, i32, i32, vp]),
     "mfb_transpose_tokens": (i32, [vp, i32, i32, i32, i32, i32, vp, i32, vp]),
     "mfb_conv_in": (i32, [vp, i32, vp, i32, i32, i32, i32, vp, vp, i32, vp, vp, vp, vp]),

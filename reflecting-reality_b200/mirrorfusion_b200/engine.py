@@ -181,10 +181,10 @@ class _Net:
         self.groupnorm(xa, xb, p + ".norm1", n1, HW, eps, True)
         h1 = self.scratch("h1", B, HW, cout)
         w1 = ops.pack_conv_weight(self.sd[p + ".conv1.weight"])
-        off = self.rowbias_off[p]
-        rb = self.rowbias[:, off:]
+        off = self.rowbias_off.get(p)          # None: a resnet without time embedding (the VAE's)
+        rb = None if off is None else self.rowbias[:, off:]
         self.emit_plan(ops.ConvPlan(n1, w1, h1, B=B, H=h, W=w, Cin=cin, Cout=cout, ksize=3, bias=self.wf(p + ".conv1.bias"),
-                                    rowbias=rb, rowbias_ld=self.rowbias.shape[1]), out=h1, gn_stats=True)
+                                    rowbias=rb, rowbias_ld=0 if rb is None else self.rowbias.shape[1]), out=h1, gn_stats=True)
         n2 = self.scratch("n2", B, HW, cout)
         self.groupnorm(h1, None, p + ".norm2", n2, HW, eps, True)
         out = self.buf(B, HW, cout)

@@ -227,6 +227,12 @@ def layernorm(x, gamma, beta, out, eps=1e-5):
     check(fn(_ptr(x), rows, Cc, eps, _ptr(gamma), _ptr(beta), _ptr(out), _stream()))
 
 
+def softmax_rows(x, out):
+    """Row softmax of a [rows, cols] bf16 matrix (fp32 math)."""
+    _req(x, bf16, "x"); _req(out, bf16, "out")
+    check(lib().mfb_softmax_rows(_ptr(x), x.shape[0], x.shape[1], _ptr(out), _stream()))
+
+
 # --------------------------------------------------------------------------------------------- attention
 def attention(q, k, v, out, *, B, heads, head_dim, Tq, Tk, ldq=None, ldk=None, ldv=None, ldo=None):
     """q [B,Tq,ldq], k / v [B,Tk,ld] (views into a fused q|k|v buffer are fine: pass the leading dimension)."""

@@ -125,3 +125,17 @@ def test_unipc_known_answer_from_reference_tests():
         residual = sample * int(t) / (int(t) + 1)
         sample = s.step(residual, t, sample)
     assert abs(sample.abs().mean().item() - 0.2464) < 1e-3
+
+
+def test_vae_decode_oracle_matches_reference_golden(golden_dir):
+    """oracle/vae_oracle.py against AutoencoderKL.decode of the reference itself on the seeded TINY_VAE weights
+    (the VAE decode is the next row after the denoise step)."""
+    from mirrorfusion_b200.vae import TINY_VAE, make_vae_state_dict, vae_decoder_param_shapes, SD_VAE
+    from oracle.vae_oracle import vae_decode
+    g = _load(golden_dir, "tiny_vae_decode.npz")
+    sd = make_vae_state_dict(TINY_VAE, int(g["seed"]))
+    img = vae_decode(sd, TINY_VAE, torch.from_numpy(g["z"]))
+    assert tuple(img.shape) == g["image"].shape
+    assert rel(img, g["image"]) < 1e-5
+    # decoder + post_quant_conv of the SD VAE: 49 490 199 parameters (AutoencoderKL(block_out_channels=(128,256,512,512)))
+    assert sum(int(np.prod(s)) for _, s in vae_decoder_param_shapes(SD_VAE)) == 49_490_199
