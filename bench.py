@@ -333,6 +333,32 @@ def run_ours(args, rank, world, local_rank):
         "whole_step_tflops": step_flops / (ms_per_step * 1e-3) / 1e12,
         "whole_step_frac_of_peak": step_flops / (ms_per_step * 1e-3) / 1e12 / peak,
     }
+    # ---------------- VAE decode of the final latents on the same kernels: secondary key, never part
+    # of `value` / `e2e` (BASELINE's metric is quoted on the denoise loop; this shows the tail the decode adds per batch)
+    vae_line = None
+    if world == 1 and not args.no_vae:
+        try:
+            from mirrorfusion_b200.vae import SD_VAE, VaeDecoderEngine, make_vae_state_dict
+            veng = VaeDecoderEngine(SD_VAE, make_vae_state_dict(SD_VAE), images, H, W, dev)
+            z = (eng.x / SD_VAE.scaling_factor).clone()
+            for _ in range(2):
+                veng.decode(z)
+            torch.cuda.synchronize()
+            v0, v1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            v0.record(stream)
+            for _ in range(3):
+                veng.decode(z)
+            v1.record(stream)
+            torch.cuda.synchronize()
+            vms = v0.elapsed_time(v1) / 3
+            vae_line = {"ms_per_batch": vms, "images": images, "pixels": f"{8 * H}x{8 * W}", "launches": veng.launches,
+                        "tflops": veng.flops / (vms * 1e-3) / 1e12,
+                        "images_per_s_loop_plus_decode": images / ((STEPS_PER_IMAGE * ms_per_step + vms) * 1e-3),
+                        "note": "AutoencoderKL.decode (SD VAE shape, random init) by VaeDecoderEngine, eager launches; secondary key"}
+            del veng
+        except Exception as ex:          # the headline measurement must not depend on the secondary one
+            vae_line = {"error": f"{type(ex).__name__}: {ex}"}
+
     # ---------------- CPU baseline (bounded sample) on this box's host cores
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
@@ -359,6 +385,8 @@ def run_ours(args, rank, world, local_rank):
         line["config"]["brushnet_cfg_dedup"] = True
     if dedup_line is not None:
         line["brushnet_cfg_dedup"] = dedup_line
+    if vae_line is not None:
+        line["vae_decode"] = vae_line
     emit_json(line)
 
 
@@ -377,6 +405,7 @@ def main():
     ap.add_argument("--report-dedup", action="store_true",
                     help="additionally time the de-duplicated engine and report it as the secondary key brushnet_cfg_dedup")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-vae", action="store_true", help="skip the secondary VAE-decode measurement")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", "0"))

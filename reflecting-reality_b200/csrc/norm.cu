@@ -442,8 +442,8 @@ static int groupnorm_impl(const void* x1, int C1, const void* x2, int C2, int B,
     if (!x2) C2 = 0;
     const int C = C1 + C2;
     MFB_REQUIRE(C1 % 8 == 0 && C2 % 8 == 0, "channel counts must be multiples of 8");
-    // an 8-channel vector may straddle at most two groups: 4 channels per group (the VAE's 128-channel level) is the minimum
-    MFB_REQUIRE(groups > 0 && groups <= 64 && C % groups == 0 && C / groups >= 4 && (C / groups) % 4 == 0,
+    // an 8-channel vector may straddle at most two groups: >= 8 channels per group, or exactly 4 (the VAE's 128-channel level)
+    MFB_REQUIRE(groups > 0 && groups <= 64 && C % groups == 0 && (C / groups >= 8 || C / groups == 4),
                 "unsupported group size (C=%d groups=%d)", C, groups);
     const int CV = C / 8;
     MFB_REQUIRE(CV <= 1024, "C too large");

@@ -436,8 +436,10 @@ class MirrorFusionB200Pipeline:
                  depth_conditioning_mode: str = "concat", normals_conditioning_mode: Optional[str] = None,
                  vae_encode: Optional[Callable[[torch.Tensor], torch.Tensor]] = None,
                  vae_decode: Optional[Callable[[torch.Tensor], torch.Tensor]] = None, vae_scale_factor: int = 8,
-                 precision: str = "bf16"):
-        """precision="fp32": the fp32 parity mode of StepEngine (BASELINE config 1), otherwise the bf16 product path."""
+                 precision: str = "bf16", vae_state_dict=None, vae_cfg=None):
+        """precision="fp32": the fp32 parity mode of StepEngine (BASELINE config 1), otherwise the bf16 product path.
+        vae_state_dict (AutoencoderKL.state_dict() keys; only post_quant_conv.* / decoder.* are read): when given and no
+        `vae_decode` callable is passed, images are decoded by VaeDecoderEngine on the same kernels (vae.py)."""
         if depth_conditioning_mode != "concat" or normals_conditioning_mode is not None:
             raise NotImplementedError("only depth_conditioning_mode='concat' (the released MirrorFusion checkpoint) is implemented")
         self.cfg, self.device = cfg, torch.device(device)
@@ -446,6 +448,18 @@ class MirrorFusionB200Pipeline:
         self.vae_encode, self.vae_decode, self.vae_scale_factor = vae_encode, vae_decode, vae_scale_factor
         self._engines: Dict[Tuple[int, int, int], StepEngine] = {}
         self.precision = precision
+        self.vae_sd, self.vae_cfg, self._vae_engines = vae_state_dict, vae_cfg, {}
+        if vae_state_dict is not None and vae_decode is None:
+            self.vae_decode = self._decode_on_kernels
+
+    def _decode_on_kernels(self, z: torch.Tensor) -> torch.Tensor:
+        from .vae import SD_VAE, VaeDecoderEngine
+        key = tuple(z.shape)
+        if key not in self._vae_engines:
+            with ops.precision(self.precision):
+                self._vae_engines[key] = VaeDecoderEngine(self.vae_cfg or SD_VAE, self.vae_sd, z.shape[0], z.shape[2], z.shape[3],
+                                                          self.device)
+        return self._vae_engines[key].decode(z).clone()
 
     def engine(self, images, H, W) -> StepEngine:
         key = (images, H, W)

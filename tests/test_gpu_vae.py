@@ -67,3 +67,29 @@ def test_sd_vae_decode_512px_runs_and_matches_fp32_mode_on_one_image():
     e, p = rel(img, ref), psnr_u8(img, ref)
     record("sd_vae_decode_512px_bf16_vs_fp32_mode", image_rel_l2=e, psnr_db=p)
     assert e < 2e-2 and p >= 40.0
+
+
+def test_pipeline_call_decodes_images_on_the_kernels():
+    """MirrorFusionB200Pipeline(vae_state_dict=...) with output_type='pt': denoise loop + VAE decode, both on the
+    kernels, against the oracle's loop followed by the oracle's decode (pipeline_brushnet.py:1337-1342)."""
+    from mirrorfusion_b200 import pipeline as P
+    from mirrorfusion_b200.config import TINY
+    from mirrorfusion_b200.synth import make_inputs, make_state_dict
+    from oracle import mf_oracle as O
+    from oracle.vae_oracle import vae_decode
+    cfg = TINY
+    usd, bsd = make_state_dict(cfg, "unet"), make_state_dict(cfg, "brushnet")
+    vsd = make_vae_state_dict(TINY_VAE, 0)
+    inp = make_inputs(cfg, 1)
+    pipe = P.MirrorFusionB200Pipeline(usd, bsd, scheduler=P.B200DDIMScheduler(), cfg=cfg, vae_state_dict=vsd, vae_cfg=TINY_VAE)
+    img = pipe(prompt_embeds=inp["prompt_embeds"][1:].cuda(), negative_prompt_embeds=inp["prompt_embeds"][:1].cuda(),
+               conditioning_latents=inp["conditioning_latents"][:1].cuda(), latents=inp["latents"].cuda(),
+               num_inference_steps=4, guidance_scale=7.5, output_type="pt").images
+    s = cfg.sample_size * 2 ** (len(TINY_VAE.block_out_channels) - 1)
+    assert tuple(img.shape) == (1, 3, s, s)
+    with torch.no_grad():
+        lat = O.denoise_loop(usd, bsd, cfg, O.DDIMOracle(), inp["latents"], inp["prompt_embeds"], inp["conditioning_latents"], 4, 7.5)
+    ref = vae_decode(vsd, TINY_VAE, lat / 0.18215)
+    p = psnr_u8(img, ref)
+    record("tiny_pipeline_images_vs_oracle", psnr_db=p, image_rel_l2=rel(img, ref))
+    assert p >= 40.0
