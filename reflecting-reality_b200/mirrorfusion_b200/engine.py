@@ -18,6 +18,7 @@ Fusions relative to the reference's op list:
 """
 from __future__ import annotations
 
+import os
 from typing import Callable, Dict, List, Optional, Sequence, Tuple
 
 import torch
@@ -45,7 +46,8 @@ class _Net:
         self.ext_reads: Dict[int, List[int]] = {}  # program position -> data_ptrs it reads (candidates for cross-net deps)
         # GroupNorm statistics produced by the igemm epilogue that wrote a tensor: data_ptr -> (partials buffer, tiles)
         self.stats_of: Dict[int, Tuple[torch.Tensor, int]] = {}
-        self.fuse_gn_stats = False    # opt-in: measured performance-neutral at the bench geometry (profiles/r01j)
+        # opt-in (env MFB_FUSE_GN_STATS=1): measured performance-neutral at the bench geometry (profiles/r01j, r01p)
+        self.fuse_gn_stats = os.environ.get("MFB_FUSE_GN_STATS", "0") == "1"
         # fused BrushNet taps: (packed weight, column offset, C, zero-conv weight [C,C] f32, bias buffer, base bias, zero-conv bias)
         self.fused_taps: List[Tuple] = []
         G = cfg.norm_num_groups
