@@ -320,7 +320,8 @@ def run_ours(args, rank, world, local_rank):
     ig = fam.get("igemm", [1e-9, 0.0, 1])
     achieved = ig[1] / (ig[0] * 1e-3) / 1e12
     peak = peaks["bf16_sustained"]
-    step_flops = FLOP_PER_SAMPLE_STEP * 2 * images
+    # SURVEY.md §8d census for 64x64 latents; other geometries (config 5: 96x96) use the engines' own plan census
+    step_flops = FLOP_PER_SAMPLE_STEP * 2 * images if (H, W) == (64, 64) else eng.flops_per_step
     roofline = {
         "bound": "tensor", "kernel": "mfb::igemm_kernel<160|128> (tcgen05 implicit-GEMM conv/linear)",
         "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
