@@ -73,6 +73,9 @@ typedef struct mfb_conv_desc {
                              pixel pre-summed); the plan issues 4 launches and never materialises the upsampled tensor */
     int igemm_mode;       /* 0 = auto (env MFB_IGEMM_MODE or independent CTAs); 1 independent CTAs, 2 CTA pair + weight multicast,
                              3 CTA pair + cta_group::2 UMMA (256-row tile) */
+    int pad0;             /* stride 2 only.  0: conv padding 1 (UNet Downsample2D).  1: F.pad(x, (0,1,0,1)) + conv padding 0 —
+                             the VAE encoder's Downsample2D(padding=0) (S/models/downsampling.py:141-143): taps read input rows
+                             2*oh + kh (not 2*oh + kh - 1), the zero row / column sits at the bottom / right edge */
     int dtype;            /* 0 = bf16 tensors, tcgen05 path (the product).  1 = fp32 PARITY MODE: x / extras / w / res / out
                              are fp32, CUDA-core FFMA accumulation (csrc/fp32mode.cu) — same descriptor semantics */
 } mfb_conv_desc;
@@ -171,6 +174,11 @@ int mfb_linear_small(const float* x, int M, int K, const void* w, const float* b
  *   b_x, b_mt, b_m0, b_eps             : x_new = b_x*x_c + b_mt*m_t + b_m0*m0 + b_eps*eps_guided  (UniP / DDIM)
  * Writes x_new -> x (in place), x_c -> last, shifts m0 -> m1 and m_t -> m0.
  */
+/* Latent sample of DiagonalGaussianDistribution (S/models/autoencoders/vae.py:769-791) times a scale:
+ * out = scale * (mean + exp(0.5 * clamp(logvar, -30, 20)) * noise); noise == NULL gives the mode (scale * mean).  fp32, n elements. */
+int mfb_latent_sample(const float* mean, const float* logvar, const float* noise, float scale, float* out, long long n,
+                      void* stream);
+
 int mfb_cfg_sched_step(const float* eps_uncond, const float* eps_cond, float* x, float* last, float* m0, float* m1,
                        const float* coef, int Bimg, long long n, void* stream);
 

@@ -188,14 +188,20 @@ def golden_vae_decode(diffusers, name="tiny_vae_decode.npz", seed=0):
                                   up_block_types=("UpDecoderBlock2D",) * n, block_out_channels=cfg.block_out_channels,
                                   layers_per_block=cfg.layers_per_block, latent_channels=cfg.latent_channels,
                                   norm_num_groups=cfg.norm_num_groups, sample_size=32, scaling_factor=cfg.scaling_factor).eval()
-    sd = make_vae_state_dict(cfg, seed)
-    res = vae.load_state_dict(sd, strict=False)
-    assert not res.unexpected_keys, res.unexpected_keys
-    assert all(k.startswith(("encoder.", "quant_conv.")) for k in res.missing_keys), res.missing_keys   # decoder fully covered
+    sd = make_vae_state_dict(cfg, seed, "both")
+    vae.load_state_dict(sd, strict=True)                 # every encoder / decoder / quant tensor comes from the seeded dict
     z = torch.randn(2, cfg.latent_channels, 16, 16, generator=torch.Generator().manual_seed(4321)) * 3.0
     img = vae.decode(z).sample
     np.savez_compressed(os.path.join(GOLD, name), z=z.numpy(), image=img.numpy(), seed=seed)
     print(f"{name}: z {tuple(z.shape)} -> image {tuple(img.shape)}, |image| = {img.norm().item():.4f}")
+    # encode: moments of the latent distribution for a synthetic image in [-1, 1], and one sample with known noise
+    x = torch.rand(2, 3, 32, 32, generator=torch.Generator().manual_seed(777)) * 2 - 1
+    dist = vae.encode(x).latent_dist
+    noise = torch.randn(dist.mean.shape, generator=torch.Generator().manual_seed(778))
+    sample = dist.mean + dist.std * noise
+    np.savez_compressed(os.path.join(GOLD, "tiny_vae_encode.npz"), x=x.numpy(), mean=dist.mean.numpy(), logvar=dist.logvar.numpy(),
+                        noise=noise.numpy(), sample=sample.numpy(), seed=seed)
+    print(f"tiny_vae_encode.npz: x {tuple(x.shape)} -> mean {tuple(dist.mean.shape)}, |mean| = {dist.mean.norm().item():.4f}")
 
 
 def golden_signatures(diffusers, name):

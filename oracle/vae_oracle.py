@@ -57,3 +57,34 @@ def vae_decode(sd: Dict[str, Tensor], cfg, z: Tensor) -> Tensor:
             x = F.conv2d(x, d[f"up_blocks.{i}.upsamplers.0.conv.weight"], d[f"up_blocks.{i}.upsamplers.0.conv.bias"], padding=1)
     x = F.silu(F.group_norm(x, g, d["conv_norm_out.weight"], d["conv_norm_out.bias"], eps))
     return F.conv2d(x, d["conv_out.weight"], d["conv_out.bias"], padding=1)
+
+
+@torch.no_grad()
+def vae_encode_moments(sd: Dict[str, Tensor], cfg, x: Tensor):
+    """AutoencoderKL.encode(x).latent_dist as (mean, logvar): S/models/autoencoders/autoencoder_kl.py:238-268,
+    Encoder.forward (S/models/autoencoders/vae.py:139-176), DownEncoderBlock2D with Downsample2D(padding=0)
+    (S/models/unets/unet_2d_blocks.py:1564-1575, S/models/downsampling.py:141-143: F.pad (0,1,0,1) then conv stride 2),
+    DiagonalGaussianDistribution (vae.py:769-776: chunk, logvar clamped to [-30, 20])."""
+    g, eps = cfg.norm_num_groups, cfg.norm_eps
+    e = {k[len("encoder."):]: v for k, v in sd.items() if k.startswith("encoder.")}
+    h = F.conv2d(x, e["conv_in.weight"], e["conv_in.bias"], padding=1)
+    n = len(cfg.block_out_channels)
+    for i in range(n):
+        for j in range(cfg.layers_per_block):
+            h = _resnet(e, f"down_blocks.{i}.resnets.{j}", h, g, eps)
+        if i != n - 1:
+            h = F.pad(h, (0, 1, 0, 1))
+            h = F.conv2d(h, e[f"down_blocks.{i}.downsamplers.0.conv.weight"], e[f"down_blocks.{i}.downsamplers.0.conv.bias"], stride=2)
+    h = _resnet(e, "mid_block.resnets.0", h, g, eps)
+    h = _attention(e, "mid_block.attentions.0", h, g, eps)
+    h = _resnet(e, "mid_block.resnets.1", h, g, eps)
+    h = F.silu(F.group_norm(h, g, e["conv_norm_out.weight"], e["conv_norm_out.bias"], eps))
+    h = F.conv2d(h, e["conv_out.weight"], e["conv_out.bias"], padding=1)
+    m = F.conv2d(h, sd["quant_conv.weight"], sd["quant_conv.bias"])
+    mean, logvar = m.chunk(2, dim=1)
+    return mean, logvar.clamp(-30.0, 20.0)
+
+
+def latent_sample(mean: Tensor, logvar: Tensor, noise: Tensor) -> Tensor:
+    """DiagonalGaussianDistribution.sample with the noise given (vae.py:782-791)."""
+    return mean + torch.exp(0.5 * logvar) * noise

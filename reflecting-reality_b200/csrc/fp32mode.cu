@@ -139,8 +139,8 @@ int conv32_build(const mfb_conv_desc* d, int up_py, int up_px, const void* w, Co
         q.ntaps = d->ksize * d->ksize;
         for (int kh = 0; kh < d->ksize; ++kh)
             for (int kw = 0; kw < d->ksize; ++kw) {
-                q.dh[kh * d->ksize + kw] = kh - d->ksize / 2;
-                q.dw[kh * d->ksize + kw] = kw - d->ksize / 2;
+                q.dh[kh * d->ksize + kw] = kh - (d->pad0 ? 0 : d->ksize / 2);      // pad0: zero row/column at the bottom/right
+                q.dw[kh * d->ksize + kw] = kw - (d->pad0 ? 0 : d->ksize / 2);
             }
         q.Ho = (d->H + d->stride - 1) / d->stride; q.Wo = (d->W + d->stride - 1) / d->stride;
         q.o_step = 1; q.o_py = 0; q.o_px = 0; q.Hf = q.Ho; q.Wf = q.Wo;

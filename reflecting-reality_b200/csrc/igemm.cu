@@ -685,8 +685,12 @@ static int build_params(const mfb_conv_desc* d, int up_py, int up_px, const void
                 rc = encode_nhwc(&p.tmA[ph * 2 + pw], d->x, d->Cin, W, H, B, 2, ph, pw, box, 128);
                 if (rc) return rc;
             }
-        // input row = 2*oh + kh - 1:  kh=0 -> (parity 1, h2 = oh-1); kh=1 -> (0, oh); kh=2 -> (1, oh)
-        const int par[3] = {1, 0, 1}, off[3] = {-1, 0, 0};
+        // padding 1: input row = 2*oh + kh - 1:  kh=0 -> (parity 1, h2 = oh-1); kh=1 -> (0, oh); kh=2 -> (1, oh)
+        // pad0 (zero row/column appended at the bottom/right, conv padding 0): input row = 2*oh + kh:
+        //                                          kh=0 -> (0, oh); kh=1 -> (1, oh); kh=2 -> (0, oh+1)
+        const int par1[3] = {1, 0, 1}, off1[3] = {-1, 0, 0}, par0[3] = {0, 1, 0}, off0[3] = {0, 0, 1};
+        const int* par = d->pad0 ? par0 : par1;
+        const int* off = d->pad0 ? off0 : off1;
         for (int kh = 0; kh < 3; ++kh)
             for (int kw = 0; kw < 3; ++kw) {
                 p.seg[nseg++] = IgemmSeg{par[kh] * 2 + par[kw], off[kh], off[kw], 0, d->Cin / 64};
@@ -810,6 +814,7 @@ extern "C" int mfb_conv_plan_create(const mfb_conv_desc* d, mfb_plan** out) {
     MFB_REQUIRE(d->x && d->w && d->out, "x / w / out must be device pointers");
     MFB_REQUIRE(!d->geglu || (d->Cout % 128 == 0 && !d->res1 && !d->res2 && !d->rowbias), "geglu needs Cout %% 128 == 0 and no residuals");
     MFB_REQUIRE(!d->up2x || (d->ksize == 3 && d->stride == 1 && !d->geglu), "up2x needs a 3x3 stride-1 conv");
+    MFB_REQUIRE(!d->pad0 || d->stride == 2, "pad0 is a stride-2 mode");
 
     Plan* pl = new Plan();
     int rc;

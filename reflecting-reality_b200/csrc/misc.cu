@@ -482,6 +482,27 @@ extern "C" int mfb_linear_small(const float* x, int M, int K, const void* w, con
     return MFB_OK;
 }
 
+namespace mfb {
+__global__ void latent_sample_kernel(const float* __restrict__ mean, const float* __restrict__ logvar, const float* __restrict__ noise,
+                                     float scale, float* __restrict__ out, long long n) {
+    pdl_trigger();
+    pdl_wait();
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float v = mean[i];
+    if (noise) v += expf(0.5f * fminf(fmaxf(logvar[i], -30.0f), 20.0f)) * noise[i];
+    out[i] = scale * v;
+}
+}  // namespace mfb
+
+extern "C" int mfb_latent_sample(const float* mean, const float* logvar, const float* noise, float scale, float* out, long long n,
+                                 void* stream) {
+    MFB_REQUIRE(mean && out && (noise == nullptr || logvar != nullptr) && n > 0, "bad arguments");
+    MFB_CUDA_OK(launch_k(latent_sample_kernel, dim3(static_cast<unsigned>((n + 255) / 256)), dim3(256), 0,
+                         static_cast<cudaStream_t>(stream), 1, mean, logvar, noise, scale, out, n));
+    return MFB_OK;
+}
+
 extern "C" int mfb_cfg_sched_step(const float* eps_uncond, const float* eps_cond, float* x, float* last, float* m0, float* m1,
                                   const float* coef, int Bimg, long long n, void* stream) {
     MFB_REQUIRE(eps_uncond && eps_cond && x && last && m0 && m1 && coef, "null pointer");

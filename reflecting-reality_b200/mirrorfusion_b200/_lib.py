@@ -23,7 +23,7 @@ class ConvDesc(C.Structure):
         ("B", i32), ("H", i32), ("W", i32), ("Cin", i32), ("Cout", i32), ("ksize", i32), ("stride", i32),
         ("x", vp), ("n_extra", i32), ("extra_x", vp * 3), ("extra_C", i32 * 3), ("w", vp), ("bias", vp),
         ("rowbias", vp), ("rowbias_ld", i32), ("alpha", vp), ("res1", vp), ("res2", vp), ("out", vp),
-        ("geglu", i32), ("block_n", i32), ("up2x", i32), ("igemm_mode", i32), ("dtype", i32),
+        ("geglu", i32), ("block_n", i32), ("up2x", i32), ("igemm_mode", i32), ("pad0", i32), ("dtype", i32),
     ]
 
 
@@ -54,6 +54,7 @@ _SIGS = {
     "mfb_f32_to_bf16": (i32, [vp, i64, vp, vp]),
     "mfb_timestep_sinusoid": (i32, [vp, i32, i32, vp, vp]),
     "mfb_linear_small": (i32, [vp, i32, i32, vp, vp, i32, i32, i32, vp, vp]),
+    "mfb_latent_sample": (i32, [vp, vp, vp, f32, vp, i64, vp]),
     "mfb_cfg_sched_step": (i32, [vp, vp, vp, vp, vp, vp, vp, i32, i64, vp]),
     # fp32 parity mode
     "mfb_groupnorm_f32": (i32, [vp, i32, vp, i32, i32, i32, i32, f32, vp, vp, i32, vp, vp]),

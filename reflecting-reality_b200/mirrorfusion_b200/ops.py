@@ -115,7 +115,8 @@ class ConvPlan:
                  Cout: int, ksize: int = 1, stride: int = 1, extras: Sequence[torch.Tensor] = (),
                  bias: Optional[torch.Tensor] = None, rowbias: Optional[torch.Tensor] = None, rowbias_ld: int = 0,
                  alpha: Optional[torch.Tensor] = None, res1: Optional[torch.Tensor] = None,
-                 res2: Optional[torch.Tensor] = None, geglu: bool = False, block_n: int = 0, igemm_mode: int = 0, up2x: bool = False):
+                 res2: Optional[torch.Tensor] = None, geglu: bool = False, block_n: int = 0, igemm_mode: int = 0, up2x: bool = False,
+                 pad0: bool = False):
         L = lib()
         dt = f32 if _is32(x) else bf16      # fp32 tensors select the parity-mode plan (mfb_conv_desc.dtype = 1)
         _req(x, dt, "x"); _req(w, dt, "w"); _req(out, dt, "out")
@@ -145,6 +146,7 @@ class ConvPlan:
         d.block_n = block_n
         d.igemm_mode = igemm_mode
         d.up2x = int(up2x)
+        d.pad0 = int(pad0)
         ktot = (4 if up2x else ksize * ksize) * Cin + sum(e.shape[-1] for e in extras)
         want = (4, Cout, ktot) if up2x else (Cout, ktot)
         if tuple(w.shape) != want:
@@ -290,6 +292,11 @@ def linear_small(x, w, b, y, act_in=False, act_out=False):
     M, K = x.shape
     fn = lib().mfb_linear_small_f32 if _is32(w) else lib().mfb_linear_small
     check(fn(_ptr(x), M, K, _ptr(w), _ptr(b), w.shape[0], int(act_in), int(act_out), _ptr(y), _stream()))
+
+
+def latent_sample(mean, logvar, noise, scale, out):
+    """out = scale * (mean + exp(0.5 * clamp(logvar)) * noise); noise=None -> the mode.  All fp32."""
+    check(lib().mfb_latent_sample(_ptr(mean), _ptr(logvar), _ptr(noise), float(scale), _ptr(out), mean.numel(), _stream()))
 
 
 def cfg_sched_step(eps_u, eps_c, x, last, m0, m1, coef):

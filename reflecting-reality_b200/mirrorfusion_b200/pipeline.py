@@ -451,6 +451,20 @@ class MirrorFusionB200Pipeline:
         self.vae_sd, self.vae_cfg, self._vae_engines = vae_state_dict, vae_cfg, {}
         if vae_state_dict is not None and vae_decode is None:
             self.vae_decode = self._decode_on_kernels
+        if vae_state_dict is not None and vae_encode is None and any(k.startswith("encoder.") for k in vae_state_dict):
+            self.vae_encode = self._encode_on_kernels
+
+    def _encode_on_kernels(self, img: torch.Tensor) -> torch.Tensor:
+        """AutoencoderKL.encode(img).latent_dist.sample() (pipeline_brushnet.py:1188-1190) by VaeEncoderEngine."""
+        from .vae import SD_VAE, VaeEncoderEngine
+        key = ("enc",) + tuple(img.shape)
+        if key not in self._vae_engines:
+            with ops.precision(self.precision):
+                self._vae_engines[key] = VaeEncoderEngine(self.vae_cfg or SD_VAE, self.vae_sd, img.shape[0], img.shape[2], img.shape[3],
+                                                          self.device)
+        eng = self._vae_engines[key]
+        noise = torch.randn(img.shape[0], eng.mean.shape[1], *eng.latent_hw, device=self.device, dtype=torch.float32)
+        return eng.encode(img, noise=noise).clone()
 
     def _decode_on_kernels(self, z: torch.Tensor) -> torch.Tensor:
         from .vae import SD_VAE, VaeDecoderEngine

@@ -93,3 +93,38 @@ def test_pipeline_call_decodes_images_on_the_kernels():
     p = psnr_u8(img, ref)
     record("tiny_pipeline_images_vs_oracle", psnr_db=p, image_rel_l2=rel(img, ref))
     assert p >= 40.0
+
+
+@pytest.mark.parametrize("precision,tol", [("bf16", 2e-2), ("fp32", 1e-4)])
+def test_tiny_vae_encode_vs_reference_golden(golden_dir, precision, tol):
+    """AutoencoderKL.encode on the kernels (VaeEncoderEngine: pad0 stride-2 convs, conv_out . quant_conv folded, fp32 moments)
+    against the reference's own latent distribution for the same seeded weights and image."""
+    from mirrorfusion_b200.vae import VaeEncoderEngine
+    g = np.load(os.path.join(golden_dir, "tiny_vae_encode.npz"))
+    sd = make_vae_state_dict(TINY_VAE, int(g["seed"]), "both")
+    x = torch.from_numpy(g["x"])
+    with ops.precision(precision):
+        eng = VaeEncoderEngine(TINY_VAE, sd, x.shape[0], x.shape[2], x.shape[3])
+    lat = eng.encode(x.cuda(), noise=torch.from_numpy(g["noise"]).cuda(), scale=1.0)
+    em, ev, es = rel(eng.mean, g["mean"]), rel(eng.logvar, g["logvar"]), rel(lat, g["sample"])
+    record("tiny_vae_encode_vs_reference", precision=precision, mean=em, logvar=ev, sample=es)
+    assert em < tol and ev < tol and es < tol
+    mode = eng.encode(x.cuda(), noise=None, scale=TINY_VAE.scaling_factor).cpu()
+    assert rel(mode, g["mean"] * TINY_VAE.scaling_factor) < tol
+
+
+def test_sd_vae_encode_512px_bf16_vs_fp32_mode():
+    """The real geometry (SD VAE, 512x512 -> 64x64 latents, mid-block attention over 4096 tokens with d = 512)."""
+    from mirrorfusion_b200.vae import VaeEncoderEngine
+    sd = make_vae_state_dict(SD_VAE, 0, "encoder")
+    x = torch.rand(1, 3, 512, 512, generator=torch.Generator().manual_seed(6)) * 2 - 1
+    eng = VaeEncoderEngine(SD_VAE, sd, 1, 512, 512)
+    eng.encode(x.cuda())
+    mean = eng.mean.clone()
+    assert tuple(mean.shape) == (1, 4, 64, 64)
+    with ops.precision("fp32"):
+        e32 = VaeEncoderEngine(SD_VAE, sd, 1, 512, 512)
+    e32.encode(x.cuda())
+    e = rel(mean, e32.mean)
+    record("sd_vae_encode_512px_bf16_vs_fp32_mode", mean=e)
+    assert e < 2e-2

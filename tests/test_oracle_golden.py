@@ -139,3 +139,15 @@ def test_vae_decode_oracle_matches_reference_golden(golden_dir):
     assert rel(img, g["image"]) < 1e-5
     # decoder + post_quant_conv of the SD VAE: 49 490 199 parameters (AutoencoderKL(block_out_channels=(128,256,512,512)))
     assert sum(int(np.prod(s)) for _, s in vae_decoder_param_shapes(SD_VAE)) == 49_490_199
+
+
+def test_vae_encode_oracle_matches_reference_golden(golden_dir):
+    from mirrorfusion_b200.vae import TINY_VAE, make_vae_state_dict, vae_encoder_param_shapes, SD_VAE
+    from oracle.vae_oracle import vae_encode_moments, latent_sample
+    g = _load(golden_dir, "tiny_vae_encode.npz")
+    sd = make_vae_state_dict(TINY_VAE, int(g["seed"]), "both")
+    mean, logvar = vae_encode_moments(sd, TINY_VAE, torch.from_numpy(g["x"]))
+    assert rel(mean, g["mean"]) < 1e-5 and rel(logvar, g["logvar"]) < 1e-5
+    assert rel(latent_sample(mean, logvar, torch.from_numpy(g["noise"])), g["sample"]) < 1e-5
+    # encoder + quant_conv of the SD VAE: 34 163 592 + 72 parameters
+    assert sum(int(np.prod(s)) for _, s in vae_encoder_param_shapes(SD_VAE)) == 34_163_664
