@@ -204,6 +204,34 @@ def golden_vae_decode(diffusers, name="tiny_vae_decode.npz", seed=0):
     print(f"tiny_vae_encode.npz: x {tuple(x.shape)} -> mean {tuple(dist.mean.shape)}, |mean| = {dist.mean.norm().item():.4f}")
 
 
+def golden_checkpoint_layout(diffusers, name="micro_checkpoint_layout.json"):
+    """What `save_pretrained(safe_serialization=True)` of the reference writes for the two networks (MICRO config):
+    config.json verbatim + the safetensors header (names, dtypes, shapes).  The loader of mirrorfusion_b200.checkpoint is
+    run on the reference-written directories right here, and must return exactly the seeded tensors."""
+    import json
+    import tempfile
+    from safetensors import safe_open
+    from mirrorfusion_b200.config import MICRO
+    from mirrorfusion_b200 import checkpoint as CK
+    unet, bn, usd, bsd = build_reference_nets(diffusers, MICRO)
+    out = {}
+    with tempfile.TemporaryDirectory() as tmp:
+        for net, mod, sd in (("unet", unet, usd), ("brushnet", bn, bsd)):
+            d = os.path.join(tmp, net)
+            mod.save_pretrained(d, safe_serialization=True)
+            with safe_open(os.path.join(d, CK.WEIGHTS[0]), framework="pt") as sf:
+                tensors = {k: [str(sf.get_slice(k).get_dtype()), list(sf.get_slice(k).get_shape())] for k in sf.keys()}
+            out[net] = {"files": sorted(os.listdir(d)), "config": json.load(open(os.path.join(d, "config.json"))), "tensors": tensors}
+        cfg, lu, lb = CK.load_mirrorfusion(os.path.join(tmp, "unet"), os.path.join(tmp, "brushnet"))
+        import dataclasses
+        assert dataclasses.asdict(cfg) == dataclasses.asdict(MICRO), (cfg, MICRO)
+        assert all(torch.equal(lu[k], usd[k]) for k in usd) and all(torch.equal(lb[k], bsd[k]) for k in bsd)
+        out["loader_verified_on_reference_written_files"] = True
+    with open(os.path.join(GOLD, name), "w") as f:
+        json.dump(out, f, indent=0)
+    print(f"{name}: {len(out['unet']['tensors'])} + {len(out['brushnet']['tensors'])} tensors; loader verified on the reference's files")
+
+
 def golden_signatures(diffusers, name):
     """Parameter names (in order) of the reference entry points the drop-in classes mirror."""
     import inspect
@@ -242,6 +270,8 @@ def main():
         golden_psnr(diffusers)
     if "vae" in which:
         golden_vae_decode(diffusers)
+    if "ckpt" in which:
+        golden_checkpoint_layout(diffusers)
     if "sigs" in which:
         golden_signatures(diffusers, "reference_signatures.json")
     if "sched" in which:

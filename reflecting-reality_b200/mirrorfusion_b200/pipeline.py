@@ -466,6 +466,15 @@ class MirrorFusionB200Pipeline:
         noise = torch.randn(img.shape[0], eng.mean.shape[1], *eng.latent_hw, device=self.device, dtype=torch.float32)
         return eng.encode(img, noise=noise).clone()
 
+    @classmethod
+    def from_checkpoint(cls, unet_dir: str, brushnet_dir: str, **kw) -> "MirrorFusionB200Pipeline":
+        """Build from the reference's on-disk layout: two diffusers model directories (config.json +
+        diffusion_pytorch_model.safetensors), e.g. `<base>/unet` and `checkpoint-N/brushnet`
+        (E/train_brushnet_mirror.py:997-1032), read without instantiating torch modules (checkpoint.py)."""
+        from .checkpoint import load_mirrorfusion
+        cfg, usd, bsd = load_mirrorfusion(unet_dir, brushnet_dir)
+        return cls(usd, bsd, cfg=cfg, **kw)
+
     def _decode_on_kernels(self, z: torch.Tensor) -> torch.Tensor:
         from .vae import SD_VAE, VaeDecoderEngine
         key = tuple(z.shape)
