@@ -174,6 +174,17 @@ int mfb_linear_small(const float* x, int M, int K, const void* w, const float* b
  *   b_x, b_mt, b_m0, b_eps             : x_new = b_x*x_c + b_mt*m_t + b_m0*m0 + b_eps*eps_guided  (UniP / DDIM)
  * Writes x_new -> x (in place), x_c -> last, shifts m0 -> m1 and m_t -> m0.
  */
+/* SynMirror input preprocessing of the eval sweep, inputs already at the target resolution:
+ *   mfb_prep_image_u8   : uint8 HWC RGB [N,H,W,3] -> fp32 NCHW in [-1,1]   (VaeImageProcessor.preprocess, S/image_processor.py:446-530)
+ *   mfb_prep_mask_depth : uint8 mask [N,H,W] (+ metric depth fp32 [N,H,W] or NULL) -> latent-resolution mask {0,1} and depth
+ *                         in [-1,1] by nearest sampling at (factor*i, factor*j)  (pipeline_brushnet.py:1139,1190-1202;
+ *                         E/dataset/dataset.py:131-145 with max_scene_depth = max depth over mask>0 + delta); scratch: N ints
+ *   mfb_post_image_u8   : fp32 NCHW in [-1,1] -> uint8 HWC                  (VaeImageProcessor.postprocess) */
+int mfb_prep_image_u8(const void* rgb_hwc, int N, int H, int W, float* out_nchw, void* stream);
+int mfb_prep_mask_depth(const void* mask_u8, const float* depth, int N, int H, int W, int factor, float delta, float* mask_lat,
+                        float* depth_lat, int* scratch_n_ints, void* stream);
+int mfb_post_image_u8(const float* img_nchw, int N, int H, int W, void* out_hwc, void* stream);
+
 /* Latent sample of DiagonalGaussianDistribution (S/models/autoencoders/vae.py:769-791) times a scale:
  * out = scale * (mean + exp(0.5 * clamp(logvar, -30, 20)) * noise); noise == NULL gives the mode (scale * mean).  fp32, n elements. */
 int mfb_latent_sample(const float* mean, const float* logvar, const float* noise, float scale, float* out, long long n,

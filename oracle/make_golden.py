@@ -232,6 +232,42 @@ def golden_checkpoint_layout(diffusers, name="micro_checkpoint_layout.json"):
     print(f"{name}: {len(out['unet']['tensors'])} + {len(out['brushnet']['tensors'])} tensors; loader verified on the reference's files")
 
 
+def golden_prep(diffusers, name="prep_golden.npz"):
+    """Input / output processing by the reference's OWN functions: VaeImageProcessor.preprocess on PIL images (as
+    E/test_brushnet.py passes them), the mask rule + F.interpolate of pipeline_brushnet.py:1139,1190-1202,
+    HDF5Dataset.apply_transforms_depth (its source is exec'd standalone: the module itself imports h5py, which is not
+    installed), VaeImageProcessor.postprocess."""
+    import ast
+    import torch.nn.functional as F
+    from PIL import Image
+    from torchvision import transforms
+    from diffusers.image_processor import VaeImageProcessor
+    rng = np.random.default_rng(5)
+    N, S, f = 2, 64, 8
+    rgb = rng.integers(0, 256, (N, S, S, 3), dtype=np.uint8)
+    mask = np.zeros((N, S, S), np.uint8)
+    mask[0, 10:40, 20:50] = 255
+    mask[1, 5:30, 3:33] = 255
+    depth = (rng.random((N, S, S), dtype=np.float32) * 6.0 + 0.2).astype(np.float32)
+    proc = VaeImageProcessor(vae_scale_factor=f, do_convert_rgb=True)                     # pipeline_brushnet.py:230
+    img_t = torch.cat([proc.preprocess(Image.fromarray(rgb[i]), height=S, width=S) for i in range(N)])
+    m_t = torch.cat([proc.preprocess(Image.fromarray(mask[i]).convert("RGB"), height=S, width=S) for i in range(N)])
+    m1 = (m_t.sum(1)[:, None] < 0).to(img_t.dtype)                                         # :1139
+    m_lat = F.interpolate(m1, size=(S // f, S // f))                                       # :1190-1196
+    src = open("/root/reference/MirrorFusion/examples/brushnet/dataset/dataset.py").read()
+    fn = next(n for n in ast.walk(ast.parse(src)) if isinstance(n, ast.FunctionDef) and n.name == "apply_transforms_depth")
+    fn.decorator_list = []
+    ns = {"np": np, "torch": torch, "transforms": transforms}
+    exec(compile(ast.Module(body=[fn], type_ignores=[]), "dataset.py", "exec"), ns)
+    d_t = torch.stack([ns["apply_transforms_depth"](depth[i], mask[i], resolution=S) for i in range(N)])   # [N,1,S,S]
+    d_lat = F.interpolate(d_t, size=(S // f, S // f))                                      # :1198-1202
+    dec = torch.randn(N, 3, S, S, generator=torch.Generator().manual_seed(3)) * 0.8
+    out_u8 = (proc.postprocess(dec, output_type="np") * 255).round().astype(np.uint8)      # numpy_to_pil's rounding
+    np.savez_compressed(os.path.join(GOLD, name), rgb=rgb, mask=mask, depth=depth, image=img_t.numpy(), mask_lat=m_lat.numpy(),
+                        depth_lat=d_lat.numpy(), decoded=dec.numpy(), out_u8=out_u8, factor=f)
+    print(f"{name}: image {tuple(img_t.shape)}, mask_lat {tuple(m_lat.shape)} (sum {m_lat.sum().item():.0f}), depth_lat {tuple(d_lat.shape)}")
+
+
 def golden_signatures(diffusers, name):
     """Parameter names (in order) of the reference entry points the drop-in classes mirror."""
     import inspect
@@ -270,6 +306,8 @@ def main():
         golden_psnr(diffusers)
     if "vae" in which:
         golden_vae_decode(diffusers)
+    if "prep" in which:
+        golden_prep(diffusers)
     if "ckpt" in which:
         golden_checkpoint_layout(diffusers)
     if "sigs" in which:

@@ -482,6 +482,95 @@ extern "C" int mfb_linear_small(const float* x, int M, int K, const void* w, con
     return MFB_OK;
 }
 
+// ---------------------------------------------------------------------------------------------- SynMirror input preprocessing
+// The eval sweep's per-image host work of the reference (PIL + numpy + torchvision, E/test_brushnet.py:186-226,
+// S/pipelines/brushnet/pipeline_brushnet.py:741-774,1116-1202, E/dataset/dataset.py:98-145) as three small kernels on
+// uint8 / fp32 arrays that are already at the target resolution.
+namespace mfb {
+// uint8 HWC RGB -> fp32 NCHW in [-1, 1]  (VaeImageProcessor.preprocess: /255 then 2x - 1)
+__global__ void prep_image_kernel(const uint8_t* __restrict__ in, int H, int W, float* __restrict__ out, long long npix) {
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;      // pixel index over N*H*W
+    if (i >= npix) return;
+    const long long n = i / (static_cast<long long>(H) * W), p = i % (static_cast<long long>(H) * W);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) out[(n * 3 + c) * H * W + p] = 2.0f * (static_cast<float>(in[i * 3 + c]) / 255.0f) - 1.0f;
+}
+// per image: max of depth over the pixels with mask > 0 (non-negative depths: the int ordering of the bit patterns is the float one)
+__global__ void depth_max_kernel(const float* __restrict__ depth, const uint8_t* __restrict__ mask, long long hw, int* __restrict__ maxbits) {
+    const int n = blockIdx.y;
+    float m = 0.f;
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < hw; i += static_cast<long long>(gridDim.x) * blockDim.x)
+        if (mask[n * hw + i] > 0) m = fmaxf(m, depth[n * hw + i]);
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(maxbits + n, __float_as_int(m));
+}
+// latent-resolution mask and depth: nearest sampling at (f*i, f*j) (F.interpolate default mode, pipeline_brushnet.py:1190-1202);
+// mask_lat = 1 where the (3-channel, [-1,1]-normalised) mask sums below 0, i.e. where the uint8 mask is < 127.5 (:1139);
+// depth_lat = 2 * clip(d, 0, dmax) / dmax - 1 with dmax = max depth over the mask + delta (dataset.py:131-145)
+__global__ void prep_mask_depth_kernel(const uint8_t* __restrict__ mask, const float* __restrict__ depth, int H, int W, int f,
+                                       const int* __restrict__ maxbits, float delta, float* __restrict__ mask_lat,
+                                       float* __restrict__ depth_lat, long long nlat) {
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= nlat) return;
+    const int h = H / f, w = W / f;
+    const long long n = i / (h * w);
+    const int y = (i / w) % h, x = i % w;
+    const long long src = (n * H + static_cast<long long>(y) * f) * W + static_cast<long long>(x) * f;
+    mask_lat[i] = mask[src] < 128 ? 1.0f : 0.0f;
+    if (depth) {
+        const float dmax = __int_as_float(maxbits[n]) + delta;
+        depth_lat[i] = 2.0f * (fminf(fmaxf(depth[src], 0.0f), dmax) / dmax) - 1.0f;
+    }
+}
+// fp32 NCHW in [-1, 1] -> uint8 HWC  (VaeImageProcessor.postprocess: (x / 2 + 0.5).clamp(0, 1), then (255 x).round())
+__global__ void post_image_kernel(const float* __restrict__ in, int H, int W, uint8_t* __restrict__ out, long long npix) {
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= npix) return;
+    const long long n = i / (static_cast<long long>(H) * W), p = i % (static_cast<long long>(H) * W);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const float v = fminf(fmaxf(in[(n * 3 + c) * H * W + p] * 0.5f + 0.5f, 0.0f), 1.0f);
+        out[i * 3 + c] = static_cast<uint8_t>(rintf(v * 255.0f));
+    }
+}
+}  // namespace mfb
+
+extern "C" int mfb_prep_image_u8(const void* rgb_hwc, int N, int H, int W, float* out_nchw, void* stream) {
+    MFB_REQUIRE(rgb_hwc && out_nchw && N > 0 && H > 0 && W > 0, "bad arguments");
+    const long long npix = static_cast<long long>(N) * H * W;
+    prep_image_kernel<<<unsigned((npix + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const uint8_t*>(rgb_hwc), H, W,
+                                                                                                  out_nchw, npix);
+    MFB_CUDA_OK(cudaGetLastError());
+    return MFB_OK;
+}
+
+extern "C" int mfb_prep_mask_depth(const void* mask_u8, const float* depth, int N, int H, int W, int factor, float delta,
+                                   float* mask_lat, float* depth_lat, int* scratch_n_ints, void* stream) {
+    MFB_REQUIRE(mask_u8 && mask_lat && N > 0 && factor > 0 && H % factor == 0 && W % factor == 0, "bad arguments");
+    MFB_REQUIRE(!depth || (depth_lat && scratch_n_ints), "depth needs depth_lat and an N-int scratch buffer");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const long long hw = static_cast<long long>(H) * W;
+    if (depth) {
+        MFB_CUDA_OK(cudaMemsetAsync(scratch_n_ints, 0, sizeof(int) * N, st));
+        depth_max_kernel<<<dim3(64, N), 256, 0, st>>>(depth, static_cast<const uint8_t*>(mask_u8), hw, scratch_n_ints);
+        MFB_CUDA_OK(cudaGetLastError());
+    }
+    const long long nlat = static_cast<long long>(N) * (H / factor) * (W / factor);
+    prep_mask_depth_kernel<<<unsigned((nlat + 255) / 256), 256, 0, st>>>(static_cast<const uint8_t*>(mask_u8), depth, H, W, factor,
+                                                                        scratch_n_ints, delta, mask_lat, depth_lat, nlat);
+    MFB_CUDA_OK(cudaGetLastError());
+    return MFB_OK;
+}
+
+extern "C" int mfb_post_image_u8(const float* img_nchw, int N, int H, int W, void* out_hwc, void* stream) {
+    MFB_REQUIRE(img_nchw && out_hwc && N > 0, "bad arguments");
+    const long long npix = static_cast<long long>(N) * H * W;
+    post_image_kernel<<<unsigned((npix + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(img_nchw, H, W,
+                                                                                                  static_cast<uint8_t*>(out_hwc), npix);
+    MFB_CUDA_OK(cudaGetLastError());
+    return MFB_OK;
+}
+
 namespace mfb {
 __global__ void latent_sample_kernel(const float* __restrict__ mean, const float* __restrict__ logvar, const float* __restrict__ noise,
                                      float scale, float* __restrict__ out, long long n) {

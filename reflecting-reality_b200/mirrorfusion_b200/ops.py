@@ -294,6 +294,25 @@ def linear_small(x, w, b, y, act_in=False, act_out=False):
     check(fn(_ptr(x), M, K, _ptr(w), _ptr(b), w.shape[0], int(act_in), int(act_out), _ptr(y), _stream()))
 
 
+def prep_image_u8(rgb_hwc, out_nchw):
+    """uint8 [N,H,W,3] -> fp32 [N,3,H,W] in [-1,1]."""
+    N, H, W, _ = rgb_hwc.shape
+    check(lib().mfb_prep_image_u8(_ptr(rgb_hwc), N, H, W, _ptr(out_nchw), _stream()))
+
+
+def prep_mask_depth(mask_u8, depth, mask_lat, depth_lat, scratch, factor=8, delta=0.5):
+    """uint8 mask [N,H,W] (+ metric depth fp32 [N,H,W]) -> latent-resolution mask {0,1} / depth [-1,1] ([N,1,H/f,W/f] fp32)."""
+    N, H, W = mask_u8.shape
+    check(lib().mfb_prep_mask_depth(_ptr(mask_u8), _ptr(depth), N, H, W, factor, float(delta), _ptr(mask_lat), _ptr(depth_lat),
+                                    _ptr(scratch), _stream()))
+
+
+def post_image_u8(img_nchw, out_hwc):
+    """fp32 [N,3,H,W] in [-1,1] -> uint8 [N,H,W,3]."""
+    N, _, H, W = img_nchw.shape
+    check(lib().mfb_post_image_u8(_ptr(img_nchw), N, H, W, _ptr(out_hwc), _stream()))
+
+
 def latent_sample(mean, logvar, noise, scale, out):
     """out = scale * (mean + exp(0.5 * clamp(logvar)) * noise); noise=None -> the mode.  All fp32."""
     check(lib().mfb_latent_sample(_ptr(mean), _ptr(logvar), _ptr(noise), float(scale), _ptr(out), mean.numel(), _stream()))

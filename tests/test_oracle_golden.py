@@ -151,3 +151,15 @@ def test_vae_encode_oracle_matches_reference_golden(golden_dir):
     assert rel(latent_sample(mean, logvar, torch.from_numpy(g["noise"])), g["sample"]) < 1e-5
     # encoder + quant_conv of the SD VAE: 34 163 592 + 72 parameters
     assert sum(int(np.prod(s)) for _, s in vae_encoder_param_shapes(SD_VAE)) == 34_163_664
+
+
+def test_prep_oracle_matches_reference_functions(golden_dir):
+    """oracle/prep_oracle.py against VaeImageProcessor.preprocess / postprocess, the mask rule + F.interpolate of the pipeline
+    and HDF5Dataset.apply_transforms_depth, all run by oracle/make_golden.py from the reference's own code."""
+    from oracle import prep_oracle as PO
+    g = _load(golden_dir, "prep_golden.npz")
+    f = int(g["factor"])
+    assert np.abs(PO.prep_image(g["rgb"]) - g["image"]).max() < 1e-6
+    assert np.array_equal(PO.prep_mask(g["mask"], f), g["mask_lat"])
+    assert np.abs(PO.prep_depth(g["depth"], g["mask"], f) - g["depth_lat"]).max() < 1e-6
+    assert np.array_equal(PO.post_image(g["decoded"]), g["out_u8"])
