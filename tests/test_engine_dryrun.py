@@ -12,7 +12,7 @@ from mirrorfusion_b200.config import SD15, TINY, param_shapes
 
 class FakePlan:
     def __init__(self, x, w, out, *, B, H, W, Cin, Cout, ksize=1, stride=1, extras=(), bias=None, rowbias=None,
-                 rowbias_ld=0, alpha=None, res1=None, res2=None, geglu=False, block_n=0, igemm_mode=0, up2x=False):
+                 rowbias_ld=0, alpha=None, res1=None, res2=None, geglu=False, block_n=0, igemm_mode=0, up2x=False, pad0=False):
         Ho, Wo = (H, W) if stride == 1 else ((H - 1) // 2 + 1, (W - 1) // 2 + 1)
         if up2x:
             Ho, Wo = 2 * H, 2 * W
@@ -35,7 +35,7 @@ class FakePlan:
             assert bias.numel() == Cout
         if rowbias is not None:
             assert rowbias.shape[0] == B and rowbias.shape[1] >= Cout and rowbias_ld >= Cout
-        self.flops = 2.0 * M * Cout * ktot
+        self.flops = 2.0 * M * Cout * ((9 * Cin + ext) if up2x else ktot)      # algorithmic: 3x3 over the upsampled tensor
         self.kind = (ksize, stride, len(extras), res1 is not None, res2 is not None)
 
     def run(self):
@@ -54,7 +54,8 @@ def stub_ops(monkeypatch):
     monkeypatch.setattr(real_ops, "linear_plan",
                         lambda x, w, out, **kw: FakePlan(x, w, out, B=1, H=1, W=x.shape[0], Cin=x.shape[1], Cout=w.shape[0], **kw))
     for name in ("groupnorm", "layernorm", "attention", "transpose_tokens", "conv_in", "conv_out", "upsample2x",
-                 "nchw_to_nhwc", "nhwc_to_nchw", "f32_to_bf16", "timestep_sinusoid", "linear_small", "cfg_sched_step"):
+                 "nchw_to_nhwc", "nhwc_to_nchw", "f32_to_bf16", "timestep_sinusoid", "linear_small", "cfg_sched_step",
+                 "softmax_rows", "latent_sample", "prep_image_u8", "prep_mask_depth", "post_image_u8"):
         monkeypatch.setattr(real_ops, name, (lambda n: (lambda *a, **k: calls.append(n)))(name))
     return calls
 
@@ -108,3 +109,22 @@ def test_tiny_program_builds_for_odd_batches(stub_ops):
         un = UNetEngine(TINY, _meta_sd(TINY, "unet"), B, 16, 16, "cpu")
         BrushNetEngine(TINY, _meta_sd(TINY, "brushnet"), B, 16, 16, "cpu", tap_bufs=un.taps)
         assert un.launches > 300
+
+
+def test_sd_vae_programs_flop_census(stub_ops):
+    """AutoencoderKL decode / encode programs at 512x512 (~1.24 TFLOP per decode, ~0.56 per encode),
+    the d = 512 mid-block attention as two GEMMs per image around the row softmax, pad0 stride-2 convs in the encoder."""
+    from mirrorfusion_b200.vae import SD_VAE, VaeDecoderEngine, VaeEncoderEngine, vae_decoder_param_shapes, vae_encoder_param_shapes
+    sd = {k: torch.zeros(s) for k, s in vae_decoder_param_shapes(SD_VAE) + vae_encoder_param_shapes(SD_VAE)}
+    B = 2
+    dec = VaeDecoderEngine(SD_VAE, sd, B, 64, 64, "cpu")
+    enc = VaeEncoderEngine(SD_VAE, sd, B, 512, 512, "cpu")
+    print("decode", dec.flops / B, "encode", enc.flops / B)
+    # 2*M*N*K census (incl. the attention GEMMs): SURVEY's "~1.24 TF decode / ~0.56 TF encode" are multiply-accumulates
+    assert abs(dec.flops / B - 2 * 1.24e12) / (2 * 1.24e12) < 0.03
+    assert abs(enc.flops / B - 2 * 0.56e12) / (2 * 0.56e12) < 0.05
+    assert tuple(dec.out.shape) == (B, 3, 512, 512) and tuple(enc.mean.shape) == (B, 4, 64, 64)
+    dec.run(); enc.run()
+    assert stub_ops.count("softmax_rows") == 2 * B and stub_ops.count("attention") == 0 and stub_ops.count("conv_out") == 1 + 2
+    assert sum(1 for p in enc.keep if isinstance(p, FakePlan) and p.kind[1] == 2) == 3
+    assert sum(1 for p in dec.keep if isinstance(p, FakePlan) and p.launches == 4) == 3
