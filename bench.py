@@ -312,7 +312,7 @@ def run_ours(args, rank, world, local_rank):
             r = fam.setdefault(k, [0.0, 0.0, 0])
             r[0] += t_ms; r[1] += fl; r[2] += n
     traffic, traffic_src = None, None
-    tp = os.path.join(ROOT, "profiles", "r01m_igemm_traffic.json")     # from the committed ncu --set full capture
+    tp = os.path.join(ROOT, "profiles", "r01o_igemm_traffic.json")     # from the committed ncu --set full capture
     if os.path.exists(tp):
         with open(tp) as f:
             tj = json.load(f)
