@@ -32,7 +32,7 @@ f32 = torch.float32
 class _Net:
     def __init__(self, cfg: NetConfig, sd: Dict[str, torch.Tensor], B: int, H: int, W: int, device, name: str):
         self.cfg, self.B, self.H, self.W, self.dev, self.name = cfg, B, H, W, device, name
-        self.act = ops.act_dtype()     # storage dtype: self.act (product) or fp32 (parity mode, `with ops.precision('fp32')`)
+        self.act = ops.act_dtype()     # storage dtype: bf16 (product) or fp32 (parity mode, `with ops.precision('fp32')`)
         self.sd = {k: v.detach().to(device=device, dtype=f32) for k, v in sd.items()}
         self.prog: List[Callable[[], None]] = []
         self.tags: List[Tuple[str, float]] = []       # (kernel family, algorithmic FLOPs) per program entry
