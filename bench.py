@@ -417,8 +417,9 @@ def main():
     ap.add_argument("--two-streams", action="store_true", help="BrushNet on a side stream with per-tap events (measured neutral)")
     ap.add_argument("--dedup-brushnet", action="store_true",
                     help="run the whole bench with the opt-in BrushNet CFG de-duplication (flagged in config)")
-    ap.add_argument("--report-dedup", action="store_true",
-                    help="additionally time the de-duplicated engine and report it as the secondary key brushnet_cfg_dedup")
+    ap.add_argument("--report-dedup", action=argparse.BooleanOptionalAction, default=True,
+                    help="also time the exact BrushNet CFG de-duplication and report it as the SECONDARY key brushnet_cfg_dedup "
+                         "(never the headline value); --no-report-dedup skips it")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-vae", action="store_true", help="skip the secondary VAE-decode measurement")
     args = ap.parse_args()
