@@ -431,6 +431,65 @@ __global__ void layernorm_kernel(const __nv_bfloat16* __restrict__ x, int rows, 
     }
 }
 
+// Rows of exactly 5 * L sixteen-byte vectors (C = 320 / 640 for L = 8 / 16 — the LayerNorms of the two large SD1.5
+// transformer levels): L lanes share a row, each lane owns 5 vectors, so a warp normalises 32 / L rows at once with every
+// lane busy and all 5 loads of a lane in flight together (C = 320: 2.5 KB in flight per warp instead of 640 B with 62 % of
+// the lanes loading, and a quarter of the CTAs).  Same two-pass arithmetic as layernorm_kernel.
+template <int L>
+__global__ void __launch_bounds__(256) layernorm5_kernel(const __nv_bfloat16* __restrict__ x, int rows, float eps,
+                                                         const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                         __nv_bfloat16* __restrict__ out) {
+    constexpr int RPW = 32 / L, C = L * 40;
+    const int lane = threadIdx.x & 31, sub = lane % L;
+    const int row = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * RPW + lane / L;
+    pdl_trigger();
+    pdl_wait();
+    const bool ok = row < rows;
+    const __nv_bfloat16* src = x + static_cast<size_t>(ok ? row : rows - 1) * C;
+    uint4 u[5];
+#pragma unroll
+    for (int i = 0; i < 5; ++i) u[i] = __ldg(reinterpret_cast<const uint4*>(src + (sub + L * i) * 8));
+    float f[5][8];
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+        unpack8(u[i], f[i]);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) sum += f[i][e];
+    }
+#pragma unroll
+    for (int o = L / 2; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float mean = sum / C;
+    float var = 0.f;
+#pragma unroll
+    for (int i = 0; i < 5; ++i)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { const float d = f[i][e] - mean; var = fmaf(d, d, var); }
+#pragma unroll
+    for (int o = L / 2; o > 0; o >>= 1) var += __shfl_xor_sync(0xffffffffu, var, o);
+    const float rstd = rsqrtf(var / C + eps);
+    if (!ok) return;
+    __nv_bfloat16* dst = out + static_cast<size_t>(row) * C;
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+        const int v = sub + L * i;
+        const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + v * 8));
+        const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + v * 8 + 4));
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + v * 8));
+        const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta + v * 8 + 4));
+        float y[8];
+        y[0] = (f[i][0] - mean) * rstd * g0.x + b0.x;
+        y[1] = (f[i][1] - mean) * rstd * g0.y + b0.y;
+        y[2] = (f[i][2] - mean) * rstd * g0.z + b0.z;
+        y[3] = (f[i][3] - mean) * rstd * g0.w + b0.w;
+        y[4] = (f[i][4] - mean) * rstd * g1.x + b1.x;
+        y[5] = (f[i][5] - mean) * rstd * g1.y + b1.y;
+        y[6] = (f[i][6] - mean) * rstd * g1.z + b1.z;
+        y[7] = (f[i][7] - mean) * rstd * g1.w + b1.w;
+        *reinterpret_cast<uint4*>(dst + v * 8) = pack8(y);
+    }
+}
+
 }  // namespace mfb
 
 using namespace mfb;
@@ -591,6 +650,16 @@ extern "C" int mfb_layernorm(const void* x, int rows, int C, float eps, const fl
     const int nv = (C / 8 + 31) / 32;
     auto X = static_cast<const __nv_bfloat16*>(x);
     auto O = static_cast<__nv_bfloat16*>(out);
+    static const bool use5 = [] { const char* e = getenv("MFB_LN5"); return !e || atoi(e) != 0; }();
+    // several rows per warp for the narrow rows (measured, tools/bench_ln.py, B200: C = 320 20.9 -> 17.6 us per 42 MB tensor,
+    // C = 640 11.3 -> 10.5 us; at C = 1280 a warp already owns one full row and the old kernel is faster: 6.4 vs 7.3 us)
+    if (use5 && (C == 320 || C == 640)) {
+        const int L = C / 40, rpw = 32 / L;
+        dim3 g5((rows + warps * rpw - 1) / (warps * rpw));
+        if (L == 8) MFB_CUDA_OK(launch_k(layernorm5_kernel<8>, g5, block, 0, st, 1, X, rows, eps, gamma, beta, O));
+        else MFB_CUDA_OK(launch_k(layernorm5_kernel<16>, g5, block, 0, st, 1, X, rows, eps, gamma, beta, O));
+        return MFB_OK;
+    }
     if (nv <= 2) MFB_CUDA_OK(launch_k(layernorm_kernel<2>, grid, block, 0, st, 1, X, rows, C, eps, gamma, beta, O));
     else if (nv <= 5) MFB_CUDA_OK(launch_k(layernorm_kernel<5>, grid, block, 0, st, 1, X, rows, C, eps, gamma, beta, O));
     else MFB_CUDA_OK(launch_k(layernorm_kernel<8>, grid, block, 0, st, 1, X, rows, C, eps, gamma, beta, O));

@@ -242,7 +242,7 @@ def test_groupnorm_with_statistics_from_the_conv_epilogue(ops, B, H, W, Cin, Cou
     assert rel(y_fused.float(), ref) < 4e-3 and rel(y_fused.float(), y_plain.float()) < 2e-3
 
 
-@pytest.mark.parametrize("rows,C", [(8192, 320), (2048, 640), (513, 1280), (64, 64), (100, 128)])
+@pytest.mark.parametrize("rows,C", [(8192, 320), (2048, 640), (513, 1280), (1001, 320), (515, 640), (64, 64), (100, 128)])
 def test_layernorm(ops, rows, C):
     x = randn(rows, C, seed=1) * 2 + 0.3
     gamma = 1 + 0.1 * randn(C, seed=2, dtype=torch.float32)
