@@ -399,3 +399,29 @@ def test_cfg_sched_kernel(ops):
     m0_old = m0.clone()
     ops.cfg_sched_step(eps[:Bi], eps[Bi:], x, last, m0, m1, coef)
     assert rel(x, xn) < 1e-6 and rel(last, xc) < 1e-6 and rel(m0, mt) < 1e-6 and torch.equal(m1, m0_old)
+
+
+@pytest.mark.parametrize("B,Cin,with_res,with_extra", [(16, 1280, True, False), (16, 2560, False, True), (2, 1280, False, False)])
+def test_conv3x3_8x8_level_long_k(ops, B, Cin, with_res, with_extra):
+    # the 8x8 latent level: 8 M tiles (or 1), K = 11520 .. 24320 with a residual or an extra 1x1 segment; run twice (plans are
+    # replayed from a CUDA graph: nothing may depend on state left by the previous launch)
+    H = W = 8
+    Cout = 1280
+    x = randn(B, H, W, Cin, seed=31)
+    w = randn(Cout, Cin, 3, 3, seed=32, dtype=torch.float32) * (Cin * 9) ** -0.5
+    bias = 0.1 * randn(Cout, seed=33, dtype=torch.float32)
+    res = randn(B, H, W, Cout, seed=34) if with_res else None
+    ex = randn(B, H, W, 1280, seed=35) if with_extra else None
+    wex = (randn(Cout, 1280, seed=36, dtype=torch.float32) * 1280 ** -0.5) if with_extra else None
+    out = torch.full((B, H, W, Cout), float("nan"), device="cuda", dtype=bf16)
+    plan = ops.ConvPlan(x, ops.pack_conv_weight(w, extras=[wex] if with_extra else []), out, B=B, H=H, W=W, Cin=Cin, Cout=Cout, ksize=3,
+                        extras=[ex] if with_extra else [], bias=bias, res1=res)
+    ref = F.conv2d(nhwc_to_nchw(x), w.to(bf16).float(), bias, padding=1)
+    if with_extra:
+        ref = ref + F.conv2d(nhwc_to_nchw(ex), wex.to(bf16).float()[:, :, None, None])
+    if with_res:
+        ref = ref + nhwc_to_nchw(res)
+    for _ in range(2):
+        out.fill_(float("nan"))
+        plan.run()
+        assert rel(nhwc_to_nchw(out), ref) < 5e-3
