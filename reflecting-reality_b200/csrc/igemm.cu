@@ -510,10 +510,14 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 1) igemm_kernel(const __grid_co
                             *reinterpret_cast<float4*>(bg) = *reinterpret_cast<const float4*>(sb + 64 + col + j * 8);
                             *reinterpret_cast<float4*>(bg + 4) = *reinterpret_cast<const float4*>(sb + 64 + col + j * 8 + 4);
 #pragma unroll
-                            for (int e = 0; e < 8; ++e) {
-                                const float val = __uint_as_float(v[c][j * 8 + e]) + bv[e];
-                                const float gate = __uint_as_float(g[c][j * 8 + e]) + bg[e];
-                                f[e] = val * gelu_erf_f(gate);
+                            for (int e = 0; e < 8; e += 2) {       // pairwise: FADD2 / FFMA2 / FMUL2 (half the issue slots)
+                                const float2 val = fadd2(make_float2(__uint_as_float(v[c][j * 8 + e]), __uint_as_float(v[c][j * 8 + e + 1])),
+                                                         make_float2(bv[e], bv[e + 1]));
+                                const float2 gate = fadd2(make_float2(__uint_as_float(g[c][j * 8 + e]), __uint_as_float(g[c][j * 8 + e + 1])),
+                                                          make_float2(bg[e], bg[e + 1]));
+                                const float2 o = fmul2(val, gelu_erf_f2(gate));
+                                f[e] = o.x;
+                                f[e + 1] = o.y;
                             }
                             *reinterpret_cast<uint4*>(stg_g + stg_off<BOXC>(r, col + j * 8)) = pack_bf16x8(f);
                         }

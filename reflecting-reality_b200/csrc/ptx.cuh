@@ -369,4 +369,46 @@ __device__ __forceinline__ float gelu_erf_f(float x) {
     return x * phi;
 }
 
+// ------------------------------------------------------------------ packed fp32 pairs (FFMA2 / FADD2 / FMUL2 on sm_100)
+// One instruction, two independent fp32 lanes (PTX fma.rn.f32x2 & co.): halves the issue slots of straight-line fp32
+// math.  Used where an epilogue is bound by instruction issue / dependent-FMA latency with only two warps per scheduler
+// (the GEGLU epilogue of the K = 320 projection: ncu r01p, issue-active 45 %, tensor pipe 41 %).
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+    float2 d;
+    asm("{ .reg .b64 ra, rb, rc, rd;\n mov.b64 ra, {%2, %3};\n mov.b64 rb, {%4, %5};\n mov.b64 rc, {%6, %7};\n"
+        " fma.rn.f32x2 rd, ra, rb, rc;\n mov.b64 {%0, %1}, rd; }"
+        : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+    return d;
+}
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
+    float2 d;
+    asm("{ .reg .b64 ra, rb, rd;\n mov.b64 ra, {%2, %3};\n mov.b64 rb, {%4, %5};\n add.rn.f32x2 rd, ra, rb;\n mov.b64 {%0, %1}, rd; }"
+        : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return d;
+}
+__device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
+    float2 d;
+    asm("{ .reg .b64 ra, rb, rd;\n mov.b64 ra, {%2, %3};\n mov.b64 rb, {%4, %5};\n mul.rn.f32x2 rd, ra, rb;\n mov.b64 {%0, %1}, rd; }"
+        : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return d;
+}
+// gelu_erf_f on two values at once: same polynomial, same results bit for bit (every operation is the same IEEE fma /
+// add / mul, only issued pairwise)
+__device__ __forceinline__ float2 gelu_erf_f2(float2 x) {
+    const float2 a = make_float2(fminf(fabsf(x.x), 6.0f), fminf(fabsf(x.y), 6.0f));
+    auto bc = [](float c) { return make_float2(c, c); };
+    float2 l = ffma2(bc(1.889626219e-06f), a, bc(-6.268139987e-05f));
+    l = ffma2(l, a, bc(9.388679173e-04f));
+    l = ffma2(l, a, bc(-8.539461531e-03f));
+    l = ffma2(l, a, bc(5.402068794e-02f));
+    l = ffma2(l, a, bc(4.584097862e-01f));
+    l = ffma2(l, a, bc(1.151269197e+00f));
+    l = ffma2(l, a, bc(9.999943376e-01f));
+    float e0, e1;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(-l.x));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(-l.y));
+    const float2 phi = make_float2(x.x < 0.f ? e0 : 1.0f - e0, x.y < 0.f ? e1 : 1.0f - e1);
+    return fmul2(x, phi);
+}
+
 }  // namespace mfb
