@@ -35,7 +35,12 @@ namespace mfb {
 constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int MAX_SEG = 16;
-constexpr int IGEMM_EPI_WARPS = 8;
+#ifndef MFB_IGEMM_EPI_WARPS     // epilogue warps per CTA: 8 or 16 (4 TMEM lane quarters x 2 or 4 column groups)
+#define MFB_IGEMM_EPI_WARPS 8
+#endif
+constexpr int IGEMM_EPI_WARPS = MFB_IGEMM_EPI_WARPS;
+constexpr int IGEMM_COL_GROUPS = IGEMM_EPI_WARPS / 4;
+static_assert(IGEMM_EPI_WARPS == 8 || IGEMM_EPI_WARPS == 16, "8 or 16 epilogue warps");
 constexpr int IGEMM_THREADS = 64 + 32 * IGEMM_EPI_WARPS;
 
 struct IgemmSeg {
@@ -340,7 +345,7 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 1) igemm_kernel(const __grid_co
         // the epilogue except the rare res2 is therefore full-line TMA traffic, and M/N tails are clipped by TMA.
         constexpr int BOXC = Cfg::BOXC;
         const int q = warp & 3;
-        const int half = warp >> 2;
+        const int half = warp >> 2;          // column group of this warp: 0 .. IGEMM_COL_GROUPS-1 (named for the 2-group layout)
         const bool leader = (warp == 0 && lane == 0);
         const int r = q * 32 + lane;  // row of the tile == TMEM lane
         const int rw = r % p.tw;
@@ -435,10 +440,12 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 1) igemm_kernel(const __grid_co
             };
 
             if (!p.geglu) {
-                constexpr int NCH = BN / 16;                 // 16-column chunks; warp `half` 0 takes the first ceil(NCH/2)
-                constexpr int MAXC = (NCH + 1) / 2;
-                const int c_begin = half ? MAXC : 0;
-                const int c_cnt = half ? NCH - MAXC : MAXC;
+                constexpr int NCH = BN / 16;                 // 16-column chunks, dealt to the column groups as evenly as possible
+                constexpr int NG = IGEMM_COL_GROUPS;
+                constexpr int MAXC = (NCH + NG - 1) / NG;
+                constexpr int CBASE = NCH / NG, CREM = NCH % NG;
+                const int c_begin = half * CBASE + (half < CREM ? half : CREM);
+                const int c_cnt = CBASE + (half < CREM ? 1 : 0);
                 mbar_wait_relaxed(tmem_full_bar(as), (li >> 1) & 1);
                 tc_fence_after();
                 // fetch this warp's whole accumulator slice with back-to-back tcgen05.ld and ONE wait
@@ -492,16 +499,17 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 1) igemm_kernel(const __grid_co
                 if constexpr (BN == 128) {
                     mbar_wait_relaxed(tmem_full_bar(as), (li >> 1) & 1);
                     tc_fence_after();
-                    uint32_t v[2][16], g[2][16];
+                    constexpr int GC = 4 / IGEMM_COL_GROUPS;                 // 16-column value chunks per column group
+                    uint32_t v[GC][16], g[GC][16];
 #pragma unroll
-                    for (int c = 0; c < 2; ++c) {
-                        tmem_ld16(trow + half * 32 + c * 16, v[c]);        // value columns; gate = +64
-                        tmem_ld16(trow + 64 + half * 32 + c * 16, g[c]);
+                    for (int c = 0; c < GC; ++c) {
+                        tmem_ld16(trow + half * (GC * 16) + c * 16, v[c]);        // value columns; gate = +64
+                        tmem_ld16(trow + 64 + half * (GC * 16) + c * 16, g[c]);
                     }
                     release_acc();
 #pragma unroll
-                    for (int c = 0; c < 2; ++c) {
-                        const int col = half * 32 + c * 16;
+                    for (int c = 0; c < GC; ++c) {
+                        const int col = half * (GC * 16) + c * 16;
 #pragma unroll
                         for (int j = 0; j < 2; ++j) {
                             float f[8], bv[8], bg[8];
