@@ -35,13 +35,9 @@ namespace mfb {
 constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int MAX_SEG = 16;
-#ifndef MFB_IGEMM_EPI_WARPS     // epilogue warps per CTA: 8 or 16 (4 TMEM lane quarters x 2 or 4 column groups)
-#define MFB_IGEMM_EPI_WARPS 8
-#endif
-constexpr int IGEMM_EPI_WARPS = MFB_IGEMM_EPI_WARPS;
-constexpr int IGEMM_COL_GROUPS = IGEMM_EPI_WARPS / 4;
-static_assert(IGEMM_EPI_WARPS == 8 || IGEMM_EPI_WARPS == 16, "8 or 16 epilogue warps");
-constexpr int IGEMM_THREADS = 64 + 32 * IGEMM_EPI_WARPS;
+// Epilogue warps per CTA (kernel template parameter EPIW): 8 or 16 = 4 TMEM lane quarters x 2 or 4 column groups.  16 halves
+// the per-tile epilogue latency (short-K and 8x8-level launches: 5-11 % faster) at the price of 96 registers per thread
+// (long-K convs: 0.5-1.5 % slower), so the plan picks it per launch (profiles/r01o_igemm_double_staging.md).
 
 struct IgemmSeg {
     int map;      // which A tensor map
@@ -177,9 +173,11 @@ struct TileIter {
 // assembled in the other buffer, and the residual tile of tile i+1 is prefetched into that buffer one whole tile ahead, so
 // the per-tile chain "previous store drained -> residual loaded -> TMEM load -> math -> store" loses its two TMA latencies.
 // The ring gives up one staging tile's worth of stages for it.
-template <int BN, int MODE>
-__global__ void __launch_bounds__(IGEMM_THREADS, 1) igemm_kernel(const __grid_constant__ IgemmParams p) {
+template <int BN, int MODE, int EPIW>
+__global__ void __launch_bounds__(64 + 32 * EPIW, 1) igemm_kernel(const __grid_constant__ IgemmParams p) {
     using Cfg = IgemmCfg<BN>;
+    static_assert(EPIW == 8 || EPIW == 16, "8 or 16 epilogue warps");
+    constexpr int IGEMM_EPI_WARPS = EPIW, IGEMM_COL_GROUPS = EPIW / 4;
     constexpr bool PAIR = MODE != 0;
     constexpr bool TWOSM = MODE == 2;
     constexpr int STAGE_BYTES = TWOSM ? Cfg::A_BYTES + Cfg::B_BYTES / 2 : Cfg::STAGE_BYTES;
@@ -595,6 +593,7 @@ struct Plan {
     dim3 grid;
     int bn;
     int mode;   // 0 independent CTAs, 1 pair + weight multicast, 2 pair + cta_group::2 UMMA
+    int epiw;   // epilogue warps of the kernel variant: 8, or 16 for short-K / few-tile launches (mode 0 only)
     int ktot;
     int stats_tiles;    // per-image tile slots of the fused GroupNorm statistics (0 = not supported for this plan)
     int stats_C;
@@ -620,15 +619,15 @@ static void pick_tile(int W, int H, int B, int* tw, int* th, int* tn) {
     }
 }
 
-template <int BN, int MODE>
+template <int BN, int MODE, int EPIW = 8>
 static int launch_igemm(const Plan& pl, const IgemmParams& prm, cudaStream_t st) {
     using Cfg = IgemmCfg<BN>;
     static bool configured = false;
     if (!configured) {
-        MFB_CUDA_OK(cudaFuncSetAttribute(igemm_kernel<BN, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        MFB_CUDA_OK(cudaFuncSetAttribute(igemm_kernel<BN, MODE, EPIW>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
         configured = true;
     }
-    MFB_CUDA_OK(launch_k(igemm_kernel<BN, MODE>, pl.grid, dim3(IGEMM_THREADS), Cfg::SMEM_BYTES, st, MODE != 0 ? 2 : 1, prm));
+    MFB_CUDA_OK(launch_k(igemm_kernel<BN, MODE, EPIW>, pl.grid, dim3(64 + 32 * EPIW), Cfg::SMEM_BYTES, st, MODE != 0 ? 2 : 1, prm));
     return MFB_OK;
 }
 
@@ -754,6 +753,15 @@ static int build_params(const mfb_conv_desc* d, int up_py, int up_px, const void
         if (d->igemm_mode >= 1 && d->igemm_mode <= 3) pl->mode = tiles_m >= 2 ? d->igemm_mode - 1 : 0;
     }
     {
+        // MFB_IGEMM_EPIW = 16: all launches on the 16-epilogue-warp variant; = 1: only short K (<= 2560) and the few-tile 8x8
+        // level.  Default 8 everywhere: per shape the 16-warp variant wins 5-11 % on those launches, per STEP neither choice
+        // is measurable (24.04-24.21 vs 24.08-24.11 vs 24.21-24.29 ms, profiles/logs/ab_epiw_auto.log)
+        const char* ew = getenv("MFB_IGEMM_EPIW");
+        const int knob = ew ? atoi(ew) : 8;
+        pl->epiw = knob == 16 ? 16 : (knob == 1 && (ktot <= 2560 || tiles_m <= 8)) ? 16 : 8;
+        if (pl->mode != 0) pl->epiw = 8;
+    }
+    {
         const int boxc = (bn % 32 == 0) ? 32 : 16;
         const int out_ld = d->geglu ? d->Cout / 2 : d->Cout;
         const uint32_t obox[4] = {uint32_t(boxc), uint32_t(p.tw), uint32_t(p.th), uint32_t(p.tn)};
@@ -874,6 +882,16 @@ extern "C" int mfb_conv_plan_create(const mfb_conv_desc* d, mfb_plan** out) {
 
 template <int MODE>
 static int run_one(const Plan& pl, const IgemmParams& prm, cudaStream_t st) {
+    if constexpr (MODE == 0) {
+        if (pl.epiw == 16) {
+            switch (pl.bn) {
+                case 160: return launch_igemm<160, 0, 16>(pl, prm, st);
+                case 128: return launch_igemm<128, 0, 16>(pl, prm, st);
+                case 80: return launch_igemm<80, 0, 16>(pl, prm, st);
+                default: return launch_igemm<64, 0, 16>(pl, prm, st);
+            }
+        }
+    }
     switch (pl.bn) {
         case 160: return launch_igemm<160, MODE>(pl, prm, st);
         case 128: return launch_igemm<128, MODE>(pl, prm, st);
