@@ -15,7 +15,7 @@ KEEP = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "sm__ops_path_tensor_op_hmma_src_bf16_dst_fp32_sparsity_off.avg.pct_of_peak_sustained_elapsed"]
 
 
-OURS = ("igemm_kernel", "attention_kernel", "gn_", "layernorm_kernel", "conv_in_kernel", "conv_out_kernel", "cfg_sched_kernel",
+OURS = ("igemm_kernel", "attention_kernel", "gn_", "layernorm", "conv_in_kernel", "conv_out_kernel", "cfg_sched_kernel",
         "transpose_tokens_kernel", "linear_small", "timestep_sinusoid", "f32_to_bf16")
 
 
