@@ -21,6 +21,7 @@
 // transposed copy of V exists anywhere (the neighbouring head's columns [d, dpad) only feed accumulator columns that
 // are never stored).
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.h"
@@ -62,24 +63,27 @@ constexpr int BQ = 128;   // query rows per tile (= TMEM lanes)
 #define MFB_ATT_POLY_EVERY 0
 #endif
 
-template <int D>
+// SHORT = the whole key sequence fits ONE tile of 80 keys (the 77-token CLIP context of every cross attention): one query
+// tile per CTA, no K/V ring, no ping-pong, a single softmax pass — instead of two 64-key iterations of which the second is
+// 80 % padding.
+template <int D, bool SHORT = false>
 struct AttCfg {
     static constexpr bool SMALL = D <= 40;
     static constexpr int DPAD = (D + 15) / 16 * 16;       // MMA K extent of QK^T and N extent of PV
     static constexpr int NKB = (D + 63) / 64;             // 64-column boxes per Q / K tile
     static constexpr bool MID = D > 40 && D <= 80;
-    static constexpr int NQ = SMALL ? MFB_ATT_NQ_SMALL : MID ? MFB_ATT_NQ_MID : 1;
-    static constexpr int BKV = SMALL ? MFB_ATT_KV_SMALL : MID ? MFB_ATT_KV_MID : 128;
+    static constexpr int NQ = SHORT ? 1 : SMALL ? MFB_ATT_NQ_SMALL : MID ? MFB_ATT_NQ_MID : 1;
+    static constexpr int BKV = SHORT ? 80 : SMALL ? MFB_ATT_KV_SMALL : MID ? MFB_ATT_KV_MID : 128;
     static constexpr bool PINGPONG = NQ == 2 && (SMALL ? MFB_ATT_PINGPONG : MFB_ATT_PINGPONG_MID);
-    static constexpr int CTAS_PER_SM = SMALL ? MFB_ATT_CTAS_SMALL : 1;
+    static constexpr int CTAS_PER_SM = SHORT ? (D <= 80 ? 2 : 1) : SMALL ? MFB_ATT_CTAS_SMALL : 1;
     static constexpr int THREADS = (4 * NQ + 2) * 32;     // NQ softmax warpgroups + TMA warp + MMA warp
-    static constexpr int STAGES = D > 80 ? 1 : 2;         // K/V ring depth (smem-limited for d = 160)
+    static constexpr int STAGES = (SHORT || D > 80) ? 1 : 2;   // K/V ring depth (smem-limited for d = 160; one tile in all if SHORT)
     static constexpr int QT_BYTES = NKB * BQ * 128;       // one query tile
     static constexpr int Q_BYTES = NQ * QT_BYTES;
     static constexpr int K_BYTES = NKB * BKV * 128;
     static constexpr int V_BYTES = K_BYTES;                   // same box shape: BKV key rows x 64-column blocks
     static constexpr int KV_BYTES = K_BYTES + V_BYTES;
-    static constexpr int P_BYTES = (BKV / 64) * BQ * 128;     // 128 x BKV bf16 as 64-key blocks, per query tile
+    static constexpr int P_BYTES = ((BKV + 63) / 64) * BQ * 128;     // 128 x BKV bf16 as 64-key blocks, per query tile
     static constexpr int TMEM_USED = NQ * (BKV + DPAD);       // S_0..S_{NQ-1} | O_0..O_{NQ-1}
     static constexpr int TMEM_COLS = TMEM_USED <= 128 ? 128 : TMEM_USED <= 256 ? 256 : 512;
     static constexpr int SMEM_BYTES = Q_BYTES + STAGES * KV_BYTES + NQ * P_BYTES + 1024 + 256;
@@ -106,9 +110,9 @@ __device__ __forceinline__ float ex2f_ordered(float x) {
     return y;
 }
 
-template <int D>
-__global__ void __launch_bounds__(AttCfg<D>::THREADS, AttCfg<D>::CTAS_PER_SM) attention_kernel(const __grid_constant__ AttParams p) {
-    using Cfg = AttCfg<D>;
+template <int D, bool SHORT>
+__global__ void __launch_bounds__(AttCfg<D, SHORT>::THREADS, AttCfg<D, SHORT>::CTAS_PER_SM) attention_kernel(const __grid_constant__ AttParams p) {
+    using Cfg = AttCfg<D, SHORT>;
     constexpr int BKV = Cfg::BKV, NQ = Cfg::NQ;
     constexpr int DPAD = Cfg::DPAD, NKB = Cfg::NKB, STAGES = Cfg::STAGES;
     constexpr int TMA_WARP = 4 * NQ, MMA_WARP = 4 * NQ + 1;
@@ -273,10 +277,14 @@ __global__ void __launch_bounds__(AttCfg<D>::THREADS, AttCfg<D>::CTAS_PER_SM) at
         for (int j = 0; j < ntiles; ++j) {
             mbar_wait_relaxed(s_full(t), j & 1);
             tc_fence_after();
-            constexpr int NC = BKV / 32;               // 32-column chunks of the score tile
-            uint32_t sv[NC][32];
+            constexpr int CW = (BKV % 32 == 0) ? 32 : 16;      // TMEM load width: 32-column chunks (16 for the 80-key tile)
+            constexpr int NC = BKV / CW;
+            uint32_t sv[NC][CW];
 #pragma unroll
-            for (int c = 0; c < NC; ++c) tmem_ld32(tS + c * 32, sv[c]);
+            for (int c = 0; c < NC; ++c) {
+                if constexpr (CW == 32) tmem_ld32(tS + c * 32, sv[c]);
+                else tmem_ld16(tS + c * 16, sv[c]);
+            }
             tmem_wait_ld();
             const int kbase = j * BKV;
             const bool tail = kbase + BKV > p.Tk;
@@ -290,15 +298,15 @@ __global__ void __launch_bounds__(AttCfg<D>::THREADS, AttCfg<D>::CTAS_PER_SM) at
 #pragma unroll
                 for (int c = 0; c < NC; ++c)
 #pragma unroll
-                    for (int i = 0; i < 32; ++i)
-                        if (kbase + c * 32 + i >= p.Tk) sv[c][i] = 0xff800000u;     // -inf
+                    for (int i = 0; i < CW; ++i)
+                        if (kbase + c * CW + i >= p.Tk) sv[c][i] = 0xff800000u;     // -inf
             }
             // row max of the RAW scores (scale > 0 commutes with max), four independent chains
             float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
             for (int c = 0; c < NC; ++c)
 #pragma unroll
-                for (int i = 0; i < 32; ++i) m4[i & 3] = fmaxf(m4[i & 3], __uint_as_float(sv[c][i]));
+                for (int i = 0; i < CW; ++i) m4[i & 3] = fmaxf(m4[i & 3], __uint_as_float(sv[c][i]));
             const float mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])) * p.scale_log2;
             float alpha = 1.f;
             if (mx > m_used + 8.f) {  // lazy rescale: keep a stale max while the row max grew by < 2^8
@@ -326,7 +334,7 @@ __global__ void __launch_bounds__(AttCfg<D>::THREADS, AttCfg<D>::CTAS_PER_SM) at
 #pragma unroll
             for (int c = 0; c < NC; ++c) {
 #pragma unroll
-                for (int i8 = 0; i8 < 4; ++i8) {
+                for (int i8 = 0; i8 < CW / 8; ++i8) {
                     float e[8];
 #if MFB_ATT_PACKED_MATH
                     // pairwise: one FFMA2 (scale, subtract the max) and one FADD2 (row sums) per two scores
@@ -355,12 +363,12 @@ __global__ void __launch_bounds__(AttCfg<D>::THREADS, AttCfg<D>::CTAS_PER_SM) at
                     pk.y = pack_bf16x2(e[2], e[3]);
                     pk.z = pack_bf16x2(e[4], e[5]);
                     pk.w = pack_bf16x2(e[6], e[7]);
-                    const int col = c * 32 + i8 * 8;           // key column inside the tile
+                    const int col = c * CW + i8 * 8;           // key column inside the tile
                     const int blk = col >> 6, ch = (col & 63) >> 3;
                     *reinterpret_cast<uint4*>(prow + blk * BQ * 128 + ((ch ^ (r & 7)) << 4)) = pk;
                     // hand the turn over, optionally a few groups early so the other warpgroup's wake-up latency
                     // overlaps the tail of this one (the very last hand-over of warpgroup 1 would have no taker)
-                    if (kPingPong && c * 4 + i8 == NC * 4 - 1 - MFB_ATT_HANDOFF_EARLY && !(t == 1 && j == ntiles - 1))
+                    if (kPingPong && c * (CW / 8) + i8 == NC * (CW / 8) - 1 - MFB_ATT_HANDOFF_EARLY && !(t == 1 && j == ntiles - 1))
                         named_bar_arrive(TURN_BAR + (t ^ 1), 256);
                 }
             }
@@ -403,17 +411,21 @@ __global__ void __launch_bounds__(AttCfg<D>::THREADS, AttCfg<D>::CTAS_PER_SM) at
     }
 }
 
-template <int D>
-static int launch_attention(const AttParams& p, int B, cudaStream_t st) {
-    using Cfg = AttCfg<D>;
+template <int D, bool SHORT>
+static int launch_attention_v(const AttParams& p, int B, cudaStream_t st) {
+    using Cfg = AttCfg<D, SHORT>;
     static bool configured = false;
     if (!configured) {
-        MFB_CUDA_OK(cudaFuncSetAttribute(attention_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        MFB_CUDA_OK(cudaFuncSetAttribute(attention_kernel<D, SHORT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
         configured = true;
     }
     dim3 grid((p.Tq + Cfg::NQ * BQ - 1) / (Cfg::NQ * BQ), p.heads, B);
-    MFB_CUDA_OK(launch_k(attention_kernel<D>, grid, dim3(Cfg::THREADS), Cfg::SMEM_BYTES, st, 1, p));
+    MFB_CUDA_OK(launch_k(attention_kernel<D, SHORT>, grid, dim3(Cfg::THREADS), Cfg::SMEM_BYTES, st, 1, p));
     return MFB_OK;
+}
+template <int D>
+static int launch_attention(const AttParams& p, int B, bool short_kv, cudaStream_t st) {
+    return short_kv ? launch_attention_v<D, true>(p, B, st) : launch_attention_v<D, false>(p, B, st);
 }
 
 }  // namespace mfb
@@ -433,7 +445,13 @@ extern "C" int mfb_attention(const void* q, int ldq, const void* k, int ldk, con
     // heads reach past them, and those columns must come back as TMA zero fill, not as whatever follows in memory
     // (for a v view into a fused q|k|v buffer that would be the next row — and past the allocation on the last row)
     const uint64_t width = uint64_t(heads) * head_dim;
-    const uint32_t kv_box = uint32_t(head_dim <= 40 ? AttCfg<40>::BKV : head_dim <= 80 ? AttCfg<80>::BKV : 128);   // AttCfg<D>::BKV keys per tile
+    // the one-tile variant for short key sequences (cross attention to the 77-token context); MFB_ATT_SHORTKV=0 disables it
+    static const bool short_on = [] { const char* e = getenv("MFB_ATT_SHORTKV"); return !e || atoi(e) != 0; }();
+    // (measured, profiles/logs/ab_shortkv.log: d = 80 0.0264 -> 0.0212 ms, d = 160 0.0144 -> 0.0125 ms, d = 40 unchanged -> kept on the
+    // two-query-tile kernel there)
+    const bool short_kv = short_on && Tk <= AttCfg<40, true>::BKV && head_dim > 40;
+    const uint32_t kv_box = short_kv ? uint32_t(AttCfg<40, true>::BKV)
+                                     : uint32_t(head_dim <= 40 ? AttCfg<40>::BKV : head_dim <= 80 ? AttCfg<80>::BKV : 128);   // keys per tile
     {
         const uint64_t dims[3] = {width, uint64_t(Tq), uint64_t(B)};
         const uint64_t str[2] = {uint64_t(ldq) * 2, uint64_t(Tq) * ldq * 2};
@@ -463,11 +481,11 @@ extern "C" int mfb_attention(const void* q, int ldq, const void* k, int ldk, con
     p.scale_log2 = 1.4426950408889634f / sqrtf(static_cast<float>(head_dim));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     switch (head_dim) {
-        case 32: return launch_attention<32>(p, B, st);
-        case 40: return launch_attention<40>(p, B, st);
-        case 64: return launch_attention<64>(p, B, st);
-        case 80: return launch_attention<80>(p, B, st);
-        case 160: return launch_attention<160>(p, B, st);
+        case 32: return launch_attention<32>(p, B, short_kv, st);
+        case 40: return launch_attention<40>(p, B, short_kv, st);
+        case 64: return launch_attention<64>(p, B, short_kv, st);
+        case 80: return launch_attention<80>(p, B, short_kv, st);
+        case 160: return launch_attention<160>(p, B, short_kv, st);
         default:
             set_error("head_dim %d is not instantiated (supported: 32, 40, 64, 80, 160)", head_dim);
             return MFB_EINVAL;
