@@ -212,6 +212,45 @@ int mfb_conv_out_f32(const float* x, int Cin, int B, int H, int W, const float* 
 int mfb_linear_small_f32(const float* x, int M, int K, const float* w, const float* b, int N, int act_in, int act_out,
                          float* y, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * Training-step glue of the BrushNet fine-tune step (BASELINE config 4): the part of
+ * E/train_brushnet_mirror.py:1404-1466 around the two nets.  fp32 tensors; every reduction is fixed-order (deterministic).
+ */
+/* DDPMScheduler.add_noise / get_velocity (S/schedulers/scheduling_ddpm.py:501-546): per sample b with a = alphas_cumprod[t_b]
+ *   noisy = sqrt(a) x0 + sqrt(1-a) noise ;  velocity = sqrt(a) noise - sqrt(1-a) x0     (either output may be NULL)
+ * x0 / noise / outputs [B, n] fp32, timesteps [B] int64 (device), alphas_cumprod [num_train_timesteps] fp32 (device). */
+int mfb_add_noise(const float* x0, const float* noise, const long long* timesteps, const float* alphas_cumprod,
+                  int num_train_timesteps, int B, long long n, float* noisy, float* velocity, void* stream);
+/* F.mse_loss(pred.float(), target.float(), "mean") and the min-SNR weighted form (train_brushnet_mirror.py:1433-1450):
+ *   per_sample[b] = mean_n (pred - target)^2 ;  loss = mean_b( weights[b] * per_sample[b] )   (weights NULL = 1)
+ * and, in the same pass, grad = d loss / d pred = 2 (pred - target) weights[b] / (B n)  (grad / per_sample may be NULL).
+ * ws: MFB_MSE_WS_FLOATS(B) floats of scratch. */
+#define MFB_MSE_MAX_CHUNKS 64
+#define MFB_MSE_WS_FLOATS(B) ((B) * MFB_MSE_MAX_CHUNKS)
+int mfb_mse_loss(const float* pred, const float* target, const float* weights, int B, long long n, float* per_sample,
+                 float* loss, float* grad, float* ws, void* stream);
+/* Sum of squares of a flat fp32 gradient buffer -> *out_sq (device scalar; accumulate=1 adds to it): the total_norm^2 of
+ * torch.nn.utils.clip_grad_norm_ as accelerator.clip_grad_norm_ calls it (train_brushnet_mirror.py:1460-1463).
+ * ws: MFB_SQNORM_WS_FLOATS floats of scratch. */
+#define MFB_SQNORM_WS_FLOATS 1184
+int mfb_grad_sqnorm(const float* g, long long n, float* ws, float* out_sq, int accumulate, void* stream);
+/* Gradient clipping + torch.optim.AdamW (train_brushnet_mirror.py:1190-1200,1464) + re-quantisation of the working
+ * weights, one pass over flat fp32 buffers of n elements:
+ *   g' = grad * grad_scale * min(1, max_grad_norm / (sqrt(*grad_sqnorm) * |grad_scale| + 1e-6))   (no clipping if grad_sqnorm NULL or max <= 0)
+ *   p *= 1 - lr*wd ; m = lerp(m, g', 1-beta1) ; v = beta2 v + (1-beta2) g'^2 ; p -= lr/bc1 * m / (sqrt(v)/sqrt(bc2) + eps)
+ * hyper (device, 8 floats): lr, beta1, beta2, eps, weight_decay, bc1 = 1-beta1^step, sqrt(bc2) = sqrt(1-beta2^step), grad_scale.
+ * param_bf16 (optional) receives the bf16 rounding of the updated parameters (what the tcgen05 kernels read). */
+int mfb_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, void* param_bf16, long long n,
+                   const float* hyper, const float* grad_sqnorm, float max_grad_norm, void* stream);
+/* Weight (and bias) gradient of a stride-1 conv3x3 / conv1x1 / linear layer (autograd of F.conv2d / F.linear behind
+ * LoRACompatibleConv/Linear, S/models/lora.py:363-377,445-451):
+ *   dw[co][(kh, kw, ci)] (+)= sum_{b,h,w} dy[b,h,w,co] * x[b,h+kh-k/2,w+kw-k/2,ci] ;  dbias[co] (+)= sum dy[.,co]
+ * x [B,H,W,Cin], dy [B,H,W,Cout] NHWC, dtype 0 = bf16 / 1 = fp32; dw fp32 in the packed [Cout, k*k*Cin] K order of
+ * mfb_conv_desc.w.  CUDA-core kernel with fp32 accumulation, one CTA per output tile (deterministic).  The DATA gradient
+ * of the same layer is mfb_conv_plan_create on dy with the flipped / transposed weight (ops.pack_conv_dgrad_weight). */
+int mfb_conv_wgrad(const void* x, const void* dy, int dtype, int B, int H, int W, int Cin, int Cout, int ksize, float* dw,
+                   float* dbias, int accumulate, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

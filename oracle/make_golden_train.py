@@ -1,0 +1,58 @@
+"""Generate tests/golden/train_glue.npz from the REFERENCE ITSELF (run in the build container only; needs /root/reference).
+
+    python oracle/make_golden_train.py
+
+Calls the reference's own `DDPMScheduler.add_noise` / `get_velocity` (S/schedulers/scheduling_ddpm.py:501-546) with the
+SD1.5 training noise schedule and `diffusers.training_utils.compute_snr` (S/training_utils.py:50-73), then evaluates the
+loss block of E/train_brushnet_mirror.py:1433-1450 (plain and min-SNR weighted) on seeded tensors with torch autograd.
+TEST INFRASTRUCTURE ONLY."""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+from make_golden import GOLD, import_reference  # noqa: E402
+
+
+def main():
+    diffusers = import_reference()
+    from diffusers.training_utils import compute_snr
+    sched = diffusers.DDPMScheduler(num_train_timesteps=1000, beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear")
+    g = torch.Generator().manual_seed(4321)
+    B, shape = 6, (4, 16, 16)
+    x0 = torch.randn(B, *shape, generator=g)
+    noise = torch.randn(B, *shape, generator=g)
+    t = torch.tensor([0, 1, 17, 500, 998, 999], dtype=torch.long)
+    noisy = sched.add_noise(x0, noise, t)
+    vel = sched.get_velocity(x0, noise, t)
+    snr = compute_snr(sched, t)
+
+    pred = torch.randn(B, *shape, generator=g, requires_grad=True)
+    out = {}
+    for name, gamma in (("plain", None), ("snr5", 5.0)):
+        pred.grad = None
+        target = noise
+        if gamma is None:
+            loss = torch.nn.functional.mse_loss(pred.float(), target.float(), reduction="mean")
+            w = torch.ones(B)
+        else:   # train_brushnet_mirror.py:1439-1450, prediction_type == "epsilon"
+            w = torch.stack([snr, gamma * torch.ones_like(t)], dim=1).min(dim=1)[0] / snr
+            loss = torch.nn.functional.mse_loss(pred.float(), target.float(), reduction="none")
+            loss = loss.mean(dim=list(range(1, len(loss.shape)))) * w
+            loss = loss.mean()
+        loss.backward()
+        out[f"loss_{name}"] = loss.detach().numpy()
+        out[f"grad_{name}"] = pred.grad.detach().numpy().copy()
+        out[f"w_{name}"] = w.numpy()
+    np.savez_compressed(os.path.join(GOLD, "train_glue.npz"), alphas_cumprod=sched.alphas_cumprod.numpy(), x0=x0.numpy(),
+                        noise=noise.numpy(), t=t.numpy(), noisy=noisy.numpy(), velocity=vel.numpy(), snr=snr.numpy(),
+                        pred=pred.detach().numpy(), **out)
+    print("wrote train_glue.npz", {k: float(v) for k, v in out.items() if k.startswith("loss")})
+
+
+if __name__ == "__main__":
+    main()

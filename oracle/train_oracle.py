@@ -1,0 +1,95 @@
+"""CPU restatement (numpy, float64 where it matters) of the training-step glue of the BrushNet fine-tune step —
+TEST INFRASTRUCTURE ONLY (only tests/, smoke() and bench.py's cpu_baseline leg may import oracle/).
+
+Follows E/train_brushnet_mirror.py:1404-1466 (E/ = /root/reference/MirrorFusion/examples/brushnet/):
+  * DDPMScheduler.add_noise / get_velocity        S/schedulers/scheduling_ddpm.py:501-546
+  * compute_snr + min-SNR loss weights            S/training_utils.py:50-73, train_brushnet_mirror.py:1433-1450
+  * F.mse_loss(pred.float(), target.float())      train_brushnet_mirror.py:1433
+  * accelerator.clip_grad_norm_ -> torch.nn.utils.clip_grad_norm_   train_brushnet_mirror.py:1460-1463
+  * torch.optim.AdamW (single-tensor update)      train_brushnet_mirror.py:1190-1200,1464
+Parity PINNED: tests/test_oracle_train.py checks add_noise / get_velocity / compute_snr against vectors produced by the
+reference's own DDPMScheduler and compute_snr (tests/golden/train_glue.npz, written by oracle/make_golden_train.py),
+and the clip + AdamW restatement against torch.nn.utils.clip_grad_norm_ + torch.optim.AdamW themselves (the reference
+calls exactly those; torch is present wherever the tests run)."""
+from __future__ import annotations
+
+import numpy as np
+
+
+def alphas_cumprod(num_train_timesteps=1000, beta_start=0.00085, beta_end=0.012) -> np.ndarray:
+    """scaled_linear betas in float32 as the reference builds them (scheduling_ddpm.py:198-205)."""
+    import torch
+    betas = torch.linspace(beta_start ** 0.5, beta_end ** 0.5, num_train_timesteps, dtype=torch.float32) ** 2
+    return torch.cumprod(1.0 - betas, dim=0).numpy()
+
+
+def add_noise(x0: np.ndarray, noise: np.ndarray, t: np.ndarray, acp: np.ndarray) -> np.ndarray:
+    a = acp[t].astype(np.float32)
+    sa = (a ** 0.5).reshape(-1, *([1] * (x0.ndim - 1)))
+    so = ((1 - a) ** 0.5).reshape(-1, *([1] * (x0.ndim - 1)))
+    return (sa * x0 + so * noise).astype(np.float32)                       # scheduling_ddpm.py:524
+
+
+def get_velocity(x0: np.ndarray, noise: np.ndarray, t: np.ndarray, acp: np.ndarray) -> np.ndarray:
+    a = acp[t].astype(np.float32)
+    sa = (a ** 0.5).reshape(-1, *([1] * (x0.ndim - 1)))
+    so = ((1 - a) ** 0.5).reshape(-1, *([1] * (x0.ndim - 1)))
+    return (sa * noise - so * x0).astype(np.float32)                       # scheduling_ddpm.py:545
+
+
+def compute_snr(t: np.ndarray, acp: np.ndarray) -> np.ndarray:
+    alpha = acp.astype(np.float32) ** 0.5
+    sigma = (1.0 - acp.astype(np.float32)) ** 0.5
+    return ((alpha[t] / sigma[t]) ** 2).astype(np.float32)                 # training_utils.py:72
+
+
+def snr_weights(t: np.ndarray, acp: np.ndarray, snr_gamma: float, prediction_type: str = "epsilon") -> np.ndarray:
+    snr = compute_snr(t, acp)
+    w = np.minimum(snr, np.float32(snr_gamma))                             # train_brushnet_mirror.py:1440-1442
+    if prediction_type == "epsilon":
+        return (w / snr).astype(np.float32)
+    if prediction_type == "v_prediction":
+        return (w / (snr + 1)).astype(np.float32)
+    raise ValueError(prediction_type)
+
+
+def mse_loss(pred: np.ndarray, target: np.ndarray, weights: np.ndarray | None = None):
+    """-> (loss, per_sample [B], d loss / d pred).  weights=None is F.mse_loss(reduction="mean")."""
+    B = pred.shape[0]
+    d = pred.astype(np.float64) - target.astype(np.float64)
+    n = d[0].size
+    per = (d.reshape(B, -1) ** 2).mean(1)
+    w = np.ones(B) if weights is None else weights.astype(np.float64)
+    loss = float((per * w).mean())
+    grad = 2.0 * d * w.reshape(-1, *([1] * (pred.ndim - 1))) / (B * n)
+    return loss, per, grad
+
+
+def clip_coef(grads: list[np.ndarray], max_norm: float):
+    """torch.nn.utils.clip_grad_norm_: total = || (||g_i||) ||_2 ; coef = min(1, max_norm / (total + 1e-6))."""
+    total = float(np.sqrt(sum(float((g.astype(np.float64) ** 2).sum()) for g in grads)))
+    return min(1.0, max_norm / (total + 1e-6)), total
+
+
+def adamw_step(p, g, m, v, *, step: int, lr=5e-6, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=1e-2):
+    """torch/optim/adamw.py `_single_tensor_adamw` (no amsgrad, not maximize), float64.  Returns new (p, m, v)."""
+    p, g, m, v = (a.astype(np.float64) for a in (p, g, m, v))
+    p = p * (1 - lr * weight_decay)
+    m = m + (1 - beta1) * (g - m)
+    v = v * beta2 + (1 - beta2) * g * g
+    bc1 = 1 - beta1 ** step
+    bc2 = 1 - beta2 ** step
+    denom = np.sqrt(v) / np.sqrt(bc2) + eps
+    p = p - (lr / bc1) * (m / denom)
+    return p, m, v
+
+
+def conv_grads(x_nchw, w_oihw, dy_nchw):
+    """Autograd of F.conv2d(x, w, padding=k//2) — what the reference's backward runs.  -> (dx, dw, dbias), float64."""
+    import torch
+    x = torch.tensor(x_nchw, dtype=torch.float64, requires_grad=True)
+    w = torch.tensor(w_oihw, dtype=torch.float64, requires_grad=True)
+    b = torch.zeros(w.shape[0], dtype=torch.float64, requires_grad=True)
+    y = torch.nn.functional.conv2d(x, w, b, padding=w.shape[-1] // 2)
+    y.backward(torch.tensor(dy_nchw, dtype=torch.float64))
+    return x.grad.numpy(), w.grad.numpy(), b.grad.numpy()

@@ -66,6 +66,12 @@ _SIGS = {
     "mfb_conv_in_f32": (i32, [vp, i32, vp, i32, i32, i32, i32, vp, vp, i32, vp, vp, vp, vp]),
     "mfb_conv_out_f32": (i32, [vp, i32, i32, i32, i32, vp, vp, i32, vp, vp]),
     "mfb_linear_small_f32": (i32, [vp, i32, i32, vp, vp, i32, i32, i32, vp, vp]),
+    # training-step glue (config 4)
+    "mfb_add_noise": (i32, [vp, vp, vp, vp, i32, i32, i64, vp, vp, vp]),
+    "mfb_mse_loss": (i32, [vp, vp, vp, i32, i64, vp, vp, vp, vp, vp]),
+    "mfb_grad_sqnorm": (i32, [vp, i64, vp, vp, i32, vp]),
+    "mfb_adamw_step": (i32, [vp, vp, vp, vp, vp, i64, vp, vp, f32, vp]),
+    "mfb_conv_wgrad": (i32, [vp, vp, i32, i32, i32, i32, i32, i32, i32, vp, vp, i32, vp]),
 }
 EXPORTS = tuple(_SIGS)
 

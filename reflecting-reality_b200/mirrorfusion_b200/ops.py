@@ -323,3 +323,59 @@ def cfg_sched_step(eps_u, eps_c, x, last, m0, m1, coef):
     n = x.numel() // Bimg
     check(lib().mfb_cfg_sched_step(_ptr(eps_u), _ptr(eps_c), _ptr(x), _ptr(last), _ptr(m0), _ptr(m1), _ptr(coef), Bimg, n,
                                    _stream()))
+
+
+# --------------------------------------------------------------------------------------------- training-step glue (config 4)
+MSE_MAX_CHUNKS = 64          # MFB_MSE_MAX_CHUNKS
+SQNORM_WS_FLOATS = 1184      # MFB_SQNORM_WS_FLOATS
+
+
+def pack_conv_dgrad_weight(w: torch.Tensor) -> torch.Tensor:
+    """Packed weight of the DATA gradient of a stride-1 conv / linear layer.  d x = conv(d y, W') with
+    W'[ci, co, kh, kw] = W[co, ci, k-1-kh, k-1-kw] (a linear layer: W' = W^T), so the backward-data pass of every
+    stride-1 conv3x3 / conv1x1 / linear is the SAME tcgen05 implicit GEMM run on d y: ConvPlan(dy, packed, dx,
+    Cin=Cout_fwd, Cout=Cin_fwd).  OIHW or [out, in] in, [Cin_fwd, k*k*Cout_fwd] out."""
+    if w.dim() == 2:
+        w = w[:, :, None, None]
+    return pack_conv_weight(w.flip(2, 3).transpose(0, 1))
+
+
+def add_noise(x0, noise, timesteps, alphas_cumprod, noisy=None, velocity=None):
+    """DDPMScheduler.add_noise / get_velocity; x0 / noise [B, ...] fp32, timesteps [B] int64, all on the device."""
+    _req(x0, f32, "x0"); _req(noise, f32, "noise"); _req(timesteps, torch.int64, "timesteps"); _req(alphas_cumprod, f32, "alphas_cumprod")
+    B = x0.shape[0]
+    check(lib().mfb_add_noise(_ptr(x0), _ptr(noise), _ptr(timesteps), _ptr(alphas_cumprod), alphas_cumprod.numel(), B,
+                              x0.numel() // B, _ptr(noisy), _ptr(velocity), _stream()))
+
+
+def mse_loss(pred, target, loss, ws, weights=None, per_sample=None, grad=None):
+    """loss = mean_b(w_b mean_n (pred - target)^2) and (optionally) its gradient w.r.t. pred, one deterministic pass."""
+    _req(pred, f32, "pred"); _req(target, f32, "target"); _req(loss, f32, "loss")
+    B = pred.shape[0]
+    if ws.numel() < B * MSE_MAX_CHUNKS:
+        raise ValueError("mse_loss: workspace smaller than MFB_MSE_WS_FLOATS(B)")
+    check(lib().mfb_mse_loss(_ptr(pred), _ptr(target), _ptr(weights), B, pred.numel() // B, _ptr(per_sample), _ptr(loss),
+                             _ptr(grad), _ptr(ws), _stream()))
+
+
+def grad_sqnorm(g, ws, out_sq, accumulate=False):
+    _req(g, f32, "g")
+    check(lib().mfb_grad_sqnorm(_ptr(g), g.numel(), _ptr(ws), _ptr(out_sq), int(accumulate), _stream()))
+
+
+def adamw_step(param, grad, exp_avg, exp_avg_sq, hyper, param_bf16=None, grad_sqnorm=None, max_grad_norm=0.0):
+    for name, t in (("param", param), ("grad", grad), ("exp_avg", exp_avg), ("exp_avg_sq", exp_avg_sq), ("hyper", hyper)):
+        _req(t, f32, name)
+    check(lib().mfb_adamw_step(_ptr(param), _ptr(grad), _ptr(exp_avg), _ptr(exp_avg_sq), _ptr(param_bf16), param.numel(),
+                               _ptr(hyper), _ptr(grad_sqnorm), float(max_grad_norm), _stream()))
+
+
+def conv_wgrad(x, dy, dw, dbias=None, *, B, H, W, ksize, accumulate=False):
+    """dw [Cout, k*k*Cin] fp32 (packed K order) and dbias [Cout] of a stride-1 conv / linear; x, dy NHWC bf16 or fp32."""
+    is32 = _is32(x)
+    _req(dy, x.dtype, "dy"); _req(dw, f32, "dw")
+    Cin, Cout = x.shape[-1], dy.shape[-1]
+    if tuple(dw.shape) != (Cout, ksize * ksize * Cin):
+        raise ValueError(f"dw shape {tuple(dw.shape)} != {(Cout, ksize * ksize * Cin)}")
+    check(lib().mfb_conv_wgrad(_ptr(x), _ptr(dy), int(is32), B, H, W, Cin, Cout, ksize, _ptr(dw), _ptr(dbias), int(accumulate),
+                               _stream()))

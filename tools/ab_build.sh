@@ -8,7 +8,7 @@ mkdir -p $ROOT/build/ab
 while [ $# -ge 2 ]; do
   name=$1; flags=$2; shift 2
   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -shared $flags \
-       -o $ROOT/build/ab/$name.so $CSRC/api.cu $CSRC/igemm.cu $CSRC/norm.cu $CSRC/misc.cu $CSRC/attn.cu $CSRC/fp32mode.cu &
+       -o $ROOT/build/ab/$name.so $CSRC/api.cu $CSRC/igemm.cu $CSRC/norm.cu $CSRC/misc.cu $CSRC/attn.cu $CSRC/fp32mode.cu $CSRC/train.cu &
 done
 wait
 ls -la $ROOT/build/ab
