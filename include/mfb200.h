@@ -238,8 +238,10 @@ int mfb_grad_sqnorm(const float* g, long long n, float* ws, float* out_sq, int a
  * weights, one pass over flat fp32 buffers of n elements:
  *   g' = grad * grad_scale * min(1, max_grad_norm / (sqrt(*grad_sqnorm) * |grad_scale| + 1e-6))   (no clipping if grad_sqnorm NULL or max <= 0)
  *   p *= 1 - lr*wd ; m = lerp(m, g', 1-beta1) ; v = beta2 v + (1-beta2) g'^2 ; p -= lr/bc1 * m / (sqrt(v)/sqrt(bc2) + eps)
- * hyper (device, 8 floats): lr, beta1, beta2, eps, weight_decay, bc1 = 1-beta1^step, sqrt(bc2) = sqrt(1-beta2^step), grad_scale.
+ * hyper (device, MFB_ADAMW_HYPER_FLOATS = 12): lr, beta1, beta2, eps, weight_decay, bc1 = 1-beta1^step, sqrt(bc2) = sqrt(1-beta2^step),
+ * grad_scale, 1-beta1, 1-beta2, 1-lr*wd, lr/bc1 — the last four evaluated by the caller in float64 like torch does (1 - 0.999f in fp32 is off by 1.3e-5).
  * param_bf16 (optional) receives the bf16 rounding of the updated parameters (what the tcgen05 kernels read). */
+#define MFB_ADAMW_HYPER_FLOATS 12
 int mfb_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, void* param_bf16, long long n,
                    const float* hyper, const float* grad_sqnorm, float max_grad_norm, void* stream);
 /* Weight (and bias) gradient of a stride-1 conv3x3 / conv1x1 / linear layer (autograd of F.conv2d / F.linear behind

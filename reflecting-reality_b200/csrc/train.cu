@@ -127,21 +127,23 @@ __global__ void sqnorm_final_kernel(const float* __restrict__ partial, int m, fl
 }
 
 // ---------------------------------------------------------------------------------------------- clip + AdamW + bf16 working copy
-// hyper (device, 8 floats): lr, beta1, beta2, eps, weight_decay, bias_correction1 = 1 - beta1^step,
-// sqrt(bias_correction2) = sqrt(1 - beta2^step), grad_scale (1 / world size after a SUM all-reduce, 1 / accumulation ...).
+// hyper (device, 12 floats): lr, beta1, beta2, eps, weight_decay, bias_correction1 = 1 - beta1^step,
+// sqrt(bias_correction2) = sqrt(1 - beta2^step), grad_scale (1 / world size after a SUM all-reduce, 1 / accumulation ...),
+// then the derived scalars torch evaluates in Python float64 before they reach a kernel: 1 - beta1, 1 - beta2,
+// 1 - lr*weight_decay, lr / bias_correction1  (1 - 0.999f evaluated in fp32 is off by 1.3e-5: it has to come from the host).
 // torch.optim.AdamW single-tensor update order (torch/optim/adamw.py _single_tensor_adamw):
 //   p *= 1 - lr*wd ; m = lerp(m, g, 1-b1) ; v = b2*v + (1-b2) g^2 ; p -= (lr/bc1) * m / (sqrt(v)/sqrt(bc2) + eps)
 // clip_grad_norm_ (torch/nn/utils/clip_grad.py): g *= min(1, max_norm / (total_norm + 1e-6)).
 struct AdamScalars {
-    float lr, b1, b2, eps, wd, bc1, sbc2, gscale;
+    float lr, b1, b2, eps, wd, bc1, sbc2, gscale, omb1, omb2, decay, step_size;
 };
 
-__device__ __forceinline__ void adam_one(float& p, float g, float& m, float& v, const AdamScalars& h, float step_size) {
-    p *= 1.0f - h.lr * h.wd;
-    m += (1.0f - h.b1) * (g - m);
-    v = v * h.b2 + (1.0f - h.b2) * g * g;
+__device__ __forceinline__ void adam_one(float& p, float g, float& m, float& v, const AdamScalars& h) {
+    p *= h.decay;
+    m += h.omb1 * (g - m);
+    v = v * h.b2 + h.omb2 * (g * g);
     const float denom = sqrtf(v) / h.sbc2 + h.eps;
-    p -= step_size * (m / denom);
+    p -= h.step_size * (m / denom);
 }
 
 __global__ void adamw_kernel(float* __restrict__ param, const float* __restrict__ grad, float* __restrict__ m, float* __restrict__ v,
@@ -149,13 +151,12 @@ __global__ void adamw_kernel(float* __restrict__ param, const float* __restrict_
                              const float* __restrict__ sqnorm, float max_norm) {
     pdl_trigger();
     pdl_wait();
-    AdamScalars h{hyper[0], hyper[1], hyper[2], hyper[3], hyper[4], hyper[5], hyper[6], hyper[7]};
+    AdamScalars h{hyper[0], hyper[1], hyper[2], hyper[3], hyper[4], hyper[5], hyper[6], hyper[7], hyper[8], hyper[9], hyper[10], hyper[11]};
     float gmul = h.gscale;
     if (sqnorm && max_norm > 0.f) {
         const float total = sqrtf(*sqnorm) * fabsf(h.gscale);       // norm of the SCALED gradient
         gmul *= fminf(1.0f, max_norm / (total + 1e-6f));
     }
-    const float step_size = h.lr / h.bc1;
     const long long n4 = n >> 2;
     float4* p4 = reinterpret_cast<float4*>(param);
     const float4* g4 = reinterpret_cast<const float4*>(grad);
@@ -165,10 +166,10 @@ __global__ void adamw_kernel(float* __restrict__ param, const float* __restrict_
          i += static_cast<long long>(gridDim.x) * blockDim.x) {
         float4 p = p4[i], mm = m4[i], vv = v4[i];
         const float4 g = g4[i];
-        adam_one(p.x, g.x * gmul, mm.x, vv.x, h, step_size);
-        adam_one(p.y, g.y * gmul, mm.y, vv.y, h, step_size);
-        adam_one(p.z, g.z * gmul, mm.z, vv.z, h, step_size);
-        adam_one(p.w, g.w * gmul, mm.w, vv.w, h, step_size);
+        adam_one(p.x, g.x * gmul, mm.x, vv.x, h);
+        adam_one(p.y, g.y * gmul, mm.y, vv.y, h);
+        adam_one(p.z, g.z * gmul, mm.z, vv.z, h);
+        adam_one(p.w, g.w * gmul, mm.w, vv.w, h);
         p4[i] = p;
         m4[i] = mm;
         v4[i] = vv;
@@ -183,7 +184,7 @@ __global__ void adamw_kernel(float* __restrict__ param, const float* __restrict_
     if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
         const long long i = (n4 << 2) + threadIdx.x;
         float p = param[i], mm = m[i], vv = v[i];
-        adam_one(p, grad[i] * gmul, mm, vv, h, step_size);
+        adam_one(p, grad[i] * gmul, mm, vv, h);
         param[i] = p;
         m[i] = mm;
         v[i] = vv;

@@ -75,27 +75,43 @@ class B200AdamW:
     lr scheduler can drive it), fused with clip_grad_norm_ and the bf16 re-quantisation.  `grad_scale` multiplies the
     gradient first (1 / world size after a SUM all-reduce, 1 / gradient_accumulation_steps)."""
 
+    _RING = 8
+    _NH = 12     # MFB_ADAMW_HYPER_FLOATS
+
     def __init__(self, flat: FlatParams, lr=5e-6, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2):
         self.flat = flat
         self.param_groups = [dict(lr=lr, betas=tuple(betas), eps=eps, weight_decay=weight_decay)]
         self.step_count = 0
         dev = flat.param.device
-        self._hyper = torch.zeros(8, device=dev, dtype=torch.float32)
-        self._hyper_host = torch.zeros(8, dtype=torch.float32).pin_memory() if dev.type == "cuda" else torch.zeros(8)
+        self._hyper = torch.zeros(self._NH, device=dev, dtype=torch.float32)
+        # pinned staging ring for the per-step scalars: a slot is rewritten only after the async copy that read it has
+        # finished (the host never waits on the GPU unless it runs more than _RING optimizer steps ahead)
+        self._ring = torch.zeros(self._RING, self._NH, dtype=torch.float32)
+        self._ring_ev = [None] * self._RING
+        if dev.type == "cuda":
+            self._ring = self._ring.pin_memory()
         self._sq = torch.zeros(1, device=dev, dtype=torch.float32)
         self._ws = torch.zeros(ops.SQNORM_WS_FLOATS, device=dev, dtype=torch.float32)
 
     def hyper(self, step: int, grad_scale: float = 1.0) -> np.ndarray:
-        """The 8 scalars of mfb_adamw_step for optimizer step `step` (1-based), float64 on the host."""
+        """The 12 scalars of mfb_adamw_step for optimizer step `step` (1-based), evaluated in float64 on the host (the
+        derived ones — 1-beta1, 1-beta2, 1-lr*wd, lr/bc1 — exactly as torch/optim/adamw.py evaluates them in Python)."""
         g = self.param_groups[0]
         b1, b2 = g["betas"]
-        return np.array([g["lr"], b1, b2, g["eps"], g["weight_decay"], 1.0 - b1 ** step, math.sqrt(1.0 - b2 ** step), grad_scale],
-                        dtype=np.float64)
+        bc1 = 1.0 - b1 ** step
+        return np.array([g["lr"], b1, b2, g["eps"], g["weight_decay"], bc1, math.sqrt(1.0 - b2 ** step), grad_scale,
+                         1.0 - b1, 1.0 - b2, 1.0 - g["lr"] * g["weight_decay"], g["lr"] / bc1], dtype=np.float64)
 
     def step(self, max_grad_norm: Optional[float] = None, grad_scale: float = 1.0):
         self.step_count += 1
-        self._hyper_host.copy_(torch.from_numpy(self.hyper(self.step_count, grad_scale).astype(np.float32)))
-        self._hyper.copy_(self._hyper_host, non_blocking=True)
+        slot = self.step_count % self._RING
+        if self._ring_ev[slot] is not None:
+            self._ring_ev[slot].synchronize()
+        self._ring[slot].copy_(torch.from_numpy(self.hyper(self.step_count, grad_scale).astype(np.float32)))
+        self._hyper.copy_(self._ring[slot], non_blocking=True)
+        if self._hyper.is_cuda:
+            self._ring_ev[slot] = torch.cuda.Event()
+            self._ring_ev[slot].record()
         f = self.flat
         sq = None
         if max_grad_norm is not None and max_grad_norm > 0:

@@ -29,7 +29,9 @@ def test_adamw_scalars():
     fp = FlatParams({"w": (4,)}, "cpu", with_bf16=False)
     opt = B200AdamW(fp, lr=5e-6, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2)
     h = opt.hyper(3, grad_scale=0.125)
-    assert np.allclose(h, [5e-6, 0.9, 0.999, 1e-8, 1e-2, 1 - 0.9 ** 3, math.sqrt(1 - 0.999 ** 3), 0.125])
+    assert np.allclose(h, [5e-6, 0.9, 0.999, 1e-8, 1e-2, 1 - 0.9 ** 3, math.sqrt(1 - 0.999 ** 3), 0.125, 0.1, 0.001, 1 - 5e-8,
+                           5e-6 / (1 - 0.9 ** 3)], rtol=1e-12)
+    assert abs(h[9] - 0.001) < 1e-15      # NOT 1 - float32(0.999)
     opt.param_groups[0]["lr"] = 1e-4       # what an lr scheduler does
     assert opt.hyper(1)[0] == 1e-4
 
