@@ -252,6 +252,14 @@ int mfb_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_a
  * of the same layer is mfb_conv_plan_create on dy with the flipped / transposed weight (ops.pack_conv_dgrad_weight). */
 int mfb_conv_wgrad(const void* x, const void* dy, int dtype, int B, int H, int W, int Cin, int Cout, int ksize, float* dw,
                    float* dbias, int accumulate, void* stream);
+/* Backward of GroupNorm (+SiLU) (autograd of F.group_norm + F.silu, S/models/resnet.py:337-338,381,393), NHWC, dtype 0 = bf16 /
+ * 1 = fp32 tensors, fp32 / fp64 math, statistics recomputed from x.  x2 / dx2: the second tensor of a channel concat (or NULL, C2 = 0)
+ * exactly as in mfb_groupnorm; dy is [B, HW, C1+C2].  dgamma / dbeta [C1+C2] fp32 ((+)= with accumulate; either may be NULL).
+ * ws: MFB_GN_BWD_WS_FLOATS(B, C) floats of scratch.  Deterministic (fixed-order reductions). */
+#define MFB_GN_BWD_WS_FLOATS(B, C) (2 * (B) * (C))
+int mfb_groupnorm_bwd(const void* x1, int C1, const void* x2, int C2, const void* dy, int dtype, int B, int HW, int groups, float eps,
+                      const float* gamma, const float* beta, int silu, void* dx1, void* dx2, float* dgamma, float* dbeta, float* ws,
+                      int accumulate, void* stream);
 
 #ifdef __cplusplus
 }

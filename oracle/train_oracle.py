@@ -93,3 +93,17 @@ def conv_grads(x_nchw, w_oihw, dy_nchw):
     y = torch.nn.functional.conv2d(x, w, b, padding=w.shape[-1] // 2)
     y.backward(torch.tensor(dy_nchw, dtype=torch.float64))
     return x.grad.numpy(), w.grad.numpy(), b.grad.numpy()
+
+
+def groupnorm_silu_grads(x_nchw, gamma, beta, dy_nchw, groups, eps, silu=True):
+    """Autograd of F.silu(F.group_norm(x, groups, gamma, beta, eps)) (S/models/resnet.py:337-338,381,393), float64.
+    -> (dx, dgamma, dbeta)."""
+    import torch
+    x = torch.tensor(x_nchw, dtype=torch.float64, requires_grad=True)
+    g = torch.tensor(gamma, dtype=torch.float64, requires_grad=True)
+    b = torch.tensor(beta, dtype=torch.float64, requires_grad=True)
+    y = torch.nn.functional.group_norm(x, groups, g, b, eps)
+    if silu:
+        y = torch.nn.functional.silu(y)
+    y.backward(torch.tensor(dy_nchw, dtype=torch.float64))
+    return x.grad.numpy(), g.grad.numpy(), b.grad.numpy()

@@ -271,6 +271,124 @@ __global__ void __launch_bounds__(256) wgrad_kernel(const T* __restrict__ x, con
     }
 }
 
+// ---------------------------------------------------------------------------------------------- GroupNorm (+SiLU) backward
+// y = silu(gamma * xhat + beta), xhat = (x - mean) * rstd over the (HW x C/groups) slab of (image, group); NHWC, x optionally the
+// channel concat of two tensors (the up blocks' skip concat, as in the forward kernel).  With dz = dy * silu'(z):
+//   dgamma[c] = sum dz * xhat ; dbeta[c] = sum dz ; dx = rstd * (dz*gamma - mean_slab(dz*gamma) - xhat * mean_slab(dz*gamma*xhat))
+// One CTA per (group, image).  Thread t owns channel t % cpg and every (blockDim / cpg)-th pixel, so the per-channel sums
+// are private until a fixed-order smem reduction; slab sums in fp64; statistics are recomputed from x (nothing is saved by the
+// forward pass).  Three reads of x, two of dy, one write: a first CUDA-core version (correct and deterministic, not yet tuned).
+template <typename T>
+__device__ __forceinline__ void st_from_float(T* p, float v);
+template <>
+__device__ __forceinline__ void st_from_float<float>(float* p, float v) { *p = v; }
+template <>
+__device__ __forceinline__ void st_from_float<__nv_bfloat16>(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+
+__device__ __forceinline__ double block_sum_all(double v, double* sm /* >= 33 */) {
+    const double r = block_sum(v, sm);
+    if (threadIdx.x == 0) sm[32] = r;
+    __syncthreads();
+    return sm[32];
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) gn_bwd_kernel(const T* __restrict__ x1, int C1, const T* __restrict__ x2, int C2,
+                                                     const T* __restrict__ dy, int HW, int groups, float eps,
+                                                     const float* __restrict__ gamma, const float* __restrict__ beta, int silu,
+                                                     T* __restrict__ dx1, T* __restrict__ dx2, float* __restrict__ ws_dgamma,
+                                                     float* __restrict__ ws_dbeta) {
+    pdl_trigger();
+    pdl_wait();
+    __shared__ double smd[33];
+    __shared__ float red[2][256];
+    const int C = C1 + C2, cpg = C / groups;
+    const int b = blockIdx.y, c0 = blockIdx.x * cpg;
+    const int rows = blockDim.x / cpg;
+    const bool active = static_cast<int>(threadIdx.x) < rows * cpg;
+    const int cl = threadIdx.x % cpg, r = threadIdx.x / cpg, c = c0 + cl;
+    const bool in1 = c < C1;
+    const T* xs = in1 ? x1 + static_cast<size_t>(b) * HW * C1 + c : x2 + static_cast<size_t>(b) * HW * C2 + (c - C1);
+    T* dxs = in1 ? dx1 + static_cast<size_t>(b) * HW * C1 + c : dx2 + static_cast<size_t>(b) * HW * C2 + (c - C1);
+    const int ldx = in1 ? C1 : C2;
+    const T* dys = dy + static_cast<size_t>(b) * HW * C + c;
+    const double m = static_cast<double>(HW) * cpg;
+
+    double s = 0.0, ss = 0.0;
+    if (active)
+        for (int p = r; p < HW; p += rows) {
+            const double v = ld_as_float(xs + static_cast<size_t>(p) * ldx);
+            s += v;
+            ss += v * v;
+        }
+    const double mean_d = block_sum_all(s, smd) / m;
+    __syncthreads();
+    const double var_d = fmax(block_sum_all(ss, smd) / m - mean_d * mean_d, 0.0);
+    __syncthreads();
+    const float mean = static_cast<float>(mean_d);
+    const float rstd = static_cast<float>(1.0 / sqrt(var_d + static_cast<double>(eps)));
+    const float gm = active ? gamma[c] : 0.f, bt = active ? beta[c] : 0.f;
+
+    float dg = 0.f, db = 0.f;
+    double s1 = 0.0, s2 = 0.0;
+    if (active)
+        for (int p = r; p < HW; p += rows) {
+            const float xh = (ld_as_float(xs + static_cast<size_t>(p) * ldx) - mean) * rstd;
+            float dz = ld_as_float(dys + static_cast<size_t>(p) * C);
+            if (silu) {
+                const float z = gm * xh + bt;
+                const float sg = 1.0f / (1.0f + expf(-z));
+                dz *= sg * (1.0f + z * (1.0f - sg));
+            }
+            dg += dz * xh;
+            db += dz;
+            s1 += static_cast<double>(dz * gm);
+            s2 += static_cast<double>(dz * gm * xh);
+        }
+    const float S1 = static_cast<float>(block_sum_all(s1, smd) / m);
+    __syncthreads();
+    const float S2 = static_cast<float>(block_sum_all(s2, smd) / m);
+    red[0][threadIdx.x] = dg;
+    red[1][threadIdx.x] = db;
+    __syncthreads();
+    if (static_cast<int>(threadIdx.x) < cpg) {
+        float a = 0.f, bsum = 0.f;
+        for (int q = 0; q < rows; ++q) {
+            a += red[0][q * cpg + threadIdx.x];
+            bsum += red[1][q * cpg + threadIdx.x];
+        }
+        ws_dgamma[static_cast<size_t>(b) * C + c0 + threadIdx.x] = a;
+        ws_dbeta[static_cast<size_t>(b) * C + c0 + threadIdx.x] = bsum;
+    }
+    if (active)
+        for (int p = r; p < HW; p += rows) {
+            const float xh = (ld_as_float(xs + static_cast<size_t>(p) * ldx) - mean) * rstd;
+            float dz = ld_as_float(dys + static_cast<size_t>(p) * C);
+            if (silu) {
+                const float z = gm * xh + bt;
+                const float sg = 1.0f / (1.0f + expf(-z));
+                dz *= sg * (1.0f + z * (1.0f - sg));
+            }
+            st_from_float(dxs + static_cast<size_t>(p) * ldx, rstd * (dz * gm - S1 - xh * S2));
+        }
+}
+
+// dgamma[c] (+)= sum_b ws[b][c] in image order (same for dbeta): thread per channel
+__global__ void gn_bwd_final_kernel(const float* __restrict__ ws_dgamma, const float* __restrict__ ws_dbeta, int B, int C,
+                                    float* __restrict__ dgamma, float* __restrict__ dbeta, int accumulate) {
+    pdl_trigger();
+    pdl_wait();
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    float a = 0.f, bsum = 0.f;
+    for (int b = 0; b < B; ++b) {
+        a += ws_dgamma[static_cast<size_t>(b) * C + c];
+        bsum += ws_dbeta[static_cast<size_t>(b) * C + c];
+    }
+    if (dgamma) dgamma[c] = a + (accumulate ? dgamma[c] : 0.f);
+    if (dbeta) dbeta[c] = bsum + (accumulate ? dbeta[c] : 0.f);
+}
+
 }  // namespace mfb
 
 using namespace mfb;
@@ -340,6 +458,35 @@ extern "C" int mfb_conv_wgrad(const void* x, const void* dy, int dtype, int B, i
     } else {
         MFB_CUDA_OK(launch_k(wgrad_kernel<__nv_bfloat16>, grid, dim3(256), 0, st, 1, static_cast<const __nv_bfloat16*>(x),
                              static_cast<const __nv_bfloat16*>(dy), B, H, W, Cin, Cout, ksize, dw, dbias, accumulate));
+    }
+    return MFB_OK;
+}
+
+extern "C" int mfb_groupnorm_bwd(const void* x1, int C1, const void* x2, int C2, const void* dy, int dtype, int B, int HW, int groups,
+                                 float eps, const float* gamma, const float* beta, int silu, void* dx1, void* dx2, float* dgamma,
+                                 float* dbeta, float* ws, int accumulate, void* stream) {
+    MFB_REQUIRE(x1 && dy && gamma && beta && dx1 && ws, "null pointer");
+    MFB_REQUIRE(dtype == 0 || dtype == 1, "dtype must be 0 (bf16) or 1 (fp32)");
+    MFB_REQUIRE((C2 == 0) == (x2 == nullptr) && (C2 == 0 || dx2 != nullptr), "x2 / dx2 / C2 disagree");
+    const int C = C1 + C2;
+    MFB_REQUIRE(B > 0 && B <= 65535 && HW > 0 && groups > 0 && C % groups == 0 && C / groups <= 256, "bad geometry B=%d HW=%d C=%d groups=%d",
+                B, HW, C, groups);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    float* wg = ws;
+    float* wb = ws + static_cast<size_t>(B) * C;
+    if (dtype == 1) {
+        MFB_CUDA_OK(launch_k(gn_bwd_kernel<float>, dim3(groups, B), dim3(256), 0, st, 1, static_cast<const float*>(x1), C1,
+                             static_cast<const float*>(x2), C2, static_cast<const float*>(dy), HW, groups, eps, gamma, beta, silu,
+                             static_cast<float*>(dx1), static_cast<float*>(dx2), wg, wb));
+    } else {
+        MFB_CUDA_OK(launch_k(gn_bwd_kernel<__nv_bfloat16>, dim3(groups, B), dim3(256), 0, st, 1,
+                             static_cast<const __nv_bfloat16*>(x1), C1, static_cast<const __nv_bfloat16*>(x2), C2,
+                             static_cast<const __nv_bfloat16*>(dy), HW, groups, eps, gamma, beta, silu,
+                             static_cast<__nv_bfloat16*>(dx1), static_cast<__nv_bfloat16*>(dx2), wg, wb));
+    }
+    if (dgamma || dbeta) {
+        MFB_CUDA_OK(launch_k(gn_bwd_final_kernel, dim3((C + 127) / 128), dim3(128), 0, st, 1, static_cast<const float*>(wg),
+                             static_cast<const float*>(wb), B, C, dgamma, dbeta, accumulate));
     }
     return MFB_OK;
 }

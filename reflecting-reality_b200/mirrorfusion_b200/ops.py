@@ -379,3 +379,15 @@ def conv_wgrad(x, dy, dw, dbias=None, *, B, H, W, ksize, accumulate=False):
         raise ValueError(f"dw shape {tuple(dw.shape)} != {(Cout, ksize * ksize * Cin)}")
     check(lib().mfb_conv_wgrad(_ptr(x), _ptr(dy), int(is32), B, H, W, Cin, Cout, ksize, _ptr(dw), _ptr(dbias), int(accumulate),
                                _stream()))
+
+
+def groupnorm_bwd(x1, x2, dy, gamma, beta, dx1, dx2, ws, *, B, HW, groups, eps, silu, dgamma=None, dbeta=None, accumulate=False):
+    """Backward of groupnorm(): dx (per source tensor of the concat), dgamma, dbeta.  ws: 2*B*C floats."""
+    is32 = _is32(x1)
+    C1 = x1.shape[-1]
+    C2 = 0 if x2 is None else x2.shape[-1]
+    _req(dy, x1.dtype, "dy"); _req(dx1, x1.dtype, "dx1")
+    if ws.numel() < 2 * B * (C1 + C2):
+        raise ValueError("groupnorm_bwd: workspace smaller than MFB_GN_BWD_WS_FLOATS(B, C)")
+    check(lib().mfb_groupnorm_bwd(_ptr(x1), C1, _ptr(x2), C2, _ptr(dy), int(is32), B, HW, groups, eps, _ptr(gamma), _ptr(beta),
+                                  int(silu), _ptr(dx1), _ptr(dx2), _ptr(dgamma), _ptr(dbeta), _ptr(ws), int(accumulate), _stream()))

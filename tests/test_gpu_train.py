@@ -233,3 +233,34 @@ def test_one_layer_training_loop_end_to_end(ops):
         # by up to lr * 1e-2 (measured: 1.6e-5 rel-L2 after the first step, from less than one such element of 36 864)
         assert rel(flat.p("weight"), tw.detach().permute(0, 2, 3, 1).reshape(Cout, -1)) < 1e-4, step
         assert rel(flat.p("bias"), tb.detach()) < 1e-4, step
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, bf16])
+@pytest.mark.parametrize("B,HW,C1,C2,groups,silu,eps", [(2, 64, 320, 0, 32, True, 1e-5), (3, 100, 64, 0, 32, False, 1e-6),
+                                                       (2, 256, 640, 320, 32, True, 1e-5), (1, 64, 1280, 1280, 32, True, 1e-5),
+                                                       (2, 36, 128, 0, 32, True, 1e-5)])
+def test_groupnorm_silu_backward_vs_autograd(ops, dtype, B, HW, C1, C2, groups, silu, eps):
+    """(2, 256, 640, 320): the 960-channel skip concat, group 21 straddles the two source tensors."""
+    C = C1 + C2
+    x1 = _randn(B, HW, C1, seed=1, dtype=dtype) * 1.5 + 0.3
+    x2 = (_randn(B, HW, C2, seed=2, dtype=dtype) * 0.7 - 0.2) if C2 else None
+    dy = _randn(B, HW, C, seed=3, dtype=dtype)
+    gamma, beta = 1.0 + 0.2 * _randn(C, seed=4), 0.1 * _randn(C, seed=5)
+    xcat = x1 if x2 is None else torch.cat([x1, x2], -1)
+    to_nchw = lambda t: t.float().permute(0, 2, 1).reshape(B, -1, HW, 1).cpu().numpy()
+    dx_ref, dg_ref, db_ref = T.groupnorm_silu_grads(to_nchw(xcat), gamma.cpu().numpy(), beta.cpu().numpy(), to_nchw(dy), groups, eps, silu)
+    dx_ref = torch.from_numpy(dx_ref).reshape(B, C, HW).permute(0, 2, 1)
+    dx1 = torch.full_like(x1, float("nan"))
+    dx2 = torch.full_like(x2, float("nan")) if C2 else None
+    dg, db = torch.full((C,), float("nan"), device="cuda"), torch.full((C,), float("nan"), device="cuda")
+    ws = torch.zeros(2 * B * C, device="cuda")
+    ops.groupnorm_bwd(x1, x2, dy, gamma, beta, dx1, dx2, ws, B=B, HW=HW, groups=groups, eps=eps, silu=silu, dgamma=dg, dbeta=db)
+    dx = dx1 if dx2 is None else torch.cat([dx1, dx2], -1)
+    tol = 2e-5 if dtype == torch.float32 else 4e-3       # bf16: rounding of the stored dx alone is ~1.5e-3
+    assert rel(dx.float().cpu(), dx_ref) < tol
+    assert rel(dg.cpu(), torch.from_numpy(dg_ref)) < 2e-5 and rel(db.cpu(), torch.from_numpy(db_ref)) < 2e-5
+    again = torch.full_like(x1, float("nan"))
+    ops.groupnorm_bwd(x1, x2, dy, gamma, beta, again, dx2, ws, B=B, HW=HW, groups=groups, eps=eps, silu=silu, dgamma=dg, dbeta=db,
+                      accumulate=True)
+    assert torch.equal(again, dx1)                         # deterministic
+    assert rel(dg.cpu(), 2 * torch.from_numpy(dg_ref)) < 2e-5
