@@ -252,6 +252,13 @@ int mfb_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_a
  * of the same layer is mfb_conv_plan_create on dy with the flipped / transposed weight (ops.pack_conv_dgrad_weight). */
 int mfb_conv_wgrad(const void* x, const void* dy, int dtype, int B, int H, int W, int Cin, int Cout, int ksize, float* dw,
                    float* dbias, int accumulate, void* stream);
+/* The same weight gradient for bf16 operands on the tensor cores: split-K warp-MMA GEMM (mma.sync.m16n8k16, fp32 accumulate) that
+ * consumes x and dy as stored (the pixel index is the reduction dimension: ldmatrix.trans, no transposed copies), fp32 partial
+ * tiles per K slice in ws, summed in slice order (deterministic).  Needs Cin % 8 == 0 and Cout % 8 == 0 (every layer of the two
+ * nets except conv_in / conv_in_condition, which take the CUDA-core mfb_conv_wgrad).  ws: mfb_conv_wgrad_tc_ws_floats(...) floats. */
+long long mfb_conv_wgrad_tc_ws_floats(int B, int H, int W, int Cin, int Cout, int ksize);
+int mfb_conv_wgrad_tc(const void* x, const void* dy, int B, int H, int W, int Cin, int Cout, int ksize, float* dw, float* dbias,
+                      int accumulate, float* ws, long long ws_floats, void* stream);
 /* Backward of GroupNorm (+SiLU) (autograd of F.group_norm + F.silu, S/models/resnet.py:337-338,381,393), NHWC, dtype 0 = bf16 /
  * 1 = fp32 tensors, fp32 / fp64 math, statistics recomputed from x.  x2 / dx2: the second tensor of a channel concat (or NULL, C2 = 0)
  * exactly as in mfb_groupnorm; dy is [B, HW, C1+C2].  dgamma / dbeta [C1+C2] fp32 ((+)= with accumulate; either may be NULL).

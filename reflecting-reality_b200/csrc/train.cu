@@ -389,6 +389,186 @@ __global__ void gn_bwd_final_kernel(const float* __restrict__ ws_dgamma, const f
     if (dbeta) dbeta[c] = bsum + (accumulate ? dbeta[c] : 0.f);
 }
 
+// ---------------------------------------------------------------------------------------------- weight gradient on tensor cores
+// Same contraction as wgrad_kernel for bf16 operands, as a split-K warp-MMA GEMM: CTA = 128 co x 128 ci of ONE filter tap over a
+// contiguous range of 64-pixel slabs.  Both operands arrive "transposed" (the reduction index, the pixel, is the slow dimension
+// of dy [P, Cout] and x [P, Cin]), which is exactly what ldmatrix.trans feeds to mma.sync.m16n8k16: the smem tiles are
+// [pixel][channel] as stored in HBM, no transposed copy is ever made.  cp.async (16 B, zero-fill for padding / tails / shifted
+// pixels outside the image) into a 3-stage ring, rows padded to 136 elements (ldmatrix bank-conflict free).  Each slice writes
+// its fp32 partial tile; wgrad_reduce_kernel sums the slices in order (deterministic) into dw.  8 warps = 2 (co) x 4 (ci),
+// warp tile 64 x 32.  ncu (profiles/r01t_wgrad_tc.md): the legacy HMMA path peaks at 2048 op/clk/SM on B200 (a quarter of tcgen05).  (A tcgen05 version needs both operands as MN-major UMMA descriptors — next step)
+constexpr int TC_BM = 128, TC_BN = 128, TC_BK = 64, TC_LD = 136, TC_STAGES = 3;
+constexpr int TC_SMEM = TC_STAGES * 2 * TC_BK * TC_LD * 2;
+
+__device__ __forceinline__ void cp_async16_zfill(uint32_t dst, const void* src, bool valid) {
+    const int sz = valid ? 16 : 0;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void mma_bf16_16816(float* c, const uint32_t* a, uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+__global__ void __launch_bounds__(256, 2) wgrad_tc_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy, int B,
+                                                       int H, int W, int Cin, int Cout, int ksize, int slabs_per_slice,
+                                                       float* __restrict__ part) {
+    pdl_trigger();
+    pdl_wait();
+    extern __shared__ __align__(16) unsigned char tc_smem[];
+    __nv_bfloat16* sA = reinterpret_cast<__nv_bfloat16*>(tc_smem);        // [stage][pixel][co]
+    __nv_bfloat16* sB = sA + TC_STAGES * TC_BK * TC_LD;                   // [stage][pixel][ci]
+    const int mtiles = (Cout + TC_BM - 1) / TC_BM;
+    const int tap = blockIdx.y / mtiles, mt = blockIdx.y % mtiles;
+    const int co0 = mt * TC_BM, ci0 = blockIdx.x * TC_BN;
+    const int pad = ksize / 2;
+    const int dh = tap / ksize - pad, dwo = tap % ksize - pad;
+    const long long P = static_cast<long long>(B) * H * W;
+    const int nslab_all = static_cast<int>((P + TC_BK - 1) / TC_BK);
+    const int s_lo = blockIdx.z * slabs_per_slice;
+    const int s_hi = min(s_lo + slabs_per_slice, nslab_all);
+    const int nslab = max(s_hi - s_lo, 0);
+    const int ktot = ksize * ksize * Cin;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wm = warp >> 2, wn = warp & 3;
+
+    // loader role: column chunk ch (8 channels) of rows tid/16 + 16 i
+    const int ch = tid & 15, row0 = tid >> 4;
+    const bool a_col_ok = co0 + ch * 8 < Cout, b_col_ok = ci0 + ch * 8 < Cin;
+    // (h, w) of this thread's four rows, packed h << 16 | w and advanced by 64 pixels per slab (slabs are loaded in order): the
+    // per-row 64-bit divisions of the first version cost more issue slots than the MMAs
+    uint32_t hw[TC_BK / 16];
+    const int adv_w = TC_BK % W, adv_h = TC_BK / W;
+#pragma unroll
+    for (int i = 0; i < TC_BK / 16; ++i) {
+        const long long p = static_cast<long long>(s_lo) * TC_BK + row0 + 16 * i;
+        hw[i] = (static_cast<uint32_t>((p / W) % H) << 16) | static_cast<uint32_t>(p % W);
+    }
+    auto load_slab = [&](int stage, int slab) {
+        const long long p0 = static_cast<long long>(slab) * TC_BK;
+#pragma unroll
+        for (int i = 0; i < TC_BK / 16; ++i) {
+            const int row = row0 + 16 * i;
+            const long long p = p0 + row;
+            const bool pv = p < P;
+            const bool av = pv && a_col_ok;
+            const __nv_bfloat16* asrc = av ? dy + p * Cout + co0 + ch * 8 : dy;
+            cp_async16_zfill(smem_u32(sA + (stage * TC_BK + row) * TC_LD + ch * 8), asrc, av);
+            int h_ = static_cast<int>(hw[i] >> 16), w_ = static_cast<int>(hw[i] & 0xffffu);
+            const int hs = h_ + dh, ws = w_ + dwo;
+            const bool bv = pv && b_col_ok && hs >= 0 && hs < H && ws >= 0 && ws < W;
+            const __nv_bfloat16* bsrc = bv ? x + (p + static_cast<long long>(dh) * W + dwo) * Cin + ci0 + ch * 8 : x;
+            cp_async16_zfill(smem_u32(sB + (stage * TC_BK + row) * TC_LD + ch * 8), bsrc, bv);
+            w_ += adv_w;
+            h_ += adv_h;
+            if (w_ >= W) {
+                w_ -= W;
+                ++h_;
+            }
+            while (h_ >= H) h_ -= H;
+            hw[i] = (static_cast<uint32_t>(h_) << 16) | static_cast<uint32_t>(w_);
+        }
+    };
+
+    float acc[4][4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) acc[i][j][k] = 0.f;
+
+#pragma unroll
+    for (int s = 0; s < TC_STAGES - 1; ++s) {
+        if (s < nslab) load_slab(s, s_lo + s);
+        cp_async_commit();
+    }
+    const int lj = lane >> 3, lr = lane & 7;
+    const bool warp_active = co0 + wm * 64 < Cout && ci0 + wn * 32 < Cin;
+    for (int it = 0; it < nslab; ++it) {
+        cp_async_wait<TC_STAGES - 2>();
+        __syncthreads();
+        {
+            const int nx = it + TC_STAGES - 1;
+            if (nx < nslab) load_slab(nx % TC_STAGES, s_lo + nx);
+            cp_async_commit();
+        }
+        const int st = it % TC_STAGES;
+        const __nv_bfloat16* tA = sA + st * TC_BK * TC_LD;
+        const __nv_bfloat16* tB = sB + st * TC_BK * TC_LD;
+        // a warp whose 64 x 32 sub-tile lies entirely in the channel tail (320 = 128 + 128 + 64) has nothing to multiply
+        if (!warp_active) continue;
+#pragma unroll
+        for (int kk = 0; kk < TC_BK / 16; ++kk) {
+            uint32_t a[4][4], b[2][4];
+#pragma unroll
+            for (int mi = 0; mi < 4; ++mi)   // matrices: (k lo, m lo), (k lo, m hi), (k hi, m lo), (k hi, m hi) = a0..a3
+                ldmatrix_x4_trans(smem_u32(tA + (kk * 16 + (lj >> 1) * 8 + lr) * TC_LD + wm * 64 + mi * 16 + (lj & 1) * 8), a[mi][0],
+                                  a[mi][1], a[mi][2], a[mi][3]);
+#pragma unroll
+            for (int n2 = 0; n2 < 2; ++n2)   // matrices: (k lo, n lo), (k hi, n lo), (k lo, n hi), (k hi, n hi) = b0, b1 of two n8 tiles
+                ldmatrix_x4_trans(smem_u32(tB + (kk * 16 + (lj & 1) * 8 + lr) * TC_LD + wn * 32 + n2 * 16 + (lj >> 1) * 8), b[n2][0],
+                                  b[n2][1], b[n2][2], b[n2][3]);
+#pragma unroll
+            for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+                for (int ni = 0; ni < 4; ++ni) mma_bf16_16816(acc[mi][ni], a[mi], b[ni >> 1][(ni & 1) * 2], b[ni >> 1][(ni & 1) * 2 + 1]);
+        }
+    }
+    cp_async_wait<0>();
+
+    float* outp = part + static_cast<size_t>(blockIdx.z) * Cout * ktot;
+    const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+    for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            const int co = co0 + wm * 64 + mi * 16 + g + half * 8;
+            if (co >= Cout) continue;
+#pragma unroll
+            for (int ni = 0; ni < 4; ++ni) {
+                const int ci = ci0 + wn * 32 + ni * 8 + 2 * t;
+                if (ci >= Cin) continue;   // Cin % 8 == 0: the pair (ci, ci + 1) is valid together
+                *reinterpret_cast<float2*>(outp + static_cast<size_t>(co) * ktot + static_cast<size_t>(tap) * Cin + ci) =
+                    make_float2(acc[mi][ni][half * 2], acc[mi][ni][half * 2 + 1]);
+            }
+        }
+}
+
+// dw[i] (+)= sum over slices (in order) of part[s][i]
+__global__ void wgrad_reduce_kernel(const float* __restrict__ part, int slices, long long n, float* __restrict__ dw, int accumulate) {
+    pdl_trigger();
+    pdl_wait();
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        float a = 0.f;
+        for (int s = 0; s < slices; ++s) a += part[static_cast<size_t>(s) * n + i];
+        dw[i] = a + (accumulate ? dw[i] : 0.f);
+    }
+}
+
+// bias gradient: column sums of dy.  grid (ceil(Cout/64), slices), 256 threads = 4 pixel phases x 64 channels
+__global__ void dbias_partial_kernel(const __nv_bfloat16* __restrict__ dy, long long P, int Cout, float* __restrict__ part) {
+    pdl_trigger();
+    pdl_wait();
+    __shared__ float sm[4][64];
+    const int c = blockIdx.x * 64 + (threadIdx.x & 63), rg = threadIdx.x >> 6;
+    const long long per = (P + gridDim.y - 1) / gridDim.y;
+    const long long lo = blockIdx.y * per, hi = (lo + per < P) ? lo + per : P;
+    float a = 0.f;
+    if (c < Cout)
+        for (long long p = lo + rg; p < hi; p += 4) a += __bfloat162float(dy[p * Cout + c]);
+    sm[rg][threadIdx.x & 63] = a;
+    __syncthreads();
+    if (threadIdx.x < 64 && c < Cout) part[static_cast<size_t>(blockIdx.y) * Cout + c] = (sm[0][threadIdx.x] + sm[1][threadIdx.x]) + (sm[2][threadIdx.x] + sm[3][threadIdx.x]);
+}
+
 }  // namespace mfb
 
 using namespace mfb;
@@ -487,6 +667,75 @@ extern "C" int mfb_groupnorm_bwd(const void* x1, int C1, const void* x2, int C2,
     if (dgamma || dbeta) {
         MFB_CUDA_OK(launch_k(gn_bwd_final_kernel, dim3((C + 127) / 128), dim3(128), 0, st, 1, static_cast<const float*>(wg),
                              static_cast<const float*>(wb), B, C, dgamma, dbeta, accumulate));
+    }
+    return MFB_OK;
+}
+
+// split-K plan of the tensor-core weight gradient.  Two CTAs fit an SM (104 KB smem, 126 registers), so one wave holds
+// 2 x 148 CTAs; the slice count minimises  waves(tiles * S) x slabs-per-slice  (wave quantisation cost the first version
+// almost 2x: 324 CTAs = 1.09 waves), at least 4 slabs per slice, at most 32 slices (the reduce pass reads S partial tiles).
+static void wgrad_tc_plan(int B, int H, int W, int Cin, int Cout, int ksize, int* slices, int* slabs_per_slice) {
+    const long long P = static_cast<long long>(B) * H * W;
+    const int nslab = static_cast<int>((P + TC_BK - 1) / TC_BK);
+    const int tiles = ((Cin + TC_BN - 1) / TC_BN) * ((Cout + TC_BM - 1) / TC_BM) * ksize * ksize;
+    const int wave = 2 * 148;
+    int smax = nslab / 4;
+    if (smax > 32) smax = 32;
+    if (smax < 1) smax = 1;
+    int best = 1;
+    long long best_cost = -1;
+    for (int s = 1; s <= smax; ++s) {
+        const long long waves = (static_cast<long long>(tiles) * s + wave - 1) / wave;
+        const long long cost = waves * ((nslab + s - 1) / s) + s;   // + s: one partial tile more to write and reduce
+        if (best_cost < 0 || cost < best_cost) {
+            best_cost = cost;
+            best = s;
+        }
+    }
+    const int per = (nslab + best - 1) / best;
+    *slabs_per_slice = per;
+    *slices = (nslab + per - 1) / per;
+}
+
+#define MFB_DBIAS_SLICES 32
+
+extern "C" long long mfb_conv_wgrad_tc_ws_floats(int B, int H, int W, int Cin, int Cout, int ksize) {
+    if (B <= 0 || H <= 0 || W <= 0 || Cin <= 0 || Cout <= 0 || (ksize != 1 && ksize != 3)) return 0;
+    int slices, per;
+    wgrad_tc_plan(B, H, W, Cin, Cout, ksize, &slices, &per);
+    return static_cast<long long>(slices) * Cout * ksize * ksize * Cin + static_cast<long long>(MFB_DBIAS_SLICES) * Cout;
+}
+
+extern "C" int mfb_conv_wgrad_tc(const void* x, const void* dy, int B, int H, int W, int Cin, int Cout, int ksize, float* dw,
+                                 float* dbias, int accumulate, float* ws, long long ws_floats, void* stream) {
+    MFB_REQUIRE(x && dy && dw && ws, "null pointer");
+    MFB_REQUIRE((ksize == 1 || ksize == 3) && B > 0 && H > 0 && W > 0 && H < 65536 && W < 65536, "bad geometry");
+    MFB_REQUIRE(Cin > 0 && Cout > 0 && Cin % 8 == 0 && Cout % 8 == 0, "tensor-core weight gradient needs Cin %% 8 == 0 and Cout %% 8 == 0 (got %d, %d)",
+                Cin, Cout);
+    MFB_REQUIRE(ws_floats >= mfb_conv_wgrad_tc_ws_floats(B, H, W, Cin, Cout, ksize), "workspace too small");
+    int slices, per;
+    wgrad_tc_plan(B, H, W, Cin, Cout, ksize, &slices, &per);
+    const int taps = ksize * ksize, ktot = taps * Cin;
+    const int mtiles = (Cout + TC_BM - 1) / TC_BM, ntiles = (Cin + TC_BN - 1) / TC_BN;
+    MFB_REQUIRE(mtiles * taps <= 65535, "Cout too large");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    static bool attr_set = false;
+    if (!attr_set) {
+        MFB_CUDA_OK(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
+        attr_set = true;
+    }
+    MFB_CUDA_OK(launch_k(wgrad_tc_kernel, dim3(ntiles, mtiles * taps, slices), dim3(256), TC_SMEM, st, 1,
+                         static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(dy), B, H, W, Cin, Cout, ksize, per, ws));
+    const long long n = static_cast<long long>(Cout) * ktot;
+    MFB_CUDA_OK(launch_k(wgrad_reduce_kernel, dim3(chunks_for(n, 256, 148 * 8)), dim3(256), 0, st, 1, static_cast<const float*>(ws), slices,
+                         n, dw, accumulate));
+    if (dbias) {
+        float* bpart = ws + static_cast<size_t>(slices) * n;
+        const long long P = static_cast<long long>(B) * H * W;
+        MFB_CUDA_OK(launch_k(dbias_partial_kernel, dim3((Cout + 63) / 64, MFB_DBIAS_SLICES), dim3(256), 0, st, 1,
+                             static_cast<const __nv_bfloat16*>(dy), P, Cout, bpart));
+        MFB_CUDA_OK(launch_k(wgrad_reduce_kernel, dim3(chunks_for(Cout, 256, 8)), dim3(256), 0, st, 1, static_cast<const float*>(bpart),
+                             MFB_DBIAS_SLICES, static_cast<long long>(Cout), dbias, accumulate));
     }
     return MFB_OK;
 }

@@ -36,6 +36,7 @@ def main():
     ap.add_argument("--batch", type=int, default=32)
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--skip-wgrad", action="store_true")
+    ap.add_argument("--only-conv", action="store_true", help="only the conv forward / dgrad / wgrad section (ncu captures)")
     args = ap.parse_args()
     ops.lib()
     peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -53,7 +54,7 @@ def main():
         res["kernels"][name] = r
         print(name, r, flush=True)
 
-    n = args.params
+    n = args.params if not args.only_conv else 1024
     flat = FlatParams({"all": (n,)}, "cuda")
     flat.param.normal_(0, 0.02)
     flat.grad.normal_(0, 1e-3)
@@ -87,10 +88,15 @@ def main():
     fl = 2.0 * B * H * W * Cout * 9 * Cin
     rec("conv3x3 320->320 @64x64 forward (tcgen05)", timed(fwd.run, 20), flops=fl)
     rec("conv3x3 320->320 @64x64 dgrad (tcgen05, same kernel)", timed(bwd.run, 20), flops=fl)
+    dw, db = torch.empty(Cout, 9 * Cin, device="cuda"), torch.empty(Cout, device="cuda")
+    wws = torch.empty(ops.conv_wgrad_ws_floats(B, H, W, Cin, Cout, 3), device="cuda")
+    rec("conv3x3 320->320 @64x64 wgrad + dbias (tensor cores, split-K mma.sync; 4 launches)",
+        timed(lambda: ops.conv_wgrad(x, dy, dw, db, B=B, H=H, W=W, ksize=3, ws=wws), 20), flops=fl)
+    rec("conv3x3 320->320 @64x64 wgrad only (tensor cores; 2 launches)",
+        timed(lambda: ops.conv_wgrad(x, dy, dw, None, B=B, H=H, W=W, ksize=3, ws=wws), 20), flops=fl)
     if not args.skip_wgrad:
-        dw, db = torch.empty(Cout, 9 * Cin, device="cuda"), torch.empty(Cout, device="cuda")
         rec("conv3x3 320->320 @64x64 wgrad (CUDA cores, first version)",
-            timed(lambda: ops.conv_wgrad(x, dy, dw, db, B=B, H=H, W=W, ksize=3), 3, warm=1), flops=fl)
+            timed(lambda: ops.conv_wgrad(x, dy, dw, db, B=B, H=H, W=W, ksize=3, cuda_cores=True), 3, warm=1), flops=fl)
     gamma, beta = torch.ones(Cin, device="cuda"), torch.zeros(Cin, device="cuda")
     gws = torch.zeros(2 * B * Cin, device="cuda")
     dg, dbt = torch.empty(Cin, device="cuda"), torch.empty(Cin, device="cuda")
