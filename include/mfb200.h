@@ -262,11 +262,16 @@ int mfb_conv_wgrad_tc(const void* x, const void* dy, int B, int H, int W, int Ci
 /* Backward of GroupNorm (+SiLU) (autograd of F.group_norm + F.silu, S/models/resnet.py:337-338,381,393), NHWC, dtype 0 = bf16 /
  * 1 = fp32 tensors, fp32 / fp64 math, statistics recomputed from x.  x2 / dx2: the second tensor of a channel concat (or NULL, C2 = 0)
  * exactly as in mfb_groupnorm; dy is [B, HW, C1+C2].  dgamma / dbeta [C1+C2] fp32 ((+)= with accumulate; either may be NULL).
+ * dres (optional, [B, HW, C1+C2], same dtype): a gradient arriving over the residual / shortcut path, added to dx in the same pass
+ * (ResnetBlock2D: d x = GroupNorm-backward(...) + d out, S/models/resnet.py:403).
  * ws: MFB_GN_BWD_WS_FLOATS(B, C) floats of scratch.  Deterministic (fixed-order reductions). */
 #define MFB_GN_BWD_WS_FLOATS(B, C) (2 * (B) * (C))
 int mfb_groupnorm_bwd(const void* x1, int C1, const void* x2, int C2, const void* dy, int dtype, int B, int HW, int groups, float eps,
-                      const float* gamma, const float* beta, int silu, void* dx1, void* dx2, float* dgamma, float* dbeta, float* ws,
-                      int accumulate, void* stream);
+                      const float* gamma, const float* beta, int silu, const void* dres, void* dx1, void* dx2, float* dgamma,
+                      float* dbeta, float* ws, int accumulate, void* stream);
+/* out[b][c] = sum over image b's HW pixels of dy[b][p][c] (fp32 [B, C]): the gradient of the per-image row bias
+ * time_emb_proj(silu(emb))[:, :, None, None] (S/models/resnet.py:369-379).  dtype 0 = bf16 / 1 = fp32 dy. */
+int mfb_rowsum_per_image(const void* dy, int dtype, int B, int HW, int C, float* out, void* stream);
 
 #ifdef __cplusplus
 }

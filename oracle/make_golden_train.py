@@ -16,6 +16,7 @@ import torch
 
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 from make_golden import GOLD, import_reference  # noqa: E402
+from train_oracle import resnet_block_case  # noqa: E402
 
 
 def main():
@@ -54,5 +55,38 @@ def main():
     print("wrote train_glue.npz", {k: float(v) for k, v in out.items() if k.startswith("loss")})
 
 
+def resnet_block_golden():
+    """The reference's OWN ResnetBlock2D (S/models/resnet.py:184-405), forward + autograd in fp32 on the seeded case: full out / dx /
+    d rowbias, and for every parameter gradient its L2 norm and 64 entries at seeded positions (keeps the fixture small)."""
+    diffusers = import_reference()
+    from diffusers.models.resnet import ResnetBlock2D
+    out = {}
+    for tag, cin, cout in (("id", 64, 64), ("sc", 64, 128)):
+        sd, x, emb, d_out = resnet_block_case(cin, cout, seed=77)
+        blk = ResnetBlock2D(in_channels=cin, out_channels=cout, temb_channels=emb.shape[1], groups=32, eps=1e-5)
+        blk.load_state_dict({k[2:]: v for k, v in sd.items()}, strict=True)
+        keep = {}
+
+        def hook(module, inputs, output):          # keep the projected row bias and its gradient (returns None: output unchanged)
+            output.retain_grad()
+            keep["rb"] = output
+
+        blk.time_emb_proj.register_forward_hook(hook)
+        x = x.clone().requires_grad_(True)
+        y = blk(x, emb)
+        y.backward(d_out)
+        out[f"{tag}_out"], out[f"{tag}_dx"], out[f"{tag}_d_rowbias"] = y.detach().numpy(), x.grad.numpy(), keep["rb"].grad.numpy()
+        gi = torch.Generator().manual_seed(5)
+        for name, prm in blk.named_parameters():
+            gflat = prm.grad.reshape(-1)
+            idx = torch.randint(0, gflat.numel(), (64,), generator=gi)
+            out[f"{tag}_g_{name}_norm"] = gflat.double().norm().numpy()
+            out[f"{tag}_g_{name}_idx"] = idx.numpy()
+            out[f"{tag}_g_{name}_val"] = gflat[idx].numpy()
+    np.savez_compressed(os.path.join(GOLD, "resnet_block_grad.npz"), **out)
+    print("wrote resnet_block_grad.npz", len(out), "arrays")
+
+
 if __name__ == "__main__":
     main()
+    resnet_block_golden()

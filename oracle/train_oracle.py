@@ -107,3 +107,50 @@ def groupnorm_silu_grads(x_nchw, gamma, beta, dy_nchw, groups, eps, silu=True):
         y = torch.nn.functional.silu(y)
     y.backward(torch.tensor(dy_nchw, dtype=torch.float64))
     return x.grad.numpy(), g.grad.numpy(), b.grad.numpy()
+
+
+def resnet_block_grads(sd, prefix, x_nchw, emb, d_out_nchw, groups=32, eps=1e-5):
+    """Autograd (float64) through the oracle's ResnetBlock2D restatement (oracle/mf_oracle.py `resnet`, pinned to the reference's
+    block by tests/golden/resnet_block_grad.npz).  -> dict: out, dx, d_rowbias (gradient at time_emb_proj's OUTPUT), and the
+    parameter gradients by state_dict name (OIHW)."""
+    import torch
+    from . import mf_oracle as O
+    p = {k: v.detach().double().clone().requires_grad_(True) for k, v in sd.items() if k.startswith(prefix + ".")}
+    x = torch.as_tensor(x_nchw).double().clone().requires_grad_(True)
+    e = torch.as_tensor(emb).double()
+    rb = torch.nn.functional.linear(torch.nn.functional.silu(e), p[f"{prefix}.time_emb_proj.weight"], p[f"{prefix}.time_emb_proj.bias"])
+    rb.retain_grad()
+    # same algebra as O.resnet with the row bias exposed (it is the block boundary of the kernel program)
+    F = torch.nn.functional
+    h = F.silu(F.group_norm(x, groups, p[f"{prefix}.norm1.weight"], p[f"{prefix}.norm1.bias"], eps))
+    h = F.conv2d(h, p[f"{prefix}.conv1.weight"], p[f"{prefix}.conv1.bias"], padding=1) + rb[:, :, None, None]
+    h = F.silu(F.group_norm(h, groups, p[f"{prefix}.norm2.weight"], p[f"{prefix}.norm2.bias"], eps))
+    h = F.conv2d(h, p[f"{prefix}.conv2.weight"], p[f"{prefix}.conv2.bias"], padding=1)
+    sc = x
+    if f"{prefix}.conv_shortcut.weight" in p:
+        sc = F.conv2d(x, p[f"{prefix}.conv_shortcut.weight"], p[f"{prefix}.conv_shortcut.bias"])
+    out = sc + h
+    with torch.no_grad():
+        ref = O.resnet({k: v.detach() for k, v in p.items()}, prefix, x.detach(), e, groups, eps)
+    assert torch.allclose(out.detach(), ref, rtol=1e-12, atol=1e-12)
+    out.backward(torch.as_tensor(d_out_nchw).double())
+    res = {"out": out.detach(), "dx": x.grad, "d_rowbias": rb.grad, "rowbias": rb.detach()}
+    res.update({k: v.grad for k, v in p.items()})
+    return res
+
+
+def resnet_block_case(cin, cout, seed=77):
+    """Seeded tensors of one ResnetBlock2D case (weights in state_dict naming under the prefix "r")."""
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    B, H, W, T = 2, 8, 8, 96
+    rn = lambda *s, scale=1.0: torch.randn(*s, generator=g) * scale
+    sd = {"r.norm1.weight": 1 + 0.2 * rn(cin), "r.norm1.bias": 0.1 * rn(cin),
+          "r.conv1.weight": rn(cout, cin, 3, 3, scale=(9 * cin) ** -0.5), "r.conv1.bias": 0.1 * rn(cout),
+          "r.time_emb_proj.weight": rn(cout, T, scale=T ** -0.5), "r.time_emb_proj.bias": 0.1 * rn(cout),
+          "r.norm2.weight": 1 + 0.2 * rn(cout), "r.norm2.bias": 0.1 * rn(cout),
+          "r.conv2.weight": rn(cout, cout, 3, 3, scale=(9 * cout) ** -0.5), "r.conv2.bias": 0.1 * rn(cout)}
+    if cin != cout:
+        sd["r.conv_shortcut.weight"] = rn(cout, cin, 1, 1, scale=cin ** -0.5)
+        sd["r.conv_shortcut.bias"] = 0.1 * rn(cout)
+    return sd, rn(B, cin, H, W), rn(B, T), rn(B, cout, H, W)

@@ -297,7 +297,7 @@ __global__ void __launch_bounds__(256) gn_bwd_kernel(const T* __restrict__ x1, i
                                                      const T* __restrict__ dy, int HW, int groups, float eps,
                                                      const float* __restrict__ gamma, const float* __restrict__ beta, int silu,
                                                      T* __restrict__ dx1, T* __restrict__ dx2, float* __restrict__ ws_dgamma,
-                                                     float* __restrict__ ws_dbeta) {
+                                                     float* __restrict__ ws_dbeta, const T* __restrict__ dres) {
     pdl_trigger();
     pdl_wait();
     __shared__ double smd[33];
@@ -312,6 +312,7 @@ __global__ void __launch_bounds__(256) gn_bwd_kernel(const T* __restrict__ x1, i
     T* dxs = in1 ? dx1 + static_cast<size_t>(b) * HW * C1 + c : dx2 + static_cast<size_t>(b) * HW * C2 + (c - C1);
     const int ldx = in1 ? C1 : C2;
     const T* dys = dy + static_cast<size_t>(b) * HW * C + c;
+    const T* drs = dres ? dres + static_cast<size_t>(b) * HW * C + c : nullptr;   // gradient arriving over the residual / shortcut path
     const double m = static_cast<double>(HW) * cpg;
 
     double s = 0.0, ss = 0.0;
@@ -369,7 +370,9 @@ __global__ void __launch_bounds__(256) gn_bwd_kernel(const T* __restrict__ x1, i
                 const float sg = 1.0f / (1.0f + expf(-z));
                 dz *= sg * (1.0f + z * (1.0f - sg));
             }
-            st_from_float(dxs + static_cast<size_t>(p) * ldx, rstd * (dz * gm - S1 - xh * S2));
+            float r = rstd * (dz * gm - S1 - xh * S2);
+            if (drs) r += ld_as_float(drs + static_cast<size_t>(p) * C);
+            st_from_float(dxs + static_cast<size_t>(p) * ldx, r);
         }
 }
 
@@ -569,6 +572,24 @@ __global__ void dbias_partial_kernel(const __nv_bfloat16* __restrict__ dy, long 
     if (threadIdx.x < 64 && c < Cout) part[static_cast<size_t>(blockIdx.y) * Cout + c] = (sm[0][threadIdx.x] + sm[1][threadIdx.x]) + (sm[2][threadIdx.x] + sm[3][threadIdx.x]);
 }
 
+// out[b][c] = sum over the HW pixels of image b of dy[b][p][c]: the gradient of the per-image row bias
+// (time_emb_proj(silu(emb))[:, :, None, None], S/models/resnet.py:369-379).  grid (ceil(C/64), B), 4 pixel phases x 64 channels.
+template <typename T>
+__global__ void rowsum_kernel(const T* __restrict__ dy, int HW, int C, float* __restrict__ out) {
+    pdl_trigger();
+    pdl_wait();
+    __shared__ float sm[4][64];
+    const int c = blockIdx.x * 64 + (threadIdx.x & 63), rg = threadIdx.x >> 6, b = blockIdx.y;
+    const T* src = dy + static_cast<size_t>(b) * HW * C;
+    float a = 0.f;
+    if (c < C)
+        for (int p = rg; p < HW; p += 4) a += ld_as_float(src + static_cast<size_t>(p) * C + c);
+    sm[rg][threadIdx.x & 63] = a;
+    __syncthreads();
+    if (threadIdx.x < 64 && c < C)
+        out[static_cast<size_t>(b) * C + c] = (sm[0][threadIdx.x] + sm[1][threadIdx.x]) + (sm[2][threadIdx.x] + sm[3][threadIdx.x]);
+}
+
 }  // namespace mfb
 
 using namespace mfb;
@@ -643,8 +664,8 @@ extern "C" int mfb_conv_wgrad(const void* x, const void* dy, int dtype, int B, i
 }
 
 extern "C" int mfb_groupnorm_bwd(const void* x1, int C1, const void* x2, int C2, const void* dy, int dtype, int B, int HW, int groups,
-                                 float eps, const float* gamma, const float* beta, int silu, void* dx1, void* dx2, float* dgamma,
-                                 float* dbeta, float* ws, int accumulate, void* stream) {
+                                 float eps, const float* gamma, const float* beta, int silu, const void* dres, void* dx1, void* dx2,
+                                 float* dgamma, float* dbeta, float* ws, int accumulate, void* stream) {
     MFB_REQUIRE(x1 && dy && gamma && beta && dx1 && ws, "null pointer");
     MFB_REQUIRE(dtype == 0 || dtype == 1, "dtype must be 0 (bf16) or 1 (fp32)");
     MFB_REQUIRE((C2 == 0) == (x2 == nullptr) && (C2 == 0 || dx2 != nullptr), "x2 / dx2 / C2 disagree");
@@ -657,12 +678,13 @@ extern "C" int mfb_groupnorm_bwd(const void* x1, int C1, const void* x2, int C2,
     if (dtype == 1) {
         MFB_CUDA_OK(launch_k(gn_bwd_kernel<float>, dim3(groups, B), dim3(256), 0, st, 1, static_cast<const float*>(x1), C1,
                              static_cast<const float*>(x2), C2, static_cast<const float*>(dy), HW, groups, eps, gamma, beta, silu,
-                             static_cast<float*>(dx1), static_cast<float*>(dx2), wg, wb));
+                             static_cast<float*>(dx1), static_cast<float*>(dx2), wg, wb, static_cast<const float*>(dres)));
     } else {
         MFB_CUDA_OK(launch_k(gn_bwd_kernel<__nv_bfloat16>, dim3(groups, B), dim3(256), 0, st, 1,
                              static_cast<const __nv_bfloat16*>(x1), C1, static_cast<const __nv_bfloat16*>(x2), C2,
                              static_cast<const __nv_bfloat16*>(dy), HW, groups, eps, gamma, beta, silu,
-                             static_cast<__nv_bfloat16*>(dx1), static_cast<__nv_bfloat16*>(dx2), wg, wb));
+                             static_cast<__nv_bfloat16*>(dx1), static_cast<__nv_bfloat16*>(dx2), wg, wb,
+                             static_cast<const __nv_bfloat16*>(dres)));
     }
     if (dgamma || dbeta) {
         MFB_CUDA_OK(launch_k(gn_bwd_final_kernel, dim3((C + 127) / 128), dim3(128), 0, st, 1, static_cast<const float*>(wg),
@@ -737,5 +759,18 @@ extern "C" int mfb_conv_wgrad_tc(const void* x, const void* dy, int B, int H, in
         MFB_CUDA_OK(launch_k(wgrad_reduce_kernel, dim3(chunks_for(Cout, 256, 8)), dim3(256), 0, st, 1, static_cast<const float*>(bpart),
                              MFB_DBIAS_SLICES, static_cast<long long>(Cout), dbias, accumulate));
     }
+    return MFB_OK;
+}
+
+extern "C" int mfb_rowsum_per_image(const void* dy, int dtype, int B, int HW, int C, float* out, void* stream) {
+    MFB_REQUIRE(dy && out, "null pointer");
+    MFB_REQUIRE(dtype == 0 || dtype == 1, "dtype must be 0 (bf16) or 1 (fp32)");
+    MFB_REQUIRE(B > 0 && B <= 65535 && HW > 0 && C > 0, "bad geometry");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const dim3 grid((C + 63) / 64, B);
+    if (dtype == 1)
+        MFB_CUDA_OK(launch_k(rowsum_kernel<float>, grid, dim3(256), 0, st, 1, static_cast<const float*>(dy), HW, C, out));
+    else
+        MFB_CUDA_OK(launch_k(rowsum_kernel<__nv_bfloat16>, grid, dim3(256), 0, st, 1, static_cast<const __nv_bfloat16*>(dy), HW, C, out));
     return MFB_OK;
 }

@@ -1,0 +1,160 @@
+"""Forward-for-training and backward of one ResnetBlock2D (S/models/resnet.py:329-405) as a launch program over the kernels —
+the unit the BrushNet branch is made of (22 per net; BASELINE config 4).  First piece of the
+backward PROGRAM of the nets; the net-level program (saved activations of all blocks, the samplers, the frozen UNet's
+dgrad-only chain) is not built yet.
+
+Block boundary: (x [B, HW, Cin], rowbias [B, Cout] = time_emb_proj(silu(emb))) -> out [B, HW, Cout]; backward takes d out and
+returns (d x, d rowbias) and ACCUMULATES the parameter gradients into the flat gradient buffer.  The timestep MLP and
+`time_emb_proj` themselves live in the hoisted timestep path (engine.build_time_path); their (GEMV-sized) backward consumes
+d rowbias and is part of the net-level program.
+
+Parameters live in a `train.FlatParams` in the layout the kernels consume — conv weights PACKED [Cout, kh*kw*Cin] — so that
+    forward        reads   flat.w(name) (bf16 working copy) / flat.p(name) (fp32 parity mode)
+    weight grad    writes  flat.g(name) in the same packed order (ops.conv_wgrad)
+    AdamW          updates master and working copy in one launch (train.B200AdamW)
+with no per-step repacking except the flipped / transposed copies the data-gradient plans read (`refresh_dgrad_weights`).
+
+`K` is the kernel namespace (default: `ops`, the C-ABI library).  tests/torch_kernels.py provides a CPU stand-in with the same
+call signatures so that the program's dataflow is checked against the reference's autograd without a GPU; the product path
+never uses it (ops raises without CUDA)."""
+from __future__ import annotations
+
+from typing import Dict, Optional, Tuple
+
+import torch
+
+from . import ops as _ops
+from .train import FlatParams
+
+
+def resnet_param_shapes(prefix: str, Cin: int, Cout: int) -> Dict[str, Tuple[int, ...]]:
+    """Flat-buffer entries of one block, conv weights in packed [Cout, k*k*Cin] layout."""
+    s = {f"{prefix}.norm1.weight": (Cin,), f"{prefix}.norm1.bias": (Cin,),
+         f"{prefix}.conv1.weight": (Cout, 9 * Cin), f"{prefix}.conv1.bias": (Cout,),
+         f"{prefix}.norm2.weight": (Cout,), f"{prefix}.norm2.bias": (Cout,),
+         f"{prefix}.conv2.weight": (Cout, 9 * Cout), f"{prefix}.conv2.bias": (Cout,)}
+    if Cin != Cout:
+        s[f"{prefix}.conv_shortcut.weight"] = (Cout, Cin)
+        s[f"{prefix}.conv_shortcut.bias"] = (Cout,)
+    return s
+
+
+def pack_resnet_state_dict(prefix: str, sd: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+    """Reference state_dict entries (OIHW) of the block -> fp32 tensors in the flat-buffer layout."""
+    out = {}
+    for k, v in sd.items():
+        if not k.startswith(prefix + ".") or ".time_emb_proj." in k:
+            continue
+        v = v.float()
+        out[k] = v.permute(0, 2, 3, 1).reshape(v.shape[0], -1).contiguous() if v.dim() == 4 else v.contiguous()
+    return out
+
+
+def unpack_conv_grad(g: torch.Tensor, ksize: int) -> torch.Tensor:
+    """Packed [Cout, k*k*Cin] gradient / weight -> OIHW (for comparison with the reference's .grad)."""
+    Cout = g.shape[0]
+    return g.view(Cout, ksize, ksize, -1).permute(0, 3, 1, 2).contiguous()
+
+
+def _dgrad_from_packed(wp: torch.Tensor, ksize: int, dtype) -> torch.Tensor:
+    """Packed forward weight [Cout, k*k*Cin] -> packed data-gradient weight [Cin, k*k*Cout] (flip taps, swap channels)."""
+    Cout = wp.shape[0]
+    w = wp.view(Cout, ksize, ksize, -1).flip(1, 2).permute(3, 1, 2, 0)
+    return w.reshape(w.shape[0], -1).to(dtype).contiguous()
+
+
+class ResnetBlockTrainer:
+    def __init__(self, flat: FlatParams, prefix: str, *, B: int, H: int, W: int, Cin: int, Cout: int, groups: int = 32,
+                 eps: float = 1e-5, precision: str = "bf16", K=None):
+        K = _ops if K is None else K
+        self.K, self.flat, self.p = K, flat, prefix
+        self.B, self.H, self.W, self.HW, self.Cin, self.Cout, self.groups, self.eps = B, H, W, H * W, Cin, Cout, groups, eps
+        self.dt = torch.float32 if precision == "fp32" else torch.bfloat16
+        self.shortcut = Cin != Cout
+        dev = flat.param.device
+        act = lambda c: torch.zeros(B, self.HW, c, device=dev, dtype=self.dt)
+        # forward buffers (kept for the backward pass) and gradient buffers, allocated once: fixed addresses
+        self.x, self.n1, self.c1, self.n2, self.out = act(Cin), act(Cin), act(Cout), act(Cout), act(Cout)
+        self.sc = act(Cout) if self.shortcut else None
+        self.rowbias = torch.zeros(B, Cout, device=dev, dtype=torch.float32)
+        self.d_out, self.dn2, self.dc1, self.dn1, self.dx = act(Cout), act(Cout), act(Cout), act(Cin), act(Cin)
+        self.dsc = act(Cin) if self.shortcut else None
+        self.d_rowbias = torch.zeros(B, Cout, device=dev, dtype=torch.float32)
+        self.gn_ws = torch.zeros(K.gn_ws_floats(B, groups), device=dev, dtype=torch.float32)
+        self.gnb_ws = torch.zeros(2 * B * max(Cin, Cout), device=dev, dtype=torch.float32)
+        wsrc = flat.p if self.dt == torch.float32 else flat.w        # fp32 masters (parity mode) or the bf16 working copy
+        n = lambda s: f"{prefix}.{s}"
+        self._wsrc = wsrc
+        geo = dict(B=B, H=H, W=W)
+        self.plan1 = K.ConvPlan(self.n1, wsrc(n("conv1.weight")), self.c1, Cin=Cin, Cout=Cout, ksize=3, bias=flat.p(n("conv1.bias")),
+                                rowbias=self.rowbias, rowbias_ld=Cout, **geo)
+        if self.shortcut:
+            self.plan_sc = K.ConvPlan(self.x, wsrc(n("conv_shortcut.weight")), self.sc, Cin=Cin, Cout=Cout, ksize=1,
+                                      bias=flat.p(n("conv_shortcut.bias")), **geo)
+        self.plan2 = K.ConvPlan(self.n2, wsrc(n("conv2.weight")), self.out, Cin=Cout, Cout=Cout, ksize=3, bias=flat.p(n("conv2.bias")),
+                                res1=self.sc if self.shortcut else self.x, **geo)
+        # data-gradient plans: the same implicit-GEMM kernel over the incoming gradient with flipped / transposed weights
+        self.w1d = torch.zeros(Cin, 9 * Cout, device=dev, dtype=self.dt)
+        self.w2d = torch.zeros(Cout, 9 * Cout, device=dev, dtype=self.dt)
+        self.plan_d2 = K.ConvPlan(self.d_out, self.w2d, self.dn2, Cin=Cout, Cout=Cout, ksize=3, **geo)
+        self.plan_d1 = K.ConvPlan(self.dc1, self.w1d, self.dn1, Cin=Cout, Cout=Cin, ksize=3, **geo)
+        if self.shortcut:
+            self.wscd = torch.zeros(Cin, Cout, device=dev, dtype=self.dt)
+            self.plan_dsc = K.ConvPlan(self.d_out, self.wscd, self.dsc, Cin=Cout, Cout=Cin, ksize=1, **geo)
+        self.refresh_dgrad_weights()
+
+    def refresh_dgrad_weights(self):
+        """Re-derive the data-gradient weights from the current parameters (after every optimizer step): a permuting copy."""
+        n = lambda s: f"{self.p}.{s}"
+        self.w1d.copy_(_dgrad_from_packed(self._wsrc(n("conv1.weight")), 3, self.dt))
+        self.w2d.copy_(_dgrad_from_packed(self._wsrc(n("conv2.weight")), 3, self.dt))
+        if self.shortcut:
+            self.wscd.copy_(_dgrad_from_packed(self._wsrc(n("conv_shortcut.weight")), 1, self.dt))
+
+    # ------------------------------------------------------------------------------------------------ forward
+    def forward(self, x: torch.Tensor, rowbias: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """x [B, HW, Cin] (activation dtype), rowbias [B, Cout] fp32 (None = 0).  Returns the block's output buffer."""
+        K, f, n = self.K, self.flat, (lambda s: f"{self.p}.{s}")
+        self.x.copy_(x.view_as(self.x))
+        if rowbias is None:
+            self.rowbias.zero_()
+        else:
+            self.rowbias.copy_(rowbias)
+        gn = dict(B=self.B, HW=self.HW, groups=self.groups, eps=self.eps, silu=True)
+        K.groupnorm(self.x, None, f.p(n("norm1.weight")), f.p(n("norm1.bias")), self.n1, self.gn_ws, **gn)     # resnet.py:337-338
+        self.plan1.run()                                                                                      # :367 + :369-379
+        K.groupnorm(self.c1, None, f.p(n("norm2.weight")), f.p(n("norm2.bias")), self.n2, self.gn_ws, **gn)    # :381,393
+        if self.shortcut:
+            self.plan_sc.run()                                                                                # :398-401
+        self.plan2.run()                                                                                      # :396 + :403
+        return self.out
+
+    # ------------------------------------------------------------------------------------------------ backward
+    def backward(self, d_out: torch.Tensor):
+        """d_out [B, HW, Cout].  Accumulates parameter gradients into flat.g(...); returns (d x, d rowbias) buffers."""
+        K, f, n = self.K, self.flat, (lambda s: f"{self.p}.{s}")
+        B, H, W, HW = self.B, self.H, self.W, self.HW
+        self.d_out.copy_(d_out.view_as(self.d_out))
+        gnb = dict(B=B, HW=HW, groups=self.groups, eps=self.eps, silu=True, accumulate=True)
+        # out = conv2(n2) + bias2 + shortcut(x)
+        K.conv_wgrad(self.n2, self.d_out, f.g(n("conv2.weight")), f.g(n("conv2.bias")), B=B, H=H, W=W, ksize=3, accumulate=True)
+        self.plan_d2.run()                                                          # d n2
+        # n2 = silu(groupnorm(c1))
+        K.groupnorm_bwd(self.c1, None, self.dn2, f.p(n("norm2.weight")), f.p(n("norm2.bias")), self.dc1, None, self.gnb_ws,
+                        dgamma=f.g(n("norm2.weight")), dbeta=f.g(n("norm2.bias")), **gnb)
+        # c1 = conv1(n1) + bias1 + rowbias[:, :, None, None]
+        K.conv_wgrad(self.n1, self.dc1, f.g(n("conv1.weight")), f.g(n("conv1.bias")), B=B, H=H, W=W, ksize=3, accumulate=True)
+        K.rowsum_per_image(self.dc1, self.d_rowbias, B=B, HW=HW)
+        self.plan_d1.run()                                                          # d n1
+        # shortcut path: identity -> d out itself; 1x1 conv -> its data gradient (+ its weight gradient)
+        if self.shortcut:
+            K.conv_wgrad(self.x, self.d_out, f.g(n("conv_shortcut.weight")), f.g(n("conv_shortcut.bias")), B=B, H=H, W=W, ksize=1,
+                         accumulate=True)
+            self.plan_dsc.run()
+            dres = self.dsc
+        else:
+            dres = self.d_out
+        # n1 = silu(groupnorm(x)); d x = that + the shortcut path's gradient, in the same pass
+        K.groupnorm_bwd(self.x, None, self.dn1, f.p(n("norm1.weight")), f.p(n("norm1.bias")), self.dx, None, self.gnb_ws,
+                        dgamma=f.g(n("norm1.weight")), dbeta=f.g(n("norm1.bias")), dres=dres, **gnb)
+        return self.dx, self.d_rowbias

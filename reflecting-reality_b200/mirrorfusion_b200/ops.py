@@ -340,6 +340,28 @@ def pack_conv_dgrad_weight(w: torch.Tensor) -> torch.Tensor:
     return pack_conv_weight(w.flip(2, 3).transpose(0, 1))
 
 
+def pack_conv_s2_dgrad_weight(w: torch.Tensor) -> torch.Tensor:
+    """Packed weight of the DATA gradient of the stride-2 conv3x3 (padding 1) of Downsample2D, for an `up2x` plan run on d y.
+    Output pixel (2i+py, 2j+px) of d x only receives the taps whose parity matches: along one axis, py = 0 takes kh = 1 from
+    d y[i]; py = 1 takes kh = 2 from d y[i] and kh = 0 from d y[i+1] — exactly the (phase, low-resolution offset) structure of
+    the sub-pixel Upsample2D plan ({-1, 0} for phase 0, {0, +1} for phase 1), with the unused tap zero.  So Downsample2D's
+    backward-data pass is ConvPlan(dy, packed, dx, B, H=Ho, W=Wo, Cin=Cout_fwd, Cout=Cin_fwd, ksize=3, up2x=True) on the
+    tcgen05 kernel (9 of the 16 phase taps carry weight).  OIHW [Cout, Cin, 3, 3] -> [4, Cin, 4*Cout]."""
+    w = w.float()
+    k_of = [[None, 1], [2, 0]]          # [phase][tap] -> kernel index (tap 0 / 1 = the lower / upper low-res offset of that phase)
+    zero = torch.zeros(w.shape[1], w.shape[0], dtype=w.dtype, device=w.device)
+    out = []
+    for py in range(2):
+        for px in range(2):
+            taps = []
+            for ty in range(2):
+                for tx in range(2):
+                    kh, kw = k_of[py][ty], k_of[px][tx]
+                    taps.append(zero if kh is None or kw is None else w[:, :, kh, kw].t())      # [Cin_fwd, Cout_fwd]
+            out.append(torch.stack(taps, 1).reshape(w.shape[1], -1))
+    return torch.stack(out, 0).to(act_dtype()).contiguous()
+
+
 def add_noise(x0, noise, timesteps, alphas_cumprod, noisy=None, velocity=None):
     """DDPMScheduler.add_noise / get_velocity; x0 / noise [B, ...] fp32, timesteps [B] int64, all on the device."""
     _req(x0, f32, "x0"); _req(noise, f32, "noise"); _req(timesteps, torch.int64, "timesteps"); _req(alphas_cumprod, f32, "alphas_cumprod")
@@ -396,8 +418,10 @@ def conv_wgrad(x, dy, dw, dbias=None, *, B, H, W, ksize, accumulate=False, ws=No
                                _stream()))
 
 
-def groupnorm_bwd(x1, x2, dy, gamma, beta, dx1, dx2, ws, *, B, HW, groups, eps, silu, dgamma=None, dbeta=None, accumulate=False):
-    """Backward of groupnorm(): dx (per source tensor of the concat), dgamma, dbeta.  ws: 2*B*C floats."""
+def groupnorm_bwd(x1, x2, dy, gamma, beta, dx1, dx2, ws, *, B, HW, groups, eps, silu, dgamma=None, dbeta=None, accumulate=False,
+                  dres=None):
+    """Backward of groupnorm(): dx (per source tensor of the concat), dgamma, dbeta.  ws: 2*B*C floats.
+    dres [B, HW, C]: gradient of the residual / shortcut path, added to dx in the same pass."""
     is32 = _is32(x1)
     C1 = x1.shape[-1]
     C2 = 0 if x2 is None else x2.shape[-1]
@@ -405,4 +429,11 @@ def groupnorm_bwd(x1, x2, dy, gamma, beta, dx1, dx2, ws, *, B, HW, groups, eps, 
     if ws.numel() < 2 * B * (C1 + C2):
         raise ValueError("groupnorm_bwd: workspace smaller than MFB_GN_BWD_WS_FLOATS(B, C)")
     check(lib().mfb_groupnorm_bwd(_ptr(x1), C1, _ptr(x2), C2, _ptr(dy), int(is32), B, HW, groups, eps, _ptr(gamma), _ptr(beta),
-                                  int(silu), _ptr(dx1), _ptr(dx2), _ptr(dgamma), _ptr(dbeta), _ptr(ws), int(accumulate), _stream()))
+                                  int(silu), _ptr(dres), _ptr(dx1), _ptr(dx2), _ptr(dgamma), _ptr(dbeta), _ptr(ws), int(accumulate),
+                                  _stream()))
+
+
+def rowsum_per_image(dy, out, *, B, HW):
+    """out [B, C] fp32 = per-image sums of dy [B, HW, C] over the pixels (gradient of the time-embedding row bias)."""
+    _req(out, f32, "out")
+    check(lib().mfb_rowsum_per_image(_ptr(dy), int(_is32(dy)), B, HW, dy.shape[-1], _ptr(out), _stream()))

@@ -22,11 +22,11 @@ import torch
 from . import ops
 from .schedulers import _alphas_cumprod
 
-_ALIGN = 4   # elements: every tensor starts on a 16-byte boundary of the fp32 buffers (8 bytes of the bf16 copy)
+_ALIGN = 8   # elements: every tensor starts on a 16-byte boundary of the bf16 working copy (TMA tensor-map bases) and 32 B of the fp32 buffers
 
 
 def flat_layout(shapes: Mapping[str, Tuple[int, ...]]) -> Tuple[Dict[str, Tuple[int, int]], int]:
-    """name -> (offset, numel) in the flat buffers, in the mapping's order, each offset a multiple of 4 elements."""
+    """name -> (offset, numel) in the flat buffers, in the mapping's order, each offset a multiple of 8 elements."""
     table, off = {}, 0
     for name, shp in shapes.items():
         n = int(np.prod(shp)) if len(shp) else 1

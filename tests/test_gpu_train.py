@@ -275,3 +275,76 @@ def test_groupnorm_silu_backward_vs_autograd(ops, dtype, B, HW, C1, C2, groups, 
                       accumulate=True)
     assert torch.equal(again, dx1)                         # deterministic
     assert rel(dg.cpu(), 2 * torch.from_numpy(dg_ref)) < 2e-5
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+@pytest.mark.parametrize("B,H,W,Cin,Cout", [(2, 16, 16, 64, 64), (1, 32, 32, 320, 320), (3, 8, 12, 128, 64)])
+def test_downsample_dgrad_runs_on_the_up2x_plan(ops, mode, B, H, W, Cin, Cout):
+    """Data gradient of Downsample2D's stride-2 conv3x3 (S/models/downsampling.py:146-152) = the sub-pixel up2x plan over dy
+    with the parity-selected taps (ops.pack_conv_s2_dgrad_weight); H, W are the forward INPUT size."""
+    dt = torch.float32 if mode == "fp32" else bf16
+    w = _randn(Cout, Cin, 3, 3, seed=3, scale=(9 * Cout) ** -0.5).to(dt).float()
+    dy = _randn(B, H // 2, W // 2, Cout, seed=2, dtype=dt)
+    x = torch.zeros(B, Cin, H, W, dtype=torch.float64, requires_grad=True)
+    F.conv2d(x, w.double().cpu(), stride=2, padding=1).backward(dy.double().permute(0, 3, 1, 2).cpu())
+    with ops.precision(mode):
+        wp = ops.pack_conv_s2_dgrad_weight(w)
+    dx = torch.full((B, H, W, Cin), float("nan"), device="cuda", dtype=dt)
+    plan = ops.ConvPlan(dy, wp, dx, B=B, H=H // 2, W=W // 2, Cin=Cout, Cout=Cin, ksize=3, up2x=True)
+    assert plan.launches == 4
+    plan.run()
+    err = rel(dx.float().permute(0, 3, 1, 2).cpu(), x.grad)
+    assert err < (1e-5 if mode == "fp32" else 4e-3)
+
+
+def test_rowsum_per_image(ops):
+    for dt in (torch.float32, bf16):
+        dy = _randn(3, 50, 72, seed=1, dtype=dt)
+        out = torch.full((3, 72), float("nan"), device="cuda")
+        ops.rowsum_per_image(dy, out, B=3, HW=50)
+        assert rel(out, dy.float().sum(1)) < 1e-6
+
+
+def test_groupnorm_backward_residual_addend(ops):
+    B, HW, C = 2, 64, 128
+    x, dy, dres = _randn(B, HW, C, seed=1), _randn(B, HW, C, seed=2), _randn(B, HW, C, seed=3)
+    gamma, beta = 1.0 + 0.2 * _randn(C, seed=4), 0.1 * _randn(C, seed=5)
+    ws = torch.zeros(2 * B * C, device="cuda")
+    a, b = torch.empty_like(x), torch.empty_like(x)
+    ops.groupnorm_bwd(x, None, dy, gamma, beta, a, None, ws, B=B, HW=HW, groups=32, eps=1e-5, silu=True)
+    ops.groupnorm_bwd(x, None, dy, gamma, beta, b, None, ws, B=B, HW=HW, groups=32, eps=1e-5, silu=True, dres=dres)
+    assert torch.allclose(b, a + dres, rtol=1e-6, atol=1e-6)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("tag", ["id", "sc"])
+def test_resnet_block_forward_backward_vs_reference_autograd(ops, precision, tag):
+    """One ResnetBlock2D trained on the kernels (mirrorfusion_b200/backward.py): forward, then backward twice (gradient
+    accumulation) against float64 autograd of the oracle block, which tests/test_oracle_train.py pins to the reference's own
+    ResnetBlock2D autograd.  fp32 parity mode: 5e-5; bf16 (two convs + two norms deep, bf16 activations and gradients): 3e-2."""
+    from mirrorfusion_b200.backward import ResnetBlockTrainer, pack_resnet_state_dict, resnet_param_shapes, unpack_conv_grad
+    from mirrorfusion_b200.train import FlatParams
+    if precision == "fp32":     # the reference-golden geometries
+        cin, cout = (64, 64) if tag == "id" else (64, 128)
+    else:                       # the bf16 GroupNorm kernels take 4 or >= 8 channels per group (every SD1.5 / VAE level)
+        cin, cout = (256, 256) if tag == "id" else (128, 256)
+    sd, x, emb, d_out = T.resnet_block_case(cin, cout)
+    ref = T.resnet_block_grads(sd, "r", x, emb, d_out)
+    B, _, H, W = x.shape
+    flat = FlatParams(resnet_param_shapes("r", cin, cout), "cuda")
+    flat.load_state_dict(pack_resnet_state_dict("r", sd))
+    blk = ResnetBlockTrainer(flat, "r", B=B, H=H, W=W, Cin=cin, Cout=cout, precision=precision)
+    dt = torch.float32 if precision == "fp32" else bf16
+    nhwc = lambda t: t.permute(0, 2, 3, 1).reshape(B, H * W, -1).contiguous()
+    tol = 5e-5 if precision == "fp32" else 3e-2
+    out = blk.forward(nhwc(x).cuda().to(dt), ref["rowbias"].float().cuda())
+    assert rel(out.float().cpu(), nhwc(ref["out"])) < (tol if precision == "fp32" else 1e-2)
+    for rep in range(2):
+        dx, drb = blk.backward(nhwc(d_out).cuda().to(dt))
+    assert rel(dx.float().cpu(), nhwc(ref["dx"])) < tol
+    assert rel(drb.cpu(), ref["d_rowbias"]) < tol
+    for name in flat.table:
+        want = ref[name]
+        got = flat.g(name).cpu()
+        got = unpack_conv_grad(got, 3) if want.dim() == 4 and want.shape[-1] == 3 else got.reshape(want.shape)
+        assert rel(got, 2 * want) < tol, name

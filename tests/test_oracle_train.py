@@ -5,6 +5,7 @@ Also the host-only weight transform of the conv data gradient."""
 import os
 
 import numpy as np
+import pytest
 import torch
 import torch.nn.functional as F
 
@@ -73,3 +74,76 @@ def test_dgrad_weight_transform_is_the_data_gradient():
         np.testing.assert_allclose(got.numpy(), dx, rtol=1e-4, atol=1e-4)
         # and the wgrad K order the kernel writes: dw[co][(kh, kw, ci)]
         assert dw.transpose(0, 2, 3, 1).reshape(24, -1).shape == (24, k * k * 16)
+
+
+def test_stride2_dgrad_weight_is_the_downsample_data_gradient():
+    # evaluate the four phase convolutions of the packed weight with plain torch and interleave them: must equal autograd's dx
+    import mirrorfusion_b200.ops as ops
+    gen = torch.Generator().manual_seed(3)
+    Cin, Cout, H, W = 6, 10, 8, 12
+    x = torch.randn(2, Cin, H, W, generator=gen, dtype=torch.float64, requires_grad=True)
+    w = torch.randn(Cout, Cin, 3, 3, generator=gen, dtype=torch.float64)
+    dy = torch.randn(2, Cout, H // 2, W // 2, generator=gen, dtype=torch.float64)
+    F.conv2d(x, w, stride=2, padding=1).backward(dy)
+    with ops.precision("fp32"):
+        wp = ops.pack_conv_s2_dgrad_weight(w).double()                   # [4, Cin, 4*Cout]
+    assert tuple(wp.shape) == (4, Cin, 4 * Cout)
+    dx = torch.zeros_like(x)
+    dyp = F.pad(dy, (1, 1, 1, 1))
+    for py in range(2):
+        for px in range(2):
+            wk = wp[py * 2 + px].view(Cin, 2, 2, Cout).permute(0, 3, 1, 2)  # taps (ty, tx) at low-res offsets {-1,0} / {0,+1}
+            y0 = 0 if py == 0 else 1
+            x0 = 0 if px == 0 else 1
+            win = dyp[:, :, y0:y0 + H // 2 + 1, x0:x0 + W // 2 + 1]
+            dx[:, :, py::2, px::2] = F.conv2d(win, wk)
+    np.testing.assert_allclose(dx.numpy(), x.grad.numpy(), rtol=1e-5, atol=1e-5)      # the packed weight is fp32
+
+
+def _block_case(tag):
+    cin, cout = (64, 64) if tag == "id" else (64, 128)
+    return (cin, cout) + T.resnet_block_case(cin, cout)
+
+
+@pytest.mark.parametrize("tag", ["id", "sc"])
+def test_resnet_block_grads_oracle_vs_reference_autograd(golden_dir, tag):
+    """oracle/train_oracle.resnet_block_grads against the reference's OWN ResnetBlock2D forward + autograd (fp32)."""
+    g = np.load(os.path.join(golden_dir, "resnet_block_grad.npz"))
+    cin, cout, sd, x, emb, d_out = _block_case(tag)
+    r = T.resnet_block_grads(sd, "r", x, emb, d_out)
+    for k in ("out", "dx", "d_rowbias"):
+        np.testing.assert_allclose(r[k].numpy(), g[f"{tag}_{k}"], rtol=2e-4, atol=2e-5)
+    for name in sd:
+        short = name[2:]
+        gr = r[name].reshape(-1)
+        assert abs(float(gr.norm()) - float(g[f"{tag}_g_{short}_norm"])) < 1e-4 * float(g[f"{tag}_g_{short}_norm"]), name
+        np.testing.assert_allclose(gr[torch.from_numpy(g[f"{tag}_g_{short}_idx"])].numpy(), g[f"{tag}_g_{short}_val"], rtol=2e-3, atol=2e-5)
+
+
+@pytest.mark.parametrize("tag", ["id", "sc"])
+def test_resnet_block_program_dataflow_on_the_cpu_stand_in(tag):
+    """The launch program of mirrorfusion_b200/backward.py (forward + backward of one block) run on tests/torch_kernels.py —
+    same call sequence, torch math — must reproduce the oracle's gradients: checks the PROGRAM (which buffer feeds which op,
+    the residual path, accumulation into the flat gradient buffer), not the kernels."""
+    import torch_kernels as TK
+    from mirrorfusion_b200.backward import ResnetBlockTrainer, pack_resnet_state_dict, resnet_param_shapes, unpack_conv_grad
+    from mirrorfusion_b200.train import FlatParams
+    cin, cout, sd, x, emb, d_out = _block_case(tag)
+    ref = T.resnet_block_grads(sd, "r", x, emb, d_out)
+    B, _, H, W = x.shape
+    flat = FlatParams(resnet_param_shapes("r", cin, cout), "cpu", with_bf16=False)
+    for k, v in pack_resnet_state_dict("r", sd).items():
+        flat.p(k).copy_(v)
+    blk = ResnetBlockTrainer(flat, "r", B=B, H=H, W=W, Cin=cin, Cout=cout, precision="fp32", K=TK)
+    nhwc = lambda t: t.permute(0, 2, 3, 1).reshape(B, H * W, -1).contiguous()
+    out = blk.forward(nhwc(x), ref["rowbias"].float())
+    np.testing.assert_allclose(out.numpy(), nhwc(ref["out"]).numpy(), rtol=1e-4, atol=1e-4)
+    for rep in range(2):                                   # gradients ACCUMULATE over micro-batches
+        dx, drb = blk.backward(nhwc(d_out))
+    np.testing.assert_allclose(dx.numpy(), nhwc(ref["dx"]).numpy(), rtol=1e-4, atol=1e-4)
+    np.testing.assert_allclose(drb.numpy(), ref["d_rowbias"].numpy(), rtol=1e-4, atol=1e-4)
+    for name in flat.table:
+        got = flat.g(name)
+        want = ref[name]
+        got = unpack_conv_grad(got, 3) if want.dim() == 4 and want.shape[-1] == 3 else got.reshape(want.shape)
+        np.testing.assert_allclose(got.numpy(), 2 * want.numpy(), rtol=2e-4, atol=2e-4, err_msg=name)

@@ -16,13 +16,13 @@ from oracle import train_oracle as T
 def test_flat_layout_alignment_and_views():
     shapes = {"a.weight": (5, 3), "a.bias": (5,), "s": (), "b.weight": (8, 4, 3, 3)}
     table, total = flat_layout(shapes)
-    assert all(off % 4 == 0 for off, _ in table.values())
-    assert table["a.weight"] == (0, 15) and table["a.bias"] == (16, 5) and table["s"] == (24, 1) and table["b.weight"][0] == 28
-    assert total == 28 + 288
+    assert all(off % 8 == 0 for off, _ in table.values())        # 16 B in the bf16 copy: TMA tensor-map bases
+    assert table["a.weight"] == (0, 15) and table["a.bias"] == (16, 5) and table["s"] == (24, 1) and table["b.weight"][0] == 32
+    assert total == 32 + 288
     fp = FlatParams(shapes, "cpu", with_bf16=False)
     fp.p("a.bias").fill_(2.0)
     assert fp.param[16:21].eq(2).all() and fp.param[21:24].eq(0).all()
-    assert fp.g("b.weight").shape == (8, 4, 3, 3) and fp.g("b.weight").data_ptr() == fp.grad[28:].data_ptr()
+    assert fp.g("b.weight").shape == (8, 4, 3, 3) and fp.g("b.weight").data_ptr() == fp.grad[32:].data_ptr()
 
 
 def test_adamw_scalars():

@@ -1,0 +1,79 @@
+"""CPU stand-in for the kernel namespace `mirrorfusion_b200.ops` — TEST INFRASTRUCTURE ONLY.  Same call signatures, plain torch fp32
+math on NHWC tensors, so that launch PROGRAMS written against the kernels (mirrorfusion_b200/backward.py) can be checked for their
+dataflow against the reference's autograd without a GPU.  It is never imported by the package; the product path has no CPU
+fallback (ops raises without CUDA)."""
+import torch
+import torch.nn.functional as F
+
+from mirrorfusion_b200.ops import gn_ws_floats, pack_conv_weight  # noqa: F401  (pure host functions)
+
+
+def _nchw(t, B, H, W):
+    return t.reshape(B, H, W, -1).permute(0, 3, 1, 2)
+
+
+def _nhwc(t):
+    return t.permute(0, 2, 3, 1)
+
+
+class ConvPlan:
+    """stride-1 subset of mfb_conv_desc: packed weight [Cout, k*k*Cin], bias, rowbias, res1."""
+
+    def __init__(self, x, w, out, *, B, H, W, Cin, Cout, ksize=1, bias=None, rowbias=None, rowbias_ld=0, res1=None):
+        assert tuple(w.shape) == (Cout, ksize * ksize * Cin)
+        self.a = (x, w, out, B, H, W, Cin, Cout, ksize, bias, rowbias, res1)
+        self.launches = 1
+
+    def run(self):
+        x, w, out, B, H, W, Cin, Cout, k, bias, rowbias, res1 = self.a
+        wk = w.view(Cout, k, k, Cin).permute(0, 3, 1, 2)
+        y = F.conv2d(_nchw(x, B, H, W).float(), wk.float(), bias, padding=k // 2)
+        if rowbias is not None:
+            y = y + rowbias[:, :Cout, None, None]
+        y = _nhwc(y).reshape(out.shape)
+        if res1 is not None:
+            y = y + res1.reshape(out.shape)
+        out.copy_(y)
+
+
+def groupnorm(x1, x2, gamma, beta, out, stats_ws, *, B, HW, groups, eps, silu, part1=None, part2=None):
+    x = x1 if x2 is None else torch.cat([x1, x2], -1)
+    y = F.group_norm(x.reshape(B, HW, -1).permute(0, 2, 1), groups, gamma, beta, eps)
+    if silu:
+        y = F.silu(y)
+    out.copy_(y.permute(0, 2, 1).reshape(out.shape))
+
+
+def groupnorm_bwd(x1, x2, dy, gamma, beta, dx1, dx2, ws, *, B, HW, groups, eps, silu, dgamma=None, dbeta=None, accumulate=False,
+                  dres=None):
+    x = (x1 if x2 is None else torch.cat([x1, x2], -1)).reshape(B, HW, -1).permute(0, 2, 1).detach().clone().requires_grad_(True)
+    g, b = gamma.detach().clone().requires_grad_(True), beta.detach().clone().requires_grad_(True)
+    y = F.group_norm(x, groups, g, b, eps)
+    if silu:
+        y = F.silu(y)
+    y.backward(dy.reshape(B, HW, -1).permute(0, 2, 1))
+    dx = x.grad.permute(0, 2, 1)
+    if dres is not None:
+        dx = dx + dres.reshape(B, HW, -1)
+    C1 = x1.shape[-1]
+    dx1.copy_(dx[..., :C1].reshape(dx1.shape))
+    if dx2 is not None:
+        dx2.copy_(dx[..., C1:].reshape(dx2.shape))
+    for dst, src in ((dgamma, g.grad), (dbeta, b.grad)):
+        if dst is not None:
+            dst.copy_(src + (dst if accumulate else 0))
+
+
+def conv_wgrad(x, dy, dw, dbias=None, *, B, H, W, ksize, accumulate=False, ws=None, cuda_cores=False):
+    Cin, Cout = x.shape[-1], dy.shape[-1]
+    w = torch.zeros(Cout, Cin, ksize, ksize, requires_grad=True)
+    b = torch.zeros(Cout, requires_grad=True)
+    F.conv2d(_nchw(x, B, H, W).float(), w, b, padding=ksize // 2).backward(_nchw(dy, B, H, W).float())
+    gw = w.grad.permute(0, 2, 3, 1).reshape(Cout, -1)
+    dw.copy_(gw + (dw if accumulate else 0))
+    if dbias is not None:
+        dbias.copy_(b.grad + (dbias if accumulate else 0))
+
+
+def rowsum_per_image(dy, out, *, B, HW):
+    out.copy_(dy.reshape(B, HW, -1).float().sum(1))
