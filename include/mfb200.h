@@ -244,21 +244,22 @@ int mfb_grad_sqnorm(const float* g, long long n, float* ws, float* out_sq, int a
 #define MFB_ADAMW_HYPER_FLOATS 12
 int mfb_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, void* param_bf16, long long n,
                    const float* hyper, const float* grad_sqnorm, float max_grad_norm, void* stream);
-/* Weight (and bias) gradient of a stride-1 conv3x3 / conv1x1 / linear layer (autograd of F.conv2d / F.linear behind
+/* Weight (and bias) gradient of a conv3x3 (stride 1 or 2) / conv1x1 / linear layer (autograd of F.conv2d / F.linear behind
  * LoRACompatibleConv/Linear, S/models/lora.py:363-377,445-451):
  *   dw[co][(kh, kw, ci)] (+)= sum_{b,h,w} dy[b,h,w,co] * x[b,h+kh-k/2,w+kw-k/2,ci] ;  dbias[co] (+)= sum dy[.,co]
- * x [B,H,W,Cin], dy [B,H,W,Cout] NHWC, dtype 0 = bf16 / 1 = fp32; dw fp32 in the packed [Cout, k*k*Cin] K order of
+ * x [B,H,W,Cin], dy [B,H/stride,W/stride,Cout] NHWC, dtype 0 = bf16 / 1 = fp32; stride 1, or 2 with ksize 3 and even H, W (Downsample2D,
+ * S/models/downsampling.py:146-152: taps read x[b, 2*oh+kh-1, 2*ow+kw-1]); dw fp32 in the packed [Cout, k*k*Cin] K order of
  * mfb_conv_desc.w.  CUDA-core kernel with fp32 accumulation, one CTA per output tile (deterministic).  The DATA gradient
  * of the same layer is mfb_conv_plan_create on dy with the flipped / transposed weight (ops.pack_conv_dgrad_weight). */
-int mfb_conv_wgrad(const void* x, const void* dy, int dtype, int B, int H, int W, int Cin, int Cout, int ksize, float* dw,
+int mfb_conv_wgrad(const void* x, const void* dy, int dtype, int B, int H, int W, int Cin, int Cout, int ksize, int stride, float* dw,
                    float* dbias, int accumulate, void* stream);
 /* The same weight gradient for bf16 operands on the tensor cores: split-K warp-MMA GEMM (mma.sync.m16n8k16, fp32 accumulate) that
  * consumes x and dy as stored (the pixel index is the reduction dimension: ldmatrix.trans, no transposed copies), fp32 partial
  * tiles per K slice in ws, summed in slice order (deterministic).  Needs Cin % 8 == 0 and Cout % 8 == 0 (every layer of the two
  * nets except conv_in / conv_in_condition, which take the CUDA-core mfb_conv_wgrad).  ws: mfb_conv_wgrad_tc_ws_floats(...) floats. */
-long long mfb_conv_wgrad_tc_ws_floats(int B, int H, int W, int Cin, int Cout, int ksize);
-int mfb_conv_wgrad_tc(const void* x, const void* dy, int B, int H, int W, int Cin, int Cout, int ksize, float* dw, float* dbias,
-                      int accumulate, float* ws, long long ws_floats, void* stream);
+long long mfb_conv_wgrad_tc_ws_floats(int B, int H, int W, int Cin, int Cout, int ksize, int stride);
+int mfb_conv_wgrad_tc(const void* x, const void* dy, int B, int H, int W, int Cin, int Cout, int ksize, int stride, float* dw,
+                      float* dbias, int accumulate, float* ws, long long ws_floats, void* stream);
 /* Backward of GroupNorm (+SiLU) (autograd of F.group_norm + F.silu, S/models/resnet.py:337-338,381,393), NHWC, dtype 0 = bf16 /
  * 1 = fp32 tensors, fp32 / fp64 math, statistics recomputed from x.  x2 / dx2: the second tensor of a channel concat (or NULL, C2 = 0)
  * exactly as in mfb_groupnorm; dy is [B, HW, C1+C2].  dgamma / dbeta [C1+C2] fp32 ((+)= with accumulate; either may be NULL).

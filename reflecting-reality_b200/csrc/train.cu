@@ -209,8 +209,9 @@ constexpr int WG_T = 64, WG_K = 16;
 
 template <typename T>
 __global__ void __launch_bounds__(256) wgrad_kernel(const T* __restrict__ x, const T* __restrict__ dy, int B, int H, int W, int Cin,
-                                                    int Cout, int ksize, float* __restrict__ dw, float* __restrict__ dbias,
-                                                    int accumulate) {
+                                                    int Cout, int ksize, int stride, float* __restrict__ dw,
+                                                    float* __restrict__ dbias, int accumulate) {
+    // H, W: the grid of dy (the conv OUTPUT); x is [B, H*stride, W*stride, Cin]
     pdl_trigger();
     pdl_wait();
     __shared__ __align__(16) float sdy[WG_K][WG_T];
@@ -234,9 +235,10 @@ __global__ void __launch_bounds__(256) wgrad_kernel(const T* __restrict__ x, con
             if (p < P) {
                 if (co0 + c < Cout) a = ld_as_float(dy + p * Cout + co0 + c);
                 const int w_ = static_cast<int>(p % W), h_ = static_cast<int>((p / W) % H);
-                const int hs = h_ + dh, ws = w_ + dwo;
-                if (hs >= 0 && hs < H && ws >= 0 && ws < W && ci0 + c < Cin)
-                    bv = ld_as_float(x + (p + static_cast<long long>(dh) * W + dwo) * Cin + ci0 + c);
+                const long long b_ = p / (static_cast<long long>(H) * W);
+                const int hs = h_ * stride + dh, ws = w_ * stride + dwo;
+                if (hs >= 0 && hs < H * stride && ws >= 0 && ws < W * stride && ci0 + c < Cin)
+                    bv = ld_as_float(x + ((b_ * (H * stride) + hs) * (W * stride) + ws) * Cin + ci0 + c);
             }
             sdy[k][c] = a;
             sx[k][c] = bv;
@@ -420,8 +422,9 @@ __device__ __forceinline__ void mma_bf16_16816(float* c, const uint32_t* a, uint
 }
 
 __global__ void __launch_bounds__(256, 2) wgrad_tc_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy, int B,
-                                                       int H, int W, int Cin, int Cout, int ksize, int slabs_per_slice,
+                                                       int H, int W, int Cin, int Cout, int ksize, int stride, int slabs_per_slice,
                                                        float* __restrict__ part) {
+    // H, W: the grid of dy (the conv OUTPUT); x is [B, H*stride, W*stride, Cin], stride 1 or 2
     pdl_trigger();
     pdl_wait();
     extern __shared__ __align__(16) unsigned char tc_smem[];
@@ -464,9 +467,12 @@ __global__ void __launch_bounds__(256, 2) wgrad_tc_kernel(const __nv_bfloat16* _
             const __nv_bfloat16* asrc = av ? dy + p * Cout + co0 + ch * 8 : dy;
             cp_async16_zfill(smem_u32(sA + (stage * TC_BK + row) * TC_LD + ch * 8), asrc, av);
             int h_ = static_cast<int>(hw[i] >> 16), w_ = static_cast<int>(hw[i] & 0xffffu);
-            const int hs = h_ + dh, ws = w_ + dwo;
-            const bool bv = pv && b_col_ok && hs >= 0 && hs < H && ws >= 0 && ws < W;
-            const __nv_bfloat16* bsrc = bv ? x + (p + static_cast<long long>(dh) * W + dwo) * Cin + ci0 + ch * 8 : x;
+            const int hs = h_ * stride + dh, ws = w_ * stride + dwo;
+            const bool bv = pv && b_col_ok && hs >= 0 && hs < H * stride && ws >= 0 && ws < W * stride;
+            // source pixel of x: stride 1: p + dh*W + dw.  stride 2 (input 2H x 2W): ((b*2H + 2h + dh)*2W + 2w + dw) = 4p - 2w + dh*2W + dw
+            const long long sp = stride == 1 ? p + static_cast<long long>(dh) * W + dwo
+                                             : 4 * p - 2 * w_ + static_cast<long long>(dh) * (2 * W) + dwo;
+            const __nv_bfloat16* bsrc = bv ? x + sp * Cin + ci0 + ch * 8 : x;
             cp_async16_zfill(smem_u32(sB + (stage * TC_BK + row) * TC_LD + ch * 8), bsrc, bv);
             w_ += adv_w;
             h_ += adv_h;
@@ -645,9 +651,11 @@ extern "C" int mfb_adamw_step(float* param, const float* grad, float* exp_avg, f
     return MFB_OK;
 }
 
-extern "C" int mfb_conv_wgrad(const void* x, const void* dy, int dtype, int B, int H, int W, int Cin, int Cout, int ksize,
+extern "C" int mfb_conv_wgrad(const void* x, const void* dy, int dtype, int B, int H, int W, int Cin, int Cout, int ksize, int stride,
                               float* dw, float* dbias, int accumulate, void* stream) {
     MFB_REQUIRE(x && dy && dw, "null pointer");
+    MFB_REQUIRE((stride == 1 || (stride == 2 && ksize == 3)) && H % stride == 0 && W % stride == 0, "stride must be 1, or 2 with ksize 3 and even H, W");
+    const int Ho = H / stride, Wo = W / stride;
     MFB_REQUIRE((ksize == 1 || ksize == 3) && B > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0, "bad geometry");
     MFB_REQUIRE(dtype == 0 || dtype == 1, "dtype must be 0 (bf16) or 1 (fp32)");
     const dim3 grid((Cin + WG_T - 1) / WG_T, (Cout + WG_T - 1) / WG_T, ksize * ksize);
@@ -655,10 +663,10 @@ extern "C" int mfb_conv_wgrad(const void* x, const void* dy, int dtype, int B, i
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (dtype == 1) {
         MFB_CUDA_OK(launch_k(wgrad_kernel<float>, grid, dim3(256), 0, st, 1, static_cast<const float*>(x),
-                             static_cast<const float*>(dy), B, H, W, Cin, Cout, ksize, dw, dbias, accumulate));
+                             static_cast<const float*>(dy), B, Ho, Wo, Cin, Cout, ksize, stride, dw, dbias, accumulate));
     } else {
         MFB_CUDA_OK(launch_k(wgrad_kernel<__nv_bfloat16>, grid, dim3(256), 0, st, 1, static_cast<const __nv_bfloat16*>(x),
-                             static_cast<const __nv_bfloat16*>(dy), B, H, W, Cin, Cout, ksize, dw, dbias, accumulate));
+                             static_cast<const __nv_bfloat16*>(dy), B, Ho, Wo, Cin, Cout, ksize, stride, dw, dbias, accumulate));
     }
     return MFB_OK;
 }
@@ -696,7 +704,7 @@ extern "C" int mfb_groupnorm_bwd(const void* x1, int C1, const void* x2, int C2,
 // split-K plan of the tensor-core weight gradient.  Two CTAs fit an SM (104 KB smem, 126 registers), so one wave holds
 // 2 x 148 CTAs; the slice count minimises  waves(tiles * S) x slabs-per-slice  (wave quantisation cost the first version
 // almost 2x: 324 CTAs = 1.09 waves), at least 4 slabs per slice, at most 32 slices (the reduce pass reads S partial tiles).
-static void wgrad_tc_plan(int B, int H, int W, int Cin, int Cout, int ksize, int* slices, int* slabs_per_slice) {
+static void wgrad_tc_plan(int B, int H, int W, int Cin, int Cout, int ksize, int* slices, int* slabs_per_slice) {   // H, W: dy grid
     const long long P = static_cast<long long>(B) * H * W;
     const int nslab = static_cast<int>((P + TC_BK - 1) / TC_BK);
     const int tiles = ((Cin + TC_BN - 1) / TC_BN) * ((Cout + TC_BM - 1) / TC_BM) * ksize * ksize;
@@ -721,22 +729,26 @@ static void wgrad_tc_plan(int B, int H, int W, int Cin, int Cout, int ksize, int
 
 #define MFB_DBIAS_SLICES 32
 
-extern "C" long long mfb_conv_wgrad_tc_ws_floats(int B, int H, int W, int Cin, int Cout, int ksize) {
-    if (B <= 0 || H <= 0 || W <= 0 || Cin <= 0 || Cout <= 0 || (ksize != 1 && ksize != 3)) return 0;
+extern "C" long long mfb_conv_wgrad_tc_ws_floats(int B, int H, int W, int Cin, int Cout, int ksize, int stride) {
+    if (B <= 0 || H <= 0 || W <= 0 || Cin <= 0 || Cout <= 0 || (ksize != 1 && ksize != 3) || (stride != 1 && stride != 2) ||
+        H % stride || W % stride)
+        return 0;
     int slices, per;
-    wgrad_tc_plan(B, H, W, Cin, Cout, ksize, &slices, &per);
+    wgrad_tc_plan(B, H / stride, W / stride, Cin, Cout, ksize, &slices, &per);
     return static_cast<long long>(slices) * Cout * ksize * ksize * Cin + static_cast<long long>(MFB_DBIAS_SLICES) * Cout;
 }
 
-extern "C" int mfb_conv_wgrad_tc(const void* x, const void* dy, int B, int H, int W, int Cin, int Cout, int ksize, float* dw,
-                                 float* dbias, int accumulate, float* ws, long long ws_floats, void* stream) {
+extern "C" int mfb_conv_wgrad_tc(const void* x, const void* dy, int B, int H, int W, int Cin, int Cout, int ksize, int stride,
+                                 float* dw, float* dbias, int accumulate, float* ws, long long ws_floats, void* stream) {
     MFB_REQUIRE(x && dy && dw && ws, "null pointer");
+    MFB_REQUIRE((stride == 1 || (stride == 2 && ksize == 3)) && H % stride == 0 && W % stride == 0, "stride must be 1, or 2 with ksize 3 and even H, W");
     MFB_REQUIRE((ksize == 1 || ksize == 3) && B > 0 && H > 0 && W > 0 && H < 65536 && W < 65536, "bad geometry");
     MFB_REQUIRE(Cin > 0 && Cout > 0 && Cin % 8 == 0 && Cout % 8 == 0, "tensor-core weight gradient needs Cin %% 8 == 0 and Cout %% 8 == 0 (got %d, %d)",
                 Cin, Cout);
-    MFB_REQUIRE(ws_floats >= mfb_conv_wgrad_tc_ws_floats(B, H, W, Cin, Cout, ksize), "workspace too small");
+    MFB_REQUIRE(ws_floats >= mfb_conv_wgrad_tc_ws_floats(B, H, W, Cin, Cout, ksize, stride), "workspace too small");
+    const int Ho = H / stride, Wo = W / stride;
     int slices, per;
-    wgrad_tc_plan(B, H, W, Cin, Cout, ksize, &slices, &per);
+    wgrad_tc_plan(B, Ho, Wo, Cin, Cout, ksize, &slices, &per);
     const int taps = ksize * ksize, ktot = taps * Cin;
     const int mtiles = (Cout + TC_BM - 1) / TC_BM, ntiles = (Cin + TC_BN - 1) / TC_BN;
     MFB_REQUIRE(mtiles * taps <= 65535, "Cout too large");
@@ -747,13 +759,14 @@ extern "C" int mfb_conv_wgrad_tc(const void* x, const void* dy, int B, int H, in
         attr_set = true;
     }
     MFB_CUDA_OK(launch_k(wgrad_tc_kernel, dim3(ntiles, mtiles * taps, slices), dim3(256), TC_SMEM, st, 1,
-                         static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(dy), B, H, W, Cin, Cout, ksize, per, ws));
+                         static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(dy), B, Ho, Wo, Cin, Cout, ksize, stride,
+                         per, ws));
     const long long n = static_cast<long long>(Cout) * ktot;
     MFB_CUDA_OK(launch_k(wgrad_reduce_kernel, dim3(chunks_for(n, 256, 148 * 8)), dim3(256), 0, st, 1, static_cast<const float*>(ws), slices,
                          n, dw, accumulate));
     if (dbias) {
         float* bpart = ws + static_cast<size_t>(slices) * n;
-        const long long P = static_cast<long long>(B) * H * W;
+        const long long P = static_cast<long long>(B) * Ho * Wo;
         MFB_CUDA_OK(launch_k(dbias_partial_kernel, dim3((Cout + 63) / 64, MFB_DBIAS_SLICES), dim3(256), 0, st, 1,
                              static_cast<const __nv_bfloat16*>(dy), P, Cout, bpart));
         MFB_CUDA_OK(launch_k(wgrad_reduce_kernel, dim3(chunks_for(Cout, 256, 8)), dim3(256), 0, st, 1, static_cast<const float*>(bpart),

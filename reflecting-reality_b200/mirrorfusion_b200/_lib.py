@@ -71,9 +71,9 @@ _SIGS = {
     "mfb_mse_loss": (i32, [vp, vp, vp, i32, i64, vp, vp, vp, vp, vp]),
     "mfb_grad_sqnorm": (i32, [vp, i64, vp, vp, i32, vp]),
     "mfb_adamw_step": (i32, [vp, vp, vp, vp, vp, i64, vp, vp, f32, vp]),
-    "mfb_conv_wgrad": (i32, [vp, vp, i32, i32, i32, i32, i32, i32, i32, vp, vp, i32, vp]),
-    "mfb_conv_wgrad_tc_ws_floats": (i64, [i32, i32, i32, i32, i32, i32]),
-    "mfb_conv_wgrad_tc": (i32, [vp, vp, i32, i32, i32, i32, i32, i32, vp, vp, i32, vp, i64, vp]),
+    "mfb_conv_wgrad": (i32, [vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, vp, vp, i32, vp]),
+    "mfb_conv_wgrad_tc_ws_floats": (i64, [i32, i32, i32, i32, i32, i32, i32]),
+    "mfb_conv_wgrad_tc": (i32, [vp, vp, i32, i32, i32, i32, i32, i32, i32, vp, vp, i32, vp, i64, vp]),
     "mfb_groupnorm_bwd": (i32, [vp, i32, vp, i32, vp, i32, i32, i32, i32, f32, vp, vp, i32, vp, vp, vp, vp, vp, vp, i32, vp]),
     "mfb_rowsum_per_image": (i32, [vp, i32, i32, i32, i32, vp, vp]),
 }

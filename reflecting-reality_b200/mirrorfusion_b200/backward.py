@@ -158,3 +158,55 @@ class ResnetBlockTrainer:
         K.groupnorm_bwd(self.x, None, self.dn1, f.p(n("norm1.weight")), f.p(n("norm1.bias")), self.dx, None, self.gnb_ws,
                         dgamma=f.g(n("norm1.weight")), dbeta=f.g(n("norm1.bias")), dres=dres, **gnb)
         return self.dx, self.d_rowbias
+
+
+class DownsampleTrainer:
+    """Downsample2D (conv3x3, stride 2, padding 1; S/models/downsampling.py:134-154) forward and backward on the kernels.
+    Forward: the stride-2 implicit-GEMM plan (four parity-view tensor maps).  Backward: weight / bias gradient by the stride-2
+    weight-gradient kernel, data gradient by the sub-pixel `up2x` plan over d y with parity-selected taps
+    (ops.pack_conv_s2_dgrad_weight) — the same tcgen05 kernel again.  Flat entries: `<prefix>.conv.weight` packed [C, 9*C],
+    `<prefix>.conv.bias` [C]."""
+
+    def __init__(self, flat: FlatParams, prefix: str, *, B: int, H: int, W: int, C: int, precision: str = "bf16", K=None):
+        K = _ops if K is None else K
+        if H % 2 or W % 2:
+            raise ValueError("Downsample2D backward needs even H, W")
+        self.K, self.flat, self.p, self.B, self.H, self.W, self.C = K, flat, prefix, B, H, W, C
+        self.dt = torch.float32 if precision == "fp32" else torch.bfloat16
+        dev = flat.param.device
+        self._wsrc = flat.p if self.dt == torch.float32 else flat.w
+        self.x = torch.zeros(B, H * W, C, device=dev, dtype=self.dt)
+        self.out = torch.zeros(B, (H // 2) * (W // 2), C, device=dev, dtype=self.dt)
+        self.d_out, self.dx = torch.zeros_like(self.out), torch.zeros_like(self.x)
+        self.plan = K.ConvPlan(self.x, self._wsrc(f"{prefix}.conv.weight"), self.out, B=B, H=H, W=W, Cin=C, Cout=C, ksize=3, stride=2,
+                               bias=flat.p(f"{prefix}.conv.bias"))
+        self.wd = torch.zeros(4, C, 4 * C, device=dev, dtype=self.dt)
+        self.plan_d = K.ConvPlan(self.d_out, self.wd, self.dx, B=B, H=H // 2, W=W // 2, Cin=C, Cout=C, ksize=3, up2x=True)
+        self.refresh_dgrad_weights()
+
+    def refresh_dgrad_weights(self):
+        w = unpack_conv_grad(self._wsrc(f"{self.p}.conv.weight").float(), 3)          # packed -> OIHW
+        k_of = [[None, 1], [2, 0]]          # see ops.pack_conv_s2_dgrad_weight
+        for py in range(2):
+            for px in range(2):
+                for ty in range(2):
+                    for tx in range(2):
+                        kh, kw = k_of[py][ty], k_of[px][tx]
+                        blk = self.wd[py * 2 + px].view(self.C, 4, self.C)[:, ty * 2 + tx]
+                        if kh is None or kw is None:
+                            blk.zero_()
+                        else:
+                            blk.copy_(w[:, :, kh, kw].t().to(self.dt))
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        self.x.copy_(x.view_as(self.x))
+        self.plan.run()
+        return self.out
+
+    def backward(self, d_out: torch.Tensor) -> torch.Tensor:
+        f = self.flat
+        self.d_out.copy_(d_out.view_as(self.d_out))
+        self.K.conv_wgrad(self.x, self.d_out, f.g(f"{self.p}.conv.weight"), f.g(f"{self.p}.conv.bias"), B=self.B, H=self.H, W=self.W,
+                          ksize=3, stride=2, accumulate=True)
+        self.plan_d.run()
+        return self.dx

@@ -392,13 +392,14 @@ def adamw_step(param, grad, exp_avg, exp_avg_sq, hyper, param_bf16=None, grad_sq
                                _ptr(hyper), _ptr(grad_sqnorm), float(max_grad_norm), _stream()))
 
 
-def conv_wgrad_ws_floats(B, H, W, Cin, Cout, ksize) -> int:
-    """Workspace (floats) of the tensor-core weight gradient for this layer geometry."""
-    return int(_lib.load().mfb_conv_wgrad_tc_ws_floats(B, H, W, Cin, Cout, ksize))
+def conv_wgrad_ws_floats(B, H, W, Cin, Cout, ksize, stride=1) -> int:
+    """Workspace (floats) of the tensor-core weight gradient for this layer geometry (H, W: the conv INPUT size)."""
+    return int(_lib.load().mfb_conv_wgrad_tc_ws_floats(B, H, W, Cin, Cout, ksize, stride))
 
 
-def conv_wgrad(x, dy, dw, dbias=None, *, B, H, W, ksize, accumulate=False, ws=None, cuda_cores=False):
-    """dw [Cout, k*k*Cin] fp32 (packed K order) and dbias [Cout] of a stride-1 conv / linear; x, dy NHWC bf16 or fp32.
+def conv_wgrad(x, dy, dw, dbias=None, *, B, H, W, ksize, stride=1, accumulate=False, ws=None, cuda_cores=False):
+    """dw [Cout, k*k*Cin] fp32 (packed K order) and dbias [Cout] of a conv (stride 1, or 2 for the 3x3 of Downsample2D) / linear;
+    x [B,H,W,Cin], dy [B,H/stride,W/stride,Cout] NHWC bf16 or fp32.
     bf16 operands with Cin, Cout multiples of 8 run on the tensor cores (ws: conv_wgrad_ws_floats(...) floats, allocated per call
     if not given); fp32 operands (parity mode), ragged channel counts or cuda_cores=True take the CUDA-core kernel."""
     is32 = _is32(x)
@@ -407,14 +408,14 @@ def conv_wgrad(x, dy, dw, dbias=None, *, B, H, W, ksize, accumulate=False, ws=No
     if tuple(dw.shape) != (Cout, ksize * ksize * Cin):
         raise ValueError(f"dw shape {tuple(dw.shape)} != {(Cout, ksize * ksize * Cin)}")
     if not is32 and not cuda_cores and Cin % 8 == 0 and Cout % 8 == 0:
-        need = conv_wgrad_ws_floats(B, H, W, Cin, Cout, ksize)
+        need = conv_wgrad_ws_floats(B, H, W, Cin, Cout, ksize, stride)
         if ws is None:
             ws = torch.empty(need, device=x.device, dtype=f32)
         _req(ws, f32, "ws")
-        check(lib().mfb_conv_wgrad_tc(_ptr(x), _ptr(dy), B, H, W, Cin, Cout, ksize, _ptr(dw), _ptr(dbias), int(accumulate), _ptr(ws),
-                                      ws.numel(), _stream()))
+        check(lib().mfb_conv_wgrad_tc(_ptr(x), _ptr(dy), B, H, W, Cin, Cout, ksize, stride, _ptr(dw), _ptr(dbias), int(accumulate),
+                                      _ptr(ws), ws.numel(), _stream()))
         return
-    check(lib().mfb_conv_wgrad(_ptr(x), _ptr(dy), int(is32), B, H, W, Cin, Cout, ksize, _ptr(dw), _ptr(dbias), int(accumulate),
+    check(lib().mfb_conv_wgrad(_ptr(x), _ptr(dy), int(is32), B, H, W, Cin, Cout, ksize, stride, _ptr(dw), _ptr(dbias), int(accumulate),
                                _stream()))
 
 

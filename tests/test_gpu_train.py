@@ -348,3 +348,49 @@ def test_resnet_block_forward_backward_vs_reference_autograd(ops, precision, tag
         got = flat.g(name).cpu()
         got = unpack_conv_grad(got, 3) if want.dim() == 4 and want.shape[-1] == 3 else got.reshape(want.shape)
         assert rel(got, 2 * want) < tol, name
+
+
+@pytest.mark.parametrize("path", ["fp32", "bf16_cuda_cores", "bf16_tensor_cores"])
+@pytest.mark.parametrize("B,H,W,Cin,Cout", [(2, 16, 16, 64, 64), (1, 32, 32, 320, 320), (3, 8, 12, 24, 40)])
+def test_conv_wgrad_stride2_vs_autograd(ops, path, B, H, W, Cin, Cout):
+    """Weight / bias gradient of Downsample2D's stride-2 conv3x3 (x [B,H,W,Cin], dy [B,H/2,W/2,Cout])."""
+    dtype = torch.float32 if path == "fp32" else bf16
+    x = _randn(B, H, W, Cin, seed=1, dtype=dtype)
+    dy = _randn(B, H // 2, W // 2, Cout, seed=2, dtype=dtype)
+    w = torch.zeros(Cout, Cin, 3, 3, dtype=torch.float64, requires_grad=True)
+    b = torch.zeros(Cout, dtype=torch.float64, requires_grad=True)
+    F.conv2d(x.double().permute(0, 3, 1, 2).cpu(), w, b, stride=2, padding=1).backward(dy.double().permute(0, 3, 1, 2).cpu())
+    dw_ref = w.grad.permute(0, 2, 3, 1).reshape(Cout, -1)
+    dw = torch.full((Cout, 9 * Cin), float("nan"), device="cuda")
+    db = torch.full((Cout,), float("nan"), device="cuda")
+    ops.conv_wgrad(x, dy, dw, db, B=B, H=H, W=W, ksize=3, stride=2, cuda_cores=(path == "bf16_cuda_cores"))
+    tol = 2e-5 if path == "bf16_tensor_cores" else 5e-6
+    assert rel(dw.cpu(), dw_ref) < tol and rel(db.cpu(), b.grad) < tol
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_downsample_forward_backward_vs_autograd(ops, precision):
+    """Downsample2D trained on the kernels (backward.DownsampleTrainer) against float64 autograd of the oracle's downsample."""
+    from mirrorfusion_b200.backward import DownsampleTrainer, unpack_conv_grad
+    from mirrorfusion_b200.train import FlatParams
+    from oracle import mf_oracle as O
+    gen = torch.Generator().manual_seed(21)
+    B, C, H, W = 2, 128, 16, 16
+    sd = {"d.conv.weight": (torch.randn(C, C, 3, 3, generator=gen, dtype=torch.float64) * (9 * C) ** -0.5).requires_grad_(True),
+          "d.conv.bias": (torch.randn(C, generator=gen, dtype=torch.float64) * 0.1).requires_grad_(True)}
+    x = torch.randn(B, C, H, W, generator=gen, dtype=torch.float64, requires_grad=True)
+    d_out = torch.randn(B, C, H // 2, W // 2, generator=gen, dtype=torch.float64)
+    y = O.downsample(sd, "d", x)
+    y.backward(d_out)
+    flat = FlatParams({"d.conv.weight": (C, 9 * C), "d.conv.bias": (C,)}, "cuda")
+    flat.load_state_dict({"d.conv.weight": sd["d.conv.weight"].detach().permute(0, 2, 3, 1).reshape(C, -1).float(),
+                          "d.conv.bias": sd["d.conv.bias"].detach().float()})
+    blk = DownsampleTrainer(flat, "d", B=B, H=H, W=W, C=C, precision=precision)
+    dt = torch.float32 if precision == "fp32" else bf16
+    nhwc = lambda t: t.detach().permute(0, 2, 3, 1).reshape(B, -1, C).contiguous()
+    tol = 2e-5 if precision == "fp32" else 1e-2
+    assert rel(blk.forward(nhwc(x).float().cuda().to(dt)).float().cpu(), nhwc(y)) < tol
+    dx = blk.backward(nhwc(d_out).float().cuda().to(dt))
+    assert rel(dx.float().cpu(), nhwc(x.grad)) < tol
+    assert rel(unpack_conv_grad(flat.g("d.conv.weight"), 3).cpu(), sd["d.conv.weight"].grad) < tol
+    assert rel(flat.g("d.conv.bias").cpu(), sd["d.conv.bias"].grad) < tol

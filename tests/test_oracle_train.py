@@ -147,3 +147,30 @@ def test_resnet_block_program_dataflow_on_the_cpu_stand_in(tag):
         want = ref[name]
         got = unpack_conv_grad(got, 3) if want.dim() == 4 and want.shape[-1] == 3 else got.reshape(want.shape)
         np.testing.assert_allclose(got.numpy(), 2 * want.numpy(), rtol=2e-4, atol=2e-4, err_msg=name)
+
+
+def test_downsample_program_dataflow_on_the_cpu_stand_in():
+    """DownsampleTrainer (forward stride-2 plan, weight gradient, data gradient through the up2x plan) on tests/torch_kernels.py
+    against autograd of the oracle's Downsample2D (oracle/mf_oracle.py `downsample`)."""
+    import torch_kernels as TK
+    from mirrorfusion_b200.backward import DownsampleTrainer, unpack_conv_grad
+    from mirrorfusion_b200.train import FlatParams
+    from oracle import mf_oracle as O
+    gen = torch.Generator().manual_seed(21)
+    B, C, H, W = 2, 16, 8, 12
+    sd = {"d.conv.weight": (torch.randn(C, C, 3, 3, generator=gen) * 0.1).requires_grad_(True),
+          "d.conv.bias": (torch.randn(C, generator=gen) * 0.1).requires_grad_(True)}
+    x = torch.randn(B, C, H, W, generator=gen, requires_grad=True)
+    d_out = torch.randn(B, C, H // 2, W // 2, generator=gen)
+    y = O.downsample(sd, "d", x)
+    y.backward(d_out)
+    flat = FlatParams({"d.conv.weight": (C, 9 * C), "d.conv.bias": (C,)}, "cpu", with_bf16=False)
+    flat.p("d.conv.weight").copy_(sd["d.conv.weight"].detach().permute(0, 2, 3, 1).reshape(C, -1))
+    flat.p("d.conv.bias").copy_(sd["d.conv.bias"].detach())
+    blk = DownsampleTrainer(flat, "d", B=B, H=H, W=W, C=C, precision="fp32", K=TK)
+    nhwc = lambda t: t.detach().permute(0, 2, 3, 1).reshape(B, -1, C).contiguous()
+    np.testing.assert_allclose(blk.forward(nhwc(x)).numpy(), nhwc(y).numpy(), rtol=1e-5, atol=1e-5)
+    dx = blk.backward(nhwc(d_out))
+    np.testing.assert_allclose(dx.numpy(), nhwc(x.grad).numpy(), rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(unpack_conv_grad(flat.g("d.conv.weight"), 3).numpy(), sd["d.conv.weight"].grad.numpy(), rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(flat.g("d.conv.bias").numpy(), sd["d.conv.bias"].grad.numpy(), rtol=1e-4, atol=1e-5)

@@ -17,17 +17,29 @@ def _nhwc(t):
 
 
 class ConvPlan:
-    """stride-1 subset of mfb_conv_desc: packed weight [Cout, k*k*Cin], bias, rowbias, res1."""
+    """Subset of mfb_conv_desc: packed weight [Cout, k*k*Cin], stride 1 / 2, bias, rowbias, res1, and the `up2x` sub-pixel form
+    ([4, Cout, 4*Cin]: phase (py, px) is a 2x2 conv over the low-resolution input at offsets {-1, 0} / {0, +1})."""
 
-    def __init__(self, x, w, out, *, B, H, W, Cin, Cout, ksize=1, bias=None, rowbias=None, rowbias_ld=0, res1=None):
-        assert tuple(w.shape) == (Cout, ksize * ksize * Cin)
+    def __init__(self, x, w, out, *, B, H, W, Cin, Cout, ksize=1, stride=1, bias=None, rowbias=None, rowbias_ld=0, res1=None,
+                 up2x=False):
+        assert tuple(w.shape) == ((4, Cout, 4 * Cin) if up2x else (Cout, ksize * ksize * Cin))
         self.a = (x, w, out, B, H, W, Cin, Cout, ksize, bias, rowbias, res1)
-        self.launches = 1
+        self.stride, self.up2x = stride, up2x
+        self.launches = 4 if up2x else 1
 
     def run(self):
         x, w, out, B, H, W, Cin, Cout, k, bias, rowbias, res1 = self.a
+        if self.up2x:
+            xp = F.pad(_nchw(x, B, H, W).float(), (1, 1, 1, 1))
+            y = torch.zeros(B, Cout, 2 * H, 2 * W)
+            for py in range(2):
+                for px in range(2):
+                    wk = w[py * 2 + px].view(Cout, 2, 2, Cin).permute(0, 3, 1, 2).float()
+                    y[:, :, py::2, px::2] = F.conv2d(xp[:, :, py:py + H + 1, px:px + W + 1], wk, bias)
+            out.copy_(_nhwc(y).reshape(out.shape))
+            return
         wk = w.view(Cout, k, k, Cin).permute(0, 3, 1, 2)
-        y = F.conv2d(_nchw(x, B, H, W).float(), wk.float(), bias, padding=k // 2)
+        y = F.conv2d(_nchw(x, B, H, W).float(), wk.float(), bias, stride=self.stride, padding=k // 2)
         if rowbias is not None:
             y = y + rowbias[:, :Cout, None, None]
         y = _nhwc(y).reshape(out.shape)
@@ -64,11 +76,11 @@ def groupnorm_bwd(x1, x2, dy, gamma, beta, dx1, dx2, ws, *, B, HW, groups, eps, 
             dst.copy_(src + (dst if accumulate else 0))
 
 
-def conv_wgrad(x, dy, dw, dbias=None, *, B, H, W, ksize, accumulate=False, ws=None, cuda_cores=False):
+def conv_wgrad(x, dy, dw, dbias=None, *, B, H, W, ksize, stride=1, accumulate=False, ws=None, cuda_cores=False):
     Cin, Cout = x.shape[-1], dy.shape[-1]
     w = torch.zeros(Cout, Cin, ksize, ksize, requires_grad=True)
     b = torch.zeros(Cout, requires_grad=True)
-    F.conv2d(_nchw(x, B, H, W).float(), w, b, padding=ksize // 2).backward(_nchw(dy, B, H, W).float())
+    F.conv2d(_nchw(x, B, H, W).float(), w, b, stride=stride, padding=ksize // 2).backward(_nchw(dy, B, H // stride, W // stride).float())
     gw = w.grad.permute(0, 2, 3, 1).reshape(Cout, -1)
     dw.copy_(gw + (dw if accumulate else 0))
     if dbias is not None:
