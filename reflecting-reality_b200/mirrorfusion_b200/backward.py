@@ -210,3 +210,144 @@ class DownsampleTrainer:
                           ksize=3, stride=2, accumulate=True)
         self.plan_d.run()
         return self.dx
+
+
+class ZeroConvTap:
+    """One BrushNet zero-conv (1x1, S/models/brushnet.py:831-834,851): tap = conv1x1(h) (+ bias), forward and backward.
+    Backward also folds the fan-out of h: d h = W^T d tap + (the gradient arriving from h's other consumer), the sum done by
+    the data-gradient plan's residual epilogue.  Flat entries `<name>.weight` [C, C] (a packed 1x1) and `<name>.bias` [C]."""
+
+    def __init__(self, flat: FlatParams, name: str, h: torch.Tensor, d_other: Optional[torch.Tensor], *, B, H, W, C, dt, K):
+        self.K, self.flat, self.name, self.h, self.geo = K, flat, name, h, dict(B=B, H=H, W=W)
+        dev = flat.param.device
+        self._wsrc = flat.p if dt == torch.float32 else flat.w
+        self.tap = torch.zeros(B, H * W, C, device=dev, dtype=dt)
+        self.d_tap, self.dh = torch.zeros_like(self.tap), torch.zeros_like(self.tap)
+        self.wd = torch.zeros(C, C, device=dev, dtype=dt)
+        self.plan = K.ConvPlan(h, self._wsrc(f"{name}.weight"), self.tap, Cin=C, Cout=C, ksize=1, bias=flat.p(f"{name}.bias"), **self.geo)
+        self.plan_d = K.ConvPlan(self.d_tap, self.wd, self.dh, Cin=C, Cout=C, ksize=1, res1=d_other, **self.geo)
+        self.refresh_dgrad_weights()
+
+    def refresh_dgrad_weights(self):
+        self.wd.copy_(self._wsrc(f"{self.name}.weight").t())
+
+    def forward(self):
+        self.plan.run()
+        return self.tap
+
+    def backward(self, d_tap: torch.Tensor) -> torch.Tensor:
+        f = self.flat
+        self.d_tap.copy_(d_tap.view_as(self.d_tap))
+        self.K.conv_wgrad(self.h, self.d_tap, f.g(f"{self.name}.weight"), f.g(f"{self.name}.bias"), ksize=1, accumulate=True, **self.geo)
+        self.plan_d.run()
+        return self.dh
+
+
+def brushnet_down_mid_shapes(cfg) -> Dict[str, Tuple[int, ...]]:
+    """Flat-buffer entries (packed layouts) of BrushNet's down path, mid block and their 13 zero-convs
+    (S/models/brushnet.py:296-372,831-851) — everything between conv_in_condition's output and the mid tap."""
+    boc = cfg.block_out_channels
+    s: Dict[str, Tuple[int, ...]] = {}
+    cin = boc[0]
+    k = 0
+    s[f"brushnet_down_blocks.{k}.weight"], s[f"brushnet_down_blocks.{k}.bias"] = (cin, cin), (cin,)
+    for i, cout in enumerate(boc):
+        for j in range(cfg.layers_per_block):
+            s.update(resnet_param_shapes(f"down_blocks.{i}.resnets.{j}", cin, cout))
+            cin = cout
+            k += 1
+            s[f"brushnet_down_blocks.{k}.weight"], s[f"brushnet_down_blocks.{k}.bias"] = (cout, cout), (cout,)
+        if i != len(boc) - 1:
+            s[f"down_blocks.{i}.downsamplers.0.conv.weight"], s[f"down_blocks.{i}.downsamplers.0.conv.bias"] = (cout, 9 * cout), (cout,)
+            k += 1
+            s[f"brushnet_down_blocks.{k}.weight"], s[f"brushnet_down_blocks.{k}.bias"] = (cout, cout), (cout,)
+    for j in range(2):
+        s.update(resnet_param_shapes(f"mid_block.resnets.{j}", boc[-1], boc[-1]))
+    s["brushnet_mid_block.weight"], s["brushnet_mid_block.bias"] = (boc[-1], boc[-1]), (boc[-1],)
+    return s
+
+
+def pack_brushnet_down_mid(cfg, sd: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+    """Reference state_dict (OIHW) -> fp32 tensors in the layout of brushnet_down_mid_shapes."""
+    out = {}
+    for name, shp in brushnet_down_mid_shapes(cfg).items():
+        v = sd[name].float()
+        out[name] = (v.permute(0, 2, 3, 1).reshape(v.shape[0], -1) if v.dim() == 4 else v).reshape(shp).contiguous()
+    return out
+
+
+class BrushNetDownMidTrainer:
+    """Forward-for-training and backward of the BrushNet branch from conv_in_condition's output to the mid tap: the down blocks
+    (resnets + downsamplers), MidBlock2D, and the 12 + 1 zero-conv taps (oracle/mf_oracle.py `brushnet_forward`, first half;
+    S/models/brushnet.py:810-851).  Net-level composition of ResnetBlockTrainer / DownsampleTrainer / ZeroConvTap: every hidden
+    state feeds the next block AND its zero-conv, so in backward its gradient is the sum of the two — formed by the zero-conv's
+    data-gradient plan (residual epilogue), never by a separate add.  conditioning_scale is 1 as in the reference's training
+    script.  Not covered yet: conv_in_condition itself (boundary kernel), the up blocks (two-source resnets, Upsample2D backward),
+    the timestep path (consumes the d rowbias this class returns)."""
+
+    def __init__(self, flat: FlatParams, cfg, *, B: int, H: int, W: int, precision: str = "bf16", K=None):
+        K = _ops if K is None else K
+        self.K, self.flat, self.cfg = K, flat, cfg
+        dt = torch.float32 if precision == "fp32" else torch.bfloat16
+        boc = cfg.block_out_channels
+        common = dict(precision=precision, K=K)
+        self.blocks = []            # (kind, trainer) in forward order
+        h, w, cin = H, W, boc[0]
+        for i, cout in enumerate(boc):
+            for j in range(cfg.layers_per_block):
+                self.blocks.append(("resnet", ResnetBlockTrainer(flat, f"down_blocks.{i}.resnets.{j}", B=B, H=h, W=w, Cin=cin, Cout=cout,
+                                                                 groups=cfg.norm_num_groups, eps=cfg.norm_eps, **common)))
+                cin = cout
+            if i != len(boc) - 1:
+                self.blocks.append(("down", DownsampleTrainer(flat, f"down_blocks.{i}.downsamplers.0", B=B, H=h, W=w, C=cout, **common)))
+                h, w = h // 2, w // 2
+        self.mid = [ResnetBlockTrainer(flat, f"mid_block.resnets.{j}", B=B, H=h, W=w, Cin=boc[-1], Cout=boc[-1], groups=cfg.norm_num_groups,
+                                       eps=cfg.norm_eps, **common) for j in range(2)]
+        # hidden states in forward order: h0 (the input), then each block's output; consumer k of hidden k is block k (or mid 0)
+        self.h0 = torch.zeros(B, H * W, boc[0], device=flat.param.device, dtype=dt)
+        hidden = [(self.h0, H, W, boc[0])]
+        hh, ww = H, W
+        for kind, t in self.blocks:
+            if kind == "down":
+                hh, ww = hh // 2, ww // 2
+            hidden.append((t.out, hh, ww, t.out.shape[-1]))
+        consumers = [t for _, t in self.blocks] + [self.mid[0]]
+        self.taps = [ZeroConvTap(flat, f"brushnet_down_blocks.{k}", hb, consumers[k].dx, B=B, H=hh_, W=ww_, C=c, dt=dt, K=K)
+                     for k, (hb, hh_, ww_, c) in enumerate(hidden)]
+        self.mid_tap = ZeroConvTap(flat, "brushnet_mid_block", self.mid[1].out, None, B=B, H=h, W=w, C=boc[-1], dt=dt, K=K)
+
+    def resnet_prefixes(self):
+        return [t.p for kind, t in self.blocks if kind == "resnet"] + [t.p for t in self.mid]
+
+    def refresh_dgrad_weights(self):
+        for _, t in self.blocks:
+            t.refresh_dgrad_weights()
+        for t in self.mid + self.taps + [self.mid_tap]:
+            t.refresh_dgrad_weights()
+
+    def forward(self, h0: torch.Tensor, rowbias: Dict[str, torch.Tensor]):
+        """h0: conv_in_condition's output [B, HW, C0]; rowbias[prefix] = time_emb_proj(silu(emb)) of each resnet ([B, Cout] fp32).
+        Returns (down taps [12 for SD1.5], mid tap) — buffers owned by the trainer."""
+        self.h0.copy_(h0.view_as(self.h0))
+        x = self.h0
+        for kind, t in self.blocks:
+            x = t.forward(x, rowbias[t.p]) if kind == "resnet" else t.forward(x)
+        for t in self.mid:
+            x = t.forward(x, rowbias[t.p])
+        return [z.forward() for z in self.taps], self.mid_tap.forward()
+
+    def backward(self, d_down_taps, d_mid_tap):
+        """Gradients of the 12 + 1 taps in.  Accumulates every parameter gradient into the flat buffer; returns
+        (d h0, {resnet prefix: d rowbias})."""
+        d_rb = {}
+        d = self.mid_tap.backward(d_mid_tap)                       # gradient at mid.resnets.1's output (its only consumer)
+        for t in reversed(self.mid):
+            d, d_rb[t.p] = t.backward(d)                           # leaves mid[0].dx = gradient from the mid block at the last hidden state
+        for k in range(len(self.blocks), 0, -1):                   # hidden k is produced by block k-1, consumed by block k (or mid[0])
+            d = self.taps[k].backward(d_down_taps[k])              # W_k^T d tap_k + consumer's dx (residual epilogue)
+            kind, t = self.blocks[k - 1]
+            if kind == "resnet":
+                _, d_rb[t.p] = t.backward(d)
+            else:
+                t.backward(d)
+        return self.taps[0].backward(d_down_taps[0]), d_rb

@@ -1,0 +1,52 @@
+"""Net-level backward program on the GPU (runs last): BrushNet's down path + mid block + 13 zero-conv taps
+(mirrorfusion_b200/backward.BrushNetDownMidTrainer) in fp32 parity mode against float64 autograd through the oracle's
+brushnet_forward.  The same program is checked on the CPU stand-in in tests/test_oracle_train.py."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def test_brushnet_down_mid_forward_backward_fp32_vs_autograd():
+    from mirrorfusion_b200 import ops
+    from mirrorfusion_b200.backward import BrushNetDownMidTrainer, brushnet_down_mid_shapes, pack_brushnet_down_mid, unpack_conv_grad
+    from mirrorfusion_b200.config import TINY
+    from mirrorfusion_b200.synth import make_state_dict
+    from mirrorfusion_b200.train import FlatParams
+    from oracle import mf_oracle as O
+    ops.lib()
+    cfg = TINY
+    B, H, W = 2, 16, 16
+    gen = torch.Generator().manual_seed(8)
+    sd = {k: v.double().requires_grad_(True) for k, v in make_state_dict(cfg, "brushnet").items()}
+    sample = torch.randn(B, cfg.in_channels, H, W, generator=gen, dtype=torch.float64)
+    cond = torch.randn(B, cfg.conditioning_channels, H, W, generator=gen, dtype=torch.float64)
+    t = torch.tensor([500, 20])
+    down, mid, _ = O.brushnet_forward(sd, cfg, sample, t, cond)
+    d_down = [torch.randn(d.shape, generator=gen, dtype=torch.float64) for d in down]
+    d_mid = torch.randn(mid.shape, generator=gen, dtype=torch.float64)
+    (sum((a * b).sum() for a, b in zip(down, d_down)) + (mid * d_mid).sum()).backward()
+    with torch.no_grad():
+        h0 = F.conv2d(torch.cat([sample, cond], 1), sd["conv_in_condition.weight"], sd["conv_in_condition.bias"], padding=1)
+        emb = O.time_embed(sd, t, B, cfg.block_out_channels[0], torch.float64)
+    flat = FlatParams(brushnet_down_mid_shapes(cfg), "cuda")
+    flat.load_state_dict(pack_brushnet_down_mid(cfg, {k: v.detach() for k, v in sd.items()}))
+    net = BrushNetDownMidTrainer(flat, cfg, B=B, H=H, W=W, precision="fp32")
+    rb = {p: F.linear(F.silu(emb), sd[f"{p}.time_emb_proj.weight"], sd[f"{p}.time_emb_proj.bias"]).detach().float().cuda()
+          for p in net.resnet_prefixes()}
+    nhwc = lambda x: x.detach().permute(0, 2, 3, 1).reshape(B, -1, x.shape[1]).float().contiguous()
+    rel = lambda a, b: float((a.double().cpu() - b.double()).norm() / (b.double().norm() + 1e-2))
+    taps, mid_tap = net.forward(nhwc(h0).cuda(), rb)
+    for a, b in zip(taps + [mid_tap], down + [mid]):
+        assert rel(a, nhwc(b)) < 1e-4
+    d_h0, d_rb = net.backward([nhwc(d).cuda() for d in d_down], nhwc(d_mid).cuda())
+    # fp32 kernels vs float64 autograd through 22 layers (8 / 16 channels per GroupNorm group, maps down to 2x2): 1e-3 rel-L2
+    assert rel(d_h0.sum((0, 1)), sd["conv_in_condition.bias"].grad) < 1e-3
+    for name in flat.table:
+        want = sd[name].grad
+        got = flat.g(name)
+        got = unpack_conv_grad(got, 3) if want.dim() == 4 and want.shape[-1] == 3 else got.reshape(want.shape)
+        assert rel(got, want) < 1e-3, name
+    for p, g in d_rb.items():
+        assert rel(g.sum(0), sd[f"{p}.time_emb_proj.bias"].grad) < 1e-3, p

@@ -174,3 +174,55 @@ def test_downsample_program_dataflow_on_the_cpu_stand_in():
     np.testing.assert_allclose(dx.numpy(), nhwc(x.grad).numpy(), rtol=1e-5, atol=1e-5)
     np.testing.assert_allclose(unpack_conv_grad(flat.g("d.conv.weight"), 3).numpy(), sd["d.conv.weight"].grad.numpy(), rtol=1e-4, atol=1e-5)
     np.testing.assert_allclose(flat.g("d.conv.bias").numpy(), sd["d.conv.bias"].grad.numpy(), rtol=1e-4, atol=1e-5)
+
+
+def test_brushnet_down_mid_program_dataflow_on_the_cpu_stand_in():
+    """BrushNetDownMidTrainer (down blocks + mid block + 13 zero-conv taps; fan-out gradients summed in the zero-conv
+    data-gradient epilogue) on tests/torch_kernels.py against autograd through the oracle's brushnet_forward (pinned to the
+    reference's BrushNetModel by tests/golden/micro_step.npz): taps, d h0, every parameter gradient, and the row-bias gradients via
+    d time_emb_proj.bias = sum_b d rowbias[b]."""
+    import torch_kernels as TK
+    from mirrorfusion_b200.backward import BrushNetDownMidTrainer, brushnet_down_mid_shapes, pack_brushnet_down_mid, unpack_conv_grad
+    from mirrorfusion_b200.config import MICRO
+    from mirrorfusion_b200.synth import make_state_dict
+    from mirrorfusion_b200.train import FlatParams
+    from oracle import mf_oracle as O
+    cfg = MICRO
+    B, H, W = 2, 16, 16          # 2x2 at the deepest level (at 1x1 a 1-channel GroupNorm group has zero variance)
+    gen = torch.Generator().manual_seed(8)
+    sd = {k: v.double().requires_grad_(True) for k, v in make_state_dict(cfg, "brushnet").items()}
+    sample = torch.randn(B, cfg.in_channels, H, W, generator=gen, dtype=torch.float64)
+    cond = torch.randn(B, cfg.conditioning_channels, H, W, generator=gen, dtype=torch.float64)
+    t = torch.tensor([500, 20])
+    down, mid, _ = O.brushnet_forward(sd, cfg, sample, t, cond)
+    d_down = [torch.randn(d.shape, generator=gen, dtype=torch.float64) for d in down]
+    d_mid = torch.randn(mid.shape, generator=gen, dtype=torch.float64)
+    (sum((a * b).sum() for a, b in zip(down, d_down)) + (mid * d_mid).sum()).backward()
+
+    with torch.no_grad():                                          # the trainer's inputs: conv_in_condition output and the row biases
+        h0 = F.conv2d(torch.cat([sample, cond], 1), sd["conv_in_condition.weight"], sd["conv_in_condition.bias"], padding=1)
+        emb = O.time_embed(sd, t, B, cfg.block_out_channels[0], torch.float64)
+    flat = FlatParams(brushnet_down_mid_shapes(cfg), "cpu", with_bf16=False)
+    for k, v in pack_brushnet_down_mid(cfg, {k: v.detach() for k, v in sd.items()}).items():
+        flat.p(k).copy_(v)
+    net = BrushNetDownMidTrainer(flat, cfg, B=B, H=H, W=W, precision="fp32", K=TK)
+    rb = {p: F.linear(F.silu(emb), sd[f"{p}.time_emb_proj.weight"], sd[f"{p}.time_emb_proj.bias"]).detach().float()
+          for p in net.resnet_prefixes()}
+    nhwc = lambda x: x.detach().permute(0, 2, 3, 1).reshape(B, -1, x.shape[1]).float().contiguous()
+    taps, mid_tap = net.forward(nhwc(h0), rb)
+    assert len(taps) == len(down) == 12
+    for a, b in zip(taps + [mid_tap], down + [mid]):
+        np.testing.assert_allclose(a.numpy(), nhwc(b).numpy(), rtol=2e-4, atol=2e-4)
+    d_h0, d_rb = net.backward([nhwc(d) for d in d_down], nhwc(d_mid))
+    # (+ 1e-2: gradients that are analytically zero — a bias in front of a 1-channel-per-group GroupNorm — compare as absolute)
+    rel = lambda a, b: float((a.double() - b.double()).norm() / (b.double().norm() + 1e-2))
+    # fp32 stand-in vs float64 autograd through ~20 layers with 1-channel GroupNorm groups over as few as 4 pixels: 1e-3 rel-L2
+    # d h0 is the gradient at conv_in_condition's output: its sum over pixels is that conv's bias gradient
+    assert rel(d_h0.sum((0, 1)), sd["conv_in_condition.bias"].grad) < 1e-3
+    for name in flat.table:
+        want = sd[name].grad
+        got = flat.g(name)
+        got = unpack_conv_grad(got, 3) if want.dim() == 4 and want.shape[-1] == 3 else got.reshape(want.shape)
+        assert rel(got, want) < 1e-3, name
+    for p, g in d_rb.items():
+        assert rel(g.sum(0), sd[f"{p}.time_emb_proj.bias"].grad) < 1e-3, p
