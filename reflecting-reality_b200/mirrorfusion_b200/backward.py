@@ -351,3 +351,173 @@ class BrushNetDownMidTrainer:
             else:
                 t.backward(d)
         return self.taps[0].backward(d_down_taps[0]), d_rb
+
+
+class UpsampleTrainer:
+    """Upsample2D (nearest x2 + conv3x3; S/models/upsampling.py:145-186) forward and backward on the kernels.
+    Forward: the sub-pixel `up2x` plan (no upsampled tensor).  Backward: the weight gradient needs the upsampled input once
+    (mfb_upsample2x + the stride-1 weight-gradient kernel); the data gradient is the stride-1 data-gradient plan at high
+    resolution followed by a 2x2 sum-pool, which runs as a stride-2 plan with a fixed 0/1 weight (taps kh, kw in {1, 2},
+    identity over channels) — a first version on existing kernels; a pooling kernel would do it in 4 adds per element.
+    Flat entries: `<prefix>.conv.weight` packed [C, 9*C], `<prefix>.conv.bias` [C].
+    STATUS: dataflow verified on the CPU stand-in only (tests/test_oracle_train.py); not yet run on a GPU."""
+
+    def __init__(self, flat: FlatParams, prefix: str, *, B: int, H: int, W: int, C: int, precision: str = "bf16", K=None):
+        K = _ops if K is None else K
+        self.K, self.flat, self.p, self.B, self.H, self.W, self.C = K, flat, prefix, B, H, W, C
+        self.dt = torch.float32 if precision == "fp32" else torch.bfloat16
+        dev = flat.param.device
+        self._wsrc = flat.p if self.dt == torch.float32 else flat.w
+        z = lambda hw: torch.zeros(B, hw, C, device=dev, dtype=self.dt)
+        self.x, self.dx = z(H * W), z(H * W)
+        self.out, self.d_out, self.xu, self.du = z(4 * H * W), z(4 * H * W), z(4 * H * W), z(4 * H * W)
+        self.w_up = torch.zeros(4, C, 4 * C, device=dev, dtype=self.dt)
+        self.wd = torch.zeros(C, 9 * C, device=dev, dtype=self.dt)
+        pool = torch.zeros(C, 3, 3, C, device=dev, dtype=torch.float32)
+        eye = torch.eye(C, device=dev)
+        for kh in (1, 2):
+            for kw in (1, 2):
+                pool[:, kh, kw, :] = eye
+        self.w_pool = pool.reshape(C, 9 * C).to(self.dt).contiguous()
+        self.plan = K.ConvPlan(self.x, self.w_up, self.out, B=B, H=H, W=W, Cin=C, Cout=C, ksize=3, up2x=True, bias=flat.p(f"{prefix}.conv.bias"))
+        self.plan_d = K.ConvPlan(self.d_out, self.wd, self.du, B=B, H=2 * H, W=2 * W, Cin=C, Cout=C, ksize=3)
+        self.plan_pool = K.ConvPlan(self.du, self.w_pool, self.dx, B=B, H=2 * H, W=2 * W, Cin=C, Cout=C, ksize=3, stride=2)
+        self.refresh_dgrad_weights()
+
+    def refresh_dgrad_weights(self):
+        """Derived weight copies: the four sub-pixel phases of the forward plan and the flipped / transposed data-gradient weight."""
+        wp = self._wsrc(f"{self.p}.conv.weight")
+        old = _ops._ACT[0]
+        _ops._ACT[0] = self.dt                     # pack_upconv_weight rounds to the activation dtype of the engine being built
+        try:
+            self.w_up.copy_(_ops.pack_upconv_weight(unpack_conv_grad(wp.float(), 3)))
+        finally:
+            _ops._ACT[0] = old
+        self.wd.copy_(_dgrad_from_packed(wp, 3, self.dt))
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        self.x.copy_(x.view_as(self.x))
+        self.plan.run()
+        return self.out
+
+    def backward(self, d_out: torch.Tensor) -> torch.Tensor:
+        K, f, B, H, W = self.K, self.flat, self.B, self.H, self.W
+        self.d_out.copy_(d_out.view_as(self.d_out))
+        # nearest x2 of the saved input: a pure pixel-vector copy, so fp32 tensors go through the bf16 kernel as 2*C "channels"
+        bf = torch.bfloat16
+        K.upsample2x(self.x.view(bf) if self.dt != bf else self.x, self.xu.view(bf) if self.dt != bf else self.xu, B=B, H=H, W=W)
+        K.conv_wgrad(self.xu, self.d_out, f.g(f"{self.p}.conv.weight"), f.g(f"{self.p}.conv.bias"), B=B, H=2 * H, W=2 * W, ksize=3,
+                     accumulate=True)
+        self.plan_d.run()            # gradient at the upsampled tensor
+        self.plan_pool.run()         # sum over each 2x2 block = gradient at the low-resolution input
+        return self.dx
+
+
+def skip_resnet_param_shapes(prefix: str, C1: int, C2: int, Cout: int) -> Dict[str, Tuple[int, ...]]:
+    """Flat entries of an up-block resnet over cat([x, skip]) (S/models/unets/unet_2d_blocks.py:2711-2728).  The 1x1 shortcut
+    weight is stored as its two column blocks (`.a` over x, `.b` over the skip) so each half is a dense matrix for the
+    weight-gradient kernel and for its own data-gradient plan."""
+    s = resnet_param_shapes(prefix, C1 + C2, Cout)
+    del s[f"{prefix}.conv_shortcut.weight"]
+    s[f"{prefix}.conv_shortcut.weight.a"] = (Cout, C1)
+    s[f"{prefix}.conv_shortcut.weight.b"] = (Cout, C2)
+    return s
+
+
+def pack_skip_resnet_state_dict(prefix: str, sd: Dict[str, torch.Tensor], C1: int) -> Dict[str, torch.Tensor]:
+    out = pack_resnet_state_dict(prefix, sd)
+    w = out.pop(f"{prefix}.conv_shortcut.weight")
+    out[f"{prefix}.conv_shortcut.weight.a"] = w[:, :C1].contiguous()
+    out[f"{prefix}.conv_shortcut.weight.b"] = w[:, C1:].contiguous()
+    return out
+
+
+class SkipResnetBlockTrainer:
+    """ResnetBlock2D over the channel concat of two tensors (x from below, skip from the down path) — the resnets of
+    BrushNet's up blocks.  The concat is never materialised except normalised (GroupNorm reads both sources, as in the
+    inference engine).  Backward returns one gradient per source: the GroupNorm backward writes its two halves, and the two
+    data-gradient plans of the shortcut halves add them in their residual epilogue (d x = W_a^T d out + GN-half; same for
+    the skip).  STATUS: dataflow verified on the CPU stand-in only; not yet run on a GPU."""
+
+    def __init__(self, flat: FlatParams, prefix: str, *, B: int, H: int, W: int, C1: int, C2: int, Cout: int, groups: int = 32,
+                 eps: float = 1e-5, precision: str = "bf16", K=None):
+        K = _ops if K is None else K
+        self.K, self.flat, self.p = K, flat, prefix
+        self.B, self.H, self.W, self.HW, self.C1, self.C2, self.Cout, self.groups, self.eps = B, H, W, H * W, C1, C2, Cout, groups, eps
+        Cin = C1 + C2
+        self.dt = torch.float32 if precision == "fp32" else torch.bfloat16
+        dev = flat.param.device
+        act = lambda c: torch.zeros(B, self.HW, c, device=dev, dtype=self.dt)
+        self.x1, self.x2, self.n1, self.c1, self.n2 = act(C1), act(C2), act(Cin), act(Cout), act(Cout)
+        self.sc_a, self.sc, self.out = act(Cout), act(Cout), act(Cout)
+        self.rowbias = torch.zeros(B, Cout, device=dev, dtype=torch.float32)
+        self.d_out, self.dn2, self.dc1, self.dn1 = act(Cout), act(Cout), act(Cout), act(Cin)
+        self.g1, self.g2, self.dx, self.dx2 = act(C1), act(C2), act(C1), act(C2)     # self.dx: gradient of the main input (like the other trainers)
+        self.d_rowbias = torch.zeros(B, Cout, device=dev, dtype=torch.float32)
+        self.gn_ws = torch.zeros(K.gn_ws_floats(B, groups), device=dev, dtype=torch.float32)
+        self.gnb_ws = torch.zeros(2 * B * max(Cin, Cout), device=dev, dtype=torch.float32)
+        self._wsrc = wsrc = flat.p if self.dt == torch.float32 else flat.w
+        n = lambda s: f"{prefix}.{s}"
+        geo = dict(B=B, H=H, W=W)
+        self.plan1 = K.ConvPlan(self.n1, wsrc(n("conv1.weight")), self.c1, Cin=Cin, Cout=Cout, ksize=3, bias=flat.p(n("conv1.bias")),
+                                rowbias=self.rowbias, rowbias_ld=Cout, **geo)
+        self.plan_sc_a = K.ConvPlan(self.x1, wsrc(n("conv_shortcut.weight.a")), self.sc_a, Cin=C1, Cout=Cout, ksize=1,
+                                    bias=flat.p(n("conv_shortcut.bias")), **geo)
+        self.plan_sc_b = K.ConvPlan(self.x2, wsrc(n("conv_shortcut.weight.b")), self.sc, Cin=C2, Cout=Cout, ksize=1, res1=self.sc_a, **geo)
+        self.plan2 = K.ConvPlan(self.n2, wsrc(n("conv2.weight")), self.out, Cin=Cout, Cout=Cout, ksize=3, bias=flat.p(n("conv2.bias")),
+                                res1=self.sc, **geo)
+        self.w1d = torch.zeros(Cin, 9 * Cout, device=dev, dtype=self.dt)
+        self.w2d = torch.zeros(Cout, 9 * Cout, device=dev, dtype=self.dt)
+        self.wad = torch.zeros(C1, Cout, device=dev, dtype=self.dt)
+        self.wbd = torch.zeros(C2, Cout, device=dev, dtype=self.dt)
+        self.plan_d2 = K.ConvPlan(self.d_out, self.w2d, self.dn2, Cin=Cout, Cout=Cout, ksize=3, **geo)
+        self.plan_d1 = K.ConvPlan(self.dc1, self.w1d, self.dn1, Cin=Cout, Cout=Cin, ksize=3, **geo)
+        self.plan_da = K.ConvPlan(self.d_out, self.wad, self.dx, Cin=Cout, Cout=C1, ksize=1, res1=self.g1, **geo)
+        self.plan_db = K.ConvPlan(self.d_out, self.wbd, self.dx2, Cin=Cout, Cout=C2, ksize=1, res1=self.g2, **geo)
+        self.refresh_dgrad_weights()
+
+    def refresh_dgrad_weights(self):
+        n = lambda s: f"{self.p}.{s}"
+        self.w1d.copy_(_dgrad_from_packed(self._wsrc(n("conv1.weight")), 3, self.dt))
+        self.w2d.copy_(_dgrad_from_packed(self._wsrc(n("conv2.weight")), 3, self.dt))
+        self.wad.copy_(self._wsrc(n("conv_shortcut.weight.a")).t())
+        self.wbd.copy_(self._wsrc(n("conv_shortcut.weight.b")).t())
+
+    def forward(self, x1: torch.Tensor, x2: torch.Tensor, rowbias: Optional[torch.Tensor] = None) -> torch.Tensor:
+        K, f, n = self.K, self.flat, (lambda s: f"{self.p}.{s}")
+        self.x1.copy_(x1.view_as(self.x1))
+        self.x2.copy_(x2.view_as(self.x2))
+        if rowbias is None:
+            self.rowbias.zero_()
+        else:
+            self.rowbias.copy_(rowbias)
+        gn = dict(B=self.B, HW=self.HW, groups=self.groups, eps=self.eps, silu=True)
+        K.groupnorm(self.x1, self.x2, f.p(n("norm1.weight")), f.p(n("norm1.bias")), self.n1, self.gn_ws, **gn)
+        self.plan1.run()
+        K.groupnorm(self.c1, None, f.p(n("norm2.weight")), f.p(n("norm2.bias")), self.n2, self.gn_ws, **gn)
+        self.plan_sc_a.run()
+        self.plan_sc_b.run()
+        self.plan2.run()
+        return self.out
+
+    def backward(self, d_out: torch.Tensor):
+        """-> (d x, d skip, d rowbias)."""
+        K, f, n = self.K, self.flat, (lambda s: f"{self.p}.{s}")
+        B, H, W, HW = self.B, self.H, self.W, self.HW
+        self.d_out.copy_(d_out.view_as(self.d_out))
+        gnb = dict(B=B, HW=HW, groups=self.groups, eps=self.eps, silu=True, accumulate=True)
+        wg = dict(B=B, H=H, W=W, accumulate=True)
+        K.conv_wgrad(self.n2, self.d_out, f.g(n("conv2.weight")), f.g(n("conv2.bias")), ksize=3, **wg)
+        self.plan_d2.run()
+        K.groupnorm_bwd(self.c1, None, self.dn2, f.p(n("norm2.weight")), f.p(n("norm2.bias")), self.dc1, None, self.gnb_ws,
+                        dgamma=f.g(n("norm2.weight")), dbeta=f.g(n("norm2.bias")), **gnb)
+        K.conv_wgrad(self.n1, self.dc1, f.g(n("conv1.weight")), f.g(n("conv1.bias")), ksize=3, **wg)
+        K.rowsum_per_image(self.dc1, self.d_rowbias, B=B, HW=HW)
+        self.plan_d1.run()
+        K.groupnorm_bwd(self.x1, self.x2, self.dn1, f.p(n("norm1.weight")), f.p(n("norm1.bias")), self.g1, self.g2, self.gnb_ws,
+                        dgamma=f.g(n("norm1.weight")), dbeta=f.g(n("norm1.bias")), **gnb)
+        K.conv_wgrad(self.x1, self.d_out, f.g(n("conv_shortcut.weight.a")), f.g(n("conv_shortcut.bias")), ksize=1, **wg)
+        K.conv_wgrad(self.x2, self.d_out, f.g(n("conv_shortcut.weight.b")), None, ksize=1, **wg)
+        self.plan_da.run()            # d x    = W_a^T d out + GroupNorm-backward half 1
+        self.plan_db.run()            # d skip = W_b^T d out + GroupNorm-backward half 2
+        return self.dx, self.dx2, self.d_rowbias

@@ -226,3 +226,62 @@ def test_brushnet_down_mid_program_dataflow_on_the_cpu_stand_in():
         assert rel(got, want) < 1e-3, name
     for p, g in d_rb.items():
         assert rel(g.sum(0), sd[f"{p}.time_emb_proj.bias"].grad) < 1e-3, p
+
+
+def test_upsample_program_dataflow_on_the_cpu_stand_in():
+    """UpsampleTrainer (sub-pixel forward; weight gradient over the materialised x2 input; data gradient = stride-1 plan + 2x2
+    sum-pool as a stride-2 plan with a 0/1 weight) on tests/torch_kernels.py against autograd of the oracle's Upsample2D."""
+    import torch_kernels as TK
+    from mirrorfusion_b200.backward import UpsampleTrainer, unpack_conv_grad
+    from mirrorfusion_b200.train import FlatParams
+    from oracle import mf_oracle as O
+    gen = torch.Generator().manual_seed(22)
+    B, C, H, W = 2, 16, 6, 4
+    sd = {"u.conv.weight": (torch.randn(C, C, 3, 3, generator=gen) * 0.1).requires_grad_(True),
+          "u.conv.bias": (torch.randn(C, generator=gen) * 0.1).requires_grad_(True)}
+    x = torch.randn(B, C, H, W, generator=gen, requires_grad=True)
+    d_out = torch.randn(B, C, 2 * H, 2 * W, generator=gen)
+    y = O.upsample(sd, "u", x)
+    y.backward(d_out)
+    flat = FlatParams({"u.conv.weight": (C, 9 * C), "u.conv.bias": (C,)}, "cpu", with_bf16=False)
+    flat.p("u.conv.weight").copy_(sd["u.conv.weight"].detach().permute(0, 2, 3, 1).reshape(C, -1))
+    flat.p("u.conv.bias").copy_(sd["u.conv.bias"].detach())
+    blk = UpsampleTrainer(flat, "u", B=B, H=H, W=W, C=C, precision="fp32", K=TK)
+    nhwc = lambda t: t.detach().permute(0, 2, 3, 1).reshape(B, -1, C).contiguous()
+    np.testing.assert_allclose(blk.forward(nhwc(x)).numpy(), nhwc(y).numpy(), rtol=1e-5, atol=1e-5)
+    dx = blk.backward(nhwc(d_out))
+    np.testing.assert_allclose(dx.numpy(), nhwc(x.grad).numpy(), rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(unpack_conv_grad(flat.g("u.conv.weight"), 3).numpy(), sd["u.conv.weight"].grad.numpy(), rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(flat.g("u.conv.bias").numpy(), sd["u.conv.bias"].grad.numpy(), rtol=1e-4, atol=1e-5)
+
+
+def test_skip_resnet_program_dataflow_on_the_cpu_stand_in():
+    """SkipResnetBlockTrainer (resnet over cat([x, skip]) of BrushNet's up blocks) on the stand-in against autograd of the oracle
+    block evaluated on the concatenated input."""
+    import torch_kernels as TK
+    from mirrorfusion_b200.backward import (SkipResnetBlockTrainer, pack_skip_resnet_state_dict, skip_resnet_param_shapes,
+                                            unpack_conv_grad)
+    from mirrorfusion_b200.train import FlatParams
+    C1, C2, cout = 64, 32, 64
+    sd, x, emb, d_out = T.resnet_block_case(C1 + C2, cout, seed=78)
+    ref = T.resnet_block_grads(sd, "r", x, emb, d_out)
+    B, _, H, W = x.shape
+    flat = FlatParams(skip_resnet_param_shapes("r", C1, C2, cout), "cpu", with_bf16=False)
+    for k, v in pack_skip_resnet_state_dict("r", sd, C1).items():
+        flat.p(k).copy_(v)
+    blk = SkipResnetBlockTrainer(flat, "r", B=B, H=H, W=W, C1=C1, C2=C2, Cout=cout, precision="fp32", K=TK)
+    nhwc = lambda t: t.permute(0, 2, 3, 1).reshape(B, H * W, -1).contiguous()
+    out = blk.forward(nhwc(x[:, :C1]), nhwc(x[:, C1:]), ref["rowbias"].float())
+    np.testing.assert_allclose(out.numpy(), nhwc(ref["out"]).numpy(), rtol=1e-4, atol=1e-4)
+    dx1, dx2, drb = blk.backward(nhwc(d_out))
+    np.testing.assert_allclose(torch.cat([dx1, dx2], -1).numpy(), nhwc(ref["dx"]).numpy(), rtol=1e-4, atol=1e-4)
+    np.testing.assert_allclose(drb.numpy(), ref["d_rowbias"].numpy(), rtol=1e-4, atol=1e-4)
+    got_sc = torch.cat([flat.g("r.conv_shortcut.weight.a"), flat.g("r.conv_shortcut.weight.b")], 1)
+    np.testing.assert_allclose(got_sc.numpy(), ref["r.conv_shortcut.weight"][:, :, 0, 0].numpy(), rtol=2e-4, atol=2e-4)
+    for name in flat.table:
+        if "conv_shortcut.weight" in name:
+            continue
+        want = ref[name]
+        got = flat.g(name)
+        got = unpack_conv_grad(got, 3) if want.dim() == 4 and want.shape[-1] == 3 else got.reshape(want.shape)
+        np.testing.assert_allclose(got.numpy(), want.numpy(), rtol=2e-4, atol=2e-4, err_msg=name)

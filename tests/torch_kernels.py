@@ -21,9 +21,10 @@ class ConvPlan:
     ([4, Cout, 4*Cin]: phase (py, px) is a 2x2 conv over the low-resolution input at offsets {-1, 0} / {0, +1})."""
 
     def __init__(self, x, w, out, *, B, H, W, Cin, Cout, ksize=1, stride=1, bias=None, rowbias=None, rowbias_ld=0, res1=None,
-                 up2x=False):
+                 res2=None, up2x=False):
         assert tuple(w.shape) == ((4, Cout, 4 * Cin) if up2x else (Cout, ksize * ksize * Cin))
         self.a = (x, w, out, B, H, W, Cin, Cout, ksize, bias, rowbias, res1)
+        self.res2 = res2
         self.stride, self.up2x = stride, up2x
         self.launches = 4 if up2x else 1
 
@@ -45,6 +46,8 @@ class ConvPlan:
         y = _nhwc(y).reshape(out.shape)
         if res1 is not None:
             y = y + res1.reshape(out.shape)
+        if self.res2 is not None:
+            y = y + self.res2.reshape(out.shape)
         out.copy_(y)
 
 
@@ -89,3 +92,9 @@ def conv_wgrad(x, dy, dw, dbias=None, *, B, H, W, ksize, stride=1, accumulate=Fa
 
 def rowsum_per_image(dy, out, *, B, HW):
     out.copy_(dy.reshape(B, HW, -1).float().sum(1))
+
+
+def upsample2x(x, out, *, B, H, W):
+    """nearest x2 of NHWC pixel vectors (dtype-agnostic copy, like the kernel)."""
+    v = x.reshape(B, H, W, -1)
+    out.copy_(v.repeat_interleave(2, 1).repeat_interleave(2, 2).reshape(out.shape))
