@@ -217,7 +217,8 @@ class ZeroConvTap:
     Backward also folds the fan-out of h: d h = W^T d tap + (the gradient arriving from h's other consumer), the sum done by
     the data-gradient plan's residual epilogue.  Flat entries `<name>.weight` [C, C] (a packed 1x1) and `<name>.bias` [C]."""
 
-    def __init__(self, flat: FlatParams, name: str, h: torch.Tensor, d_other: Optional[torch.Tensor], *, B, H, W, C, dt, K):
+    def __init__(self, flat: FlatParams, name: str, h: torch.Tensor, d_other: Optional[torch.Tensor], *, B, H, W, C, dt, K,
+                 d_other2: Optional[torch.Tensor] = None):
         self.K, self.flat, self.name, self.h, self.geo = K, flat, name, h, dict(B=B, H=H, W=W)
         dev = flat.param.device
         self._wsrc = flat.p if dt == torch.float32 else flat.w
@@ -225,7 +226,8 @@ class ZeroConvTap:
         self.d_tap, self.dh = torch.zeros_like(self.tap), torch.zeros_like(self.tap)
         self.wd = torch.zeros(C, C, device=dev, dtype=dt)
         self.plan = K.ConvPlan(h, self._wsrc(f"{name}.weight"), self.tap, Cin=C, Cout=C, ksize=1, bias=flat.p(f"{name}.bias"), **self.geo)
-        self.plan_d = K.ConvPlan(self.d_tap, self.wd, self.dh, Cin=C, Cout=C, ksize=1, res1=d_other, **self.geo)
+        # up to two more consumers of h (the next block; the up-block resnet that takes h as its skip): both residual inputs
+        self.plan_d = K.ConvPlan(self.d_tap, self.wd, self.dh, Cin=C, Cout=C, ksize=1, res1=d_other, res2=d_other2, **self.geo)
         self.refresh_dgrad_weights()
 
     def refresh_dgrad_weights(self):
@@ -312,9 +314,15 @@ class BrushNetDownMidTrainer:
                 hh, ww = hh // 2, ww // 2
             hidden.append((t.out, hh, ww, t.out.shape[-1]))
         consumers = [t for _, t in self.blocks] + [self.mid[0]]
-        self.taps = [ZeroConvTap(flat, f"brushnet_down_blocks.{k}", hb, consumers[k].dx, B=B, H=hh_, W=ww_, C=c, dt=dt, K=K)
+        self.hidden, self._mid_hw = hidden, (h, w)
+        skip_grads, mid_other = self._build_up_path(B, dt, common)          # (None, None) here; the full branch overrides it
+        self.taps = [ZeroConvTap(flat, f"brushnet_down_blocks.{k}", hb, consumers[k].dx, B=B, H=hh_, W=ww_, C=c, dt=dt, K=K,
+                                 d_other2=None if skip_grads is None else skip_grads[k])
                      for k, (hb, hh_, ww_, c) in enumerate(hidden)]
-        self.mid_tap = ZeroConvTap(flat, "brushnet_mid_block", self.mid[1].out, None, B=B, H=h, W=w, C=boc[-1], dt=dt, K=K)
+        self.mid_tap = ZeroConvTap(flat, "brushnet_mid_block", self.mid[1].out, mid_other, B=B, H=h, W=w, C=boc[-1], dt=dt, K=K)
+
+    def _build_up_path(self, B, dt, common):
+        return None, None
 
     def resnet_prefixes(self):
         return [t.p for kind, t in self.blocks if kind == "resnet"] + [t.p for t in self.mid]
@@ -521,3 +529,116 @@ class SkipResnetBlockTrainer:
         self.plan_da.run()            # d x    = W_a^T d out + GroupNorm-backward half 1
         self.plan_db.run()            # d skip = W_b^T d out + GroupNorm-backward half 2
         return self.dx, self.dx2, self.d_rowbias
+
+
+def brushnet_branch_shapes(cfg) -> Dict[str, Tuple[int, ...]]:
+    """Flat entries of the whole BrushNet branch behind conv_in_condition: down path, mid block, up blocks and all 28 zero-convs
+    (SD1.5: 12 + 1 + 15; S/models/brushnet.py:296-449)."""
+    s = brushnet_down_mid_shapes(cfg)
+    boc = cfg.block_out_channels
+    down_c = [boc[0]]
+    for i, c in enumerate(boc):
+        down_c += [c] * cfg.layers_per_block + ([c] if i != len(boc) - 1 else [])
+    rev = list(reversed(boc))
+    cx, k, nl = boc[-1], 0, cfg.layers_per_block + 1
+    for i, cout in enumerate(rev):
+        for j in range(nl):
+            cskip = down_c[len(down_c) - 1 - (i * nl + j)]
+            s.update(skip_resnet_param_shapes(f"up_blocks.{i}.resnets.{j}", cx, cskip, cout))
+            cx = cout
+            s[f"brushnet_up_blocks.{k}.weight"], s[f"brushnet_up_blocks.{k}.bias"] = (cout, cout), (cout,)
+            k += 1
+        if i != len(rev) - 1:
+            s[f"up_blocks.{i}.upsamplers.0.conv.weight"], s[f"up_blocks.{i}.upsamplers.0.conv.bias"] = (cout, 9 * cout), (cout,)
+            s[f"brushnet_up_blocks.{k}.weight"], s[f"brushnet_up_blocks.{k}.bias"] = (cout, cout), (cout,)
+            k += 1
+    return s
+
+
+def pack_brushnet_branch(cfg, sd: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+    """Reference state_dict (OIHW) -> fp32 tensors in the layout of brushnet_branch_shapes."""
+    out = {}
+    for name, shp in brushnet_branch_shapes(cfg).items():
+        if name.endswith(".conv_shortcut.weight.a") or name.endswith(".conv_shortcut.weight.b"):
+            w = sd[name[:-2]].float()[:, :, 0, 0]
+            c1 = brushnet_branch_shapes(cfg)[name[:-2] + ".a"][1]
+            out[name] = (w[:, :c1] if name.endswith(".a") else w[:, c1:]).contiguous()
+            continue
+        v = sd[name].float()
+        out[name] = (v.permute(0, 2, 3, 1).reshape(v.shape[0], -1) if v.dim() == 4 else v).reshape(shp).contiguous()
+    return out
+
+
+class BrushNetBranchTrainer(BrushNetDownMidTrainer):
+    """The whole BrushNet branch behind conv_in_condition, forward-for-training and backward: down path, MidBlock2D, the up
+    blocks (resnets over cat([x, skip]), Upsample2D) and all 28 zero-conv taps (oracle/mf_oracle.py `brushnet_forward`;
+    S/models/brushnet.py:810-906).  A down-path hidden state now has up to three consumers — the next block, its zero-conv and
+    the up-block resnet that takes it as skip — and its gradient is still formed inside ONE data-gradient plan (the zero-conv's,
+    with both other gradients as residual inputs).  Backward order: up path in reverse (which leaves every skip gradient in the
+    dx2 buffer of its resnet), mid block, down path.
+    STATUS: dataflow verified on the CPU stand-in (tests/test_oracle_train.py); the down / mid half has run on B200
+    (tests/test_gpu_zz_train_net.py), the up half has not."""
+
+    def _build_up_path(self, B, dt, common):
+        cfg, flat = self.cfg, self.flat
+        boc = cfg.block_out_channels
+        rev = list(reversed(boc))
+        nl = cfg.layers_per_block + 1
+        h, w = self._mid_hw
+        n_hidden = len(self.hidden)
+        self.up_seq = []                # (kind, trainer, skip hidden index or None) in forward order
+        cx = boc[-1]
+        for i, cout in enumerate(rev):
+            for j in range(nl):
+                idx = n_hidden - 1 - (i * nl + j)
+                cskip = self.hidden[idx][3]
+                self.up_seq.append(("resnet", SkipResnetBlockTrainer(flat, f"up_blocks.{i}.resnets.{j}", B=B, H=h, W=w, C1=cx, C2=cskip, Cout=cout,
+                                                                     groups=cfg.norm_num_groups, eps=cfg.norm_eps, **common), idx))
+                cx = cout
+            if i != len(rev) - 1:
+                self.up_seq.append(("up", UpsampleTrainer(flat, f"up_blocks.{i}.upsamplers.0", B=B, H=h, W=w, C=cout, **common), None))
+                h, w = 2 * h, 2 * w
+        # zero-convs of the up hidden states: consumer = the next block of the up sequence (none for the last)
+        self.up_taps = []
+        hh, ww = self._mid_hw
+        for k, (kind, t, _) in enumerate(self.up_seq):
+            if kind == "up":
+                hh, ww = 2 * hh, 2 * ww
+            nxt = self.up_seq[k + 1][1].dx if k + 1 < len(self.up_seq) else None
+            self.up_taps.append(ZeroConvTap(flat, f"brushnet_up_blocks.{k}", t.out, nxt, B=B, H=hh, W=ww, C=t.out.shape[-1], dt=dt, K=self.K))
+        skip_grads = [None] * n_hidden
+        for kind, t, idx in self.up_seq:
+            if kind == "resnet":
+                skip_grads[idx] = t.dx2
+        return skip_grads, self.up_seq[0][1].dx
+
+    def resnet_prefixes(self):
+        return super().resnet_prefixes() + [t.p for kind, t, _ in self.up_seq if kind == "resnet"]
+
+    def refresh_dgrad_weights(self):
+        super().refresh_dgrad_weights()
+        for _, t, _ in self.up_seq:
+            t.refresh_dgrad_weights()
+        for t in self.up_taps:
+            t.refresh_dgrad_weights()
+
+    def forward(self, h0: torch.Tensor, rowbias: Dict[str, torch.Tensor]):
+        """-> (down taps, mid tap, up taps)."""
+        down_taps, mid_tap = super().forward(h0, rowbias)
+        x = self.mid[1].out
+        for kind, t, idx in self.up_seq:
+            x = t.forward(x, self.hidden[idx][0], rowbias[t.p]) if kind == "resnet" else t.forward(x)
+        return down_taps, mid_tap, [z.forward() for z in self.up_taps]
+
+    def backward(self, d_down_taps, d_mid_tap, d_up_taps):
+        d_rb = {}
+        for k in range(len(self.up_seq) - 1, -1, -1):
+            d = self.up_taps[k].backward(d_up_taps[k])             # + the next up block's dx
+            kind, t, _ = self.up_seq[k]
+            if kind == "resnet":
+                _, _, d_rb[t.p] = t.backward(d)                    # leaves d x in t.dx and the skip gradient in t.dx2
+            else:
+                t.backward(d)
+        d_h0, d_rb_down = super().backward(d_down_taps, d_mid_tap)  # mid tap adds up_seq[0].dx; down taps add the skip gradients
+        d_rb.update(d_rb_down)
+        return d_h0, d_rb

@@ -285,3 +285,67 @@ def test_skip_resnet_program_dataflow_on_the_cpu_stand_in():
         got = flat.g(name)
         got = unpack_conv_grad(got, 3) if want.dim() == 4 and want.shape[-1] == 3 else got.reshape(want.shape)
         np.testing.assert_allclose(got.numpy(), want.numpy(), rtol=2e-4, atol=2e-4, err_msg=name)
+
+
+def test_brushnet_branch_program_dataflow_on_the_cpu_stand_in():
+    """The WHOLE BrushNet branch behind conv_in_condition (down, mid, up blocks, all 28 zero-conv taps) as one forward + backward
+    launch program on the stand-in, against autograd through the oracle's brushnet_forward: every tap, d h0, every parameter
+    gradient, every row-bias gradient.  Down-path hidden states have three consumers here (next block, zero-conv, skip)."""
+    import torch_kernels as TK
+    from mirrorfusion_b200.backward import BrushNetBranchTrainer, brushnet_branch_shapes, pack_brushnet_branch, unpack_conv_grad
+    from mirrorfusion_b200.config import MICRO
+    from mirrorfusion_b200.synth import make_state_dict
+    from mirrorfusion_b200.train import FlatParams
+    from oracle import mf_oracle as O
+    cfg = MICRO
+    B, H, W = 2, 16, 16
+    gen = torch.Generator().manual_seed(9)
+    sd = {k: v.double().requires_grad_(True) for k, v in make_state_dict(cfg, "brushnet").items()}
+    sample = torch.randn(B, cfg.in_channels, H, W, generator=gen, dtype=torch.float64)
+    cond = torch.randn(B, cfg.conditioning_channels, H, W, generator=gen, dtype=torch.float64)
+    t = torch.tensor([700, 3])
+    down, mid, up = O.brushnet_forward(sd, cfg, sample, t, cond)
+    assert (len(down), len(up)) == (12, 15)
+    rnd = lambda ts: [torch.randn(x.shape, generator=gen, dtype=torch.float64) for x in ts]
+    d_down, d_up, d_mid = rnd(down), rnd(up), rnd([mid])[0]
+    (sum((a * b).sum() for a, b in zip(down + up, d_down + d_up)) + (mid * d_mid).sum()).backward()
+    with torch.no_grad():
+        h0 = F.conv2d(torch.cat([sample, cond], 1), sd["conv_in_condition.weight"], sd["conv_in_condition.bias"], padding=1)
+        emb = O.time_embed(sd, t, B, cfg.block_out_channels[0], torch.float64)
+    shapes = brushnet_branch_shapes(cfg)
+    flat = FlatParams(shapes, "cpu", with_bf16=False)
+    for k, v in pack_brushnet_branch(cfg, {k: v.detach() for k, v in sd.items()}).items():
+        flat.p(k).copy_(v)
+    net = BrushNetBranchTrainer(flat, cfg, B=B, H=H, W=W, precision="fp32", K=TK)
+    rb = {p: F.linear(F.silu(emb), sd[f"{p}.time_emb_proj.weight"], sd[f"{p}.time_emb_proj.bias"]).detach().float()
+          for p in net.resnet_prefixes()}
+    assert len(rb) == 8 + 2 + 12
+    nhwc = lambda x: x.detach().permute(0, 2, 3, 1).reshape(B, -1, x.shape[1]).float().contiguous()
+
+    def rel(a, b):      # gradients that are analytically zero (a bias in front of a 1-channel-per-group GroupNorm): absolute
+        a, b = a.double(), b.double()
+        return float(a.norm()) if float(b.norm()) < 1e-9 else float((a - b).norm() / b.norm())
+
+    td, tm, tu = net.forward(nhwc(h0), rb)
+    for a, b in zip(td + [tm] + tu, down + [mid] + up):
+        assert rel(a, nhwc(b)) < 1e-4
+    d_h0, d_rb = net.backward([nhwc(d) for d in d_down], nhwc(d_mid), [nhwc(d) for d in d_up])
+    assert rel(d_h0.sum((0, 1)), sd["conv_in_condition.bias"].grad) < 1e-3
+    # every trainable tensor of the branch except conv_in_condition and the timestep path is in the flat buffer
+    covered = {n[:-2] if n.endswith((".weight.a", ".weight.b")) else n for n in shapes}
+    skipped = [k for k in sd if k not in covered]
+    assert all(k.startswith(("conv_in_condition.", "time_embedding.")) or ".time_emb_proj." in k for k in skipped), skipped
+    for name in shapes:
+        if name.endswith(".weight.b"):
+            continue
+        if name.endswith(".weight.a"):
+            want = sd[name[:-2]].grad[:, :, 0, 0]
+            got = torch.cat([flat.g(name), flat.g(name[:-2] + ".b")], 1)
+        else:
+            want = sd[name].grad
+            got = flat.g(name)
+            got = unpack_conv_grad(got, 3) if want.dim() == 4 and want.shape[-1] == 3 else got.reshape(want.shape)
+        assert rel(got, want) < 1e-3, name
+    for p, g in d_rb.items():
+        assert rel(g.sum(0), sd[f"{p}.time_emb_proj.bias"].grad) < 1e-3, p
+    assert len(d_rb) == 22
