@@ -50,3 +50,61 @@ def test_brushnet_down_mid_forward_backward_fp32_vs_autograd():
         assert rel(got, want) < 1e-3, name
     for p, g in d_rb.items():
         assert rel(g.sum(0), sd[f"{p}.time_emb_proj.bias"].grad) < 1e-3, p
+
+
+@pytest.mark.xfail(strict=False, reason="first GPU run pending: written after the round's GPU budget was spent.  The program's dataflow is "
+                                        "verified on the CPU stand-in (tests/test_oracle_train.py) and its down / mid half on B200 (test above); "
+                                        "an XPASS here is the first GPU confirmation of the up half.")
+def test_brushnet_whole_branch_forward_backward_fp32_vs_autograd():
+    """All 28 taps: BrushNetBranchTrainer in fp32 parity mode against float64 autograd through the oracle's brushnet_forward."""
+    from mirrorfusion_b200 import ops
+    from mirrorfusion_b200.backward import BrushNetBranchTrainer, brushnet_branch_shapes, pack_brushnet_branch, unpack_conv_grad
+    from mirrorfusion_b200.config import TINY
+    from mirrorfusion_b200.synth import make_state_dict
+    from mirrorfusion_b200.train import FlatParams
+    from oracle import mf_oracle as O
+    ops.lib()
+    cfg = TINY
+    B, H, W = 2, 16, 16
+    gen = torch.Generator().manual_seed(9)
+    sd = {k: v.double().requires_grad_(True) for k, v in make_state_dict(cfg, "brushnet").items()}
+    sample = torch.randn(B, cfg.in_channels, H, W, generator=gen, dtype=torch.float64)
+    cond = torch.randn(B, cfg.conditioning_channels, H, W, generator=gen, dtype=torch.float64)
+    t = torch.tensor([700, 3])
+    down, mid, up = O.brushnet_forward(sd, cfg, sample, t, cond)
+    rnd = lambda ts: [torch.randn(x.shape, generator=gen, dtype=torch.float64) for x in ts]
+    d_down, d_up, d_mid = rnd(down), rnd(up), rnd([mid])[0]
+    (sum((a * b).sum() for a, b in zip(down + up, d_down + d_up)) + (mid * d_mid).sum()).backward()
+    with torch.no_grad():
+        h0 = F.conv2d(torch.cat([sample, cond], 1), sd["conv_in_condition.weight"], sd["conv_in_condition.bias"], padding=1)
+        emb = O.time_embed(sd, t, B, cfg.block_out_channels[0], torch.float64)
+    shapes = brushnet_branch_shapes(cfg)
+    flat = FlatParams(shapes, "cuda")
+    flat.load_state_dict(pack_brushnet_branch(cfg, {k: v.detach() for k, v in sd.items()}))
+    net = BrushNetBranchTrainer(flat, cfg, B=B, H=H, W=W, precision="fp32")
+    rb = {p: F.linear(F.silu(emb), sd[f"{p}.time_emb_proj.weight"], sd[f"{p}.time_emb_proj.bias"]).detach().float().cuda()
+          for p in net.resnet_prefixes()}
+    nhwc = lambda x: x.detach().permute(0, 2, 3, 1).reshape(B, -1, x.shape[1]).float().contiguous()
+
+    def rel(a, b):
+        a, b = a.double().cpu(), b.double()
+        return float(a.norm()) if float(b.norm()) < 1e-9 else float((a - b).norm() / b.norm())
+
+    td, tm, tu = net.forward(nhwc(h0).cuda(), rb)
+    for a, b in zip(td + [tm] + tu, down + [mid] + up):
+        assert rel(a, nhwc(b)) < 1e-4
+    d_h0, d_rb = net.backward([nhwc(d).cuda() for d in d_down], nhwc(d_mid).cuda(), [nhwc(d).cuda() for d in d_up])
+    assert rel(d_h0.sum((0, 1)), sd["conv_in_condition.bias"].grad) < 1e-3
+    for name in shapes:
+        if name.endswith(".weight.b"):
+            continue
+        if name.endswith(".weight.a"):
+            want = sd[name[:-2]].grad[:, :, 0, 0]
+            got = torch.cat([flat.g(name), flat.g(name[:-2] + ".b")], 1)
+        else:
+            want = sd[name].grad
+            got = flat.g(name)
+            got = unpack_conv_grad(got, 3) if want.dim() == 4 and want.shape[-1] == 3 else got.reshape(want.shape)
+        assert rel(got, want) < 1e-3, name
+    for p, g in d_rb.items():
+        assert rel(g.sum(0), sd[f"{p}.time_emb_proj.bias"].grad) < 1e-3, p
