@@ -52,6 +52,7 @@ def test_brushnet_down_mid_forward_backward_fp32_vs_autograd():
         assert rel(g.sum(0), sd[f"{p}.time_emb_proj.bias"].grad) < 1e-3, p
 
 
+@pytest.mark.timeout(180)
 @pytest.mark.xfail(strict=False, reason="first GPU run pending: written after the round's GPU budget was spent.  The program's dataflow is "
                                         "verified on the CPU stand-in (tests/test_oracle_train.py) and its down / mid half on B200 (test above); "
                                         "an XPASS here is the first GPU confirmation of the up half.")
