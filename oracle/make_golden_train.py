@@ -87,6 +87,26 @@ def resnet_block_golden():
     print("wrote resnet_block_grad.npz", len(out), "arrays")
 
 
+def lr_schedule_golden():
+    """Multipliers of the reference's own get_scheduler (S/optimization.py:289-352) for the schedules the script can select."""
+    import_reference()
+    from diffusers.optimization import get_scheduler
+    out = {}
+    for name in ("constant", "constant_with_warmup", "linear", "cosine"):
+        prm = torch.nn.Parameter(torch.zeros(1))
+        opt = torch.optim.AdamW([prm], lr=1e-4)
+        sch = get_scheduler(name, optimizer=opt, num_warmup_steps=5, num_training_steps=40)
+        lrs = []
+        for _ in range(45):
+            lrs.append(sch.get_last_lr()[0])
+            opt.step()
+            sch.step()
+        out[name] = np.array(lrs)
+    np.savez_compressed(os.path.join(GOLD, "lr_schedules.npz"), **out)
+    print("wrote lr_schedules.npz")
+
+
 if __name__ == "__main__":
     main()
     resnet_block_golden()
+    lr_schedule_golden()

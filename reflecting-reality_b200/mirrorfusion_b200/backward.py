@@ -642,3 +642,27 @@ class BrushNetBranchTrainer(BrushNetDownMidTrainer):
         d_h0, d_rb_down = super().backward(d_down_taps, d_mid_tap)  # mid tap adds up_seq[0].dx; down taps add the skip gradients
         d_rb.update(d_rb_down)
         return d_h0, d_rb
+
+
+def unpack_brushnet_branch(cfg, flat: FlatParams) -> Dict[str, torch.Tensor]:
+    """Inverse of pack_brushnet_branch: the trained branch parameters back in the reference's state_dict naming and OIHW layout
+    (what `BrushNetModel.save_pretrained` writes at a checkpoint, E/train_brushnet_mirror.py:997-1032) — fp32 masters, on the host.
+    conv_in_condition and the timestep path are not in the flat buffer yet and keep their loaded values."""
+    shapes = brushnet_branch_shapes(cfg)
+    out: Dict[str, torch.Tensor] = {}
+    for name, shp in shapes.items():
+        if name.endswith(".conv_shortcut.weight.b"):
+            continue
+        v = flat.p(name).detach().float().cpu()
+        if name.endswith(".conv_shortcut.weight.a"):
+            v = torch.cat([v, flat.p(name[:-2] + ".b").detach().float().cpu()], 1)
+            out[name[:-2]] = v[:, :, None, None].contiguous()
+        elif name.endswith(".weight") and len(shp) == 2 and ".norm" not in name:
+            Cout, k = shp
+            if name.startswith("brushnet_") or ".conv_shortcut." in name:      # 1x1 convs
+                out[name] = v[:, :, None, None].contiguous()
+            else:                                                            # packed 3x3: [Cout, (kh, kw, ci)] -> OIHW
+                out[name] = unpack_conv_grad(v, 3)
+        else:
+            out[name] = v.clone()
+    return out

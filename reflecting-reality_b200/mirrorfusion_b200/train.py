@@ -176,3 +176,43 @@ class TrainLoss:
     def __call__(self, pred, target, weights=None, grad=None):
         ops.mse_loss(pred, target, self.loss, self.ws, weights=weights, per_sample=self.per_sample, grad=grad)
         return self.loss
+
+
+class LRSchedule:
+    """The learning-rate schedules `diffusers.optimization.get_scheduler` builds for the fine-tune script
+    (S/optimization.py:40-78,123-185; E/train_brushnet_mirror.py:1257-1265; default "constant"): a multiplier of the initial
+    learning rate as a function of the optimizer step, applied by writing `param_groups[0]["lr"]` like torch's LambdaLR does.
+    `step()` after every optimizer step; `get_last_lr()` for logging (:1517)."""
+
+    NAMES = ("constant", "constant_with_warmup", "linear", "cosine")
+
+    def __init__(self, optimizer: B200AdamW, name: str = "constant", num_warmup_steps: int = 0, num_training_steps: int = 0,
+                 num_cycles: float = 0.5):
+        if name not in self.NAMES:
+            raise ValueError(f"unknown lr schedule {name!r}; supported: {self.NAMES}")
+        self.opt, self.name, self.warmup, self.total, self.cycles = optimizer, name, num_warmup_steps, num_training_steps, num_cycles
+        self.base_lr = optimizer.param_groups[0]["lr"]
+        self.last_epoch = 0
+        self._apply()
+
+    def multiplier(self, step: int) -> float:
+        if self.name == "constant":
+            return 1.0
+        if step < self.warmup:
+            return float(step) / float(max(1, self.warmup))
+        if self.name == "constant_with_warmup":
+            return 1.0
+        if self.name == "linear":
+            return max(0.0, float(self.total - step) / float(max(1, self.total - self.warmup)))
+        progress = float(step - self.warmup) / float(max(1, self.total - self.warmup))
+        return max(0.0, 0.5 * (1.0 + math.cos(math.pi * float(self.cycles) * 2.0 * progress)))
+
+    def _apply(self):
+        self.opt.param_groups[0]["lr"] = self.base_lr * self.multiplier(self.last_epoch)
+
+    def step(self):
+        self.last_epoch += 1
+        self._apply()
+
+    def get_last_lr(self):
+        return [self.opt.param_groups[0]["lr"]]

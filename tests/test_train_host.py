@@ -90,3 +90,35 @@ def test_flat_grad_allreduce_gloo_world2():
     for rank, g, loss, nworks in res:
         assert torch.equal(g, torch.arange(1000, dtype=torch.float32) * 3)   # SUM over ranks; the mean is the AdamW grad_scale
         assert loss == 1.5 and nworks == 3
+
+
+def test_lr_schedules_match_the_reference_get_scheduler(golden_dir):
+    from mirrorfusion_b200.train import LRSchedule
+    g = np.load(os.path.join(golden_dir, "lr_schedules.npz"))
+    for name in LRSchedule.NAMES:
+        opt = B200AdamW(FlatParams({"w": (4,)}, "cpu", with_bf16=False), lr=1e-4)
+        sch = LRSchedule(opt, name, num_warmup_steps=5, num_training_steps=40)
+        lrs = []
+        for _ in range(45):
+            lrs.append(sch.get_last_lr()[0])
+            sch.step()
+        np.testing.assert_allclose(lrs, g[name], rtol=1e-12, atol=1e-18, err_msg=name)
+    with pytest.raises(ValueError):
+        LRSchedule(opt, "polynomial")
+
+
+def test_brushnet_branch_pack_unpack_roundtrip():
+    """Checkpoint export: flat packed layout -> the reference's state_dict naming / OIHW layout, bit-exact."""
+    from mirrorfusion_b200.backward import brushnet_branch_shapes, pack_brushnet_branch, unpack_brushnet_branch
+    from mirrorfusion_b200.config import MICRO
+    from mirrorfusion_b200.synth import make_state_dict
+    sd = make_state_dict(MICRO, "brushnet")
+    flat = FlatParams(brushnet_branch_shapes(MICRO), "cpu", with_bf16=False)
+    for k, v in pack_brushnet_branch(MICRO, sd).items():
+        flat.p(k).copy_(v)
+    back = unpack_brushnet_branch(MICRO, flat)
+    assert len(back) >= 250
+    for k, v in back.items():
+        assert v.shape == sd[k].shape and torch.equal(v, sd[k].float()), k
+    missing = [k for k in sd if k not in back]
+    assert all(k.startswith(("conv_in_condition.", "time_embedding.")) or ".time_emb_proj." in k for k in missing)
