@@ -273,6 +273,9 @@ int mfb_groupnorm_bwd(const void* x1, int C1, const void* x2, int C2, const void
 /* out[b][c] = sum over image b's HW pixels of dy[b][p][c] (fp32 [B, C]): the gradient of the per-image row bias
  * time_emb_proj(silu(emb))[:, :, None, None] (S/models/resnet.py:369-379).  dtype 0 = bf16 / 1 = fp32 dy. */
 int mfb_rowsum_per_image(const void* dy, int dtype, int B, int HW, int C, float* out, void* stream);
+/* y = silu(x) and / or dx = dy * silu'(x) over n fp32 elements (dy: dtype 0 = bf16 / 1 = fp32; y or dx may be NULL): the elementwise
+ * piece of the timestep MLP's backward (S/models/embeddings.py:226-237, S/models/resnet.py:369-376). */
+int mfb_silu_bwd(const float* x, const void* dy, int dy_dtype, float* y, float* dx, long long n, void* stream);
 
 #ifdef __cplusplus
 }

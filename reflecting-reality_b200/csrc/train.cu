@@ -596,6 +596,23 @@ __global__ void rowsum_kernel(const T* __restrict__ dy, int HW, int C, float* __
         out[static_cast<size_t>(b) * C + c] = (sm[0][threadIdx.x] + sm[1][threadIdx.x]) + (sm[2][threadIdx.x] + sm[3][threadIdx.x]);
 }
 
+// ---------------------------------------------------------------------------------------------- SiLU forward value + backward
+// y = silu(x) (optional) and dx = dy * silu'(x) (optional), fp32 x; dy fp32 or bf16.  The timestep MLP's backward
+// (S/models/embeddings.py:226-237, S/models/resnet.py:369-376) is GEMV-sized: this is its only elementwise piece.
+template <typename T>
+__global__ void silu_bwd_kernel(const float* __restrict__ x, const T* __restrict__ dy, float* __restrict__ y, float* __restrict__ dx,
+                                long long n) {
+    pdl_trigger();
+    pdl_wait();
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const float v = x[i];
+        const float sg = 1.0f / (1.0f + expf(-v));
+        if (y) y[i] = v * sg;
+        if (dx) dx[i] = ld_as_float(dy + i) * (sg * (1.0f + v * (1.0f - sg)));
+    }
+}
+
 }  // namespace mfb
 
 using namespace mfb;
@@ -785,5 +802,18 @@ extern "C" int mfb_rowsum_per_image(const void* dy, int dtype, int B, int HW, in
         MFB_CUDA_OK(launch_k(rowsum_kernel<float>, grid, dim3(256), 0, st, 1, static_cast<const float*>(dy), HW, C, out));
     else
         MFB_CUDA_OK(launch_k(rowsum_kernel<__nv_bfloat16>, grid, dim3(256), 0, st, 1, static_cast<const __nv_bfloat16*>(dy), HW, C, out));
+    return MFB_OK;
+}
+
+extern "C" int mfb_silu_bwd(const float* x, const void* dy, int dy_dtype, float* y, float* dx, long long n, void* stream) {
+    MFB_REQUIRE(x && (y || dx) && n > 0, "null pointer / empty buffer");
+    MFB_REQUIRE(dx == nullptr || dy != nullptr, "dx needs dy");
+    MFB_REQUIRE(dy_dtype == 0 || dy_dtype == 1, "dy_dtype must be 0 (bf16) or 1 (fp32)");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int grid = chunks_for(n, 256, 148 * 8);
+    if (dy_dtype == 1)
+        MFB_CUDA_OK(launch_k(silu_bwd_kernel<float>, dim3(grid), dim3(256), 0, st, 1, x, static_cast<const float*>(dy), y, dx, n));
+    else
+        MFB_CUDA_OK(launch_k(silu_bwd_kernel<__nv_bfloat16>, dim3(grid), dim3(256), 0, st, 1, x, static_cast<const __nv_bfloat16*>(dy), y, dx, n));
     return MFB_OK;
 }

@@ -76,6 +76,7 @@ _SIGS = {
     "mfb_conv_wgrad_tc": (i32, [vp, vp, i32, i32, i32, i32, i32, i32, i32, vp, vp, i32, vp, i64, vp]),
     "mfb_groupnorm_bwd": (i32, [vp, i32, vp, i32, vp, i32, i32, i32, i32, f32, vp, vp, i32, vp, vp, vp, vp, vp, vp, i32, vp]),
     "mfb_rowsum_per_image": (i32, [vp, i32, i32, i32, i32, vp, vp]),
+    "mfb_silu_bwd": (i32, [vp, vp, i32, vp, vp, i64, vp]),
 }
 EXPORTS = tuple(_SIGS)
 

@@ -666,3 +666,103 @@ def unpack_brushnet_branch(cfg, flat: FlatParams) -> Dict[str, torch.Tensor]:
         else:
             out[name] = v.clone()
     return out
+
+
+def time_path_shapes(cfg, resnet_prefixes) -> Dict[str, Tuple[int, ...]]:
+    """Flat entries of the timestep path: the TimestepEmbedding MLP and ALL time_emb_proj layers of the net concatenated into
+    one [sum Cout, temb] matrix in the order of `resnet_prefixes` (one GEMV forward, one weight-gradient call backward)."""
+    c0, temb = cfg.block_out_channels[0], cfg.time_embed_dim
+    return {"time_embedding.linear_1.weight": (temb, c0), "time_embedding.linear_1.bias": (temb,),
+            "time_embedding.linear_2.weight": (temb, temb), "time_embedding.linear_2.bias": (temb,),
+            "time_emb_proj.wcat": (sum(resnet_cout(cfg, p) for p in resnet_prefixes), temb),
+            "time_emb_proj.bcat": (sum(resnet_cout(cfg, p) for p in resnet_prefixes),)}
+
+
+def resnet_cout(cfg, prefix: str) -> int:
+    """Output channels of a BrushNet resnet by its state_dict prefix."""
+    boc = cfg.block_out_channels
+    parts = prefix.split(".")
+    if parts[0] == "mid_block":
+        return boc[-1]
+    i = int(parts[1])
+    return boc[i] if parts[0] == "down_blocks" else list(reversed(boc))[i]
+
+
+def pack_time_path(cfg, sd, resnet_prefixes) -> Dict[str, torch.Tensor]:
+    out = {k: sd[k].float().contiguous() for k in ("time_embedding.linear_1.weight", "time_embedding.linear_1.bias",
+                                                    "time_embedding.linear_2.weight", "time_embedding.linear_2.bias")}
+    out["time_emb_proj.wcat"] = torch.cat([sd[p + ".time_emb_proj.weight"].float() for p in resnet_prefixes], 0).contiguous()
+    out["time_emb_proj.bcat"] = torch.cat([sd[p + ".time_emb_proj.bias"].float() for p in resnet_prefixes], 0).contiguous()
+    return out
+
+
+class TimePathTrainer:
+    """Timestep path forward and backward (S/models/embeddings.py:27-67,226-237; S/models/resnet.py:369-376):
+    sinusoid(t) -> linear_1 -> SiLU -> linear_2 -> SiLU -> the concatenated time_emb_proj GEMV -> row-bias table [B, sum Cout].
+    Backward consumes the per-resnet d rowbias of the block programs.  Everything is GEMV-sized (M = batch): the weight gradients
+    are `conv_wgrad` calls with the batch as the "pixels", the data gradients are one implicit-GEMM plan (K = sum Cout is too long
+    for the small-linear kernel) and one small linear, the activation derivative is `silu_bwd`.
+    STATUS: dataflow verified on the CPU stand-in only; not yet run on a GPU."""
+
+    def __init__(self, flat: FlatParams, cfg, resnet_prefixes, *, B: int, precision: str = "bf16", K=None):
+        K = _ops if K is None else K
+        self.K, self.flat, self.cfg, self.B, self.prefixes = K, flat, cfg, B, list(resnet_prefixes)
+        self.dt = torch.float32 if precision == "fp32" else torch.bfloat16
+        dev = flat.param.device
+        c0, temb = cfg.block_out_channels[0], cfg.time_embed_dim
+        self.N = N = sum(resnet_cout(cfg, p) for p in self.prefixes)
+        self.off, o = {}, 0
+        for p in self.prefixes:
+            self.off[p] = (o, resnet_cout(cfg, p))
+            o += resnet_cout(cfg, p)
+        f32 = torch.float32
+        z = lambda *s, dt=f32: torch.zeros(*s, device=dev, dtype=dt)
+        self.t, self.sin, self.h1, self.s1, self.e, self.s2 = z(B), z(B, c0), z(B, temb), z(B, temb), z(B, temb), z(B, temb)
+        self.rowbias, self.d_rb = z(B, N), z(B, N)
+        self.d_rb_act, self.d_s2_act = z(B, N, dt=self.dt), z(B, temb, dt=self.dt)
+        self.d_e, self.d_s1, self.d_h1 = z(B, temb), z(B, temb), z(B, temb)
+        self.zero_bias = z(temb)
+        # working copies the small-linear kernel reads (activation dtype), and the transposed ones of the data gradients
+        self.w1, self.w2, self.wcat = z(temb, c0, dt=self.dt), z(temb, temb, dt=self.dt), z(N, temb, dt=self.dt)
+        self.w2t, self.wcat_t = z(temb, temb, dt=self.dt), z(temb, N, dt=self.dt)
+        self.plan_ds2 = K.ConvPlan(self.d_rb_act, self.wcat_t, self.d_s2_act, B=1, H=1, W=B, Cin=N, Cout=temb, ksize=1)
+        self.refresh_dgrad_weights()
+
+    def refresh_dgrad_weights(self):
+        f = self.flat
+        self.w1.copy_(f.p("time_embedding.linear_1.weight"))
+        self.w2.copy_(f.p("time_embedding.linear_2.weight"))
+        self.wcat.copy_(f.p("time_emb_proj.wcat"))
+        self.w2t.copy_(f.p("time_embedding.linear_2.weight").t())
+        self.wcat_t.copy_(f.p("time_emb_proj.wcat").t())
+
+    def rowbias_of(self, prefix: str) -> torch.Tensor:
+        o, c = self.off[prefix]
+        return self.rowbias[:, o:o + c]
+
+    def forward(self, timesteps: torch.Tensor) -> Dict[str, torch.Tensor]:
+        """timesteps [B] (any numeric dtype) -> {resnet prefix: rowbias view [B, Cout]}."""
+        K, f = self.K, self.flat
+        self.t.copy_(timesteps.to(torch.float32))
+        K.timestep_sinusoid(self.t, self.sin)
+        K.linear_small(self.sin, self.w1, f.p("time_embedding.linear_1.bias"), self.h1)                 # pre-activation kept
+        K.linear_small(self.h1, self.w2, f.p("time_embedding.linear_2.bias"), self.e, act_in=True)
+        K.linear_small(self.e, self.wcat, f.p("time_emb_proj.bcat"), self.rowbias, act_in=True)
+        return {p: self.rowbias_of(p) for p in self.prefixes}
+
+    def backward(self, d_rowbias: Dict[str, torch.Tensor]):
+        K, f, B = self.K, self.flat, self.B
+        for p, g in d_rowbias.items():
+            o, c = self.off[p]
+            self.d_rb[:, o:o + c].copy_(g)
+        wg = dict(B=B, H=1, W=1, ksize=1, accumulate=True)
+        K.silu_bwd(self.e, y=self.s2)                                                              # silu(e), recomputed
+        K.conv_wgrad(self.s2, self.d_rb, f.g("time_emb_proj.wcat"), f.g("time_emb_proj.bcat"), **wg)
+        K.f32_to_bf16(self.d_rb, self.d_rb_act)
+        self.plan_ds2.run()                                                                        # d silu(e) = d rb . Wcat
+        K.silu_bwd(self.e, dy=self.d_s2_act, dx=self.d_e)
+        K.silu_bwd(self.h1, y=self.s1)
+        K.conv_wgrad(self.s1, self.d_e, f.g("time_embedding.linear_2.weight"), f.g("time_embedding.linear_2.bias"), **wg)
+        K.linear_small(self.d_e, self.w2t, self.zero_bias, self.d_s1)                              # d silu(h1) = d e . W2
+        K.silu_bwd(self.h1, dy=self.d_s1, dx=self.d_h1)
+        K.conv_wgrad(self.sin, self.d_h1, f.g("time_embedding.linear_1.weight"), f.g("time_embedding.linear_1.bias"), **wg)

@@ -438,3 +438,9 @@ def rowsum_per_image(dy, out, *, B, HW):
     """out [B, C] fp32 = per-image sums of dy [B, HW, C] over the pixels (gradient of the time-embedding row bias)."""
     _req(out, f32, "out")
     check(lib().mfb_rowsum_per_image(_ptr(dy), int(_is32(dy)), B, HW, dy.shape[-1], _ptr(out), _stream()))
+
+
+def silu_bwd(x, dy=None, y=None, dx=None):
+    """y = silu(x) and / or dx = dy * silu'(x); x, y, dx fp32, dy fp32 or bf16."""
+    _req(x, f32, "x")
+    check(lib().mfb_silu_bwd(_ptr(x), _ptr(dy), 1 if dy is None else int(_is32(dy)), _ptr(y), _ptr(dx), x.numel(), _stream()))

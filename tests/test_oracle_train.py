@@ -349,3 +349,37 @@ def test_brushnet_branch_program_dataflow_on_the_cpu_stand_in():
     for p, g in d_rb.items():
         assert rel(g.sum(0), sd[f"{p}.time_emb_proj.bias"].grad) < 1e-3, p
     assert len(d_rb) == 22
+
+
+def test_time_path_program_dataflow_on_the_cpu_stand_in():
+    """TimePathTrainer (sinusoid -> TimestepEmbedding MLP -> all time_emb_proj as one GEMV; backward from the per-resnet row-bias
+    gradients) on the stand-in against autograd of the oracle's time_embed + per-resnet projections."""
+    import torch_kernels as TK
+    from mirrorfusion_b200.backward import TimePathTrainer, pack_time_path, time_path_shapes
+    from mirrorfusion_b200.config import MICRO
+    from mirrorfusion_b200.synth import make_state_dict
+    from mirrorfusion_b200.train import FlatParams
+    from oracle import mf_oracle as O
+    cfg, B = MICRO, 3
+    gen = torch.Generator().manual_seed(4)
+    sd = {k: v.double().requires_grad_(True) for k, v in make_state_dict(cfg, "brushnet").items()}
+    prefixes = sorted({k[:-len(".time_emb_proj.weight")] for k in sd if k.endswith(".time_emb_proj.weight")})
+    assert len(prefixes) == 22
+    t = torch.tensor([999, 0, 421])
+    emb = O.time_embed(sd, t, B, cfg.block_out_channels[0], torch.float64)
+    rb = {p: F.linear(F.silu(emb), sd[f"{p}.time_emb_proj.weight"], sd[f"{p}.time_emb_proj.bias"]) for p in prefixes}
+    d_rb = {p: torch.randn(v.shape, generator=gen, dtype=torch.float64) for p, v in rb.items()}
+    sum((rb[p] * d_rb[p]).sum() for p in prefixes).backward()
+    flat = FlatParams(time_path_shapes(cfg, prefixes), "cpu", with_bf16=False)
+    for k, v in pack_time_path(cfg, {k: v.detach() for k, v in sd.items()}, prefixes).items():
+        flat.p(k).copy_(v)
+    tp = TimePathTrainer(flat, cfg, prefixes, B=B, precision="fp32", K=TK)
+    got = tp.forward(t)
+    for p in prefixes:
+        np.testing.assert_allclose(got[p].numpy(), rb[p].detach().numpy(), rtol=1e-4, atol=1e-5)
+    tp.backward({p: g.float() for p, g in d_rb.items()})
+    rel = lambda a, b: float((a.double() - b.double()).norm() / b.double().norm())
+    for k in ("time_embedding.linear_1.weight", "time_embedding.linear_1.bias", "time_embedding.linear_2.weight", "time_embedding.linear_2.bias"):
+        assert rel(flat.g(k), sd[k].grad) < 1e-4, k
+    assert rel(flat.g("time_emb_proj.wcat"), torch.cat([sd[p + ".time_emb_proj.weight"].grad for p in prefixes], 0)) < 1e-4
+    assert rel(flat.g("time_emb_proj.bcat"), torch.cat([sd[p + ".time_emb_proj.bias"].grad for p in prefixes], 0)) < 1e-4

@@ -98,3 +98,26 @@ def upsample2x(x, out, *, B, H, W):
     """nearest x2 of NHWC pixel vectors (dtype-agnostic copy, like the kernel)."""
     v = x.reshape(B, H, W, -1)
     out.copy_(v.repeat_interleave(2, 1).repeat_interleave(2, 2).reshape(out.shape))
+
+
+def timestep_sinusoid(t, out):
+    from oracle import mf_oracle as O
+    out.copy_(O.timestep_embedding(t, out.shape[-1]))
+
+
+def linear_small(x, w, b, y, act_in=False, act_out=False):
+    v = F.silu(x) if act_in else x
+    r = F.linear(v.float(), w.float(), b)
+    y.copy_(F.silu(r) if act_out else r)
+
+
+def silu_bwd(x, dy=None, y=None, dx=None):
+    if y is not None:
+        y.copy_(F.silu(x))
+    if dx is not None:
+        sg = torch.sigmoid(x)
+        dx.copy_(dy.float() * (sg * (1 + x * (1 - sg))))
+
+
+def f32_to_bf16(x, out):
+    out.copy_(x.view_as(out))
