@@ -766,3 +766,84 @@ class TimePathTrainer:
         K.linear_small(self.d_e, self.w2t, self.zero_bias, self.d_s1)                              # d silu(h1) = d e . W2
         K.silu_bwd(self.h1, dy=self.d_s1, dx=self.d_h1)
         K.conv_wgrad(self.sin, self.d_h1, f.g("time_embedding.linear_1.weight"), f.g("time_embedding.linear_1.bias"), **wg)
+
+
+def brushnet_resnet_prefixes(cfg):
+    """state_dict prefixes of BrushNet's 22 resnets in forward order (down, mid, up)."""
+    n, nl = len(cfg.block_out_channels), cfg.layers_per_block
+    return ([f"down_blocks.{i}.resnets.{j}" for i in range(n) for j in range(nl)] + [f"mid_block.resnets.{j}" for j in range(2)] +
+            [f"up_blocks.{i}.resnets.{j}" for i in range(n) for j in range(nl + 1)])
+
+
+def brushnet_shapes(cfg) -> Dict[str, Tuple[int, ...]]:
+    """Flat entries of the WHOLE BrushNetModel: conv_in_condition (packed), the timestep path, the branch and its 28 zero-convs."""
+    cin = cfg.in_channels + cfg.conditioning_channels
+    s = {"conv_in_condition.weight": (cfg.block_out_channels[0], 9 * cin), "conv_in_condition.bias": (cfg.block_out_channels[0],)}
+    s.update(time_path_shapes(cfg, brushnet_resnet_prefixes(cfg)))
+    s.update(brushnet_branch_shapes(cfg))
+    return s
+
+
+def pack_brushnet(cfg, sd) -> Dict[str, torch.Tensor]:
+    w = sd["conv_in_condition.weight"].float()
+    out = {"conv_in_condition.weight": w.permute(0, 2, 3, 1).reshape(w.shape[0], -1).contiguous(),
+           "conv_in_condition.bias": sd["conv_in_condition.bias"].float().contiguous()}
+    out.update(pack_time_path(cfg, sd, brushnet_resnet_prefixes(cfg)))
+    out.update(pack_brushnet_branch(cfg, sd))
+    return out
+
+
+class BrushNetTrainer:
+    """BrushNetModel.forward (S/models/brushnet.py:678-925) for training and its backward, end to end on the kernels:
+    (sample, brushnet_cond, timesteps) -> 12 + 1 + 15 taps; backward(d taps) accumulates the gradient of EVERY BrushNet parameter
+    (618.8 M for SD1.5) into the flat buffer.  = conv_in_condition (boundary kernel forward, CUDA-core weight gradient over its
+    10 input channels) + TimePathTrainer + BrushNetBranchTrainer.  The tap gradients are what the frozen UNet's backward will
+    deliver (not built).  conditioning_scale = 1 (training).
+    STATUS: dataflow verified on the CPU stand-in against autograd of the oracle BrushNet over all parameters; on a GPU only the
+    down / mid half of the branch has run."""
+
+    def __init__(self, flat: FlatParams, cfg, *, B: int, H: int, W: int, precision: str = "bf16", K=None):
+        K = _ops if K is None else K
+        self.K, self.flat, self.cfg, self.B, self.H, self.W = K, flat, cfg, B, H, W
+        self.dt = torch.float32 if precision == "fp32" else torch.bfloat16
+        dev = flat.param.device
+        self.cin = cfg.in_channels + cfg.conditioning_channels
+        c0 = cfg.block_out_channels[0]
+        self.xcat = torch.zeros(B, self.cin, H, W, device=dev, dtype=torch.float32)
+        self.xcat_nhwc = torch.zeros(B, H * W, self.cin, device=dev, dtype=self.dt)
+        self.h0 = torch.zeros(B, H * W, c0, device=dev, dtype=self.dt)
+        self.w_in = torch.zeros(3, 3, self.cin, c0, device=dev, dtype=torch.float32)
+        self.time = TimePathTrainer(flat, cfg, brushnet_resnet_prefixes(cfg), B=B, precision=precision, K=K)
+        self.branch = BrushNetBranchTrainer(flat, cfg, B=B, H=H, W=W, precision=precision, K=K)
+        self.refresh_dgrad_weights(parts=False)
+
+    def refresh_dgrad_weights(self, parts: bool = True):
+        """After every optimizer step: re-derive the weight copies the kernels read in another layout."""
+        c0 = self.cfg.block_out_channels[0]
+        self.w_in.copy_(self.flat.p("conv_in_condition.weight").view(c0, 3, 3, self.cin).permute(1, 2, 3, 0))
+        if parts:
+            self.time.refresh_dgrad_weights()
+            self.branch.refresh_dgrad_weights()
+
+    def forward(self, sample: torch.Tensor, brushnet_cond: torch.Tensor, timesteps: torch.Tensor):
+        """sample [B,4,H,W], brushnet_cond [B,6,H,W] fp32 NCHW (the reference layout), timesteps [B].
+        -> (down taps, mid tap, up taps) as NHWC buffers owned by the trainer."""
+        K, f = self.K, self.flat
+        ca = sample.shape[1]
+        self.xcat[:, :ca].copy_(sample)
+        self.xcat[:, ca:].copy_(brushnet_cond)                                   # torch.cat([sample, cond], 1), brushnet.py:810
+        K.conv_in(self.xcat[:, :ca].contiguous(), self.xcat[:, ca:].contiguous(), self.w_in, f.p("conv_in_condition.bias"), self.h0)
+        rb = self.time.forward(timesteps)
+        return self.branch.forward(self.h0, rb)
+
+    def backward(self, d_down_taps, d_mid_tap, d_up_taps):
+        K, f = self.K, self.flat
+        d_h0, d_rb = self.branch.backward(d_down_taps, d_mid_tap, d_up_taps)
+        self.time.backward(d_rb)
+        # conv_in_condition: weight / bias gradient over the 10-channel input (NHWC copy in the activation dtype)
+        if self.dt == torch.bfloat16:
+            K.nchw_to_nhwc(self.xcat, self.xcat_nhwc)
+        else:
+            self.xcat_nhwc.copy_(self.xcat.permute(0, 2, 3, 1).reshape(self.xcat_nhwc.shape))
+        K.conv_wgrad(self.xcat_nhwc, d_h0, f.g("conv_in_condition.weight"), f.g("conv_in_condition.bias"), B=self.B, H=self.H, W=self.W,
+                     ksize=3, accumulate=True)

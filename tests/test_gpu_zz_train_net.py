@@ -109,3 +109,57 @@ def test_brushnet_whole_branch_forward_backward_fp32_vs_autograd():
         assert rel(got, want) < 1e-3, name
     for p, g in d_rb.items():
         assert rel(g.sum(0), sd[f"{p}.time_emb_proj.bias"].grad) < 1e-3, p
+
+
+@pytest.mark.timeout(180)
+@pytest.mark.xfail(strict=False, reason="first GPU run pending (written after the round's GPU budget was spent); dataflow verified on the CPU "
+                                        "stand-in: tests/test_oracle_train.py::test_whole_brushnet_program_every_parameter_gradient_on_the_cpu_stand_in")
+def test_whole_brushnet_every_parameter_gradient_fp32_vs_autograd():
+    """BrushNetTrainer in fp32 parity mode: (sample, cond, timesteps) -> 28 taps and back; every parameter of the BrushNetModel
+    state_dict against float64 autograd through the oracle's brushnet_forward."""
+    from mirrorfusion_b200 import ops
+    from mirrorfusion_b200.backward import BrushNetTrainer, brushnet_resnet_prefixes, brushnet_shapes, pack_brushnet, unpack_conv_grad
+    from mirrorfusion_b200.config import TINY
+    from mirrorfusion_b200.synth import make_state_dict
+    from mirrorfusion_b200.train import FlatParams
+    from oracle import mf_oracle as O
+    ops.lib()
+    cfg = TINY
+    B, H, W = 2, 16, 16
+    gen = torch.Generator().manual_seed(10)
+    sd = {k: v.double().requires_grad_(True) for k, v in make_state_dict(cfg, "brushnet").items()}
+    sample = torch.randn(B, cfg.in_channels, H, W, generator=gen, dtype=torch.float64)
+    cond = torch.randn(B, cfg.conditioning_channels, H, W, generator=gen, dtype=torch.float64)
+    t = torch.tensor([850, 12])
+    down, mid, up = O.brushnet_forward(sd, cfg, sample, t, cond)
+    rnd = lambda ts: [torch.randn(x.shape, generator=gen, dtype=torch.float64) for x in ts]
+    d_down, d_up, d_mid = rnd(down), rnd(up), rnd([mid])[0]
+    (sum((a * b).sum() for a, b in zip(down + up, d_down + d_up)) + (mid * d_mid).sum()).backward()
+    shapes = brushnet_shapes(cfg)
+    flat = FlatParams(shapes, "cuda")
+    flat.load_state_dict(pack_brushnet(cfg, {k: v.detach() for k, v in sd.items()}))
+    net = BrushNetTrainer(flat, cfg, B=B, H=H, W=W, precision="fp32")
+    nhwc = lambda x: x.detach().permute(0, 2, 3, 1).reshape(B, -1, x.shape[1]).float().contiguous()
+
+    def rel(a, b):
+        a, b = a.double().cpu(), b.double()
+        return float(a.norm()) if float(b.norm()) < 1e-9 else float((a - b).norm() / b.norm())
+
+    td, tm, tu = net.forward(sample.float().cuda(), cond.float().cuda(), t.cuda())
+    for a, b in zip(td + [tm] + tu, down + [mid] + up):
+        assert rel(a, nhwc(b)) < 1e-4
+    net.backward([nhwc(d).cuda() for d in d_down], nhwc(d_mid).cuda(), [nhwc(d).cuda() for d in d_up])
+    prefixes = brushnet_resnet_prefixes(cfg)
+    for name in shapes:
+        if name.endswith(".weight.b"):
+            continue
+        if name == "time_emb_proj.wcat":
+            want, got = torch.cat([sd[p + ".time_emb_proj.weight"].grad for p in prefixes], 0), flat.g(name)
+        elif name == "time_emb_proj.bcat":
+            want, got = torch.cat([sd[p + ".time_emb_proj.bias"].grad for p in prefixes], 0), flat.g(name)
+        elif name.endswith(".weight.a"):
+            want, got = sd[name[:-2]].grad[:, :, 0, 0], torch.cat([flat.g(name), flat.g(name[:-2] + ".b")], 1)
+        else:
+            want, got = sd[name].grad, flat.g(name)
+            got = unpack_conv_grad(got, 3) if want.dim() == 4 and want.shape[-1] == 3 else got.reshape(want.shape)
+        assert rel(got, want) < 1e-3, name

@@ -383,3 +383,66 @@ def test_time_path_program_dataflow_on_the_cpu_stand_in():
         assert rel(flat.g(k), sd[k].grad) < 1e-4, k
     assert rel(flat.g("time_emb_proj.wcat"), torch.cat([sd[p + ".time_emb_proj.weight"].grad for p in prefixes], 0)) < 1e-4
     assert rel(flat.g("time_emb_proj.bcat"), torch.cat([sd[p + ".time_emb_proj.bias"].grad for p in prefixes], 0)) < 1e-4
+
+
+def test_whole_brushnet_program_every_parameter_gradient_on_the_cpu_stand_in():
+    """BrushNetTrainer: (sample, cond, timesteps) -> 28 taps and back, EVERY parameter of the BrushNetModel state_dict receives its
+    gradient (conv_in_condition, timestep MLP, 22 time_emb_proj, 22 resnets, 3 + 3 samplers, 28 zero-convs) — compared with float64
+    autograd through the oracle's brushnet_forward, no parameter excluded."""
+    import torch_kernels as TK
+    from mirrorfusion_b200.backward import BrushNetTrainer, brushnet_resnet_prefixes, brushnet_shapes, pack_brushnet, unpack_conv_grad
+    from mirrorfusion_b200.config import MICRO
+    from mirrorfusion_b200.synth import make_state_dict
+    from mirrorfusion_b200.train import FlatParams
+    from oracle import mf_oracle as O
+    cfg = MICRO
+    B, H, W = 2, 16, 16
+    gen = torch.Generator().manual_seed(10)
+    sd = {k: v.double().requires_grad_(True) for k, v in make_state_dict(cfg, "brushnet").items()}
+    sample = torch.randn(B, cfg.in_channels, H, W, generator=gen, dtype=torch.float64)
+    cond = torch.randn(B, cfg.conditioning_channels, H, W, generator=gen, dtype=torch.float64)
+    t = torch.tensor([850, 12])
+    down, mid, up = O.brushnet_forward(sd, cfg, sample, t, cond)
+    rnd = lambda ts: [torch.randn(x.shape, generator=gen, dtype=torch.float64) for x in ts]
+    d_down, d_up, d_mid = rnd(down), rnd(up), rnd([mid])[0]
+    (sum((a * b).sum() for a, b in zip(down + up, d_down + d_up)) + (mid * d_mid).sum()).backward()
+    shapes = brushnet_shapes(cfg)
+    flat = FlatParams(shapes, "cpu", with_bf16=False)
+    for k, v in pack_brushnet(cfg, {k: v.detach() for k, v in sd.items()}).items():
+        flat.p(k).copy_(v)
+    assert flat.numel >= sum(v.numel() for v in sd.values())           # every parameter lives in the flat buffer (+ alignment padding)
+    net = BrushNetTrainer(flat, cfg, B=B, H=H, W=W, precision="fp32", K=TK)
+    nhwc = lambda x: x.detach().permute(0, 2, 3, 1).reshape(B, -1, x.shape[1]).float().contiguous()
+
+    def rel(a, b):
+        a, b = a.double(), b.double()
+        return float(a.norm()) if float(b.norm()) < 1e-9 else float((a - b).norm() / b.norm())
+
+    td, tm, tu = net.forward(sample.float(), cond.float(), t)
+    for a, b in zip(td + [tm] + tu, down + [mid] + up):
+        assert rel(a, nhwc(b)) < 1e-4
+    net.backward([nhwc(d) for d in d_down], nhwc(d_mid), [nhwc(d) for d in d_up])
+    prefixes = brushnet_resnet_prefixes(cfg)
+    checked = set()
+    for name in shapes:
+        if name.endswith(".weight.b"):
+            continue
+        if name == "time_emb_proj.wcat":
+            want = torch.cat([sd[p + ".time_emb_proj.weight"].grad for p in prefixes], 0)
+            got = flat.g(name)
+            checked |= {p + ".time_emb_proj.weight" for p in prefixes}
+        elif name == "time_emb_proj.bcat":
+            want = torch.cat([sd[p + ".time_emb_proj.bias"].grad for p in prefixes], 0)
+            got = flat.g(name)
+            checked |= {p + ".time_emb_proj.bias" for p in prefixes}
+        elif name.endswith(".weight.a"):
+            want = sd[name[:-2]].grad[:, :, 0, 0]
+            got = torch.cat([flat.g(name), flat.g(name[:-2] + ".b")], 1)
+            checked.add(name[:-2])
+        else:
+            want = sd[name].grad
+            got = flat.g(name)
+            got = unpack_conv_grad(got, 3) if want.dim() == 4 and want.shape[-1] == 3 else got.reshape(want.shape)
+            checked.add(name)
+        assert rel(got, want) < 1e-3, name
+    assert checked == set(sd.keys())                                   # no parameter of the reference state_dict left out

@@ -121,3 +121,14 @@ def silu_bwd(x, dy=None, y=None, dx=None):
 
 def f32_to_bf16(x, out):
     out.copy_(x.view_as(out))
+
+
+def conv_in(sample, cond, w, bias, out, tap=None, out_post=None):
+    """NCHW fp32 inputs, w [3,3,Cin,Cout] -> NHWC out."""
+    x = sample if cond is None else torch.cat([sample, cond], 1)
+    y = F.conv2d(x.float(), w.permute(3, 2, 0, 1).float(), bias, padding=1)
+    out.copy_(_nhwc(y).reshape(out.shape))
+
+
+def nchw_to_nhwc(x, out):
+    out.copy_(_nhwc(x).reshape(out.shape))
