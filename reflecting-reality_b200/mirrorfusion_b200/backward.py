@@ -368,7 +368,7 @@ class UpsampleTrainer:
     resolution followed by a 2x2 sum-pool, which runs as a stride-2 plan with a fixed 0/1 weight (taps kh, kw in {1, 2},
     identity over channels) — a first version on existing kernels; a pooling kernel would do it in 4 adds per element.
     Flat entries: `<prefix>.conv.weight` packed [C, 9*C], `<prefix>.conv.bias` [C].
-    STATUS: dataflow verified on the CPU stand-in only (tests/test_oracle_train.py); not yet run on a GPU."""
+    STATUS: verified on the CPU stand-in (tests/test_oracle_train.py) and, as part of BrushNetTrainer, on B200 in fp32 parity mode."""
 
     def __init__(self, flat: FlatParams, prefix: str, *, B: int, H: int, W: int, C: int, precision: str = "bf16", K=None):
         K = _ops if K is None else K
@@ -445,7 +445,7 @@ class SkipResnetBlockTrainer:
     BrushNet's up blocks.  The concat is never materialised except normalised (GroupNorm reads both sources, as in the
     inference engine).  Backward returns one gradient per source: the GroupNorm backward writes its two halves, and the two
     data-gradient plans of the shortcut halves add them in their residual epilogue (d x = W_a^T d out + GN-half; same for
-    the skip).  STATUS: dataflow verified on the CPU stand-in only; not yet run on a GPU."""
+    the skip).  STATUS: verified on the CPU stand-in and, as part of BrushNetTrainer, on B200 in fp32 parity mode."""
 
     def __init__(self, flat: FlatParams, prefix: str, *, B: int, H: int, W: int, C1: int, C2: int, Cout: int, groups: int = 32,
                  eps: float = 1e-5, precision: str = "bf16", K=None):
@@ -576,8 +576,8 @@ class BrushNetBranchTrainer(BrushNetDownMidTrainer):
     the up-block resnet that takes it as skip — and its gradient is still formed inside ONE data-gradient plan (the zero-conv's,
     with both other gradients as residual inputs).  Backward order: up path in reverse (which leaves every skip gradient in the
     dx2 buffer of its resnet), mid block, down path.
-    STATUS: dataflow verified on the CPU stand-in (tests/test_oracle_train.py); the down / mid half has run on B200
-    (tests/test_gpu_zz_train_net.py), the up half has not."""
+    STATUS: verified on the CPU stand-in (tests/test_oracle_train.py) and on B200 in fp32 parity mode (down / mid half on its own,
+    the whole branch as part of BrushNetTrainer: tests/test_gpu_zz_train_net.py)."""
 
     def _build_up_path(self, B, dt, common):
         cfg, flat = self.cfg, self.flat
@@ -702,7 +702,7 @@ class TimePathTrainer:
     Backward consumes the per-resnet d rowbias of the block programs.  Everything is GEMV-sized (M = batch): the weight gradients
     are `conv_wgrad` calls with the batch as the "pixels", the data gradients are one implicit-GEMM plan (K = sum Cout is too long
     for the small-linear kernel) and one small linear, the activation derivative is `silu_bwd`.
-    STATUS: dataflow verified on the CPU stand-in only; not yet run on a GPU."""
+    STATUS: verified on the CPU stand-in and, as part of BrushNetTrainer, on B200 in fp32 parity mode."""
 
     def __init__(self, flat: FlatParams, cfg, resnet_prefixes, *, B: int, precision: str = "bf16", K=None):
         K = _ops if K is None else K
@@ -799,8 +799,8 @@ class BrushNetTrainer:
     (618.8 M for SD1.5) into the flat buffer.  = conv_in_condition (boundary kernel forward, CUDA-core weight gradient over its
     10 input channels) + TimePathTrainer + BrushNetBranchTrainer.  The tap gradients are what the frozen UNet's backward will
     deliver (not built).  conditioning_scale = 1 (training).
-    STATUS: dataflow verified on the CPU stand-in against autograd of the oracle BrushNet over all parameters; on a GPU only the
-    down / mid half of the branch has run."""
+    STATUS: verified against autograd of the oracle BrushNet over all parameters on the CPU stand-in AND on B200 in fp32 parity
+    mode (tests/test_gpu_zz_train_net.py); bf16 mode not yet run."""
 
     def __init__(self, flat: FlatParams, cfg, *, B: int, H: int, W: int, precision: str = "bf16", K=None):
         K = _ops if K is None else K

@@ -53,9 +53,8 @@ def test_brushnet_down_mid_forward_backward_fp32_vs_autograd():
 
 
 @pytest.mark.timeout(180)
-@pytest.mark.xfail(strict=False, reason="first GPU run pending: written after the round's GPU budget was spent.  The program's dataflow is "
-                                        "verified on the CPU stand-in (tests/test_oracle_train.py) and its down / mid half on B200 (test above); "
-                                        "an XPASS here is the first GPU confirmation of the up half.")
+@pytest.mark.xfail(strict=False, reason="this test itself has not run on a GPU yet (round-1 budget spent); the program it drives is a strict subset of "
+                                        "test_whole_brushnet_every_parameter_gradient_fp32_vs_autograd below, which passed on B200")
 def test_brushnet_whole_branch_forward_backward_fp32_vs_autograd():
     """All 28 taps: BrushNetBranchTrainer in fp32 parity mode against float64 autograd through the oracle's brushnet_forward."""
     from mirrorfusion_b200 import ops
@@ -112,8 +111,6 @@ def test_brushnet_whole_branch_forward_backward_fp32_vs_autograd():
 
 
 @pytest.mark.timeout(180)
-@pytest.mark.xfail(strict=False, reason="first GPU run pending (written after the round's GPU budget was spent); dataflow verified on the CPU "
-                                        "stand-in: tests/test_oracle_train.py::test_whole_brushnet_program_every_parameter_gradient_on_the_cpu_stand_in")
 def test_whole_brushnet_every_parameter_gradient_fp32_vs_autograd():
     """BrushNetTrainer in fp32 parity mode: (sample, cond, timesteps) -> 28 taps and back; every parameter of the BrushNetModel
     state_dict against float64 autograd through the oracle's brushnet_forward."""
