@@ -154,3 +154,60 @@ def resnet_block_case(cin, cout, seed=77):
         sd["r.conv_shortcut.weight"] = rn(cout, cin, 1, 1, scale=cin ** -0.5)
         sd["r.conv_shortcut.bias"] = 0.1 * rn(cout)
     return sd, rn(B, cin, H, W), rn(B, T), rn(B, cout, H, W)
+
+
+# ------------------------------------------------------------------------------------------------------------------------------
+# Restatements of the three backward passes the frozen UNet's dgrad-only chain still needs in the FORM the
+# kernels will compute them, so that the algorithms are pinned (tests/test_oracle_train.py, against torch autograd of the ops the
+# reference calls) before any CUDA is written.
+
+def attention_backward_two_pass(q, k, v, d_out, scale=None):
+    """Backward of F.scaled_dot_product_attention (S/models/attention_processor.py:1266-1268; no mask, no dropout) as the two
+    deterministic passes of a flash-style kernel pair, float64.  q [T, d], k / v [S, d] of ONE (batch, head).
+      forward statistics per query i:  L_i = logsumexp_j(scale q_i.k_j),  O_i = sum_j p_ij v_j,  D_i = dO_i . O_i
+      pass A (per query i):            p_ij = exp(scale q_i.k_j - L_i);  dS_ij = p_ij (dO_i.v_j - D_i);  dq_i = scale sum_j dS_ij k_j
+      pass B (per key j):              dv_j = sum_i p_ij dO_i;            dk_j = scale sum_i dS_ij q_i
+    Nothing of size T x S is stored; both passes recompute p from L.  -> (dq, dk, dv, L, D)."""
+    q, k, v, d_out = (np.asarray(a, dtype=np.float64) for a in (q, k, v, d_out))
+    scale = q.shape[-1] ** -0.5 if scale is None else scale
+    s = scale * q @ k.T
+    m = s.max(1, keepdims=True)
+    L = (m + np.log(np.exp(s - m).sum(1, keepdims=True)))[:, 0]
+    dq = np.zeros_like(q)
+    D = np.zeros(q.shape[0])
+    for i in range(q.shape[0]):                              # pass A: one query per warp
+        p = np.exp(scale * k @ q[i] - L[i])
+        o = p @ v
+        D[i] = d_out[i] @ o
+        ds = p * (v @ d_out[i] - D[i])
+        dq[i] = scale * ds @ k
+    dk, dv = np.zeros_like(k), np.zeros_like(v)
+    for j in range(k.shape[0]):                              # pass B: one key per warp, queries in order (deterministic)
+        p = np.exp(scale * q @ k[j] - L)
+        dv[j] = p @ d_out
+        ds = p * (d_out @ v[j] - D)
+        dk[j] = scale * ds @ q
+    return dq, dk, dv, L, D
+
+
+def layernorm_backward_dx(x, gamma, dy, eps=1e-5):
+    """Data gradient of F.layer_norm over the last dim (S/models/attention.py:313,360,386; the UNet is frozen, so no dgamma / dbeta):
+    with xhat = (x - mean) rstd and g = dy * gamma:  dx = rstd (g - mean(g) - xhat mean(g xhat)), row by row."""
+    x, gamma, dy = (np.asarray(a, dtype=np.float64) for a in (x, gamma, dy))
+    mean = x.mean(-1, keepdims=True)
+    rstd = 1.0 / np.sqrt(x.var(-1, keepdims=True) + eps)
+    xhat = (x - mean) * rstd
+    g = dy * gamma
+    return rstd * (g - g.mean(-1, keepdims=True) - xhat * (g * xhat).mean(-1, keepdims=True))
+
+
+def geglu_backward(proj, d_out):
+    """Backward of GEGLU's `h, gate = proj.chunk(2, -1); h * gelu(gate)` (S/models/activations.py:100-103, exact erf GELU):
+    d h = d out * gelu(gate);  d gate = d out * h * (Phi(gate) + gate phi(gate)).  -> d proj [.., 2*C]."""
+    from math import erf, pi, sqrt
+    proj, d_out = np.asarray(proj, dtype=np.float64), np.asarray(d_out, dtype=np.float64)
+    C = proj.shape[-1] // 2
+    h, gate = proj[..., :C], proj[..., C:]
+    Phi = 0.5 * (1.0 + np.vectorize(erf)(gate / sqrt(2.0)))
+    phi = np.exp(-0.5 * gate * gate) / sqrt(2.0 * pi)
+    return np.concatenate([d_out * gate * Phi, d_out * h * (Phi + gate * phi)], -1)

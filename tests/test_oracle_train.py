@@ -446,3 +446,28 @@ def test_whole_brushnet_program_every_parameter_gradient_on_the_cpu_stand_in():
             checked.add(name)
         assert rel(got, want) < 1e-3, name
     assert checked == set(sd.keys())                                   # no parameter of the reference state_dict left out
+
+
+def test_next_backward_algorithms_match_autograd():
+    """The kernel-shaped restatements of attention / LayerNorm / GEGLU backward (the frozen UNet's dgrad chain, next to be built)
+    against torch autograd of the functions the reference calls."""
+    gen = torch.Generator().manual_seed(31)
+    Tq, S, d = 37, 77, 40                                     # ragged: 37 queries against the 77-token CLIP context, head dim 40
+    q, k, v, do = (torch.randn(n, d, generator=gen, dtype=torch.float64) for n in (Tq, S, S, Tq))
+    q.requires_grad_(True); k.requires_grad_(True); v.requires_grad_(True)
+    F.scaled_dot_product_attention(q[None, None], k[None, None], v[None, None])[0, 0].backward(do)
+    dq, dk, dv, L, D = T.attention_backward_two_pass(q.detach().numpy(), k.detach().numpy(), v.detach().numpy(), do.numpy())
+    for got, want in ((dq, q.grad), (dk, k.grad), (dv, v.grad)):
+        np.testing.assert_allclose(got, want.numpy(), rtol=1e-9, atol=1e-11)
+
+    x = torch.randn(5, 9, 320, generator=gen, dtype=torch.float64, requires_grad=True)
+    gamma, beta = torch.randn(320, generator=gen, dtype=torch.float64), torch.randn(320, generator=gen, dtype=torch.float64)
+    dy = torch.randn(5, 9, 320, generator=gen, dtype=torch.float64)
+    F.layer_norm(x, (320,), gamma, beta, 1e-5).backward(dy)
+    np.testing.assert_allclose(T.layernorm_backward_dx(x.detach().numpy(), gamma.numpy(), dy.numpy()), x.grad.numpy(), rtol=1e-9, atol=1e-11)
+
+    proj = torch.randn(4, 6, 128, generator=gen, dtype=torch.float64, requires_grad=True)
+    dout = torch.randn(4, 6, 64, generator=gen, dtype=torch.float64)
+    h, gate = proj.chunk(2, -1)
+    (h * F.gelu(gate)).backward(dout)
+    np.testing.assert_allclose(T.geglu_backward(proj.detach().numpy(), dout.numpy()), proj.grad.numpy(), rtol=1e-9, atol=1e-11)
