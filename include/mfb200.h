@@ -277,6 +277,20 @@ int mfb_rowsum_per_image(const void* dy, int dtype, int B, int HW, int C, float*
  * piece of the timestep MLP's backward (S/models/embeddings.py:226-237, S/models/resnet.py:369-376). */
 int mfb_silu_bwd(const float* x, const void* dy, int dy_dtype, float* y, float* dx, long long n, void* stream);
 
+/* fp32 parity-mode backward of the three ops the frozen UNet's data-gradient chain adds (BASELINE config 4): CUDA-core correctness
+ * instruments written to the algorithms pinned in oracle/train_oracle.py.  NOT YET RUN ON A GPU (round 1); the tensor-core versions follow.
+ * mfb_attention_bwd_f32: backward of F.scaled_dot_product_attention (S/models/attention_processor.py:1266-1268), same tensor layout as
+ *   mfb_attention_f32 (head h at columns [h*d, (h+1)*d)); two deterministic passes (per query: L, D = dO.O, dq; per key: dk, dv);
+ *   stats_ws: 2 * B * heads * Tq floats.  head_dim <= 160.
+ * mfb_layernorm_bwd_f32: data gradient of F.layer_norm over the last dim (S/models/attention.py:313,360,386).
+ * mfb_geglu_f32: on an un-fused GEGLU projection [rows, 2C] = [h | gate] (S/models/activations.py:100-103): out = h * gelu_erf(gate)
+ *   (if out != NULL) and d_proj from d_out (if d_proj != NULL). */
+int mfb_attention_bwd_f32(const float* q, int ldq, const float* k, int ldk, const float* v, int ldv, const float* d_out, int ldo, float* dq,
+                          int lddq, float* dk, int lddk, float* dv, int lddv, float* stats_ws, int B, int heads, int head_dim, int Tq, int Tk,
+                          void* stream);
+int mfb_layernorm_bwd_f32(const float* x, const float* dy, int rows, int C, float eps, const float* gamma, float* dx, void* stream);
+int mfb_geglu_f32(const float* proj, long long rows, int C, float* out, const float* d_out, float* d_proj, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -613,6 +613,239 @@ __global__ void silu_bwd_kernel(const float* __restrict__ x, const T* __restrict
     }
 }
 
+// ---------------------------------------------------------------------------------------------- fp32 parity-mode backward of the
+// three ops the frozen UNet's dgrad-only chain adds: CUDA-core correctness instruments like csrc/fp32mode.cu,
+// written to the algorithms pinned in oracle/train_oracle.py (attention_backward_two_pass, layernorm_backward_dx, geglu_backward).
+// NOT YET RUN ON A GPU (added after the round's GPU budget was spent): tests/test_gpu_zz_train_net.py guards them with xfail.
+constexpr int AB_MAXD = 160;   // SD1.5 head dims: 40 / 80 / 160
+
+// pass A, one warp per (batch, head, query): L = logsumexp of the scaled scores, D = dO . O, dq.  lane = key for the score /
+// dO.v dot products, lane = dims {lane, lane+32, ...} for the dq accumulation.  Three sweeps over the keys (nothing T x S stored).
+__global__ void __launch_bounds__(128) attn_bwd_q_kernel(const float* __restrict__ q, int ldq, const float* __restrict__ k, int ldk,
+                                                         const float* __restrict__ v, int ldv, const float* __restrict__ dO, int ldo,
+                                                         float* __restrict__ dq, int lddq, float* __restrict__ stats, int heads, int d,
+                                                         int Tq, int Tk, float scale) {
+    pdl_trigger();
+    pdl_wait();
+    __shared__ float qs[4][AB_MAXD], dos[4][AB_MAXD];
+    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int row = blockIdx.x * 4 + wid, h = blockIdx.y, b = blockIdx.z;
+    if (row >= Tq) return;
+    const float* qr = q + (static_cast<size_t>(b) * Tq + row) * ldq + h * d;
+    const float* dor = dO + (static_cast<size_t>(b) * Tq + row) * ldo + h * d;
+    for (int c = lane; c < d; c += 32) {
+        qs[wid][c] = qr[c] * scale;
+        dos[wid][c] = dor[c];
+    }
+    __syncwarp();
+    const float* kb = k + static_cast<size_t>(b) * Tk * ldk + h * d;
+    const float* vb = v + static_cast<size_t>(b) * Tk * ldv + h * d;
+    // sweep 1: running max / sum -> L
+    float mrun = -INFINITY, l = 0.f;
+    for (int j0 = 0; j0 < Tk; j0 += 32) {
+        const int j = j0 + lane;
+        float sc = -INFINITY;
+        if (j < Tk) {
+            const float* kr = kb + static_cast<size_t>(j) * ldk;
+            float acc = 0.f;
+            for (int c = 0; c < d; ++c) acc = fmaf(qs[wid][c], kr[c], acc);
+            sc = acc;
+        }
+        float mx = sc;
+        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        const float mnew = fmaxf(mrun, mx);
+        float ps = j < Tk ? expf(sc - mnew) : 0.f;
+        for (int o = 16; o > 0; o >>= 1) ps += __shfl_xor_sync(0xffffffffu, ps, o);
+        l = l * expf(mrun - mnew) + ps;
+        mrun = mnew;
+    }
+    const float L = mrun + logf(l);
+    // sweep 2: D = sum_j p_j (dO . v_j)
+    float dacc = 0.f;
+    for (int j0 = 0; j0 < Tk; j0 += 32) {
+        const int j = j0 + lane;
+        if (j < Tk) {
+            const float* kr = kb + static_cast<size_t>(j) * ldk;
+            const float* vr = vb + static_cast<size_t>(j) * ldv;
+            float sc = 0.f, t = 0.f;
+            for (int c = 0; c < d; ++c) {
+                sc = fmaf(qs[wid][c], kr[c], sc);
+                t = fmaf(dos[wid][c], vr[c], t);
+            }
+            dacc += expf(sc - L) * t;
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) dacc += __shfl_xor_sync(0xffffffffu, dacc, o);
+    const float D = dacc;
+    // sweep 3: dq = scale * sum_j p_j (dO . v_j - D) k_j
+    float acc_dq[AB_MAXD / 32];
+#pragma unroll
+    for (int i = 0; i < AB_MAXD / 32; ++i) acc_dq[i] = 0.f;
+    for (int j0 = 0; j0 < Tk; j0 += 32) {
+        const int j = j0 + lane;
+        float ds = 0.f;
+        if (j < Tk) {
+            const float* kr = kb + static_cast<size_t>(j) * ldk;
+            const float* vr = vb + static_cast<size_t>(j) * ldv;
+            float sc = 0.f, t = 0.f;
+            for (int c = 0; c < d; ++c) {
+                sc = fmaf(qs[wid][c], kr[c], sc);
+                t = fmaf(dos[wid][c], vr[c], t);
+            }
+            ds = expf(sc - L) * (t - D);
+        }
+        const int nk = min(32, Tk - j0);
+        for (int jj = 0; jj < nk; ++jj) {
+            const float dsb = __shfl_sync(0xffffffffu, ds, jj);
+            const float* kr = kb + static_cast<size_t>(j0 + jj) * ldk;
+#pragma unroll
+            for (int i = 0; i < AB_MAXD / 32; ++i) {
+                const int c = lane + 32 * i;
+                if (c < d) acc_dq[i] = fmaf(dsb, kr[c], acc_dq[i]);
+            }
+        }
+    }
+    float* dqr = dq + (static_cast<size_t>(b) * Tq + row) * lddq + h * d;
+#pragma unroll
+    for (int i = 0; i < AB_MAXD / 32; ++i) {
+        const int c = lane + 32 * i;
+        if (c < d) dqr[c] = acc_dq[i] * scale;
+    }
+    if (lane == 0) {
+        float* st = stats + ((static_cast<size_t>(b) * heads + h) * Tq + row) * 2;
+        st[0] = L;
+        st[1] = D;
+    }
+}
+
+// pass B, one warp per (batch, head, key): dv_j = sum_i p_ij dO_i, dk_j = scale sum_i p_ij (dO_i . v_j - D_i) q_i, queries in order.
+__global__ void __launch_bounds__(128) attn_bwd_kv_kernel(const float* __restrict__ q, int ldq, const float* __restrict__ k, int ldk,
+                                                          const float* __restrict__ v, int ldv, const float* __restrict__ dO, int ldo,
+                                                          float* __restrict__ dk, int lddk, float* __restrict__ dv, int lddv,
+                                                          const float* __restrict__ stats, int heads, int d, int Tq, int Tk, float scale) {
+    pdl_trigger();
+    pdl_wait();
+    __shared__ float ks[4][AB_MAXD], vs[4][AB_MAXD];
+    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int j = blockIdx.x * 4 + wid, h = blockIdx.y, b = blockIdx.z;
+    if (j >= Tk) return;
+    const float* kr = k + (static_cast<size_t>(b) * Tk + j) * ldk + h * d;
+    const float* vr = v + (static_cast<size_t>(b) * Tk + j) * ldv + h * d;
+    for (int c = lane; c < d; c += 32) {
+        ks[wid][c] = kr[c] * scale;
+        vs[wid][c] = vr[c];
+    }
+    __syncwarp();
+    const float* qb = q + static_cast<size_t>(b) * Tq * ldq + h * d;
+    const float* dob = dO + static_cast<size_t>(b) * Tq * ldo + h * d;
+    const float* st = stats + (static_cast<size_t>(b) * heads + h) * Tq * 2;
+    float acc_dk[AB_MAXD / 32], acc_dv[AB_MAXD / 32];
+#pragma unroll
+    for (int i = 0; i < AB_MAXD / 32; ++i) acc_dk[i] = acc_dv[i] = 0.f;
+    for (int i0 = 0; i0 < Tq; i0 += 32) {
+        const int i = i0 + lane;
+        float p = 0.f, ds = 0.f;
+        if (i < Tq) {
+            const float* qr = qb + static_cast<size_t>(i) * ldq;
+            const float* dor = dob + static_cast<size_t>(i) * ldo;
+            float sc = 0.f, t = 0.f;
+            for (int c = 0; c < d; ++c) {
+                sc = fmaf(qr[c], ks[wid][c], sc);
+                t = fmaf(dor[c], vs[wid][c], t);
+            }
+            p = expf(sc - st[2 * i]);
+            ds = p * (t - st[2 * i + 1]);
+        }
+        const int nq = min(32, Tq - i0);
+        for (int ii = 0; ii < nq; ++ii) {
+            const float pb = __shfl_sync(0xffffffffu, p, ii), dsb = __shfl_sync(0xffffffffu, ds, ii);
+            const float* qr = qb + static_cast<size_t>(i0 + ii) * ldq;
+            const float* dor = dob + static_cast<size_t>(i0 + ii) * ldo;
+#pragma unroll
+            for (int m = 0; m < AB_MAXD / 32; ++m) {
+                const int c = lane + 32 * m;
+                if (c < d) {
+                    acc_dv[m] = fmaf(pb, dor[c], acc_dv[m]);
+                    acc_dk[m] = fmaf(dsb, qr[c], acc_dk[m]);
+                }
+            }
+        }
+    }
+    float* dkr = dk + (static_cast<size_t>(b) * Tk + j) * lddk + h * d;
+    float* dvr = dv + (static_cast<size_t>(b) * Tk + j) * lddv + h * d;
+#pragma unroll
+    for (int m = 0; m < AB_MAXD / 32; ++m) {
+        const int c = lane + 32 * m;
+        if (c < d) {
+            dkr[c] = acc_dk[m] * scale;
+            dvr[c] = acc_dv[m];
+        }
+    }
+}
+
+// LayerNorm data gradient, one warp per row: dx = rstd (g - mean(g) - xhat mean(g xhat)), g = dy * gamma
+__global__ void __launch_bounds__(128) ln_bwd32_kernel(const float* __restrict__ x, const float* __restrict__ dy, int rows, int C, float eps,
+                                                       const float* __restrict__ gamma, float* __restrict__ dx) {
+    pdl_trigger();
+    pdl_wait();
+    const int lane = threadIdx.x & 31;
+    const int row = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const float* xr = x + static_cast<size_t>(row) * C;
+    const float* dyr = dy + static_cast<size_t>(row) * C;
+    double s = 0.0;
+    for (int c = lane; c < C; c += 32) s += xr[c];
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const double mean = s / C;
+    double vs = 0.0;
+    for (int c = lane; c < C; c += 32) {
+        const double dlt = xr[c] - mean;
+        vs += dlt * dlt;
+    }
+    for (int o = 16; o > 0; o >>= 1) vs += __shfl_xor_sync(0xffffffffu, vs, o);
+    const float rstd = static_cast<float>(1.0 / sqrt(vs / C + static_cast<double>(eps)));
+    const float meanf = static_cast<float>(mean);
+    double a = 0.0, bsum = 0.0;
+    for (int c = lane; c < C; c += 32) {
+        const float g = dyr[c] * gamma[c];
+        a += g;
+        bsum += static_cast<double>(g) * ((xr[c] - meanf) * rstd);
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, o);
+        bsum += __shfl_xor_sync(0xffffffffu, bsum, o);
+    }
+    const float mg = static_cast<float>(a / C), mgx = static_cast<float>(bsum / C);
+    float* dxr = dx + static_cast<size_t>(row) * C;
+    for (int c = lane; c < C; c += 32) {
+        const float xh = (xr[c] - meanf) * rstd;
+        dxr[c] = rstd * (dyr[c] * gamma[c] - mg - xh * mgx);
+    }
+}
+
+// GEGLU on an un-fused projection [rows, 2C] = [h | gate]: out = h * gelu_erf(gate) (forward, optional) and
+// d proj = [d out * gelu(gate) | d out * h * (Phi(gate) + gate phi(gate))] (backward, optional)
+__global__ void geglu32_kernel(const float* __restrict__ proj, long long rows, int C, float* __restrict__ out,
+                               const float* __restrict__ d_out, float* __restrict__ d_proj) {
+    pdl_trigger();
+    pdl_wait();
+    const long long n = rows * C;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const long long r = i / C;
+        const int c = static_cast<int>(i - r * C);
+        const float hv = proj[r * 2 * C + c], g = proj[r * 2 * C + C + c];
+        const float Phi = 0.5f * (1.0f + erff(g * 0.70710678118654752f));
+        if (out) out[i] = hv * g * Phi;
+        if (d_proj) {
+            const float phi = 0.39894228040143268f * expf(-0.5f * g * g);
+            const float dov = d_out[i];
+            d_proj[r * 2 * C + c] = dov * g * Phi;
+            d_proj[r * 2 * C + C + c] = dov * hv * (Phi + g * phi);
+        }
+    }
+}
+
 }  // namespace mfb
 
 using namespace mfb;
@@ -815,5 +1048,34 @@ extern "C" int mfb_silu_bwd(const float* x, const void* dy, int dy_dtype, float*
         MFB_CUDA_OK(launch_k(silu_bwd_kernel<float>, dim3(grid), dim3(256), 0, st, 1, x, static_cast<const float*>(dy), y, dx, n));
     else
         MFB_CUDA_OK(launch_k(silu_bwd_kernel<__nv_bfloat16>, dim3(grid), dim3(256), 0, st, 1, x, static_cast<const __nv_bfloat16*>(dy), y, dx, n));
+    return MFB_OK;
+}
+
+extern "C" int mfb_attention_bwd_f32(const float* q, int ldq, const float* k, int ldk, const float* v, int ldv, const float* d_out, int ldo,
+                                     float* dq, int lddq, float* dk, int lddk, float* dv, int lddv, float* stats_ws, int B, int heads,
+                                     int head_dim, int Tq, int Tk, void* stream) {
+    MFB_REQUIRE(q && k && v && d_out && dq && dk && dv && stats_ws, "null pointer");
+    MFB_REQUIRE(head_dim > 0 && head_dim <= AB_MAXD && Tq > 0 && Tk > 0 && B > 0 && B <= 65535 && heads > 0 && heads <= 65535,
+                "unsupported attention shape");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const float scale = 1.0f / sqrtf(static_cast<float>(head_dim));
+    MFB_CUDA_OK(launch_k(attn_bwd_q_kernel, dim3((Tq + 3) / 4, heads, B), dim3(128), 0, st, 1, q, ldq, k, ldk, v, ldv, d_out, ldo, dq, lddq,
+                         stats_ws, heads, head_dim, Tq, Tk, scale));
+    MFB_CUDA_OK(launch_k(attn_bwd_kv_kernel, dim3((Tk + 3) / 4, heads, B), dim3(128), 0, st, 1, q, ldq, k, ldk, v, ldv, d_out, ldo, dk, lddk,
+                         dv, lddv, static_cast<const float*>(stats_ws), heads, head_dim, Tq, Tk, scale));
+    return MFB_OK;
+}
+
+extern "C" int mfb_layernorm_bwd_f32(const float* x, const float* dy, int rows, int C, float eps, const float* gamma, float* dx, void* stream) {
+    MFB_REQUIRE(x && dy && gamma && dx && rows > 0 && C > 0, "bad arguments");
+    MFB_CUDA_OK(launch_k(ln_bwd32_kernel, dim3((rows + 3) / 4), dim3(128), 0, static_cast<cudaStream_t>(stream), 1, x, dy, rows, C, eps, gamma, dx));
+    return MFB_OK;
+}
+
+extern "C" int mfb_geglu_f32(const float* proj, long long rows, int C, float* out, const float* d_out, float* d_proj, void* stream) {
+    MFB_REQUIRE(proj && (out || d_proj) && rows > 0 && C > 0, "bad arguments");
+    MFB_REQUIRE(d_proj == nullptr || d_out != nullptr, "d_proj needs d_out");
+    MFB_CUDA_OK(launch_k(geglu32_kernel, dim3(chunks_for(rows * C, 256, 148 * 8)), dim3(256), 0, static_cast<cudaStream_t>(stream), 1, proj, rows,
+                         C, out, d_out, d_proj));
     return MFB_OK;
 }

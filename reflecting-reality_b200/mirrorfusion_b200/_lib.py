@@ -77,6 +77,10 @@ _SIGS = {
     "mfb_groupnorm_bwd": (i32, [vp, i32, vp, i32, vp, i32, i32, i32, i32, f32, vp, vp, i32, vp, vp, vp, vp, vp, vp, i32, vp]),
     "mfb_rowsum_per_image": (i32, [vp, i32, i32, i32, i32, vp, vp]),
     "mfb_silu_bwd": (i32, [vp, vp, i32, vp, vp, i64, vp]),
+    # fp32 parity-mode backward of attention / LayerNorm / GEGLU (not yet run on a GPU)
+    "mfb_attention_bwd_f32": (i32, [vp, i32, vp, i32, vp, i32, vp, i32, vp, i32, vp, i32, vp, i32, vp, i32, i32, i32, i32, i32, vp]),
+    "mfb_layernorm_bwd_f32": (i32, [vp, vp, i32, i32, f32, vp, vp, vp]),
+    "mfb_geglu_f32": (i32, [vp, i64, i32, vp, vp, vp, vp]),
 }
 EXPORTS = tuple(_SIGS)
 

@@ -444,3 +444,26 @@ def silu_bwd(x, dy=None, y=None, dx=None):
     """y = silu(x) and / or dx = dy * silu'(x); x, y, dx fp32, dy fp32 or bf16."""
     _req(x, f32, "x")
     check(lib().mfb_silu_bwd(_ptr(x), _ptr(dy), 1 if dy is None else int(_is32(dy)), _ptr(y), _ptr(dx), x.numel(), _stream()))
+
+
+# fp32 parity-mode backward of attention / LayerNorm / GEGLU (the frozen UNet's data-gradient chain; not yet run on a GPU)
+def attention_bwd_f32(q, k, v, d_out, dq, dk, dv, stats_ws, *, B, heads, head_dim, Tq, Tk):
+    for name, t in (("q", q), ("k", k), ("v", v), ("d_out", d_out), ("dq", dq), ("dk", dk), ("dv", dv), ("stats_ws", stats_ws)):
+        _req(t, f32, name)
+    if stats_ws.numel() < 2 * B * heads * Tq:
+        raise ValueError("attention_bwd_f32: stats workspace smaller than 2*B*heads*Tq floats")
+    check(lib().mfb_attention_bwd_f32(_ptr(q), q.shape[-1], _ptr(k), k.shape[-1], _ptr(v), v.shape[-1], _ptr(d_out), d_out.shape[-1],
+                                      _ptr(dq), dq.shape[-1], _ptr(dk), dk.shape[-1], _ptr(dv), dv.shape[-1], _ptr(stats_ws), B, heads,
+                                      head_dim, Tq, Tk, _stream()))
+
+
+def layernorm_bwd_f32(x, dy, gamma, dx, eps=1e-5):
+    for name, t in (("x", x), ("dy", dy), ("gamma", gamma), ("dx", dx)):
+        _req(t, f32, name)
+    check(lib().mfb_layernorm_bwd_f32(_ptr(x), _ptr(dy), x.numel() // x.shape[-1], x.shape[-1], eps, _ptr(gamma), _ptr(dx), _stream()))
+
+
+def geglu_f32(proj, out=None, d_out=None, d_proj=None):
+    _req(proj, f32, "proj")
+    Cc = proj.shape[-1] // 2
+    check(lib().mfb_geglu_f32(_ptr(proj), proj.numel() // proj.shape[-1], Cc, _ptr(out), _ptr(d_out), _ptr(d_proj), _stream()))

@@ -160,3 +160,53 @@ def test_whole_brushnet_every_parameter_gradient_fp32_vs_autograd():
             want, got = sd[name].grad, flat.g(name)
             got = unpack_conv_grad(got, 3) if want.dim() == 4 and want.shape[-1] == 3 else got.reshape(want.shape)
         assert rel(got, want) < 1e-3, name
+
+
+_PENDING = ("kernel written after the round's GPU budget was spent: it compiles for sm_100a and follows the algorithm pinned on the CPU in "
+            "tests/test_oracle_train.py::test_next_backward_algorithms_match_autograd, but has never run on a GPU")
+
+
+@pytest.mark.timeout(120)
+@pytest.mark.xfail(strict=False, reason=_PENDING)
+def test_pending_layernorm_and_geglu_backward_f32():
+    import numpy as np
+    from mirrorfusion_b200 import ops
+    from oracle import train_oracle as T
+    ops.lib()
+    g = torch.Generator().manual_seed(1)
+    x, dy = torch.randn(37, 320, generator=g), torch.randn(37, 320, generator=g)
+    gamma = 1 + 0.2 * torch.randn(320, generator=g)
+    dx = torch.full_like(x, float("nan")).cuda()
+    ops.layernorm_bwd_f32(x.cuda(), dy.cuda(), gamma.cuda(), dx)
+    ref = T.layernorm_backward_dx(x.numpy(), gamma.numpy(), dy.numpy())
+    assert np.linalg.norm(dx.cpu().numpy() - ref) / np.linalg.norm(ref) < 1e-5
+    proj, dout = torch.randn(50, 256, generator=g), torch.randn(50, 128, generator=g)
+    out, dproj = torch.full((50, 128), float("nan")).cuda(), torch.full((50, 256), float("nan")).cuda()
+    ops.geglu_f32(proj.cuda(), out=out, d_out=dout.cuda(), d_proj=dproj)
+    h, gate = proj.chunk(2, -1)
+    assert torch.allclose(out.cpu(), h * F.gelu(gate), rtol=1e-5, atol=1e-6)
+    ref = T.geglu_backward(proj.numpy(), dout.numpy())
+    assert np.linalg.norm(dproj.cpu().numpy() - ref) / np.linalg.norm(ref) < 1e-5
+
+
+@pytest.mark.timeout(120)
+@pytest.mark.xfail(strict=False, reason=_PENDING)
+def test_pending_attention_backward_f32():
+    import numpy as np
+    from mirrorfusion_b200 import ops
+    from oracle import train_oracle as T
+    ops.lib()
+    g = torch.Generator().manual_seed(2)
+    B, heads, d, Tq, Tk = 2, 2, 40, 37, 77
+    q, do = torch.randn(B, Tq, heads * d, generator=g), torch.randn(B, Tq, heads * d, generator=g)
+    k, v = torch.randn(B, Tk, heads * d, generator=g), torch.randn(B, Tk, heads * d, generator=g)
+    dq, dk, dv = (torch.full_like(t, float("nan")).cuda() for t in (q, k, v))
+    ws = torch.zeros(2 * B * heads * Tq).cuda()
+    ops.attention_bwd_f32(q.cuda(), k.cuda(), v.cuda(), do.cuda(), dq, dk, dv, ws, B=B, heads=heads, head_dim=d, Tq=Tq, Tk=Tk)
+    for b in range(B):
+        for h in range(heads):
+            sl = slice(h * d, (h + 1) * d)
+            rq, rk, rv, _, _ = T.attention_backward_two_pass(q[b, :, sl].numpy(), k[b, :, sl].numpy(), v[b, :, sl].numpy(), do[b, :, sl].numpy())
+            for got, want in ((dq, rq), (dk, rk), (dv, rv)):
+                got = got[b, :, sl].cpu().numpy()
+                assert np.linalg.norm(got - want) / np.linalg.norm(want) < 1e-5
