@@ -64,10 +64,13 @@ def _dgrad_from_packed(wp: torch.Tensor, ksize: int, dtype) -> torch.Tensor:
 
 
 class ResnetBlockTrainer:
+    """`frozen=True`: data gradients only (d x, d rowbias) — a block of the frozen UNet, whose backward only has to carry the
+    gradient to the BrushNet taps; no weight / affine gradients are computed or written."""
+
     def __init__(self, flat: FlatParams, prefix: str, *, B: int, H: int, W: int, Cin: int, Cout: int, groups: int = 32,
-                 eps: float = 1e-5, precision: str = "bf16", K=None):
+                 eps: float = 1e-5, precision: str = "bf16", K=None, frozen: bool = False):
         K = _ops if K is None else K
-        self.K, self.flat, self.p = K, flat, prefix
+        self.K, self.flat, self.p, self.frozen = K, flat, prefix, frozen
         self.B, self.H, self.W, self.HW, self.Cin, self.Cout, self.groups, self.eps = B, H, W, H * W, Cin, Cout, groups, eps
         self.dt = torch.float32 if precision == "fp32" else torch.bfloat16
         self.shortcut = Cin != Cout
@@ -137,26 +140,31 @@ class ResnetBlockTrainer:
         self.d_out.copy_(d_out.view_as(self.d_out))
         gnb = dict(B=B, HW=HW, groups=self.groups, eps=self.eps, silu=True, accumulate=True)
         # out = conv2(n2) + bias2 + shortcut(x)
-        K.conv_wgrad(self.n2, self.d_out, f.g(n("conv2.weight")), f.g(n("conv2.bias")), B=B, H=H, W=W, ksize=3, accumulate=True)
+        tr = not self.frozen
+        G = (lambda name: f.g(n(name))) if tr else (lambda name: None)
+        if tr:
+            K.conv_wgrad(self.n2, self.d_out, f.g(n("conv2.weight")), f.g(n("conv2.bias")), B=B, H=H, W=W, ksize=3, accumulate=True)
         self.plan_d2.run()                                                          # d n2
         # n2 = silu(groupnorm(c1))
         K.groupnorm_bwd(self.c1, None, self.dn2, f.p(n("norm2.weight")), f.p(n("norm2.bias")), self.dc1, None, self.gnb_ws,
-                        dgamma=f.g(n("norm2.weight")), dbeta=f.g(n("norm2.bias")), **gnb)
+                        dgamma=G("norm2.weight"), dbeta=G("norm2.bias"), **gnb)
         # c1 = conv1(n1) + bias1 + rowbias[:, :, None, None]
-        K.conv_wgrad(self.n1, self.dc1, f.g(n("conv1.weight")), f.g(n("conv1.bias")), B=B, H=H, W=W, ksize=3, accumulate=True)
+        if tr:
+            K.conv_wgrad(self.n1, self.dc1, f.g(n("conv1.weight")), f.g(n("conv1.bias")), B=B, H=H, W=W, ksize=3, accumulate=True)
         K.rowsum_per_image(self.dc1, self.d_rowbias, B=B, HW=HW)
         self.plan_d1.run()                                                          # d n1
         # shortcut path: identity -> d out itself; 1x1 conv -> its data gradient (+ its weight gradient)
         if self.shortcut:
-            K.conv_wgrad(self.x, self.d_out, f.g(n("conv_shortcut.weight")), f.g(n("conv_shortcut.bias")), B=B, H=H, W=W, ksize=1,
-                         accumulate=True)
+            if tr:
+                K.conv_wgrad(self.x, self.d_out, f.g(n("conv_shortcut.weight")), f.g(n("conv_shortcut.bias")), B=B, H=H, W=W, ksize=1,
+                             accumulate=True)
             self.plan_dsc.run()
             dres = self.dsc
         else:
             dres = self.d_out
         # n1 = silu(groupnorm(x)); d x = that + the shortcut path's gradient, in the same pass
         K.groupnorm_bwd(self.x, None, self.dn1, f.p(n("norm1.weight")), f.p(n("norm1.bias")), self.dx, None, self.gnb_ws,
-                        dgamma=f.g(n("norm1.weight")), dbeta=f.g(n("norm1.bias")), dres=dres, **gnb)
+                        dgamma=G("norm1.weight"), dbeta=G("norm1.bias"), dres=dres, **gnb)
         return self.dx, self.d_rowbias
 
 
@@ -167,11 +175,12 @@ class DownsampleTrainer:
     (ops.pack_conv_s2_dgrad_weight) — the same tcgen05 kernel again.  Flat entries: `<prefix>.conv.weight` packed [C, 9*C],
     `<prefix>.conv.bias` [C]."""
 
-    def __init__(self, flat: FlatParams, prefix: str, *, B: int, H: int, W: int, C: int, precision: str = "bf16", K=None):
+    def __init__(self, flat: FlatParams, prefix: str, *, B: int, H: int, W: int, C: int, precision: str = "bf16", K=None,
+                 frozen: bool = False):
         K = _ops if K is None else K
         if H % 2 or W % 2:
             raise ValueError("Downsample2D backward needs even H, W")
-        self.K, self.flat, self.p, self.B, self.H, self.W, self.C = K, flat, prefix, B, H, W, C
+        self.K, self.flat, self.p, self.B, self.H, self.W, self.C, self.frozen = K, flat, prefix, B, H, W, C, frozen
         self.dt = torch.float32 if precision == "fp32" else torch.bfloat16
         dev = flat.param.device
         self._wsrc = flat.p if self.dt == torch.float32 else flat.w
@@ -206,8 +215,9 @@ class DownsampleTrainer:
     def backward(self, d_out: torch.Tensor) -> torch.Tensor:
         f = self.flat
         self.d_out.copy_(d_out.view_as(self.d_out))
-        self.K.conv_wgrad(self.x, self.d_out, f.g(f"{self.p}.conv.weight"), f.g(f"{self.p}.conv.bias"), B=self.B, H=self.H, W=self.W,
-                          ksize=3, stride=2, accumulate=True)
+        if not self.frozen:     # frozen (UNet): data gradient only
+            self.K.conv_wgrad(self.x, self.d_out, f.g(f"{self.p}.conv.weight"), f.g(f"{self.p}.conv.bias"), B=self.B, H=self.H, W=self.W,
+                              ksize=3, stride=2, accumulate=True)
         self.plan_d.run()
         return self.dx
 

@@ -471,3 +471,24 @@ def test_next_backward_algorithms_match_autograd():
     h, gate = proj.chunk(2, -1)
     (h * F.gelu(gate)).backward(dout)
     np.testing.assert_allclose(T.geglu_backward(proj.detach().numpy(), dout.numpy()), proj.grad.numpy(), rtol=1e-9, atol=1e-11)
+
+
+@pytest.mark.parametrize("tag", ["id", "sc"])
+def test_frozen_resnet_block_carries_only_data_gradients(tag):
+    """frozen=True (a block of the frozen UNet): same d x / d rowbias, no parameter gradient touched."""
+    import torch_kernels as TK
+    from mirrorfusion_b200.backward import ResnetBlockTrainer, pack_resnet_state_dict, resnet_param_shapes
+    from mirrorfusion_b200.train import FlatParams
+    cin, cout, sd, x, emb, d_out = _block_case(tag)
+    ref = T.resnet_block_grads(sd, "r", x, emb, d_out)
+    B, _, H, W = x.shape
+    flat = FlatParams(resnet_param_shapes("r", cin, cout), "cpu", with_bf16=False)
+    for k, v in pack_resnet_state_dict("r", sd).items():
+        flat.p(k).copy_(v)
+    blk = ResnetBlockTrainer(flat, "r", B=B, H=H, W=W, Cin=cin, Cout=cout, precision="fp32", K=TK, frozen=True)
+    nhwc = lambda t: t.permute(0, 2, 3, 1).reshape(B, H * W, -1).contiguous()
+    blk.forward(nhwc(x), ref["rowbias"].float())
+    dx, drb = blk.backward(nhwc(d_out))
+    np.testing.assert_allclose(dx.numpy(), nhwc(ref["dx"]).numpy(), rtol=1e-4, atol=1e-4)
+    np.testing.assert_allclose(drb.numpy(), ref["d_rowbias"].numpy(), rtol=1e-4, atol=1e-4)
+    assert float(flat.grad.abs().max()) == 0.0
