@@ -66,7 +66,9 @@ def main():
     torch.cuda.synchronize()
     res["forward_ms"] = ev[0].elapsed_time(ev[1]) / args.iters
     res["backward_ms"] = ev[1].elapsed_time(ev[2]) / args.iters
-    print(f"forward {res['forward_ms']:.2f} ms, backward {res['backward_ms']:.2f} ms (eager launches, B={B}, {H}x{W})")
+    res["max_memory_gb"] = torch.cuda.max_memory_allocated() / 2 ** 30
+    print(f"forward {res['forward_ms']:.2f} ms, backward {res['backward_ms']:.2f} ms (eager launches, B={B}, {H}x{W}); "
+          f"peak device memory {res['max_memory_gb']:.1f} GiB")
 
     if not args.no_check:
         from oracle import mf_oracle as O
