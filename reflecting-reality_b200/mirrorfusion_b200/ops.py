@@ -392,6 +392,9 @@ def adamw_step(param, grad, exp_avg, exp_avg_sq, hyper, param_bf16=None, grad_sq
                                _ptr(hyper), _ptr(grad_sqnorm), float(max_grad_norm), _stream()))
 
 
+_WGRAD_WS: dict = {}
+
+
 def conv_wgrad_ws_floats(B, H, W, Cin, Cout, ksize, stride=1) -> int:
     """Workspace (floats) of the tensor-core weight gradient for this layer geometry (H, W: the conv INPUT size)."""
     return int(_lib.load().mfb_conv_wgrad_tc_ws_floats(B, H, W, Cin, Cout, ksize, stride))
@@ -400,8 +403,8 @@ def conv_wgrad_ws_floats(B, H, W, Cin, Cout, ksize, stride=1) -> int:
 def conv_wgrad(x, dy, dw, dbias=None, *, B, H, W, ksize, stride=1, accumulate=False, ws=None, cuda_cores=False):
     """dw [Cout, k*k*Cin] fp32 (packed K order) and dbias [Cout] of a conv (stride 1, or 2 for the 3x3 of Downsample2D) / linear;
     x [B,H,W,Cin], dy [B,H/stride,W/stride,Cout] NHWC bf16 or fp32.
-    bf16 operands with Cin, Cout multiples of 8 run on the tensor cores (ws: conv_wgrad_ws_floats(...) floats, allocated per call
-    if not given); fp32 operands (parity mode), ragged channel counts or cuda_cores=True take the CUDA-core kernel."""
+    bf16 operands with Cin, Cout multiples of 8 run on the tensor cores (ws: conv_wgrad_ws_floats(...) floats; if not given, a
+    grow-only per-device workspace is used); fp32 operands (parity mode), ragged channel counts or cuda_cores=True take the CUDA-core kernel."""
     is32 = _is32(x)
     _req(dy, x.dtype, "dy"); _req(dw, f32, "dw")
     Cin, Cout = x.shape[-1], dy.shape[-1]
@@ -409,8 +412,10 @@ def conv_wgrad(x, dy, dw, dbias=None, *, B, H, W, ksize, stride=1, accumulate=Fa
         raise ValueError(f"dw shape {tuple(dw.shape)} != {(Cout, ksize * ksize * Cin)}")
     if not is32 and not cuda_cores and Cin % 8 == 0 and Cout % 8 == 0:
         need = conv_wgrad_ws_floats(B, H, W, Cin, Cout, ksize, stride)
-        if ws is None:
-            ws = torch.empty(need, device=x.device, dtype=f32)
+        if ws is None:      # one grow-only workspace per device, shared by all layers (launches on one stream serialise on it)
+            ws = _WGRAD_WS.get(x.device)
+            if ws is None or ws.numel() < need:
+                ws = _WGRAD_WS[x.device] = torch.empty(need, device=x.device, dtype=f32)
         _req(ws, f32, "ws")
         check(lib().mfb_conv_wgrad_tc(_ptr(x), _ptr(dy), B, H, W, Cin, Cout, ksize, stride, _ptr(dw), _ptr(dbias), int(accumulate),
                                       _ptr(ws), ws.numel(), _stream()))
