@@ -33,6 +33,12 @@ import torch  # noqa: E402
 
 STEPS_PER_IMAGE = 50
 METRIC = "images_per_s_512x512_50_unipc_steps_cfg7.5"
+# BASELINE.json `configs` presets (index = position in that list): images per GPU, latent side
+CONFIG_PRESETS = {2: (8, 64), 3: (16, 64), 5: (4, 96)}
+
+
+def metric_name(latent: int) -> str:
+    return METRIC if latent == 64 else f"images_per_s_{8 * latent}x{8 * latent}_50_unipc_steps_cfg7.5"
 FLOP_PER_SAMPLE_STEP = 1.2446e12          # BrushNet 4.413e11 + UNet 8.033e11 at 64x64 latents
 
 
@@ -148,12 +154,51 @@ def cpu_reference_run(steps: int, warmup: int, images: int = 1):
                       f"torch CPU with {cores} threads"}
 
 
+def gpu_eager_baseline(images: int, latent: int, dev, steps: int = 3, warmup: int = 2):
+    """"The kernel to beat" (BASELINE.md §4.3): the reference's algorithm run EAGERLY in bf16 on this B200 by
+    PyTorch's own libraries (cuDNN convs, cuBLAS linears, SDPA flash / cuDNN attention, ATen norms) at the same batch.  The
+    reference package is not on the GPU box, so the op list is the oracle port (`oracle/mf_oracle.py`, pinned to the
+    reference), moved to the device: a BASELINE leg like `cpu_baseline`, never part of `value` / `e2e`."""
+    from oracle import mf_oracle as O
+    from mirrorfusion_b200.config import SD15
+    from mirrorfusion_b200.synth import make_inputs, make_state_dict
+    cfg, bf = SD15, torch.bfloat16
+    usd = {k: v.to(dev, bf) for k, v in make_state_dict(cfg, "unet").items()}
+    bsd = {k: v.to(dev, bf) for k, v in make_state_dict(cfg, "brushnet").items()}
+    inp = make_inputs(cfg, images, height=latent, width=latent)
+    ehs, cond = inp["prompt_embeds"].to(dev, bf), inp["conditioning_latents"].to(dev, bf)
+    sched = O.UniPCOracle()
+    sched.set_timesteps(STEPS_PER_IMAGE)
+    lat = inp["latents"].to(dev, bf)
+    old = (O.USE_SDPA, torch.backends.cudnn.benchmark)
+    O.USE_SDPA, torch.backends.cudnn.benchmark = True, True
+    try:
+        evs = []
+        with torch.no_grad():
+            for i in range(warmup + steps):
+                t = sched.timesteps[i]
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                eps, _ = O.noise_pred_step(usd, bsd, cfg, torch.cat([lat] * 2), t, ehs, cond, 1.0)
+                lat = sched.step(O.cfg_combine(eps, 7.5), t, lat)
+                b.record()
+                evs.append((a, b))
+        torch.cuda.synchronize()
+    finally:
+        O.USE_SDPA, torch.backends.cudnn.benchmark = old
+    ms = statistics.median(a.elapsed_time(b) for a, b in evs[warmup:])
+    return {"value": images / (STEPS_PER_IMAGE * ms * 1e-3), "unit": "images/s", "ms_per_step": ms, "dtype": "bf16",
+            "kind": "port on cuda (torch eager: cuDNN / cuBLAS / SDPA)", "torch": torch.__version__, "cudnn": torch.backends.cudnn.version(),
+            "sample": f"{images} images (net batch {2 * images}) x {steps} denoise steps at {latent}x{latent} latents, median; "
+                      f"{warmup} warm-up steps (cudnn.benchmark on), eager launches, no CUDA graph"}
+
+
 def run_reference(args, rank):
     if rank != 0:
         return
     r = cpu_reference_run(args.steps, min(args.warmup, 1), images=1)
     line = {
-        "impl": "reference", "metric": METRIC, "value": r["images_per_s"], "unit": "images/s", "n_gpus": args.gpus,
+        "impl": "reference", "metric": metric_name(args.latent), "value": r["images_per_s"], "unit": "images/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": r["sec_per_step"] * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "MirrorFusion 512x512, 50 UniPC steps, CFG 7.5 (reference algorithm on host CPU; bounded sample: "
@@ -302,23 +347,25 @@ def run_ours(args, rank, world, local_rank):
                               "(tests/test_gpu_model.py::test_brushnet_cfg_dedup_is_exact); NOT the headline value"}
         del eng_dd
 
+    launches_per_step = eng.launches_per_step
     if rank != 0:
         return
     # ---------------- live per-kernel-family timing (CUDA events around every launch of one step)
     peaks = load_peaks()
     fam = {}
     for e in (eng.bn, eng.unet):
-        for k, (t_ms, fl, n) in e.run_timed(skip=e.n_time_ops).items():      # the timestep path is hoisted out of the step
-            r = fam.setdefault(k, [0.0, 0.0, 0])
-            r[0] += t_ms; r[1] += fl; r[2] += n
+        for k, (t_ms, fl, n, xf) in e.run_timed(skip=e.n_time_ops).items():  # the timestep path is hoisted out of the step
+            r = fam.setdefault(k, [0.0, 0.0, 0, 0.0])
+            r[0] += t_ms; r[1] += fl; r[2] += n; r[3] += xf
     traffic, traffic_src = None, None
     tp = os.path.join(ROOT, "profiles", "r01o_igemm_traffic.json")     # from the committed ncu --set full capture
     if os.path.exists(tp):
         with open(tp) as f:
             tj = json.load(f)
         traffic, traffic_src = tj.get("dram_bytes_per_launch_avg"), tj.get("source")
-    ig = fam.get("igemm", [1e-9, 0.0, 1])
+    ig = fam.get("igemm", [1e-9, 0.0, 1, 0.0])
     achieved = ig[1] / (ig[0] * 1e-3) / 1e12
+    executed = ig[3] / (ig[0] * 1e-3) / 1e12
     peak = peaks["bf16_sustained"]
     # SURVEY.md §8d census for 64x64 latents; other geometries (config 5: 96x96) use the engines' own plan census
     step_flops = FLOP_PER_SAMPLE_STEP * 2 * images if (H, W) == (64, 64) else eng.flops_per_step
@@ -327,13 +374,26 @@ def run_ours(args, rank, world, local_rank):
         "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
         "peak_source": peaks["source"] + ", sustained bf16 (kernel timed inside a long step)",
         "traffic": traffic, "traffic_unit": "DRAM bytes per launch (read + write)", "traffic_source": traffic_src,
+        "frac_vs_burst": achieved / peaks["bf16_burst"], "peak_burst": peaks["bf16_burst"],
+        # the sub-pixel Upsample2D plans issue 4/9 of the MMAs the algorithmic count credits them with: utilisation of the
+        # tensor pipe is the EXECUTED figure
+        "executed_flops_per_step": ig[3], "executed_tflops": executed, "executed_frac": executed / peak,
+        "executed_frac_vs_burst": executed / peaks["bf16_burst"],
         "launches_per_step": ig[2], "avg_launch_ms": ig[0] / max(ig[2], 1),
         "algorithmic_flops_per_step": ig[1],
         "share_of_step_time": ig[0] / sum(v[0] for v in fam.values()),
         "families_ms_per_step": {k: round(v[0], 4) for k, v in sorted(fam.items())},
         "whole_step_tflops": step_flops / (ms_per_step * 1e-3) / 1e12,
         "whole_step_frac_of_peak": step_flops / (ms_per_step * 1e-3) / 1e12 / peak,
+        "whole_step_frac_vs_burst": step_flops / (ms_per_step * 1e-3) / 1e12 / peaks["bf16_burst"],
     }
+    # bandwidth-bound families against the measured HBM peak: ALGORITHMIC bytes (bf16, read + write once)
+    if (H, W) == (64, 64):
+        for famname, mb in (("groupnorm", 309e6), ("layernorm", 139e6)):
+            if famname in fam:
+                gbs = mb * 2 * images / (fam[famname][0] * 1e-3) / 1e9
+                roofline[famname + "_hbm"] = {"algorithmic_gb_per_step": mb * 2 * images / 1e9, "achieved_gbs": gbs,
+                                              "frac_of_hbm_peak": gbs / peaks["hbm_gbs"]}
     # ---------------- VAE decode of the final latents on the same kernels: secondary key, never part
     # of `value` / `e2e` (BASELINE's metric is quoted on the denoise loop; this shows the tail the decode adds per batch)
     vae_line = None
@@ -379,8 +439,17 @@ def run_ours(args, rank, world, local_rank):
     if world == 1 and not args.no_cpu_baseline:
         r = cpu_reference_run(steps=2, warmup=1, images=1)
         cpu = {"value": r["images_per_s"], "unit": "images/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]}
+    eager = None
+    if world == 1 and not args.no_eager_baseline:
+        try:
+            del eng
+            torch.cuda.empty_cache()
+            eager = gpu_eager_baseline(images, H, dev)
+            eager["ours_over_eager"] = value / eager["value"]
+        except Exception as ex:          # a baseline leg must not take the headline down with it
+            eager = {"error": f"{type(ex).__name__}: {ex}"}
     line = {
-        "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "metric": metric_name(H), "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
         "data": "synthetic",
         "config": {"workload": f"MirrorFusion (SD1.5 UNet + BrushNet, depth-concat cond) {8 * H}x{8 * W}, batch {images} images/GPU "
@@ -392,7 +461,7 @@ def run_ours(args, rank, world, local_rank):
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": e2e_ms / args.steps},
-        "gpu_launches": eng.launches_per_step * args.steps,
+        "gpu_launches": launches_per_step * args.steps,
         "roofline": roofline,
         "cpu_baseline": cpu,
     }
@@ -402,6 +471,8 @@ def run_ours(args, rank, world, local_rank):
         line["brushnet_cfg_dedup"] = dedup_line
     if vae_line is not None:
         line["vae_decode"] = vae_line
+    if eager is not None:
+        line["gpu_eager_baseline"] = eager
     emit_json(line)
 
 
@@ -422,7 +493,13 @@ def main():
                          "(never the headline value); --no-report-dedup skips it")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-vae", action="store_true", help="skip the secondary VAE-decode measurement")
+    ap.add_argument("--config", type=int, choices=sorted(CONFIG_PRESETS), default=None,
+                    help="BASELINE.json configs preset: 2 = 8 images/GPU at 64x64 (default workload), 3 = 16 images/GPU (the sharded "
+                         "eval sweep's per-GPU load), 5 = 768x768 (96x96 latents, 9216-token attention) batch 4")
+    ap.add_argument("--no-eager-baseline", action="store_true", help="skip the secondary gpu_eager_baseline measurement")
     args = ap.parse_args()
+    if args.config is not None:
+        args.images, args.latent = CONFIG_PRESETS[args.config]
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

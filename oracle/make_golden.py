@@ -178,6 +178,70 @@ def golden_psnr(diffusers, steps=20):
     print(f"sd15 {steps}-step reference loop: {time.time() - t0:.0f}s, |lat|={lat.norm():.3f}, image range [{img.min():.2f},{img.max():.2f}]")
 
 
+def golden_step_geometry(diffusers, name, images, hw, t=500, seed=0):
+    """One reference step of the SD1.5-shaped nets at a geometry bench.py actually runs (config 2: 8 images = net batch 16
+    at 64x64; config 5: 96x96 latents = 9216 tokens).  Fixture kept small: full noise_pred in float16-free fp32 only for the
+    first and last sample of each CFG half plus norms and a strided sample of the whole tensor and of every tap."""
+    from mirrorfusion_b200.config import SD15
+    from mirrorfusion_b200.synth import make_inputs
+    unet, bn, _, _ = build_reference_nets(diffusers, SD15, seed)
+    inp = make_inputs(SD15, images, height=hw, width=hw)
+    x = torch.cat([inp["latents"]] * 2)
+    t0 = time.time()
+    eps, d, m, u = ref_step(unet, bn, x, torch.tensor(t), inp["prompt_embeds"], inp["conditioning_latents"], 1.0)
+    dt = time.time() - t0
+    keep = sorted({0, images - 1, images, 2 * images - 1})
+    out = {"t": np.int64(t), "images": np.int64(images), "hw": np.int64(hw), "seed": np.int64(seed),
+           "noise_pred_l2": np.float64(eps.double().norm().item()),
+           "noise_pred_l2_per_sample": eps.double().flatten(1).norm(dim=1).numpy(),
+           "noise_pred_stride": np.int64(7), "noise_pred_strided": eps.flatten()[::7].numpy().copy(),
+           "keep": np.array(keep, np.int64), "noise_pred_keep": eps[keep].numpy().copy()}
+    for k, a in enumerate(list(d) + [m] + list(u)):
+        out[f"tap{k:02d}_l2"] = np.float64(a.double().norm().item())
+        out[f"tap{k:02d}_sample"] = a.flatten()[:: max(1, a.numel() // 4096)][:4096].numpy().copy()
+    np.savez_compressed(os.path.join(GOLD, name), **out)
+    print(f"{name}: {images} images at {hw}x{hw}: ref step {dt:.1f}s  |eps|={eps.norm():.4f}")
+
+
+def golden_psnr50(diffusers, steps=50, name="sd15_loop_unipc50_sdvae.npz"):
+    """north_star's final-image protocol at full size: the REFERENCE loop (SD1.5-shaped nets, 50 UniPC steps, CFG 7.5, fp32
+    CPU) followed by the REFERENCE AutoencoderKL.decode with the SD VAE architecture at 512x512 (seeded weights from
+    vae.make_vae_state_dict(SD_VAE), loaded strict), postprocessed to uint8 by the reference's VaeImageProcessor."""
+    from diffusers.image_processor import VaeImageProcessor
+    from mirrorfusion_b200.config import SD15
+    from mirrorfusion_b200.synth import make_inputs
+    from mirrorfusion_b200.vae import SD_VAE, make_vae_state_dict
+    cfg = SD_VAE
+    n = len(cfg.block_out_channels)
+    vae = diffusers.AutoencoderKL(in_channels=3, out_channels=cfg.out_channels, down_block_types=("DownEncoderBlock2D",) * n,
+                                  up_block_types=("UpDecoderBlock2D",) * n, block_out_channels=cfg.block_out_channels,
+                                  layers_per_block=cfg.layers_per_block, latent_channels=cfg.latent_channels,
+                                  norm_num_groups=cfg.norm_num_groups, sample_size=512, scaling_factor=cfg.scaling_factor).eval()
+    vae.load_state_dict(make_vae_state_dict(cfg, 0, "both"), strict=True)
+    unet, bn, _, _ = build_reference_nets(diffusers, SD15, 0)
+    inp = make_inputs(SD15, 1)
+    base = diffusers.DDIMScheduler(beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear",
+                                   clip_sample=False, set_alpha_to_one=False, steps_offset=1)
+    sched = diffusers.UniPCMultistepScheduler.from_config(base.config)
+    sched.set_timesteps(steps)
+    lat = inp["latents"] * sched.init_noise_sigma
+    t0 = time.time()
+    traj = []
+    for t in sched.timesteps:                                      # pipeline_brushnet.py:1250-1315
+        x = torch.cat([lat] * 2)
+        eps, *_ = ref_step(unet, bn, x, t, inp["prompt_embeds"], inp["conditioning_latents"])
+        u_, c_ = eps.chunk(2)
+        lat = sched.step(u_ + 7.5 * (c_ - u_), t, lat, return_dict=False)[0]
+        traj.append(np.float64(lat.double().norm().item()))
+    with torch.no_grad():
+        img = vae.decode(lat / cfg.scaling_factor, return_dict=False)[0]                   # pipeline_brushnet.py:1342
+    u8 = (VaeImageProcessor(vae_scale_factor=8).postprocess(img, output_type="np") * 255).round().astype(np.uint8)
+    np.savez_compressed(os.path.join(GOLD, name), latents=lat.numpy(), image_u8=u8, latent_norms=np.array(traj),
+                        image_f32_sample=img.flatten()[::64].numpy().copy(), steps=np.int64(steps), guidance=np.float64(7.5))
+    print(f"{name}: {steps}-step reference loop + SD-VAE decode: {time.time() - t0:.0f}s, |lat|={lat.norm():.3f}, "
+          f"image range [{img.min():.2f},{img.max():.2f}], uint8 mean {u8.mean():.1f}")
+
+
 @torch.no_grad()
 def golden_vae_decode(diffusers, name="tiny_vae_decode.npz", seed=0):
     """AutoencoderKL.decode of the reference on the seeded TINY_VAE decoder weights (vae.make_vae_state_dict)."""
@@ -304,6 +368,12 @@ def main():
     which = sys.argv[1:] or ["sched", "micro", "tiny", "sd15", "sigs"]
     if "psnr" in which:
         golden_psnr(diffusers)
+    if "psnr50" in which:
+        golden_psnr50(diffusers)
+    if "b16" in which:
+        golden_step_geometry(diffusers, "sd15_step_b16.npz", images=8, hw=64)
+    if "g96" in which:
+        golden_step_geometry(diffusers, "sd15_step_96.npz", images=2, hw=96)
     if "vae" in which:
         golden_vae_decode(diffusers)
     if "prep" in which:

@@ -81,6 +81,13 @@ def upsample(sd, p: str, x: Tensor, size: Optional[Sequence[int]] = None) -> Ten
     return F.conv2d(x, sd[f"{p}.conv.weight"], sd[f"{p}.conv.bias"], padding=1)
 
 
+# The reference's DEFAULT processor is AttnProcessor2_0 = F.scaled_dot_product_attention (attention_processor.py:212-216,
+# 1266-1268); AttnProcessor (:732-798: baddbmm + softmax + bmm) is the math it is equivalent to and what this restatement spells
+# out.  The eager-GPU baseline (bench.py `gpu_eager_baseline`) flips this switch so that "the kernel to beat" runs the library
+# flash / cuDNN attention the reference would run on a B200, not a materialised score matrix.
+USE_SDPA = False
+
+
 def attention(sd, p: str, x: Tensor, ctx: Optional[Tensor], heads: int) -> Tensor:
     """Attention + AttnProcessor2_0.__call__, S/models/attention_processor.py:1204-1286
     (no mask, q/k/v without bias, to_out[0] with bias, scale = dim_head^-0.5)."""
@@ -93,8 +100,11 @@ def attention(sd, p: str, x: Tensor, ctx: Optional[Tensor], heads: int) -> Tenso
     q = q.view(b, n, heads, d).transpose(1, 2)
     k = k.view(b, -1, heads, d).transpose(1, 2)
     v = v.view(b, -1, heads, d).transpose(1, 2)
-    s = torch.matmul(q, k.transpose(-1, -2)) * (d ** -0.5)
-    o = torch.matmul(torch.softmax(s.float(), dim=-1).to(q.dtype), v)
+    if USE_SDPA:
+        o = F.scaled_dot_product_attention(q, k, v, attn_mask=None, dropout_p=0.0, is_causal=False)
+    else:
+        s = torch.matmul(q, k.transpose(-1, -2)) * (d ** -0.5)
+        o = torch.matmul(torch.softmax(s.float(), dim=-1).to(q.dtype), v)
     o = o.transpose(1, 2).reshape(b, n, c)
     return F.linear(o, sd[f"{p}.to_out.0.weight"], sd[f"{p}.to_out.0.bias"])
 

@@ -657,7 +657,7 @@ class BrushNetBranchTrainer(BrushNetDownMidTrainer):
 def unpack_brushnet_branch(cfg, flat: FlatParams) -> Dict[str, torch.Tensor]:
     """Inverse of pack_brushnet_branch: the trained branch parameters back in the reference's state_dict naming and OIHW layout
     (what `BrushNetModel.save_pretrained` writes at a checkpoint, E/train_brushnet_mirror.py:997-1032) — fp32 masters, on the host.
-    conv_in_condition and the timestep path are not in the flat buffer yet and keep their loaded values."""
+    Only the branch behind conv_in_condition; `unpack_brushnet` exports the whole model."""
     shapes = brushnet_branch_shapes(cfg)
     out: Dict[str, torch.Tensor] = {}
     for name, shp in shapes.items():
@@ -800,6 +800,26 @@ def pack_brushnet(cfg, sd) -> Dict[str, torch.Tensor]:
            "conv_in_condition.bias": sd["conv_in_condition.bias"].float().contiguous()}
     out.update(pack_time_path(cfg, sd, brushnet_resnet_prefixes(cfg)))
     out.update(pack_brushnet_branch(cfg, sd))
+    return out
+
+
+def unpack_brushnet(cfg, flat: FlatParams) -> Dict[str, torch.Tensor]:
+    """Inverse of pack_brushnet: EVERY parameter BrushNetTrainer trains, back in the reference's state_dict naming and layouts
+    (`BrushNetModel.save_pretrained` at a checkpoint, E/train_brushnet_mirror.py:997-1032): the branch, conv_in_condition (OIHW)
+    and the timestep path — the concatenated `time_emb_proj.wcat` / `.bcat` split back into the 22 per-resnet layers.  The key set
+    passes `checkpoint.check_state_dict(..., "brushnet")`; fp32 masters, on the host."""
+    out = unpack_brushnet_branch(cfg, flat)
+    host = lambda name: flat.p(name).detach().float().cpu()
+    out["conv_in_condition.weight"] = unpack_conv_grad(host("conv_in_condition.weight"), 3)
+    out["conv_in_condition.bias"] = host("conv_in_condition.bias").clone()
+    for k in ("time_embedding.linear_1.weight", "time_embedding.linear_1.bias", "time_embedding.linear_2.weight", "time_embedding.linear_2.bias"):
+        out[k] = host(k).clone()
+    wcat, bcat, o = host("time_emb_proj.wcat"), host("time_emb_proj.bcat"), 0
+    for p in brushnet_resnet_prefixes(cfg):
+        c = resnet_cout(cfg, p)
+        out[p + ".time_emb_proj.weight"] = wcat[o:o + c].clone()
+        out[p + ".time_emb_proj.bias"] = bcat[o:o + c].clone()
+        o += c
     return out
 
 

@@ -37,6 +37,7 @@ class _Net:
         self.prog: List[Callable[[], None]] = []
         self.tags: List[Tuple[str, float]] = []       # (kernel family, algorithmic FLOPs) per program entry
         self.notes: List[Optional[str]] = []          # shape note per program entry (igemm plans only)
+        self.exec_flops: List[float] = []             # FLOPs of the MMAs actually issued per entry (< algorithmic for the sub-pixel upsample)
         self.keep: List[object] = []
         self._scratch: Dict[Tuple, torch.Tensor] = {}
         self.flops = 0.0
@@ -89,6 +90,7 @@ class _Net:
         self.prog.append(fn)
         self.tags.append((tag, flops))
         self.notes.append(None)
+        self.exec_flops.append(flops)
         self.launches += n_launch
         if out is not None:
             self.writer_pos[out.data_ptr()] = pos
@@ -110,6 +112,7 @@ class _Net:
         self.flops += plan.flops
         self.emit(plan.run, getattr(plan, "launches", 1), "igemm", plan.flops, out=out, reads=reads)
         self.notes[-1] = getattr(plan, "note", None)
+        self.exec_flops[-1] = getattr(plan, "exec_flops", plan.flops)
 
     def groupnorm(self, x1, x2, prefix: str, out, HW: int, eps: float, silu: bool):
         g, b = self.wf(prefix + ".weight"), self.wf(prefix + ".bias")
@@ -261,7 +264,7 @@ class _Net:
 
     def run_timed(self, per_entry: bool = False, skip: int = 0):
         """Run the program once with a CUDA-event pair around every entry (on the current stream) and return
-        {family: (milliseconds, algorithmic FLOPs, entries)} — the live per-kernel timing bench.py reports.
+        {family: (milliseconds, algorithmic FLOPs, entries, executed FLOPs)} — the live per-kernel timing bench.py reports.
         per_entry=True returns [(family, note, ms, FLOPs)] per program entry instead (tools/profile_step.py).
         skip: leading entries to leave out (the hoisted timestep path: `n_time_ops`)."""
         evs = []
@@ -275,11 +278,12 @@ class _Net:
         if per_entry:
             return [(tag, note, a.elapsed_time(b), fl) for (a, b), (tag, fl), note in zip(evs, self.tags[skip:], self.notes[skip:])]
         out: Dict[str, List[float]] = {}
-        for (a, b), (tag, fl) in zip(evs, self.tags[skip:]):
-            r = out.setdefault(tag, [0.0, 0.0, 0])
+        for (a, b), (tag, fl), xf in zip(evs, self.tags[skip:], self.exec_flops[skip:]):
+            r = out.setdefault(tag, [0.0, 0.0, 0, 0.0])
             r[0] += a.elapsed_time(b)
             r[1] += fl
             r[2] += 1
+            r[3] += xf
         return out
 
 

@@ -159,6 +159,9 @@ class ConvPlan:
         self.flops = L.mfb_plan_flops(h)
         self.launches = L.mfb_plan_launches(h)
         Ho, Wo = (2 * H, 2 * W) if up2x else ((H + stride - 1) // stride, (W + stride - 1) // stride)
+        # MMA work actually issued: the sub-pixel upsample plan runs 4 taps per output pixel where `flops` counts the 9 of the
+        # reference's conv over the upsampled tensor
+        self.exec_flops = 2.0 * B * Ho * Wo * Cout * ktot
         self.note = (f"M={B * Ho * Wo} N={Cout} K={ktot} k{ksize}" + (" s2" if stride == 2 else "") + (" up2x" if up2x else "") +
                      (" geglu" if geglu else "") + (" +res1" if res1 is not None else "") + (" +res2" if res2 is not None else "") +
                      (f" +{len(extras)}seg" if extras else ""))

@@ -334,9 +334,11 @@ class StepEngine:
     def prepare_timesteps(self, timesteps):
         """Hoist the timestep path (sinusoid -> MLP -> all 22+22 time_emb_proj, embeddings.py:27-67,226-237,
         resnet.py:369-376) out of the loop: it depends only on t, so both nets' row-bias tables for the whole
-        schedule are computed once.  Must be called before the step graph is captured."""
-        if self.graph is not None:
-            raise RuntimeError("prepare_timesteps() must run before the first captured step")
+        schedule are computed once.  The first call must precede the capture of the step graph (the captured program skips
+        the timestep ops); later calls — another step count, another scheduler — just rebuild the tables: they are not baked
+        into the graph, `step()` copies the row of the current timestep into the row-bias buffers before every replay."""
+        if self.graph is not None and self.time_tables is None:
+            raise RuntimeError("this step graph was captured with the timestep path inside; it cannot switch to hoisted tables")
         ts = [float(t) for t in timesteps]
         self.time_tables = ({t: i for i, t in enumerate(ts)}, self.bn.timestep_table(ts), self.unet.timestep_table(ts))
         self.launches_per_step = self.unet.launches + self.bn.launches + 1 - 8
@@ -415,10 +417,8 @@ class StepEngine:
         for t_ in (self.last, self.m0, self.m1):
             t_.zero_()
         ts = scheduler.timesteps.tolist()
-        if self.graph is None:
+        if self.graph is None or (self.time_tables is not None and any(float(t) not in self.time_tables[0] for t in ts)):
             self.prepare_timesteps(ts)
-        elif self.time_tables is not None and any(float(t) not in self.time_tables[0] for t in ts):
-            raise RuntimeError("this StepEngine was captured for a different timestep schedule")
         for i, t in enumerate(ts):
             sc = 1.0 if conditioning_scales is None else conditioning_scales[i]
             self.step(float(t), table[i], sc)
@@ -436,8 +436,9 @@ class MirrorFusionB200Pipeline:
                  depth_conditioning_mode: str = "concat", normals_conditioning_mode: Optional[str] = None,
                  vae_encode: Optional[Callable[[torch.Tensor], torch.Tensor]] = None,
                  vae_decode: Optional[Callable[[torch.Tensor], torch.Tensor]] = None, vae_scale_factor: int = 8,
-                 precision: str = "bf16", vae_state_dict=None, vae_cfg=None):
-        """precision="fp32": the fp32 parity mode of StepEngine (BASELINE config 1), otherwise the bf16 product path.
+                 precision: str = "bf16", vae_state_dict=None, vae_cfg=None, empty_prompt_embeds: Optional[torch.Tensor] = None):
+        """empty_prompt_embeds: the text encoder's embedding of "" — what the reference substitutes when no negative prompt is given.
+        precision="fp32": the fp32 parity mode of StepEngine (BASELINE config 1), otherwise the bf16 product path.
         vae_state_dict (AutoencoderKL.state_dict() keys; only post_quant_conv.* / decoder.* are read): when given and no
         `vae_decode` callable is passed, images are decoded by VaeDecoderEngine on the same kernels (vae.py)."""
         if depth_conditioning_mode != "concat" or normals_conditioning_mode is not None:
@@ -448,6 +449,7 @@ class MirrorFusionB200Pipeline:
         self.vae_encode, self.vae_decode, self.vae_scale_factor = vae_encode, vae_decode, vae_scale_factor
         self._engines: Dict[Tuple[int, int, int], StepEngine] = {}
         self.precision = precision
+        self.empty_prompt_embeds = empty_prompt_embeds
         self.vae_sd, self.vae_cfg, self._vae_engines = vae_state_dict, vae_cfg, {}
         if vae_state_dict is not None and vae_decode is None:
             self.vae_decode = self._decode_on_kernels
@@ -537,7 +539,13 @@ class MirrorFusionB200Pipeline:
         if not do_cfg:
             raise NotImplementedError("the fused step is built for classifier-free guidance (guidance_scale > 1)")
         if negative_prompt_embeds is None:
-            negative_prompt_embeds = torch.zeros_like(prompt_embeds)
+            # the reference encodes "" through CLIP for the unconditional half (encode_prompt, :417-446) — not a zero tensor;
+            # the text encoder is outside this package, so its embedding of the empty prompt must be handed in once
+            if self.empty_prompt_embeds is None:
+                raise ValueError("`negative_prompt_embeds` is None: pass it, or construct the pipeline with `empty_prompt_embeds` "
+                                 "(the text encoder's embedding of the empty prompt, [1 or b, 77, ctx]); zeros are not what the "
+                                 "reference uses for the unconditional half")
+            negative_prompt_embeds = self.empty_prompt_embeds.to(prompt_embeds).expand(prompt_embeds.shape[0], -1, -1)
         b = prompt_embeds.shape[0]
         ehs = torch.cat([negative_prompt_embeds, prompt_embeds])                           # uncond first (:1102-1103)
         if conditioning_latents is None:

@@ -37,6 +37,17 @@ def _alphas_cumprod(num_train_timesteps, beta_start, beta_end, beta_schedule) ->
     return torch.cumprod(1.0 - betas, dim=0).numpy()
 
 
+class _Config(dict):
+    """Scheduler config with key AND attribute access, like the reference's FrozenDict (S/configuration_utils.py:52-87): the
+    reference's own `SomeScheduler.from_config(ours.config)` (E/test_brushnet.py:158) takes it as the dict it expects."""
+
+    def __getattr__(self, k):
+        try:
+            return self[k]
+        except KeyError:
+            raise AttributeError(k) from None
+
+
 class _Base:
     order = 1
     init_noise_sigma = 1.0
@@ -92,7 +103,7 @@ class B200DDIMScheduler(_Base):
                  clip_sample=False, set_alpha_to_one=False, steps_offset=1, prediction_type="epsilon"):
         if clip_sample or prediction_type != "epsilon":
             raise NotImplementedError("clip_sample / non-epsilon prediction are not on the MirrorFusion path")
-        self.config = SimpleNamespace(num_train_timesteps=num_train_timesteps, beta_start=beta_start, beta_end=beta_end,
+        self.config = _Config(num_train_timesteps=num_train_timesteps, beta_start=beta_start, beta_end=beta_end,
                                       beta_schedule=beta_schedule, clip_sample=clip_sample,
                                       set_alpha_to_one=set_alpha_to_one, steps_offset=steps_offset,
                                       prediction_type=prediction_type)
@@ -165,7 +176,7 @@ class B200UniPCScheduler(_Base):
         if solver_order != 2 or prediction_type != "epsilon" or not predict_x0 or solver_type != "bh2" \
                 or timestep_spacing != "linspace":
             raise NotImplementedError("only the MirrorFusion UniPC configuration (order 2, bh2, x0-prediction) is implemented")
-        self.config = SimpleNamespace(num_train_timesteps=num_train_timesteps, beta_start=beta_start, beta_end=beta_end,
+        self.config = _Config(num_train_timesteps=num_train_timesteps, beta_start=beta_start, beta_end=beta_end,
                                       beta_schedule=beta_schedule, solver_order=solver_order,
                                       prediction_type=prediction_type, predict_x0=predict_x0, solver_type=solver_type,
                                       lower_order_final=lower_order_final, timestep_spacing=timestep_spacing,

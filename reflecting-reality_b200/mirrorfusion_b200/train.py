@@ -127,6 +127,22 @@ class B200AdamW:
     def zero_grad(self, set_to_none: bool = False):
         self.flat.grad.zero_()
 
+    def state_dict(self) -> Dict[str, object]:
+        """What `accelerator.save_state` keeps of torch.optim.AdamW (E/train_brushnet_mirror.py:1488-1509): the two moment
+        buffers (flat, host copies), the step count that drives the bias correction, and the hyper-parameters."""
+        return {"exp_avg": self.flat.exp_avg.detach().cpu().clone(), "exp_avg_sq": self.flat.exp_avg_sq.detach().cpu().clone(),
+                "step_count": int(self.step_count), "param_groups": [dict(g) for g in self.param_groups],
+                "layout": dict(self.flat.table)}
+
+    def load_state_dict(self, sd: Mapping[str, object]):
+        """Resume (`--resume_from_checkpoint`, :1271-1300): save -> load -> step is bit-identical to an uninterrupted run."""
+        if dict(sd["layout"]) != dict(self.flat.table):
+            raise ValueError("optimizer state was saved for a different flat parameter layout")
+        self.flat.exp_avg.copy_(sd["exp_avg"])
+        self.flat.exp_avg_sq.copy_(sd["exp_avg_sq"])
+        self.step_count = int(sd["step_count"])
+        self.param_groups = [dict(g, betas=tuple(g["betas"])) for g in sd["param_groups"]]
+
 
 class NoiseSchedule:
     """The training-time half of DDPMScheduler (SD1.5 schedule by default): add_noise, get_velocity, min-SNR weights."""
@@ -216,3 +232,16 @@ class LRSchedule:
 
     def get_last_lr(self):
         return [self.opt.param_groups[0]["lr"]]
+
+    def state_dict(self) -> Dict[str, object]:
+        return {"name": self.name, "last_epoch": int(self.last_epoch), "base_lr": float(self.base_lr), "num_warmup_steps": self.warmup,
+                "num_training_steps": self.total, "num_cycles": self.cycles}
+
+    def load_state_dict(self, sd: Mapping[str, object]):
+        """Restores `base_lr` too: a scheduler constructed over a resumed optimizer would otherwise take the already-decayed
+        learning rate as its base."""
+        if sd["name"] != self.name:
+            raise ValueError(f"lr schedule state is for {sd['name']!r}, this schedule is {self.name!r}")
+        self.last_epoch, self.base_lr = int(sd["last_epoch"]), float(sd["base_lr"])
+        self.warmup, self.total, self.cycles = sd["num_warmup_steps"], sd["num_training_steps"], sd["num_cycles"]
+        self._apply()

@@ -1,0 +1,153 @@
+"""Parity at the geometries bench.py actually runs (VERDICT r01 "what's weak" item 2), against vectors produced by the
+REFERENCE itself (oracle/make_golden.py b16 / g96 / psnr50):
+
+  * config 2: 8 images = net batch 16 at 64x64 (the igemm picks other tile widths / BN at the 8x8 and 16x16 levels than
+    at net batch 2, igemm.cu pick_tile / build_params);
+  * config 5: 96x96 latents = 9216-token self-attention;
+  * north_star's final-image protocol at full size: 50 UniPC steps, CFG 7.5, then AutoencoderKL.decode with the SD VAE
+    architecture at 512x512, PSNR on uint8 images >= 40 dB;
+  * checkpoint import on the device: `from_checkpoint` builds an engine bit-identical to the state-dict constructor.
+
+Bar (BASELINE.json north_star): per-step noise prediction within rel-L2 1e-2 of the fp32 reference in bf16 mode.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from mirrorfusion_b200.config import SD15, TINY
+from mirrorfusion_b200.synth import make_inputs, make_state_dict
+
+BF16_TOL = 1e-2
+
+
+def rel(a, b):
+    a = torch.as_tensor(a).double().cpu()
+    b = torch.as_tensor(b).double().cpu()
+    return ((a - b).norm() / b.norm()).item()
+
+
+def record(name, **vals):
+    d = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    os.makedirs(d, exist_ok=True)
+    with open(os.path.join(d, "parity_metrics.jsonl"), "a") as f:
+        f.write(json.dumps({"test": name, **vals}) + "\n")
+
+
+@pytest.fixture(scope="module")
+def P():
+    from mirrorfusion_b200 import ops, pipeline
+    ops.lib()
+    return pipeline
+
+
+@pytest.mark.parametrize("fixture", ["sd15_step_b16.npz", "sd15_step_96.npz"])
+def test_sd15_bench_geometry_step_vs_reference_golden(P, golden_dir, fixture):
+    g = np.load(os.path.join(golden_dir, fixture))
+    images, hw, t = int(g["images"]), int(g["hw"]), float(g["t"])
+    usd, bsd = make_state_dict(SD15, "unet"), make_state_dict(SD15, "brushnet")
+    inp = make_inputs(SD15, images, height=hw, width=hw)
+    eng = P.StepEngine(SD15, usd, bsd, images, hw, hw, use_graph=False, fuse_taps=True)      # the engine bench.py times
+    eng.set_conditioning(inp["prompt_embeds"].cuda(), inp["conditioning_latents"].cuda())
+    eng.x.copy_(inp["latents"].cuda())
+    eng.step(t, torch.zeros(12, device="cuda"), 1.0)
+    eps = eng.unet.out.float().cpu()
+    assert eps.shape == (2 * images, 4, hw, hw)
+    keep = [int(k) for k in g["keep"]]
+    e_keep = [rel(eps[k], g["noise_pred_keep"][i]) for i, k in enumerate(keep)]
+    e_strided = rel(eps.flatten()[:: int(g["noise_pred_stride"])], g["noise_pred_strided"])
+    norms = eps.double().flatten(1).norm(dim=1).numpy()
+    norm_dev = float(np.abs(norms / g["noise_pred_l2_per_sample"] - 1).max())
+    record("sd15_bench_geometry_step_vs_reference", fixture=fixture, images=images, latent=hw, noise_pred_strided=e_strided,
+           noise_pred_kept_samples=e_keep, per_sample_norm_dev=norm_dev)
+    assert norm_dev < 5e-3
+    assert max(e_keep) < BF16_TOL, e_keep
+    assert e_strided < BF16_TOL
+
+    # API mode at the same geometry: all 28 taps as tensors (zero-conv epilogue) against the reference's tap statistics
+    del eng
+    torch.cuda.empty_cache()
+    bn = P.B200BrushNetModel(bsd, SD15)
+    x = torch.cat([inp["latents"]] * 2).cuda()
+    d, m, u = bn(x, torch.tensor(int(t)), encoder_hidden_states=inp["prompt_embeds"].cuda(),
+                 brushnet_cond=inp["conditioning_latents"].cuda(), conditioning_scale=1.0, return_dict=False)
+    errs = []
+    for k, a in enumerate(list(d) + [m] + list(u)):
+        a = a.float().cpu()
+        errs.append(rel(a.flatten()[:: max(1, a.numel() // 4096)][:4096], g[f"tap{k:02d}_sample"]))
+        assert abs(a.double().norm().item() / float(g[f"tap{k:02d}_l2"]) - 1) < 1e-2
+    record("sd15_bench_geometry_taps_vs_reference", fixture=fixture, worst_tap=max(errs))
+    assert max(errs) < 2e-2, errs
+
+
+def test_sd15_50_step_final_image_psnr_sd_vae(P, golden_dir):
+    """north_star: "final decoded images within PSNR >= 40 dB of the reference" at full size — 50 UniPC steps, CFG 7.5, SD1.5
+    nets, then the SD VAE decoder at 512x512 (VaeDecoderEngine on our side; the reference's own loop + AutoencoderKL.decode +
+    VaeImageProcessor.postprocess produced the golden uint8 image)."""
+    from mirrorfusion_b200 import ops
+    from mirrorfusion_b200.vae import SD_VAE, VaeDecoderEngine, make_vae_state_dict
+    g = np.load(os.path.join(golden_dir, "sd15_loop_unipc50_sdvae.npz"))
+    usd, bsd = make_state_dict(SD15, "unet"), make_state_dict(SD15, "brushnet")
+    inp = make_inputs(SD15, 1)
+    eng = P.StepEngine(SD15, usd, bsd, 1, 64, 64, use_graph=True)
+    eng.set_conditioning(inp["prompt_embeds"].cuda(), inp["conditioning_latents"].cuda())
+    norms = []
+    lat = eng.denoise(inp["latents"].cuda(), P.B200UniPCScheduler(), int(g["steps"]), float(g["guidance"]),
+                      callback=lambda i, t, x: norms.append(x.double().norm().item())).clone()
+    e_lat = rel(lat, g["latents"])
+    dec = VaeDecoderEngine(SD_VAE, make_vae_state_dict(SD_VAE, 0, "decoder"), 1, 64, 64)
+    ref_u8 = torch.from_numpy(g["image_u8"]).cuda()                                      # [1, 512, 512, 3]
+
+    def decode_u8(z):
+        img = dec.decode(z / SD_VAE.scaling_factor)
+        out = torch.empty(1, 512, 512, 3, device="cuda", dtype=torch.uint8)
+        ops.post_image_u8(img.float().contiguous(), out)
+        return out, img
+
+    def psnr(a, b):
+        mse = (a.float() - b.float()).pow(2).mean().item()
+        return float(10 * np.log10(255.0 ** 2 / max(mse, 1e-12)))
+
+    ours_u8, _ = decode_u8(lat)
+    refdec_u8, refdec = decode_u8(torch.from_numpy(g["latents"]).cuda())
+    p_full = psnr(ours_u8, ref_u8)                   # our loop + our decoder        vs reference loop + reference decoder
+    p_dec = psnr(refdec_u8, ref_u8)                  # reference latents, our decoder vs reference decoder (decoder alone)
+    e_dec = rel(refdec.float().flatten()[::64], g["image_f32_sample"])
+    record("sd15_unipc50_sdvae_final_image", psnr_db=p_full, psnr_decoder_only_db=p_dec, latents_rel_l2=e_lat,
+           decoder_rel_l2=e_dec, latent_norm_dev=float(np.abs(np.array(norms) / g["latent_norms"] - 1).max()))
+    assert p_dec >= 40.0, p_dec
+    assert p_full >= 40.0, (p_full, e_lat)
+
+
+def test_from_checkpoint_builds_a_bit_identical_engine(P, golden_dir, tmp_path):
+    """SURVEY §8f-3 on the device: the reference's directory layout (config.json verbatim from what its save_pretrained wrote,
+    tests/golden/micro_checkpoint_layout.json, + safetensors) -> MirrorFusionB200Pipeline.from_checkpoint must give exactly
+    the latents of the pipeline built from the state dicts."""
+    from safetensors.torch import save_file
+    from mirrorfusion_b200 import checkpoint as CK
+    with open(os.path.join(golden_dir, "micro_checkpoint_layout.json")) as f:
+        layout = json.load(f)
+    cfg = TINY          # MICRO's 32-channel maps are below the tcgen05 path's 64-channel granularity: same keys, TINY's sizes
+    usd, bsd = make_state_dict(cfg, "unet"), make_state_dict(cfg, "brushnet")
+    dirs = {}
+    for net, sd in (("unet", usd), ("brushnet", bsd)):
+        d = tmp_path / net
+        d.mkdir()
+        cj = dict(layout[net]["config"], block_out_channels=list(cfg.block_out_channels), attention_head_dim=cfg.heads,
+                  cross_attention_dim=cfg.cross_attention_dim, sample_size=cfg.sample_size, norm_num_groups=cfg.norm_num_groups)
+        (d / "config.json").write_text(json.dumps(cj))
+        save_file({k: v.contiguous() for k, v in sd.items()}, str(d / CK.WEIGHTS[0]))
+        dirs[net] = str(d)
+    inp = make_inputs(cfg, 2, seed=3)
+    outs = []
+    for pipe in (P.MirrorFusionB200Pipeline(usd, bsd, cfg=cfg), P.MirrorFusionB200Pipeline.from_checkpoint(dirs["unet"], dirs["brushnet"])):
+        assert pipe.cfg == cfg
+        outs.append(pipe(prompt_embeds=inp["prompt_embeds"][2:].cuda(), negative_prompt_embeds=inp["prompt_embeds"][:2].cuda(),
+                         conditioning_latents=inp["conditioning_latents"][:2].cuda(), latents=inp["latents"].cuda(),
+                         num_inference_steps=3, guidance_scale=7.5, output_type="latent").images.clone())
+    assert torch.isfinite(outs[0]).all()
+    assert torch.equal(outs[0], outs[1])

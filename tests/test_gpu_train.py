@@ -144,6 +144,48 @@ def test_flat_adamw_matches_torch_adamw(ops, max_norm):
     assert flat.param.cpu()[pads].eq(0).all()                    # alignment padding never moves
 
 
+def test_optimizer_and_lr_schedule_resume_is_bit_identical(ops):
+    """save -> load -> step equals an uninterrupted run bit for bit (moments, step count -> bias correction, lr
+    schedule position and base lr), like accelerator.save_state / --resume_from_checkpoint (E/train_brushnet_mirror.py:1271-1300,1488-1509)."""
+    from mirrorfusion_b200.train import B200AdamW, FlatParams, LRSchedule
+    shapes = {"a.weight": (64, 27), "a.bias": (64,), "b.weight": (33, 65)}
+    gen = torch.Generator().manual_seed(5)
+    sd = {k: torch.randn(s, generator=gen) for k, s in shapes.items()}
+    grads = [{k: torch.randn(s, generator=gen) for k, s in shapes.items()} for _ in range(7)]
+
+    def run(flat, opt, sched, lo, hi):
+        for i in range(lo, hi):
+            for k in shapes:
+                flat.g(k).copy_(grads[i][k])
+            opt.step(max_grad_norm=1.0)
+            sched.step()
+
+    mk = lambda: FlatParams.from_state_dict(sd, "cuda")
+    f1 = mk()
+    o1 = B200AdamW(f1, lr=1e-2)
+    s1 = LRSchedule(o1, "cosine", num_warmup_steps=2, num_training_steps=10)
+    run(f1, o1, s1, 0, 7)
+    f2 = mk()
+    o2 = B200AdamW(f2, lr=1e-2)
+    s2 = LRSchedule(o2, "cosine", num_warmup_steps=2, num_training_steps=10)
+    run(f2, o2, s2, 0, 4)
+    ck = {"params": f2.state_dict(), "opt": o2.state_dict(), "lr": s2.state_dict()}
+    assert ck["opt"]["step_count"] == 4 and ck["lr"]["last_epoch"] == 4 and ck["opt"]["exp_avg"].device.type == "cpu"
+    f3 = FlatParams(shapes, "cuda")
+    f3.load_state_dict(ck["params"])
+    o3 = B200AdamW(f3, lr=123.0)                       # wrong on purpose: the saved groups / base lr must win
+    s3 = LRSchedule(o3, "cosine")
+    o3.load_state_dict(ck["opt"])
+    s3.load_state_dict(ck["lr"])
+    assert s3.get_last_lr() == s2.get_last_lr() and s3.base_lr == 1e-2
+    run(f3, o3, s3, 4, 7)
+    for a, b in ((f1.param, f3.param), (f1.exp_avg, f3.exp_avg), (f1.exp_avg_sq, f3.exp_avg_sq), (f1.work, f3.work)):
+        assert torch.equal(a, b)
+    assert s1.get_last_lr() == s3.get_last_lr() and o1.step_count == o3.step_count == 7
+    with pytest.raises(ValueError):
+        B200AdamW(FlatParams({"x": (3,)}, "cuda")).load_state_dict(ck["opt"])
+
+
 def test_adamw_grad_scale_is_the_allreduce_mean(ops):
     # SUM-all-reduced gradients of W ranks with grad_scale 1/W == the mean gradient, clipping on the mean's norm
     from mirrorfusion_b200.train import B200AdamW, FlatParams

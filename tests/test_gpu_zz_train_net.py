@@ -53,8 +53,6 @@ def test_brushnet_down_mid_forward_backward_fp32_vs_autograd():
 
 
 @pytest.mark.timeout(180)
-@pytest.mark.xfail(strict=False, reason="this test itself has not run on a GPU yet (round-1 budget spent); the program it drives is a strict subset of "
-                                        "test_whole_brushnet_every_parameter_gradient_fp32_vs_autograd below, which passed on B200")
 def test_brushnet_whole_branch_forward_backward_fp32_vs_autograd():
     """All 28 taps: BrushNetBranchTrainer in fp32 parity mode against float64 autograd through the oracle's brushnet_forward."""
     from mirrorfusion_b200 import ops
@@ -162,13 +160,8 @@ def test_whole_brushnet_every_parameter_gradient_fp32_vs_autograd():
         assert rel(got, want) < 1e-3, name
 
 
-_PENDING = ("kernel written after the round's GPU budget was spent: it compiles for sm_100a and follows the algorithm pinned on the CPU in "
-            "tests/test_oracle_train.py::test_next_backward_algorithms_match_autograd, but has never run on a GPU")
-
-
 @pytest.mark.timeout(120)
-@pytest.mark.xfail(strict=False, reason=_PENDING)
-def test_pending_layernorm_and_geglu_backward_f32():
+def test_layernorm_and_geglu_backward_f32():
     import numpy as np
     from mirrorfusion_b200 import ops
     from oracle import train_oracle as T
@@ -190,8 +183,7 @@ def test_pending_layernorm_and_geglu_backward_f32():
 
 
 @pytest.mark.timeout(120)
-@pytest.mark.xfail(strict=False, reason=_PENDING)
-def test_pending_attention_backward_f32():
+def test_attention_backward_f32():
     import numpy as np
     from mirrorfusion_b200 import ops
     from oracle import train_oracle as T

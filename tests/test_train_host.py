@@ -122,3 +122,26 @@ def test_brushnet_branch_pack_unpack_roundtrip():
         assert v.shape == sd[k].shape and torch.equal(v, sd[k].float()), k
     missing = [k for k in sd if k not in back]
     assert all(k.startswith(("conv_in_condition.", "time_embedding.")) or ".time_emb_proj." in k for k in missing)
+
+
+def test_unpack_brushnet_round_trip_covers_every_trained_parameter():
+    """the export must be the exact inverse of pack_brushnet over EVERY parameter BrushNetTrainer trains — branch,
+    conv_in_condition (OIHW) and the timestep path (wcat / bcat split back per resnet) — and pass the strict census check."""
+    import torch
+    from mirrorfusion_b200 import checkpoint as CK
+    from mirrorfusion_b200.backward import brushnet_shapes, pack_brushnet, unpack_brushnet
+    from mirrorfusion_b200.config import MICRO
+    from mirrorfusion_b200.synth import make_state_dict
+    from mirrorfusion_b200.train import FlatParams
+    sd = make_state_dict(MICRO, "brushnet", seed=3)
+    flat = FlatParams(brushnet_shapes(MICRO), "cpu", with_bf16=False)
+    flat.load_state_dict(pack_brushnet(MICRO, sd))
+    out = unpack_brushnet(MICRO, flat)
+    CK.check_state_dict(out, MICRO, "brushnet")                 # names and shapes of the reference's BrushNetModel.state_dict()
+    assert set(out) == set(sd)
+    for k, v in sd.items():
+        assert torch.equal(out[k], v), k
+    # a "trained" buffer: every element changed -> every exported tensor changes (nothing is exported from stale copies)
+    flat.param.add_(1.0)
+    out2 = unpack_brushnet(MICRO, flat)
+    assert all(not torch.equal(out2[k], sd[k]) for k in sd)
