@@ -34,7 +34,7 @@ import torch  # noqa: E402
 STEPS_PER_IMAGE = 50
 METRIC = "images_per_s_512x512_50_unipc_steps_cfg7.5"
 # BASELINE.json `configs` presets (index = position in that list): images per GPU, latent side
-CONFIG_PRESETS = {2: (8, 64), 3: (16, 64), 5: (4, 96)}
+CONFIG_PRESETS = {2: (8, 64), 3: (16, 64), 4: (8, 64), 5: (4, 96)}      # 4 = the fine-tune step (--train; batch from --train-batch)
 
 
 def metric_name(latent: int) -> str:
@@ -176,7 +176,7 @@ def gpu_eager_baseline(images: int, latent: int, dev, steps: int = 3, warmup: in
         evs = []
         with torch.no_grad():
             for i in range(warmup + steps):
-                t = sched.timesteps[i]
+                t = torch.as_tensor(sched.timesteps[i]).to(dev)        # the pipeline's timesteps live on the device (:1171)
                 a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 a.record()
                 eps, _ = O.noise_pred_step(usd, bsd, cfg, torch.cat([lat] * 2), t, ehs, cond, 1.0)
@@ -206,6 +206,125 @@ def run_reference(args, rank):
         "cpu_baseline": {"value": r["images_per_s"], "unit": "images/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]},
         "e2e": {"value": r["images_per_s"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
+    }
+    emit_json(line)
+
+
+
+# ----------------------------------------------------------------------------------------------------- config 4: fine-tune step
+TRAIN_METRIC = "samples_per_s_brushnet_finetune_step_512x512_bf16"
+
+
+def run_train(args, rank, world, local_rank):
+    """BASELINE.json configs[3]: one BrushNet-branch fine-tune step (UNet frozen), bf16, `--train-batch` samples per GPU (32), the
+    flat BrushNet gradient all-reduced over NCCL.  A step = add_noise + BrushNet forward + UNet forward + loss + frozen-UNet
+    data-gradient chain + BrushNet backward (data + weight gradients) + all-reduce + clip + AdamW (E/train_brushnet_mirror.py:1404-1466)."""
+    import torch.distributed as dist
+    from mirrorfusion_b200.config import SD15
+    from mirrorfusion_b200.finetune import FineTuneStep
+    from mirrorfusion_b200.synth import make_inputs, make_state_dict
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; mirrorfusion_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    cfg, B, H = SD15, args.train_batch, args.latent
+    ft = FineTuneStep(cfg, make_state_dict(cfg, "unet"), make_state_dict(cfg, "brushnet"), batch=B, H=H, W=H, device=dev, lr=5e-6,
+                      max_grad_norm=1.0)
+    g = torch.Generator().manual_seed(1000 + rank)                   # every rank trains on its own samples
+    inp = make_inputs(cfg, B, seed=77 + rank, height=H, width=H, cfg_duplicate=False)
+    host = {"latents": torch.randn(B, 4, H, H, generator=g) * 0.8, "noise": torch.randn(B, 4, H, H, generator=g),
+            "cond": inp["conditioning_latents"].contiguous(), "ehs": inp["prompt_embeds"].contiguous()}
+    host = {k: v.pin_memory() for k, v in host.items()}
+    tsteps = [torch.randint(0, 1000, (B,), generator=g).pin_memory() for _ in range(8)]
+    d = {k: v.to(dev) for k, v in host.items()}
+    stream = torch.cuda.current_stream()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def one_step(i):
+        return ft.step(d["latents"], d["noise"], tsteps[i % len(tsteps)], d["cond"], d["ehs"])
+
+    for i in range(args.warmup):
+        one_step(i)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for i in range(args.steps):
+        loss = one_step(args.warmup + i)
+    e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    if world > 1:
+        tmax = torch.tensor([ms], device=dev)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        ms = tmax.item()
+    ms_per_step = ms / args.steps
+    value = world * B / (ms_per_step * 1e-3)
+    # end to end: every step's batch comes from pinned host memory, the loss goes back to the host
+    h2d = sum(v.numel() * 4 for v in host.values()) + B * 8
+    loss_host = torch.zeros(1).pin_memory()
+
+    def e2e_step(i):
+        for k in d:
+            d[k].copy_(host[k], non_blocking=True)
+        l = ft.step(d["latents"], d["noise"], tsteps[i % len(tsteps)], d["cond"], d["ehs"])
+        loss_host.copy_(l, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    e2e_step(0)
+    barrier()
+    t0 = time.perf_counter()
+    n_e2e = max(2, args.steps // 2)
+    for i in range(n_e2e):
+        e2e_step(i)
+    barrier()
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / n_e2e
+    if world > 1:
+        tmax = torch.tensor([e2e_ms], device=dev)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        e2e_ms = tmax.item()
+    # phase split (rank 0, one extra step, CUDA events)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    ev[0].record(stream)
+    ft.forward(d["latents"], d["noise"], tsteps[0], d["cond"], d["ehs"])
+    ev[1].record(stream)
+    ft.backward()
+    ev[2].record(stream)
+    ft.optimize()
+    ev[3].record(stream)
+    barrier()
+    if rank != 0:
+        return
+    peaks = load_peaks()
+    flops = ft.flops_per_step
+    tf = flops / (ms_per_step * 1e-3) / 1e12
+    line = {
+        "metric": TRAIN_METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": f"BrushNet-branch fine-tune step (SD1.5 UNet frozen), {8 * H}x{8 * H}, batch {B}/GPU, bf16 kernels + fp32 "
+                               "master weights, clip 1.0 + AdamW, NCCL all-reduce of the 618.8 M BrushNet gradients, random-init weights",
+                   "batch_per_gpu": B, "latent": f"{H}x{H}", "parallelism": f"dp{world} (replicas; one flat-gradient all-reduce per step)",
+                   "cuda_graph": False, "trainable_params": int(ft.flat.numel),
+                   "l2": "inputs larger than L2: >10 GB of activations and 3.7 GB of weights stream per step (L2 = 126 MB)"},
+        "clocks": clocks,
+        "e2e": {"value": world * B / (e2e_ms * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                "ms_per_step": e2e_ms},
+        "gpu_launches": None,
+        "roofline": {"bound": "tensor", "kernel": "whole step (igemm forward / data-gradient plans, wgrad, attention forward / backward)",
+                     "achieved": tf, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s", "frac": tf / peaks["bf16_sustained"],
+                     "frac_vs_burst": tf / peaks["bf16_burst"], "peak_source": peaks["source"] + ", sustained bf16", "traffic": None,
+                     "algorithmic_flops_per_step": flops,
+                     "phases_ms": {"forward": ev[0].elapsed_time(ev[1]), "backward": ev[1].elapsed_time(ev[2]),
+                                   "allreduce_clip_adamw_refresh": ev[2].elapsed_time(ev[3])}},
+        "cpu_baseline": None,
+        "loss": float(loss.item()), "max_memory_gb": torch.cuda.max_memory_allocated() / 2 ** 30,
     }
     emit_json(line)
 
@@ -497,6 +616,8 @@ def main():
                     help="BASELINE.json configs preset: 2 = 8 images/GPU at 64x64 (default workload), 3 = 16 images/GPU (the sharded "
                          "eval sweep's per-GPU load), 5 = 768x768 (96x96 latents, 9216-token attention) batch 4")
     ap.add_argument("--no-eager-baseline", action="store_true", help="skip the secondary gpu_eager_baseline measurement")
+    ap.add_argument("--train", action="store_true", help="BASELINE.json configs[3]: time the BrushNet fine-tune step instead of the denoise step")
+    ap.add_argument("--train-batch", type=int, default=32, help="samples per GPU per fine-tune step (config 4: 32)")
     args = ap.parse_args()
     if args.config is not None:
         args.images, args.latent = CONFIG_PRESETS[args.config]
@@ -513,7 +634,10 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     try:
-        run_ours(args, rank, world, local_rank)
+        if args.train or args.config == 4:
+            run_train(args, rank, world, local_rank)
+        else:
+            run_ours(args, rank, world, local_rank)
     finally:
         if world > 1:
             import torch.distributed as dist

@@ -278,7 +278,7 @@ int mfb_rowsum_per_image(const void* dy, int dtype, int B, int HW, int C, float*
 int mfb_silu_bwd(const float* x, const void* dy, int dy_dtype, float* y, float* dx, long long n, void* stream);
 
 /* fp32 parity-mode backward of the three ops the frozen UNet's data-gradient chain adds (BASELINE config 4): CUDA-core correctness
- * instruments written to the algorithms pinned in oracle/train_oracle.py.  NOT YET RUN ON A GPU (round 1); the tensor-core versions follow.
+ * instruments written to the algorithms pinned in oracle/train_oracle.py.  Verified on B200 (tests/test_gpu_zz_train_net.py); the bf16 product-path versions are below.
  * mfb_attention_bwd_f32: backward of F.scaled_dot_product_attention (S/models/attention_processor.py:1266-1268), same tensor layout as
  *   mfb_attention_f32 (head h at columns [h*d, (h+1)*d)); two deterministic passes (per query: L, D = dO.O, dq; per key: dk, dv);
  *   stats_ws: 2 * B * heads * Tq floats.  head_dim <= 160.
@@ -290,6 +290,45 @@ int mfb_attention_bwd_f32(const float* q, int ldq, const float* k, int ldk, cons
                           void* stream);
 int mfb_layernorm_bwd_f32(const float* x, const float* dy, int rows, int C, float eps, const float* gamma, float* dx, void* stream);
 int mfb_geglu_f32(const float* proj, long long rows, int C, float* out, const float* d_out, float* d_proj, void* stream);
+
+/* ---- bf16 backward of the bandwidth-bound ops (BASELINE config 4; csrc/train_bf16.cu): what autograd runs under accelerator.backward
+ * (E/train_brushnet_mirror.py:1459) for the ops below.  All tensors bf16 channels-last unless noted; fp32 math; deterministic.
+ * mfb_groupnorm_stats: stats_ws[0 : 2*B*groups] = per-(image, group) {sum, sum of squares} of the (two-source) input — the forward
+ *   statistics pass alone (workspace contract of mfb_groupnorm); the backward below reads them.
+ * mfb_groupnorm_bwd2: backward of F.group_norm (+ F.silu if silu) (S/models/resnet.py:337-338,381,393; transformer_2d.py:338; eps per
+ *   call site), two-source concat like mfb_groupnorm.  dx1 / dx2 per source; dres / dres2 ([B, HW, C1+C2], may be NULL): gradients
+ *   arriving over residual / skip paths, added in the same pass (S/models/resnet.py:403; the UNet's skip fan-out).  dgamma / dbeta
+ *   [C] fp32 (NULL for a frozen layer), accumulate != 0 adds to them.  ws: mfb_groupnorm_bwd2_ws_floats(B, C, groups) floats, zero on
+ *   first use (ticket counters).  Two vectorised passes (per-channel sums -> group means; dx).
+ * mfb_layernorm_bwd: data gradient of F.layer_norm over the last dim (S/models/attention.py:313,360,386) + optional residual-path
+ *   gradient dres [rows, C] (the transformer's `+ hidden_states`, :330,372,409).
+ * mfb_geglu: un-fused GEGLU on proj [rows, 2C] = [h | gate] (S/models/activations.py:100-103): out [rows, C] = h * gelu_erf(gate) if
+ *   out != NULL; d_proj [rows, 2C] from d_out [rows, C] if d_proj != NULL (training keeps proj for the backward).
+ * mfb_conv_out_bwd: data gradient of conv_out (3x3, Cin -> Cout, S/models/unets/unet_2d_condition.py:1339): dy fp32 NCHW
+ *   [B, Cout, H, W] (d loss / d model_pred, from mfb_mse_loss), w fp32 [Cout, 3, 3, Cin] (the layout mfb_conv_out reads),
+ *   dx bf16 [B, H*W, Cin]. */
+/* mfb_attention_lse: mfb_attention that also writes lse [B, heads, Tq] fp32 = log2 sum_j 2^(q_i.k_j * d^-1/2 * log2 e), kept for the backward.
+ * mfb_attention_bwd: backward of F.scaled_dot_product_attention (S/models/attention_processor.py:1266-1268) on tcgen05, flash style
+ *   (csrc/attn_bwd.cu): q / k / v / o / d_o bf16 in the layouts of mfb_attention (leading dimensions in elements, head h at columns
+ *   [h*d, (h+1)*d)); lse from the forward; dvec [B, heads, Tq] fp32 scratch (D = dO . O, written here); dq always; dk / dv both or
+ *   neither (NULL: cross attention to a frozen context, only the query-side kernel runs).  Deterministic: every output element
+ *   has one writer. */
+int mfb_attention_lse(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* out, int ldo, int B, int heads,
+                      int head_dim, int Tq, int Tk, float* lse, void* stream);
+int mfb_attention_bwd(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, const void* o, int ldo, const void* d_o,
+                      int lddo, const float* lse, float* dvec, void* dq, int lddq, void* dk, int lddk, void* dv, int lddv, int B,
+                      int heads, int head_dim, int Tq, int Tk, void* stream);
+long long mfb_groupnorm_bwd2_ws_floats(int B, int C, int groups);
+int mfb_groupnorm_stats(const void* x1, int C1, const void* x2, int C2, int B, int HW, int groups, float* stats_ws, void* stream);
+int mfb_groupnorm_bwd2(const void* x1, int C1, const void* x2, int C2, const void* dy, int B, int HW, int groups, float eps,
+                       const float* gamma, const float* beta, int silu, const float* stats, const void* dres, const void* dres2,
+                       void* dx1, void* dx2, float* dgamma, float* dbeta, float* ws, int accumulate, void* stream);
+int mfb_layernorm_bwd(const void* x, const void* dy, int rows, int C, float eps, const float* gamma, const void* dres, void* dx,
+                      void* stream);
+int mfb_geglu(const void* proj, long long rows, int C, void* out, const void* d_out, void* d_proj, void* stream);
+int mfb_conv_out_bwd(const float* dy, int B, int H, int W, int Cin, int Cout, const float* w, void* dx, void* stream);
+/* Adjoint of Upsample2D's nearest-x2 replication (S/models/upsampling.py:167-173): dx [B, H*W, C] = 2x2 sums of du [B, 2H*2W, C] (bf16). */
+int mfb_sumpool2x2(const void* du, int B, int H, int W, int C, void* dx, void* stream);
 
 #ifdef __cplusplus
 }

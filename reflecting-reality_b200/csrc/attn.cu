@@ -96,6 +96,7 @@ struct AttParams {
     int ldo;
     int Tq, Tk, heads;
     float scale_log2;  // head_dim^-0.5 * log2(e)
+    float* lse;        // optional [B, heads, Tq]: log2 sum_j 2^(s_ij) of every query row (kept for the backward pass, attn_bwd.cu)
 };
 
 __device__ __forceinline__ float ex2f(float x) {
@@ -382,6 +383,7 @@ __global__ void __launch_bounds__(AttCfg<D, SHORT>::THREADS, AttCfg<D, SHORT>::C
         tc_fence_after();
         const float inv_l = 1.f / l;
         const int qrow = q0 + t * BQ + r;
+        if (p.lse != nullptr && qrow < p.Tq) p.lse[(static_cast<size_t>(b) * p.heads + h) * p.Tq + qrow] = m_used + log2f(l);
         __nv_bfloat16* dst = p.out + (static_cast<size_t>(b) * p.Tq + qrow) * p.ldo + h * D;
 #pragma unroll
         for (int c = 0; c < DPAD / 16; ++c) {
@@ -432,8 +434,8 @@ static int launch_attention(const AttParams& p, int B, bool short_kv, cudaStream
 
 using namespace mfb;
 
-extern "C" int mfb_attention(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* out, int ldo,
-                             int B, int heads, int head_dim, int Tq, int Tk, void* stream) {
+static int attention_impl(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* out, int ldo, int B, int heads,
+                          int head_dim, int Tq, int Tk, float* lse, void* stream) {
     MFB_REQUIRE(q && k && v && out, "null pointer");
     MFB_REQUIRE(ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 && ldo % 8 == 0, "leading dimensions must be multiples of 8");
     MFB_REQUIRE(Tq > 0 && Tk > 0, "bad sequence lengths");
@@ -479,6 +481,7 @@ extern "C" int mfb_attention(const void* q, int ldq, const void* k, int ldk, con
     p.Tk = Tk;
     p.heads = heads;
     p.scale_log2 = 1.4426950408889634f / sqrtf(static_cast<float>(head_dim));
+    p.lse = lse;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     switch (head_dim) {
         case 32: return launch_attention<32>(p, B, short_kv, st);
@@ -490,4 +493,16 @@ extern "C" int mfb_attention(const void* q, int ldq, const void* k, int ldk, con
             set_error("head_dim %d is not instantiated (supported: 32, 40, 64, 80, 160)", head_dim);
             return MFB_EINVAL;
     }
+}
+
+extern "C" int mfb_attention(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* out, int ldo, int B, int heads,
+                             int head_dim, int Tq, int Tk, void* stream) {
+    return attention_impl(q, ldq, k, ldk, v, ldv, out, ldo, B, heads, head_dim, Tq, Tk, nullptr, stream);
+}
+
+// Forward for training: same kernel, and the per-row log-sum-exp (log2 domain, scale folded in) the backward needs.
+extern "C" int mfb_attention_lse(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* out, int ldo, int B,
+                                 int heads, int head_dim, int Tq, int Tk, float* lse, void* stream) {
+    MFB_REQUIRE(lse, "null lse");
+    return attention_impl(q, ldq, k, ldk, v, ldv, out, ldo, B, heads, head_dim, Tq, Tk, lse, stream);
 }

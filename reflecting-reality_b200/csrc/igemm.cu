@@ -68,9 +68,10 @@ struct IgemmParams {
     __nv_bfloat16* out;    // [M, out_ld]
     int out_ld;
     int geglu;             // BN == 128 only: cols [0,64) value, [64,128) gate -> out[:, nt*64 + j]
-    float* stats;          // optional per-(image, tile, channel) {sum, sumsq} of the bf16 OUTPUT (GroupNorm statistics of the
-                           // consumer, fused here): [Bn][stats_tiles][out_ld][2]; null = off
-    int stats_tiles, stats_tile_base;
+    float* stats;          // optional per-(image, slot, channel) {sum, sumsq} of the bf16 OUTPUT (GroupNorm statistics of the
+                           // consumer, fused here): [Bn][stats_tiles][out_ld][2]; a slot = one epilogue warp's 32 rows of a tile; null = off
+    int stats_tiles, stats_tile_base;   // slots per image; first slot of this launch (sub-pixel phases)
+    int stats_rows_img;                 // tn > 1 (a tile spans whole images): rows per image (tw * th, a multiple of 32)
     int o_step, o_py, o_px, o_Hf, o_Wf;   // rows map to output pixel (o_step*oh + o_py, o_step*ow + o_px) of [Bn, o_Hf, o_Wf]
     int stages;            // operand ring depth actually used (<= IgemmCfg::STAGES)
     int nstg;              // staging tiles: 1, or 2 = double-buffered epilogue (short-K launches, see igemm_kernel)
@@ -127,6 +128,23 @@ __device__ __forceinline__ uint4 pack_bf16x8(const float (&f)[8]) {
     o.z = pack_bf16x2(f[4], f[5]);
     o.w = pack_bf16x2(f[6], f[7]);
     return o;
+}
+
+// Column sums of a 32-row x 16-column register block (one row per lane): a transposing butterfly — at every level a lane keeps
+// half of its columns and hands the other half to its partner, so 8 + 4 + 2 + 1 + 1 = 16 shuffles reduce 16 columns over 32 rows
+// (a plain per-column xor-reduction would take 80).  On return every lane pair (l, l^1) holds the sum of column l >> 1.
+__device__ __forceinline__ float colsum16(const float (&x)[16], int lane) {
+    const unsigned full = 0xffffffffu;
+    float a8[8], a4[4], a2[2];
+    const bool h4 = (lane & 16) != 0, h3 = (lane & 8) != 0, h2 = (lane & 4) != 0, h1 = (lane & 2) != 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a8[i] = (h4 ? x[8 + i] : x[i]) + __shfl_xor_sync(full, h4 ? x[i] : x[8 + i], 16);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) a4[i] = (h3 ? a8[4 + i] : a8[i]) + __shfl_xor_sync(full, h3 ? a8[i] : a8[4 + i], 8);
+#pragma unroll
+    for (int i = 0; i < 2; ++i) a2[i] = (h2 ? a4[2 + i] : a4[i]) + __shfl_xor_sync(full, h2 ? a4[i] : a4[2 + i], 4);
+    const float a1 = (h1 ? a2[1] : a2[0]) + __shfl_xor_sync(full, h1 ? a2[0] : a2[1], 2);
+    return a1 + __shfl_xor_sync(full, a1, 1);
 }
 
 // Walks the tile sequence tile0, tile0 + step, ... of one CTA without per-tile integer divisions: the position is kept
@@ -453,12 +471,17 @@ __global__ void __launch_bounds__(64 + 32 * EPIW, 1) igemm_kernel(const __grid_c
                     if (i < c_cnt) tmem_ld16(trow + (c_begin + i) * 16, v[i]);
                 release_acc();
                 if (p.res1) mbar_wait_relaxed(res_full_bar, li & 1);
+                // fused output statistics: which (image, slot) this warp's 32 rows belong to
+                const bool do_stats = p.stats != nullptr;
+                const int stat_img = p.tn == 1 ? n0 : n0 + (q * 32) / p.stats_rows_img;
+                const int stat_slot = p.stats_tile_base + (p.tn == 1 ? (mt % (p.tiles_w * p.tiles_h)) * 4 + q : ((q * 32) % p.stats_rows_img) >> 5);
                 auto body = [&](auto res1_c, auto extra_c) {
                     constexpr bool RES1 = decltype(res1_c)::value, EXTRA = decltype(extra_c)::value;
 #pragma unroll
                     for (int i = 0; i < MAXC; ++i) {
                         if (i < c_cnt) {
                             const int col = (c_begin + i) * 16;
+                            float xs[16];
 #pragma unroll
                             for (int j = 0; j < 2; ++j) {
                                 uint4* sp = reinterpret_cast<uint4*>(stg_g + stg_off<BOXC>(r, col + j * 8));
@@ -484,7 +507,32 @@ __global__ void __launch_bounds__(64 + 32 * EPIW, 1) igemm_kernel(const __grid_c
                                 } else if constexpr (RES1) {
                                     add_bf16x8(f, *sp);
                                 }
-                                *sp = pack_bf16x8(f);
+                                const uint4 pk = pack_bf16x8(f);
+                                *sp = pk;
+                                if (do_stats) {        // the ROUNDED values, as a separate statistics pass over the tensor would see them
+                                    float2 t2;
+                                    t2 = unpack_bf16x2(pk.x); xs[j * 8 + 0] = t2.x; xs[j * 8 + 1] = t2.y;
+                                    t2 = unpack_bf16x2(pk.y); xs[j * 8 + 2] = t2.x; xs[j * 8 + 3] = t2.y;
+                                    t2 = unpack_bf16x2(pk.z); xs[j * 8 + 4] = t2.x; xs[j * 8 + 5] = t2.y;
+                                    t2 = unpack_bf16x2(pk.w); xs[j * 8 + 6] = t2.x; xs[j * 8 + 7] = t2.y;
+                                }
+                            }
+                            if (do_stats) {
+                                // Fused GroupNorm statistics from the epilogue REGISTERS: per-column sum / sum of squares over this
+                                // warp's 32 rows (rows outside the tensor contribute zero), written — not accumulated — to the warp's
+                                // own slot, so the consumer's reduction order is fixed (deterministic) and no barrier or shared-memory
+                                // round trip is added to the tile.
+                                float sq16[16];
+#pragma unroll
+                                for (int e = 0; e < 16; ++e) {
+                                    xs[e] = valid ? xs[e] : 0.f;
+                                    sq16[e] = xs[e] * xs[e];
+                                }
+                                const float csum = colsum16(xs, lane), csq = colsum16(sq16, lane);
+                                const int nn = nt * BN + col + (lane >> 1);
+                                if ((lane & 1) == 0 && stat_img < p.Bn && nn < p.out_ld)
+                                    reinterpret_cast<float2*>(p.stats)[(static_cast<size_t>(stat_img) * p.stats_tiles + stat_slot) * p.out_ld + nn] =
+                                        make_float2(csum, csq);
                             }
                         }
                     }
@@ -532,32 +580,6 @@ __global__ void __launch_bounds__(64 + 32 * EPIW, 1) igemm_kernel(const __grid_c
             }
             fence_proxy_async_smem();                  // generic-proxy writes of the staging tile -> visible to TMA
             named_bar_sync(1, IGEMM_EPI_WARPS * 32);
-            if (p.stats != nullptr && int(threadIdx.x) < bn_out && nt * bn_out + int(threadIdx.x) < p.out_ld) {
-                // Fused GroupNorm statistics: thread = output channel; sum / sum-of-squares of the ROUNDED (bf16) values of
-                // this tile's valid rows, per image, read back from the staging tile.  Written (not accumulated) to a
-                // per-(image, tile) slot, so the consumer's reduction order is fixed -> deterministic.
-                const int c = threadIdx.x;
-                const int vw = min(p.tw, p.Wo - w0), vh = min(p.th, p.Ho - h0), vn = min(p.tn, p.Bn - n0);
-                const int tile_in_img = (p.tn == 1 ? mt % (p.tiles_w * p.tiles_h) : 0) + p.stats_tile_base;
-                const uint8_t* colp = stg_g + (c & 7) * 2;
-                for (int in_ = 0; in_ < vn; ++in_) {
-                    float sm = 0.f, sq = 0.f;
-                    for (int ih = 0; ih < vh; ++ih) {
-                        const int rbase = (in_ * p.th + ih) * p.tw;
-                        for (int iw = 0; iw < vw; ++iw) {
-                            const float v = __bfloat162float(
-                                *reinterpret_cast<const __nv_bfloat16*>(colp + stg_off<BOXC>(rbase + iw, c & ~7)));
-                            sm += v;
-                            sq = fmaf(v, v, sq);
-                        }
-                    }
-                    float2* dst = reinterpret_cast<float2*>(p.stats) +
-                                  (static_cast<size_t>(n0 + in_) * p.stats_tiles + tile_in_img) * p.out_ld + nt * bn_out + c;
-                    *dst = make_float2(sm, sq);
-                }
-            }
-            // the next tile's res1 TMA load overwrites the staging tile: nobody may still be reading it
-            if (p.stats != nullptr) named_bar_sync(1, IGEMM_EPI_WARPS * 32);
             if (leader) {
                 for (int bx = 0; bx < nbox; ++bx)
                     tma_store_4d(&p.tmOut, stg_b + bx * (BM * BOXC * 2), nt * bn_out + bx * BOXC, w0, h0, n0);
@@ -773,16 +795,20 @@ static int build_params(const mfb_conv_desc* d, int up_py, int up_px, const void
         }
     }
     {
-        // fused output statistics are available when every tile belongs to ONE image, or one tile covers whole images
+        // fused output statistics: every epilogue warp (32 rows of a tile) must lie in ONE image: tiles inside an image
+        // (tn == 1), or tiles of whole images whose pixel count is a multiple of 32.  A slot = one warp's rows: 4 per tile.
         const int per_img = p.tiles_w * p.tiles_h;
-        const bool ok = !d->geglu && (p.tn == 1 || per_img == 1);
+        const int rows_img = p.tw * p.th;
+        const bool ok = !d->geglu && (p.tn == 1 || (per_img == 1 && rows_img % 32 == 0));
         const int nphase = up ? 4 : 1;
-        pl->stats_tiles = ok ? per_img * nphase : 0;
+        const int slots = p.tn == 1 ? per_img * 4 : rows_img / 32;
+        pl->stats_tiles = ok ? slots * nphase : 0;
         pl->stats_C = d->Cout;
         pl->stats_B = B;
         p.stats = nullptr;
         p.stats_tiles = pl->stats_tiles;
-        p.stats_tile_base = up ? (up_py * 2 + up_px) * per_img : 0;
+        p.stats_tile_base = up ? (up_py * 2 + up_px) * slots : 0;
+        p.stats_rows_img = rows_img;
     }
     p.bias = d->bias;
     p.rowbias = d->rowbias;

@@ -155,39 +155,55 @@ __global__ void gn_stats_kernel(const __nv_bfloat16* __restrict__ x1, int C1, co
     }
 }
 
-// Statistics already produced by the igemm epilogue as per-(image, tile, channel) partials: reduce them to
-// stats[b][g] in a fixed order.  grid (B), block (8 lanes x groups): lane j of group g takes every 8th (channel, tile)
-// pair of the group, then the 8 partials are added in lane order.
-__global__ void gn_finalize_kernel(const float2* __restrict__ part1, int C1, int tiles1, const float2* __restrict__ part2, int C2,
-                                   int tiles2, int groups, float* __restrict__ stats) {
-    __shared__ float2 red[64 * 8];
+// Statistics already produced by the igemm epilogue as per-(image, slot, channel) partials (a slot = the 32 rows of one epilogue
+// warp): reduce them to stats[b][g].  grid (groups, B), block 128: thread t takes the (slot, channel) pairs t, t + 128, ... of the
+// group (channels of the first source, then of the second: a group of a concat may straddle both), then the 128 partials are
+// added by a fixed binary tree -> deterministic.
+__global__ void __launch_bounds__(128) gn_finalize_kernel(const float2* __restrict__ part1, int C1, int tiles1,
+                                                          const float2* __restrict__ part2, int C2, int tiles2, int groups,
+                                                          float* __restrict__ stats) {
+    __shared__ float2 red[128];
     pdl_trigger();
     pdl_wait();
-    const int b = blockIdx.x;
-    const int g = threadIdx.x >> 3, j = threadIdx.x & 7;
+    const int g = blockIdx.x, b = blockIdx.y, t = threadIdx.x;
     const int C = C1 + C2, cpg = C / groups;
+    const int lo = g * cpg, hi = lo + cpg;
     float sm = 0.f, sq = 0.f;
-    if (g < groups) {
-        for (int ci = j; ci < cpg; ci += 8) {
-            const int c = g * cpg + ci;
-            const float2* src;
-            int tiles, Cs, cc;
-            if (c < C1) { src = part1; tiles = tiles1; Cs = C1; cc = c; } else { src = part2; tiles = tiles2; Cs = C2; cc = c - C1; }
-            const float2* pb = src + static_cast<size_t>(b) * tiles * Cs + cc;
-            for (int t = 0; t < tiles; ++t) {
-                const float2 v = __ldcg(pb + static_cast<size_t>(t) * Cs);
+    {   // channels [lo, min(hi, C1)) of source 1
+        const int n = min(hi, C1) - lo;
+        if (n > 0) {
+            const float2* pb = part1 + static_cast<size_t>(b) * tiles1 * C1 + lo;
+            for (int i = t; i < n * tiles1; i += 128) {
+                const float2 v = __ldcg(pb + static_cast<size_t>(i / n) * C1 + (i % n));
                 sm += v.x;
                 sq += v.y;
             }
         }
-        red[threadIdx.x] = make_float2(sm, sq);
     }
+    {   // channels [max(lo, C1), hi) of source 2
+        const int l2 = max(lo, C1), n = hi - l2;
+        if (n > 0 && C2 > 0) {
+            const float2* pb = part2 + static_cast<size_t>(b) * tiles2 * C2 + (l2 - C1);
+            for (int i = t; i < n * tiles2; i += 128) {
+                const float2 v = __ldcg(pb + static_cast<size_t>(i / n) * C2 + (i % n));
+                sm += v.x;
+                sq += v.y;
+            }
+        }
+    }
+    red[t] = make_float2(sm, sq);
     __syncthreads();
-    if (g < groups && j == 0) {
-        float a = 0.f, q2 = 0.f;
-        for (int k = 0; k < 8; ++k) { a += red[g * 8 + k].x; q2 += red[g * 8 + k].y; }
-        stats[(static_cast<size_t>(b) * groups + g) * 2 + 0] = a;
-        stats[(static_cast<size_t>(b) * groups + g) * 2 + 1] = q2;
+#pragma unroll
+    for (int o = 64; o > 0; o >>= 1) {
+        if (t < o) {
+            red[t].x += red[t + o].x;
+            red[t].y += red[t + o].y;
+        }
+        __syncthreads();
+    }
+    if (t == 0) {
+        stats[(static_cast<size_t>(b) * groups + g) * 2 + 0] = red[0].x;
+        stats[(static_cast<size_t>(b) * groups + g) * 2 + 1] = red[0].y;
     }
 }
 
@@ -556,7 +572,7 @@ static int groupnorm_impl(const void* x1, int C1, const void* x2, int C2, int B,
     dim3 grid(chunks, B), block(CV, PY);
     if (part1 != nullptr && (C2 == 0 || part2 != nullptr)) {
         // statistics came with the producing GEMM(s): only the tiny fixed-order reduction is left
-        MFB_CUDA_OK(launch_k(gn_finalize_kernel, dim3(B), dim3(8 * groups), 0, st, 1, reinterpret_cast<const float2*>(part1), C1, tiles1,
+        MFB_CUDA_OK(launch_k(gn_finalize_kernel, dim3(groups, B), dim3(128), 0, st, 1, reinterpret_cast<const float2*>(part1), C1, tiles1,
                              reinterpret_cast<const float2*>(part2), C2, tiles2, groups, stats_ws));
     } else {
         MFB_CUDA_OK(launch_k(gn_stats_kernel, grid, block, 0, st, 1, static_cast<const __nv_bfloat16*>(x1), C1,
@@ -565,6 +581,35 @@ static int groupnorm_impl(const void* x1, int C1, const void* x2, int C2, int B,
     MFB_CUDA_OK(launch_k(gn_apply_kernel, dim3(chunks_apply, B), block, 0, st, 1, static_cast<const __nv_bfloat16*>(x1), C1,
                          static_cast<const __nv_bfloat16*>(x2), C2, HW, groups, ppc_apply, static_cast<const float*>(stats_ws), eps, gamma,
                          beta, silu, static_cast<__nv_bfloat16*>(out)));
+    return MFB_OK;
+}
+
+// Statistics only: stats_ws[0 : 2*B*groups] = per-(image, group) {sum, sum of squares} (the layout gn_apply_kernel and the
+// GroupNorm backward read); same workspace contract as mfb_groupnorm.  Used by the training path, whose backward needs them.
+extern "C" int mfb_groupnorm_stats(const void* x1, int C1, const void* x2, int C2, int B, int HW, int groups, float* stats_ws,
+                                   void* stream) {
+    MFB_REQUIRE(x1 && stats_ws, "null pointer");
+    if (!x2) C2 = 0;
+    const int C = C1 + C2;
+    MFB_REQUIRE(C1 % 8 == 0 && C2 % 8 == 0 && groups > 0 && groups <= 64 && C % groups == 0 && (C / groups >= 8 || C / groups == 4),
+                "unsupported group size (C=%d groups=%d)", C, groups);
+    const int CV = C / 8;
+    MFB_REQUIRE(CV <= 1024, "C too large");
+    const int PY = CV >= 256 ? 1 : 256 / CV;
+    int resident = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, gn_stats_kernel, CV * PY, 0) != cudaSuccess || resident < 1) resident = 2;
+    int chunks = (resident * device_sm_count()) / B;
+    const int max_chunks = (HW + 4 * PY - 1) / (4 * PY);
+    if (chunks > max_chunks) chunks = max_chunks;
+    if (chunks > MFB_GN_MAX_CHUNKS) chunks = MFB_GN_MAX_CHUNKS;
+    if (chunks < 1) chunks = 1;
+    const int ppc = (HW + chunks - 1) / chunks;
+    chunks = (HW + ppc - 1) / ppc;
+    float* part = stats_ws + static_cast<size_t>(2) * B * groups;
+    unsigned int* counters = reinterpret_cast<unsigned int*>(part + static_cast<size_t>(2) * B * groups * MFB_GN_MAX_CHUNKS);
+    MFB_CUDA_OK(launch_k(gn_stats_kernel, dim3(chunks, B), dim3(CV, PY), 0, static_cast<cudaStream_t>(stream), 1,
+                         static_cast<const __nv_bfloat16*>(x1), C1, static_cast<const __nv_bfloat16*>(x2), C2, HW, groups, ppc, stats_ws,
+                         part, counters));
     return MFB_OK;
 }
 

@@ -77,7 +77,17 @@ _SIGS = {
     "mfb_groupnorm_bwd": (i32, [vp, i32, vp, i32, vp, i32, i32, i32, i32, f32, vp, vp, i32, vp, vp, vp, vp, vp, vp, i32, vp]),
     "mfb_rowsum_per_image": (i32, [vp, i32, i32, i32, i32, vp, vp]),
     "mfb_silu_bwd": (i32, [vp, vp, i32, vp, vp, i64, vp]),
-    # fp32 parity-mode backward of attention / LayerNorm / GEGLU (not yet run on a GPU)
+    # bf16 backward of the bandwidth-bound ops (csrc/train_bf16.cu)
+    "mfb_attention_lse": (i32, [vp, i32, vp, i32, vp, i32, vp, i32, i32, i32, i32, i32, i32, vp, vp]),
+    "mfb_attention_bwd": (i32, [vp, i32, vp, i32, vp, i32, vp, i32, vp, i32, vp, vp, vp, i32, vp, i32, vp, i32, i32, i32, i32, i32, i32, vp]),
+    "mfb_groupnorm_bwd2_ws_floats": (i64, [i32, i32, i32]),
+    "mfb_groupnorm_stats": (i32, [vp, i32, vp, i32, i32, i32, i32, vp, vp]),
+    "mfb_groupnorm_bwd2": (i32, [vp, i32, vp, i32, vp, i32, i32, i32, f32, vp, vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, i32, vp]),
+    "mfb_layernorm_bwd": (i32, [vp, vp, i32, i32, f32, vp, vp, vp, vp]),
+    "mfb_geglu": (i32, [vp, i64, i32, vp, vp, vp, vp]),
+    "mfb_conv_out_bwd": (i32, [vp, i32, i32, i32, i32, i32, vp, vp, vp]),
+    "mfb_sumpool2x2": (i32, [vp, i32, i32, i32, i32, vp, vp]),
+    # fp32 parity-mode backward of attention / LayerNorm / GEGLU
     "mfb_attention_bwd_f32": (i32, [vp, i32, vp, i32, vp, i32, vp, i32, vp, i32, vp, i32, vp, i32, vp, i32, i32, i32, i32, i32, vp]),
     "mfb_layernorm_bwd_f32": (i32, [vp, vp, i32, i32, f32, vp, vp, vp]),
     "mfb_geglu_f32": (i32, [vp, i64, i32, vp, vp, vp, vp]),

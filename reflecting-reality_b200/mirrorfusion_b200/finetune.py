@@ -1,0 +1,100 @@
+"""One BrushNet-branch fine-tune step (UNet frozen) on the kernels — BASELINE config 4, the loop body of
+E/train_brushnet_mirror.py:1404-1466:
+
+    noisy = noise_scheduler.add_noise(latents, noise, timesteps)                                   (:1416)
+    down, mid, up = brushnet(noisy, timesteps, ehs, brushnet_cond=conditioning_latents)            (MirrorFusionModel.forward :836-888)
+    model_pred = unet(noisy, timesteps, ehs, down_block_add_samples=..., mid_..., up_...)
+    loss = F.mse_loss(model_pred.float(), noise.float())                                           (:1433-1450, optional min-SNR weights)
+    accelerator.backward(loss)      -> frozen-UNet data-gradient chain -> 28 tap gradients -> every BrushNet gradient; DDP all-reduce
+    clip_grad_norm_; optimizer.step(); lr_scheduler.step(); optimizer.zero_grad()                  (:1460-1466)
+
+= `BrushNetTrainer` (backward.py) + `FrozenUNetTrainer` (unet_train.py) + the glue of train.py, with the flat gradient buffer
+all-reduced over NCCL in large contiguous buckets (sharding.allreduce_flat_grads; SUM, the 1 / world mean is the optimizer
+kernel's `grad_scale`).  Data parallel: every rank holds a full replica and its own `batch` samples; the only collective is that
+all-reduce.  bf16 tensor-core kernels with fp32 master weights (the reference's `--mixed_precision bf16` autocast + fp32 params).
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional
+
+import torch
+
+from . import ops, sharding
+from .backward import BrushNetTrainer, brushnet_shapes, pack_brushnet, unpack_brushnet
+from .config import NetConfig
+from .train import B200AdamW, FlatParams, LRSchedule, NoiseSchedule, TrainLoss
+from .unet_train import FrozenUNetTrainer
+
+f32 = torch.float32
+
+
+class FineTuneStep:
+    def __init__(self, cfg: NetConfig, unet_sd: Dict[str, torch.Tensor], brushnet_sd: Dict[str, torch.Tensor], *, batch: int, H: int,
+                 W: int, device="cuda", lr: float = 5e-6, betas=(0.9, 0.999), weight_decay: float = 1e-2, eps: float = 1e-8,
+                 max_grad_norm: Optional[float] = 1.0, lr_schedule: str = "constant", lr_warmup_steps: int = 0, max_train_steps: int = 0,
+                 snr_gamma: Optional[float] = None, ctx_len: int = 77, group=None):
+        ops.lib()
+        self.cfg, self.B, self.H, self.W, self.dev = cfg, batch, H, W, torch.device(device)
+        self.group, self.max_grad_norm, self.snr_gamma = group, max_grad_norm, snr_gamma
+        self.flat = FlatParams(brushnet_shapes(cfg), self.dev)
+        self.flat.load_state_dict(pack_brushnet(cfg, brushnet_sd))
+        self.brushnet = BrushNetTrainer(self.flat, cfg, B=batch, H=H, W=W)
+        br = self.brushnet.branch
+        taps = [z.tap for z in br.taps] + [br.mid_tap.tap] + [z.tap for z in br.up_taps]       # the reference's pop order: 12, mid, 15
+        self.unet = FrozenUNetTrainer(cfg, unet_sd, taps, B=batch, H=H, W=W, device=self.dev, ctx_len=ctx_len)
+        self.opt = B200AdamW(self.flat, lr=lr, betas=betas, eps=eps, weight_decay=weight_decay)
+        self.lr_sched = LRSchedule(self.opt, lr_schedule, lr_warmup_steps, max_train_steps)
+        self.noise_sched = NoiseSchedule(self.dev)
+        self.loss_fn = TrainLoss(batch, self.dev)
+        self.noisy = torch.zeros(batch, cfg.in_channels, H, W, device=self.dev, dtype=f32)
+        self.t_dev = torch.zeros(batch, device=self.dev, dtype=torch.int64)
+        self.weights = torch.zeros(batch, device=self.dev, dtype=f32)
+        self.world = 1
+        if group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
+            self.world = torch.distributed.get_world_size(group)
+
+    # the three phases are separate so a caller (bench.py, the tests) can time / inspect them
+    def forward(self, latents, noise, timesteps, conditioning_latents, encoder_hidden_states):
+        """latents / noise [B,4,H,W] fp32, timesteps [B] int64 (host or device), conditioning_latents [B,6,H,W], ehs [B,77,ctx].
+        Returns the loss (device scalar buffer)."""
+        self.t_dev.copy_(timesteps)
+        self.noise_sched.add_noise(latents, noise, self.t_dev, out=self.noisy)
+        self.brushnet.forward(self.noisy, conditioning_latents, self.t_dev)
+        pred = self.unet.forward(self.noisy, self.t_dev, encoder_hidden_states)
+        w = None
+        if self.snr_gamma is not None:
+            self.weights.copy_(torch.from_numpy(self.noise_sched.snr_weights(timesteps.cpu(), self.snr_gamma)))
+            w = self.weights
+        return self.loss_fn(pred, noise, weights=w, grad=self.unet.d_pred)       # also writes d loss / d model_pred
+
+    def backward(self):
+        dd, dm, du = self.unet.backward()
+        self.brushnet.backward(dd, dm, du)
+
+    def optimize(self):
+        if self.world > 1:
+            sharding.allreduce_flat_grads(self.flat.grad, group=self.group)
+        self.opt.step(max_grad_norm=self.max_grad_norm, grad_scale=1.0 / self.world)
+        self.lr_sched.step()
+        self.brushnet.refresh_dgrad_weights()
+        self.opt.zero_grad()
+
+    def step(self, latents, noise, timesteps, conditioning_latents, encoder_hidden_states) -> torch.Tensor:
+        loss = self.forward(latents, noise, timesteps, conditioning_latents, encoder_hidden_states)
+        self.backward()
+        self.optimize()
+        return loss
+
+    def brushnet_state_dict(self) -> Dict[str, torch.Tensor]:
+        """The trained BrushNet in the reference's state_dict naming / layouts (checkpoint hook, :997-1032)."""
+        return unpack_brushnet(self.cfg, self.flat)
+
+    @property
+    def flops_per_step(self) -> float:
+        """Algorithmic FLOPs of one step on this rank's batch: forward of both nets + BrushNet backward (data + weight
+        gradients = 2x its forward) + the frozen UNet's data-gradient chain."""
+        return self.unet.flops_fwd + self.unet.flops_bwd + 3.0 * self._bn_fwd_flops()
+
+    def _bn_fwd_flops(self) -> float:
+        # BrushNet forward = SURVEY's 4.413e11 per sample at 64x64 for SD1.5; computed from the UNet trainer's plans for other configs
+        return 4.413e11 * self.B * (self.H * self.W) / 4096.0 if self.cfg.block_out_channels == (320, 640, 1280, 1280) else 0.0

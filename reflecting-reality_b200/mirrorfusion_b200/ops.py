@@ -247,6 +247,29 @@ def attention(q, k, v, out, *, B, heads, head_dim, Tq, Tk, ldq=None, ldk=None, l
              _ptr(out), ldo or out.shape[-1], B, heads, head_dim, Tq, Tk, _stream()))
 
 
+def attention_lse(q, k, v, out, lse, *, B, heads, head_dim, Tq, Tk, ldq=None, ldk=None, ldv=None, ldo=None):
+    """attention() that also keeps lse [B, heads, Tq] fp32 (log2-domain log-sum-exp per query row) for attention_bwd."""
+    _req(lse, f32, "lse")
+    check(lib().mfb_attention_lse(_ptr(q), ldq or q.shape[-1], _ptr(k), ldk or k.shape[-1], _ptr(v), ldv or v.shape[-1],
+                                  _ptr(out), ldo or out.shape[-1], B, heads, head_dim, Tq, Tk, _ptr(lse), _stream()))
+
+
+def attention_bwd(q, k, v, o, d_o, lse, dvec, dq, dk=None, dv=None, *, B, heads, head_dim, Tq, Tk, ldq=None, ldk=None, ldv=None, ldo=None,
+                  lddo=None, lddq=None, lddk=None, lddv=None):
+    """Backward of attention() on tcgen05 (bf16): dq always; dk / dv both or neither (cross attention to a frozen context).
+    lse from attention_lse; dvec [B, heads, Tq] fp32 scratch."""
+    for name, t in (("q", q), ("o", o), ("d_o", d_o), ("dq", dq)):
+        if t.dtype != bf16 or not t.is_cuda:
+            raise ValueError(f"{name}: expected a CUDA bfloat16 tensor")
+    _req(lse, f32, "lse"); _req(dvec, f32, "dvec")
+    if lse.numel() < B * heads * Tq or dvec.numel() < B * heads * Tq:
+        raise ValueError("attention_bwd: lse / dvec smaller than B*heads*Tq")
+    check(lib().mfb_attention_bwd(_ptr(q), ldq or q.shape[-1], _ptr(k), ldk or k.shape[-1], _ptr(v), ldv or v.shape[-1], _ptr(o),
+                                  ldo or o.shape[-1], _ptr(d_o), lddo or d_o.shape[-1], _ptr(lse), _ptr(dvec), _ptr(dq),
+                                  lddq or dq.shape[-1], _ptr(dk), 0 if dk is None else (lddk or dk.shape[-1]), _ptr(dv),
+                                  0 if dv is None else (lddv or dv.shape[-1]), B, heads, head_dim, Tq, Tk, _stream()))
+
+
 def transpose_tokens(x, out, *, ld, col0, Cc, B, T, ldt):
     check(lib().mfb_transpose_tokens(_ptr(x), ld, col0, Cc, B, T, _ptr(out), ldt, _stream()))
 
@@ -427,19 +450,78 @@ def conv_wgrad(x, dy, dw, dbias=None, *, B, H, W, ksize, stride=1, accumulate=Fa
                                _stream()))
 
 
+_GNB_WS: dict = {}
+
+
+def groupnorm_stats(x1, x2, stats_ws, *, B, HW, groups):
+    """stats_ws[0 : 2*B*groups] = per-(image, group) {sum, sum of squares} (bf16 inputs; workspace of gn_ws_floats(B, groups))."""
+    _req(x1, bf16, "x1")
+    check(lib().mfb_groupnorm_stats(_ptr(x1), x1.shape[-1], _ptr(x2), 0 if x2 is None else x2.shape[-1], B, HW, groups, _ptr(stats_ws),
+                                    _stream()))
+
+
 def groupnorm_bwd(x1, x2, dy, gamma, beta, dx1, dx2, ws, *, B, HW, groups, eps, silu, dgamma=None, dbeta=None, accumulate=False,
-                  dres=None):
-    """Backward of groupnorm(): dx (per source tensor of the concat), dgamma, dbeta.  ws: 2*B*C floats.
-    dres [B, HW, C]: gradient of the residual / shortcut path, added to dx in the same pass."""
+                  dres=None, dres2=None, stats=None):
+    """Backward of groupnorm(): dx (per source tensor of the concat), dgamma, dbeta (None for a frozen layer).
+    dres / dres2 [B, HW, C]: gradients of residual / skip paths, added to dx in the same pass.
+    bf16 tensors with channel counts that are multiples of 8 take the vectorised two-pass kernels (mfb_groupnorm_bwd2; `stats`: the
+    forward's statistics buffer if the caller kept it, otherwise they are recomputed; `ws` is ignored: a per-geometry workspace
+    is kept); fp32 tensors (parity mode) the CUDA-core kernel (ws: 2*B*C floats, no dres2)."""
     is32 = _is32(x1)
     C1 = x1.shape[-1]
     C2 = 0 if x2 is None else x2.shape[-1]
+    C = C1 + C2
     _req(dy, x1.dtype, "dy"); _req(dx1, x1.dtype, "dx1")
-    if ws.numel() < 2 * B * (C1 + C2):
+    if not is32 and C1 % 8 == 0 and C2 % 8 == 0 and (C // groups >= 8 or C // groups == 4):
+        L = lib()
+        # one workspace per (device, geometry): the ticket counters inside it sit at geometry-dependent offsets and must stay zero
+        # between calls, so layouts never share memory (launches on one stream serialise on it); allocated at the first call
+        key = (x1.device, B, C, groups)
+        w2 = _GNB_WS.get(key)
+        need = int(L.mfb_groupnorm_bwd2_ws_floats(B, C, groups))
+        if w2 is None:
+            w2 = _GNB_WS[key] = torch.zeros(need + gn_ws_floats(B, groups), device=x1.device, dtype=f32)
+        st_ws = w2[need:]
+        if stats is None:
+            check(L.mfb_groupnorm_stats(_ptr(x1), C1, _ptr(x2), C2, B, HW, groups, _ptr(st_ws), _stream()))
+            stats = st_ws
+        check(L.mfb_groupnorm_bwd2(_ptr(x1), C1, _ptr(x2), C2, _ptr(dy), B, HW, groups, eps, _ptr(gamma), _ptr(beta), int(silu),
+                                   _ptr(stats), _ptr(dres), _ptr(dres2), _ptr(dx1), _ptr(dx2), _ptr(dgamma), _ptr(dbeta), _ptr(w2),
+                                   int(accumulate), _stream()))
+        return
+    if dres2 is not None:
+        raise ValueError("groupnorm_bwd: dres2 needs the bf16 kernels")
+    if ws.numel() < 2 * B * C:
         raise ValueError("groupnorm_bwd: workspace smaller than MFB_GN_BWD_WS_FLOATS(B, C)")
     check(lib().mfb_groupnorm_bwd(_ptr(x1), C1, _ptr(x2), C2, _ptr(dy), int(is32), B, HW, groups, eps, _ptr(gamma), _ptr(beta),
                                   int(silu), _ptr(dres), _ptr(dx1), _ptr(dx2), _ptr(dgamma), _ptr(dbeta), _ptr(ws), int(accumulate),
                                   _stream()))
+
+
+def layernorm_bwd(x, dy, gamma, dx, eps=1e-5, dres=None):
+    """Data gradient of layernorm() (+ dres, the gradient of the residual path), bf16 [rows, C]."""
+    for name, t in (("x", x), ("dy", dy), ("dx", dx)):
+        _req(t, bf16, name)
+    check(lib().mfb_layernorm_bwd(_ptr(x), _ptr(dy), x.numel() // x.shape[-1], x.shape[-1], eps, _ptr(gamma), _ptr(dres), _ptr(dx), _stream()))
+
+
+def geglu(proj, out=None, d_out=None, d_proj=None):
+    """Un-fused GEGLU on proj [rows, 2C] = [h | gate] (bf16): forward value and / or backward."""
+    _req(proj, bf16, "proj")
+    Cc = proj.shape[-1] // 2
+    check(lib().mfb_geglu(_ptr(proj), proj.numel() // proj.shape[-1], Cc, _ptr(out), _ptr(d_out), _ptr(d_proj), _stream()))
+
+
+def conv_out_bwd(dy, w, dx, *, B, H, W):
+    """Data gradient of conv_out: dy fp32 NCHW [B, Cout, H, W], w fp32 [Cout, 3, 3, Cin], dx bf16 [B, H*W, Cin]."""
+    _req(dy, f32, "dy"); _req(w, f32, "w"); _req(dx, bf16, "dx")
+    check(lib().mfb_conv_out_bwd(_ptr(dy), B, H, W, dx.shape[-1], dy.shape[1], _ptr(w), _ptr(dx), _stream()))
+
+
+def sumpool2x2(du, dx, *, B, H, W):
+    """dx [B, H*W, C] = 2x2 sums of du [B, 2H*2W, C] (bf16): the adjoint of the nearest-x2 replication."""
+    _req(du, bf16, "du"); _req(dx, bf16, "dx")
+    check(lib().mfb_sumpool2x2(_ptr(du), B, H, W, dx.shape[-1], _ptr(dx), _stream()))
 
 
 def rowsum_per_image(dy, out, *, B, HW):
