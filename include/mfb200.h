@@ -327,6 +327,10 @@ int mfb_layernorm_bwd(const void* x, const void* dy, int rows, int C, float eps,
                       void* stream);
 int mfb_geglu(const void* proj, long long rows, int C, void* out, const void* d_out, void* d_proj, void* stream);
 int mfb_conv_out_bwd(const float* dy, int B, int H, int W, int Cin, int Cout, const float* w, void* dx, void* stream);
+/* Packed weight of a stride-1 conv's / linear's DATA gradient from its packed forward weight (both bf16): wd [Cin, k*k*Cout] with
+ * wd[ci, (k*k-1-t)*Cout + co] = w[co, t*Cin + ci] (autograd's dgrad of F.conv2d / F.linear, S/models/lora.py:363-377,445-451, as
+ * "the same implicit GEMM on dy with the flipped / transposed weight"); re-derived after every optimizer step for trainable layers. */
+int mfb_dgrad_repack(const void* w, int Cout, int Cin, int ksize, void* wd, void* stream);
 /* Adjoint of Upsample2D's nearest-x2 replication (S/models/upsampling.py:167-173): dx [B, H*W, C] = 2x2 sums of du [B, 2H*2W, C] (bf16). */
 int mfb_sumpool2x2(const void* du, int B, int H, int W, int C, void* dx, void* stream);
 

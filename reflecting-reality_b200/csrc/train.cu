@@ -12,6 +12,7 @@
 
 #include "common.h"
 #include "ptx.cuh"
+#include "wgrad5.h"
 
 namespace mfb {
 
@@ -979,12 +980,19 @@ static void wgrad_tc_plan(int B, int H, int W, int Cin, int Cout, int ksize, int
 
 #define MFB_DBIAS_SLICES 32
 
+// tcgen05 version (wgrad5.cu) for channel counts >= 64; MFB_WGRAD_LEGACY=1 keeps the mma.sync kernel (A/B)
+static bool use_wgrad5(int Cin, int Cout) {
+    static const bool legacy = [] { const char* e = getenv("MFB_WGRAD_LEGACY"); return e && atoi(e) != 0; }();
+    return !legacy && mfb::wgrad5_supported(Cin, Cout);
+}
+
 extern "C" long long mfb_conv_wgrad_tc_ws_floats(int B, int H, int W, int Cin, int Cout, int ksize, int stride) {
     if (B <= 0 || H <= 0 || W <= 0 || Cin <= 0 || Cout <= 0 || (ksize != 1 && ksize != 3) || (stride != 1 && stride != 2) ||
         H % stride || W % stride)
         return 0;
     int slices, per;
-    wgrad_tc_plan(B, H / stride, W / stride, Cin, Cout, ksize, &slices, &per);
+    if (use_wgrad5(Cin, Cout)) mfb::wgrad5_plan(B, H / stride, W / stride, Cin, Cout, ksize, &slices, &per);
+    else wgrad_tc_plan(B, H / stride, W / stride, Cin, Cout, ksize, &slices, &per);
     return static_cast<long long>(slices) * Cout * ksize * ksize * Cin + static_cast<long long>(MFB_DBIAS_SLICES) * Cout;
 }
 
@@ -998,19 +1006,25 @@ extern "C" int mfb_conv_wgrad_tc(const void* x, const void* dy, int B, int H, in
     MFB_REQUIRE(ws_floats >= mfb_conv_wgrad_tc_ws_floats(B, H, W, Cin, Cout, ksize, stride), "workspace too small");
     const int Ho = H / stride, Wo = W / stride;
     int slices, per;
-    wgrad_tc_plan(B, Ho, Wo, Cin, Cout, ksize, &slices, &per);
     const int taps = ksize * ksize, ktot = taps * Cin;
-    const int mtiles = (Cout + TC_BM - 1) / TC_BM, ntiles = (Cin + TC_BN - 1) / TC_BN;
-    MFB_REQUIRE(mtiles * taps <= 65535, "Cout too large");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    static bool attr_set = false;
-    if (!attr_set) {
-        MFB_CUDA_OK(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
-        attr_set = true;
+    if (use_wgrad5(Cin, Cout)) {
+        mfb::wgrad5_plan(B, Ho, Wo, Cin, Cout, ksize, &slices, &per);
+        const int rc = mfb::wgrad5_run(x, dy, B, Ho, Wo, Cin, Cout, ksize, stride, ws, st);
+        if (rc) return rc;
+    } else {
+        wgrad_tc_plan(B, Ho, Wo, Cin, Cout, ksize, &slices, &per);
+        const int mtiles = (Cout + TC_BM - 1) / TC_BM, ntiles = (Cin + TC_BN - 1) / TC_BN;
+        MFB_REQUIRE(mtiles * taps <= 65535, "Cout too large");
+        static bool attr_set = false;
+        if (!attr_set) {
+            MFB_CUDA_OK(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
+            attr_set = true;
+        }
+        MFB_CUDA_OK(launch_k(wgrad_tc_kernel, dim3(ntiles, mtiles * taps, slices), dim3(256), TC_SMEM, st, 1,
+                             static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(dy), B, Ho, Wo, Cin, Cout, ksize, stride,
+                             per, ws));
     }
-    MFB_CUDA_OK(launch_k(wgrad_tc_kernel, dim3(ntiles, mtiles * taps, slices), dim3(256), TC_SMEM, st, 1,
-                         static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(dy), B, Ho, Wo, Cin, Cout, ksize, stride,
-                         per, ws));
     const long long n = static_cast<long long>(Cout) * ktot;
     MFB_CUDA_OK(launch_k(wgrad_reduce_kernel, dim3(chunks_for(n, 256, 148 * 8)), dim3(256), 0, st, 1, static_cast<const float*>(ws), slices,
                          n, dw, accumulate));

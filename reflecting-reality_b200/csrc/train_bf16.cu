@@ -390,6 +390,31 @@ __global__ void __launch_bounds__(256) conv_out_bwd_kernel(const float* __restri
     }
 }
 
+// ------------------------------------------------------------------------------------------------ data-gradient weight repack
+// dx = conv(dy, W') with W'[ci, (k*k-1-t), co] = W[co, t, ci] (flip the taps, swap the channel roles; ops.pack_conv_dgrad_weight):
+// after every optimizer step the trainable layers' data-gradient plans need W' re-derived from the updated packed weight.
+// One 32x32 shared-memory transpose tile per (ci tile, co tile, tap): coalesced 2-byte reads along ci and writes along co.
+__global__ void __launch_bounds__(256) dgrad_repack_kernel(const __nv_bfloat16* __restrict__ w, int Cout, int Cin, int taps,
+                                                           __nv_bfloat16* __restrict__ wd) {
+    __shared__ __nv_bfloat16 tile[32][33];
+    pdl_trigger();
+    pdl_wait();
+    const int t = blockIdx.z, ci0 = blockIdx.x * 32, co0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;      // 32 x 8
+    const size_t ktot = static_cast<size_t>(taps) * Cin, kd = static_cast<size_t>(taps) * Cout;
+#pragma unroll
+    for (int r = ty; r < 32; r += 8) {
+        const int co = co0 + r, ci = ci0 + tx;
+        tile[r][tx] = (co < Cout && ci < Cin) ? w[static_cast<size_t>(co) * ktot + static_cast<size_t>(t) * Cin + ci] : __float2bfloat16(0.f);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = ty; r < 32; r += 8) {
+        const int ci = ci0 + r, co = co0 + tx;
+        if (ci < Cin && co < Cout) wd[static_cast<size_t>(ci) * kd + static_cast<size_t>(taps - 1 - t) * Cout + co] = tile[tx][r];
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ 2x2 sum-pool
 // Adjoint of the nearest-x2 replication of Upsample2D (S/models/upsampling.py:167-173): dx[b, i, j, :] = sum of the four
 // high-resolution gradients du[b, 2i + {0,1}, 2j + {0,1}, :].  Thread = (low-resolution pixel, 8 channels).
@@ -424,6 +449,16 @@ __global__ void __launch_bounds__(256) sumpool2x2_kernel(const __nv_bfloat16* __
 }  // namespace mfb
 
 using namespace mfb;
+
+extern "C" int mfb_dgrad_repack(const void* w, int Cout, int Cin, int ksize, void* wd, void* stream) {
+    MFB_REQUIRE(w && wd && Cout > 0 && Cin > 0 && (ksize == 1 || ksize == 3), "bad arguments");
+    const int taps = ksize * ksize;
+    dim3 grid((Cin + 31) / 32, (Cout + 31) / 32, taps);
+    MFB_REQUIRE(grid.y <= 65535, "Cout too large");
+    MFB_CUDA_OK(launch_k(dgrad_repack_kernel, grid, dim3(256), 0, static_cast<cudaStream_t>(stream), 1,
+                         static_cast<const __nv_bfloat16*>(w), Cout, Cin, taps, static_cast<__nv_bfloat16*>(wd)));
+    return MFB_OK;
+}
 
 extern "C" int mfb_sumpool2x2(const void* du, int B, int H, int W, int C, void* dx, void* stream) {
     MFB_REQUIRE(du && dx && B > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0, "bad arguments (C must be a multiple of 8)");

@@ -85,10 +85,20 @@ class ResnetBlockTrainer:
         self.d_rowbias = torch.zeros(B, Cout, device=dev, dtype=torch.float32)
         self.gn_ws = torch.zeros(K.gn_ws_floats(B, groups), device=dev, dtype=torch.float32)
         self.gnb_ws = torch.zeros(2 * B * max(Cin, Cout), device=dev, dtype=torch.float32)
-        wsrc = flat.p if self.dt == torch.float32 else flat.w        # fp32 masters (parity mode) or the bf16 working copy
-        n = lambda s: f"{prefix}.{s}"
-        self._wsrc = wsrc
-        geo = dict(B=B, H=H, W=W)
+        self._wsrc = flat.p if self.dt == torch.float32 else flat.w        # fp32 masters (parity mode) or the bf16 working copy
+        # data-gradient weights: the same implicit-GEMM kernel over the incoming gradient with flipped / transposed weights
+        self.w1d = torch.zeros(Cin, 9 * Cout, device=dev, dtype=self.dt)
+        self.w2d = torch.zeros(Cout, 9 * Cout, device=dev, dtype=self.dt)
+        if self.shortcut:
+            self.wscd = torch.zeros(Cin, Cout, device=dev, dtype=self.dt)
+        self._make_plans()
+        self.refresh_dgrad_weights()
+
+    def _make_plans(self):
+        K, flat, wsrc = self.K, self.flat, self._wsrc
+        Cin, Cout = self.Cin, self.Cout
+        n = lambda s: f"{self.p}.{s}"
+        geo = dict(B=self.B, H=self.H, W=self.W)
         self.plan1 = K.ConvPlan(self.n1, wsrc(n("conv1.weight")), self.c1, Cin=Cin, Cout=Cout, ksize=3, bias=flat.p(n("conv1.bias")),
                                 rowbias=self.rowbias, rowbias_ld=Cout, **geo)
         if self.shortcut:
@@ -96,29 +106,35 @@ class ResnetBlockTrainer:
                                       bias=flat.p(n("conv_shortcut.bias")), **geo)
         self.plan2 = K.ConvPlan(self.n2, wsrc(n("conv2.weight")), self.out, Cin=Cout, Cout=Cout, ksize=3, bias=flat.p(n("conv2.bias")),
                                 res1=self.sc if self.shortcut else self.x, **geo)
-        # data-gradient plans: the same implicit-GEMM kernel over the incoming gradient with flipped / transposed weights
-        self.w1d = torch.zeros(Cin, 9 * Cout, device=dev, dtype=self.dt)
-        self.w2d = torch.zeros(Cout, 9 * Cout, device=dev, dtype=self.dt)
         self.plan_d2 = K.ConvPlan(self.d_out, self.w2d, self.dn2, Cin=Cout, Cout=Cout, ksize=3, **geo)
         self.plan_d1 = K.ConvPlan(self.dc1, self.w1d, self.dn1, Cin=Cout, Cout=Cin, ksize=3, **geo)
         if self.shortcut:
-            self.wscd = torch.zeros(Cin, Cout, device=dev, dtype=self.dt)
             self.plan_dsc = K.ConvPlan(self.d_out, self.wscd, self.dsc, Cin=Cout, Cout=Cin, ksize=1, **geo)
-        self.refresh_dgrad_weights()
+
+    def rebind(self, x=None, d_out=None):
+        """Use the producer's output buffer as this block's input (and the consumer's input-gradient buffer as its output
+        gradient) instead of private copies: forward() / backward() then skip the copy when handed exactly that tensor."""
+        if x is not None:
+            self.x = x.view_as(self.x)
+        if d_out is not None:
+            self.d_out = d_out.view_as(self.d_out)
+        self._make_plans()
 
     def refresh_dgrad_weights(self):
         """Re-derive the data-gradient weights from the current parameters (after every optimizer step): a permuting copy."""
         n = lambda s: f"{self.p}.{s}"
-        self.w1d.copy_(_dgrad_from_packed(self._wsrc(n("conv1.weight")), 3, self.dt))
-        self.w2d.copy_(_dgrad_from_packed(self._wsrc(n("conv2.weight")), 3, self.dt))
+        R = self.K.dgrad_repack
+        R(self._wsrc(n("conv1.weight")), self.w1d, 3)
+        R(self._wsrc(n("conv2.weight")), self.w2d, 3)
         if self.shortcut:
-            self.wscd.copy_(_dgrad_from_packed(self._wsrc(n("conv_shortcut.weight")), 1, self.dt))
+            R(self._wsrc(n("conv_shortcut.weight")), self.wscd, 1)
 
     # ------------------------------------------------------------------------------------------------ forward
     def forward(self, x: torch.Tensor, rowbias: Optional[torch.Tensor] = None) -> torch.Tensor:
         """x [B, HW, Cin] (activation dtype), rowbias [B, Cout] fp32 (None = 0).  Returns the block's output buffer."""
         K, f, n = self.K, self.flat, (lambda s: f"{self.p}.{s}")
-        self.x.copy_(x.view_as(self.x))
+        if x.data_ptr() != self.x.data_ptr():
+            self.x.copy_(x.view_as(self.x))
         if rowbias is None:
             self.rowbias.zero_()
         else:
@@ -137,7 +153,8 @@ class ResnetBlockTrainer:
         """d_out [B, HW, Cout].  Accumulates parameter gradients into flat.g(...); returns (d x, d rowbias) buffers."""
         K, f, n = self.K, self.flat, (lambda s: f"{self.p}.{s}")
         B, H, W, HW = self.B, self.H, self.W, self.HW
-        self.d_out.copy_(d_out.view_as(self.d_out))
+        if d_out.data_ptr() != self.d_out.data_ptr():
+            self.d_out.copy_(d_out.view_as(self.d_out))
         gnb = dict(B=B, HW=HW, groups=self.groups, eps=self.eps, silu=True, accumulate=True)
         # out = conv2(n2) + bias2 + shortcut(x)
         tr = not self.frozen
@@ -187,11 +204,22 @@ class DownsampleTrainer:
         self.x = torch.zeros(B, H * W, C, device=dev, dtype=self.dt)
         self.out = torch.zeros(B, (H // 2) * (W // 2), C, device=dev, dtype=self.dt)
         self.d_out, self.dx = torch.zeros_like(self.out), torch.zeros_like(self.x)
-        self.plan = K.ConvPlan(self.x, self._wsrc(f"{prefix}.conv.weight"), self.out, B=B, H=H, W=W, Cin=C, Cout=C, ksize=3, stride=2,
-                               bias=flat.p(f"{prefix}.conv.bias"))
         self.wd = torch.zeros(4, C, 4 * C, device=dev, dtype=self.dt)
-        self.plan_d = K.ConvPlan(self.d_out, self.wd, self.dx, B=B, H=H // 2, W=W // 2, Cin=C, Cout=C, ksize=3, up2x=True)
+        self._make_plans()
         self.refresh_dgrad_weights()
+
+    def _make_plans(self):
+        K, B, H, W, C = self.K, self.B, self.H, self.W, self.C
+        self.plan = K.ConvPlan(self.x, self._wsrc(f"{self.p}.conv.weight"), self.out, B=B, H=H, W=W, Cin=C, Cout=C, ksize=3, stride=2,
+                               bias=self.flat.p(f"{self.p}.conv.bias"))
+        self.plan_d = K.ConvPlan(self.d_out, self.wd, self.dx, B=B, H=H // 2, W=W // 2, Cin=C, Cout=C, ksize=3, up2x=True)
+
+    def rebind(self, x=None, d_out=None):
+        if x is not None:
+            self.x = x.view_as(self.x)
+        if d_out is not None:
+            self.d_out = d_out.view_as(self.d_out)
+        self._make_plans()
 
     def refresh_dgrad_weights(self):
         w = unpack_conv_grad(self._wsrc(f"{self.p}.conv.weight").float(), 3)          # packed -> OIHW
@@ -208,13 +236,15 @@ class DownsampleTrainer:
                             blk.copy_(w[:, :, kh, kw].t().to(self.dt))
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
-        self.x.copy_(x.view_as(self.x))
+        if x.data_ptr() != self.x.data_ptr():
+            self.x.copy_(x.view_as(self.x))
         self.plan.run()
         return self.out
 
     def backward(self, d_out: torch.Tensor) -> torch.Tensor:
         f = self.flat
-        self.d_out.copy_(d_out.view_as(self.d_out))
+        if d_out.data_ptr() != self.d_out.data_ptr():
+            self.d_out.copy_(d_out.view_as(self.d_out))
         if not self.frozen:     # frozen (UNet): data gradient only
             self.K.conv_wgrad(self.x, self.d_out, f.g(f"{self.p}.conv.weight"), f.g(f"{self.p}.conv.bias"), B=self.B, H=self.H, W=self.W,
                               ksize=3, stride=2, accumulate=True)
@@ -235,13 +265,23 @@ class ZeroConvTap:
         self.tap = torch.zeros(B, H * W, C, device=dev, dtype=dt)
         self.d_tap, self.dh = torch.zeros_like(self.tap), torch.zeros_like(self.tap)
         self.wd = torch.zeros(C, C, device=dev, dtype=dt)
+        self.C, self._others = C, (d_other, d_other2)
         self.plan = K.ConvPlan(h, self._wsrc(f"{name}.weight"), self.tap, Cin=C, Cout=C, ksize=1, bias=flat.p(f"{name}.bias"), **self.geo)
-        # up to two more consumers of h (the next block; the up-block resnet that takes h as its skip): both residual inputs
-        self.plan_d = K.ConvPlan(self.d_tap, self.wd, self.dh, Cin=C, Cout=C, ksize=1, res1=d_other, res2=d_other2, **self.geo)
+        self._make_plan_d()
         self.refresh_dgrad_weights()
 
+    def _make_plan_d(self):
+        # up to two more consumers of h (the next block; the up-block resnet that takes h as its skip): both residual inputs
+        self.plan_d = self.K.ConvPlan(self.d_tap, self.wd, self.dh, Cin=self.C, Cout=self.C, ksize=1, res1=self._others[0],
+                                      res2=self._others[1], **self.geo)
+
+    def bind_d_tap(self, buf: torch.Tensor):
+        """Read the tap gradient where the frozen UNet's backward leaves it (FrozenUNetTrainer.d_taps) instead of a private copy."""
+        self.d_tap = buf.view_as(self.d_tap)
+        self._make_plan_d()
+
     def refresh_dgrad_weights(self):
-        self.wd.copy_(self._wsrc(f"{self.name}.weight").t())
+        self.K.dgrad_repack(self._wsrc(f"{self.name}.weight"), self.wd, 1)
 
     def forward(self):
         self.plan.run()
@@ -249,7 +289,8 @@ class ZeroConvTap:
 
     def backward(self, d_tap: torch.Tensor) -> torch.Tensor:
         f = self.flat
-        self.d_tap.copy_(d_tap.view_as(self.d_tap))
+        if d_tap.data_ptr() != self.d_tap.data_ptr():
+            self.d_tap.copy_(d_tap.view_as(self.d_tap))
         self.K.conv_wgrad(self.h, self.d_tap, f.g(f"{self.name}.weight"), f.g(f"{self.name}.bias"), ksize=1, accumulate=True, **self.geo)
         self.plan_d.run()
         return self.dh
@@ -330,6 +371,14 @@ class BrushNetDownMidTrainer:
                                  d_other2=None if skip_grads is None else skip_grads[k])
                      for k, (hb, hh_, ww_, c) in enumerate(hidden)]
         self.mid_tap = ZeroConvTap(flat, "brushnet_mid_block", self.mid[1].out, mid_other, B=B, H=h, W=w, C=boc[-1], dt=dt, K=K)
+        # No copies between blocks: a block reads its producer's output buffer and the gradient buffer of its output's zero-conv
+        # (which already holds the sum over all consumers) in place.
+        x = self.h0
+        for k, (_, t) in enumerate(self.blocks):
+            t.rebind(x=x, d_out=self.taps[k + 1].dh)
+            x = t.out
+        self.mid[0].rebind(x=x, d_out=self.mid[1].dx)
+        self.mid[1].rebind(x=self.mid[0].out, d_out=self.mid_tap.dh)
 
     def _build_up_path(self, B, dt, common):
         return None, None
@@ -346,7 +395,8 @@ class BrushNetDownMidTrainer:
     def forward(self, h0: torch.Tensor, rowbias: Dict[str, torch.Tensor]):
         """h0: conv_in_condition's output [B, HW, C0]; rowbias[prefix] = time_emb_proj(silu(emb)) of each resnet ([B, Cout] fp32).
         Returns (down taps [12 for SD1.5], mid tap) — buffers owned by the trainer."""
-        self.h0.copy_(h0.view_as(self.h0))
+        if h0.data_ptr() != self.h0.data_ptr():
+            self.h0.copy_(h0.view_as(self.h0))
         x = self.h0
         for kind, t in self.blocks:
             x = t.forward(x, rowbias[t.p]) if kind == "resnet" else t.forward(x)
@@ -397,10 +447,21 @@ class UpsampleTrainer:
             for kw in (1, 2):
                 pool[:, kh, kw, :] = eye
         self.w_pool = pool.reshape(C, 9 * C).to(self.dt).contiguous()
-        self.plan = K.ConvPlan(self.x, self.w_up, self.out, B=B, H=H, W=W, Cin=C, Cout=C, ksize=3, up2x=True, bias=flat.p(f"{prefix}.conv.bias"))
+        self._make_plans()
+        self.refresh_dgrad_weights()
+
+    def _make_plans(self):
+        K, B, H, W, C = self.K, self.B, self.H, self.W, self.C
+        self.plan = K.ConvPlan(self.x, self.w_up, self.out, B=B, H=H, W=W, Cin=C, Cout=C, ksize=3, up2x=True, bias=self.flat.p(f"{self.p}.conv.bias"))
         self.plan_d = K.ConvPlan(self.d_out, self.wd, self.du, B=B, H=2 * H, W=2 * W, Cin=C, Cout=C, ksize=3)
         self.plan_pool = K.ConvPlan(self.du, self.w_pool, self.dx, B=B, H=2 * H, W=2 * W, Cin=C, Cout=C, ksize=3, stride=2)
-        self.refresh_dgrad_weights()
+
+    def rebind(self, x=None, d_out=None):
+        if x is not None:
+            self.x = x.view_as(self.x)
+        if d_out is not None:
+            self.d_out = d_out.view_as(self.d_out)
+        self._make_plans()
 
     def refresh_dgrad_weights(self):
         """Derived weight copies: the four sub-pixel phases of the forward plan and the flipped / transposed data-gradient weight."""
@@ -411,16 +472,18 @@ class UpsampleTrainer:
             self.w_up.copy_(_ops.pack_upconv_weight(unpack_conv_grad(wp.float(), 3)))
         finally:
             _ops._ACT[0] = old
-        self.wd.copy_(_dgrad_from_packed(wp, 3, self.dt))
+        self.K.dgrad_repack(wp, self.wd, 3)
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
-        self.x.copy_(x.view_as(self.x))
+        if x.data_ptr() != self.x.data_ptr():
+            self.x.copy_(x.view_as(self.x))
         self.plan.run()
         return self.out
 
     def backward(self, d_out: torch.Tensor) -> torch.Tensor:
         K, f, B, H, W = self.K, self.flat, self.B, self.H, self.W
-        self.d_out.copy_(d_out.view_as(self.d_out))
+        if d_out.data_ptr() != self.d_out.data_ptr():
+            self.d_out.copy_(d_out.view_as(self.d_out))
         # nearest x2 of the saved input: a pure pixel-vector copy, so fp32 tensors go through the bf16 kernel as 2*C "channels"
         bf = torch.bfloat16
         K.upsample2x(self.x.view(bf) if self.dt != bf else self.x, self.xu.view(bf) if self.dt != bf else self.xu, B=B, H=H, W=W)
@@ -477,6 +540,19 @@ class SkipResnetBlockTrainer:
         self._wsrc = wsrc = flat.p if self.dt == torch.float32 else flat.w
         n = lambda s: f"{prefix}.{s}"
         geo = dict(B=B, H=H, W=W)
+        self.w1d = torch.zeros(Cin, 9 * Cout, device=dev, dtype=self.dt)
+        self.w2d = torch.zeros(Cout, 9 * Cout, device=dev, dtype=self.dt)
+        self.wad = torch.zeros(C1, Cout, device=dev, dtype=self.dt)
+        self.wbd = torch.zeros(C2, Cout, device=dev, dtype=self.dt)
+        self._make_plans()
+        self.refresh_dgrad_weights()
+
+    def _make_plans(self):
+        K, flat, wsrc = self.K, self.flat, self._wsrc
+        C1, C2, Cout = self.C1, self.C2, self.Cout
+        Cin = C1 + C2
+        n = lambda s: f"{self.p}.{s}"
+        geo = dict(B=self.B, H=self.H, W=self.W)
         self.plan1 = K.ConvPlan(self.n1, wsrc(n("conv1.weight")), self.c1, Cin=Cin, Cout=Cout, ksize=3, bias=flat.p(n("conv1.bias")),
                                 rowbias=self.rowbias, rowbias_ld=Cout, **geo)
         self.plan_sc_a = K.ConvPlan(self.x1, wsrc(n("conv_shortcut.weight.a")), self.sc_a, Cin=C1, Cout=Cout, ksize=1,
@@ -484,27 +560,34 @@ class SkipResnetBlockTrainer:
         self.plan_sc_b = K.ConvPlan(self.x2, wsrc(n("conv_shortcut.weight.b")), self.sc, Cin=C2, Cout=Cout, ksize=1, res1=self.sc_a, **geo)
         self.plan2 = K.ConvPlan(self.n2, wsrc(n("conv2.weight")), self.out, Cin=Cout, Cout=Cout, ksize=3, bias=flat.p(n("conv2.bias")),
                                 res1=self.sc, **geo)
-        self.w1d = torch.zeros(Cin, 9 * Cout, device=dev, dtype=self.dt)
-        self.w2d = torch.zeros(Cout, 9 * Cout, device=dev, dtype=self.dt)
-        self.wad = torch.zeros(C1, Cout, device=dev, dtype=self.dt)
-        self.wbd = torch.zeros(C2, Cout, device=dev, dtype=self.dt)
         self.plan_d2 = K.ConvPlan(self.d_out, self.w2d, self.dn2, Cin=Cout, Cout=Cout, ksize=3, **geo)
         self.plan_d1 = K.ConvPlan(self.dc1, self.w1d, self.dn1, Cin=Cout, Cout=Cin, ksize=3, **geo)
         self.plan_da = K.ConvPlan(self.d_out, self.wad, self.dx, Cin=Cout, Cout=C1, ksize=1, res1=self.g1, **geo)
         self.plan_db = K.ConvPlan(self.d_out, self.wbd, self.dx2, Cin=Cout, Cout=C2, ksize=1, res1=self.g2, **geo)
-        self.refresh_dgrad_weights()
+
+    def rebind(self, x1=None, x2=None, d_out=None):
+        if x1 is not None:
+            self.x1 = x1.view_as(self.x1)
+        if x2 is not None:
+            self.x2 = x2.view_as(self.x2)
+        if d_out is not None:
+            self.d_out = d_out.view_as(self.d_out)
+        self._make_plans()
 
     def refresh_dgrad_weights(self):
         n = lambda s: f"{self.p}.{s}"
-        self.w1d.copy_(_dgrad_from_packed(self._wsrc(n("conv1.weight")), 3, self.dt))
-        self.w2d.copy_(_dgrad_from_packed(self._wsrc(n("conv2.weight")), 3, self.dt))
-        self.wad.copy_(self._wsrc(n("conv_shortcut.weight.a")).t())
-        self.wbd.copy_(self._wsrc(n("conv_shortcut.weight.b")).t())
+        R = self.K.dgrad_repack
+        R(self._wsrc(n("conv1.weight")), self.w1d, 3)
+        R(self._wsrc(n("conv2.weight")), self.w2d, 3)
+        R(self._wsrc(n("conv_shortcut.weight.a")), self.wad, 1)
+        R(self._wsrc(n("conv_shortcut.weight.b")), self.wbd, 1)
 
     def forward(self, x1: torch.Tensor, x2: torch.Tensor, rowbias: Optional[torch.Tensor] = None) -> torch.Tensor:
         K, f, n = self.K, self.flat, (lambda s: f"{self.p}.{s}")
-        self.x1.copy_(x1.view_as(self.x1))
-        self.x2.copy_(x2.view_as(self.x2))
+        if x1.data_ptr() != self.x1.data_ptr():
+            self.x1.copy_(x1.view_as(self.x1))
+        if x2.data_ptr() != self.x2.data_ptr():
+            self.x2.copy_(x2.view_as(self.x2))
         if rowbias is None:
             self.rowbias.zero_()
         else:
@@ -522,7 +605,8 @@ class SkipResnetBlockTrainer:
         """-> (d x, d skip, d rowbias)."""
         K, f, n = self.K, self.flat, (lambda s: f"{self.p}.{s}")
         B, H, W, HW = self.B, self.H, self.W, self.HW
-        self.d_out.copy_(d_out.view_as(self.d_out))
+        if d_out.data_ptr() != self.d_out.data_ptr():
+            self.d_out.copy_(d_out.view_as(self.d_out))
         gnb = dict(B=B, HW=HW, groups=self.groups, eps=self.eps, silu=True, accumulate=True)
         wg = dict(B=B, H=H, W=W, accumulate=True)
         K.conv_wgrad(self.n2, self.d_out, f.g(n("conv2.weight")), f.g(n("conv2.bias")), ksize=3, **wg)
@@ -620,6 +704,13 @@ class BrushNetBranchTrainer(BrushNetDownMidTrainer):
         for kind, t, idx in self.up_seq:
             if kind == "resnet":
                 skip_grads[idx] = t.dx2
+        x = self.mid[1].out                    # no copies between blocks (see BrushNetDownMidTrainer.__init__)
+        for k, (kind, t, idx) in enumerate(self.up_seq):
+            if kind == "resnet":
+                t.rebind(x1=x, x2=self.hidden[idx][0], d_out=self.up_taps[k].dh)
+            else:
+                t.rebind(x=x, d_out=self.up_taps[k].dh)
+            x = t.out
         return skip_grads, self.up_seq[0][1].dx
 
     def resnet_prefixes(self):
@@ -640,6 +731,8 @@ class BrushNetBranchTrainer(BrushNetDownMidTrainer):
             x = t.forward(x, self.hidden[idx][0], rowbias[t.p]) if kind == "resnet" else t.forward(x)
         return down_taps, mid_tap, [z.forward() for z in self.up_taps]
 
+    after_up_backward = None      # optional hook: called once the up path's parameter gradients are complete (overlapped all-reduce)
+
     def backward(self, d_down_taps, d_mid_tap, d_up_taps):
         d_rb = {}
         for k in range(len(self.up_seq) - 1, -1, -1):
@@ -649,6 +742,8 @@ class BrushNetBranchTrainer(BrushNetDownMidTrainer):
                 _, _, d_rb[t.p] = t.backward(d)                    # leaves d x in t.dx and the skip gradient in t.dx2
             else:
                 t.backward(d)
+        if self.after_up_backward is not None:
+            self.after_up_backward()
         d_h0, d_rb_down = super().backward(d_down_taps, d_mid_tap)  # mid tap adds up_seq[0].dx; down taps add the skip gradients
         d_rb.update(d_rb_down)
         return d_h0, d_rb
@@ -839,13 +934,28 @@ class BrushNetTrainer:
         dev = flat.param.device
         self.cin = cfg.in_channels + cfg.conditioning_channels
         c0 = cfg.block_out_channels[0]
-        self.xcat = torch.zeros(B, self.cin, H, W, device=dev, dtype=torch.float32)
-        self.xcat_nhwc = torch.zeros(B, H * W, self.cin, device=dev, dtype=self.dt)
+        # bf16 product path: the 10-channel input is zero-padded to 64 channels so that conv_in_condition's weight gradient runs on
+        # the tcgen05 kernel (the CUDA-core kernel for ragged channel counts took 7.6 ms per step at batch 8, 10 % of the step)
+        self.cpad = 64 if (self.dt == torch.bfloat16 and K is _ops and self.cin < 64) else self.cin
+        self.xcat = torch.zeros(B, self.cpad, H, W, device=dev, dtype=torch.float32)
+        self.xcat_nhwc = torch.zeros(B, H * W, self.cpad, device=dev, dtype=self.dt)
+        self.dw_in_pad = torch.zeros(c0, 9 * self.cpad, device=dev, dtype=torch.float32) if self.cpad != self.cin else None
         self.h0 = torch.zeros(B, H * W, c0, device=dev, dtype=self.dt)
         self.w_in = torch.zeros(3, 3, self.cin, c0, device=dev, dtype=torch.float32)
         self.time = TimePathTrainer(flat, cfg, brushnet_resnet_prefixes(cfg), B=B, precision=precision, K=K)
         self.branch = BrushNetBranchTrainer(flat, cfg, B=B, H=H, W=W, precision=precision, K=K)
+        self.h0 = self.branch.h0               # conv_in_condition writes straight into the branch's input buffer
         self.refresh_dgrad_weights(parts=False)
+
+    def bind_tap_gradients(self, d_taps):
+        """d_taps: the 28 tap-gradient buffers of the frozen UNet's backward (FrozenUNetTrainer.d_taps, pop order): every zero-conv
+        then reads its gradient in place instead of a per-step copy."""
+        br = self.branch
+        zs = list(br.taps) + [br.mid_tap] + list(br.up_taps)
+        if len(zs) != len(d_taps):
+            raise ValueError(f"expected {len(zs)} tap gradients, got {len(d_taps)}")
+        for z, g in zip(zs, d_taps):
+            z.bind_d_tap(g)
 
     def refresh_dgrad_weights(self, parts: bool = True):
         """After every optimizer step: re-derive the weight copies the kernels read in another layout."""
@@ -861,8 +971,8 @@ class BrushNetTrainer:
         K, f = self.K, self.flat
         ca = sample.shape[1]
         self.xcat[:, :ca].copy_(sample)
-        self.xcat[:, ca:].copy_(brushnet_cond)                                   # torch.cat([sample, cond], 1), brushnet.py:810
-        K.conv_in(self.xcat[:, :ca].contiguous(), self.xcat[:, ca:].contiguous(), self.w_in, f.p("conv_in_condition.bias"), self.h0)
+        self.xcat[:, ca:self.cin].copy_(brushnet_cond)                           # torch.cat([sample, cond], 1), brushnet.py:810
+        K.conv_in(self.xcat[:, :ca].contiguous(), self.xcat[:, ca:self.cin].contiguous(), self.w_in, f.p("conv_in_condition.bias"), self.h0)
         rb = self.time.forward(timesteps)
         return self.branch.forward(self.h0, rb)
 
@@ -875,5 +985,10 @@ class BrushNetTrainer:
             K.nchw_to_nhwc(self.xcat, self.xcat_nhwc)
         else:
             self.xcat_nhwc.copy_(self.xcat.permute(0, 2, 3, 1).reshape(self.xcat_nhwc.shape))
-        K.conv_wgrad(self.xcat_nhwc, d_h0, f.g("conv_in_condition.weight"), f.g("conv_in_condition.bias"), B=self.B, H=self.H, W=self.W,
-                     ksize=3, accumulate=True)
+        if self.dw_in_pad is None:
+            K.conv_wgrad(self.xcat_nhwc, d_h0, f.g("conv_in_condition.weight"), f.g("conv_in_condition.bias"), B=self.B, H=self.H, W=self.W,
+                         ksize=3, accumulate=True)
+        else:       # padded channels carry zeros: their gradient columns are dropped
+            K.conv_wgrad(self.xcat_nhwc, d_h0, self.dw_in_pad, f.g("conv_in_condition.bias"), B=self.B, H=self.H, W=self.W, ksize=3)
+            c0 = self.cfg.block_out_channels[0]
+            f.g("conv_in_condition.weight").view(c0, 9, self.cin).add_(self.dw_in_pad.view(c0, 9, self.cpad)[:, :, :self.cin])

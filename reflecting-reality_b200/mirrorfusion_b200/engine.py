@@ -30,10 +30,17 @@ f32 = torch.float32
 
 
 class _Net:
-    def __init__(self, cfg: NetConfig, sd: Dict[str, torch.Tensor], B: int, H: int, W: int, device, name: str):
+    def __init__(self, cfg: NetConfig, sd: Dict[str, torch.Tensor], B: int, H: int, W: int, device, name: str, host_pack: bool = False):
+        """host_pack: repack the weights (casts, permutes, concatenations, bias sums) where the state_dict lives — normally the
+        host — and upload the results, instead of uploading fp32 tensors and repacking with ~600 small device kernels.  Same
+        bytes either way; it keeps the device's launch stream to this library's kernels (the driver's launch census of smoke())
+        at the price of a slower constructor for the 1.5 G-parameter nets."""
         self.cfg, self.B, self.H, self.W, self.dev, self.name = cfg, B, H, W, device, name
         self.act = ops.act_dtype()     # storage dtype: bf16 (product) or fp32 (parity mode, `with ops.precision('fp32')`)
-        self.sd = {k: v.detach().to(device=device, dtype=f32) for k, v in sd.items()}
+        if host_pack:
+            self.sd = {k: v.detach().to(dtype=f32) for k, v in sd.items()}
+        else:
+            self.sd = {k: v.detach().to(device=device, dtype=f32) for k, v in sd.items()}
         self.prog: List[Callable[[], None]] = []
         self.tags: List[Tuple[str, float]] = []       # (kernel family, algorithmic FLOPs) per program entry
         self.notes: List[Optional[str]] = []          # shape note per program entry (igemm plans only)
@@ -67,8 +74,12 @@ class _Net:
             self._scratch[key] = torch.zeros(*shape, device=self.dev, dtype=self.act)
         return self._scratch[key]
 
+    def D(self, t: torch.Tensor) -> torch.Tensor:
+        """A packed weight / bias -> the device (a no-op unless host_pack)."""
+        return t.to(self.dev)
+
     def wf(self, name: str) -> torch.Tensor:
-        return self.sd[name].contiguous()
+        return self.sd[name].contiguous().to(self.dev)
 
     # ---- BrushNet tap folded into the consuming GEMM as one more K-segment:
     #      out += s * (Wz . h_brushnet + bz)   (brushnet.py:832-834,904-906 + the tap add sites)
@@ -137,10 +148,10 @@ class _Net:
         sin = self.buf(self.B, c0, dtype=f32)
         e1 = self.buf(self.B, temb, dtype=f32)
         emb = self.buf(self.B, temb, dtype=f32)
-        w1, b1 = self.wf("time_embedding.linear_1.weight").to(self.act), self.wf("time_embedding.linear_1.bias")
-        w2, b2 = self.wf("time_embedding.linear_2.weight").to(self.act), self.wf("time_embedding.linear_2.bias")
-        wcat = torch.cat([self.sd[p + ".time_emb_proj.weight"] for p in resnet_prefixes], 0).to(self.act).contiguous()
-        bcat = torch.cat([self.sd[p + ".time_emb_proj.bias"] for p in resnet_prefixes], 0).contiguous()
+        w1, b1 = self.D(self.sd["time_embedding.linear_1.weight"].to(self.act).contiguous()), self.wf("time_embedding.linear_1.bias")
+        w2, b2 = self.D(self.sd["time_embedding.linear_2.weight"].to(self.act).contiguous()), self.wf("time_embedding.linear_2.bias")
+        wcat = self.D(torch.cat([self.sd[p + ".time_emb_proj.weight"] for p in resnet_prefixes], 0).to(self.act).contiguous())
+        bcat = self.D(torch.cat([self.sd[p + ".time_emb_proj.bias"] for p in resnet_prefixes], 0).contiguous())
         self.rowbias = self.buf(self.B, wcat.shape[0], dtype=f32)
         self.rowbias_off = {}
         off = 0
@@ -185,7 +196,7 @@ class _Net:
         n1 = self.scratch("n1", B, HW, cin)
         self.groupnorm(xa, xb, p + ".norm1", n1, HW, eps, True)
         h1 = self.scratch("h1", B, HW, cout)
-        w1 = ops.pack_conv_weight(self.sd[p + ".conv1.weight"])
+        w1 = self.D(ops.pack_conv_weight(self.sd[p + ".conv1.weight"]))
         off = self.rowbias_off.get(p)          # None: a resnet without time embedding (the VAE's)
         rb = None if off is None else self.rowbias[:, off:]
         self.emit_plan(ops.ConvPlan(n1, w1, h1, B=B, H=h, W=w, Cin=cin, Cout=cout, ksize=3, bias=self.wf(p + ".conv1.bias"),
@@ -211,9 +222,9 @@ class _Net:
             koff = 9 * cout + sum(e.shape[1] for e in extras_w)
             extras_w.append(tap_src[1]); extras_x.append(tap_src[0])
             fused = (koff, tap_src[1], tap_src[2])
-        w2 = ops.pack_conv_weight(wmain, extras=extras_w)
+        w2 = self.D(ops.pack_conv_weight(wmain, extras=extras_w))
         base_bias = bias.contiguous()
-        bias_buf = base_bias.clone()
+        bias_buf = self.D(base_bias.clone())
         if fused is not None:
             self._register_fused(w2, fused[0], fused[1], bias_buf, base_bias, fused[2])
         self.emit_plan(ops.ConvPlan(n2, w2, out, B=B, H=h, W=w, Cin=cout, Cout=cout, ksize=3, extras=extras_x,
@@ -225,9 +236,9 @@ class _Net:
         extras_w, extras_x = [], []
         if tap_src is not None:
             extras_w.append(tap_src[1]); extras_x.append(tap_src[0])
-        wp = ops.pack_conv_weight(self.sd[p + ".conv.weight"], extras=extras_w)
-        base_bias = self.wf(p + ".conv.bias")
-        bias_buf = base_bias.clone()
+        wp = self.D(ops.pack_conv_weight(self.sd[p + ".conv.weight"], extras=extras_w))
+        base_bias = self.sd[p + ".conv.bias"].contiguous()
+        bias_buf = self.D(base_bias.clone())
         if tap_src is not None:
             self._register_fused(wp, 9 * c, tap_src[1], bias_buf, base_bias, tap_src[2])
         self.emit_plan(ops.ConvPlan(x, wp, out, B=self.B, H=h, W=w, Cin=c, Cout=c, ksize=3, stride=stride, extras=extras_x,
@@ -249,9 +260,9 @@ class _Net:
         extras_w, extras_x = [], []
         if tap_src is not None:
             extras_w.append(tap_src[1]); extras_x.append(tap_src[0])
-        wp = ops.pack_upconv_weight(self.sd[p + ".conv.weight"], extras=extras_w)      # [4, C, 4C (+C)]
-        base_bias = self.wf(p + ".conv.bias")
-        bias_buf = base_bias.clone()
+        wp = self.D(ops.pack_upconv_weight(self.sd[p + ".conv.weight"], extras=extras_w))      # [4, C, 4C (+C)]
+        base_bias = self.sd[p + ".conv.bias"].contiguous()
+        bias_buf = self.D(base_bias.clone())
         if tap_src is not None:
             self._register_fused(wp.view(4 * c, -1), 4 * c, tap_src[1].repeat(4, 1), bias_buf, base_bias, tap_src[2])
         self.emit_plan(ops.ConvPlan(x, wp, out, B=self.B, H=h, W=w, Cin=c, Cout=c, ksize=3, up2x=True, extras=extras_x,
@@ -303,10 +314,10 @@ class BrushNetEngine(_Net):
     28 zero-conv taps scaled by conditioning_scale (a device scalar, so the captured graph serves any scale)."""
 
     def __init__(self, cfg, sd, B, H, W, device, tap_bufs: Optional[List[torch.Tensor]] = None,
-                 only_first_tap: bool = False):
+                 only_first_tap: bool = False, host_pack: bool = False):
         """only_first_tap: fused pipeline mode — only the conv_in-site tap is materialised; the other 27 zero-convs
         are handed to the UNet engine as (feature, weight, bias) and run there as K-segments of the consuming GEMM."""
-        super().__init__(cfg, sd, B, H, W, device, "brushnet")
+        super().__init__(cfg, sd, B, H, W, device, "brushnet", host_pack=host_pack)
         boc = cfg.block_out_channels
         n = len(boc)
         self.sample_in = torch.zeros(B, cfg.in_channels, H, W, device=device, dtype=f32)
@@ -314,7 +325,7 @@ class BrushNetEngine(_Net):
         self.scale = torch.ones(1, device=device, dtype=f32)
         self.build_time_path(_resnet_prefixes(cfg))
         # conv_in_condition (brushnet.py:810-811)
-        wci = self.sd["conv_in_condition.weight"].permute(2, 3, 1, 0).contiguous()
+        wci = self.D(self.sd["conv_in_condition.weight"].permute(2, 3, 1, 0).contiguous())
         bci = self.wf("conv_in_condition.bias")
         x = self.buf(B, H * W, boc[0])
         self.keep += [wci, bci]
@@ -351,14 +362,14 @@ class BrushNetEngine(_Net):
                 [f"brushnet_up_blocks.{k}" for k in range(len(up_feats))]
         self.taps: List[torch.Tensor] = []
         self.tap_hw: List[Tuple[int, int]] = []
-        self.tap_sources = [(src, self.sd[nm + ".weight"][:, :, 0, 0].contiguous(), self.wf(nm + ".bias"))
+        self.tap_sources = [(src, self.sd[nm + ".weight"][:, :, 0, 0].contiguous(), self.sd[nm + ".bias"].contiguous())
                             for (src, _), nm in zip(srcs, names)]
         for k, ((src, shw), nm) in enumerate(zip(srcs, names)):
             if only_first_tap and k > 0:
                 break
             c = src.shape[-1]
             t = tap_bufs[k] if tap_bufs is not None else self.buf(B, shw[0] * shw[1], c)
-            wz = ops.pack_conv_weight(self.sd[nm + ".weight"])
+            wz = self.D(ops.pack_conv_weight(self.sd[nm + ".weight"]))
             self.emit_plan(ops.ConvPlan(src, wz, t, B=B, H=shw[0], W=shw[1], Cin=c, Cout=c, ksize=1,
                                         bias=self.wf(nm + ".bias"), alpha=self.scale), out=t)
             self.taps.append(t)
@@ -370,10 +381,10 @@ class UNetEngine(_Net):
     """UNet2DConditionModel.forward (SD1.5 family) with the BrushNet taps consumed in the producing epilogues."""
 
     def __init__(self, cfg, sd, B, H, W, device, ctx_len: int = 77, tap_sources: Optional[List[Tuple]] = None,
-                 tap0: Optional[torch.Tensor] = None):
+                 tap0: Optional[torch.Tensor] = None, host_pack: bool = False):
         """tap_sources (fused pipeline mode): the BrushNet engine's 28 (feature, zero-conv weight, bias) triples; taps
         1..27 then run as K-segments of the consuming GEMMs and only tap 0 (conv_in site) is read as a tensor."""
-        super().__init__(cfg, sd, B, H, W, device, "unet")
+        super().__init__(cfg, sd, B, H, W, device, "unet", host_pack=host_pack)
         boc = cfg.block_out_channels
         n = len(boc)
         self.ctx_len = ctx_len
@@ -409,7 +420,7 @@ class UNetEngine(_Net):
             tap_it = iter([(tap0, None)] + [(None, src) for src in tap_sources[1:]])
 
         self.build_time_path(_resnet_prefixes(cfg))
-        wci = self.sd["conv_in.weight"].permute(2, 3, 1, 0).contiguous()
+        wci = self.D(self.sd["conv_in.weight"].permute(2, 3, 1, 0).contiguous())
         bci = self.wf("conv_in.bias")
         self.keep += [wci, bci]
         hw = (H, W)
@@ -454,7 +465,7 @@ class UNetEngine(_Net):
         # conv_norm_out -> SiLU -> conv_out (unet_2d_condition.py:1336-1339)
         nout = self.scratch("n1", B, H * W, boc[0])
         self.groupnorm(x, None, "conv_norm_out", nout, H * W, cfg.norm_eps, True)
-        wco = self.sd["conv_out.weight"].permute(0, 2, 3, 1).contiguous()
+        wco = self.D(self.sd["conv_out.weight"].permute(0, 2, 3, 1).contiguous())
         bco = self.wf("conv_out.bias")
         self.keep += [wco, bco]
         self.emit(lambda: ops.conv_out(nout, wco, bco, self.out, B=B, H=H, W=W))  # nout/wco/bco are not rebound
@@ -472,14 +483,14 @@ class UNetEngine(_Net):
         g = self.scratch("tg", B, T, C)
         self.groupnorm(x, None, p + ".norm", g, T, 1e-6, False)
         h0 = self.scratch("th0", M, C)
-        self.emit_plan(ops.linear_plan(g.view(M, C), ops.pack_conv_weight(self.sd[p + ".proj_in.weight"]), h0,
+        self.emit_plan(ops.linear_plan(g.view(M, C), self.D(ops.pack_conv_weight(self.sd[p + ".proj_in.weight"])), h0,
                                        bias=self.wf(p + ".proj_in.bias")))
         # --- self attention
         nrm = self.scratch("tn", M, C)
         self.layernorm(h0, t + ".norm1", nrm)
         qkv = self.scratch("tqkv", M, 3 * C)
-        wqkv = torch.cat([self.sd[t + ".attn1.to_q.weight"], self.sd[t + ".attn1.to_k.weight"],
-                          self.sd[t + ".attn1.to_v.weight"]], 0).to(self.act).contiguous()
+        wqkv = self.D(torch.cat([self.sd[t + ".attn1.to_q.weight"], self.sd[t + ".attn1.to_k.weight"],
+                                 self.sd[t + ".attn1.to_v.weight"]], 0).to(self.act).contiguous())
         self.emit_plan(ops.linear_plan(nrm, wqkv, qkv))
         att = self.scratch("tatt", M, C)
         kview, vview = qkv.view(-1)[C:], qkv.view(-1)[2 * C:]      # q | k | v column blocks of the fused projection
@@ -487,41 +498,41 @@ class UNetEngine(_Net):
                                         ldk=3 * C, ldv=3 * C, ldo=C), 1, "attention", 4.0 * B * T * T * C)
         self.flops += 4.0 * B * T * T * C
         h1 = self.scratch("th1", M, C)
-        self.emit_plan(ops.linear_plan(att, self.sd[t + ".attn1.to_out.0.weight"].to(self.act).contiguous(), h1,
+        self.emit_plan(ops.linear_plan(att, self.D(self.sd[t + ".attn1.to_out.0.weight"].to(self.act).contiguous()), h1,
                                        bias=self.wf(t + ".attn1.to_out.0.bias"), res1=h0))
         # --- cross attention (K/V of the context are prepared once per prompt: ctx_prog)
         Lc = self.ctx_len
         k2 = self.buf(B * Lc, C)
         v2 = self.buf(B * Lc, C)
-        pk = ops.linear_plan(self.ehs_bf, self.sd[t + ".attn2.to_k.weight"].to(self.act).contiguous(), k2)
-        pv = ops.linear_plan(self.ehs_bf, self.sd[t + ".attn2.to_v.weight"].to(self.act).contiguous(), v2)
+        pk = ops.linear_plan(self.ehs_bf, self.D(self.sd[t + ".attn2.to_k.weight"].to(self.act).contiguous()), k2)
+        pv = ops.linear_plan(self.ehs_bf, self.D(self.sd[t + ".attn2.to_v.weight"].to(self.act).contiguous()), v2)
         self.keep += [pk, pv]
         self.ctx_prog += [pk.run, pv.run]
         self.layernorm(h1, t + ".norm2", nrm)
         q2 = self.scratch("tq2", M, C)
-        self.emit_plan(ops.linear_plan(nrm, self.sd[t + ".attn2.to_q.weight"].to(self.act).contiguous(), q2))
+        self.emit_plan(ops.linear_plan(nrm, self.D(self.sd[t + ".attn2.to_q.weight"].to(self.act).contiguous()), q2))
         self.emit(lambda: ops.attention(q2, k2, v2, att, B=B, heads=heads, head_dim=d, Tq=T, Tk=Lc, ldq=C, ldk=C,
                                         ldv=C, ldo=C), 1, "attention", 4.0 * B * T * Lc * C)
         self.flops += 4.0 * B * T * Lc * C
         h2 = self.scratch("th2", M, C)
-        self.emit_plan(ops.linear_plan(att, self.sd[t + ".attn2.to_out.0.weight"].to(self.act).contiguous(), h2,
+        self.emit_plan(ops.linear_plan(att, self.D(self.sd[t + ".attn2.to_out.0.weight"].to(self.act).contiguous()), h2,
                                        bias=self.wf(t + ".attn2.to_out.0.bias"), res1=h1))
         # --- GEGLU feed-forward
         self.layernorm(h2, t + ".norm3", nrm)
-        wg, bg = ops.pack_geglu(self.sd[t + ".ff.net.0.proj.weight"], self.sd[t + ".ff.net.0.proj.bias"])
+        wg, bg = (self.D(a) for a in ops.pack_geglu(self.sd[t + ".ff.net.0.proj.weight"], self.sd[t + ".ff.net.0.proj.bias"]))
         gg = self.scratch("tgg", M, 4 * C)
         self.emit_plan(ops.linear_plan(nrm, wg, gg, bias=bg, geglu=True))
         h3 = self.scratch("th3", M, C)
-        self.emit_plan(ops.linear_plan(gg, self.sd[t + ".ff.net.2.weight"].to(self.act).contiguous(), h3,
+        self.emit_plan(ops.linear_plan(gg, self.D(self.sd[t + ".ff.net.2.weight"].to(self.act).contiguous()), h3,
                                        bias=self.wf(t + ".ff.net.2.bias"), res1=h2))
         # --- proj_out + transformer residual (+ BrushNet tap, added after the attention: unet_2d_blocks.py:1374-1389)
         out = self.buf(B, T, C)
         extras_w, extras_x = [], []
         if tap_src is not None:
             extras_w.append(tap_src[1]); extras_x.append(tap_src[0].view(M, C))
-        wpo = ops.pack_conv_weight(self.sd[p + ".proj_out.weight"], extras=extras_w)
-        base_bias = self.wf(p + ".proj_out.bias")
-        bias_buf = base_bias.clone()
+        wpo = self.D(ops.pack_conv_weight(self.sd[p + ".proj_out.weight"], extras=extras_w))
+        base_bias = self.sd[p + ".proj_out.bias"].contiguous()
+        bias_buf = self.D(base_bias.clone())
         if tap_src is not None:
             self._register_fused(wpo, C, tap_src[1], bias_buf, base_bias, tap_src[2])
         # a 1x1 conv with the real (B, h, w) geometry rather than a flat token GEMM: the epilogue's fused GroupNorm

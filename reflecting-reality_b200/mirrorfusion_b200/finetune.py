@@ -42,6 +42,7 @@ class FineTuneStep:
         br = self.brushnet.branch
         taps = [z.tap for z in br.taps] + [br.mid_tap.tap] + [z.tap for z in br.up_taps]       # the reference's pop order: 12, mid, 15
         self.unet = FrozenUNetTrainer(cfg, unet_sd, taps, B=batch, H=H, W=W, device=self.dev, ctx_len=ctx_len)
+        self.brushnet.bind_tap_gradients(self.unet.d_taps)      # the zero-convs read the UNet's tap gradients in place
         self.opt = B200AdamW(self.flat, lr=lr, betas=betas, eps=eps, weight_decay=weight_decay)
         self.lr_sched = LRSchedule(self.opt, lr_schedule, lr_warmup_steps, max_train_steps)
         self.noise_sched = NoiseSchedule(self.dev)
@@ -52,6 +53,13 @@ class FineTuneStep:
         self.world = 1
         if group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
             self.world = torch.distributed.get_world_size(group)
+        # Overlap: the up path's parameters sit at the tail of the flat buffer and their gradients are complete once the up
+        # path's backward is done (the backward runs up -> mid -> down), so that range — 60 % of the 618.8 M gradients — is
+        # all-reduced on a side stream while the mid / down blocks are still in their backward pass; the head follows in optimize().
+        self._up_off = min(off for name, (off, _) in self.flat.table.items() if name.startswith(("up_blocks.", "brushnet_up_blocks.")))
+        self._side = torch.cuda.Stream(device=self.dev) if self.world > 1 else None
+        if self.world > 1:
+            br.after_up_backward = self._allreduce_tail
 
     # the three phases are separate so a caller (bench.py, the tests) can time / inspect them
     def forward(self, latents, noise, timesteps, conditioning_latents, encoder_hidden_states):
@@ -71,9 +79,16 @@ class FineTuneStep:
         dd, dm, du = self.unet.backward()
         self.brushnet.backward(dd, dm, du)
 
+    def _allreduce_tail(self):
+        cur = torch.cuda.current_stream()
+        self._side.wait_stream(cur)
+        with torch.cuda.stream(self._side):
+            sharding.allreduce_flat_grads(self.flat.grad[self._up_off:], group=self.group)
+
     def optimize(self):
         if self.world > 1:
-            sharding.allreduce_flat_grads(self.flat.grad, group=self.group)
+            sharding.allreduce_flat_grads(self.flat.grad[:self._up_off], group=self.group)
+            torch.cuda.current_stream().wait_stream(self._side)
         self.opt.step(max_grad_norm=self.max_grad_norm, grad_scale=1.0 / self.world)
         self.lr_sched.step()
         self.brushnet.refresh_dgrad_weights()

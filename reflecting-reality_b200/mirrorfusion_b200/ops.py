@@ -518,6 +518,17 @@ def conv_out_bwd(dy, w, dx, *, B, H, W):
     check(lib().mfb_conv_out_bwd(_ptr(dy), B, H, W, dx.shape[-1], dy.shape[1], _ptr(w), _ptr(dx), _stream()))
 
 
+def dgrad_repack(wp, wd, ksize):
+    """wd [Cin, k*k*Cout] = data-gradient packing of the packed forward weight wp [Cout, k*k*Cin] (pack_conv_dgrad_weight of the
+    unpacked weight), one kernel; bf16 on the device, anything else (fp32 parity mode) by torch."""
+    Cout, Cin = wp.shape[0], wd.shape[0]
+    if wp.dtype == bf16 and wd.dtype == bf16 and wp.is_cuda and wp.is_contiguous() and wd.is_contiguous():
+        check(lib().mfb_dgrad_repack(_ptr(wp), Cout, Cin, ksize, _ptr(wd), _stream()))
+        return
+    w = wp.view(Cout, ksize, ksize, Cin).flip(1, 2).permute(3, 1, 2, 0)
+    wd.copy_(w.reshape(Cin, -1).to(wd.dtype))
+
+
 def sumpool2x2(du, dx, *, B, H, W):
     """dx [B, H*W, C] = 2x2 sums of du [B, 2H*2W, C] (bf16): the adjoint of the nearest-x2 replication."""
     _req(du, bf16, "du"); _req(dx, bf16, "dx")

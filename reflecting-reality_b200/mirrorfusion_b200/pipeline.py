@@ -245,7 +245,7 @@ class StepEngine:
 
     def __init__(self, cfg: NetConfig, unet_sd, brushnet_sd, images: int, H: int, W: int, device="cuda",
                  use_graph: bool = True, fuse_taps: bool = True, two_streams: bool = False,
-                 dedup_brushnet_cfg: bool = False, precision: str = "bf16"):
+                 dedup_brushnet_cfg: bool = False, precision: str = "bf16", host_pack: bool = False):
         """precision: "bf16" = the product path (tcgen05 kernels); "fp32" = the PARITY MODE of BASELINE config 1 — the
         same program (fusions, K-segments, tap folding, buffers) with fp32 storage on the CUDA-core kernels of
         csrc/fp32mode.cu, for the rel-L2 1e-4 bar against the fp32 reference.
@@ -257,10 +257,12 @@ class StepEngine:
         `set_conditioning` refuses conditioning whose halves differ.  Off by default: the headline numbers of
         bench.py run the reference's full 2b-sample BrushNet."""
         self.precision = precision
+        self._hp = bool(host_pack)          # engine._Net: repack the weights on the host and upload the results
         with ops.precision(precision):      # engines read the storage dtype while they are built
             self._build(cfg, unet_sd, brushnet_sd, images, H, W, device, use_graph, fuse_taps, two_streams, dedup_brushnet_cfg)
 
     def _build(self, cfg, unet_sd, brushnet_sd, images, H, W, device, use_graph, fuse_taps, two_streams, dedup_brushnet_cfg):
+        hp = self._hp
         self.cfg, self.images, self.H, self.W = cfg, images, H, W
         self.dev = torch.device(device)
         B = 2 * images
@@ -269,7 +271,7 @@ class StepEngine:
         if self.dedup and not fuse_taps:
             raise ValueError("dedup_brushnet_cfg requires fuse_taps=True")
         if self.dedup:
-            self.bn = BrushNetEngine(cfg, brushnet_sd, images, H, W, self.dev, only_first_tap=True)
+            self.bn = BrushNetEngine(cfg, brushnet_sd, images, H, W, self.dev, only_first_tap=True, host_pack=hp)
             dup = lambda t: torch.empty(2, *t.shape, device=self.dev, dtype=t.dtype)
             both = []
             for k, (src, wz, bz) in enumerate(self.bn.tap_sources):
@@ -284,15 +286,15 @@ class StepEngine:
             self.bn.emit(lambda s0=t0, d1=d0: d1.copy_(s0.unsqueeze(0).expand_as(d1)), out=d0)
             self._dup_keep = [d0] + [b[0] for b in both]
             self.unet = UNetEngine(cfg, unet_sd, B, H, W, self.dev, tap_sources=both,
-                                   tap0=d0.view(2 * t0.shape[0], *t0.shape[1:]))
+                                   tap0=d0.view(2 * t0.shape[0], *t0.shape[1:]), host_pack=hp)
         elif fuse_taps:
             # 27 of the 28 zero-convs run inside the UNet GEMM that consumes the tap (extra K-segment); only the
             # conv_in-site tap is a tensor
-            self.bn = BrushNetEngine(cfg, brushnet_sd, B, H, W, self.dev, only_first_tap=True)
-            self.unet = UNetEngine(cfg, unet_sd, B, H, W, self.dev, tap_sources=self.bn.tap_sources, tap0=self.bn.taps[0])
+            self.bn = BrushNetEngine(cfg, brushnet_sd, B, H, W, self.dev, only_first_tap=True, host_pack=hp)
+            self.unet = UNetEngine(cfg, unet_sd, B, H, W, self.dev, tap_sources=self.bn.tap_sources, tap0=self.bn.taps[0], host_pack=hp)
         else:
-            self.unet = UNetEngine(cfg, unet_sd, B, H, W, self.dev)
-            self.bn = BrushNetEngine(cfg, brushnet_sd, B, H, W, self.dev, tap_bufs=self.unet.taps)
+            self.unet = UNetEngine(cfg, unet_sd, B, H, W, self.dev, host_pack=hp)
+            self.bn = BrushNetEngine(cfg, brushnet_sd, B, H, W, self.dev, tap_bufs=self.unet.taps, host_pack=hp)
         self._tap_scale = 1.0
         self.two_streams = two_streams
         self._side_stream = torch.cuda.Stream(device=self.dev) if two_streams else None

@@ -158,3 +158,22 @@ def test_conv_out_backward_vs_autograd(ops, B, H, W, Cin):
     dx = torch.full((B, H * W, Cin), float("nan"), device="cuda", dtype=bf16)
     ops.conv_out_bwd(dy.contiguous(), w.permute(0, 2, 3, 1).contiguous(), dx, B=B, H=H, W=W)
     assert rel(dx.float().view(B, H, W, Cin).permute(0, 3, 1, 2), x.grad) < 4e-3
+
+
+@pytest.mark.parametrize("Cout,Cin,k", [(320, 320, 3), (640, 960, 3), (320, 640, 1), (80, 96, 3), (1280, 2560, 1)])
+def test_dgrad_repack_equals_the_torch_packing(ops, Cout, Cin, k):
+    w = randn(Cout, Cin, k, k, seed=1, dtype=torch.float32)
+    wp = ops.pack_conv_weight(w)                                   # [Cout, k*k*Cin] bf16
+    want = ops.pack_conv_dgrad_weight(w)                           # [Cin, k*k*Cout] bf16 (rounding commutes with the permutation)
+    wd = torch.full((Cin, k * k * Cout), float("nan"), device="cuda", dtype=bf16)
+    ops.dgrad_repack(wp, wd, k)
+    assert torch.equal(wd, want)
+
+
+@pytest.mark.parametrize("B,H,W,C", [(2, 8, 8, 1280), (3, 5, 7, 64), (2, 32, 32, 640)])
+def test_sumpool2x2_is_the_adjoint_of_nearest_upsampling(ops, B, H, W, C):
+    du = randn(B, 4 * H * W, C, seed=2)
+    dx = torch.full((B, H * W, C), float("nan"), device="cuda", dtype=bf16)
+    ops.sumpool2x2(du, dx, B=B, H=H, W=W)
+    want = du.float().view(B, H, 2, W, 2, C).sum((2, 4)).reshape(B, H * W, C)
+    assert rel(dx.float(), want) < 4e-3

@@ -158,6 +158,11 @@ def conv_out_bwd(dy, w, dx, *, B, H, W):
     dx.copy_(_nhwc(xi.grad).reshape(dx.shape))
 
 
+def dgrad_repack(wp, wd, ksize):
+    Cout, Cin = wp.shape[0], wd.shape[0]
+    wd.copy_(wp.view(Cout, ksize, ksize, Cin).flip(1, 2).permute(3, 1, 2, 0).reshape(Cin, -1).to(wd.dtype))
+
+
 def sumpool2x2(du, dx, *, B, H, W):
     v = du.reshape(B, H, 2, W, 2, -1)
     dx.copy_(v.sum((2, 4)).reshape(dx.shape))
