@@ -1010,8 +1010,10 @@ extern "C" int mfb_conv_wgrad_tc(const void* x, const void* dy, int B, int H, in
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (use_wgrad5(Cin, Cout)) {
         mfb::wgrad5_plan(B, Ho, Wo, Cin, Cout, ksize, &slices, &per);
-        const int rc = mfb::wgrad5_run(x, dy, B, Ho, Wo, Cin, Cout, ksize, stride, ws, st);
+        const bool direct = slices == 1;       // one slice: the epilogue writes (adds) straight into dw
+        const int rc = mfb::wgrad5_run(x, dy, B, Ho, Wo, Cin, Cout, ksize, stride, direct ? dw : ws, direct ? accumulate : 0, st);
         if (rc) return rc;
+        if (direct) slices = 0;
     } else {
         wgrad_tc_plan(B, Ho, Wo, Cin, Cout, ksize, &slices, &per);
         const int mtiles = (Cout + TC_BM - 1) / TC_BM, ntiles = (Cin + TC_BN - 1) / TC_BN;
@@ -1026,8 +1028,9 @@ extern "C" int mfb_conv_wgrad_tc(const void* x, const void* dy, int B, int H, in
                              per, ws));
     }
     const long long n = static_cast<long long>(Cout) * ktot;
-    MFB_CUDA_OK(launch_k(wgrad_reduce_kernel, dim3(chunks_for(n, 256, 148 * 8)), dim3(256), 0, st, 1, static_cast<const float*>(ws), slices,
-                         n, dw, accumulate));
+    if (slices > 0)
+        MFB_CUDA_OK(launch_k(wgrad_reduce_kernel, dim3(chunks_for(n, 256, 148 * 8)), dim3(256), 0, st, 1, static_cast<const float*>(ws), slices,
+                             n, dw, accumulate));
     if (dbias) {
         float* bpart = ws + static_cast<size_t>(slices) * n;
         const long long P = static_cast<long long>(B) * Ho * Wo;

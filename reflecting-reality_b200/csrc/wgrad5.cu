@@ -33,6 +33,7 @@ struct Wgrad5Params {
     int tw, th, tn, tiles_w, tiles_h, ptiles;      // 64-pixel tile box and the pixel-tile grid
     int tiles_per_slice;
     float* part;                 // [slices][Cout][ktot]
+    int accumulate;              // single slice writing straight into dw: add to what is there (one writer per element: deterministic)
 };
 
 template <int BN>
@@ -145,9 +146,16 @@ __global__ void __launch_bounds__(192, 1) wgrad5_kernel(const __grid_constant__ 
             if (co < p.Cout) {
 #pragma unroll
                 for (int q = 0; q < 4; ++q)
-                    if (ci0 + c * 16 + q * 4 < p.Cin)      // Cin % 8 == 0: a float4 is valid as a whole
-                        *reinterpret_cast<float4*>(dst + c * 16 + q * 4) =
-                            make_float4(__uint_as_float(v[q * 4]), __uint_as_float(v[q * 4 + 1]), __uint_as_float(v[q * 4 + 2]), __uint_as_float(v[q * 4 + 3]));
+                    if (ci0 + c * 16 + q * 4 < p.Cin) {    // Cin % 8 == 0: a float4 is valid as a whole
+                        float4 o = make_float4(__uint_as_float(v[q * 4]), __uint_as_float(v[q * 4 + 1]), __uint_as_float(v[q * 4 + 2]),
+                                               __uint_as_float(v[q * 4 + 3]));
+                        float4* d4 = reinterpret_cast<float4*>(dst + c * 16 + q * 4);
+                        if (p.accumulate) {
+                            const float4 old = *d4;
+                            o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+                        }
+                        *d4 = o;
+                    }
             }
         }
         tc_fence_before();
@@ -223,9 +231,11 @@ static int encode_view(CUtensorMap* tm, const void* base, int C, int Wf, int Hf,
     return encode_tmap_bf16(tm, b, 4, dims, str, box, 128);
 }
 
-int wgrad5_run(const void* x, const void* dy, int B, int Ho, int Wo, int Cin, int Cout, int ksize, int stride, float* part, cudaStream_t st) {
+int wgrad5_run(const void* x, const void* dy, int B, int Ho, int Wo, int Cin, int Cout, int ksize, int stride, float* part, int accumulate,
+               cudaStream_t st) {
     Wgrad5Params p;
     memset(&p, 0, sizeof(p));
+    p.accumulate = accumulate;
     pick_tile64(Wo, Ho, B, &p.tw, &p.th, &p.tn);
     p.tiles_w = (Wo + p.tw - 1) / p.tw;
     p.tiles_h = (Ho + p.th - 1) / p.th;

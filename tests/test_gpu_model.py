@@ -14,8 +14,18 @@ pytestmark = pytest.mark.gpu
 from mirrorfusion_b200.config import SD15, TINY
 from mirrorfusion_b200.synth import make_inputs, make_state_dict
 
-BF16_TOL = 1e-2          # north_star bar, applied to the SD1.5-shaped nets
-TINY_TOL = 1.5e-2        # the 64/128-channel TINY nets at random init are less well conditioned (fewer terms per sum)
+BF16_TOL = 1e-2          # north_star bar: applied as is to the SD1.5-shaped nets
+
+
+def tiny_bar(usd, bsd, cfg, x, t, ehs, cond, scale=1.0, ref=None):
+    """Bar for the 64/128-channel TINY nets.  On them the error FLOOR of bf16 storage — the fp32 oracle made to round weights, GEMM
+    inputs and GEMM outputs to bf16 and nothing else (oracle/bf16_floor.py) — is itself 0.98-1.03e-2, i.e. AT the north_star bar, so
+    an absolute 1e-2 would test the seed, not the kernels.  The CUDA path must stay within 10 % of that floor (or under 1e-2)."""
+    from oracle import bf16_floor as BF
+    to = lambda v: v.detach().float().cpu()
+    floor = BF.noise_pred_floor({k: to(v) for k, v in usd.items()}, {k: to(v) for k, v in bsd.items()}, cfg, to(x), t, to(ehs), to(cond),
+                                scale, ref=None if ref is None else to(ref))
+    return max(BF16_TOL, 1.10 * floor), floor
 
 
 def record(name, **vals):
@@ -65,8 +75,10 @@ def test_tiny_step_vs_reference_golden(P, golden_dir):
     e = rel(eps, g["noise_pred"])
     plain = unet(x, t, encoder_hidden_states=ehs, return_dict=False)[0]
     e2 = rel(plain, g["noise_pred_no_taps"])
-    record("tiny_step_vs_reference", noise_pred=e, noise_pred_no_taps=e2, worst_tap=max(errs))
-    assert e < TINY_TOL and e2 < TINY_TOL
+    usd, bsd = make_state_dict(cfg, "unet"), make_state_dict(cfg, "brushnet")
+    bar, floor = tiny_bar(usd, bsd, cfg, x, torch.tensor(int(g["t"])), ehs, cond, float(g["scale"]), ref=torch.from_numpy(g["noise_pred"]))
+    record("tiny_step_vs_reference", noise_pred=e, noise_pred_no_taps=e2, worst_tap=max(errs), bf16_storage_floor=floor)
+    assert e < bar and e2 < bar, (e, e2, floor)
 
 
 def test_sd15_step_vs_reference_golden(P, golden_dir):
@@ -134,8 +146,11 @@ def test_fused_taps_match_unfused_and_oracle(P):
         ref, _ = O.noise_pred_step(usd, bsd, cfg, torch.cat([inp["latents"]] * 2), sched.timesteps[0], inp["prompt_embeds"],
                                    inp["conditioning_latents"], 0.6)
     e_f, e_u = rel(outs[True][0], ref), rel(outs[False][0], ref)
-    record("tiny_fused_vs_unfused", fused_vs_oracle=e_f, unfused_vs_oracle=e_u, fused_vs_unfused=rel(outs[True][0], outs[False][0]))
-    assert e_f < TINY_TOL and e_u < TINY_TOL
+    bar, floor = tiny_bar(usd, bsd, cfg, torch.cat([inp["latents"]] * 2), sched.timesteps[0], inp["prompt_embeds"],
+                          inp["conditioning_latents"], 0.6, ref=ref)
+    record("tiny_fused_vs_unfused", fused_vs_oracle=e_f, unfused_vs_oracle=e_u, fused_vs_unfused=rel(outs[True][0], outs[False][0]),
+           bf16_storage_floor=floor)
+    assert e_f < bar and e_u < bar, (e_f, e_u, floor)
     assert rel(outs[True][0], outs[False][0]) < 2e-2      # two independent bf16 rounding histories
 
 
@@ -186,8 +201,10 @@ def test_non_square_latents_vs_oracle(P, H, W, images):
         ref, _ = O.noise_pred_step(usd, bsd, cfg, torch.cat([inp["latents"]] * 2), 481.0, inp["prompt_embeds"],
                                    inp["conditioning_latents"], 1.0)
     e = rel(eng.unet.out, ref)
-    record("tiny_non_square_vs_oracle", H=H, W=W, images=images, noise_pred=e)
-    assert e < TINY_TOL
+    bar, floor = tiny_bar(usd, bsd, cfg, torch.cat([inp["latents"]] * 2), 481.0, inp["prompt_embeds"], inp["conditioning_latents"], 1.0,
+                          ref=ref)
+    record("tiny_non_square_vs_oracle", H=H, W=W, images=images, noise_pred=e, bf16_storage_floor=floor)
+    assert e < bar, (e, floor)
 
 
 def test_sd15_fused_step_vs_reference_golden(P, golden_dir):
@@ -223,9 +240,10 @@ def test_batched_step_vs_oracle_on_gpu(P):
     bsd_g = {k: v.cuda() for k, v in bsd.items()}
     with torch.no_grad():
         ref, (rd, rm, ru) = O.noise_pred_step(usd_g, bsd_g, cfg, x, tvec.cuda(), ehs, cond, 0.7)
-    record("tiny_batched_vs_oracle_gpu", noise_pred=rel(eps, ref), mid_tap=rel(m, rm))
+    bar, floor = tiny_bar(usd, bsd, cfg, x, tvec, ehs, cond, 0.7, ref=ref)
+    record("tiny_batched_vs_oracle_gpu", noise_pred=rel(eps, ref), mid_tap=rel(m, rm), bf16_storage_floor=floor)
     assert rel(m, rm) < 2e-2
-    assert rel(eps, ref) < TINY_TOL
+    assert rel(eps, ref) < bar, (rel(eps, ref), floor)
 
 
 class _FakeAttention(torch.nn.Module):
