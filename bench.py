@@ -300,6 +300,13 @@ def run_train(args, rank, world, local_rank):
     ft.optimize()
     ev[3].record(stream)
     barrier()
+    # data parallel sanity: every replica must hold bit-identical parameters after the same number of all-reduced steps
+    in_sync = None
+    if world > 1:
+        cs = torch.stack([ft.flat.param.double().sum(), ft.flat.param.double().abs().sum()]).to(dev)
+        allcs = [torch.empty_like(cs) for _ in range(world)]
+        dist.all_gather(allcs, cs)
+        in_sync = all(torch.equal(c, allcs[0]) for c in allcs)
     if rank != 0:
         return
     peaks = load_peaks()
@@ -324,7 +331,7 @@ def run_train(args, rank, world, local_rank):
                      "phases_ms": {"forward": ev[0].elapsed_time(ev[1]), "backward": ev[1].elapsed_time(ev[2]),
                                    "allreduce_clip_adamw_refresh": ev[2].elapsed_time(ev[3])}},
         "cpu_baseline": None,
-        "loss": float(loss.item()), "max_memory_gb": torch.cuda.max_memory_allocated() / 2 ** 30,
+        "loss": float(loss.item()), "max_memory_gb": torch.cuda.max_memory_allocated() / 2 ** 30, "replicas_in_sync": in_sync,
     }
     emit_json(line)
 

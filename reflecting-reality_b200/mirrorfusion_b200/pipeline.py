@@ -533,13 +533,21 @@ class MirrorFusionB200Pipeline:
             raise NotImplementedError("IP-adapter inputs are not on the MirrorFusion depth-concat path")
         if prompt is not None or negative_prompt is not None:
             raise NotImplementedError("tokenizer / CLIP are outside the hot path: pass prompt_embeds / negative_prompt_embeds")
-        if timesteps is not None or eta != 0.0 or guess_mode or num_images_per_prompt != 1:
-            raise NotImplementedError("custom timesteps / eta / guess_mode / num_images_per_prompt are not implemented")
+        if timesteps is not None:
+            # retrieve_timesteps (:112-121): neither scheduler of the path accepts a custom schedule in `set_timesteps`; same error
+            raise ValueError(f"The current scheduler class {self.scheduler.__class__}'s `set_timesteps` does not support custom"
+                             f" timestep schedules. Please check whether you are using the correct scheduler.")
+        if eta != 0.0 or guess_mode:
+            raise NotImplementedError("eta > 0 (stochastic DDIM) / guess_mode are not implemented")
         self.check_inputs(prompt_embeds, negative_prompt_embeds, brushnet_conditioning_scale, control_guidance_start,
                           control_guidance_end, callback_on_step_end_tensor_inputs)
         do_cfg = guidance_scale > 1.0                                                      # :835-836
         if not do_cfg:
-            raise NotImplementedError("the fused step is built for classifier-free guidance (guidance_scale > 1)")
+            # The reference then runs the nets on the conditional batch alone and skips the combine (:1256,1310).  The fused step
+            # is built for two CFG halves; with BOTH halves fed the conditional embeddings and a combine weight of exactly 1 the
+            # update it computes is u + 1 (c - u) with u == c bit for bit, i.e. the conditional prediction — same result, at the
+            # cost of the redundant half (guidance <= 1 is not a throughput configuration of MirrorFusion).
+            negative_prompt_embeds, guidance_scale = prompt_embeds, 1.0
         if negative_prompt_embeds is None:
             # the reference encodes "" through CLIP for the unconditional half (encode_prompt, :417-446) — not a zero tensor;
             # the text encoder is outside this package, so its embedding of the empty prompt must be handed in once
@@ -548,6 +556,12 @@ class MirrorFusionB200Pipeline:
                                  "(the text encoder's embedding of the empty prompt, [1 or b, 77, ctx]); zeros are not what the "
                                  "reference uses for the unconditional half")
             negative_prompt_embeds = self.empty_prompt_embeds.to(prompt_embeds).expand(prompt_embeds.shape[0], -1, -1)
+        if num_images_per_prompt != 1:                                                     # encode_prompt's repeat (:403-405,447-451)
+            rep = lambda t: t.repeat_interleave(num_images_per_prompt, 0)
+            prompt_embeds, negative_prompt_embeds = rep(prompt_embeds), rep(negative_prompt_embeds)
+            if conditioning_latents is not None and conditioning_latents.shape[0] * num_images_per_prompt == prompt_embeds.shape[0]:
+                conditioning_latents = rep(conditioning_latents)
+            image, mask, depth = (None if t is None else rep(t) for t in (image, mask, depth))   # prepare_image's repeat (:766)
         b = prompt_embeds.shape[0]
         ehs = torch.cat([negative_prompt_embeds, prompt_embeds])                           # uncond first (:1102-1103)
         if conditioning_latents is None:

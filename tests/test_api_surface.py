@@ -80,3 +80,7 @@ def test_pipeline_error_behaviour_mirrors_check_inputs():
         pipe(prompt="a mirror", prompt_embeds=pe)
     with pytest.raises(TypeError):
         pipe(prompt_embeds=pe, not_an_argument=1)
+    with pytest.raises(ValueError, match="does not support custom"):                  # retrieve_timesteps (:112-121), same message
+        pipe(prompt_embeds=pe, negative_prompt_embeds=pe, timesteps=[999, 500, 1])
+    with pytest.raises(ValueError, match="empty_prompt_embeds"):                      # no silent zero tensor for the unconditional half
+        pipe(prompt_embeds=pe)

@@ -329,6 +329,40 @@ def test_pipeline_call_vs_oracle_loop(P, sched_kind, steps):
     assert e < 4e-2
 
 
+def test_pipeline_call_surface_guidance_off_images_per_prompt_and_schedule_change(P):
+    """`__call__` arguments the reference supports and the eval script may use (pipeline_brushnet.py:835-836,1102-1103,403-405):
+    guidance_scale <= 1 (no CFG: the conditional prediction alone), num_images_per_prompt, `empty_prompt_embeds` for the
+    unconditional half, and a second call on the same geometry with another step count (time tables rebuilt after capture)."""
+    from oracle import mf_oracle as O
+    cfg = TINY
+    usd, bsd = make_state_dict(cfg, "unet"), make_state_dict(cfg, "brushnet")
+    inp = make_inputs(cfg, 2, seed=31)
+    neg, pos = inp["prompt_embeds"][:2].cuda(), inp["prompt_embeds"][2:].cuda()
+    cond, lat = inp["conditioning_latents"][:2].cuda(), inp["latents"].cuda()
+    pipe = P.MirrorFusionB200Pipeline(usd, bsd, scheduler=P.B200DDIMScheduler(), cfg=cfg, empty_prompt_embeds=neg[:1])
+    # guidance off: equals the oracle loop run on the conditional batch alone
+    out = pipe(prompt_embeds=pos, conditioning_latents=cond, latents=lat, num_inference_steps=3, guidance_scale=1.0).images
+    osched = O.DDIMOracle()
+    osched.set_timesteps(3)
+    x = inp["latents"].clone()
+    with torch.no_grad():
+        for t in osched.timesteps:
+            d, m, u = O.brushnet_forward(bsd, cfg, x, t, inp["conditioning_latents"][:2])
+            x = osched.step(O.unet_forward(usd, cfg, x, t, inp["prompt_embeds"][2:], d, m, u), t, x)
+    assert rel(out, x) < 4e-2
+    # another step count on the same geometry (same captured graph, rebuilt timestep tables), default negative embeds = empty prompt
+    out5 = pipe(prompt_embeds=pos, conditioning_latents=cond, latents=lat, num_inference_steps=5, guidance_scale=7.5).images
+    ref5 = pipe(prompt_embeds=pos, negative_prompt_embeds=neg[:1].expand(2, -1, -1).contiguous(), conditioning_latents=cond, latents=lat,
+                num_inference_steps=5, guidance_scale=7.5).images
+    assert torch.isfinite(out5).all() and torch.equal(out5, ref5)
+    # num_images_per_prompt: one prompt / conditioning, two latents
+    out2 = pipe(prompt_embeds=pos[:1], negative_prompt_embeds=neg[:1], conditioning_latents=cond[:1], latents=lat, num_images_per_prompt=2,
+                num_inference_steps=3, guidance_scale=7.5).images
+    both = pipe(prompt_embeds=pos[:1].expand(2, -1, -1).contiguous(), negative_prompt_embeds=neg[:1].expand(2, -1, -1).contiguous(),
+                conditioning_latents=cond[:1].expand(2, -1, -1, -1).contiguous(), latents=lat, num_inference_steps=3, guidance_scale=7.5).images
+    assert out2.shape == (2, 4, cfg.sample_size, cfg.sample_size) and torch.equal(out2, both)
+
+
 def test_sd15_final_image_psnr_vs_reference(P, golden_dir):
     """north_star: final decoded images within PSNR >= 40 dB of the reference.  The reference loop (SD1.5-shaped nets,
     20 UniPC steps, CFG 7.5, fp32 CPU) was run by oracle/make_golden.py; both sides' final latents go through the SAME
