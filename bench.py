@@ -121,12 +121,32 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------------------------------- reference arm
+def _reference_arm():
+    """baseline/reference_arm.py (the UNMODIFIED reference from baseline/_ref behind its own `__call__`), or None + why."""
+    try:
+        from baseline import reference_arm as R
+        R.import_reference()
+        return R, None
+    except Exception as ex:
+        return None, f"{type(ex).__name__}: {ex}"
+
+
 def cpu_reference_run(steps: int, warmup: int, images: int = 1):
-    """The reference's algorithm on the host cores: fp32 oracle port, SD1.5 config, `images` image(s) + CFG per step."""
-    from oracle import mf_oracle as O           # the one place bench.py executes oracle/: as the CPU baseline
+    """The reference on the host cores, fp32, SD1.5 config, `images` image(s) + CFG per step: the reference's OWN
+    `StableDiffusionBrushNetPipeline.__call__` from baseline/_ref when it is installed (kind "reference"), else the oracle
+    port of its algorithm (kind "port")."""
     from mirrorfusion_b200.config import SD15
-    from mirrorfusion_b200.synth import make_inputs, make_state_dict
     cores = os.cpu_count() or 1
+    R, why = _reference_arm()
+    if R is not None:
+        r = R.run(SD15, images, 64, steps, warmup, device="cpu", dtype=torch.float32, threads=cores)
+        sec = r["sec_per_step"]
+        return {"sec_per_step": sec, "images_per_s": images / (STEPS_PER_IMAGE * sec), "cores": cores, "kind": "reference",
+                "sample": f"{images} image(s) (net batch {2 * images}) x {r['steps_timed']} denoise step(s) (median) of the unmodified reference's "
+                          f"StableDiffusionBrushNetPipeline.__call__ ({r['where']}, diffusers {r['diffusers']}), SD1.5 config, 64x64 "
+                          f"latents, fp32, UniPC, CFG 7.5, torch CPU with {cores} threads"}
+    from oracle import mf_oracle as O           # the one place bench.py executes oracle/: as the CPU baseline
+    from mirrorfusion_b200.synth import make_inputs, make_state_dict
     torch.set_num_threads(cores)
     cfg = SD15
     usd, bsd = make_state_dict(cfg, "unet"), make_state_dict(cfg, "brushnet")
@@ -149,9 +169,9 @@ def cpu_reference_run(steps: int, warmup: int, images: int = 1):
             if i >= warmup:
                 times.append(dt)
     sec = sum(times) / len(times)
-    return {"sec_per_step": sec, "images_per_s": images / (STEPS_PER_IMAGE * sec), "cores": cores,
+    return {"sec_per_step": sec, "images_per_s": images / (STEPS_PER_IMAGE * sec), "cores": cores, "kind": "port",
             "sample": f"{images} image(s) (net batch {2 * images}) x {len(times)} denoise step(s), SD1.5 config, 64x64 latents, fp32, "
-                      f"torch CPU with {cores} threads"}
+                      f"torch CPU with {cores} threads (oracle port: {why})"}
 
 
 def gpu_eager_baseline(images: int, latent: int, dev, steps: int = 3, warmup: int = 2):
@@ -159,8 +179,20 @@ def gpu_eager_baseline(images: int, latent: int, dev, steps: int = 3, warmup: in
     PyTorch's own libraries (cuDNN convs, cuBLAS linears, SDPA flash / cuDNN attention, ATen norms) at the same batch.  The
     reference package is not on the GPU box, so the op list is the oracle port (`oracle/mf_oracle.py`, pinned to the
     reference), moved to the device: a BASELINE leg like `cpu_baseline`, never part of `value` / `e2e`."""
-    from oracle import mf_oracle as O
     from mirrorfusion_b200.config import SD15
+    R, why = _reference_arm()
+    if R is not None:
+        torch.backends.cudnn.benchmark = True
+        n = 10
+        r = R.run(SD15, images, latent, n, 3, device=str(dev), dtype=torch.bfloat16)
+        ms = r["sec_per_step"] * 1e3
+        return {"value": images / (STEPS_PER_IMAGE * ms * 1e-3), "unit": "images/s", "ms_per_step": ms, "dtype": "bf16",
+                "kind": "reference on cuda (unmodified StableDiffusionBrushNetPipeline.__call__, torch eager: cuDNN / cuBLAS / SDPA)",
+                "where": r["where"], "torch": torch.__version__, "cudnn": torch.backends.cudnn.version(),
+                "sample": f"{images} images (net batch {2 * images}) x {r['steps_timed']} UniPC steps at {latent}x{latent} latents, median of "
+                          f"CUDA-event step times taken in callback_on_step_end; 3 warm-up steps (cudnn.benchmark on), eager launches, "
+                          f"`pipe.to(cuda, bfloat16)`, AttnProcessor2_0"}
+    from oracle import mf_oracle as O
     from mirrorfusion_b200.synth import make_inputs, make_state_dict
     cfg, bf = SD15, torch.bfloat16
     usd = {k: v.to(dev, bf) for k, v in make_state_dict(cfg, "unet").items()}
@@ -196,14 +228,14 @@ def gpu_eager_baseline(images: int, latent: int, dev, steps: int = 3, warmup: in
 def run_reference(args, rank):
     if rank != 0:
         return
-    r = cpu_reference_run(args.steps, min(args.warmup, 1), images=1)
+    r = cpu_reference_run(args.steps, args.warmup, images=1)
     line = {
         "impl": "reference", "metric": metric_name(args.latent), "value": r["images_per_s"], "unit": "images/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": r["sec_per_step"] * 1e3, "higher_is_better": True,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["sec_per_step"] * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "MirrorFusion 512x512, 50 UniPC steps, CFG 7.5 (reference algorithm on host CPU; bounded sample: "
+        "config": {"workload": "MirrorFusion 512x512, 50 UniPC steps, CFG 7.5 (the reference on the host CPU; bounded sample: "
                                "1 image per step instead of 8)", "images_per_step": 1, "latent": "64x64", "steps_per_image": 50},
-        "cpu_baseline": {"value": r["images_per_s"], "unit": "images/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]},
+        "cpu_baseline": {"value": r["images_per_s"], "unit": "images/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]},
         "e2e": {"value": r["images_per_s"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -564,7 +596,7 @@ def run_ours(args, rank, world, local_rank):
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         r = cpu_reference_run(steps=2, warmup=1, images=1)
-        cpu = {"value": r["images_per_s"], "unit": "images/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]}
+        cpu = {"value": r["images_per_s"], "unit": "images/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]}
     eager = None
     if world == 1 and not args.no_eager_baseline:
         try:
