@@ -185,6 +185,20 @@ int mfb_prep_mask_depth(const void* mask_u8, const float* depth, int N, int H, i
                         float* depth_lat, int* scratch_n_ints, void* stream);
 int mfb_post_image_u8(const float* img_nchw, int N, int H, int W, void* out_hwc, void* stream);
 
+/* Inputs that are NOT at the target resolution: the dataset's `transforms.Resize(res, BICUBIC)` + `CenterCrop(res)` on float
+ * tensors (E/dataset/dataset.py:70-76 RGB, :86-92 mask, :155-165 normalised depth; torchvision resizes tensors with
+ * F.interpolate(mode="bicubic", align_corners=False, antialias=True), i.e. ATen's separable Keys a = -0.5 filter whose support
+ * grows with the down-scale factor).
+ *   mfb_resize_crop_bicubic : fp32 [NC, Hs, Ws] planes -> [NC, res/step, res/step]: shorter side resized to `res` (longer:
+ *                             int(res * long / short)), centre crop res x res (offsets int(round(d / 2)), half to even), and
+ *                             only the crop's pixels (step*i, step*j) evaluated — step = 1 is the transform itself, step = 8
+ *                             fuses the nearest sampling to latent resolution the pipeline applies to depth (:1196-1199).
+ *   mfb_depth_normalize     : metric depth fp32 [N,H,W] + uint8 mask [N,H,W] -> 2 * clip(d, 0, dmax) / dmax - 1 with
+ *                             dmax = max depth over mask > 0 + delta, at the map's own resolution (:131-145); scratch: N ints */
+int mfb_resize_crop_bicubic(const float* in, int NC, int Hs, int Ws, int res, int step, float* out, void* stream);
+int mfb_depth_normalize(const float* depth, const void* mask_u8, int N, int H, int W, float delta, float* out,
+                        int* scratch_n_ints, void* stream);
+
 /* Latent sample of DiagonalGaussianDistribution (S/models/autoencoders/vae.py:769-791) times a scale:
  * out = scale * (mean + exp(0.5 * clamp(logvar, -30, 20)) * noise); noise == NULL gives the mode (scale * mean).  fp32, n elements. */
 int mfb_latent_sample(const float* mean, const float* logvar, const float* noise, float scale, float* out, long long n,

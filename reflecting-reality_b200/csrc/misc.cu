@@ -571,6 +571,96 @@ extern "C" int mfb_post_image_u8(const float* img_nchw, int N, int H, int W, voi
     return MFB_OK;
 }
 
+// ------------------------------------------------------------------------------- dataset resize: bicubic (antialiased) + centre crop
+// torchvision `transforms.Resize(res, BICUBIC)` + `CenterCrop(res)` on a float tensor (E/dataset/dataset.py:70-76,86-92,155-165:
+// RGB / mask / normalised depth).  On tensors torchvision resizes with F.interpolate(mode="bicubic", align_corners=False,
+// antialias=True) = ATen's separable `_upsample_bicubic2d_aa`: per output index the taps cover `center +- 2*max(scale,1)` input
+// samples, weights = the Keys cubic with a = -0.5 evaluated at (tap - center + 0.5) / max(scale,1), normalised to sum 1; a horizontal
+// pass, then a vertical one.  One thread per output element runs the same two passes over its own support (row sums first, then
+// the column combination), so results agree with ATen to fp32 rounding.  `step` > 1 evaluates only the crop's pixels
+// (step*i, step*j): the depth map is consumed at latent resolution by nearest sampling (pipeline_brushnet.py:1196-1199), so the
+// resize, the crop and that sampling are one launch over 64 x 64 outputs per image.
+namespace mfb {
+__device__ __forceinline__ float cubic_aa(float x) {
+    const float a = -0.5f;
+    x = fabsf(x);
+    if (x < 1.0f) return ((a + 2.0f) * x - (a + 3.0f)) * x * x + 1.0f;
+    if (x < 2.0f) return (((x - 5.0f) * x + 8.0f) * x - 4.0f) * a;
+    return 0.0f;
+}
+// taps of output index `o` of a resize in_size -> out_size: first input index, count, and the un-normalised weights' sum
+struct AaTaps { int lo, n; float center, inv, total; };
+__device__ __forceinline__ AaTaps aa_taps(int o, int in_size, float scale) {
+    AaTaps t;
+    const float support = scale >= 1.0f ? 2.0f * scale : 2.0f;
+    t.inv = scale >= 1.0f ? 1.0f / scale : 1.0f;
+    t.center = scale * (static_cast<float>(o) + 0.5f);
+    t.lo = max(static_cast<int>(t.center - support + 0.5f), 0);
+    t.n = min(static_cast<int>(t.center + support + 0.5f), in_size) - t.lo;
+    t.total = 0.f;
+    for (int j = 0; j < t.n; ++j) t.total += cubic_aa((static_cast<float>(j + t.lo) - t.center + 0.5f) * t.inv);
+    return t;
+}
+__global__ void resize_crop_kernel(const float* __restrict__ in, int Hs, int Ws, int Hr, int Wr, int top, int left, int step,
+                                   int Ho, int Wo, float* __restrict__ out, long long total) {
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int x = static_cast<int>(i % Wo), y = static_cast<int>((i / Wo) % Ho);
+    const long long nc = i / (static_cast<long long>(Wo) * Ho);
+    const float* src = in + nc * static_cast<long long>(Hs) * Ws;
+    // area_pixel_compute_scale with align_corners = false: in / out
+    const float sy = static_cast<float>(Hs) / static_cast<float>(Hr), sx = static_cast<float>(Ws) / static_cast<float>(Wr);
+    const AaTaps ty = aa_taps(top + y * step, Hs, sy), tx = aa_taps(left + x * step, Ws, sx);
+    float acc = 0.f;
+    for (int r = 0; r < ty.n; ++r) {
+        const float* row = src + static_cast<long long>(ty.lo + r) * Ws + tx.lo;
+        float h = 0.f;
+        for (int c = 0; c < tx.n; ++c)
+            h += (cubic_aa((static_cast<float>(c + tx.lo) - tx.center + 0.5f) * tx.inv) / tx.total) * __ldg(row + c);
+        acc += (cubic_aa((static_cast<float>(r + ty.lo) - ty.center + 0.5f) * ty.inv) / ty.total) * h;
+    }
+    out[i] = acc;
+}
+// depth -> 2 * clip(d, 0, dmax) / dmax - 1 at the map's own resolution (dataset.py:131-145), dmax = max over mask > 0 (+ delta)
+__global__ void depth_normalize_kernel(const float* __restrict__ depth, const int* __restrict__ maxbits, float delta, long long hw,
+                                       float* __restrict__ out, long long total) {
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const float dmax = __int_as_float(maxbits[i / hw]) + delta;
+    out[i] = 2.0f * (fminf(fmaxf(depth[i], 0.0f), dmax) / dmax) - 1.0f;
+}
+}  // namespace mfb
+
+extern "C" int mfb_resize_crop_bicubic(const float* in, int NC, int Hs, int Ws, int res, int step, float* out, void* stream) {
+    MFB_REQUIRE(in && out && NC > 0 && Hs > 0 && Ws > 0 && res > 0 && step > 0 && res % step == 0, "bad arguments");
+    // torchvision _compute_resized_output_size: the shorter side becomes `res`, the longer int(res * long / short)
+    int Hr, Wr;
+    if (Hs <= Ws) { Hr = res; Wr = static_cast<int>(static_cast<long long>(res) * Ws / Hs); }
+    else { Wr = res; Hr = static_cast<int>(static_cast<long long>(res) * Hs / Ws); }
+    // CenterCrop: int(round((size - crop) / 2.0)) with Python's round-half-to-even
+    auto half_even = [](int d) { return (d % 2 == 0) ? d / 2 : ((d / 2) % 2 == 0 ? d / 2 : d / 2 + 1); };
+    const int top = half_even(Hr - res), left = half_even(Wr - res);
+    const int Ho = res / step, Wo = res / step;
+    const long long total = static_cast<long long>(NC) * Ho * Wo;
+    resize_crop_kernel<<<static_cast<unsigned>((total + 127) / 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(in, Hs, Ws, Hr, Wr, top, left,
+                                                                                                              step, Ho, Wo, out, total);
+    MFB_CUDA_OK(cudaGetLastError());
+    return MFB_OK;
+}
+
+extern "C" int mfb_depth_normalize(const float* depth, const void* mask_u8, int N, int H, int W, float delta, float* out,
+                                   int* scratch_n_ints, void* stream) {
+    MFB_REQUIRE(depth && mask_u8 && out && scratch_n_ints && N > 0 && H > 0 && W > 0, "bad arguments");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const long long hw = static_cast<long long>(H) * W, total = hw * N;
+    MFB_CUDA_OK(cudaMemsetAsync(scratch_n_ints, 0, sizeof(int) * N, st));
+    depth_max_kernel<<<dim3(64, N), 256, 0, st>>>(depth, static_cast<const uint8_t*>(mask_u8), hw, scratch_n_ints);
+    MFB_CUDA_OK(cudaGetLastError());
+    depth_normalize_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(depth, scratch_n_ints, delta, hw, out, total);
+    MFB_CUDA_OK(cudaGetLastError());
+    return MFB_OK;
+}
+
 namespace mfb {
 __global__ void latent_sample_kernel(const float* __restrict__ mean, const float* __restrict__ logvar, const float* __restrict__ noise,
                                      float scale, float* __restrict__ out, long long n) {

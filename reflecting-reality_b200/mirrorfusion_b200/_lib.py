@@ -57,6 +57,8 @@ _SIGS = {
     "mfb_prep_image_u8": (i32, [vp, i32, i32, i32, vp, vp]),
     "mfb_prep_mask_depth": (i32, [vp, vp, i32, i32, i32, i32, f32, vp, vp, vp, vp]),
     "mfb_post_image_u8": (i32, [vp, i32, i32, i32, vp, vp]),
+    "mfb_resize_crop_bicubic": (i32, [vp, i32, i32, i32, i32, i32, vp, vp]),
+    "mfb_depth_normalize": (i32, [vp, vp, i32, i32, i32, f32, vp, vp, vp]),
     "mfb_latent_sample": (i32, [vp, vp, vp, f32, vp, i64, vp]),
     "mfb_cfg_sched_step": (i32, [vp, vp, vp, vp, vp, vp, vp, i32, i64, vp]),
     # fp32 parity mode

@@ -333,6 +333,19 @@ def prep_mask_depth(mask_u8, depth, mask_lat, depth_lat, scratch, factor=8, delt
                                     _ptr(scratch), _stream()))
 
 
+def resize_crop_bicubic(x, out, res: int, step: int = 1):
+    """fp32 [..., Hs, Ws] -> [..., res/step, res/step]: torchvision Resize(res, BICUBIC, antialias) + CenterCrop(res), sampled every `step`."""
+    Hs, Ws = x.shape[-2:]
+    assert x.dtype == torch.float32 and x.is_contiguous() and tuple(out.shape[-2:]) == (res // step, res // step)
+    check(lib().mfb_resize_crop_bicubic(_ptr(x), x.numel() // (Hs * Ws), Hs, Ws, res, step, _ptr(out), _stream()))
+
+
+def depth_normalize(depth, mask_u8, out, scratch, delta=0.5):
+    """metric depth fp32 [N,H,W] + uint8 mask [N,H,W] -> [-1,1] by the max depth over the mask (+ delta), same resolution."""
+    N, H, W = depth.shape
+    check(lib().mfb_depth_normalize(_ptr(depth), _ptr(mask_u8), N, H, W, float(delta), _ptr(out), _ptr(scratch), _stream()))
+
+
 def post_image_u8(img_nchw, out_hwc):
     """fp32 [N,3,H,W] in [-1,1] -> uint8 [N,H,W,3]."""
     N, _, H, W = img_nchw.shape

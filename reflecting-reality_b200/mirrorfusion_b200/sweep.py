@@ -12,8 +12,11 @@ pipeline pass whose every stage runs on the kernels —
 (seed, global item index), so an item's image does not depend on the batch it rides in or on the number of GPUs
 (BASELINE config 3); the reference threads one generator through all calls, which ties results to the visiting order.
 
-Inputs are arrays at the target resolution (the SynMirror hdf5 fields / MSD files after the dataset's own resize):
-masked RGB uint8 [S,H,W,3], mask uint8 [S,H,W] (255 = mirror region), metric depth fp32 [S,H,W], prompt embeddings.
+Inputs: masked RGB uint8 [S,H,W,3] and mask uint8 [S,H,W] (255 = mirror region) at the target resolution (the pipeline takes them
+at their own size, E/test_brushnet.py:207-216), metric depth fp32 [S,Hd,Wd] at ANY resolution — when it differs from (H,W) it goes
+through the dataset's `apply_transforms_depth` (normalise at its own resolution with `depth_mask` [S,Hd,Wd], bicubic antialiased
+resize of the shorter side to the target + centre crop, E/dataset/dataset.py:98-166) fused with the nearest sampling to latent
+resolution (`ops.depth_normalize` + `ops.resize_crop_bicubic(step=f)`) — and prompt embeddings.
 Tokenizer / CLIP stay outside (embeddings in), as in the rest of the package."""
 from __future__ import annotations
 
@@ -68,9 +71,20 @@ class EvalSweep:
 
     @torch.no_grad()
     def run(self, rgb_u8: np.ndarray, mask_u8: np.ndarray, depth: np.ndarray, prompt_embeds: torch.Tensor,
-            negative_prompt_embeds: torch.Tensor, seed: int = 0, rank: int = 0, world: int = 1):
-        """Returns (uint8 images [n_local, H, W, 3] as a numpy array, the list of (sample, repeat) they belong to)."""
+            negative_prompt_embeds: torch.Tensor, seed: int = 0, rank: int = 0, world: int = 1, depth_mask: Optional[np.ndarray] = None):
+        """Returns (uint8 images [n_local, H, W, 3] as a numpy array, the list of (sample, repeat) they belong to).
+        depth_mask: uint8 [S,Hd,Wd], the mask at the depth map's own resolution (needed when (Hd,Wd) != (H,W))."""
         S = rgb_u8.shape[0]
+        native_depth = tuple(depth.shape[1:]) != (self.H, self.W)
+        if native_depth:
+            if self.H != self.W:
+                raise ValueError("depth resize + centre crop produces a square map: the sweep's H and W must be equal")
+            if depth_mask is None or depth_mask.shape != depth.shape:
+                raise ValueError("depth at its own resolution needs `depth_mask` of the same shape (apply_transforms_depth(depth, mask))")
+            Hd, Wd = depth.shape[1:]
+            dsrc = torch.zeros(self.n, Hd, Wd, device=self.dev, dtype=f32)
+            dmsk = torch.zeros(self.n, Hd, Wd, device=self.dev, dtype=torch.uint8)
+            dnorm = torch.zeros(self.n, Hd, Wd, device=self.dev, dtype=f32)
         items = self.items(S)
         mine = [items[j] for j in shard_range(len(items), rank, world)]
         gidx = list(shard_range(len(items), rank, world))
@@ -83,13 +97,22 @@ class EvalSweep:
             si = [mine[j][0] for j in pad]
             self.rgb_d.copy_(torch.from_numpy(np.ascontiguousarray(rgb_u8[si])))
             self.mask_d.copy_(torch.from_numpy(np.ascontiguousarray(mask_u8[si])))
-            self.depth_d.copy_(torch.from_numpy(np.ascontiguousarray(depth[si], dtype=np.float32)))
+            if native_depth:
+                dsrc.copy_(torch.from_numpy(np.ascontiguousarray(depth[si], dtype=np.float32)))
+                dmsk.copy_(torch.from_numpy(np.ascontiguousarray(depth_mask[si])))
+            else:
+                self.depth_d.copy_(torch.from_numpy(np.ascontiguousarray(depth[si], dtype=np.float32)))
             lat0 = torch.stack([torch.randn(lc, self.h, self.w, generator=item_generator(seed, gidx[j], 0)) for j in pad])
             vnoise = torch.stack([torch.randn(self.vae_cfg.latent_channels, self.h, self.w, generator=item_generator(seed, gidx[j], 1))
                                   for j in pad])
             # preprocessing -> masked-image latents -> conditioning (pipeline_brushnet.py:1188-1202)
             ops.prep_image_u8(self.rgb_d, self.img)
-            ops.prep_mask_depth(self.mask_d, self.depth_d, self.mask_lat, self.depth_lat, self.scratch, factor=self.f, delta=self.delta)
+            if native_depth:
+                ops.prep_mask_depth(self.mask_d, None, self.mask_lat, None, None, factor=self.f)
+                ops.depth_normalize(dsrc, dmsk, dnorm, self.scratch, delta=self.delta)
+                ops.resize_crop_bicubic(dnorm, self.depth_lat, self.H, step=self.f)
+            else:
+                ops.prep_mask_depth(self.mask_d, self.depth_d, self.mask_lat, self.depth_lat, self.scratch, factor=self.f, delta=self.delta)
             lat = self.enc.encode(self.img, noise=vnoise, scale=self.vae_cfg.scaling_factor)
             cond = torch.cat([lat, self.mask_lat, self.depth_lat], 1)
             ehs = torch.cat([negative_prompt_embeds[si] if negative_prompt_embeds.shape[0] == S else negative_prompt_embeds.expand(n, -1, -1),

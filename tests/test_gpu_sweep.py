@@ -34,6 +34,49 @@ def test_prep_and_post_kernels_vs_reference_functions(golden_dir):
     assert np.array_equal(u8.cpu().numpy(), g["out_u8"])
 
 
+RESIZE_CASES = [(512, 512, 512), (768, 1024, 512), (1024, 768, 512), (600, 901, 512), (300, 400, 512), (97, 131, 40), (33, 33, 64)]
+
+
+@pytest.mark.parametrize("Hs,Ws,res", RESIZE_CASES)
+def test_resize_crop_kernel_vs_oracle_and_torchvision(Hs, Ws, res):
+    """mfb_resize_crop_bicubic = transforms.Resize(res, BICUBIC) + CenterCrop(res) on float tensors (E/dataset/dataset.py:70-76,
+    86-92,155-165): down- and up-scaling, portrait / landscape / odd sizes; step = 8 is the crop sampled at latent resolution."""
+    from oracle.resize_oracle import resize_crop_bicubic
+    rng = np.random.default_rng(Hs * 7 + Ws)
+    x = rng.standard_normal((3, Hs, Ws)).astype(np.float32)
+    want = resize_crop_bicubic(x, res)
+    ops.lib()
+    xd = torch.from_numpy(x).cuda()
+    out = torch.empty(3, res, res, device="cuda")
+    ops.resize_crop_bicubic(xd, out, res)
+    assert np.abs(out.cpu().numpy() - want).max() < 1e-5
+    try:
+        from torchvision import transforms
+    except ImportError:
+        transforms = None
+    if transforms is not None:                 # the reference's own transform, where torchvision is installed
+        t = transforms.Compose([transforms.Resize(res, interpolation=transforms.InterpolationMode.BICUBIC), transforms.CenterCrop(res)])
+        assert (out.cpu() - t(torch.from_numpy(x))).abs().max().item() < 1e-5
+    if res % 8 == 0:
+        o8 = torch.empty(3, res // 8, res // 8, device="cuda")
+        ops.resize_crop_bicubic(xd, o8, res, step=8)
+        assert np.abs(o8.cpu().numpy() - want[:, ::8, ::8]).max() < 1e-5
+
+
+def test_depth_normalize_kernel_vs_oracle():
+    from oracle import prep_oracle as PO
+    rng = np.random.default_rng(5)
+    N, H, W = 3, 40, 56
+    depth = (rng.random((N, H, W), dtype=np.float32) * 6 - 0.5).astype(np.float32)           # some negative: clipped to 0
+    mask = np.zeros((N, H, W), np.uint8)
+    for i in range(N):
+        mask[i, 3 + i:20, 5:30 + i] = 255
+    ops.lib()
+    out = torch.empty(N, H, W, device="cuda")
+    ops.depth_normalize(torch.from_numpy(depth).cuda(), torch.from_numpy(mask).cuda(), out, torch.zeros(N, dtype=torch.int32, device="cuda"))
+    assert np.abs(out.cpu().numpy() - PO.prep_depth(depth, mask, 1)[:, 0]).max() < 1e-6
+
+
 def _inputs(S, px, cfg, seed=0):
     rng = np.random.default_rng(seed)
     rgb = rng.integers(0, 256, (S, px, px, 3), dtype=np.uint8)
@@ -100,3 +143,26 @@ def test_sweep_is_invariant_to_batching_and_sharding():
     parts = [sw2.run(rgb, mask, depth, pe, ne, seed=seed, rank=r, world=2) for r in range(2)]
     assert parts[0][1] + parts[1][1] == items
     assert np.array_equal(np.concatenate([parts[0][0], parts[1][0]]), whole)
+
+
+def test_sweep_depth_at_its_own_resolution():
+    """Depth maps that are not at the target resolution go through apply_transforms_depth (normalise at their own size, bicubic
+    antialiased resize + centre crop, E/dataset/dataset.py:98-166) fused with the nearest sampling to latent size."""
+    from oracle import prep_oracle as PO
+    from oracle.resize_oracle import resize_crop_bicubic
+    sw, px = _sweep(images_per_call=4)
+    cfg, S = TINY, 2
+    rgb, mask, _, pe, ne = _inputs(S, px, cfg)
+    rng = np.random.default_rng(3)
+    Hd, Wd = 3 * px // 2 + 1, 2 * px
+    depth = (rng.random((S, Hd, Wd), dtype=np.float32) * 4 + 0.5).astype(np.float32)
+    dmask = np.zeros((S, Hd, Wd), np.uint8)
+    dmask[:, 5:30, 8:40] = 255
+    with pytest.raises(ValueError):
+        sw.run(rgb, mask, depth, pe, ne, seed=1)
+    got, items = sw.run(rgb, mask, depth, pe, ne, seed=1, depth_mask=dmask)
+    assert got.shape == (4, px, px, 3) and items == [(0, 0), (0, 1), (1, 0), (1, 1)]
+    want = resize_crop_bicubic(PO.prep_depth(depth, dmask, 1)[:, 0], px, step=sw.f)          # [S, h, w]
+    dl = sw.depth_lat.cpu().numpy()[:, 0]
+    for j, (i, _) in enumerate(items):
+        assert np.abs(dl[j] - want[i]).max() < 1e-5

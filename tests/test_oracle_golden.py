@@ -163,3 +163,21 @@ def test_prep_oracle_matches_reference_functions(golden_dir):
     assert np.array_equal(PO.prep_mask(g["mask"], f), g["mask_lat"])
     assert np.abs(PO.prep_depth(g["depth"], g["mask"], f) - g["depth_lat"]).max() < 1e-6
     assert np.array_equal(PO.post_image(g["decoded"]), g["out_u8"])
+
+
+def test_resize_oracle_vs_torchvision():
+    """oracle/resize_oracle.py against the transform the reference applies (E/dataset/dataset.py:70-76,86-92,155-165):
+    torchvision `Resize(res, BICUBIC)` + `CenterCrop(res)` on float tensors."""
+    tv = pytest.importorskip("torchvision")
+    from torchvision import transforms
+    from oracle.resize_oracle import crop_offsets, resize_crop_bicubic, resized_size
+    rng = np.random.default_rng(0)
+    for Hs, Ws, res in [(512, 512, 512), (384, 512, 256), (512, 384, 256), (300, 451, 256), (150, 200, 256), (97, 131, 40), (33, 33, 64)]:
+        x = rng.standard_normal((2, Hs, Ws)).astype(np.float32)
+        t = transforms.Compose([transforms.Resize(res, interpolation=transforms.InterpolationMode.BICUBIC), transforms.CenterCrop(res)])
+        want = t(torch.from_numpy(x)).numpy()
+        got = resize_crop_bicubic(x, res)
+        assert got.shape == want.shape and np.abs(got - want).max() < 1e-5, (Hs, Ws, res)
+        if res % 8 == 0:
+            assert np.abs(resize_crop_bicubic(x, res, 8) - want[:, ::8, ::8]).max() < 1e-5
+    assert resized_size(300, 451, 256) == (256, 384) and crop_offsets(256, 385, 256) == (0, 64)      # round half to even: 64.5 -> 64
