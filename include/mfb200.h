@@ -43,7 +43,7 @@ const char* mfb_last_error(void);
  *   out[b,oh,ow,:] = ( sum_taps x[b, oh*s+kh-pad, ow*s+kw-pad, :] . w_tap  +  sum_e extra_x[e][b,oh,ow,:] . w_e
  *                      + bias + rowbias[b,:] ) * alpha  + res1[b,oh,ow,:] + res2[b,oh,ow,:]
  *
- * w is the packed weight [Cout, Ktot] bf16 (or fp16, see w_fp16), K order = (kh, kw, cin) then the extra segments in order.
+ * w is the packed weight [Cout, Ktot] bf16, K order = (kh, kw, cin) then the extra segments in order.
  * A linear layer over an [M, K] token matrix is ksize=1, B=1, H=1, W=M, Cin=K.
  * With geglu=1 the packed rows are interleaved per 128: 64 value rows then the 64 matching gate rows, and
  * out is [M, Cout/2] = value * gelu_erf(gate).
@@ -78,10 +78,6 @@ typedef struct mfb_conv_desc {
                              2*oh + kh (not 2*oh + kh - 1), the zero row / column sits at the bottom / right edge */
     int dtype;            /* 0 = bf16 tensors, tcgen05 path (the product).  1 = fp32 PARITY MODE: x / extras / w / res / out
                              are fp32, CUDA-core FFMA accumulation (csrc/fp32mode.cu) — same descriptor semantics */
-    int w_fp16;           /* dtype 0 only.  1: the packed weight `w` holds IEEE fp16 instead of bf16 (same 2 bytes, same layout).
-                             tcgen05.mma kind::f16 takes the A and B operand formats independently (instruction-descriptor
-                             fields a_format / b_format), so bf16 activations x fp16 weights runs at the same rate with fp32
-                             accumulation — and the weight rounding error drops 8x (11 significand bits instead of 8). */
 } mfb_conv_desc;
 
 typedef struct mfb_plan mfb_plan;

@@ -75,7 +75,6 @@ struct IgemmParams {
     int o_step, o_py, o_px, o_Hf, o_Wf;   // rows map to output pixel (o_step*oh + o_py, o_step*ow + o_px) of [Bn, o_Hf, o_Wf]
     int stages;            // operand ring depth actually used (<= IgemmCfg::STAGES)
     int nstg;              // staging tiles: 1, or 2 = double-buffered epilogue (short-K launches, see igemm_kernel)
-    int b_fp16;            // 1: the weight tile holds fp16 (instruction-descriptor b_format = F16), activations stay bf16
 };
 
 template <int BN>
@@ -322,8 +321,7 @@ __global__ void __launch_bounds__(64 + 32 * EPIW, 1) igemm_kernel(const __grid_c
     } else if (warp == IGEMM_EPI_WARPS + 1) {
         if ((!TWOSM || crank == 0) && elect_one()) {
             // ===== MMA issuer (MODE 2: leader CTA only) =====
-            // kind::f16 takes the operand formats independently: b_format (bits [10,13)) 1 = BF16, 0 = F16
-            const uint32_t idesc = make_idesc_bf16(TWOSM ? 2 * BM : BM, BN) & ~(p.b_fp16 ? (7u << 10) : 0u);
+            constexpr uint32_t idesc = make_idesc_bf16(TWOSM ? 2 * BM : BM, BN);
             int li = 0, stage = 0;
             uint32_t phase = 0;
             for (int tile = wi0; tile < num_tiles; tile += wstep, ++li) {
@@ -820,7 +818,6 @@ static int build_params(const mfb_conv_desc* d, int up_py, int up_px, const void
     p.res2 = static_cast<const __nv_bfloat16*>(d->res2);
     p.out = static_cast<__nv_bfloat16*>(d->out);
     p.geglu = d->geglu;
-    p.b_fp16 = d->w_fp16 ? 1 : 0;
     p.out_ld = d->geglu ? d->Cout / 2 : d->Cout;
     {
         // double-buffered epilogue: opt-in (env MFB_IGEMM_NSTG = 2, or MFB_IGEMM_NSTG_KMAX = largest K that gets it).
@@ -864,7 +861,6 @@ extern "C" int mfb_conv_plan_create(const mfb_conv_desc* d, mfb_plan** out) {
     MFB_REQUIRE(!d->geglu || (d->Cout % 128 == 0 && !d->res1 && !d->res2 && !d->rowbias), "geglu needs Cout %% 128 == 0 and no residuals");
     MFB_REQUIRE(!d->up2x || (d->ksize == 3 && d->stride == 1 && !d->geglu), "up2x needs a 3x3 stride-1 conv");
     MFB_REQUIRE(!d->pad0 || d->stride == 2, "pad0 is a stride-2 mode");
-    MFB_REQUIRE(!d->w_fp16 || d->dtype == 0, "w_fp16 is an option of the bf16 tensor-core path");
 
     Plan* pl = new Plan();
     int rc;

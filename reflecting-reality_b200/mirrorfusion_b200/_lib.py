@@ -23,7 +23,7 @@ class ConvDesc(C.Structure):
         ("B", i32), ("H", i32), ("W", i32), ("Cin", i32), ("Cout", i32), ("ksize", i32), ("stride", i32),
         ("x", vp), ("n_extra", i32), ("extra_x", vp * 3), ("extra_C", i32 * 3), ("w", vp), ("bias", vp),
         ("rowbias", vp), ("rowbias_ld", i32), ("alpha", vp), ("res1", vp), ("res2", vp), ("out", vp),
-        ("geglu", i32), ("block_n", i32), ("up2x", i32), ("igemm_mode", i32), ("pad0", i32), ("dtype", i32), ("w_fp16", i32),
+        ("geglu", i32), ("block_n", i32), ("up2x", i32), ("igemm_mode", i32), ("pad0", i32), ("dtype", i32),
     ]
 
 

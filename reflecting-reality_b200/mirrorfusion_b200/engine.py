@@ -37,7 +37,6 @@ class _Net:
         at the price of a slower constructor for the 1.5 G-parameter nets."""
         self.cfg, self.B, self.H, self.W, self.dev, self.name = cfg, B, H, W, device, name
         self.act = ops.act_dtype()     # storage dtype: bf16 (product) or fp32 (parity mode, `with ops.precision('fp32')`)
-        self.wdt = ops.weight_dtype()  # packed GEMM weights: fp16 next to bf16 activations (ops.weight_dtype), fp32 in parity mode
         if host_pack:
             self.sd = {k: v.detach().to(dtype=f32) for k, v in sd.items()}
         else:
@@ -77,8 +76,6 @@ class _Net:
 
     def D(self, t: torch.Tensor) -> torch.Tensor:
         """A packed weight / bias -> the device (a no-op unless host_pack)."""
-        if t.dtype == torch.float16 and not bool(torch.isfinite(t).all()):
-            raise ValueError("a weight does not fit fp16 (|w| > 65504): build the engine with MFB_WEIGHTS_FP16=0 (bf16 weights)")
         return t.to(self.dev)
 
     def wf(self, name: str) -> torch.Tensor:
@@ -93,7 +90,7 @@ class _Net:
     def set_tap_scale(self, s: float):
         """Re-scale the fused zero-conv K-segments in place (descriptors keep pointing at the same buffers)."""
         for wp, koff, c, wz, bias_buf, base_bias, bz in self.fused_taps:
-            wp[:, koff:koff + c].copy_((wz * s).to(wp.dtype))
+            wp[:, koff:koff + c].copy_((wz * s).to(self.act))
             bias_buf.copy_(base_bias + s * bz)
 
     # ---- op emitters
@@ -199,7 +196,7 @@ class _Net:
         n1 = self.scratch("n1", B, HW, cin)
         self.groupnorm(xa, xb, p + ".norm1", n1, HW, eps, True)
         h1 = self.scratch("h1", B, HW, cout)
-        w1 = self.D(ops.pack_conv_weight(self.sd[p + ".conv1.weight"], dtype=self.wdt))
+        w1 = self.D(ops.pack_conv_weight(self.sd[p + ".conv1.weight"]))
         off = self.rowbias_off.get(p)          # None: a resnet without time embedding (the VAE's)
         rb = None if off is None else self.rowbias[:, off:]
         self.emit_plan(ops.ConvPlan(n1, w1, h1, B=B, H=h, W=w, Cin=cin, Cout=cout, ksize=3, bias=self.wf(p + ".conv1.bias"),
@@ -225,7 +222,7 @@ class _Net:
             koff = 9 * cout + sum(e.shape[1] for e in extras_w)
             extras_w.append(tap_src[1]); extras_x.append(tap_src[0])
             fused = (koff, tap_src[1], tap_src[2])
-        w2 = self.D(ops.pack_conv_weight(wmain, extras=extras_w, dtype=self.wdt))
+        w2 = self.D(ops.pack_conv_weight(wmain, extras=extras_w))
         base_bias = bias.contiguous()
         bias_buf = self.D(base_bias.clone())
         if fused is not None:
@@ -239,7 +236,7 @@ class _Net:
         extras_w, extras_x = [], []
         if tap_src is not None:
             extras_w.append(tap_src[1]); extras_x.append(tap_src[0])
-        wp = self.D(ops.pack_conv_weight(self.sd[p + ".conv.weight"], extras=extras_w, dtype=self.wdt))
+        wp = self.D(ops.pack_conv_weight(self.sd[p + ".conv.weight"], extras=extras_w))
         base_bias = self.sd[p + ".conv.bias"].contiguous()
         bias_buf = self.D(base_bias.clone())
         if tap_src is not None:
@@ -263,7 +260,7 @@ class _Net:
         extras_w, extras_x = [], []
         if tap_src is not None:
             extras_w.append(tap_src[1]); extras_x.append(tap_src[0])
-        wp = self.D(ops.pack_upconv_weight(self.sd[p + ".conv.weight"], extras=extras_w, dtype=self.wdt))      # [4, C, 4C (+C)]
+        wp = self.D(ops.pack_upconv_weight(self.sd[p + ".conv.weight"], extras=extras_w))      # [4, C, 4C (+C)]
         base_bias = self.sd[p + ".conv.bias"].contiguous()
         bias_buf = self.D(base_bias.clone())
         if tap_src is not None:
@@ -372,7 +369,7 @@ class BrushNetEngine(_Net):
                 break
             c = src.shape[-1]
             t = tap_bufs[k] if tap_bufs is not None else self.buf(B, shw[0] * shw[1], c)
-            wz = self.D(ops.pack_conv_weight(self.sd[nm + ".weight"], dtype=self.wdt))
+            wz = self.D(ops.pack_conv_weight(self.sd[nm + ".weight"]))
             self.emit_plan(ops.ConvPlan(src, wz, t, B=B, H=shw[0], W=shw[1], Cin=c, Cout=c, ksize=1,
                                         bias=self.wf(nm + ".bias"), alpha=self.scale), out=t)
             self.taps.append(t)
@@ -486,14 +483,14 @@ class UNetEngine(_Net):
         g = self.scratch("tg", B, T, C)
         self.groupnorm(x, None, p + ".norm", g, T, 1e-6, False)
         h0 = self.scratch("th0", M, C)
-        self.emit_plan(ops.linear_plan(g.view(M, C), self.D(ops.pack_conv_weight(self.sd[p + ".proj_in.weight"], dtype=self.wdt)), h0,
+        self.emit_plan(ops.linear_plan(g.view(M, C), self.D(ops.pack_conv_weight(self.sd[p + ".proj_in.weight"])), h0,
                                        bias=self.wf(p + ".proj_in.bias")))
         # --- self attention
         nrm = self.scratch("tn", M, C)
         self.layernorm(h0, t + ".norm1", nrm)
         qkv = self.scratch("tqkv", M, 3 * C)
         wqkv = self.D(torch.cat([self.sd[t + ".attn1.to_q.weight"], self.sd[t + ".attn1.to_k.weight"],
-                                 self.sd[t + ".attn1.to_v.weight"]], 0).to(self.wdt).contiguous())
+                                 self.sd[t + ".attn1.to_v.weight"]], 0).to(self.act).contiguous())
         self.emit_plan(ops.linear_plan(nrm, wqkv, qkv))
         att = self.scratch("tatt", M, C)
         kview, vview = qkv.view(-1)[C:], qkv.view(-1)[2 * C:]      # q | k | v column blocks of the fused projection
@@ -501,39 +498,39 @@ class UNetEngine(_Net):
                                         ldk=3 * C, ldv=3 * C, ldo=C), 1, "attention", 4.0 * B * T * T * C)
         self.flops += 4.0 * B * T * T * C
         h1 = self.scratch("th1", M, C)
-        self.emit_plan(ops.linear_plan(att, self.D(self.sd[t + ".attn1.to_out.0.weight"].to(self.wdt).contiguous()), h1,
+        self.emit_plan(ops.linear_plan(att, self.D(self.sd[t + ".attn1.to_out.0.weight"].to(self.act).contiguous()), h1,
                                        bias=self.wf(t + ".attn1.to_out.0.bias"), res1=h0))
         # --- cross attention (K/V of the context are prepared once per prompt: ctx_prog)
         Lc = self.ctx_len
         k2 = self.buf(B * Lc, C)
         v2 = self.buf(B * Lc, C)
-        pk = ops.linear_plan(self.ehs_bf, self.D(self.sd[t + ".attn2.to_k.weight"].to(self.wdt).contiguous()), k2)
-        pv = ops.linear_plan(self.ehs_bf, self.D(self.sd[t + ".attn2.to_v.weight"].to(self.wdt).contiguous()), v2)
+        pk = ops.linear_plan(self.ehs_bf, self.D(self.sd[t + ".attn2.to_k.weight"].to(self.act).contiguous()), k2)
+        pv = ops.linear_plan(self.ehs_bf, self.D(self.sd[t + ".attn2.to_v.weight"].to(self.act).contiguous()), v2)
         self.keep += [pk, pv]
         self.ctx_prog += [pk.run, pv.run]
         self.layernorm(h1, t + ".norm2", nrm)
         q2 = self.scratch("tq2", M, C)
-        self.emit_plan(ops.linear_plan(nrm, self.D(self.sd[t + ".attn2.to_q.weight"].to(self.wdt).contiguous()), q2))
+        self.emit_plan(ops.linear_plan(nrm, self.D(self.sd[t + ".attn2.to_q.weight"].to(self.act).contiguous()), q2))
         self.emit(lambda: ops.attention(q2, k2, v2, att, B=B, heads=heads, head_dim=d, Tq=T, Tk=Lc, ldq=C, ldk=C,
                                         ldv=C, ldo=C), 1, "attention", 4.0 * B * T * Lc * C)
         self.flops += 4.0 * B * T * Lc * C
         h2 = self.scratch("th2", M, C)
-        self.emit_plan(ops.linear_plan(att, self.D(self.sd[t + ".attn2.to_out.0.weight"].to(self.wdt).contiguous()), h2,
+        self.emit_plan(ops.linear_plan(att, self.D(self.sd[t + ".attn2.to_out.0.weight"].to(self.act).contiguous()), h2,
                                        bias=self.wf(t + ".attn2.to_out.0.bias"), res1=h1))
         # --- GEGLU feed-forward
         self.layernorm(h2, t + ".norm3", nrm)
-        wg, bg = (self.D(a) for a in ops.pack_geglu(self.sd[t + ".ff.net.0.proj.weight"], self.sd[t + ".ff.net.0.proj.bias"], dtype=self.wdt))
+        wg, bg = (self.D(a) for a in ops.pack_geglu(self.sd[t + ".ff.net.0.proj.weight"], self.sd[t + ".ff.net.0.proj.bias"]))
         gg = self.scratch("tgg", M, 4 * C)
         self.emit_plan(ops.linear_plan(nrm, wg, gg, bias=bg, geglu=True))
         h3 = self.scratch("th3", M, C)
-        self.emit_plan(ops.linear_plan(gg, self.D(self.sd[t + ".ff.net.2.weight"].to(self.wdt).contiguous()), h3,
+        self.emit_plan(ops.linear_plan(gg, self.D(self.sd[t + ".ff.net.2.weight"].to(self.act).contiguous()), h3,
                                        bias=self.wf(t + ".ff.net.2.bias"), res1=h2))
         # --- proj_out + transformer residual (+ BrushNet tap, added after the attention: unet_2d_blocks.py:1374-1389)
         out = self.buf(B, T, C)
         extras_w, extras_x = [], []
         if tap_src is not None:
             extras_w.append(tap_src[1]); extras_x.append(tap_src[0].view(M, C))
-        wpo = self.D(ops.pack_conv_weight(self.sd[p + ".proj_out.weight"], extras=extras_w, dtype=self.wdt))
+        wpo = self.D(ops.pack_conv_weight(self.sd[p + ".proj_out.weight"], extras=extras_w))
         base_bias = self.sd[p + ".proj_out.bias"].contiguous()
         bias_buf = self.D(base_bias.clone())
         if tap_src is not None:

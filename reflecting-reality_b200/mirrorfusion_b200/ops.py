@@ -3,7 +3,6 @@ all math runs in libmfb200.so.  Every function requires CUDA tensors on an sm_10
 from __future__ import annotations
 
 import contextlib
-import os as _os
 import ctypes as C
 from typing import Optional, Sequence
 
@@ -38,42 +37,6 @@ def precision(mode: str):
         _ACT[0] = old
 
 
-# Storage dtype of the PACKED WEIGHTS of the inference engines.  tcgen05.mma kind::f16 takes the formats of its A and B operands
-# independently, so bf16 activations x fp16 weights run at the same rate and byte count as bf16 x bf16 — with 3 more significand
-# bits on every weight: the weight-rounding third of the bf16 error budget (5.97e-3 of 9.99e-3) all but disappears.
-# Default on for engines built in bf16 mode (env MFB_WEIGHTS_FP16=0 restores bf16 weights); a weight tensor whose magnitude does
-# not fit fp16 (> 6e4) keeps bf16 — ConvPlan reads the format off the tensor, so the choice is per launch.  The training programs
-# (backward.py / unet_train.py: bf16 working copy of the master weights, weight-gradient kernels) stay bf16.
-fp16 = torch.float16
-_WFP16 = [None]
-
-
-def weight_dtype():
-    """dtype inference engines pack their GEMM weights to: float32 in parity mode, else fp16 (default) or bf16."""
-    if _ACT[0] == f32:
-        return f32
-    on = _WFP16[0] if _WFP16[0] is not None else _os.environ.get("MFB_WEIGHTS_FP16", "1") == "1"
-    return fp16 if on else bf16
-
-
-@contextlib.contextmanager
-def weights_fp16(on: bool):
-    old = _WFP16[0]
-    _WFP16[0] = bool(on)
-    try:
-        yield
-    finally:
-        _WFP16[0] = old
-
-
-def to_weight(t: torch.Tensor, dtype=None) -> torch.Tensor:
-    """Round an fp32 weight matrix to the packed-weight dtype; fp16 falls back to bf16 for a tensor it cannot hold."""
-    dtype = dtype or act_dtype()
-    if dtype == fp16 and t.numel() and float(t.detach().abs().max()) > 6.0e4:
-        dtype = bf16
-    return t.to(dtype).contiguous()
-
-
 def _is32(t: torch.Tensor) -> bool:
     if t.dtype not in (bf16, f32):
         raise ValueError(f"activation tensors must be bfloat16 (product path) or float32 (parity mode), got {t.dtype}")
@@ -100,7 +63,7 @@ def _req(t: torch.Tensor, dtype, name: str):
 
 
 # --------------------------------------------------------------------------------------------- weight packing
-def pack_conv_weight(w: torch.Tensor, extras: Sequence[torch.Tensor] = (), dtype=None) -> torch.Tensor:
+def pack_conv_weight(w: torch.Tensor, extras: Sequence[torch.Tensor] = ()) -> torch.Tensor:
     """OIHW conv weight (or [out,in] linear weight) -> [Cout, kh*kw*Cin (+ extra 1x1 segments)] bf16,
     K ordered (kh, kw, cin) to match the tap-major K loop of the implicit GEMM."""
     if w.dim() == 2:
@@ -108,10 +71,10 @@ def pack_conv_weight(w: torch.Tensor, extras: Sequence[torch.Tensor] = (), dtype
     parts = [w.permute(0, 2, 3, 1).reshape(w.shape[0], -1)]
     for e in extras:
         parts.append(e.reshape(e.shape[0], -1))
-    return to_weight(torch.cat(parts, 1), dtype)
+    return torch.cat(parts, 1).to(act_dtype()).contiguous()
 
 
-def pack_upconv_weight(w: torch.Tensor, extras: Sequence[torch.Tensor] = (), dtype=None) -> torch.Tensor:
+def pack_upconv_weight(w: torch.Tensor, extras: Sequence[torch.Tensor] = ()) -> torch.Tensor:
     """3x3 conv applied to a nearest-2x upsampled input == four sub-pixel phases, each a 2x2 conv over the
     low-resolution input whose taps are sums of the 3x3 taps that land on the same source pixel.
     OIHW [Cout,Cin,3,3] -> [4 (py*2+px), Cout, 2*2*Cin (+ extra 1x1 segments)] bf16 (sums in fp32, one rounding)."""
@@ -131,17 +94,17 @@ def pack_upconv_weight(w: torch.Tensor, extras: Sequence[torch.Tensor] = (), dty
                     taps.append(acc)                      # [Cout, Cin]
             parts = [torch.stack(taps, 1).reshape(w.shape[0], -1)] + [e.reshape(e.shape[0], -1).float() for e in extras]
             out.append(torch.cat(parts, 1))
-    return to_weight(torch.stack(out, 0), dtype)
+    return torch.stack(out, 0).to(act_dtype()).contiguous()
 
 
-def pack_geglu(w: torch.Tensor, b: torch.Tensor, dtype=None):
+def pack_geglu(w: torch.Tensor, b: torch.Tensor):
     """GEGLU proj [8C, C]: rows [0,4C) value, [4C,8C) gate (activations.py:100-103) -> interleave per 128:
     64 value rows then the 64 matching gate rows."""
     half = w.shape[0] // 2
     wv, wg = w[:half].reshape(half // 64, 64, -1), w[half:].reshape(half // 64, 64, -1)
     wp = torch.stack([wv, wg], 1).reshape(2 * half, -1)
     bp = torch.stack([b[:half].reshape(-1, 64), b[half:].reshape(-1, 64)], 1).reshape(-1)
-    return to_weight(wp, dtype), bp.float().contiguous()
+    return wp.to(act_dtype()).contiguous(), bp.float().contiguous()
 
 
 # --------------------------------------------------------------------------------------------- implicit GEMM
@@ -156,12 +119,9 @@ class ConvPlan:
                  pad0: bool = False):
         L = lib()
         dt = f32 if _is32(x) else bf16      # fp32 tensors select the parity-mode plan (mfb_conv_desc.dtype = 1)
-        _req(x, dt, "x"); _req(out, dt, "out")
-        w_fp16 = dt == bf16 and w.dtype == fp16       # bf16 activations x fp16 weights (mfb_conv_desc.w_fp16)
-        _req(w, fp16 if w_fp16 else dt, "w")
+        _req(x, dt, "x"); _req(w, dt, "w"); _req(out, dt, "out")
         d = ConvDesc()
         d.dtype = 1 if dt == f32 else 0
-        d.w_fp16 = int(w_fp16)
         d.B, d.H, d.W, d.Cin, d.Cout, d.ksize, d.stride = B, H, W, Cin, Cout, ksize, stride
         d.x, d.w, d.out = x.data_ptr(), w.data_ptr(), out.data_ptr()
         d.n_extra = len(extras)

@@ -174,7 +174,6 @@ class B200AttnProcessor:
         if st is not None:
             return st
         bf = torch.bfloat16
-        wd = ops.weight_dtype()        # fp16 weights next to bf16 activations (ops.weight_dtype)
         heads = attn.heads
         z = lambda *shape: torch.zeros(*shape, device=dev, dtype=bf)
         st = SimpleNamespace()
@@ -182,21 +181,21 @@ class B200AttnProcessor:
         st.att = z(B * T, C)
         st.out = z(B * T, C)
         wq, wk, wv = (attn.to_q.weight.detach(), attn.to_k.weight.detach(), attn.to_v.weight.detach())
-        wo = attn.to_out[0].weight.detach().to(device=dev, dtype=wd).contiguous()
+        wo = attn.to_out[0].weight.detach().to(device=dev, dtype=bf).contiguous()
         bo = attn.to_out[0].bias
         st.bo = None if bo is None else bo.detach().to(device=dev, dtype=f32).contiguous()
         if is_self:
             st.qkv = z(B * T, 3 * C)
-            w = torch.cat([wq, wk, wv], 0).to(device=dev, dtype=wd).contiguous()
+            w = torch.cat([wq, wk, wv], 0).to(device=dev, dtype=bf).contiguous()
             st.plans = [ops.linear_plan(st.x, w, st.qkv)]
         else:
             st.ctx = z(B * Tk, Cctx)
             st.q = z(B * T, C)
             st.k = z(B * Tk, C)
             st.v = z(B * Tk, C)
-            st.plans = [ops.linear_plan(st.x, wq.to(device=dev, dtype=wd).contiguous(), st.q),
-                        ops.linear_plan(st.ctx, wk.to(device=dev, dtype=wd).contiguous(), st.k),
-                        ops.linear_plan(st.ctx, wv.to(device=dev, dtype=wd).contiguous(), st.v)]
+            st.plans = [ops.linear_plan(st.x, wq.to(device=dev, dtype=bf).contiguous(), st.q),
+                        ops.linear_plan(st.ctx, wk.to(device=dev, dtype=bf).contiguous(), st.k),
+                        ops.linear_plan(st.ctx, wv.to(device=dev, dtype=bf).contiguous(), st.v)]
         st.out_plan = ops.linear_plan(st.att, wo, st.out, bias=st.bo)
         st.heads = heads
         self._cache[key] = st

@@ -159,7 +159,7 @@ class _VaeNet(_Net):
         self.groupnorm(x, None, p + ".group_norm", g, T, cfg.norm_eps, False)
         q, k, v = self.buf(M, C), self.buf(M, C), self.buf(M, C)
         for nm, dst in (("to_q", q), ("to_k", k), ("to_v", v)):
-            self.emit_plan(ops.linear_plan(g.view(M, C), self.sd[f"{p}.{nm}.weight"].to(self.wdt).contiguous(), dst,
+            self.emit_plan(ops.linear_plan(g.view(M, C), self.sd[f"{p}.{nm}.weight"].to(act).contiguous(), dst,
                                            bias=self.wf(f"{p}.{nm}.bias")))
         att = self.buf(M, C)
         if act == f32 or C <= 160:
@@ -177,7 +177,7 @@ class _VaeNet(_Net):
                 self.emit(lambda: ops.softmax_rows(s, s), 1, "misc")
                 self.emit_plan(ops.linear_plan(s, vt[b], att[rows]))                       # O = P V
         out = self.buf(B, T, C)
-        self.emit_plan(ops.linear_plan(att, self.sd[p + ".to_out.0.weight"].to(self.wdt).contiguous(), out.view(M, C),
+        self.emit_plan(ops.linear_plan(att, self.sd[p + ".to_out.0.weight"].to(act).contiguous(), out.view(M, C),
                                        bias=self.wf(p + ".to_out.0.bias"), res1=x.view(M, C)), out=out)
         return out
 
@@ -258,7 +258,7 @@ class VaeEncoderEngine(_VaeNet):
             if i != len(boc) - 1:
                 p = f"down_blocks.{i}.downsamplers.0"
                 out = self.buf(B, (hw[0] // 2) * (hw[1] // 2), c)
-                self.emit_plan(ops.ConvPlan(x, ops.pack_conv_weight(self.sd[p + ".conv.weight"], dtype=self.wdt), out, B=B, H=hw[0], W=hw[1], Cin=c,
+                self.emit_plan(ops.ConvPlan(x, ops.pack_conv_weight(self.sd[p + ".conv.weight"]), out, B=B, H=hw[0], W=hw[1], Cin=c,
                                             Cout=c, ksize=3, stride=2, pad0=True, bias=self.wf(p + ".conv.bias")), out=out)
                 x, hw = out, (hw[0] // 2, hw[1] // 2)
         cm = boc[-1]

@@ -50,9 +50,8 @@ def test_struct_layout_matches_header(built):
         #include <stdio.h>
         #include <stddef.h>
         #include "mfb200.h"
-        int main(void) { printf("%zu %zu %zu %zu %zu %zu %zu\\n", sizeof(mfb_conv_desc), offsetof(mfb_conv_desc, x),
-                                offsetof(mfb_conv_desc, w), offsetof(mfb_conv_desc, out), offsetof(mfb_conv_desc, igemm_mode),
-                                offsetof(mfb_conv_desc, dtype), offsetof(mfb_conv_desc, w_fp16)); return 0; }
+        int main(void) { printf("%zu %zu %zu %zu %zu\\n", sizeof(mfb_conv_desc), offsetof(mfb_conv_desc, x),
+                                offsetof(mfb_conv_desc, w), offsetof(mfb_conv_desc, out), offsetof(mfb_conv_desc, igemm_mode)); return 0; }
     """)
     with tempfile.TemporaryDirectory() as d:
         c = os.path.join(d, "t.c")
@@ -61,7 +60,7 @@ def test_struct_layout_matches_header(built):
         subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), c, "-o", exe], check=True)
         got = [int(x) for x in subprocess.run([exe], capture_output=True, text=True, check=True).stdout.split()]
     D = built.ConvDesc
-    assert got == [ctypes.sizeof(D), D.x.offset, D.w.offset, D.out.offset, D.igemm_mode.offset, D.dtype.offset, D.w_fp16.offset]
+    assert got == [ctypes.sizeof(D), D.x.offset, D.w.offset, D.out.offset, D.igemm_mode.offset]
 
 
 def test_product_path_fails_loudly_without_gpu(built):

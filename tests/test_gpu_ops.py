@@ -426,72 +426,3 @@ def test_conv3x3_8x8_level_long_k(ops, B, Cin, with_res, with_extra):
         out.fill_(float("nan"))
         plan.run()
         assert rel(nhwc_to_nchw(out), ref) < 5e-3
-
-
-# ------------------------------------------------------------------------------------------------ fp16 weights x bf16 activations
-def test_fp16_weights_mixed_format_mma(ops):
-    """mfb_conv_desc.w_fp16: tcgen05.mma kind::f16 with a_format = BF16 (activations) and b_format = F16 (weights).  Weights whose
-    fp16 and bf16 roundings DIFFER (11 vs 8 significand bits) tell the two formats apart: against the fp32 product with the
-    fp16-rounded weights the kernel must be at the accumulation floor, far below the error of the bf16-rounded ones."""
-    M, K, N = 1024, 640, 320
-    x = randn(M, K, seed=1)
-    w32 = torch.randn(N, K, generator=_g(2), device="cuda") * K ** -0.5
-    out16 = torch.full((M, N), float("nan"), device="cuda", dtype=bf16)
-    outbf = torch.full((M, N), float("nan"), device="cuda", dtype=bf16)
-    w16, wbf = ops.to_weight(w32, torch.float16), ops.to_weight(w32, bf16)
-    assert w16.dtype == torch.float16 and wbf.dtype == bf16
-    ops.linear_plan(x, w16, out16).run()
-    ops.linear_plan(x, wbf, outbf).run()
-    ref32 = x.float() @ w32.t()                       # unrounded weights
-    ref16 = x.float() @ w16.float().t()
-    # each kernel reproduces ITS weights to the bf16 output rounding ...
-    assert rel(out16.float(), ref16) < 3e-3 and rel(outbf.float(), x.float() @ wbf.float().t()) < 3e-3
-    # ... and in fp32 terms (before the output rounding dominates: compare the means over a block of outputs) the fp16 weights
-    # are the closer ones to the unrounded product
-    e16 = rel((x.float() @ w16.float().t()), ref32)
-    ebf = rel((x.float() @ wbf.float().t()), ref32)
-    assert e16 < 0.2 * ebf
-    # the two kernels' outputs differ (different weight roundings) by about the bf16-weight error, not by garbage
-    d = rel(out16.float(), outbf.float())
-    assert 0.2 * ebf < d < 6e-3, (d, ebf)
-    # a tensor fp16 cannot hold keeps bf16
-    big = w32.clone(); big[0, 0] = 1.0e5
-    assert ops.to_weight(big, torch.float16).dtype == bf16
-
-
-@pytest.mark.parametrize("B,H,W,Cin,Cout", [(2, 16, 16, 128, 320), (1, 64, 64, 320, 320), (4, 8, 8, 1280, 1280)])
-def test_conv3x3_fp16_weights(ops, B, H, W, Cin, Cout):
-    x = randn(B, H, W, Cin, seed=1)
-    w = torch.randn(Cout, Cin, 3, 3, generator=_g(2), device="cuda") * (9 * Cin) ** -0.5
-    bias = randn(Cout, seed=3, dtype=torch.float32)
-    r1 = randn(B, H, W, Cout, seed=5)
-    out = torch.full((B, H, W, Cout), float("nan"), device="cuda", dtype=bf16)
-    wp = ops.pack_conv_weight(w, dtype=torch.float16)
-    assert wp.dtype == torch.float16
-    ops.ConvPlan(x, wp, out, B=B, H=H, W=W, Cin=Cin, Cout=Cout, ksize=3, bias=bias, res1=r1).run()
-    ref = F.conv2d(nhwc_to_nchw(x), w.half().float(), None, padding=1) + bias.view(1, -1, 1, 1) + nhwc_to_nchw(r1)
-    assert rel(nhwc_to_nchw(out), ref) < 3e-3
-    # before the output rounding: a K-long dot product with fp16 weights is ~8x closer to the unrounded one than with bf16 weights
-    full = F.conv2d(nhwc_to_nchw(x), w, None, padding=1)
-    assert rel(F.conv2d(nhwc_to_nchw(x), w.half().float(), None, padding=1), full) < 0.2 * rel(
-        F.conv2d(nhwc_to_nchw(x), w.to(bf16).float(), None, padding=1), full)
-
-
-def test_geglu_and_upsample_fp16_weights(ops):
-    M, K, C4 = 512, 320, 1280
-    x = randn(M, K, seed=1)
-    w = torch.randn(2 * C4, K, generator=_g(2), device="cuda") * K ** -0.5
-    b = randn(2 * C4, seed=3, dtype=torch.float32)
-    wp, bp = ops.pack_geglu(w, b, dtype=torch.float16)
-    out = torch.full((M, C4), float("nan"), device="cuda", dtype=bf16)
-    ops.linear_plan(x, wp, out, bias=bp, geglu=True).run()
-    h = x.float() @ w.half().float().t() + b
-    ref = h[:, :C4] * F.gelu(h[:, C4:])
-    assert rel(out.float(), ref) < 4e-3
-    B, H, W, C = 2, 16, 16, 64
-    xi = randn(B, H, W, C, seed=4)
-    wc = torch.randn(C, C, 3, 3, generator=_g(5), device="cuda") * (9 * C) ** -0.5
-    o2 = torch.full((B, 2 * H, 2 * W, C), float("nan"), device="cuda", dtype=bf16)
-    ops.ConvPlan(xi, ops.pack_upconv_weight(wc, dtype=torch.float16), o2, B=B, H=H, W=W, Cin=C, Cout=C, ksize=3, up2x=True).run()
-    ref2 = F.conv2d(F.interpolate(nhwc_to_nchw(xi), scale_factor=2.0, mode="nearest"), wc, None, padding=1)
-    assert rel(nhwc_to_nchw(o2), ref2) < 4e-3
