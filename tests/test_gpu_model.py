@@ -33,7 +33,7 @@ def record(name, **vals):
     import json
     d = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
     os.makedirs(d, exist_ok=True)
-    with open(os.path.join(d, "parity_metrics.jsonl"), "a") as f:
+    with open(os.environ.get("MFB_PARITY_LOG") or os.path.join(d, "parity_metrics.jsonl"), "a") as f:
         f.write(json.dumps({"test": name, **vals}) + "\n")
 
 
