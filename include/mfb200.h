@@ -347,6 +347,14 @@ int mfb_conv_out_bwd(const float* dy, int B, int H, int W, int Cin, int Cout, co
 int mfb_dgrad_repack(const void* w, int Cout, int Cin, int ksize, void* wd, void* stream);
 /* Adjoint of Upsample2D's nearest-x2 replication (S/models/upsampling.py:167-173): dx [B, H*W, C] = 2x2 sums of du [B, 2H*2W, C] (bf16). */
 int mfb_sumpool2x2(const void* du, int B, int H, int W, int C, void* dx, void* stream);
+/* fp32 PARITY-MODE forms of the two kernels above (all tensors fp32, same semantics), and y += x over n fp32 elements: in parity
+ * mode the residual / skip-path gradients that the bf16 kernels fold into their last pass (`dres` of mfb_layernorm_bwd, `dres2` of
+ * mfb_groupnorm_bwd2) are added by this launch.  Together with mfb_attention_bwd_f32 / mfb_layernorm_bwd_f32 / mfb_geglu_f32 /
+ * mfb_groupnorm_bwd(dtype 1) and the fp32 conv plans they run the frozen UNet's data-gradient chain of the fine-tune step
+ * (E/train_brushnet_mirror.py:836-888,1459) in fp32 on the device, for the 1e-3 bar against float64 autograd. */
+int mfb_conv_out_bwd_f32(const float* dy, int B, int H, int W, int Cin, int Cout, const float* w, float* dx, void* stream);
+int mfb_sumpool2x2_f32(const float* du, int B, int H, int W, int C, float* dx, void* stream);
+int mfb_add_f32(float* y, const float* x, long long n, void* stream);
 
 #ifdef __cplusplus
 }

@@ -360,8 +360,21 @@ __global__ void __launch_bounds__(256) geglu_bf16_kernel(const __nv_bfloat16* __
 // conv_out is 3x3, Cin (320) -> Cout (4), fp32 NCHW output (unet_2d_condition.py:1339).  dx[b, p, ci] = sum_{co, kh, kw}
 // dy[b, co, h + 1 - kh, w + 1 - kw] w[co, kh, kw, ci]: 36 MACs per element.  Thread = (pixel, 8 input channels); the 9 x Cout
 // gradient taps of a pixel are fetched once per thread (L1-resident across the channel vectors of the same pixel).
+// 8 consecutive channels to / from bf16 (product path) or fp32 (parity mode) storage
+__device__ __forceinline__ void store8(__nv_bfloat16* p, const float (&a)[8]) { *reinterpret_cast<uint4*>(p) = pack8b(a); }
+__device__ __forceinline__ void store8(float* p, const float (&a)[8]) {
+    *reinterpret_cast<float4*>(p) = make_float4(a[0], a[1], a[2], a[3]);
+    *reinterpret_cast<float4*>(p + 4) = make_float4(a[4], a[5], a[6], a[7]);
+}
+__device__ __forceinline__ void load8(const __nv_bfloat16* p, float (&a)[8]) { unpack8b(__ldg(reinterpret_cast<const uint4*>(p)), a); }
+__device__ __forceinline__ void load8(const float* p, float (&a)[8]) {
+    const float4 u = __ldg(reinterpret_cast<const float4*>(p)), v = __ldg(reinterpret_cast<const float4*>(p + 4));
+    a[0] = u.x; a[1] = u.y; a[2] = u.z; a[3] = u.w; a[4] = v.x; a[5] = v.y; a[6] = v.z; a[7] = v.w;
+}
+
+template <typename T>
 __global__ void __launch_bounds__(256) conv_out_bwd_kernel(const float* __restrict__ dy, int B, int H, int W, int Cin, int Cout,
-                                                           const float* __restrict__ w, __nv_bfloat16* __restrict__ dx) {
+                                                           const float* __restrict__ w, T* __restrict__ dx) {
     pdl_trigger();
     pdl_wait();
     const int cv = Cin >> 3;
@@ -386,7 +399,7 @@ __global__ void __launch_bounds__(256) conv_out_bwd_kernel(const float* __restri
                     acc[4] = fmaf(g, w1.x, acc[4]); acc[5] = fmaf(g, w1.y, acc[5]); acc[6] = fmaf(g, w1.z, acc[6]); acc[7] = fmaf(g, w1.w, acc[7]);
                 }
             }
-        *reinterpret_cast<uint4*>(dx + pix * Cin + v * 8) = pack8b(acc);
+        store8(dx + pix * Cin + v * 8, acc);
     }
 }
 
@@ -418,8 +431,8 @@ __global__ void __launch_bounds__(256) dgrad_repack_kernel(const __nv_bfloat16* 
 // ------------------------------------------------------------------------------------------------ 2x2 sum-pool
 // Adjoint of the nearest-x2 replication of Upsample2D (S/models/upsampling.py:167-173): dx[b, i, j, :] = sum of the four
 // high-resolution gradients du[b, 2i + {0,1}, 2j + {0,1}, :].  Thread = (low-resolution pixel, 8 channels).
-__global__ void __launch_bounds__(256) sumpool2x2_kernel(const __nv_bfloat16* __restrict__ du, int B, int H, int W, int C,
-                                                         __nv_bfloat16* __restrict__ dx) {
+template <typename T>
+__global__ void __launch_bounds__(256) sumpool2x2_kernel(const T* __restrict__ du, int B, int H, int W, int C, T* __restrict__ dx) {
     pdl_trigger();
     pdl_wait();
     const int cv = C >> 3;
@@ -430,20 +443,28 @@ __global__ void __launch_bounds__(256) sumpool2x2_kernel(const __nv_bfloat16* __
         const long long pix = i / cv;
         const int x_ = static_cast<int>(pix % W), y_ = static_cast<int>((pix / W) % H);
         const long long b = pix / (static_cast<long long>(W) * H);
-        const __nv_bfloat16* src = du + ((b * 2 * H + 2 * y_) * 2 * W + 2 * x_) * C + v * 8;
+        const T* src = du + ((b * 2 * H + 2 * y_) * 2 * W + 2 * x_) * C + v * 8;
         float acc[8], f[8];
-        unpack8b(__ldg(reinterpret_cast<const uint4*>(src)), acc);
-        unpack8b(__ldg(reinterpret_cast<const uint4*>(src + C)), f);
+        load8(src, acc);
+        load8(src + C, f);
 #pragma unroll
         for (int e = 0; e < 8; ++e) acc[e] += f[e];
-        unpack8b(__ldg(reinterpret_cast<const uint4*>(src + static_cast<size_t>(2) * W * C)), f);
+        load8(src + static_cast<size_t>(2) * W * C, f);
 #pragma unroll
         for (int e = 0; e < 8; ++e) acc[e] += f[e];
-        unpack8b(__ldg(reinterpret_cast<const uint4*>(src + static_cast<size_t>(2) * W * C + C)), f);
+        load8(src + static_cast<size_t>(2) * W * C + C, f);
 #pragma unroll
         for (int e = 0; e < 8; ++e) acc[e] += f[e];
-        *reinterpret_cast<uint4*>(dx + pix * C + v * 8) = pack8b(acc);
+        store8(dx + pix * C + v * 8, acc);
     }
+}
+
+// y += x over n fp32 elements (parity mode: residual / skip-path gradients that the bf16 kernels fold into their last pass)
+__global__ void add32_kernel(float* __restrict__ y, const float* __restrict__ x, long long n) {
+    pdl_trigger();
+    pdl_wait();
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n; i += static_cast<long long>(gridDim.x) * blockDim.x)
+        y[i] += x[i];
 }
 
 }  // namespace mfb
@@ -460,14 +481,28 @@ extern "C" int mfb_dgrad_repack(const void* w, int Cout, int Cin, int ksize, voi
     return MFB_OK;
 }
 
-extern "C" int mfb_sumpool2x2(const void* du, int B, int H, int W, int C, void* dx, void* stream) {
+template <typename T>
+static int sumpool2x2_launch(const void* du, int B, int H, int W, int C, void* dx, void* stream) {
     MFB_REQUIRE(du && dx && B > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0, "bad arguments (C must be a multiple of 8)");
     const long long n = static_cast<long long>(B) * H * W * (C / 8);
     long long blocks = (n + 255) / 256;
     const long long cap = 32LL * (device_sm_count() > 0 ? device_sm_count() : 148);
     if (blocks > cap) blocks = cap;
-    MFB_CUDA_OK(launch_k(sumpool2x2_kernel, dim3(static_cast<unsigned>(blocks)), dim3(256), 0, static_cast<cudaStream_t>(stream), 1,
-                         static_cast<const __nv_bfloat16*>(du), B, H, W, C, static_cast<__nv_bfloat16*>(dx)));
+    MFB_CUDA_OK(launch_k(sumpool2x2_kernel<T>, dim3(static_cast<unsigned>(blocks)), dim3(256), 0, static_cast<cudaStream_t>(stream), 1,
+                         static_cast<const T*>(du), B, H, W, C, static_cast<T*>(dx)));
+    return MFB_OK;
+}
+extern "C" int mfb_sumpool2x2(const void* du, int B, int H, int W, int C, void* dx, void* stream) {
+    return sumpool2x2_launch<__nv_bfloat16>(du, B, H, W, C, dx, stream);
+}
+extern "C" int mfb_sumpool2x2_f32(const float* du, int B, int H, int W, int C, float* dx, void* stream) {
+    return sumpool2x2_launch<float>(du, B, H, W, C, dx, stream);
+}
+extern "C" int mfb_add_f32(float* y, const float* x, long long n, void* stream) {
+    MFB_REQUIRE(y && x && n > 0, "bad arguments");
+    long long blocks = (n + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    MFB_CUDA_OK(launch_k(add32_kernel, dim3(static_cast<unsigned>(blocks)), dim3(256), 0, static_cast<cudaStream_t>(stream), 1, y, x, n));
     return MFB_OK;
 }
 
@@ -555,14 +590,21 @@ extern "C" int mfb_geglu(const void* proj, long long rows, int C, void* out, con
     return MFB_OK;
 }
 
-extern "C" int mfb_conv_out_bwd(const float* dy, int B, int H, int W, int Cin, int Cout, const float* w, void* dx, void* stream) {
+template <typename T>
+static int conv_out_bwd_launch(const float* dy, int B, int H, int W, int Cin, int Cout, const float* w, void* dx, void* stream) {
     MFB_REQUIRE(dy && w && dx, "null pointer");
     MFB_REQUIRE(Cin % 8 == 0 && Cout > 0 && B > 0 && H > 0 && W > 0, "bad geometry");
     const long long n = static_cast<long long>(B) * H * W * (Cin / 8);
     long long blocks = (n + 255) / 256;
     const long long cap = 32LL * (device_sm_count() > 0 ? device_sm_count() : 148);
     if (blocks > cap) blocks = cap;
-    MFB_CUDA_OK(launch_k(conv_out_bwd_kernel, dim3(static_cast<unsigned>(blocks)), dim3(256), 0, static_cast<cudaStream_t>(stream), 1, dy, B,
-                         H, W, Cin, Cout, w, static_cast<__nv_bfloat16*>(dx)));
+    MFB_CUDA_OK(launch_k(conv_out_bwd_kernel<T>, dim3(static_cast<unsigned>(blocks)), dim3(256), 0, static_cast<cudaStream_t>(stream), 1, dy, B,
+                         H, W, Cin, Cout, w, static_cast<T*>(dx)));
     return MFB_OK;
+}
+extern "C" int mfb_conv_out_bwd(const float* dy, int B, int H, int W, int Cin, int Cout, const float* w, void* dx, void* stream) {
+    return conv_out_bwd_launch<__nv_bfloat16>(dy, B, H, W, Cin, Cout, w, dx, stream);
+}
+extern "C" int mfb_conv_out_bwd_f32(const float* dy, int B, int H, int W, int Cin, int Cout, const float* w, float* dx, void* stream) {
+    return conv_out_bwd_launch<float>(dy, B, H, W, Cin, Cout, w, dx, stream);
 }

@@ -90,6 +90,9 @@ _SIGS = {
     "mfb_conv_out_bwd": (i32, [vp, i32, i32, i32, i32, i32, vp, vp, vp]),
     "mfb_sumpool2x2": (i32, [vp, i32, i32, i32, i32, vp, vp]),
     "mfb_dgrad_repack": (i32, [vp, i32, i32, i32, vp, vp]),
+    "mfb_conv_out_bwd_f32": (i32, [vp, i32, i32, i32, i32, i32, vp, vp, vp]),
+    "mfb_sumpool2x2_f32": (i32, [vp, i32, i32, i32, i32, vp, vp]),
+    "mfb_add_f32": (i32, [vp, vp, i64, vp]),
     # fp32 parity-mode backward of attention / LayerNorm / GEGLU
     "mfb_attention_bwd_f32": (i32, [vp, i32, vp, i32, vp, i32, vp, i32, vp, i32, vp, i32, vp, i32, vp, i32, i32, i32, i32, i32, vp]),
     "mfb_layernorm_bwd_f32": (i32, [vp, vp, i32, i32, f32, vp, vp, vp]),

@@ -32,16 +32,18 @@ class FineTuneStep:
     def __init__(self, cfg: NetConfig, unet_sd: Dict[str, torch.Tensor], brushnet_sd: Dict[str, torch.Tensor], *, batch: int, H: int,
                  W: int, device="cuda", lr: float = 5e-6, betas=(0.9, 0.999), weight_decay: float = 1e-2, eps: float = 1e-8,
                  max_grad_norm: Optional[float] = 1.0, lr_schedule: str = "constant", lr_warmup_steps: int = 0, max_train_steps: int = 0,
-                 snr_gamma: Optional[float] = None, ctx_len: int = 77, group=None):
+                 snr_gamma: Optional[float] = None, ctx_len: int = 77, group=None, precision: str = "bf16"):
+        """precision="fp32": parity mode — both programs on the fp32 CUDA-core kernels (the 1e-3 bar against float64 autograd)."""
         ops.lib()
+        self.precision = precision
         self.cfg, self.B, self.H, self.W, self.dev = cfg, batch, H, W, torch.device(device)
         self.group, self.max_grad_norm, self.snr_gamma = group, max_grad_norm, snr_gamma
         self.flat = FlatParams(brushnet_shapes(cfg), self.dev)
         self.flat.load_state_dict(pack_brushnet(cfg, brushnet_sd))
-        self.brushnet = BrushNetTrainer(self.flat, cfg, B=batch, H=H, W=W)
+        self.brushnet = BrushNetTrainer(self.flat, cfg, B=batch, H=H, W=W, precision=precision)
         br = self.brushnet.branch
         taps = [z.tap for z in br.taps] + [br.mid_tap.tap] + [z.tap for z in br.up_taps]       # the reference's pop order: 12, mid, 15
-        self.unet = FrozenUNetTrainer(cfg, unet_sd, taps, B=batch, H=H, W=W, device=self.dev, ctx_len=ctx_len)
+        self.unet = FrozenUNetTrainer(cfg, unet_sd, taps, B=batch, H=H, W=W, device=self.dev, ctx_len=ctx_len, precision=precision)
         self.brushnet.bind_tap_gradients(self.unet.d_taps)      # the zero-convs read the UNet's tap gradients in place
         self.opt = B200AdamW(self.flat, lr=lr, betas=betas, eps=eps, weight_decay=weight_decay)
         self.lr_sched = LRSchedule(self.opt, lr_schedule, lr_warmup_steps, max_train_steps)

@@ -239,6 +239,23 @@ def softmax_rows(x, out):
 
 
 # --------------------------------------------------------------------------------------------- attention
+_SCRATCH32 = {}
+
+
+def _scratch32(key, n: int, device) -> torch.Tensor:
+    """Grow-only fp32 scratch of the parity-mode backward kernels (one per role and device; launches on a stream serialise on it)."""
+    t = _SCRATCH32.get(key)
+    if t is None or t.numel() < n:
+        t = _SCRATCH32[key] = torch.zeros(n, device=device, dtype=f32)
+    return t
+
+
+def add_f32(y, x):
+    """y += x (fp32, parity mode)."""
+    _req(y, f32, "y"); _req(x, f32, "x")
+    check(lib().mfb_add_f32(_ptr(y), _ptr(x), y.numel(), _stream()))
+
+
 def attention(q, k, v, out, *, B, heads, head_dim, Tq, Tk, ldq=None, ldk=None, ldv=None, ldo=None):
     """q [B,Tq,ldq], k / v [B,Tk,ld] (views into a fused q|k|v buffer are fine: pass the leading dimension)."""
     L = lib()
@@ -250,6 +267,9 @@ def attention(q, k, v, out, *, B, heads, head_dim, Tq, Tk, ldq=None, ldk=None, l
 def attention_lse(q, k, v, out, lse, *, B, heads, head_dim, Tq, Tk, ldq=None, ldk=None, ldv=None, ldo=None):
     """attention() that also keeps lse [B, heads, Tq] fp32 (log2-domain log-sum-exp per query row) for attention_bwd."""
     _req(lse, f32, "lse")
+    if _is32(q):        # parity mode: the fp32 backward recomputes its own row statistics (attention_bwd below), lse stays unused
+        attention(q, k, v, out, B=B, heads=heads, head_dim=head_dim, Tq=Tq, Tk=Tk, ldq=ldq, ldk=ldk, ldv=ldv, ldo=ldo)
+        return
     check(lib().mfb_attention_lse(_ptr(q), ldq or q.shape[-1], _ptr(k), ldk or k.shape[-1], _ptr(v), ldv or v.shape[-1],
                                   _ptr(out), ldo or out.shape[-1], B, heads, head_dim, Tq, Tk, _ptr(lse), _stream()))
 
@@ -258,6 +278,18 @@ def attention_bwd(q, k, v, o, d_o, lse, dvec, dq, dk=None, dv=None, *, B, heads,
                   lddo=None, lddq=None, lddk=None, lddv=None):
     """Backward of attention() on tcgen05 (bf16): dq always; dk / dv both or neither (cross attention to a frozen context).
     lse from attention_lse; dvec [B, heads, Tq] fp32 scratch."""
+    if _is32(q):
+        # fp32 parity mode (CUDA-core kernels, two deterministic passes that recompute the row statistics): o / lse / dvec unused;
+        # a dq-only call (cross attention to the frozen context) gets throw-away dk / dv buffers
+        ws = _scratch32(("attn_bwd_ws", q.device), 2 * B * heads * Tq, q.device)
+        if dk is None:
+            dk = _scratch32(("attn_bwd_dk", q.device), B * Tk * heads * head_dim, q.device)
+            dv = _scratch32(("attn_bwd_dv", q.device), B * Tk * heads * head_dim, q.device)
+            lddk = lddv = heads * head_dim
+        check(lib().mfb_attention_bwd_f32(_ptr(q), ldq or q.shape[-1], _ptr(k), ldk or k.shape[-1], _ptr(v), ldv or v.shape[-1], _ptr(d_o),
+                                          lddo or d_o.shape[-1], _ptr(dq), lddq or dq.shape[-1], _ptr(dk), lddk or dk.shape[-1], _ptr(dv),
+                                          lddv or dv.shape[-1], _ptr(ws), B, heads, head_dim, Tq, Tk, _stream()))
+        return
     for name, t in (("q", q), ("o", o), ("d_o", d_o), ("dq", dq)):
         if t.dtype != bf16 or not t.is_cuda:
             raise ValueError(f"{name}: expected a CUDA bfloat16 tensor")
@@ -502,17 +534,26 @@ def groupnorm_bwd(x1, x2, dy, gamma, beta, dx1, dx2, ws, *, B, HW, groups, eps, 
                                    _ptr(stats), _ptr(dres), _ptr(dres2), _ptr(dx1), _ptr(dx2), _ptr(dgamma), _ptr(dbeta), _ptr(w2),
                                    int(accumulate), _stream()))
         return
-    if dres2 is not None:
-        raise ValueError("groupnorm_bwd: dres2 needs the bf16 kernels")
+    if dres2 is not None and not is32:
+        raise ValueError("groupnorm_bwd: dres2 needs the vectorised bf16 kernels or fp32 parity mode")
+    if ws is None and is32:
+        ws = _scratch32(("gn_bwd_ws", x1.device), 2 * B * C, x1.device)
     if ws.numel() < 2 * B * C:
         raise ValueError("groupnorm_bwd: workspace smaller than MFB_GN_BWD_WS_FLOATS(B, C)")
     check(lib().mfb_groupnorm_bwd(_ptr(x1), C1, _ptr(x2), C2, _ptr(dy), int(is32), B, HW, groups, eps, _ptr(gamma), _ptr(beta),
                                   int(silu), _ptr(dres), _ptr(dx1), _ptr(dx2), _ptr(dgamma), _ptr(dbeta), _ptr(ws), int(accumulate),
                                   _stream()))
+    if dres2 is not None:       # parity mode: the skip-path gradient of the main input, added by its own launch
+        add_f32(dx1, dres2)
 
 
 def layernorm_bwd(x, dy, gamma, dx, eps=1e-5, dres=None):
     """Data gradient of layernorm() (+ dres, the gradient of the residual path), bf16 [rows, C]."""
+    if _is32(x):
+        layernorm_bwd_f32(x, dy, gamma, dx, eps)
+        if dres is not None:
+            add_f32(dx, dres)
+        return
     for name, t in (("x", x), ("dy", dy), ("dx", dx)):
         _req(t, bf16, name)
     check(lib().mfb_layernorm_bwd(_ptr(x), _ptr(dy), x.numel() // x.shape[-1], x.shape[-1], eps, _ptr(gamma), _ptr(dres), _ptr(dx), _stream()))
@@ -520,6 +561,8 @@ def layernorm_bwd(x, dy, gamma, dx, eps=1e-5, dres=None):
 
 def geglu(proj, out=None, d_out=None, d_proj=None):
     """Un-fused GEGLU on proj [rows, 2C] = [h | gate] (bf16): forward value and / or backward."""
+    if _is32(proj):
+        return geglu_f32(proj, out=out, d_out=d_out, d_proj=d_proj)
     _req(proj, bf16, "proj")
     Cc = proj.shape[-1] // 2
     check(lib().mfb_geglu(_ptr(proj), proj.numel() // proj.shape[-1], Cc, _ptr(out), _ptr(d_out), _ptr(d_proj), _stream()))
@@ -527,7 +570,12 @@ def geglu(proj, out=None, d_out=None, d_proj=None):
 
 def conv_out_bwd(dy, w, dx, *, B, H, W):
     """Data gradient of conv_out: dy fp32 NCHW [B, Cout, H, W], w fp32 [Cout, 3, 3, Cin], dx bf16 [B, H*W, Cin]."""
-    _req(dy, f32, "dy"); _req(w, f32, "w"); _req(dx, bf16, "dx")
+    _req(dy, f32, "dy"); _req(w, f32, "w")
+    if _is32(dx):
+        _req(dx, f32, "dx")
+        check(lib().mfb_conv_out_bwd_f32(_ptr(dy), B, H, W, dx.shape[-1], dy.shape[1], _ptr(w), _ptr(dx), _stream()))
+        return
+    _req(dx, bf16, "dx")
     check(lib().mfb_conv_out_bwd(_ptr(dy), B, H, W, dx.shape[-1], dy.shape[1], _ptr(w), _ptr(dx), _stream()))
 
 
@@ -544,6 +592,10 @@ def dgrad_repack(wp, wd, ksize):
 
 def sumpool2x2(du, dx, *, B, H, W):
     """dx [B, H*W, C] = 2x2 sums of du [B, 2H*2W, C] (bf16): the adjoint of the nearest-x2 replication."""
+    if _is32(du):
+        _req(du, f32, "du"); _req(dx, f32, "dx")
+        check(lib().mfb_sumpool2x2_f32(_ptr(du), B, H, W, dx.shape[-1], _ptr(dx), _stream()))
+        return
     _req(du, bf16, "du"); _req(dx, bf16, "dx")
     check(lib().mfb_sumpool2x2(_ptr(du), B, H, W, dx.shape[-1], _ptr(dx), _stream()))
 

@@ -46,11 +46,13 @@ def _dgrad_linear(w: torch.Tensor) -> torch.Tensor:
 class FrozenUNetTrainer:
     def __init__(self, cfg: NetConfig, sd: Dict[str, torch.Tensor], taps: List[torch.Tensor], *, B: int, H: int, W: int, device,
                  ctx_len: int = 77, precision: str = "bf16", K=None):
-        """taps: the 28 tap tensors [B, h*w, C] in the reference's pop order (12 down, mid, 15 up for SD1.5) — the BrushNet
+        """precision="fp32": the PARITY MODE — the same program on the CUDA-core fp32 kernels (csrc/fp32mode.cu, train.cu), for the
+        1e-3 bar against float64 autograd of the oracle on the device.
+        taps: the 28 tap tensors [B, h*w, C] in the reference's pop order (12 down, mid, 15 up for SD1.5) — the BrushNet
         trainer's buffers, read in place by the producing epilogues (`res2`)."""
         K = _ops if K is None else K
-        if precision == "fp32" and K is _ops:
-            raise NotImplementedError("the frozen-UNet backward runs in bf16 on the kernels (fp32: CPU stand-in only)")
+        if precision not in ("bf16", "fp32"):
+            raise ValueError(f"precision must be 'bf16' or 'fp32', got {precision!r}")
         self.K, self.cfg, self.B, self.H, self.W, self.dev, self.ctx_len = K, cfg, B, H, W, torch.device(device), ctx_len
         self.act = f32 if precision == "fp32" else torch.bfloat16
         self.sd = {k: v.detach().to(device=device, dtype=f32) for k, v in sd.items()}
