@@ -83,7 +83,12 @@ class ResnetBlockTrainer:
         self.d_out, self.dn2, self.dc1, self.dn1, self.dx = act(Cout), act(Cout), act(Cout), act(Cin), act(Cin)
         self.dsc = act(Cin) if self.shortcut else None
         self.d_rowbias = torch.zeros(B, Cout, device=dev, dtype=torch.float32)
+        # one GroupNorm workspace per norm: the forward leaves its per-(image, group) {sum, sum of squares} at the head of it, and
+        # the backward reads them there instead of re-reading the tensor for a statistics pass (maps above 8x8: the single-launch
+        # kernel of the small maps keeps its statistics in registers)
         self.gn_ws = torch.zeros(K.gn_ws_floats(B, groups), device=dev, dtype=torch.float32)
+        self.gn_ws2 = torch.zeros(K.gn_ws_floats(B, groups), device=dev, dtype=torch.float32)
+        self.keep_stats = self.HW > 64
         self.gnb_ws = torch.zeros(2 * B * max(Cin, Cout), device=dev, dtype=torch.float32)
         self._wsrc = flat.p if self.dt == torch.float32 else flat.w        # fp32 masters (parity mode) or the bf16 working copy
         # data-gradient weights: the same implicit-GEMM kernel over the incoming gradient with flipped / transposed weights
@@ -142,7 +147,7 @@ class ResnetBlockTrainer:
         gn = dict(B=self.B, HW=self.HW, groups=self.groups, eps=self.eps, silu=True)
         K.groupnorm(self.x, None, f.p(n("norm1.weight")), f.p(n("norm1.bias")), self.n1, self.gn_ws, **gn)     # resnet.py:337-338
         self.plan1.run()                                                                                      # :367 + :369-379
-        K.groupnorm(self.c1, None, f.p(n("norm2.weight")), f.p(n("norm2.bias")), self.n2, self.gn_ws, **gn)    # :381,393
+        K.groupnorm(self.c1, None, f.p(n("norm2.weight")), f.p(n("norm2.bias")), self.n2, self.gn_ws2, **gn)    # :381,393
         if self.shortcut:
             self.plan_sc.run()                                                                                # :398-401
         self.plan2.run()                                                                                      # :396 + :403
@@ -164,7 +169,7 @@ class ResnetBlockTrainer:
         self.plan_d2.run()                                                          # d n2
         # n2 = silu(groupnorm(c1))
         K.groupnorm_bwd(self.c1, None, self.dn2, f.p(n("norm2.weight")), f.p(n("norm2.bias")), self.dc1, None, self.gnb_ws,
-                        dgamma=G("norm2.weight"), dbeta=G("norm2.bias"), **gnb)
+                        dgamma=G("norm2.weight"), dbeta=G("norm2.bias"), stats=self.gn_ws2 if self.keep_stats else None, **gnb)
         # c1 = conv1(n1) + bias1 + rowbias[:, :, None, None]
         if tr:
             K.conv_wgrad(self.n1, self.dc1, f.g(n("conv1.weight")), f.g(n("conv1.bias")), B=B, H=H, W=W, ksize=3, accumulate=True)
@@ -181,7 +186,7 @@ class ResnetBlockTrainer:
             dres = self.d_out
         # n1 = silu(groupnorm(x)); d x = that + the shortcut path's gradient, in the same pass
         K.groupnorm_bwd(self.x, None, self.dn1, f.p(n("norm1.weight")), f.p(n("norm1.bias")), self.dx, None, self.gnb_ws,
-                        dgamma=G("norm1.weight"), dbeta=G("norm1.bias"), dres=dres, **gnb)
+                        dgamma=G("norm1.weight"), dbeta=G("norm1.bias"), dres=dres, stats=self.gn_ws if self.keep_stats else None, **gnb)
         return self.dx, self.d_rowbias
 
 
@@ -535,7 +540,12 @@ class SkipResnetBlockTrainer:
         self.d_out, self.dn2, self.dc1, self.dn1 = act(Cout), act(Cout), act(Cout), act(Cin)
         self.g1, self.g2, self.dx, self.dx2 = act(C1), act(C2), act(C1), act(C2)     # self.dx: gradient of the main input (like the other trainers)
         self.d_rowbias = torch.zeros(B, Cout, device=dev, dtype=torch.float32)
+        # one GroupNorm workspace per norm: the forward leaves its per-(image, group) {sum, sum of squares} at the head of it, and
+        # the backward reads them there instead of re-reading the tensor for a statistics pass (maps above 8x8: the single-launch
+        # kernel of the small maps keeps its statistics in registers)
         self.gn_ws = torch.zeros(K.gn_ws_floats(B, groups), device=dev, dtype=torch.float32)
+        self.gn_ws2 = torch.zeros(K.gn_ws_floats(B, groups), device=dev, dtype=torch.float32)
+        self.keep_stats = self.HW > 64
         self.gnb_ws = torch.zeros(2 * B * max(Cin, Cout), device=dev, dtype=torch.float32)
         self._wsrc = wsrc = flat.p if self.dt == torch.float32 else flat.w
         n = lambda s: f"{prefix}.{s}"
@@ -595,7 +605,7 @@ class SkipResnetBlockTrainer:
         gn = dict(B=self.B, HW=self.HW, groups=self.groups, eps=self.eps, silu=True)
         K.groupnorm(self.x1, self.x2, f.p(n("norm1.weight")), f.p(n("norm1.bias")), self.n1, self.gn_ws, **gn)
         self.plan1.run()
-        K.groupnorm(self.c1, None, f.p(n("norm2.weight")), f.p(n("norm2.bias")), self.n2, self.gn_ws, **gn)
+        K.groupnorm(self.c1, None, f.p(n("norm2.weight")), f.p(n("norm2.bias")), self.n2, self.gn_ws2, **gn)
         self.plan_sc_a.run()
         self.plan_sc_b.run()
         self.plan2.run()
@@ -612,12 +622,12 @@ class SkipResnetBlockTrainer:
         K.conv_wgrad(self.n2, self.d_out, f.g(n("conv2.weight")), f.g(n("conv2.bias")), ksize=3, **wg)
         self.plan_d2.run()
         K.groupnorm_bwd(self.c1, None, self.dn2, f.p(n("norm2.weight")), f.p(n("norm2.bias")), self.dc1, None, self.gnb_ws,
-                        dgamma=f.g(n("norm2.weight")), dbeta=f.g(n("norm2.bias")), **gnb)
+                        dgamma=f.g(n("norm2.weight")), dbeta=f.g(n("norm2.bias")), stats=self.gn_ws2 if self.keep_stats else None, **gnb)
         K.conv_wgrad(self.n1, self.dc1, f.g(n("conv1.weight")), f.g(n("conv1.bias")), ksize=3, **wg)
         K.rowsum_per_image(self.dc1, self.d_rowbias, B=B, HW=HW)
         self.plan_d1.run()
         K.groupnorm_bwd(self.x1, self.x2, self.dn1, f.p(n("norm1.weight")), f.p(n("norm1.bias")), self.g1, self.g2, self.gnb_ws,
-                        dgamma=f.g(n("norm1.weight")), dbeta=f.g(n("norm1.bias")), **gnb)
+                        dgamma=f.g(n("norm1.weight")), dbeta=f.g(n("norm1.bias")), stats=self.gn_ws if self.keep_stats else None, **gnb)
         K.conv_wgrad(self.x1, self.d_out, f.g(n("conv_shortcut.weight.a")), f.g(n("conv_shortcut.bias")), ksize=1, **wg)
         K.conv_wgrad(self.x2, self.d_out, f.g(n("conv_shortcut.weight.b")), None, ksize=1, **wg)
         self.plan_da.run()            # d x    = W_a^T d out + GroupNorm-backward half 1

@@ -171,6 +171,14 @@ class FrozenUNetTrainer:
     def w(self, name: str) -> torch.Tensor:
         return self.sd[name].contiguous()
 
+    def gn_keep(self, HW: int):
+        """A GroupNorm workspace of its own for one norm, so that its forward statistics ({sum, sum of squares} per image and
+        group at the head of the workspace) survive until its backward: -> (workspace, what to pass as `stats` to groupnorm_bwd).
+        Maps up to 8x8 go through the single-launch kernel, which keeps the statistics in registers: their backward recomputes."""
+        ws = torch.zeros(self.K.gn_ws_floats(self.B, self.cfg.norm_num_groups), device=self.dev, dtype=f32)
+        self.keep.append(ws)
+        return ws, (ws if HW > 64 else None)
+
     def wa(self, t: torch.Tensor) -> torch.Tensor:
         return t.to(self.act).contiguous()
 
@@ -264,8 +272,9 @@ class _Resnet(_Block):
         plan2 = T.plan(n2, _ops.pack_conv_weight(T.sd[p + ".conv2.weight"], extras=extras_w), self.out, B=B, H=h, W=w, Cin=cout, Cout=cout,
                        ksize=3, extras=extras_x, bias=bias.contiguous(), res1=res1, res2=tap)
         gn = dict(B=B, HW=HW, groups=T.cfg.norm_num_groups, eps=T.cfg.norm_eps, silu=True)
-        T.fwd += [lambda: K.groupnorm(xa, xb, g1, b1, n1, T.gn_ws, **gn), plan1.run,
-                  lambda: K.groupnorm(self.c1, None, g2, b2, n2, T.gn_ws, **gn), plan2.run]
+        (ws1, self.st1), (ws2, self.st2) = T.gn_keep(HW), T.gn_keep(HW)
+        T.fwd += [lambda: K.groupnorm(xa, xb, g1, b1, n1, ws1, **gn), plan1.run,
+                  lambda: K.groupnorm(self.c1, None, g2, b2, n2, ws2, **gn), plan2.run]
 
     def build_backward(self, d_out, extra_in):
         """d_out: total gradient of self.out.  extra_in: gradient of the MAIN input arriving over the skip path (or None), added
@@ -280,7 +289,7 @@ class _Resnet(_Block):
         plan_d2 = T.plan(d_out, _ops.pack_conv_dgrad_weight(T.sd[p + ".conv2.weight"]), dn2, B=B, H=h, W=w, Cin=cout, Cout=cout, ksize=3, bwd=True)
         plan_d1 = T.plan(dc1, _ops.pack_conv_dgrad_weight(T.sd[p + ".conv1.weight"]), dn1, B=B, H=h, W=w, Cin=cout, Cout=cin, ksize=3, bwd=True)
         gnb = dict(B=B, HW=HW, groups=T.cfg.norm_num_groups, eps=T.cfg.norm_eps, silu=True)
-        T.bwd += [plan_d2.run, lambda: K.groupnorm_bwd(self.c1, None, dn2, g2, b2, dc1, None, None, **gnb), plan_d1.run]
+        T.bwd += [plan_d2.run, lambda: K.groupnorm_bwd(self.c1, None, dn2, g2, b2, dc1, None, None, stats=self.st2, **gnb), plan_d1.run]
         if self.has_sc:      # shortcut path: its data gradient over the whole (concatenated) input, one 1x1 plan
             dsc = T.scratch("dsc", B, HW, cin)
             plan_dsc = T.plan(d_out, T.wa(_dgrad_linear(T.sd[p + ".conv_shortcut.weight"])), dsc, B=B, H=h, W=w, Cin=cout, Cout=cin, ksize=1, bwd=True)
@@ -288,7 +297,8 @@ class _Resnet(_Block):
             dres = dsc
         else:
             dres = d_out     # identity shortcut (resnet.py:403)
-        T.bwd.append(lambda: K.groupnorm_bwd(self.xa, self.xb, dn1, g1, b1, self.dxa, self.dxb, None, dres=dres, dres2=extra_in, **gnb))
+        T.bwd.append(lambda: K.groupnorm_bwd(self.xa, self.xb, dn1, g1, b1, self.dxa, self.dxb, None, dres=dres, dres2=extra_in,
+                                             stats=self.st1, **gnb))
         return self.dxa
 
 
@@ -379,8 +389,9 @@ class _Transformer(_Block):
         qkv = self.qkv
         kview, vview = qkv.view(-1)[C:], qkv.view(-1)[2 * C:]
         self.geo = dict(B=B, heads=heads, head_dim=d, Tq=Tn)
+        ws_gn, self.st = T.gn_keep(Tn)
         T.fwd += [
-            lambda: K.groupnorm(x, None, gnw, gnb_, g, T.gn_ws, B=B, HW=Tn, groups=cfg.norm_num_groups, eps=1e-6, silu=False),
+            lambda: K.groupnorm(x, None, gnw, gnb_, g, ws_gn, B=B, HW=Tn, groups=cfg.norm_num_groups, eps=1e-6, silu=False),
             p_in.run,
             lambda: K.layernorm(self.h0, l1g, l1b, nrm, 1e-5), p_qkv.run,
             lambda: K.attention_lse(qkv, kview, vview, self.att, self.lse, Tk=Tn, ldq=3 * C, ldk=3 * C, ldv=3 * C, ldo=C, **self.geo),
@@ -441,7 +452,7 @@ class _Transformer(_Block):
             lambda: K.layernorm_bwd(self.h0, dn, l1g, dh0, 1e-5, dres=dh1),                    # total d h0
             b_in.run,
             lambda: K.groupnorm_bwd(self.x, None, dg, gnw, gnb_, self.dx, None, None, B=B, HW=Tn, groups=cfg.norm_num_groups, eps=1e-6,
-                                    silu=False, dres=d_out)]                                    # + the transformer's residual
+                                    silu=False, dres=d_out, stats=self.st)]                     # + the transformer's residual
         T.flops_bwd += 2.5 * 4.0 * B * Tn * Tn * C + 1.5 * 4.0 * B * Tn * Lc * C
         return self.dx
 
@@ -460,7 +471,8 @@ class _Head:
         bco = T.w("conv_out.bias")
         g, b, wco = self.g, self.b, self.wco
         T.keep += [wco, bco]
-        T.fwd += [lambda: K.groupnorm(x, None, g, b, nout, T.gn_ws, B=B, HW=h * w, groups=cfg.norm_num_groups, eps=cfg.norm_eps, silu=True),
+        ws_gn, self.st = T.gn_keep(h * w)
+        T.fwd += [lambda: K.groupnorm(x, None, g, b, nout, ws_gn, B=B, HW=h * w, groups=cfg.norm_num_groups, eps=cfg.norm_eps, silu=True),
                   lambda: K.conv_out(nout, wco, bco, T.out, B=B, H=h, W=w)]
 
     def build_backward(self):
@@ -472,5 +484,5 @@ class _Head:
         g, b, wco = self.g, self.b, self.wco
         T.bwd += [lambda: K.conv_out_bwd(T.d_pred, wco, dn, B=B, H=h, W=w),
                   lambda: K.groupnorm_bwd(self.x, None, dn, g, b, self.dx, None, None, B=B, HW=h * w, groups=cfg.norm_num_groups,
-                                          eps=cfg.norm_eps, silu=True)]
+                                          eps=cfg.norm_eps, silu=True, stats=self.st)]
         return self.dx
