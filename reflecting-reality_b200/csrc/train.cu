@@ -579,6 +579,76 @@ __global__ void dbias_partial_kernel(const __nv_bfloat16* __restrict__ dy, long 
     if (threadIdx.x < 64 && c < Cout) part[static_cast<size_t>(blockIdx.y) * Cout + c] = (sm[0][threadIdx.x] + sm[1][threadIdx.x]) + (sm[2][threadIdx.x] + sm[3][threadIdx.x]);
 }
 
+// Vectorised form for bf16 tensors with C % 8 == 0 (every conv of the path): thread = one 8-channel vector (16-byte loads) of a
+// row phase, block = V vectors x R rows (V = C / 8, R = 256 / V), 4 loads in flight per thread; grid.x = row slices, grid.y =
+// independent segments of `seg_rows` rows each (1 segment = the bias gradient, one per image = the row-bias gradient).
+// part[(seg * slices + slice) * C + c]; slices are summed in order by the caller's reduce: deterministic.
+__global__ void __launch_bounds__(256) colsum8_kernel(const __nv_bfloat16* __restrict__ dy, long long seg_rows, int C,
+                                                      float* __restrict__ part) {
+    pdl_trigger();
+    pdl_wait();
+    __shared__ float sm[256 * 8];
+    const int V = C >> 3, R = blockDim.x / V;
+    const int v = threadIdx.x % V, r = threadIdx.x / V;
+    const long long per = (seg_rows + gridDim.x - 1) / gridDim.x;
+    const long long lo = blockIdx.x * per, hi = (lo + per < seg_rows) ? lo + per : seg_rows;
+    const __nv_bfloat16* src = dy + static_cast<size_t>(blockIdx.y) * seg_rows * C + v * 8;
+    float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (r < R) {
+        long long p = lo + r;
+        for (; p + 3LL * R < hi; p += 4LL * R) {
+            uint4 u[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) u[k] = __ldg(reinterpret_cast<const uint4*>(src + (p + static_cast<long long>(k) * R) * C));
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u[k]);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float2 f = __bfloat1622float2(h[e]);
+                    a[2 * e] += f.x;
+                    a[2 * e + 1] += f.y;
+                }
+            }
+        }
+        for (; p < hi; p += R) {
+            const uint4 u = __ldg(reinterpret_cast<const uint4*>(src + p * C));
+            const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float2 f = __bfloat1622float2(h[e]);
+                a[2 * e] += f.x;
+                a[2 * e + 1] += f.y;
+            }
+        }
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) sm[threadIdx.x * 8 + e] = a[e];
+    __syncthreads();
+    if (threadIdx.x < V) {            // row phases summed in order
+        float t[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) t[e] = sm[threadIdx.x * 8 + e];
+        for (int q = 1; q < R; ++q)
+#pragma unroll
+            for (int e = 0; e < 8; ++e) t[e] += sm[(q * V + threadIdx.x) * 8 + e];
+        float* dst = part + (static_cast<size_t>(blockIdx.y) * gridDim.x + blockIdx.x) * C + threadIdx.x * 8;
+        *reinterpret_cast<float4*>(dst) = make_float4(t[0], t[1], t[2], t[3]);
+        *reinterpret_cast<float4*>(dst + 4) = make_float4(t[4], t[5], t[6], t[7]);
+    }
+}
+// out[seg][c] (+)= sum over slices (in order) of part[(seg * slices + s) * C + c]
+__global__ void colsum_reduce_kernel(const float* __restrict__ part, int slices, int C, float* __restrict__ out, int accumulate) {
+    pdl_trigger();
+    pdl_wait();
+    const int c = blockIdx.x * blockDim.x + threadIdx.x, seg = blockIdx.y;
+    if (c >= C) return;
+    float a = 0.f;
+    for (int s = 0; s < slices; ++s) a += part[(static_cast<size_t>(seg) * slices + s) * C + c];
+    float* o = out + static_cast<size_t>(seg) * C + c;
+    *o = a + (accumulate ? *o : 0.f);
+}
+
 // out[b][c] = sum over the HW pixels of image b of dy[b][p][c]: the gradient of the per-image row bias
 // (time_emb_proj(silu(emb))[:, :, None, None], S/models/resnet.py:369-379).  grid (ceil(C/64), B), 4 pixel phases x 64 channels.
 template <typename T>
@@ -978,7 +1048,7 @@ static void wgrad_tc_plan(int B, int H, int W, int Cin, int Cout, int ksize, int
     *slices = (nslab + per - 1) / per;
 }
 
-#define MFB_DBIAS_SLICES 32
+#define MFB_DBIAS_SLICES 256
 
 // tcgen05 version (wgrad5.cu) for channel counts >= 64; MFB_WGRAD_LEGACY=1 keeps the mma.sync kernel (A/B)
 static bool use_wgrad5(int Cin, int Cout) {
@@ -1034,10 +1104,22 @@ extern "C" int mfb_conv_wgrad_tc(const void* x, const void* dy, int B, int H, in
     if (dbias) {
         float* bpart = ws + static_cast<size_t>(slices) * n;
         const long long P = static_cast<long long>(B) * Ho * Wo;
-        MFB_CUDA_OK(launch_k(dbias_partial_kernel, dim3((Cout + 63) / 64, MFB_DBIAS_SLICES), dim3(256), 0, st, 1,
-                             static_cast<const __nv_bfloat16*>(dy), P, Cout, bpart));
-        MFB_CUDA_OK(launch_k(wgrad_reduce_kernel, dim3(chunks_for(Cout, 256, 8)), dim3(256), 0, st, 1, static_cast<const float*>(bpart),
-                             MFB_DBIAS_SLICES, static_cast<long long>(Cout), dbias, accumulate));
+        if (Cout % 8 == 0 && Cout / 8 <= 256) {
+            // enough slices for one wave of CTAs, at least 16 rows per row phase of a slice
+            const int V = Cout / 8, R = 256 / V;
+            long long sl = P / (16LL * R);
+            if (sl > MFB_DBIAS_SLICES) sl = MFB_DBIAS_SLICES;
+            if (sl < 1) sl = 1;
+            MFB_CUDA_OK(launch_k(colsum8_kernel, dim3(static_cast<unsigned>(sl), 1), dim3(V * R), 0, st, 1,
+                                 static_cast<const __nv_bfloat16*>(dy), P, Cout, bpart));
+            MFB_CUDA_OK(launch_k(colsum_reduce_kernel, dim3((Cout + 127) / 128, 1), dim3(128), 0, st, 1, static_cast<const float*>(bpart),
+                                 static_cast<int>(sl), Cout, dbias, accumulate));
+        } else {
+            MFB_CUDA_OK(launch_k(dbias_partial_kernel, dim3((Cout + 63) / 64, 32), dim3(256), 0, st, 1,
+                                 static_cast<const __nv_bfloat16*>(dy), P, Cout, bpart));
+            MFB_CUDA_OK(launch_k(wgrad_reduce_kernel, dim3(chunks_for(Cout, 256, 8)), dim3(256), 0, st, 1, static_cast<const float*>(bpart),
+                                 32, static_cast<long long>(Cout), dbias, accumulate));
+        }
     }
     return MFB_OK;
 }
