@@ -136,6 +136,51 @@ def golden_sched_only(diffusers, name):
     print(f"{name}: scheduler trajectories written")
 
 
+def golden_step_guess_mode(diffusers, cfg, name, images=2, t=500, seed=0, scale=0.9):
+    """guess_mode with CFG as the reference pipeline runs it (pipeline_brushnet.py:1262-1301): BrushNetModel.forward(guess_mode=True)
+    on the conditional half, zeros concatenated for the unconditional half, then the UNet."""
+    from mirrorfusion_b200.synth import make_inputs
+    unet, bn, _, _ = build_reference_nets(diffusers, cfg, seed)
+    inp = make_inputs(cfg, images)
+    x = torch.cat([inp["latents"]] * 2)
+    n = images
+    with torch.no_grad():
+        d, m, u = bn(x[n:], torch.tensor(t), encoder_hidden_states=inp["prompt_embeds"][n:], brushnet_cond=inp["conditioning_latents"][n:],
+                     conditioning_scale=scale, guess_mode=True, return_dict=False)
+        d = [torch.cat([torch.zeros_like(a), a]) for a in d]
+        m = torch.cat([torch.zeros_like(m), m])
+        u = [torch.cat([torch.zeros_like(a), a]) for a in u]
+        eps = unet(x, torch.tensor(t), encoder_hidden_states=inp["prompt_embeds"], down_block_add_samples=[a.clone() for a in d],
+                   mid_block_add_sample=m, up_block_add_samples=[a.clone() for a in u], return_dict=False)[0]
+    out = {"noise_pred": eps.numpy(), "t": np.int64(t), "images": np.int64(images), "seed": np.int64(seed), "scale": np.float64(scale)}
+    for k, a in enumerate(list(d) + [m] + list(u)):
+        out[f"tap{k:02d}_l2"] = np.float64(a.double().norm().item())
+    np.savez_compressed(os.path.join(GOLD, name), **out)
+    print(f"{name}: guess-mode step |eps|={eps.norm():.4f}")
+
+
+def golden_sched_eta(diffusers, name):
+    """Stochastic DDIM (eta > 0): the reference's DDIMScheduler.step draws its variance noise from `generator` with randn_tensor
+    (scheduling_ddim.py:452-464); trajectory on the pseudo-model of golden_sched_only."""
+    g = torch.Generator().manual_seed(3)
+    x0 = torch.randn(2, 4, 8, 8, generator=g)
+    out = {"x0": x0.numpy()}
+    for eta, n, seed in ((0.7, 6, 11), (1.0, 10, 5)):
+        s = diffusers.DDIMScheduler(beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear", clip_sample=False,
+                                    set_alpha_to_one=False, steps_offset=1)
+        s.set_timesteps(n)
+        gen = torch.Generator().manual_seed(seed)
+        x = x0.clone()
+        traj = []
+        for t in s.timesteps:
+            eps = torch.sin(3.0 * x + 0.01 * float(t)) * 0.9 + 0.1 * x
+            x = s.step(eps, t, x, eta=eta, generator=gen, return_dict=False)[0]
+            traj.append(x.numpy().copy())
+        out[f"eta{eta}_n{n}_seed{seed}_traj"] = np.stack(traj)
+    np.savez_compressed(os.path.join(GOLD, name), **out)
+    print(f"{name}: stochastic DDIM trajectories written")
+
+
 def golden_psnr(diffusers, steps=20):
     """Final-image protocol of north_star: run the REFERENCE loop (SD1.5-shaped random-init nets, UniPC, CFG 7.5, fp32 CPU),
     keep the final latents, and trace a small random-init reference AutoencoderKL decoder to TorchScript so that the
@@ -384,6 +429,10 @@ def main():
         golden_signatures(diffusers, "reference_signatures.json")
     if "sched" in which:
         golden_sched_only(diffusers, "sched_traj.npz")
+    if "guess" in which:
+        golden_step_guess_mode(diffusers, TINY, "tiny_step_guess_mode.npz")
+    if "sched_eta" in which:
+        golden_sched_eta(diffusers, "sched_eta_traj.npz")
     if "micro" in which:
         golden_step(diffusers, MICRO, "micro_step.npz", images=2, t=321, scale=0.8)
         golden_loop(diffusers, MICRO, "micro_loop_ddim4.npz", "ddim", 4)

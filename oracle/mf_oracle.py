@@ -134,10 +134,11 @@ def transformer2d(sd, p: str, x: Tensor, ehs: Tensor, heads: int, groups: int) -
 
 
 # ----------------------------------------------------------------------------- BrushNet
-def brushnet_forward(sd, cfg, sample: Tensor, t, brushnet_cond: Tensor, conditioning_scale: float = 1.0
-                     ) -> Tuple[List[Tensor], Tensor, List[Tensor]]:
+def brushnet_forward(sd, cfg, sample: Tensor, t, brushnet_cond: Tensor, conditioning_scale: float = 1.0,
+                     guess_mode: bool = False) -> Tuple[List[Tensor], Tensor, List[Tensor]]:
     """BrushNetModel.forward, S/models/brushnet.py:678-925 (MirrorFusion path: resnet-only blocks,
-    no guess_mode, no global pooling).  Returns (down taps[12], mid tap, up taps[15]) for SD1.5."""
+    no global pooling).  Returns (down taps[12], mid tap, up taps[15]) for SD1.5.
+    guess_mode: tap k is scaled by conditioning_scale * logspace(-1, 0, 28)[k] (:896-902)."""
     G, eps = cfg.norm_num_groups, cfg.norm_eps
     boc = cfg.block_out_channels
     emb = time_embed(sd, t, sample.shape[0], boc[0], sample.dtype)
@@ -171,6 +172,10 @@ def brushnet_forward(sd, cfg, sample: Tensor, t, brushnet_cond: Tensor, conditio
             ups.append(x)
     up_taps = [F.conv2d(h, sd[f"brushnet_up_blocks.{k}.weight"], sd[f"brushnet_up_blocks.{k}.bias"])
                for k, h in enumerate(ups)]
+    if guess_mode:                                                               # brushnet.py:896-902
+        sc = torch.logspace(-1, 0, len(down_taps) + 1 + len(up_taps)) * conditioning_scale
+        nd = len(down_taps)
+        return [d * sc[k] for k, d in enumerate(down_taps)], mid_tap * sc[nd], [u * sc[nd + 1 + k] for k, u in enumerate(up_taps)]
     s = conditioning_scale                                                       # brushnet.py:904-906
     return [d * s for d in down_taps], mid_tap * s, [u * s for u in up_taps]
 
@@ -231,8 +236,16 @@ def unet_forward(sd, cfg, sample: Tensor, t, ehs: Tensor,
     return F.conv2d(x, sd["conv_out.weight"], sd["conv_out.bias"], padding=1)
 
 
-def noise_pred_step(unet_sd, bn_sd, cfg, latent_in: Tensor, t, ehs: Tensor, cond: Tensor, scale: float = 1.0):
-    """Loop body S/pipelines/brushnet/pipeline_brushnet.py:1277-1307: BrushNet then UNet with taps."""
+def noise_pred_step(unet_sd, bn_sd, cfg, latent_in: Tensor, t, ehs: Tensor, cond: Tensor, scale: float = 1.0, guess_mode: bool = False):
+    """Loop body S/pipelines/brushnet/pipeline_brushnet.py:1277-1307: BrushNet then UNet with taps.
+    guess_mode (with CFG, :1262-1301): BrushNet sees the conditional half only (`cond` has half the batch), its taps are log-scaled,
+    and the unconditional half of the UNet gets zeros."""
+    if guess_mode:
+        n = latent_in.shape[0] // 2
+        d, m, u = brushnet_forward(bn_sd, cfg, latent_in[n:], t, cond[-n:], scale, guess_mode=True)
+        z = lambda a: torch.cat([torch.zeros_like(a), a])
+        d, m, u = [z(a) for a in d], z(m), [z(a) for a in u]
+        return unet_forward(unet_sd, cfg, latent_in, t, ehs, d, m, u), (d, m, u)
     d, m, u = brushnet_forward(bn_sd, cfg, latent_in, t, cond, scale)
     return unet_forward(unet_sd, cfg, latent_in, t, ehs, d, m, u), (d, m, u)
 

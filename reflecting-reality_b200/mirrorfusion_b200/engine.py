@@ -322,7 +322,13 @@ class BrushNetEngine(_Net):
         n = len(boc)
         self.sample_in = torch.zeros(B, cfg.in_channels, H, W, device=device, dtype=f32)
         self.cond_in = torch.zeros(B, cfg.conditioning_channels, H, W, device=device, dtype=f32)
-        self.scale = torch.ones(1, device=device, dtype=f32)
+        # zero-conv output scales, one device scalar per tap (epilogue alpha): conditioning_scale, times logspace(-1, 0, 28) in
+        # guess mode (brushnet.py:896-906).  set_scale() rewrites them; the captured graph reads them at replay.
+        ntap = sum(cfg.layers_per_block + (i != len(cfg.block_out_channels) - 1) for i in range(len(cfg.block_out_channels))) + 1 + 1 + \
+            sum(cfg.layers_per_block + 1 + (i != len(cfg.block_out_channels) - 1) for i in range(len(cfg.block_out_channels)))
+        self.scales = torch.ones(ntap, device=device, dtype=f32)
+        self._scale_base = torch.ones(ntap, dtype=f32)
+        self.scale = self.scales[:1]             # the conv_in-site tap's scale (fused mode materialises only that tap)
         self.build_time_path(_resnet_prefixes(cfg))
         # conv_in_condition (brushnet.py:810-811)
         wci = self.D(self.sd["conv_in_condition.weight"].permute(2, 3, 1, 0).contiguous())
@@ -371,10 +377,21 @@ class BrushNetEngine(_Net):
             t = tap_bufs[k] if tap_bufs is not None else self.buf(B, shw[0] * shw[1], c)
             wz = self.D(ops.pack_conv_weight(self.sd[nm + ".weight"]))
             self.emit_plan(ops.ConvPlan(src, wz, t, B=B, H=shw[0], W=shw[1], Cin=c, Cout=c, ksize=1,
-                                        bias=self.wf(nm + ".bias"), alpha=self.scale), out=t)
+                                        bias=self.wf(nm + ".bias"), alpha=self.scales[k:k + 1]), out=t)
             self.taps.append(t)
             self.tap_hw.append(shw)
         self.n_down = len(down_feats)
+        assert len(srcs) == ntap
+
+    def set_scale(self, conditioning_scale: float, guess_mode: bool = False):
+        """conditioning_scale for every tap; guess_mode: times torch.logspace(-1, 0, 28) (0.1 ... 1.0 from the first down tap to the
+        last up tap, brushnet.py:896-902)."""
+        key = (float(conditioning_scale), bool(guess_mode))
+        if getattr(self, "_scale_key", None) == key:
+            return
+        base = torch.logspace(-1, 0, self.scales.numel(), dtype=f32) if guess_mode else self._scale_base
+        self.scales.copy_(base * float(conditioning_scale))
+        self._scale_key = key
 
 
 class UNetEngine(_Net):

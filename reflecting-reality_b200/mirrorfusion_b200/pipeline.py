@@ -74,8 +74,8 @@ class B200BrushNetModel:
                 cross_attention_kwargs=None, guess_mode: bool = False, return_dict: bool = True):
         if brushnet_cond is None:
             raise ValueError("brushnet_cond is required")
-        if guess_mode or class_labels is not None or timestep_cond is not None or added_cond_kwargs:
-            raise NotImplementedError("guess_mode / class / additional embeddings are not on the MirrorFusion path")
+        if class_labels is not None or timestep_cond is not None or added_cond_kwargs:
+            raise NotImplementedError("class / additional embeddings are not on the MirrorFusion path")
         B, _, H, W = sample.shape
         if brushnet_cond.shape[1] != self.cfg.conditioning_channels:
             raise ValueError(f"brushnet_cond has {brushnet_cond.shape[1]} channels, expected {self.cfg.conditioning_channels}")
@@ -83,7 +83,7 @@ class B200BrushNetModel:
         e.sample_in.copy_(sample)
         e.cond_in.copy_(brushnet_cond)
         e.t_dev.copy_(_as_timestep_vector(timestep, B, self.device))
-        e.scale.fill_(float(conditioning_scale))
+        e.set_scale(float(conditioning_scale), guess_mode=bool(guess_mode))     # guess mode: log-spaced tap scales (brushnet.py:896-902)
         e.run()
         outs = []
         for t, (h, w) in zip(e.taps, e.tap_hw):
@@ -245,7 +245,7 @@ class StepEngine:
 
     def __init__(self, cfg: NetConfig, unet_sd, brushnet_sd, images: int, H: int, W: int, device="cuda",
                  use_graph: bool = True, fuse_taps: bool = True, two_streams: bool = False,
-                 dedup_brushnet_cfg: bool = False, precision: str = "bf16", host_pack: bool = False):
+                 dedup_brushnet_cfg: bool = False, precision: str = "bf16", host_pack: bool = False, guess_mode: bool = False):
         """precision: "bf16" = the product path (tcgen05 kernels); "fp32" = the PARITY MODE of BASELINE config 1 — the
         same program (fusions, K-segments, tap folding, buffers) with fp32 storage on the CUDA-core kernels of
         csrc/fp32mode.cu, for the rel-L2 1e-4 bar against the fp32 reference.
@@ -255,7 +255,14 @@ class StepEngine:
         pipeline_brushnet.py:1256,1188-1202).  The branch is then evaluated on `images` samples and its 28 features
         are broadcast to both halves before the UNet consumes them — bit-identical taps, 18 % fewer FLOPs per step.
         `set_conditioning` refuses conditioning whose halves differ.  Off by default: the headline numbers of
-        bench.py run the reference's full 2b-sample BrushNet."""
+        bench.py run the reference's full 2b-sample BrushNet.
+        guess_mode: the pipeline's guess mode with CFG (pipeline_brushnet.py:1262-1301): BrushNet runs on the CONDITIONAL batch
+        only (`images` samples), its 28 taps are scaled by conditioning_scale x logspace(-1, 0, 28) (brushnet.py:896-902) and the
+        unconditional half of the UNet receives zeros — here the zero-convs write straight into the second half of the UNet's tap
+        buffers, whose first half stays zero."""
+        self.guess_mode = bool(guess_mode)
+        if self.guess_mode and (dedup_brushnet_cfg or two_streams):
+            raise ValueError("guess_mode excludes dedup_brushnet_cfg / two_streams")
         self.precision = precision
         self._hp = bool(host_pack)          # engine._Net: repack the weights on the host and upload the results
         with ops.precision(precision):      # engines read the storage dtype while they are built
@@ -270,7 +277,11 @@ class StepEngine:
         self.dedup = bool(dedup_brushnet_cfg)
         if self.dedup and not fuse_taps:
             raise ValueError("dedup_brushnet_cfg requires fuse_taps=True")
-        if self.dedup:
+        if self.guess_mode:
+            self.fuse_taps = fuse_taps = False
+            self.unet = UNetEngine(cfg, unet_sd, B, H, W, self.dev, host_pack=hp)
+            self.bn = BrushNetEngine(cfg, brushnet_sd, images, H, W, self.dev, tap_bufs=[t[images:] for t in self.unet.taps], host_pack=hp)
+        elif self.dedup:
             self.bn = BrushNetEngine(cfg, brushnet_sd, images, H, W, self.dev, only_first_tap=True, host_pack=hp)
             dup = lambda t: torch.empty(2, *t.shape, device=self.dev, dtype=t.dtype)
             both = []
@@ -309,7 +320,10 @@ class StepEngine:
 
     def set_conditioning(self, prompt_embeds: torch.Tensor, conditioning_latents: torch.Tensor):
         self.unet.set_context(prompt_embeds)
-        if self.dedup:
+        if self.guess_mode:        # prepare_image does not duplicate the conditioning in guess mode (:771-772): `images` samples
+            n = self.images
+            self.bn.cond_in.copy_(conditioning_latents[-n:])
+        elif self.dedup:
             n = self.images
             if not torch.equal(conditioning_latents[:n], conditioning_latents[n:]):
                 raise ValueError("dedup_brushnet_cfg: the two CFG halves of conditioning_latents differ")
@@ -382,7 +396,7 @@ class StepEngine:
         else:
             self.bn.t_dev.fill_(float(t))
             self.unet.t_dev.fill_(float(t))
-        self.bn.scale.fill_(float(scale))
+        self.bn.set_scale(float(scale), guess_mode=self.guess_mode)
         if self.fuse_taps and float(scale) != self._tap_scale:      # rare: only at control-guidance window edges
             self.unet.set_tap_scale(float(scale))
             self._tap_scale = float(scale)
@@ -412,9 +426,14 @@ class StepEngine:
 
     def denoise(self, latents: torch.Tensor, scheduler, num_inference_steps: int, guidance_scale: float = 7.5,
                 conditioning_scales: Optional[List[float]] = None,
-                callback: Optional[Callable[[int, int, torch.Tensor], Optional[torch.Tensor]]] = None) -> torch.Tensor:
+                callback: Optional[Callable[[int, int, torch.Tensor], Optional[torch.Tensor]]] = None, eta: float = 0.0,
+                generator=None) -> torch.Tensor:
+        """eta / generator: the `extra_step_kwargs` of the reference loop (pipeline_brushnet.py:556-571,1315) — used by DDIM only
+        (UniPC's `step` takes neither, so the reference drops them).  With eta > 0 every step's variance noise is drawn exactly
+        like `randn_tensor` in DDIMScheduler.step does and rides into the fused kernel as its `m0` operand."""
         scheduler.set_timesteps(num_inference_steps, device="cpu")
-        table = scheduler.coefficient_table(guidance_scale).to(self.dev)
+        stochastic = bool(eta) and getattr(scheduler, "takes_variance_noise", False)
+        table = (scheduler.coefficient_table(guidance_scale, eta) if stochastic else scheduler.coefficient_table(guidance_scale)).to(self.dev)
         self.x.copy_(latents.to(device=self.dev, dtype=f32) * scheduler.init_noise_sigma)
         for t_ in (self.last, self.m0, self.m1):
             t_.zero_()
@@ -423,6 +442,8 @@ class StepEngine:
             self.prepare_timesteps(ts)
         for i, t in enumerate(ts):
             sc = 1.0 if conditioning_scales is None else conditioning_scales[i]
+            if stochastic:
+                self.m0.copy_(scheduler.variance_noise(self.x.shape, generator, self.dev, f32))
             self.step(float(t), table[i], sc)
             if callback is not None:
                 new = callback(i, int(t), self.x)
@@ -488,11 +509,11 @@ class MirrorFusionB200Pipeline:
                                                           self.device)
         return self._vae_engines[key].decode(z).clone()
 
-    def engine(self, images, H, W) -> StepEngine:
-        key = (images, H, W)
+    def engine(self, images, H, W, guess_mode: bool = False) -> StepEngine:
+        key = (images, H, W) + (("guess",) if guess_mode else ())
         if key not in self._engines:
             self._engines[key] = StepEngine(self.cfg, self.unet_sd, self.brushnet_sd, images, H, W, self.device,
-                                            precision=self.precision)
+                                            precision=self.precision, guess_mode=guess_mode)
         return self._engines[key]
 
     def check_inputs(self, prompt_embeds, negative_prompt_embeds, brushnet_conditioning_scale, control_guidance_start,
@@ -537,8 +558,6 @@ class MirrorFusionB200Pipeline:
             # retrieve_timesteps (:112-121): neither scheduler of the path accepts a custom schedule in `set_timesteps`; same error
             raise ValueError(f"The current scheduler class {self.scheduler.__class__}'s `set_timesteps` does not support custom"
                              f" timestep schedules. Please check whether you are using the correct scheduler.")
-        if eta != 0.0 or guess_mode:
-            raise NotImplementedError("eta > 0 (stochastic DDIM) / guess_mode are not implemented")
         self.check_inputs(prompt_embeds, negative_prompt_embeds, brushnet_conditioning_scale, control_guidance_start,
                           control_guidance_end, callback_on_step_end_tensor_inputs)
         do_cfg = guidance_scale > 1.0                                                      # :835-836
@@ -566,13 +585,14 @@ class MirrorFusionB200Pipeline:
         ehs = torch.cat([negative_prompt_embeds, prompt_embeds])                           # uncond first (:1102-1103)
         if conditioning_latents is None:
             conditioning_latents = self._prepare_conditioning(image, mask, depth, b)
-        if conditioning_latents.shape[0] == b:
-            conditioning_latents = torch.cat([conditioning_latents] * 2)                   # CFG duplicate (:771-772)
+        if conditioning_latents.shape[0] == b and not guess_mode:
+            conditioning_latents = torch.cat([conditioning_latents] * 2)                   # CFG duplicate (:771-772; not in guess mode)
         H, W = conditioning_latents.shape[-2:]
         if latents is None:
             latents = torch.randn(b, self.cfg.in_channels, H, W, generator=generator,
                                   device=generator.device if generator is not None else "cpu")   # randn_tensor semantics
-        eng = self.engine(b, H, W)
+        # guess_mode (:1076-1081,1262-1301): BrushNet on the conditional batch only, log-spaced tap scales, zeros for the uncond half
+        eng = self.engine(b, H, W, guess_mode=bool(guess_mode))
         eng.set_conditioning(ehs, conditioning_latents)
         n = num_inference_steps
         keep = [1.0 - float(i / n < control_guidance_start or (i + 1) / n > control_guidance_end) for i in range(n)]   # :1236-1242
@@ -582,7 +602,8 @@ class MirrorFusionB200Pipeline:
             def cb(i, t, x):
                 out = callback_on_step_end(self, i, t, {"latents": x})
                 return None if out is None else out.pop("latents", None)
-        x = eng.denoise(latents, self.scheduler, n, guidance_scale, scales, cb)
+        # eta / generator = prepare_extra_step_kwargs (:556-571): forwarded to the scheduler step only if it takes them (DDIM)
+        x = eng.denoise(latents, self.scheduler, n, guidance_scale, scales, cb, eta=eta, generator=generator)
         result = x.clone()
         if output_type != "latent":
             if self.vae_decode is None:

@@ -65,28 +65,49 @@ class _Base:
             self._coef = torch.zeros(12, device=sample.device, dtype=torch.float32)
             self._state_shape = shape
 
-    def coefficient_table(self, guidance_scale: float) -> torch.Tensor:
+    def coefficient_table(self, guidance_scale: float, eta: float = 0.0) -> torch.Tensor:
         rows = []
         for i in range(self.num_inference_steps):
-            c = self.coefficients(i)
+            c = self.coefficients(i, eta) if eta else self.coefficients(i)
             c[G] = guidance_scale
             rows.append(c)
         return torch.tensor(np.stack(rows), dtype=torch.float32)
 
-    def _step(self, model_output: torch.Tensor, timestep, sample: torch.Tensor, eta: float = 0.0, return_dict: bool = True):
+    # eta > 0 (stochastic DDIM): the variance noise rides in the kernel's `m0` operand, which DDIM does not use otherwise
+    takes_variance_noise = False
+
+    @staticmethod
+    def variance_noise(shape, generator, device, dtype=torch.float32) -> torch.Tensor:
+        """The draw of `randn_tensor(model_output.shape, generator=generator, device=..., dtype=...)` (scheduling_ddim.py:455-458,
+        S/utils/torch_utils.py:39-88): a CPU generator draws on the host and the tensor is moved, a device generator (or none) draws
+        on the device."""
+        if isinstance(generator, (list, tuple)):
+            if len(generator) != shape[0]:
+                raise ValueError(f"got {len(generator)} generators for a batch of {shape[0]}")
+            return torch.cat([_Base.variance_noise((1,) + tuple(shape[1:]), g, device, dtype) for g in generator], 0)
+        if generator is not None and generator.device.type == "cpu":
+            return torch.randn(tuple(shape), generator=generator, dtype=dtype).to(device)
+        return torch.randn(tuple(shape), generator=generator, device=device, dtype=dtype)
+
+    def _step(self, model_output: torch.Tensor, timestep, sample: torch.Tensor, eta: float = 0.0, return_dict: bool = True,
+              generator=None, variance_noise: Optional[torch.Tensor] = None):
         """Reference-compatible single step on an already guided `model_output` (same kernel, g = 0)."""
         if self.num_inference_steps is None:
             raise ValueError("Number of inference steps is 'None', you need to run 'set_timesteps' after creating the scheduler")
-        if eta != 0.0:
-            raise NotImplementedError("eta > 0 (stochastic DDIM) is not on the MirrorFusion path")
+        if eta != 0.0 and not self.takes_variance_noise:
+            raise NotImplementedError("eta is a DDIM parameter (the reference ignores it for other schedulers, pipeline_brushnet.py:556-571)")
         if not sample.is_cuda:
             raise RuntimeError("mirrorfusion_b200 schedulers run on the GPU only (no CPU fallback)")
         i = self._index_for(timestep)
         self._ensure_state(sample)
         self._x.copy_(sample)
         eps = model_output.to(torch.float32).contiguous()
-        c = self.coefficients(i)
+        c = self.coefficients(i, eta) if eta else self.coefficients(i)
         c[G] = 0.0
+        if eta:
+            if variance_noise is None:
+                variance_noise = self.variance_noise(model_output.shape, generator, model_output.device, model_output.dtype)
+            self._m0.copy_(variance_noise.to(torch.float32))
         self._coef.copy_(torch.tensor(c, dtype=torch.float32), non_blocking=False)
         ops.cfg_sched_step(eps, eps, self._x, self._last, self._m0, self._m1, self._coef)
         self._advance(i)
@@ -97,7 +118,10 @@ class _Base:
 
 
 class B200DDIMScheduler(_Base):
-    """DDIMScheduler (S/schedulers/scheduling_ddim.py): leading spacing + steps_offset (:299-342), eta = 0 step (:404-450)."""
+    """DDIMScheduler (S/schedulers/scheduling_ddim.py): leading spacing + steps_offset (:299-342), the step (:404-466) incl. eta > 0:
+    sigma_t = eta * sqrt((1 - a_prev) / (1 - a_t) * (1 - a_t / a_prev)) (:260-267,426-428), direction sqrt(1 - a_prev - sigma_t^2) eps
+    (:444), + sigma_t * noise (:452-464)."""
+    takes_variance_noise = True
 
     def __init__(self, num_train_timesteps=1000, beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear",
                  clip_sample=False, set_alpha_to_one=False, steps_offset=1, prediction_type="epsilon"):
@@ -149,11 +173,15 @@ class B200DDIMScheduler(_Base):
              variance_noise=None, return_dict: bool = True):
         """DDIMScheduler.step (scheduling_ddim.py:344-466), same signature (the pipeline picks `eta` / `generator` by
         signature inspection, pipeline_brushnet.py:556-571)."""
-        if use_clipped_model_output or variance_noise is not None:
-            raise NotImplementedError("use_clipped_model_output / variance_noise are not on the MirrorFusion path")
-        return self._step(model_output, timestep, sample, eta=eta, return_dict=return_dict)
+        if use_clipped_model_output:
+            raise NotImplementedError("use_clipped_model_output is not on the MirrorFusion path")
+        if generator is not None and variance_noise is not None:
+            raise ValueError("Cannot pass both generator and variance_noise. Please make sure that either `generator` or"
+                             " `variance_noise` stays `None`.")                              # :452-456
+        return self._step(model_output, timestep, sample, eta=eta, return_dict=return_dict, generator=generator,
+                          variance_noise=variance_noise)
 
-    def coefficients(self, i: int) -> np.ndarray:
+    def coefficients(self, i: int, eta: float = 0.0) -> np.ndarray:
         t = int(self._ts[i])
         prev_t = t - self.config.num_train_timesteps // self.num_inference_steps
         a_t = float(self.alphas_cumprod[t])
@@ -161,8 +189,11 @@ class B200DDIMScheduler(_Base):
         c = np.zeros(12, dtype=np.float64)
         c[C_X] = 1.0 / math.sqrt(a_t)                       # x0 = (x - sqrt(1-a_t) eps) / sqrt(a_t)   (:420)
         c[C_EPS] = -math.sqrt(1.0 - a_t) / math.sqrt(a_t)
-        c[B_MT] = math.sqrt(a_prev)                         # x_prev = sqrt(a_prev) x0 + sqrt(1-a_prev) eps   (:447-450)
-        c[B_EPS] = math.sqrt(1.0 - a_prev)
+        var = (1.0 - a_prev) / (1.0 - a_t) * (1.0 - a_t / a_prev)                               # _get_variance (:260-267)
+        std = eta * math.sqrt(max(var, 0.0))                                                    # :428
+        c[B_MT] = math.sqrt(a_prev)                         # x_prev = sqrt(a_prev) x0 + sqrt(1-a_prev-std^2) eps (+ std noise)   (:444-464)
+        c[B_EPS] = math.sqrt(max(1.0 - a_prev - std * std, 0.0))
+        c[B_M0] = std                                       # the variance noise is handed over in the m0 operand
         return c
 
 

@@ -181,3 +181,20 @@ def test_resize_oracle_vs_torchvision():
         if res % 8 == 0:
             assert np.abs(resize_crop_bicubic(x, res, 8) - want[:, ::8, ::8]).max() < 1e-5
     assert resized_size(300, 451, 256) == (256, 384) and crop_offsets(256, 385, 256) == (0, 64)      # round half to even: 64.5 -> 64
+
+
+def test_guess_mode_step_matches_reference(golden_dir):
+    """guess_mode with CFG (pipeline_brushnet.py:1262-1301; brushnet.py:896-902): BrushNet on the conditional half with log-spaced tap
+    scales, zeros for the unconditional half — vector written by the reference's own BrushNetModel.forward(guess_mode=True) + UNet."""
+    g = _load(golden_dir, "tiny_step_guess_mode.npz")
+    cfg, images = TINY, int(g["images"])
+    usd, bsd = make_state_dict(cfg, "unet", int(g["seed"])), make_state_dict(cfg, "brushnet", int(g["seed"]))
+    inp = make_inputs(cfg, images)
+    x = torch.cat([inp["latents"]] * 2)
+    with torch.no_grad():
+        eps, (d, m, u) = O.noise_pred_step(usd, bsd, cfg, x, torch.tensor(int(g["t"])), inp["prompt_embeds"],
+                                           inp["conditioning_latents"][images:], float(g["scale"]), guess_mode=True)
+    assert rel(eps, g["noise_pred"]) < 1e-4
+    for k, a in enumerate(list(d) + [m] + list(u)):
+        assert abs(a.double().norm().item() / float(g[f"tap{k:02d}_l2"]) - 1) < 1e-4
+        assert float(a[:images].abs().max()) == 0.0                     # the unconditional half gets zeros

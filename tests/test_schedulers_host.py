@@ -62,3 +62,29 @@ def test_scheduler_surface_matches_reference_contract():
     # DDIM from a UniPC config and vice versa (E/test_brushnet.py:158 builds UniPC from the pipeline scheduler's config)
     u = S.B200UniPCScheduler.from_config(S.B200DDIMScheduler().config)
     assert u.config.beta_schedule == "scaled_linear"
+
+
+@pytest.mark.parametrize("eta,n,seed", [(0.7, 6, 11), (1.0, 10, 5)])
+def test_stochastic_ddim_coefficients_reproduce_reference_trajectory(golden_dir, eta, n, seed):
+    """eta > 0 (scheduling_ddim.py:426-464): sigma_t in the B_M0 slot, the direction coefficient shrunk to sqrt(1 - a_prev - sigma^2),
+    and the variance noise — drawn per step from the caller's generator exactly like `randn_tensor` does — handed over as `m0`."""
+    import torch
+    g = np.load(os.path.join(golden_dir, "sched_eta_traj.npz"))
+    s = S.B200DDIMScheduler()
+    s.set_timesteps(n)
+    table = s.coefficient_table(0.0, eta).numpy()
+    assert (table[:, S.B_M0] > 0).all() and (s.coefficient_table(0.0).numpy()[:, S.B_M0] == 0).all()
+    gen = torch.Generator().manual_seed(seed)
+    x = g["x0"].astype(np.float32)
+    z = np.zeros_like(x)
+    for i, t in enumerate(s.timesteps.numpy()):
+        eps = (np.sin(3.0 * x + 0.01 * float(t)) * 0.9 + 0.1 * x).astype(np.float32)
+        noise = s.variance_noise(x.shape, gen, "cpu").numpy()
+        x = apply_kernel_math(table[i], eps, eps, x, z, noise, z)[0].astype(np.float32)
+        ref = g[f"eta{eta}_n{n}_seed{seed}_traj"][i]
+        err = np.linalg.norm(x - ref) / np.linalg.norm(ref)
+        assert err < 5e-6, f"step {i}: {err}"
+    # UniPC takes neither eta nor generator (the pipeline's signature inspection drops them, pipeline_brushnet.py:556-571)
+    import inspect
+    assert "eta" not in inspect.signature(S.B200UniPCScheduler.step).parameters
+    assert {"eta", "generator"} <= set(inspect.signature(S.B200DDIMScheduler.step).parameters)
