@@ -466,7 +466,7 @@ def test_guess_mode_step_vs_reference_golden(P, golden_dir):
     from mirrorfusion_b200 import schedulers as S
     g = np.load(os.path.join(golden_dir, "tiny_step_guess_mode.npz"))
     cfg, n = TINY, int(g["images"])
-    usd, bsd = _nets(P, cfg)
+    usd, bsd = make_state_dict(cfg, "unet"), make_state_dict(cfg, "brushnet")
     inp = make_inputs(cfg, n)
     eng = P.StepEngine(cfg, usd, bsd, n, cfg.sample_size, cfg.sample_size, guess_mode=True)
     eng.set_conditioning(inp["prompt_embeds"], inp["conditioning_latents"][n:])
