@@ -80,6 +80,24 @@ typedef struct mfb_conv_desc {
                              are fp32, CUDA-core FFMA accumulation (csrc/fp32mode.cu) — same descriptor semantics */
 } mfb_conv_desc;
 
+/* ------------------------------------------------------------------------------------------------------------
+ * Recorded launch programs: the model-level entry point.
+ * Between mfb_program_begin and mfb_program_end every step-level call made ON THE SAME THREAD (mfb_plan_run, mfb_groupnorm[_prestat],
+ * mfb_layernorm, mfb_attention, mfb_conv_in / _out, mfb_cfg_sched_step, mfb_timestep_sinusoid, mfb_linear_small, the layout / dtype
+ * conversions, mfb_softmax_rows, mfb_transpose_tokens, mfb_latent_sample, mfb_copy_f32 and their *_f32 parity-mode forms) is
+ * executed AND appended to the program with its arguments; mfb_program_run replays the whole sequence on a stream from ONE call.
+ * Recorded once over StepEngine's step it is `mfb_step_fused` of SURVEY.md §8b: latents -> BrushNetModel.forward -> UNet2DConditionModel
+ * .forward with the 28 taps -> CFG combine -> scheduler step (pipeline_brushnet.py:1250-1315), 512 launches, no host language in the
+ * loop; per-step inputs (latents, the 12 scheduler coefficients, the timestep's row biases, the tap scales) live in fixed device
+ * buffers the caller rewrites between runs.  Everything a recorded call references (buffers, plans) must outlive the program. */
+typedef struct mfb_program mfb_program;
+int mfb_program_begin(mfb_program** out);
+int mfb_program_end(void);
+int mfb_program_size(const mfb_program* prog);            /* recorded calls */
+int mfb_program_run(mfb_program* prog, void* stream);
+int mfb_program_destroy(mfb_program* prog);
+int mfb_copy_f32(float* dst, const float* src, long long n, void* stream);   /* dst[i] = src[i]: the `torch.cat([latents] * 2)` of the loop */
+
 typedef struct mfb_plan mfb_plan;
 int mfb_conv_plan_create(const mfb_conv_desc* desc, mfb_plan** out);
 int mfb_plan_run(mfb_plan* plan, void* stream);

@@ -24,6 +24,14 @@ void set_error(const char* fmt, ...) {
 
 int device_sm_count() { return g_sms; }
 
+static thread_local Program* g_recording = nullptr;
+Program* recording() { return g_recording; }
+
+__global__ void copy32_kernel(float* __restrict__ dst, const float* __restrict__ src, long long n) {
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n; i += static_cast<long long>(gridDim.x) * blockDim.x)
+        dst[i] = src[i];
+}
+
 bool pdl_enabled() {
     static int v = -1;
     if (v < 0) {
@@ -102,5 +110,52 @@ extern "C" int mfb_init(int device) {
     }
     g_encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
     g_device = device;
+    return MFB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- recorded launch programs
+extern "C" int mfb_program_begin(mfb_program** out) {
+    MFB_REQUIRE(out, "null argument");
+    MFB_REQUIRE(g_recording == nullptr, "a program is already being recorded on this thread");
+    g_recording = new Program();
+    *out = reinterpret_cast<mfb_program*>(g_recording);
+    return MFB_OK;
+}
+
+extern "C" int mfb_program_end(void) {
+    MFB_REQUIRE(g_recording != nullptr, "no program is being recorded on this thread");
+    g_recording = nullptr;
+    return MFB_OK;
+}
+
+extern "C" int mfb_program_size(const mfb_program* prog) {
+    return prog ? static_cast<int>(reinterpret_cast<const Program*>(prog)->ops.size()) : 0;
+}
+
+extern "C" int mfb_program_run(mfb_program* prog, void* stream) {
+    MFB_REQUIRE(prog, "null program");
+    Program* p = reinterpret_cast<Program*>(prog);
+    MFB_REQUIRE(p != g_recording, "the program is still being recorded (call mfb_program_end first)");
+    for (auto& op : p->ops) {
+        const int rc = op(stream);
+        if (rc) return rc;
+    }
+    return MFB_OK;
+}
+
+extern "C" int mfb_program_destroy(mfb_program* prog) {
+    Program* p = reinterpret_cast<Program*>(prog);
+    if (p && p == g_recording) g_recording = nullptr;
+    delete p;
+    return MFB_OK;
+}
+
+extern "C" int mfb_copy_f32(float* dst, const float* src, long long n, void* stream) {
+    MFB_RECORD(mfb_copy_f32(dst, src, n, stream));
+    MFB_REQUIRE(dst && src && n > 0, "bad arguments");
+    long long blocks = (n + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    copy32_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(dst, src, n);
+    MFB_CUDA_OK(cudaGetLastError());
     return MFB_OK;
 }

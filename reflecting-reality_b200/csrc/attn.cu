@@ -497,6 +497,7 @@ static int attention_impl(const void* q, int ldq, const void* k, int ldk, const 
 
 extern "C" int mfb_attention(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* out, int ldo, int B, int heads,
                              int head_dim, int Tq, int Tk, void* stream) {
+    MFB_RECORD(mfb_attention(q, ldq, k, ldk, v, ldv, out, ldo, B, heads, head_dim, Tq, Tk, stream));
     return attention_impl(q, ldq, k, ldk, v, ldv, out, ldo, B, heads, head_dim, Tq, Tk, nullptr, stream);
 }
 

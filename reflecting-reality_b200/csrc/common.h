@@ -6,7 +6,24 @@
 
 #include "../../include/mfb200.h"
 
+#include <functional>
+#include <vector>
+
 namespace mfb {
+
+// A recorded launch program (mfb_program_* in mfb200.h): while a recorder is active on the calling thread, every step-level entry
+// point appends a closure of itself — its arguments by value, the stream left open — before executing; mfb_program_run replays the
+// closures in order on the stream it is given.  Buffers and plans referenced by the recorded calls must outlive the program (the
+// engines allocate everything once per geometry, which is what CUDA-graph capture needs as well).
+struct Program {
+    std::vector<std::function<int(void*)>> ops;
+};
+Program* recording();
+#define MFB_RECORD(...)                                                                                   \
+    do {                                                                                                  \
+        if (::mfb::Program* _rec = ::mfb::recording())                                                    \
+            _rec->ops.emplace_back([=](void* stream) -> int { return __VA_ARGS__; });                    \
+    } while (0)
 
 void set_error(const char* fmt, ...);
 int device_sm_count();

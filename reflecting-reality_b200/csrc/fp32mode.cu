@@ -366,6 +366,7 @@ using namespace mfb;
 
 extern "C" int mfb_groupnorm_f32(const float* x1, int C1, const float* x2, int C2, int B, int HW, int groups, float eps,
                                  const float* gamma, const float* beta, int silu, float* out, void* stream) {
+    MFB_RECORD(mfb_groupnorm_f32(x1, C1, x2, C2, B, HW, groups, eps, gamma, beta, silu, out, stream));
     MFB_REQUIRE(x1 && gamma && beta && out, "null pointer");
     MFB_REQUIRE((C1 + C2) % groups == 0 && (x2 != nullptr) == (C2 > 0), "bad channel split");
     gn32_kernel<<<dim3(groups, B), 256, 0, static_cast<cudaStream_t>(stream)>>>(x1, C1, x2, C2, HW, groups, eps, gamma, beta, silu, out);
@@ -375,6 +376,7 @@ extern "C" int mfb_groupnorm_f32(const float* x1, int C1, const float* x2, int C
 
 extern "C" int mfb_layernorm_f32(const float* x, int rows, int C, float eps, const float* gamma, const float* beta, float* out,
                                  void* stream) {
+    MFB_RECORD(mfb_layernorm_f32(x, rows, C, eps, gamma, beta, out, stream));
     MFB_REQUIRE(x && gamma && beta && out, "null pointer");
     ln32_kernel<<<(rows + 7) / 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, rows, C, eps, gamma, beta, out);
     MFB_CUDA_OK(cudaGetLastError());
@@ -383,6 +385,7 @@ extern "C" int mfb_layernorm_f32(const float* x, int rows, int C, float eps, con
 
 extern "C" int mfb_attention_f32(const float* q, int ldq, const float* k, int ldk, const float* v, int ldv, float* out, int ldo,
                                  int B, int heads, int head_dim, int Tq, int Tk, void* stream) {
+    MFB_RECORD(mfb_attention_f32(q, ldq, k, ldk, v, ldv, out, ldo, B, heads, head_dim, Tq, Tk, stream));
     MFB_REQUIRE(q && k && v && out, "null pointer");
     MFB_REQUIRE(head_dim > 0 && head_dim <= A32_MAXD && Tq > 0 && Tk > 0, "unsupported attention shape");
     attn32_kernel<<<dim3((Tq + 3) / 4, heads, B), 128, 0, static_cast<cudaStream_t>(stream)>>>(
@@ -393,6 +396,7 @@ extern "C" int mfb_attention_f32(const float* q, int ldq, const float* k, int ld
 
 extern "C" int mfb_conv_in_f32(const float* sample, int Ca, const float* cond, int Cb, int B, int H, int W, const float* w,
                                const float* bias, int Cout, float* out, const float* tap, float* out_post, void* stream) {
+    MFB_RECORD(mfb_conv_in_f32(sample, Ca, cond, Cb, B, H, W, w, bias, Cout, out, tap, out_post, stream));
     MFB_REQUIRE(sample && w && bias && out && (cond != nullptr) == (Cb > 0) && (tap == nullptr || out_post != nullptr), "bad arguments");
     const size_t total = static_cast<size_t>(B) * H * W * Cout;
     conv_in32_kernel<<<unsigned((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(sample, Ca, cond, Cb, B, H, W, w, bias,
@@ -403,6 +407,7 @@ extern "C" int mfb_conv_in_f32(const float* sample, int Ca, const float* cond, i
 
 extern "C" int mfb_conv_out_f32(const float* x, int Cin, int B, int H, int W, const float* w, const float* bias, int Cout, float* out,
                                 void* stream) {
+    MFB_RECORD(mfb_conv_out_f32(x, Cin, B, H, W, w, bias, Cout, out, stream));
     MFB_REQUIRE(x && w && bias && out, "null pointer");
     const size_t warps = static_cast<size_t>(B) * Cout * H * W;
     conv_out32_kernel<<<unsigned((warps * 32 + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, Cin, B, H, W, w, bias, Cout, out);
@@ -412,6 +417,7 @@ extern "C" int mfb_conv_out_f32(const float* x, int Cin, int B, int H, int W, co
 
 extern "C" int mfb_linear_small_f32(const float* x, int M, int K, const float* w, const float* b, int N, int act_in, int act_out,
                                     float* y, void* stream) {
+    MFB_RECORD(mfb_linear_small_f32(x, M, K, w, b, N, act_in, act_out, y, stream));
     MFB_REQUIRE(x && w && y, "null pointer");
     linear_small32_kernel<<<(N * 32 + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, M, K, w, b, N, act_in, act_out, y);
     MFB_CUDA_OK(cudaGetLastError());

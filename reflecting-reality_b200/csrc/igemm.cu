@@ -927,6 +927,7 @@ static int run_one(const Plan& pl, const IgemmParams& prm, cudaStream_t st) {
 }
 
 extern "C" int mfb_plan_run(mfb_plan* plan, void* stream) {
+    MFB_RECORD(mfb_plan_run(plan, stream));
     MFB_REQUIRE(plan, "null plan");
     Plan* pl = reinterpret_cast<Plan*>(plan);
     cudaStream_t st = static_cast<cudaStream_t>(stream);

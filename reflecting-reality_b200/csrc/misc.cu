@@ -381,6 +381,7 @@ static inline int grid_for(long long n, int block, int cap = 148 * 8) {
 
 extern "C" int mfb_conv_in(const float* sample, int Ca, const float* cond, int Cb, int B, int H, int W, const float* w,
                            const float* bias, int Cout, void* out, const void* tap, void* out_post, void* stream) {
+    MFB_RECORD(mfb_conv_in(sample, Ca, cond, Cb, B, H, W, w, bias, Cout, out, tap, out_post, stream));
     MFB_REQUIRE(sample && w && bias && out, "null pointer");
     if (!cond) Cb = 0;
     MFB_REQUIRE(Cout % 8 == 0, "Cout must be a multiple of 8");
@@ -399,6 +400,7 @@ extern "C" int mfb_conv_in(const float* sample, int Ca, const float* cond, int C
 
 extern "C" int mfb_conv_out(const void* x, int Cin, int B, int H, int W, const float* w, const float* bias, int Cout,
                             float* out, void* stream) {
+    MFB_RECORD(mfb_conv_out(x, Cin, B, H, W, w, bias, Cout, out, stream));
     MFB_REQUIRE(x && w && bias && out, "null pointer");
     MFB_REQUIRE(Cout >= 1 && Cout <= 4 && Cin % 8 == 0, "conv_out supports Cout <= 4, Cin %% 8 == 0");
     const size_t smem = static_cast<size_t>(9) * ((Cin / 8 + 7) / 8) * 64 * sizeof(float4);
@@ -418,6 +420,7 @@ extern "C" int mfb_conv_out(const void* x, int Cin, int B, int H, int W, const f
 }
 
 extern "C" int mfb_upsample2x(const void* x, int B, int H, int W, int C, void* out, void* stream) {
+    MFB_RECORD(mfb_upsample2x(x, B, H, W, C, out, stream));
     MFB_REQUIRE(x && out && C % 8 == 0, "bad arguments");
     const long long total = static_cast<long long>(B) * 4 * H * W * (C / 8);
     upsample2x_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
@@ -427,6 +430,7 @@ extern "C" int mfb_upsample2x(const void* x, int B, int H, int W, int C, void* o
 }
 
 extern "C" int mfb_nchw_f32_to_nhwc_bf16(const float* x, int B, int C, int H, int W, void* out, void* stream) {
+    MFB_RECORD(mfb_nchw_f32_to_nhwc_bf16(x, B, C, H, W, out, stream));
     MFB_REQUIRE(x && out, "null pointer");
     dim3 grid((H * W + 31) / 32, (C + 31) / 32, B), block(32, 8);
     nchw_to_nhwc_kernel<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(x, C, H * W, static_cast<__nv_bfloat16*>(out));
@@ -435,6 +439,7 @@ extern "C" int mfb_nchw_f32_to_nhwc_bf16(const float* x, int B, int C, int H, in
 }
 
 extern "C" int mfb_nhwc_bf16_to_nchw_f32(const void* x, int B, int C, int H, int W, float* out, void* stream) {
+    MFB_RECORD(mfb_nhwc_bf16_to_nchw_f32(x, B, C, H, W, out, stream));
     MFB_REQUIRE(x && out, "null pointer");
     dim3 grid((H * W + 31) / 32, (C + 31) / 32, B), block(32, 8);
     nhwc_to_nchw_kernel<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const __nv_bfloat16*>(x), C, H * W, out);
@@ -443,6 +448,7 @@ extern "C" int mfb_nhwc_bf16_to_nchw_f32(const void* x, int B, int C, int H, int
 }
 
 extern "C" int mfb_f32_to_bf16(const float* x, long long n, void* out, void* stream) {
+    MFB_RECORD(mfb_f32_to_bf16(x, n, out, stream));
     MFB_REQUIRE(x && out, "null pointer");
     f32_to_bf16_kernel<<<grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, n, static_cast<__nv_bfloat16*>(out));
     MFB_CUDA_OK(cudaGetLastError());
@@ -450,6 +456,7 @@ extern "C" int mfb_f32_to_bf16(const float* x, long long n, void* out, void* str
 }
 
 extern "C" int mfb_transpose_tokens(const void* x, int ld, int col0, int C, int B, int T, void* out, int ldt, void* stream) {
+    MFB_RECORD(mfb_transpose_tokens(x, ld, col0, C, B, T, out, ldt, stream));
     MFB_REQUIRE(x && out && ldt >= T, "bad arguments");
     MFB_REQUIRE(ld % 8 == 0 && col0 % 8 == 0 && C % 8 == 0 && ldt % 8 == 0, "transpose_tokens needs ld, col0, C, ldt to be multiples of 8");
     dim3 grid((ldt + 63) / 64, (C + 63) / 64, B), block(256);
@@ -459,6 +466,7 @@ extern "C" int mfb_transpose_tokens(const void* x, int ld, int col0, int C, int 
 }
 
 extern "C" int mfb_timestep_sinusoid(const float* t, int M, int dim, float* out, void* stream) {
+    MFB_RECORD(mfb_timestep_sinusoid(t, M, dim, out, stream));
     MFB_REQUIRE(t && out && dim % 2 == 0, "bad arguments");
     const int n = M * dim / 2;
     sinusoid_kernel<<<(n + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(t, M, dim, out);
@@ -468,6 +476,7 @@ extern "C" int mfb_timestep_sinusoid(const float* t, int M, int dim, float* out,
 
 extern "C" int mfb_linear_small(const float* x, int M, int K, const void* w, const float* b, int N, int act_in, int act_out,
                                 float* y, void* stream) {
+    MFB_RECORD(mfb_linear_small(x, M, K, w, b, N, act_in, act_out, y, stream));
     MFB_REQUIRE(x && w && y && K % 8 == 0 && K <= 4096, "linear_small needs K %% 8 == 0 and K <= 4096");
     const size_t smem = static_cast<size_t>(8) * K * sizeof(float);
     static bool configured = false;
@@ -676,6 +685,7 @@ __global__ void latent_sample_kernel(const float* __restrict__ mean, const float
 
 extern "C" int mfb_latent_sample(const float* mean, const float* logvar, const float* noise, float scale, float* out, long long n,
                                  void* stream) {
+    MFB_RECORD(mfb_latent_sample(mean, logvar, noise, scale, out, n, stream));
     MFB_REQUIRE(mean && out && (noise == nullptr || logvar != nullptr) && n > 0, "bad arguments");
     MFB_CUDA_OK(launch_k(latent_sample_kernel, dim3(static_cast<unsigned>((n + 255) / 256)), dim3(256), 0,
                          static_cast<cudaStream_t>(stream), 1, mean, logvar, noise, scale, out, n));
@@ -684,6 +694,7 @@ extern "C" int mfb_latent_sample(const float* mean, const float* logvar, const f
 
 extern "C" int mfb_cfg_sched_step(const float* eps_uncond, const float* eps_cond, float* x, float* last, float* m0, float* m1,
                                   const float* coef, int Bimg, long long n, void* stream) {
+    MFB_RECORD(mfb_cfg_sched_step(eps_uncond, eps_cond, x, last, m0, m1, coef, Bimg, n, stream));
     MFB_REQUIRE(eps_uncond && eps_cond && x && last && m0 && m1 && coef, "null pointer");
     const long long total = static_cast<long long>(Bimg) * n;
     MFB_CUDA_OK(launch_k(cfg_sched_kernel, dim3(grid_for(total, 256)), dim3(256), 0, static_cast<cudaStream_t>(stream), 1,

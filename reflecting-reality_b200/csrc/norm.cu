@@ -615,12 +615,14 @@ extern "C" int mfb_groupnorm_stats(const void* x1, int C1, const void* x2, int C
 
 extern "C" int mfb_groupnorm(const void* x1, int C1, const void* x2, int C2, int B, int HW, int groups, float eps,
                              const float* gamma, const float* beta, int silu, float* stats_ws, void* out, void* stream) {
+    MFB_RECORD(mfb_groupnorm(x1, C1, x2, C2, B, HW, groups, eps, gamma, beta, silu, stats_ws, out, stream));
     return groupnorm_impl(x1, C1, x2, C2, B, HW, groups, eps, gamma, beta, silu, stats_ws, out, stream, nullptr, 0, nullptr, 0);
 }
 
 extern "C" int mfb_groupnorm_prestat(const void* x1, int C1, const float* part1, int tiles1, const void* x2, int C2,
                                      const float* part2, int tiles2, int B, int HW, int groups, float eps, const float* gamma,
                                      const float* beta, int silu, float* stats_ws, void* out, void* stream) {
+    MFB_RECORD(mfb_groupnorm_prestat(x1, C1, part1, tiles1, x2, C2, part2, tiles2, B, HW, groups, eps, gamma, beta, silu, stats_ws, out, stream));
     MFB_REQUIRE(part1 && tiles1 > 0 && (!x2 || (part2 && tiles2 > 0)), "mfb_groupnorm_prestat needs the partial statistics of every source");
     MFB_REQUIRE(groups <= 64, "at most 64 groups");
     return groupnorm_impl(x1, C1, x2, C2, B, HW, groups, eps, gamma, beta, silu, stats_ws, out, stream, part1, tiles1, part2, tiles2);
@@ -678,6 +680,7 @@ __global__ void __launch_bounds__(256) softmax_rows_kernel(const __nv_bfloat16* 
 }  // namespace mfb
 
 extern "C" int mfb_softmax_rows(const void* x, int rows, int cols, void* out, void* stream) {
+    MFB_RECORD(mfb_softmax_rows(x, rows, cols, out, stream));
     MFB_REQUIRE(x && out && rows > 0, "null pointer");
     MFB_REQUIRE(cols > 0 && cols % 8 == 0, "cols must be a positive multiple of 8 (got %d)", cols);
     MFB_CUDA_OK(launch_k(softmax_rows_kernel, dim3(rows), dim3(256), 0, static_cast<cudaStream_t>(stream), 1,
@@ -687,6 +690,7 @@ extern "C" int mfb_softmax_rows(const void* x, int rows, int cols, void* out, vo
 
 extern "C" int mfb_layernorm(const void* x, int rows, int C, float eps, const float* gamma, const float* beta, void* out,
                              void* stream) {
+    MFB_RECORD(mfb_layernorm(x, rows, C, eps, gamma, beta, out, stream));
     MFB_REQUIRE(x && out && gamma && beta, "null pointer");
     MFB_REQUIRE(C % 8 == 0 && C <= 2048, "C must be a multiple of 8 and <= 2048 (got %d)", C);
     cudaStream_t st = static_cast<cudaStream_t>(stream);

@@ -31,6 +31,12 @@ _SIGS = {
     "mfb_abi_version": (i32, []),
     "mfb_init": (i32, [i32]),
     "mfb_last_error": (C.c_char_p, []),
+    "mfb_program_begin": (i32, [C.POINTER(vp)]),
+    "mfb_program_end": (i32, []),
+    "mfb_program_size": (i32, [vp]),
+    "mfb_program_run": (i32, [vp, vp]),
+    "mfb_program_destroy": (i32, [vp]),
+    "mfb_copy_f32": (i32, [vp, vp, i64, vp]),
     "mfb_conv_plan_create": (i32, [C.POINTER(ConvDesc), C.POINTER(vp)]),
     "mfb_plan_run": (i32, [vp, vp]),
     "mfb_plan_destroy": (i32, [vp]),

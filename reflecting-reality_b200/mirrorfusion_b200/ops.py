@@ -62,6 +62,46 @@ def _req(t: torch.Tensor, dtype, name: str):
         raise ValueError(f"{name}: expected contiguous CUDA {dtype} tensor, got {t.dtype} {t.device} contiguous={t.is_contiguous()}")
 
 
+# --------------------------------------------------------------------------------------------- recorded launch programs
+class Program:
+    """`with ops.Program() as prog: <launches>` executes the launches and records them inside libmfb200 (mfb_program_begin / _end);
+    `prog.run()` replays the whole sequence from one C call — no Python between the kernels."""
+
+    def __init__(self):
+        self._L = lib()
+        self._h = C.c_void_p()
+
+    def __enter__(self):
+        check(self._L.mfb_program_begin(C.byref(self._h)))
+        return self
+
+    def __exit__(self, *exc):
+        check(self._L.mfb_program_end())
+        return False
+
+    def __len__(self):
+        return int(self._L.mfb_program_size(self._h))
+
+    def run(self):
+        check(self._L.mfb_program_run(self._h, _stream()))
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                self._L.mfb_program_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+
+def copy_f32(dst, src):
+    """dst[:] = src (fp32, contiguous) by a library kernel, so the copy is part of a recorded program."""
+    _req(dst, f32, "dst"); _req(src, f32, "src")
+    if dst.numel() != src.numel():
+        raise ValueError("copy_f32: size mismatch")
+    check(lib().mfb_copy_f32(_ptr(dst), _ptr(src), dst.numel(), _stream()))
+
+
 # --------------------------------------------------------------------------------------------- weight packing
 def pack_conv_weight(w: torch.Tensor, extras: Sequence[torch.Tensor] = ()) -> torch.Tensor:
     """OIHW conv weight (or [out,in] linear weight) -> [Cout, kh*kw*Cin (+ extra 1x1 segments)] bf16,

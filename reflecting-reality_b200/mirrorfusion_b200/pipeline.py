@@ -13,6 +13,8 @@ VAE / CLIP / image preprocessing stay outside: the pipeline tak
 """
 from __future__ import annotations
 
+import os
+
 import inspect
 from types import SimpleNamespace
 from typing import Any, Callable, Dict, List, Optional, Tuple, Union
@@ -315,6 +317,10 @@ class StepEngine:
         self.coef = torch.zeros(12, device=self.dev, dtype=f32)
         self.use_graph = use_graph
         self.graph: Optional[torch.cuda.CUDAGraph] = None
+        # eager mode (use_graph=False): replay the step as a program recorded inside the library (ops.Program) instead of walking
+        # the Python launch list; MFB_NATIVE_PROGRAM=0 keeps the Python loop (A/B, debugging)
+        self.native_program = os.environ.get("MFB_NATIVE_PROGRAM", "1") == "1"
+        self._program: Optional[ops.Program] = None
         self.launches_per_step = self.unet.launches + self.bn.launches + 1
         self.flops_per_step = self.unet.flops + self.bn.flops
 
@@ -334,9 +340,9 @@ class StepEngine:
     def _enqueue(self):
         n = self.images
         for e in (self.bn, self.unet):                    # latent_model_input = cat([latents] * 2) (:1256)
-            e.sample_in[:n].copy_(self.x)
-            if e.sample_in.shape[0] > n:                  # (the de-duplicated BrushNet sees each latent once)
-                e.sample_in[n:].copy_(self.x)
+            ops.copy_f32(e.sample_in[:n], self.x)         # (a library kernel: part of the recorded program / graph)
+            if e.sample_in.shape[0] > n:                  # (the de-duplicated / guess-mode BrushNet sees each latent once)
+                ops.copy_f32(e.sample_in[n:], self.x)
         skip = 0 if self.time_tables is None else None    # hoisted timestep path: row biases were copied in by step()
         if self.two_streams:
             self._run_two_streams(skip)
@@ -358,6 +364,7 @@ class StepEngine:
         ts = [float(t) for t in timesteps]
         self.time_tables = ({t: i for i, t in enumerate(ts)}, self.bn.timestep_table(ts), self.unet.timestep_table(ts))
         self.launches_per_step = self.unet.launches + self.bn.launches + 1 - 8
+        self._program = None          # a recorded program that still holds the timestep ops is re-recorded at the next step
 
     def _run_two_streams(self, skip):
         """BrushNet on a side stream, UNet on the current one.  The UNet entry that consumes BrushNet tensor k (a fused
@@ -402,6 +409,16 @@ class StepEngine:
             self._tap_scale = float(scale)
         self.coef.copy_(coef_row, non_blocking=True)
         if not self.use_graph:
+            if self.native_program and not (self.two_streams or self.dedup):
+                # the whole step from ONE C call: the launch sequence is recorded inside libmfb200 the first time it runs
+                # (mfb_program_begin / _end) and replayed by mfb_program_run afterwards — no Python between the 512 launches
+                if self._program is None:
+                    with ops.Program() as prog:
+                        self._enqueue()
+                    self._program = prog
+                else:
+                    self._program.run()
+                return
             self._enqueue()
             return
         if self.graph is None:

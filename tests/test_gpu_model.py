@@ -502,6 +502,29 @@ def test_guess_mode_step_vs_reference_golden(P, golden_dir):
     assert torch.isfinite(a).all() and rel(a, b) > 1e-3 and torch.equal(a, pipe(guess_mode=True, **kw).images)
 
 
+def test_native_program_replay_is_bit_identical(P):
+    """use_graph=False runs the step as a program recorded inside libmfb200 (mfb_program_begin / _end, replayed by ONE
+    mfb_program_run call per step): bit-identical to the Python launch loop and to the CUDA graph, every launch of the step in it."""
+    from mirrorfusion_b200 import ops
+    cfg, n = TINY, 2
+    usd, bsd = make_state_dict(cfg, "unet"), make_state_dict(cfg, "brushnet")
+    inp = make_inputs(cfg, n)
+    outs = {}
+    for mode in ("graph", "native", "python"):
+        eng = P.StepEngine(cfg, usd, bsd, n, cfg.sample_size, cfg.sample_size, use_graph=(mode == "graph"))
+        eng.native_program = mode == "native"
+        eng.set_conditioning(inp["prompt_embeds"], inp["conditioning_latents"])
+        outs[mode] = eng.denoise(inp["latents"], P.B200UniPCScheduler(), 4, 7.5).clone()
+        if mode == "native":
+            assert eng._program is not None
+            nrec = len(eng._program)
+    assert torch.equal(outs["native"], outs["python"]) and torch.equal(outs["native"], outs["graph"])
+    # nothing leaks: a program records only between begin and end
+    with ops.Program() as empty:
+        pass
+    assert len(empty) == 0 and nrec > 100
+
+
 def test_smoke_entry():
     import __graft_entry__ as ge
     ge.smoke()
