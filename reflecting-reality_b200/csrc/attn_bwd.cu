@@ -451,17 +451,21 @@ __global__ void __launch_bounds__(192, BwdCfg<D>::CTAS) attn_bwd_dkv_kernel(cons
         uint8_t* dsrow = gen_base + (dst_smem - base) + r * 128;
         float* ld_gen = reinterpret_cast<float*>(gen_base + (ld_smem - base));
         const size_t sbase = (static_cast<size_t>(b) * p.heads + h) * p.Tq;
+        // per-column L and D of a query tile (threads 0..63: L, 64..127: D); columns past Tq get L = +inf (P = 0).  The value of
+        // tile i+1 is fetched while tile i is being processed, so the global-load latency is off the per-tile critical path.
+        auto fetch_ld = [&](int i) {
+            const int qi = i * BQT + (r & 63);
+            float v = r < 64 ? INFINITY : 0.f;
+            if (i < ntiles && qi < p.Tq) v = __ldg((r < 64 ? p.lse : p.dvec) + sbase + qi);
+            return v;
+        };
+        float ld_next = fetch_ld(0);
         for (int i = 0; i < ntiles; ++i) {
-            // per-column L and D of this query tile -> smem (threads 0..63: L, 64..127: D); columns past Tq get L = +inf (P = 0)
             float* Ls = ld_gen + (i % STAGES) * 128;
-            {
-                const int c = r & 63, qi = i * BQT + c;
-                float v = r < 64 ? INFINITY : 0.f;
-                if (qi < p.Tq) v = __ldg((r < 64 ? p.lse : p.dvec) + sbase + qi);
-                if (STAGES == 1 && i > 0) named_bar_sync(2, 128);      // one buffer: everybody has finished reading tile i-1's values
-                Ls[r] = v;
-            }
+            if (STAGES == 1 && i > 0) named_bar_sync(2, 128);          // one buffer: everybody has finished reading tile i-1's values
+            Ls[r] = ld_next;
             named_bar_sync(1, 128);
+            ld_next = fetch_ld(i + 1);
             mbar_wait_relaxed(s_full, i & 1);
             tc_fence_after();
 #pragma unroll
