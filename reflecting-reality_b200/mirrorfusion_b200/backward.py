@@ -19,6 +19,8 @@ call signatures so that the program's dataflow is checked against the reference'
 never uses it (ops raises without CUDA)."""
 from __future__ import annotations
 
+import os
+
 from typing import Dict, Optional, Tuple
 
 import torch
@@ -88,7 +90,7 @@ class ResnetBlockTrainer:
         # kernel of the small maps keeps its statistics in registers)
         self.gn_ws = torch.zeros(K.gn_ws_floats(B, groups), device=dev, dtype=torch.float32)
         self.gn_ws2 = torch.zeros(K.gn_ws_floats(B, groups), device=dev, dtype=torch.float32)
-        self.keep_stats = self.HW > 64
+        self.keep_stats = self.HW > 64 and os.environ.get("MFB_TRAIN_KEEP_GN_STATS", "1") == "1"      # =0: recompute in the backward (A/B)
         self.gnb_ws = torch.zeros(2 * B * max(Cin, Cout), device=dev, dtype=torch.float32)
         self._wsrc = flat.p if self.dt == torch.float32 else flat.w        # fp32 masters (parity mode) or the bf16 working copy
         # data-gradient weights: the same implicit-GEMM kernel over the incoming gradient with flipped / transposed weights
@@ -545,7 +547,7 @@ class SkipResnetBlockTrainer:
         # kernel of the small maps keeps its statistics in registers)
         self.gn_ws = torch.zeros(K.gn_ws_floats(B, groups), device=dev, dtype=torch.float32)
         self.gn_ws2 = torch.zeros(K.gn_ws_floats(B, groups), device=dev, dtype=torch.float32)
-        self.keep_stats = self.HW > 64
+        self.keep_stats = self.HW > 64 and os.environ.get("MFB_TRAIN_KEEP_GN_STATS", "1") == "1"      # =0: recompute in the backward (A/B)
         self.gnb_ws = torch.zeros(2 * B * max(Cin, Cout), device=dev, dtype=torch.float32)
         self._wsrc = wsrc = flat.p if self.dt == torch.float32 else flat.w
         n = lambda s: f"{prefix}.{s}"

@@ -25,6 +25,8 @@ check the DATAFLOW against float64 autograd of the oracle UNet.  The product pat
 """
 from __future__ import annotations
 
+import os
+
 from typing import Callable, Dict, List, Optional, Tuple
 
 import torch
@@ -177,7 +179,7 @@ class FrozenUNetTrainer:
         Maps up to 8x8 go through the single-launch kernel, which keeps the statistics in registers: their backward recomputes."""
         ws = torch.zeros(self.K.gn_ws_floats(self.B, self.cfg.norm_num_groups), device=self.dev, dtype=f32)
         self.keep.append(ws)
-        return ws, (ws if HW > 64 else None)
+        return ws, (ws if HW > 64 and os.environ.get("MFB_TRAIN_KEEP_GN_STATS", "1") == "1" else None)      # =0: recompute (A/B)
 
     def wa(self, t: torch.Tensor) -> torch.Tensor:
         return t.to(self.act).contiguous()
