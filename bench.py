@@ -398,7 +398,8 @@ def run_ours(args, rank, world, local_rank):
     # value / e2e always run the reference's full 2b-sample BrushNet)
     eng_dd = None
     if args.report_dedup and not args.dedup_brushnet and world == 1:
-        eng_dd = StepEngine(cfg, usd, bsd, images, H, W, dev, use_graph=not args.no_graph, dedup_brushnet_cfg=True)
+        eng_dd = StepEngine(cfg, usd, bsd, images, H, W, dev, use_graph=not args.no_graph, two_streams=args.two_streams,
+                            dedup_brushnet_cfg=True)
     del usd, bsd
     eng.set_conditioning(ehs.to(dev), cond.to(dev))
     sched = B200UniPCScheduler()
@@ -643,7 +644,10 @@ def main():
     ap.add_argument("--latent", type=int, default=64, help="latent side (64 = 512x512 pixels)")
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--no-graph", action="store_true")
-    ap.add_argument("--two-streams", action="store_true", help="BrushNet on a side stream with per-tap events (measured neutral)")
+    ap.add_argument("--two-streams", action=argparse.BooleanOptionalAction, default=True,
+                    help="BrushNet on a side launch stream, the UNet waiting per tap on its events (bit-identical results, "
+                         "tests/test_gpu_model.py::test_two_launch_streams_are_bit_identical; -1.2 ... -1.4 %% per step on a "
+                         "power-capped B200, profiles/r02u_two_streams_ab.md); --no-two-streams = one stream")
     ap.add_argument("--dedup-brushnet", action="store_true",
                     help="run the whole bench with the opt-in BrushNet CFG de-duplication (flagged in config)")
     ap.add_argument("--report-dedup", action=argparse.BooleanOptionalAction, default=True,

@@ -843,7 +843,11 @@ static int build_params(const mfb_conv_desc* d, int up_py, int up_px, const void
             pl->grid = dim3(unsigned(2 * (pairs < maxp ? pairs : maxp)), 1, 1);
         } else {
             const long total = long(p.tiles_m) * p.tiles_nn;
-            pl->grid = dim3(unsigned(total < sms ? total : sms), 1, 1);
+            // A/B knob (MFB_IGEMM_MAX_CTAS): cap the persistent grid so that two launch streams (BrushNet || UNet, StepEngine
+            // two_streams) share the SMs spatially instead of time-slicing them — the tile loop is the same, results bit-identical
+            static const int cap = [] { const char* e = getenv("MFB_IGEMM_MAX_CTAS"); return e ? atoi(e) : 0; }();
+            const long lim = (cap > 0 && cap < sms) ? cap : sms;
+            pl->grid = dim3(unsigned(total < lim ? total : lim), 1, 1);
         }
     }
     return MFB_OK;

@@ -314,7 +314,7 @@ class BrushNetEngine(_Net):
     28 zero-conv taps scaled by conditioning_scale (a device scalar, so the captured graph serves any scale)."""
 
     def __init__(self, cfg, sd, B, H, W, device, tap_bufs: Optional[List[torch.Tensor]] = None,
-                 only_first_tap: bool = False, host_pack: bool = False):
+                 only_first_tap: bool = False, host_pack: bool = False, dup_halves: bool = False):
         """only_first_tap: fused pipeline mode — only the conv_in-site tap is materialised; the other 27 zero-convs
         are handed to the UNet engine as (feature, weight, bias) and run there as K-segments of the consuming GEMM."""
         super().__init__(cfg, sd, B, H, W, device, "brushnet", host_pack=host_pack)
@@ -336,43 +336,33 @@ class BrushNetEngine(_Net):
         x = self.buf(B, H * W, boc[0])
         self.keep += [wci, bci]
         self.emit(lambda x0=x: ops.conv_in(self.sample_in, self.cond_in, wci, bci, x0), out=x)   # bind now: `x` is reassigned below
-        hw = (H, W)
-        feats: List[Tuple[torch.Tensor, Tuple[int, int]]] = [(x, hw)]
-        for i in range(n):
-            for j in range(cfg.layers_per_block):
-                x = self.resnet(f"down_blocks.{i}.resnets.{j}", x, None, hw, boc[i])
-                feats.append((x, hw))
-            if i != n - 1:
-                x = self.downsample(f"down_blocks.{i}.downsamplers.0", x, hw)
-                hw = (hw[0] // 2, hw[1] // 2)
-                feats.append((x, hw))
-        down_feats = list(feats)
-        x = self.resnet("mid_block.resnets.0", x, None, hw, boc[-1])
-        x = self.resnet("mid_block.resnets.1", x, None, hw, boc[-1])
-        mid_feat = (x, hw)
-        up_feats = []
-        skips = list(feats)
-        for i, layers in enumerate(up_block_channels(cfg)):
-            for j, (_cin, _hid, _skip, cout) in enumerate(layers):
-                s, shw = skips.pop()
-                assert shw == hw
-                x = self.resnet(f"up_blocks.{i}.resnets.{j}", x, s, hw, cout)
-                up_feats.append((x, hw))
-            if i != n - 1:
-                x = self.upsample(f"up_blocks.{i}.upsamplers.0", x, hw)
-                hw = (hw[0] * 2, hw[1] * 2)
-                up_feats.append((x, hw))
-        # zero-convs (brushnet.py:831-834,851,890-893) with the conditioning scale (:904-906) as epilogue alpha
-        srcs = down_feats + [mid_feat] + up_feats
-        names = [f"brushnet_down_blocks.{k}" for k in range(len(down_feats))] + ["brushnet_mid_block"] + \
-                [f"brushnet_up_blocks.{k}" for k in range(len(up_feats))]
+        # zero-convs (brushnet.py:831-834,851,890-893) with the conditioning scale (:904-906) as epilogue alpha.  Each one is emitted
+        # RIGHT AFTER the feature it reads: a consumer on another launch stream (the UNet under StepEngine(two_streams=True)) can
+        # then start as soon as its tap exists — emitted at the end of the program, the conv_in-site tap made the UNet's very first
+        # kernel wait for the whole BrushNet, which serialised the two streams completely.
         self.taps: List[torch.Tensor] = []
         self.tap_hw: List[Tuple[int, int]] = []
-        self.tap_sources = [(src, self.sd[nm + ".weight"][:, :, 0, 0].contiguous(), self.sd[nm + ".bias"].contiguous())
-                            for (src, _), nm in zip(srcs, names)]
-        for k, ((src, shw), nm) in enumerate(zip(srcs, names)):
+        self.tap_sources: List[Tuple] = []
+
+        # dup_halves (StepEngine's exact CFG de-duplication): the branch runs on b samples; every feature the UNet consumes (and the
+        # conv_in-site tap) is broadcast to both CFG halves right after it is produced: dup_sources[k] / dup_tap0 are [2b, HW, C]
+        self.dup_sources: List[Tuple] = []
+        self.dup_tap0: Optional[torch.Tensor] = None
+
+        def dup(t):
+            d = torch.empty(2, *t.shape, device=self.dev, dtype=t.dtype)
+            self.keep.append(d)
+            self.emit(lambda s0=t, d0=d: d0.copy_(s0.unsqueeze(0).expand_as(d0)), out=d)
+            return d.view(2 * t.shape[0], *t.shape[1:])
+
+        def tap(src, shw, nm):
+            k = len(self.tap_sources)
+            wz, bz = self.sd[nm + ".weight"][:, :, 0, 0].contiguous(), self.sd[nm + ".bias"].contiguous()
+            self.tap_sources.append((src, wz, bz))
+            if dup_halves:
+                self.dup_sources.append((src if k == 0 else dup(src), wz, bz))
             if only_first_tap and k > 0:
-                break
+                return
             c = src.shape[-1]
             t = tap_bufs[k] if tap_bufs is not None else self.buf(B, shw[0] * shw[1], c)
             wz = self.D(ops.pack_conv_weight(self.sd[nm + ".weight"]))
@@ -380,8 +370,42 @@ class BrushNetEngine(_Net):
                                         bias=self.wf(nm + ".bias"), alpha=self.scales[k:k + 1]), out=t)
             self.taps.append(t)
             self.tap_hw.append(shw)
+            if dup_halves and k == 0:
+                self.dup_tap0 = dup(t)
+
+        hw = (H, W)
+        feats: List[Tuple[torch.Tensor, Tuple[int, int]]] = [(x, hw)]
+        tap(x, hw, "brushnet_down_blocks.0")
+        for i in range(n):
+            for j in range(cfg.layers_per_block):
+                x = self.resnet(f"down_blocks.{i}.resnets.{j}", x, None, hw, boc[i])
+                feats.append((x, hw))
+                tap(x, hw, f"brushnet_down_blocks.{len(feats) - 1}")
+            if i != n - 1:
+                x = self.downsample(f"down_blocks.{i}.downsamplers.0", x, hw)
+                hw = (hw[0] // 2, hw[1] // 2)
+                feats.append((x, hw))
+                tap(x, hw, f"brushnet_down_blocks.{len(feats) - 1}")
+        down_feats = list(feats)
+        x = self.resnet("mid_block.resnets.0", x, None, hw, boc[-1])
+        x = self.resnet("mid_block.resnets.1", x, None, hw, boc[-1])
+        tap(x, hw, "brushnet_mid_block")
+        n_up = 0
+        skips = list(feats)
+        for i, layers in enumerate(up_block_channels(cfg)):
+            for j, (_cin, _hid, _skip, cout) in enumerate(layers):
+                s, shw = skips.pop()
+                assert shw == hw
+                x = self.resnet(f"up_blocks.{i}.resnets.{j}", x, s, hw, cout)
+                tap(x, hw, f"brushnet_up_blocks.{n_up}")
+                n_up += 1
+            if i != n - 1:
+                x = self.upsample(f"up_blocks.{i}.upsamplers.0", x, hw)
+                hw = (hw[0] * 2, hw[1] * 2)
+                tap(x, hw, f"brushnet_up_blocks.{n_up}")
+                n_up += 1
         self.n_down = len(down_feats)
-        assert len(srcs) == ntap
+        assert len(self.tap_sources) == ntap
 
     def set_scale(self, conditioning_scale: float, guess_mode: bool = False):
         """conditioning_scale for every tap; guess_mode: times torch.logspace(-1, 0, 28) (0.1 ... 1.0 from the first down tap to the

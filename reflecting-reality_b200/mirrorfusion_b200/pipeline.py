@@ -284,22 +284,8 @@ class StepEngine:
             self.unet = UNetEngine(cfg, unet_sd, B, H, W, self.dev, host_pack=hp)
             self.bn = BrushNetEngine(cfg, brushnet_sd, images, H, W, self.dev, tap_bufs=[t[images:] for t in self.unet.taps], host_pack=hp)
         elif self.dedup:
-            self.bn = BrushNetEngine(cfg, brushnet_sd, images, H, W, self.dev, only_first_tap=True, host_pack=hp)
-            dup = lambda t: torch.empty(2, *t.shape, device=self.dev, dtype=t.dtype)
-            both = []
-            for k, (src, wz, bz) in enumerate(self.bn.tap_sources):
-                if k == 0:                                   # the conv_in-site tap is consumed as a tensor (tap0)
-                    both.append((src, wz, bz))
-                    continue
-                d = dup(src)
-                self.bn.emit(lambda s0=src, d0=d: d0.copy_(s0.unsqueeze(0).expand_as(d0)), out=d)
-                both.append((d.view(2 * src.shape[0], *src.shape[1:]), wz, bz))
-            t0 = self.bn.taps[0]
-            d0 = dup(t0)
-            self.bn.emit(lambda s0=t0, d1=d0: d1.copy_(s0.unsqueeze(0).expand_as(d1)), out=d0)
-            self._dup_keep = [d0] + [b[0] for b in both]
-            self.unet = UNetEngine(cfg, unet_sd, B, H, W, self.dev, tap_sources=both,
-                                   tap0=d0.view(2 * t0.shape[0], *t0.shape[1:]), host_pack=hp)
+            self.bn = BrushNetEngine(cfg, brushnet_sd, images, H, W, self.dev, only_first_tap=True, host_pack=hp, dup_halves=True)
+            self.unet = UNetEngine(cfg, unet_sd, B, H, W, self.dev, tap_sources=self.bn.dup_sources, tap0=self.bn.dup_tap0, host_pack=hp)
         elif fuse_taps:
             # 27 of the 28 zero-convs run inside the UNet GEMM that consumes the tap (extra K-segment); only the
             # conv_in-site tap is a tensor

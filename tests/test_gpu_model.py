@@ -525,6 +525,27 @@ def test_native_program_replay_is_bit_identical(P):
     assert len(empty) == 0 and nrec > 100
 
 
+@pytest.mark.parametrize("graph", [False, True])
+@pytest.mark.parametrize("mode", ["fused", "unfused", "dedup"])
+def test_two_launch_streams_are_bit_identical(P, graph, mode):
+    """StepEngine(two_streams=True): BrushNet on a side stream, the UNet waiting per tap on the event of the BrushNet entry that writes
+    what it reads (every zero-conv is emitted right after its feature, so the UNet starts as soon as the conv_in-site tap exists).
+    Same kernels, same order per net: the latents must equal the single-stream run bit for bit, eagerly and as a captured graph."""
+    cfg, n = TINY, 2
+    usd, bsd = make_state_dict(cfg, "unet"), make_state_dict(cfg, "brushnet")
+    inp = make_inputs(cfg, n)
+    kw = dict(use_graph=graph, fuse_taps=(mode != "unfused"), dedup_brushnet_cfg=(mode == "dedup"))
+    outs = []
+    for two in (False, True):
+        eng = P.StepEngine(cfg, usd, bsd, n, cfg.sample_size, cfg.sample_size, two_streams=two, **kw)
+        eng.set_conditioning(inp["prompt_embeds"], inp["conditioning_latents"])
+        outs.append(eng.denoise(inp["latents"], P.B200UniPCScheduler(), 4, 7.5).clone())
+        if two:      # the UNet's first BrushNet dependency is the conv_in-site tap, written by the BrushNet's second main-path entry
+            first = min(eng.bn.writer_pos[p] for ptrs in eng.unet.ext_reads.values() for p in ptrs if p in eng.bn.writer_pos)
+            assert first <= eng.bn.n_time_ops + 2          # conv_in, its zero-conv (, the de-duplication broadcast)
+    assert torch.equal(outs[0], outs[1])
+
+
 def test_smoke_entry():
     import __graft_entry__ as ge
     ge.smoke()
