@@ -515,8 +515,9 @@ class MirrorFusionB200Pipeline:
     def engine(self, images, H, W, guess_mode: bool = False) -> StepEngine:
         key = (images, H, W) + (("guess",) if guess_mode else ())
         if key not in self._engines:
+            # BrushNet on a second launch stream (bit-identical, fills the bubbles at kernel transitions): not with guess mode
             self._engines[key] = StepEngine(self.cfg, self.unet_sd, self.brushnet_sd, images, H, W, self.device,
-                                            precision=self.precision, guess_mode=guess_mode)
+                                            precision=self.precision, guess_mode=guess_mode, two_streams=not guess_mode)
         return self._engines[key]
 
     def check_inputs(self, prompt_embeds, negative_prompt_embeds, brushnet_conditioning_scale, control_guidance_start,

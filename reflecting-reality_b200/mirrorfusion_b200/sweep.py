@@ -57,7 +57,7 @@ class EvalSweep:
         with ops.precision(precision):
             self.enc = VaeEncoderEngine(vae_cfg, vae_sd, n, H, W, self.dev)
             self.dec = VaeDecoderEngine(vae_cfg, vae_sd, n, self.h, self.w, self.dev)
-        self.eng = StepEngine(cfg, unet_sd, brushnet_sd, n, self.h, self.w, self.dev, precision=precision)
+        self.eng = StepEngine(cfg, unet_sd, brushnet_sd, n, self.h, self.w, self.dev, precision=precision, two_streams=True)
         z = lambda *s, dt=f32: torch.zeros(*s, device=self.dev, dtype=dt)
         self.rgb_d, self.mask_d, self.depth_d = z(n, H, W, 3, dt=torch.uint8), z(n, H, W, dt=torch.uint8), z(n, H, W)
         self.img = z(n, 3, H, W)
