@@ -553,6 +553,25 @@ def run_ours(args, rank, world, local_rank):
                 gbs = mb * 2 * images / (fam[famname][0] * 1e-3) / 1e9
                 roofline[famname + "_hbm"] = {"algorithmic_gb_per_step": mb * 2 * images / 1e9, "achieved_gbs": gbs,
                                               "frac_of_hbm_peak": gbs / peaks["hbm_gbs"]}
+    # attention against ITS bound, the exponential unit: one ex2 per (query, key, head), 16 ex2 / clk / SM
+    if "attention" in fam:
+        n_ex2 = 0.0
+        hw_l, boc = H * W, cfg.block_out_channels
+        for i, has in enumerate(cfg.down_has_attn):                      # transformer census: down (layers_per_block each), mid, up (+1 each)
+            T = hw_l // (4 ** i)
+            if has:
+                n_ex2 += cfg.layers_per_block * (T * T + T * 77)
+        n_ex2 += (hw_l // (4 ** (len(boc) - 1))) * ((hw_l // (4 ** (len(boc) - 1))) + 77)
+        for i, has in enumerate(cfg.up_has_attn):
+            T = hw_l // (4 ** (len(boc) - 1 - i))
+            if has:
+                n_ex2 += (cfg.layers_per_block + 1) * (T * T + T * 77)
+        n_ex2 *= 2 * images * cfg.heads
+        mhz = clocks.get("sm_mhz") or 1700.0
+        mufu_peak = 16.0 * (device_sms := torch.cuda.get_device_properties(dev).multi_processor_count) * mhz * 1e6
+        roofline["attention_mufu"] = {"ex2_per_step": n_ex2, "achieved_ex2_per_s": n_ex2 / (fam["attention"][0] * 1e-3),
+                                      "peak_ex2_per_s": mufu_peak, "frac": n_ex2 / (fam["attention"][0] * 1e-3) / mufu_peak,
+                                      "note": f"16 ex2 / clk / SM x {device_sms} SMs at the SM clock sampled under load ({mhz:.0f} MHz)"}
     # ---------------- VAE decode of the final latents on the same kernels: secondary key, never part
     # of `value` / `e2e` (BASELINE's metric is quoted on the denoise loop; this shows the tail the decode adds per batch)
     vae_line = None
