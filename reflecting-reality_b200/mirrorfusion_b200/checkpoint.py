@@ -1,4 +1,4 @@
-"""Checkpoint import without instantiating torch modules.
+"""Checkpoint import / export without instantiating torch modules.
 
 The reference stores each network as a diffusers model directory — `config.json` + `diffusion_pytorch_model.safetensors`
 (`ModelMixin.save_pretrained`, S/models/modeling_utils.py:303-391) — and the fine-tuning script writes
@@ -113,3 +113,38 @@ def load_mirrorfusion(unet_dir: str, brushnet_dir: str):
     import dataclasses
     cfg = dataclasses.replace(ucfg, conditioning_channels=bcfg.conditioning_channels)
     return cfg, usd, bsd
+
+
+# ---------------------------------------------------------------------------------------------------------------- export
+def brushnet_config_json(cfg: NetConfig) -> dict:
+    """The `config.json` `BrushNetModel.save_pretrained` writes for the MirrorFusion branch (S/models/brushnet.py:138-214 constructor
+    arguments as registered by `register_to_config`; values of the architecture-independent keys as `BrushNetModel.from_unet` sets
+    them, :466-500) — what `BrushNetModel.from_pretrained(dir)` needs to rebuild the module the state_dict belongs to."""
+    n = len(cfg.block_out_channels)
+    return {
+        "_class_name": "BrushNetModel", "_diffusers_version": "0.27.0.dev0", "act_fn": "silu", "addition_embed_type": None,
+        "addition_embed_type_num_heads": 64, "addition_time_embed_dim": None, "attention_head_dim": cfg.heads,
+        "block_out_channels": list(cfg.block_out_channels), "brushnet_conditioning_channel_order": "rgb", "class_embed_type": None,
+        "conditioning_channels": cfg.conditioning_channels, "conditioning_embedding_out_channels": [16, 32, 96, 256],
+        "cross_attention_dim": cfg.cross_attention_dim, "down_block_types": ["DownBlock2D"] * n, "downsample_padding": 1,
+        "encoder_hid_dim": None, "encoder_hid_dim_type": None, "flip_sin_to_cos": True, "freq_shift": 0, "global_pool_conditions": False,
+        "in_channels": cfg.in_channels, "layers_per_block": cfg.layers_per_block, "mid_block_scale_factor": 1, "mid_block_type": "MidBlock2D",
+        "norm_eps": cfg.norm_eps, "norm_num_groups": cfg.norm_num_groups, "num_attention_heads": None, "num_class_embeds": None,
+        "only_cross_attention": False, "projection_class_embeddings_input_dim": None, "resnet_time_scale_shift": "default",
+        "transformer_layers_per_block": 1, "up_block_types": ["UpBlock2D"] * n, "upcast_attention": False, "use_linear_projection": False,
+    }
+
+
+def save_brushnet_dir(path: str, cfg: NetConfig, sd: Dict[str, torch.Tensor]):
+    """Write a trained BrushNet as the diffusers model directory the reference's checkpoint hook writes
+    (`checkpoint-N/brushnet/`: config.json + diffusion_pytorch_model.safetensors, E/train_brushnet_mirror.py:997-1032,
+    S/models/modeling_utils.py:303-391), after the strict census check: `BrushNetModel.from_pretrained(path)` of the reference and
+    `load_model_dir(path, "brushnet")` both read it back."""
+    from safetensors.torch import save_file
+    check_state_dict(sd, cfg, "brushnet")
+    os.makedirs(path, exist_ok=True)
+    with open(os.path.join(path, "config.json"), "w") as f:
+        json.dump(brushnet_config_json(cfg), f, indent=2, sort_keys=True)
+        f.write("\n")
+    save_file({k: v.detach().to("cpu", torch.float32).contiguous() for k, v in sd.items()}, os.path.join(path, WEIGHTS[0]),
+              metadata={"format": "pt"})

@@ -106,6 +106,15 @@ class FineTuneStep:
         """The trained BrushNet in the reference's state_dict naming / layouts (checkpoint hook, :997-1032)."""
         return unpack_brushnet(self.cfg, self.flat)
 
+    def save_checkpoint(self, path: str):
+        """The reference's save hook (:997-1032): `<path>/brushnet/` as a diffusers model directory (readable by the reference's
+        `BrushNetModel.from_pretrained` and by `MirrorFusionB200Pipeline.from_checkpoint`) + the optimizer / lr-scheduler state
+        for a bit-identical resume (`<path>/optimizer.pt`)."""
+        import os
+        from .checkpoint import save_brushnet_dir
+        save_brushnet_dir(os.path.join(path, "brushnet"), self.cfg, self.brushnet_state_dict())
+        torch.save({"optimizer": self.opt.state_dict(), "lr_scheduler": self.lr_sched.state_dict()}, os.path.join(path, "optimizer.pt"))
+
     @property
     def flops_per_step(self) -> float:
         """Algorithmic FLOPs of one step on this rank's batch: forward of both nets + BrushNet backward (data + weight

@@ -65,3 +65,42 @@ def test_errors_are_loud(tmp_path, layout):
         (tmp_path / "empty").mkdir()
         ((tmp_path / "empty") / "config.json").write_text(json.dumps(layout["unet"]["config"]))
         CK.load_model_dir(str(tmp_path / "empty"), "unet")
+
+
+def test_exported_brushnet_directory_loads_in_the_reference(tmp_path):
+    """checkpoint.save_brushnet_dir writes what the reference's checkpoint hook writes (E/train_brushnet_mirror.py:997-1032): the
+    reference's own `BrushNetModel.from_pretrained` rebuilds the module from our config.json and loads our safetensors strictly, and
+    the config.json equals, key for key, the one `save_pretrained` of the reference wrote for the same architecture."""
+    import json
+    import sys
+    from mirrorfusion_b200 import checkpoint as CK
+    from mirrorfusion_b200.config import MICRO
+    from mirrorfusion_b200.synth import make_state_dict
+    sd = make_state_dict(MICRO, "brushnet", seed=3)
+    d = str(tmp_path / "checkpoint-7" / "brushnet")
+    CK.save_brushnet_dir(d, MICRO, sd)
+    assert sorted(os.listdir(d)) == ["config.json", "diffusion_pytorch_model.safetensors"]
+    gold = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "micro_checkpoint_layout.json")))
+    assert json.load(open(os.path.join(d, "config.json"))) == gold["brushnet"]["config"]       # what the reference itself wrote
+    cfg, back = CK.load_model_dir(d, "brushnet")
+    assert all(torch.equal(back[k], sd[k]) for k in sd) and cfg.block_out_channels == MICRO.block_out_channels
+    ref_src = "/root/reference/MirrorFusion/src"
+    if not os.path.isdir(ref_src):
+        return
+    import transformers.utils as tu
+    if not hasattr(tu, "FLAX_WEIGHTS_NAME"):
+        tu.FLAX_WEIGHTS_NAME = "flax_model.msgpack"
+    saved = {k: v for k, v in sys.modules.items() if k == "diffusers" or k.startswith("diffusers.")}
+    for k in saved:
+        del sys.modules[k]
+    sys.path.insert(0, ref_src)
+    try:
+        import diffusers
+        bn = diffusers.BrushNetModel.from_pretrained(d)              # the reference's own loader, strict
+        rsd = bn.state_dict()
+        assert set(rsd) == set(sd) and all(torch.equal(rsd[k], sd[k]) for k in sd)
+    finally:
+        sys.path.remove(ref_src)
+        for k in [k for k in sys.modules if k == "diffusers" or k.startswith("diffusers.")]:
+            del sys.modules[k]
+        sys.modules.update(saved)

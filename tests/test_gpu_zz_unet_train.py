@@ -89,7 +89,7 @@ def nhwc_inv(t, like):
 
 @pytest.mark.timeout(600)
 @pytest.mark.parametrize("precision", ["bf16", "fp32"])
-def test_fine_tune_step_every_brushnet_gradient_and_one_adamw_step_vs_autograd(precision):
+def test_fine_tune_step_every_brushnet_gradient_and_one_adamw_step_vs_autograd(precision, tmp_path):
     from mirrorfusion_b200 import checkpoint as CK
     from mirrorfusion_b200.backward import unpack_conv_grad
     from mirrorfusion_b200.finetune import FineTuneStep
@@ -153,6 +153,12 @@ def test_fine_tune_step_every_brushnet_gradient_and_one_adamw_step_vs_autograd(p
     assert ft.flat.grad.abs().max().item() == 0.0
     out = ft.brushnet_state_dict()
     CK.check_state_dict(out, cfg, "brushnet")
+    # the save hook (:997-1032): checkpoint-N/brushnet as a diffusers model directory + optimizer state, read back exactly
+    ft.save_checkpoint(str(tmp_path / "checkpoint-1"))
+    cfg2, back = CK.load_model_dir(str(tmp_path / "checkpoint-1" / "brushnet"), "brushnet")
+    assert cfg2.block_out_channels == cfg.block_out_channels and all(torch.equal(back[k], out[k].float().cpu()) for k in out)
+    st = torch.load(str(tmp_path / "checkpoint-1" / "optimizer.pt"), weights_only=False)
+    assert {"optimizer", "lr_scheduler"} <= set(st)
     # a second step runs on the updated weights and lowers nothing to NaN
     loss2 = ft.step(latents.cuda(), noise.cuda(), tsteps, cond.cuda(), ehs.cuda())
     assert torch.isfinite(loss2).all()
