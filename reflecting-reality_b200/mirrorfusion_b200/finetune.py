@@ -115,6 +115,19 @@ class FineTuneStep:
         save_brushnet_dir(os.path.join(path, "brushnet"), self.cfg, self.brushnet_state_dict())
         torch.save({"optimizer": self.opt.state_dict(), "lr_scheduler": self.lr_sched.state_dict()}, os.path.join(path, "optimizer.pt"))
 
+    def load_checkpoint(self, path: str):
+        """`--resume_from_checkpoint` (:1269-1296): the BrushNet weights of `<path>/brushnet/`, the optimizer moments / step count and
+        the lr-scheduler position of `<path>/optimizer.pt`; the next step is bit-identical to the one an uninterrupted run takes."""
+        import os
+        from .checkpoint import load_model_dir
+        _cfg, sd = load_model_dir(os.path.join(path, "brushnet"), "brushnet")
+        self.flat.load_state_dict(pack_brushnet(self.cfg, sd))      # fp32 masters + the bf16 working copy
+        self.brushnet.refresh_dgrad_weights()                       # the flipped / transposed copies the data-gradient plans read
+        st = torch.load(os.path.join(path, "optimizer.pt"), map_location=self.dev, weights_only=False)
+        self.opt.load_state_dict(st["optimizer"])
+        self.lr_sched.load_state_dict(st["lr_scheduler"])
+        self.opt.zero_grad()
+
     @property
     def flops_per_step(self) -> float:
         """Algorithmic FLOPs of one step on this rank's batch: forward of both nets + BrushNet backward (data + weight

@@ -162,3 +162,28 @@ def test_fine_tune_step_every_brushnet_gradient_and_one_adamw_step_vs_autograd(p
     # a second step runs on the updated weights and lowers nothing to NaN
     loss2 = ft.step(latents.cuda(), noise.cuda(), tsteps, cond.cuda(), ehs.cuda())
     assert torch.isfinite(loss2).all()
+
+
+@pytest.mark.timeout(600)
+def test_fine_tune_resume_from_checkpoint_is_bit_identical(tmp_path):
+    """save_checkpoint after step 1, then step 2 — against a fresh FineTuneStep that loads the checkpoint and takes step 2
+    (E/train_brushnet_mirror.py:997-1032 save hook, :1269-1296 resume): same loss, same parameters, bit for bit."""
+    from mirrorfusion_b200.finetune import FineTuneStep
+    cfg, B, H, W = TINY, 2, 16, 16
+    usd, bsd = make_state_dict(cfg, "unet", seed=2), make_state_dict(cfg, "brushnet", seed=2)
+    inp = make_inputs(cfg, B, seed=9, height=H, width=W, cfg_duplicate=False)
+    g = torch.Generator().manual_seed(4)
+    batches = [(torch.randn(B, 4, H, W, generator=g).cuda(), torch.randn(B, 4, H, W, generator=g).cuda(),
+                torch.randint(0, 1000, (B,), generator=g)) for _ in range(2)]
+    cond, ehs = inp["conditioning_latents"].cuda(), inp["prompt_embeds"].cuda()
+    kw = dict(batch=B, H=H, W=W, lr=1e-3, max_grad_norm=1.0, lr_schedule="cosine", lr_warmup_steps=1, max_train_steps=10)
+    a = FineTuneStep(cfg, usd, bsd, **kw)
+    a.step(*batches[0], cond, ehs)
+    a.save_checkpoint(str(tmp_path / "checkpoint-1"))
+    loss_a = a.step(*batches[1], cond, ehs).clone()
+    b = FineTuneStep(cfg, usd, make_state_dict(cfg, "brushnet", seed=5), **kw)          # other weights: everything must come from the checkpoint
+    b.load_checkpoint(str(tmp_path / "checkpoint-1"))
+    loss_b = b.step(*batches[1], cond, ehs).clone()
+    assert torch.equal(loss_a, loss_b)
+    assert torch.equal(a.flat.param, b.flat.param) and torch.equal(a.flat.work, b.flat.work)
+    assert a.opt.param_groups[0]["lr"] == b.opt.param_groups[0]["lr"]
