@@ -184,7 +184,7 @@ def test_brushnet_cfg_dedup_is_exact(P):
         eng.set_conditioning(inp["prompt_embeds"].cuda(), bad.cuda())
 
 
-@pytest.mark.parametrize("H,W,images", [(24, 40, 3), (8, 8, 1), (40, 16, 2)])
+@pytest.mark.parametrize("H,W,images", [(24, 40, 3), (8, 8, 1), (40, 16, 2), (128, 128, 1)])      # 128 x 128 latents = 1024 x 1024 images
 def test_non_square_latents_vs_oracle(P, H, W, images):
     """Latent sizes that are not powers of two and not multiples of the 128-row GEMM tile (192x320, 64x64 and 320x128
     pixel images; the reference accepts any multiple of 8): M / N tails of every tile, clipped TMA stores, odd image

@@ -257,7 +257,8 @@ def test_layernorm(ops, rows, C):
     (2, 8, 40, 4096, 4096), (2, 8, 80, 1024, 1024), (2, 8, 160, 256, 256), (2, 8, 160, 64, 64),
     (2, 8, 40, 4096, 77), (2, 8, 80, 1024, 77), (2, 8, 160, 256, 77), (2, 8, 160, 64, 77),
     (2, 2, 32, 256, 256), (2, 2, 64, 64, 64), (2, 2, 64, 16, 77), (1, 8, 40, 200, 333),
-    (1, 8, 40, 9216, 9216), (1, 8, 40, 9216, 77), (1, 8, 80, 2304, 2304)])      # config 5: 96x96 latents (768x768 images)
+    (1, 8, 40, 9216, 9216), (1, 8, 40, 9216, 77), (1, 8, 80, 2304, 2304),       # config 5: 96x96 latents (768x768 images)
+    (1, 8, 40, 16384, 16384)])                                                    # 128x128 latents (1024x1024 images)
 def test_attention(ops, B, heads, d, Tq, Tk):
     Cc = heads * d
     q = randn(B, Tq, Cc, seed=1)
