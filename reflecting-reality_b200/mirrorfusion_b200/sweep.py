@@ -124,3 +124,34 @@ class EvalSweep:
             ops.post_image_u8(img, self.out_u8)
             out[chunk[0]:chunk[-1] + 1] = self.out_u8[: len(chunk)].cpu().numpy()
         return out, mine
+
+
+@torch.no_grad()
+def dataset_transforms(rgb_u8: torch.Tensor, masked_rgb_u8: torch.Tensor, mask_u8: torch.Tensor, depth: Optional[torch.Tensor] = None,
+                       resolution: int = 512, depth_delta: float = 0.5) -> Dict[str, torch.Tensor]:
+    """The tensors `HDF5Dataset.__getitem__` builds for one training / evaluation sample (E/dataset/dataset.py:229-271), for a batch
+    of equally sized samples, on the device: `apply_transforms_rgb` (image, masked image: /255, bicubic antialiased resize of the
+    shorter side to `resolution`, centre crop, Normalize([0.5], [0.5]); :70-82), `apply_transforms_mask` (/255, same resize + crop;
+    :84-96) and `apply_transforms_depth` (max-scene-depth normalisation over mask > 0 + delta to [-1, 1], same resize + crop; :98-166).
+    rgb_u8 / masked_rgb_u8 uint8 [N,H,W,3], mask_u8 uint8 [N,H,W], depth fp32 [N,H,W] or None, all on the device.
+    The normalisation 2x - 1 is applied before the resize here (the filter weights sum to 1, so it commutes up to fp32 rounding)."""
+    N, Hs, Ws, _ = rgb_u8.shape
+    dev = rgb_u8.device
+    out: Dict[str, torch.Tensor] = {}
+    tmp = torch.empty(N, 3, Hs, Ws, device=dev, dtype=f32)
+    for key, src in (("pixel_values", rgb_u8), ("conditioning_pixel_values", masked_rgb_u8)):
+        ops.prep_image_u8(src.contiguous(), tmp)
+        o = torch.empty(N, 3, resolution, resolution, device=dev, dtype=f32)
+        ops.resize_crop_bicubic(tmp, o, resolution)
+        out[key] = o
+    m = mask_u8.to(f32).div_(255.0).contiguous()                              # layout / dtype plumbing of the uint8 mask
+    mo = torch.empty(N, 1, resolution, resolution, device=dev, dtype=f32)
+    ops.resize_crop_bicubic(m, mo.view(N, resolution, resolution), resolution)
+    out["masks"] = mo
+    if depth is not None:
+        dn = torch.empty(N, Hs, Ws, device=dev, dtype=f32)
+        ops.depth_normalize(depth.contiguous(), mask_u8.contiguous(), dn, torch.zeros(N, device=dev, dtype=torch.int32), delta=depth_delta)
+        do = torch.empty(N, 1, resolution, resolution, device=dev, dtype=f32)
+        ops.resize_crop_bicubic(dn, do.view(N, resolution, resolution), resolution)
+        out["depth"] = do
+    return out

@@ -166,3 +166,39 @@ def test_sweep_depth_at_its_own_resolution():
     dl = sw.depth_lat.cpu().numpy()[:, 0]
     for j, (i, _) in enumerate(items):
         assert np.abs(dl[j] - want[i]).max() < 1e-5
+
+
+@pytest.mark.parametrize("Hs,Ws,res", [(96, 128, 64), (80, 80, 64), (50, 70, 64)])
+def test_dataset_transforms_vs_the_reference_functions(Hs, Ws, res):
+    """sweep.dataset_transforms = the per-sample tensors of HDF5Dataset.__getitem__ (E/dataset/dataset.py:229-271): the reference's
+    apply_transforms_rgb / _mask are `Compose([Resize(res, BICUBIC), CenterCrop(res), Normalize([0.5], [0.5])])` on tensor / 255
+    (:70-96) — evaluated here with torchvision exactly as written there — and apply_transforms_depth as restated in oracle/
+    (pinned to the reference's own function by prep_golden.npz) followed by the same resize."""
+    tv = pytest.importorskip("torchvision")
+    from torchvision import transforms
+    from mirrorfusion_b200.sweep import dataset_transforms
+    from oracle import prep_oracle as PO
+    from oracle.resize_oracle import resize_crop_bicubic
+    rng = np.random.default_rng(Hs + Ws)
+    N = 2
+    rgb = rng.integers(0, 256, (N, Hs, Ws, 3), dtype=np.uint8)
+    mask = np.zeros((N, Hs, Ws), np.uint8)
+    mask[:, 10:40, 12:50] = 255
+    masked = rgb.copy()
+    masked[mask == 255] = 0                                                   # get_masked_image (:60-67)
+    depth = (rng.random((N, Hs, Ws), dtype=np.float32) * 4 + 0.5).astype(np.float32)
+    ops.lib()
+    got = dataset_transforms(torch.from_numpy(rgb).cuda(), torch.from_numpy(masked).cuda(), torch.from_numpy(mask).cuda(),
+                             torch.from_numpy(depth).cuda(), resolution=res)
+    t_rgb = transforms.Compose([transforms.Resize(res, interpolation=transforms.InterpolationMode.BICUBIC), transforms.CenterCrop(res),
+                                transforms.Normalize([0.5], [0.5])])
+    t_mask = transforms.Compose([transforms.Resize(res, interpolation=transforms.InterpolationMode.BICUBIC), transforms.CenterCrop(res)])
+    for i in range(N):
+        want = t_rgb(torch.tensor(rgb[i], dtype=torch.float32).permute(2, 0, 1) / 255.0)
+        assert (got["pixel_values"][i].cpu() - want).abs().max().item() < 2e-5
+        want = t_rgb(torch.tensor(masked[i], dtype=torch.float32).permute(2, 0, 1) / 255.0)
+        assert (got["conditioning_pixel_values"][i].cpu() - want).abs().max().item() < 2e-5
+        want = t_mask((torch.tensor(mask[i], dtype=torch.float32) / 255.0).unsqueeze(0))
+        assert (got["masks"][i].cpu() - want).abs().max().item() < 2e-5
+    want_d = resize_crop_bicubic(PO.prep_depth(depth, mask, 1)[:, 0], res)
+    assert np.abs(got["depth"].cpu().numpy()[:, 0] - want_d).max() < 2e-5
