@@ -126,12 +126,6 @@ int mfb_plan_set_stats(mfb_plan* plan, float* buf);
 int mfb_groupnorm(const void* x1, int C1, const void* x2, int C2, int B, int HW, int groups, float eps,
                   const float* gamma, const float* beta, int silu, float* stats_ws, void* out, void* stream);
 
-/* How many kernels mfb_groupnorm launches for a [B, HW, C] input: 1 where one launch computes the statistics AND normalises —
- * maps up to 8x8 (one CTA per slab of groups) and every map a thread-block cluster can hold in registers (16x16 .. 64x64 at
- * the SD1.5 widths: read once, statistics exchanged over distributed shared memory, written once); 2 for the two-pass path
- * (statistics kernel + apply kernel).  Host-side accounting only (bench.py's gpu_launches). */
-int mfb_groupnorm_launches(int C, int B, int HW, int groups);
-
 /* Same, with the statistics of each source already available as igemm partials (mfb_plan_set_stats): the full-tensor
  * statistics pass is replaced by a tiny fixed-order reduction. */
 int mfb_groupnorm_prestat(const void* x1, int C1, const float* part1, int tiles1, const void* x2, int C2, const float* part2,

@@ -386,187 +386,6 @@ __global__ void __launch_bounds__(1024) gn_small_kernel(const __nv_bfloat16* __r
     }
 }
 
-__device__ __forceinline__ float2 ld_cluster_f2(uint32_t cluster_addr) {
-    float2 v;
-    asm volatile("ld.shared::cluster.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(cluster_addr) : "memory");
-    return v;
-}
-
-// Mid-size feature maps (16x16 .. 64x64 at SD1.5 widths): statistics and normalisation in ONE launch and ONE pass over HBM.
-// A thread-block CLUSTER of CS CTAs owns (image b, slab of G whole groups, G*cpg a multiple of 8 channels); CTA `rank` of the
-// cluster takes the pixels [rank*ppc, (rank+1)*ppc) of the slab and keeps them in registers (<= MAXP 16-byte vectors per thread,
-// every load in flight at once).  The per-group {sum, sum of squares} of each CTA are exchanged through distributed shared
-// memory and added in rank order, so the result does not depend on scheduling (deterministic); then every CTA normalises the
-// pixels it still holds.  HBM traffic: read x once, write y once (the two-kernel path reads x twice and pays two dependent
-// launches).  block = nvec*PY threads rounded up to whole warps: thread t -> (channel vector t % nvec, pixel lane t / nvec).
-// Rank 0 also leaves {sum, sum of squares} in stats[b][g] — the contract of the two-kernel path that the fine-tune step's
-// GroupNorm backward relies on.
-template <int MAXP>
-__global__ void __launch_bounds__(512, (MAXP <= 8 ? 2 : 1))
-gn_cluster_kernel(const __nv_bfloat16* __restrict__ x1, int C1, const __nv_bfloat16* __restrict__ x2, int C2, int HW, int groups,
-                  int G, int nvec, int PY, int CS, int ppc, float eps, const float* __restrict__ gamma,
-                  const float* __restrict__ beta, int silu, float* __restrict__ stats, __nv_bfloat16* __restrict__ out) {
-    __shared__ float4 ps[512];
-    __shared__ float4 vs[64];
-    __shared__ __align__(16) float sgam[512], sbet[512];     // gamma / beta of the slab (nvec <= 64 vectors)
-    __shared__ __align__(8) float2 cl[8];
-    __shared__ float g_mean[8], g_rstd[8];
-    const int C = C1 + C2;
-    const int cpg = C / groups;                       // even (host check): a bf16 pair never straddles two groups
-    const int b = blockIdx.y;
-    const int tid = threadIdx.x;
-    const int slab = blockIdx.x / CS;
-    const int rank = blockIdx.x - slab * CS;          // == %cluster_ctarank for cluster dims (CS, 1, 1)
-    const int v = tid % nvec, ty = tid / nvec;
-    const bool active = ty < PY;
-    const int cs = slab * G * cpg;                    // first channel of the slab
-    const int c0 = cs + v * 8;
-    pdl_trigger();
-    pdl_wait();
-    for (int i = tid; i < nvec * 8; i += blockDim.x) {   // visible after the first __syncthreads below
-        sgam[i] = __ldg(&gamma[cs + i]);
-        sbet[i] = __ldg(&beta[cs + i]);
-    }
-    const __nv_bfloat16* src;
-    int ld, cc;
-    if (c0 < C1) { src = x1; ld = C1; cc = c0; } else { src = x2; ld = C2; cc = c0 - C1; }
-    const int p0 = rank * ppc;
-    const int p1 = min(HW, p0 + ppc);
-    // this thread's pixels: p0 + ty + k*PY for k < nk (one base pointer + a constant vector stride: no per-load address registers)
-    const int nk = active ? min(MAXP, max(0, (p1 - p0 - ty + PY - 1) / PY)) : 0;
-    const uint4* src4 = reinterpret_cast<const uint4*>(src + (static_cast<size_t>(b) * HW + p0 + ty) * ld + cc);
-    const int sstride = PY * (ld >> 3);
-    uint4 u[MAXP];
-#pragma unroll
-    for (int k = 0; k < MAXP; ++k) u[k] = k < nk ? __ldg(src4 + k * sstride) : make_uint4(0, 0, 0, 0);
-    // per bf16 PAIR accumulators (the group boundary inside a vector, if any, falls between pairs)
-    float s[4] = {0.f, 0.f, 0.f, 0.f}, q[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-    for (int k = 0; k < MAXP; ++k) {
-        const uint32_t w[4] = {u[k].x, u[k].y, u[k].z, u[k].w};
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const float2 t = unpack_bf16x2(w[j]);
-            s[j] += t.x + t.y;
-            q[j] = fmaf(t.x, t.x, fmaf(t.y, t.y, q[j]));
-        }
-    }
-    // 8 consecutive channels touch at most two groups (cpg >= 8, or cpg == 4 with the vector exactly two groups wide)
-    const int g0 = (v * 8) / cpg;                     // slab-local group of the vector's first channel
-    const int split = (g0 + 1) * cpg - v * 8;         // vector-local index of the first channel of the next group (>= 8: none)
-    float sa = 0.f, qa = 0.f, sb = 0.f, qb = 0.f;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        if (2 * j < split) { sa += s[j]; qa += q[j]; } else { sb += s[j]; qb += q[j]; }
-    }
-    ps[tid] = make_float4(sa, qa, sb, qb);
-    __syncthreads();
-    // level 1: one warp per channel vector — lane l adds pixel lanes l, l + 32, ... in order, then a fixed shuffle tree
-    {
-        const int warp = tid >> 5, lane = tid & 31, nwarps = blockDim.x >> 5;
-        for (int vv = warp; vv < nvec; vv += nwarps) {
-            float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-            for (int y = lane; y < PY; y += 32) {
-                const float4 t = ps[y * nvec + vv];
-                a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w;
-            }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                a.x += __shfl_xor_sync(0xffffffffu, a.x, o);
-                a.y += __shfl_xor_sync(0xffffffffu, a.y, o);
-                a.z += __shfl_xor_sync(0xffffffffu, a.z, o);
-                a.w += __shfl_xor_sync(0xffffffffu, a.w, o);
-            }
-            if (lane == 0) vs[vv] = a;
-        }
-    }
-    __syncthreads();
-    // level 2: thread g adds the (few) vectors that touch slab-local group g, in channel order
-    if (tid < G) {
-        float a = 0.f, q2 = 0.f;
-        int v0 = (tid * cpg) / 8 - 1;
-        if (v0 < 0) v0 = 0;
-        int v1 = ((tid + 1) * cpg - 1) / 8;
-        if (v1 > nvec - 1) v1 = nvec - 1;
-        for (int vv = v0; vv <= v1; ++vv) {
-            const int gv = (vv * 8) / cpg;
-            const float4 pv = vs[vv];
-            if (gv == tid) { a += pv.x; q2 += pv.y; }
-            else if (gv + 1 == tid) { a += pv.z; q2 += pv.w; }
-        }
-        cl[tid] = make_float2(a, q2);
-    }
-    if (CS > 1) cluster_sync_all(); else __syncthreads();
-    if (tid < G) {
-        float a = 0.f, q2 = 0.f;
-        if (CS > 1) {
-            const uint32_t mine = smem_u32(&cl[tid]);
-            for (int r = 0; r < CS; ++r) {                // rank order: every CTA of the cluster computes identical statistics
-                const float2 t = ld_cluster_f2(mapa_shared(mine, static_cast<uint32_t>(r)));
-                a += t.x; q2 += t.y;
-            }
-        } else {
-            a = cl[tid].x; q2 = cl[tid].y;
-        }
-        const float inv_cnt = 1.0f / (static_cast<float>(HW) * cpg);
-        const float mean = a * inv_cnt;
-        const float var = fmaxf(q2 * inv_cnt - mean * mean, 0.f);
-        g_mean[tid] = mean;
-        g_rstd[tid] = rsqrtf(var + eps);
-        if (rank == 0) {
-            float* st = stats + (static_cast<size_t>(b) * groups + slab * G + tid) * 2;
-            st[0] = a;
-            st[1] = q2;
-        }
-    }
-    __syncthreads();
-    // peers may still be reading this CTA's cl[]: arrive now, wait just before exit (the stores below overlap the barrier)
-    if (CS > 1) asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-    if (active) {
-        const int g1 = min(g0 + 1, G - 1);
-        const float m0 = g_mean[g0], r0 = g_rstd[g0], m1 = g_mean[g1], r1 = g_rstd[g1];
-        float sc[8], sh[8];
-        {
-            const float4 ga = *reinterpret_cast<const float4*>(&sgam[v * 8]), gb = *reinterpret_cast<const float4*>(&sgam[v * 8 + 4]);
-            const float4 ba = *reinterpret_cast<const float4*>(&sbet[v * 8]), bb = *reinterpret_cast<const float4*>(&sbet[v * 8 + 4]);
-            const float gm[8] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};
-            const float bt[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-                const bool lo = e < split;
-                sc[e] = (lo ? r0 : r1) * gm[e];
-                sh[e] = bt[e] - (lo ? m0 : m1) * sc[e];
-            }
-        }
-        uint4* dst4 = reinterpret_cast<uint4*>(out + (static_cast<size_t>(b) * HW + p0 + ty) * C + c0);
-        const int dstride = PY * (C >> 3);
-        if (silu) {
-#pragma unroll
-            for (int k = 0; k < MAXP; ++k) {
-                if (k < nk) {
-                    float f[8];
-                    unpack8(u[k], f);
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) f[e] = silu_f(fmaf(f[e], sc[e], sh[e]));
-                    dst4[k * dstride] = pack8(f);
-                }
-            }
-        } else {
-#pragma unroll
-            for (int k = 0; k < MAXP; ++k) {
-                if (k < nk) {
-                    float f[8];
-                    unpack8(u[k], f);
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) f[e] = fmaf(f[e], sc[e], sh[e]);
-                    dst4[k * dstride] = pack8(f);
-                }
-            }
-        }
-    }
-    if (CS > 1) asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-
 // one warp per row, two-pass (mean, then centred variance) on register-resident data
 template <int NV>
 __global__ void layernorm_kernel(const __nv_bfloat16* __restrict__ x, int rows, int C, float eps,
@@ -691,69 +510,6 @@ __global__ void __launch_bounds__(256) layernorm5_kernel(const __nv_bfloat16* __
 
 using namespace mfb;
 
-// Launch geometry of gn_cluster_kernel for a [B, HW, C] tensor, or ok = false when the two-kernel path has to take it
-// (maps too large to hold in registers, group widths that do not tile into 16-byte vectors).
-struct GnClusterCfg {
-    bool ok;
-    int G, nvec, PY, CS, ppc, maxp, threads;
-};
-static GnClusterCfg gn_cluster_cfg(int C, int B, int HW, int groups) {
-    GnClusterCfg c = {false, 0, 0, 0, 0, 0, 0, 0};
-    static const int mode = [] { const char* e = getenv("MFB_GN_CLUSTER"); return e ? atoi(e) : 1; }();
-    if (!mode || groups <= 0 || C % groups) return c;
-    const int cpg = C / groups;
-    if (cpg % 2) return c;                            // the kernel accumulates per bf16 pair
-    int G = 1;
-    while (G <= 8 && ((G * cpg) % 8 != 0 || groups % G != 0)) G *= 2;
-    if (G > 8) return c;
-    while (G * cpg < 32 && G * 2 <= 8 && groups % (G * 2) == 0) G *= 2;     // at least 64 contiguous bytes per pixel
-    const int nvec = G * cpg / 8;
-    if (nvec > 64) return c;
-    int PY = 512 / nvec;
-    for (int CS = 1; CS <= 8; CS *= 2) {
-        const int ppc = (HW + CS - 1) / CS;
-        const int py = PY < ppc ? PY : ppc;
-        const int maxp = (ppc + py - 1) / py;
-        // the smallest cluster whose CTAs hold their pixels in <= 8 vectors per thread; 16 only when 8 CTAs are not enough
-        if (maxp <= 8 || (CS == 8 && maxp <= 16)) {
-            // small batches: keep splitting the pixels while the grid stays within one resident wave (2 CTAs per SM)
-            int cs2 = CS, ppc2 = ppc, py2 = py, maxp2 = maxp;
-            while (cs2 < 8 && maxp2 >= 2 && B * (groups / G) * cs2 * 2 <= 2 * (device_sm_count() > 0 ? device_sm_count() : 148)) {
-                cs2 *= 2;
-                ppc2 = (HW + cs2 - 1) / cs2;
-                py2 = PY < ppc2 ? PY : ppc2;
-                maxp2 = (ppc2 + py2 - 1) / py2;
-            }
-            c.ok = true;
-            c.G = G; c.nvec = nvec; c.PY = py2; c.CS = cs2; c.ppc = ppc2; c.maxp = maxp2;
-            c.threads = ((nvec * py2 + 31) / 32) * 32;
-            return c;
-        }
-    }
-    return c;
-}
-
-static int gn_small_max_hw() {
-    static const int v = [] { const char* e = getenv("MFB_GN_SMALL_HW"); return e ? atoi(e) : 64; }();
-    return v;
-}
-
-// Number of kernel launches mfb_groupnorm makes for this geometry (1: gn_small_kernel or gn_cluster_kernel; 2: statistics + apply).
-extern "C" int mfb_groupnorm_launches(int C, int B, int HW, int groups) {
-    if (groups <= 0 || C % groups) return 2;
-    if (HW <= gn_small_max_hw()) {
-        const int cpg = C / groups;
-        int G = 1;
-        while (G <= 4 && (G * cpg) % 8 != 0) G *= 2;
-        const int nvec = G * cpg / 8;
-        if (G <= 4 && groups % G == 0 && nvec <= 64) {
-            const int py = 256 / nvec < HW ? 256 / nvec : HW;
-            if ((HW + py - 1) / py <= 4) return 1;
-        }
-    }
-    return gn_cluster_cfg(C, B, HW, groups).ok ? 1 : 2;
-}
-
 static int groupnorm_impl(const void* x1, int C1, const void* x2, int C2, int B, int HW, int groups, float eps, const float* gamma,
                           const float* beta, int silu, float* stats_ws, void* out, void* stream, const float* part1, int tiles1,
                           const float* part2, int tiles2) {
@@ -768,7 +524,7 @@ static int groupnorm_impl(const void* x1, int C1, const void* x2, int C2, int B,
     MFB_REQUIRE(CV <= 1024, "C too large");
     const int PY = CV >= 256 ? 1 : 256 / CV;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const int small_max_hw = gn_small_max_hw();
+    static const int small_max_hw = [] { const char* e = getenv("MFB_GN_SMALL_HW"); return e ? atoi(e) : 64; }();
     if (part1 == nullptr && HW <= small_max_hw) {
         // single-launch path for the small feature maps
         const int cpg = C / groups;
@@ -790,26 +546,6 @@ static int groupnorm_impl(const void* x1, int C1, const void* x2, int C2, int B,
                 MFB_CUDA_OK(launch_k(gn_small_kernel<4>, g2, b2, 0, st, 1, X1, C1, X2, C2, HW, groups, G, eps, gamma, beta, silu, O));
                 return MFB_OK;
             }
-        }
-    }
-    if (part1 == nullptr) {
-        // single-launch, single-pass path for the mid-size maps: a cluster per (image, slab of groups), data held in registers
-        const GnClusterCfg cc = gn_cluster_cfg(C, B, HW, groups);
-        if (cc.ok) {
-            auto X1 = static_cast<const __nv_bfloat16*>(x1);
-            auto X2 = static_cast<const __nv_bfloat16*>(x2);
-            auto O = static_cast<__nv_bfloat16*>(out);
-            const dim3 g3((groups / cc.G) * cc.CS, B), b3(cc.threads);
-            if (cc.maxp <= 4)
-                MFB_CUDA_OK(launch_k(gn_cluster_kernel<4>, g3, b3, 0, st, cc.CS, X1, C1, X2, C2, HW, groups, cc.G, cc.nvec, cc.PY, cc.CS,
-                                     cc.ppc, eps, gamma, beta, silu, stats_ws, O));
-            else if (cc.maxp <= 8)
-                MFB_CUDA_OK(launch_k(gn_cluster_kernel<8>, g3, b3, 0, st, cc.CS, X1, C1, X2, C2, HW, groups, cc.G, cc.nvec, cc.PY, cc.CS,
-                                     cc.ppc, eps, gamma, beta, silu, stats_ws, O));
-            else
-                MFB_CUDA_OK(launch_k(gn_cluster_kernel<16>, g3, b3, 0, st, cc.CS, X1, C1, X2, C2, HW, groups, cc.G, cc.nvec, cc.PY, cc.CS,
-                                     cc.ppc, eps, gamma, beta, silu, stats_ws, O));
-            return MFB_OK;
         }
     }
     // Grid = ONE full wave of resident CTAs (occupancy API x SM count), every CTA an equal pixel chunk: a grid a

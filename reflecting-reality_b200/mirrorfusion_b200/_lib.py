@@ -47,7 +47,6 @@ _SIGS = {
     "mfb_plan_stats_tiles": (i32, [vp]),
     "mfb_plan_set_stats": (i32, [vp, vp]),
     "mfb_groupnorm_prestat": (i32, [vp, i32, vp, i32, vp, i32, vp, i32, i32, i32, i32, f32, vp, vp, i32, vp, vp, vp]),
-    "mfb_groupnorm_launches": (i32, [i32, i32, i32, i32]),
     "mfb_groupnorm": (i32, [vp, i32, vp, i32, i32, i32, i32, f32, vp, vp, i32, vp, vp, vp]),
     "mfb_layernorm": (i32, [vp, i32, i32, f32, vp, vp, vp, vp]),
     "mfb_softmax_rows": (i32, [vp, i32, i32, vp, vp]),

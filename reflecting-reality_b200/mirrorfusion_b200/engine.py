@@ -134,9 +134,7 @@ class _Net:
         if p1 is None or (x2 is not None and p2 is None):
             p1 = p2 = None
         self.emit(lambda: ops.groupnorm(x1, x2, g, b, out, self.gn_ws, B=self.B, HW=HW, groups=G, eps=eps, silu=silu,
-                                        part1=p1, part2=p2),
-                  2 if p1 is not None else ops.groupnorm_launches(x1.shape[-1] + (0 if x2 is None else x2.shape[-1]), self.B, HW, G),
-                  "groupnorm")   # single-launch kernels (<= 8x8: one CTA per slab; mid-size maps: one cluster per slab), else 2
+                                        part1=p1, part2=p2), 1 if HW <= 64 else 2, "groupnorm")   # <= 8x8 maps: single-launch kernel
 
     def layernorm(self, x, prefix: str, out):
         g, b = self.wf(prefix + ".weight"), self.wf(prefix + ".bias")

@@ -247,11 +247,6 @@ def gn_ws_floats(B: int, groups: int) -> int:
     return 2 * B * groups * (1 + GN_MAX_CHUNKS) + B
 
 
-def groupnorm_launches(C: int, B: int, HW: int, groups: int) -> int:
-    """Kernel launches of groupnorm() without igemm partials for this geometry (1 or 2; include/mfb200.h)."""
-    return int(lib().mfb_groupnorm_launches(C, B, HW, groups))
-
-
 def groupnorm(x1, x2, gamma, beta, out, stats_ws, *, B, HW, groups, eps, silu, part1=None, part2=None):
     """part1 / part2: (buffer, tiles) from ConvPlan.enable_output_stats of the GEMM that produced x1 / x2."""
     L = lib()

@@ -204,54 +204,6 @@ def test_groupnorm(ops, B, HW, C1, C2, groups, eps, silu):
     assert rel(out.float(), ref.transpose(1, 2)) < 4e-3
 
 
-@pytest.mark.parametrize("B,HW,C1,C2,groups,silu", [
-    # the single-pass cluster kernel (csrc/norm.cu gn_cluster_kernel): SD1.5 shapes incl. the 960-channel concat (16 vectors per
-    # thread) and 96x96 = 9216 tokens, ragged pixel counts (last CTA of the cluster short / empty), the VAE's widths
-    # (4, 8, 16 channels per group), a concat whose boundary falls inside a slab
-    (16, 4096, 640, 320, 32, True), (2, 9216, 320, 0, 32, True), (3, 1000, 640, 0, 32, True), (2, 4095, 320, 320, 32, False),
-    (2, 4096, 128, 0, 32, True), (2, 1024, 256, 0, 32, True), (2, 4096, 512, 0, 32, False), (5, 67, 1280, 640, 32, True),
-    (2, 1024, 1280, 640, 32, True), (1, 16384, 256, 0, 32, True), (2, 300, 2560, 0, 32, True), (2, 1024, 72, 88, 4, True)])
-def test_groupnorm_cluster_path(ops, B, HW, C1, C2, groups, silu):
-    Cc = C1 + C2
-    assert ops.groupnorm_launches(Cc, B, HW, groups) == 1
-    x1 = randn(B, HW, C1, seed=1) + 0.5
-    x2 = randn(B, HW, C2, seed=2, scale=2.0) - 0.25 if C2 else None
-    gamma = 1 + 0.1 * randn(Cc, seed=3, dtype=torch.float32)
-    beta = 0.1 * randn(Cc, seed=4, dtype=torch.float32)
-    out = torch.full((B, HW, Cc), float("nan"), device="cuda", dtype=bf16)
-    ws = torch.zeros(ops.gn_ws_floats(B, groups), device="cuda")
-    ops.groupnorm(x1, x2, gamma, beta, out, ws, B=B, HW=HW, groups=groups, eps=1e-5, silu=silu)
-    first = out.clone()
-    ops.groupnorm(x1, x2, gamma, beta, out, ws, B=B, HW=HW, groups=groups, eps=1e-5, silu=silu)
-    assert torch.equal(first, out)                                           # fixed-order reductions: bitwise repeatable
-    xin = x1.float() if x2 is None else torch.cat([x1.float(), x2.float()], -1)
-    ref = F.group_norm(xin.transpose(1, 2), groups, gamma, beta, 1e-5)
-    if silu:
-        ref = F.silu(ref)
-    assert rel(out.float(), ref.transpose(1, 2)) < 4e-3
-    # the head of the workspace holds {sum, sum of squares} per (image, group): what the fine-tune step's backward reads
-    xg = xin.double().view(B, HW, groups, Cc // groups)
-    st = ws[:2 * B * groups].view(B, groups, 2).double()
-    assert rel(st[..., 0], xg.sum((1, 3))) < 1e-5 and rel(st[..., 1], (xg * xg).sum((1, 3))) < 1e-5
-    # same statistics as the statistics kernel of the two-pass path
-    ws2 = torch.zeros_like(ws)
-    ops.groupnorm_stats(x1, x2, ws2, B=B, HW=HW, groups=groups)
-    assert rel(ws[:2 * B * groups], ws2[:2 * B * groups]) < 1e-5
-
-
-def test_groupnorm_launch_census(ops):
-    assert ops.groupnorm_launches(1280, 16, 64, 32) == 1          # 8x8: one CTA per slab
-    assert ops.groupnorm_launches(320, 16, 4096, 32) == 1         # cluster kernel
-    assert ops.groupnorm_launches(128, 1, 512 * 512, 32) == 2     # VAE at full resolution: two-pass path
-    x = randn(1, 512 * 512, 128, seed=1)
-    gamma, beta = torch.ones(128, device="cuda"), torch.zeros(128, device="cuda")
-    out = torch.empty_like(x)
-    ws = torch.zeros(ops.gn_ws_floats(1, 32), device="cuda")
-    ops.groupnorm(x, None, gamma, beta, out, ws, B=1, HW=512 * 512, groups=32, eps=1e-6, silu=False)
-    ref = F.group_norm(x.float().transpose(1, 2), 32, gamma, beta, 1e-6)
-    assert rel(out.float(), ref.transpose(1, 2)) < 4e-3
-
-
 @pytest.mark.parametrize("B,H,W,Cin,Cout,up", [(2, 32, 32, 64, 320, False), (4, 8, 8, 64, 640, False), (2, 12, 12, 64, 160, False),
                                                (2, 8, 8, 64, 320, True), (3, 16, 16, 128, 1280, False)])
 def test_groupnorm_with_statistics_from_the_conv_epilogue(ops, B, H, W, Cin, Cout, up):
