@@ -456,13 +456,15 @@ def run_ours(args, rank, world, local_rank):
     d2h = host_out.numel() * 4
     table_host = table.cpu().pin_memory()
 
+    host_bufs = [host_in, host_out]
+
     def e2e_step(i):
         j = i % STEPS_PER_IMAGE
-        eng.x.copy_(host_in, non_blocking=True)                     # this step's latents from pinned host memory
+        src, dst = host_bufs[i % 2], host_bufs[(i + 1) % 2]         # the result read back in step i is the input of step i + 1
+        eng.x.copy_(src, non_blocking=True)                         # this step's latents from pinned host memory
         eng.step(float(ts[j]), table_host[j], 1.0)                  # coefficients also come from the host
-        host_out.copy_(eng.x, non_blocking=True)                    # read the step's result back
+        dst.copy_(eng.x, non_blocking=True)                         # read the step's result back
         torch.cuda.current_stream().synchronize()
-        host_in.copy_(host_out)
 
     for i in range(min(args.warmup, 3)):
         e2e_step(i)
@@ -546,6 +548,55 @@ def run_ours(args, rank, world, local_rank):
         "whole_step_frac_of_peak": step_flops / (ms_per_step * 1e-3) / 1e12 / peak,
         "whole_step_frac_vs_burst": step_flops / (ms_per_step * 1e-3) / 1e12 / peaks["bf16_burst"],
     }
+    # the same families back to back inside a CUDA graph (one graph per family, single stream): no event pair and no launch gap
+    # between the kernels — what a family costs inside the captured step, where the next kernel's CTAs start as the previous
+    # one's drain.  Secondary: `achieved` / `frac` above stay on the (longer) eager per-launch event times.
+    try:
+        in_graph = {}
+        for tag in sorted(fam):
+            fns = [f for e in (eng.bn, eng.unet) for f, (t_, _) in zip(e.prog[e.n_time_ops:], e.tags[e.n_time_ops:]) if t_ == tag]
+            if not fns:
+                continue
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for f in fns:
+                    f()
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            g_f = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g_f):
+                for f in fns:
+                    f()
+            g_f.replay()
+            torch.cuda.synchronize()
+            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            f0.record(stream)
+            for _ in range(5):
+                g_f.replay()
+            f1.record(stream)
+            torch.cuda.synchronize()
+            in_graph[tag] = f0.elapsed_time(f1) / 5
+            del g_f
+        ig_ms = in_graph.get("igemm")
+        roofline["in_graph"] = {
+            "families_ms_per_step": {k: round(v, 4) for k, v in in_graph.items()},
+            "sum_ms": round(sum(in_graph.values()), 4),
+            "igemm_tflops": ig[1] / (ig_ms * 1e-3) / 1e12 if ig_ms else None,
+            "igemm_frac": ig[1] / (ig_ms * 1e-3) / 1e12 / peak if ig_ms else None,
+            "igemm_frac_vs_burst": ig[1] / (ig_ms * 1e-3) / 1e12 / peaks["bf16_burst"] if ig_ms else None,
+            "igemm_executed_frac": ig[3] / (ig_ms * 1e-3) / 1e12 / peak if ig_ms else None,
+            "note": "each family's launches of one step replayed back to back from its own CUDA graph (stale inputs; the kernels' "
+                    "timing does not depend on the data), CUDA events around 5 replays",
+        }
+        if (H, W) == (64, 64):
+            for famname, mb in (("groupnorm", 309e6), ("layernorm", 139e6)):
+                if famname in in_graph:
+                    gbs = mb * 2 * images / (in_graph[famname] * 1e-3) / 1e9
+                    roofline["in_graph"][famname + "_gbs"] = gbs
+                    roofline["in_graph"][famname + "_frac_of_hbm_peak"] = gbs / peaks["hbm_gbs"]
+    except Exception as ex:              # a secondary measurement must not take the headline down with it
+        roofline["in_graph"] = {"error": f"{type(ex).__name__}: {ex}"}
     # bandwidth-bound families against the measured HBM peak: ALGORITHMIC bytes (bf16, read + write once)
     if (H, W) == (64, 64):
         for famname, mb in (("groupnorm", 309e6), ("layernorm", 139e6)):
