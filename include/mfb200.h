@@ -71,8 +71,10 @@ typedef struct mfb_conv_desc {
                              B,H,W are the LOW-resolution input dims, out/res/extras are [B,2H,2W,.]; w holds the four
                              sub-pixel phases [4][Cout][4*Cin + extras] (phase = py*2+px, taps that hit the same source
                              pixel pre-summed); the plan issues 4 launches and never materialises the upsampled tensor */
-    int igemm_mode;       /* 0 = auto (env MFB_IGEMM_MODE or independent CTAs); 1 independent CTAs, 2 CTA pair + weight multicast,
-                             3 CTA pair + cta_group::2 UMMA (256-row tile) */
+    int igemm_mode;       /* 0 = auto (env MFB_IGEMM_MODE / MFB_IGEMM_SPLITK or independent CTAs); 1 independent CTAs, 2 CTA pair + weight
+                             multicast, 3 CTA pair + cta_group::2 UMMA (256-row tile), 4 split-K CTA pair where the geometry qualifies
+                             (few-tile launches: both CTAs of a pair work on one wide tile, each on half of the K blocks, partial
+                             accumulator handed over through distributed shared memory), independent CTAs otherwise */
     int pad0;             /* stride 2 only.  0: conv padding 1 (UNet Downsample2D).  1: F.pad(x, (0,1,0,1)) + conv padding 0 —
                              the VAE encoder's Downsample2D(padding=0) (S/models/downsampling.py:141-143): taps read input rows
                              2*oh + kh (not 2*oh + kh - 1), the zero row / column sits at the bottom / right edge */
@@ -104,6 +106,7 @@ int mfb_plan_run(mfb_plan* plan, void* stream);
 int mfb_plan_destroy(mfb_plan* plan);
 double mfb_plan_flops(const mfb_plan* plan); /* 2*M*N*Ktot */
 int mfb_plan_ktotal(const mfb_plan* plan);
+int mfb_plan_igemm_mode(const mfb_plan* plan); /* kernel variant the plan chose: 0 independent CTAs, 1 / 2 the pair modes, 3 split-K pair */
 int mfb_plan_launches(const mfb_plan* plan); /* kernel launches per mfb_plan_run (4 for up2x plans) */
 /* Fused GroupNorm statistics: the epilogue can also emit, per (image, tile, output channel), the sum and sum of squares
  * of the bf16 values it stores — the statistics F.group_norm of the CONSUMER would otherwise re-read the tensor for

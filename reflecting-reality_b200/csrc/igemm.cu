@@ -196,12 +196,18 @@ __global__ void __launch_bounds__(64 + 32 * EPIW, 1) igemm_kernel(const __grid_c
     using Cfg = IgemmCfg<BN>;
     static_assert(EPIW == 8 || EPIW == 16, "8 or 16 epilogue warps");
     constexpr int IGEMM_EPI_WARPS = EPIW, IGEMM_COL_GROUPS = EPIW / 4;
-    constexpr bool PAIR = MODE != 0;
+    constexpr bool PAIR = MODE == 1 || MODE == 2;   // a pair works on two M tiles
     constexpr bool TWOSM = MODE == 2;
+    // MODE 3: split-K — BOTH CTAs of a pair work on the SAME tile, each on half of the K blocks; rank 1 hands its fp32 partial
+    // accumulator to rank 0 through distributed shared memory (into rank 0's operand ring, which is idle once its MMAs have
+    // completed) and rank 0 runs the epilogue.  One tile per pair (host: tiles <= SMs / 2): the few-tile launches of the 8x8
+    // level keep the wide 128 x 160 tile (shared-memory operand bandwidth is what bounds 128 x 80 tiles) on all SMs.
+    constexpr bool SPLITK = MODE == 3;
+    constexpr bool CLUSTER2 = MODE != 0;
     constexpr int STAGE_BYTES = TWOSM ? Cfg::A_BYTES + Cfg::B_BYTES / 2 : Cfg::STAGE_BYTES;
     constexpr int MAXS = Cfg::MAX_STAGES;
     const int STAGES = p.stages;
-    const int nstg = PAIR ? 1 : p.nstg;
+    const int nstg = CLUSTER2 ? 1 : p.nstg;
     extern __shared__ uint8_t smem_raw[];
     // 1024-byte alignment is required by the 128B swizzle atoms
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -213,6 +219,8 @@ __global__ void __launch_bounds__(64 + 32 * EPIW, 1) igemm_kernel(const __grid_c
     auto tmem_empty_bar = [&](int a) { return bar_base + 8u * (2 * MAXS + 2 + a); };
     const uint32_t res_full_bar = bar_base + 8u * (2 * MAXS + 4);
     const uint32_t tmem_slot = bar_base + 8u * (2 * MAXS + 5);
+    const uint32_t xfree_bar = bar_base + 8u * (2 * MAXS + 6);   // MODE 3, in rank 1: rank 0's MMAs have completed (its ring is idle)
+    const uint32_t xfull_bar = bar_base + 8u * (2 * MAXS + 7);   // MODE 3, in rank 0: rank 1's partial accumulator has landed
     uint8_t* stg_gen = smem_raw + (stg_base - smem_u32(smem_raw));   // generic pointer to the staging tile
     uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
     float* sbias = reinterpret_cast<float*>(smem_raw + (bar_base + 256 - smem_u32(smem_raw)));   // [2][BN]
@@ -223,13 +231,16 @@ __global__ void __launch_bounds__(64 + 32 * EPIW, 1) igemm_kernel(const __grid_c
     const int tiles_n = p.tiles_nn;
     // work items: PAIR -> (pair of M tiles, N tile); this CTA takes M tile 2*mp + rank (a tile past the end is all
     // out-of-bounds: zero-filled loads, clipped stores)
-    const uint32_t crank = PAIR ? cluster_ctarank() : 0u;
+    const uint32_t crank = CLUSTER2 ? cluster_ctarank() : 0u;
     const int num_tiles = (PAIR ? (p.tiles_m + 1) / 2 : p.tiles_m) * tiles_n;
-    const int wi0 = PAIR ? int(blockIdx.x >> 1) : int(blockIdx.x);
-    const int wstep = PAIR ? int(gridDim.x >> 1) : int(gridDim.x);
+    const int wi0 = CLUSTER2 ? int(blockIdx.x >> 1) : int(blockIdx.x);
+    const int wstep = CLUSTER2 ? int(gridDim.x >> 1) : int(gridDim.x);
 
     int total_kb = 0;
     for (int s = 0; s < p.nseg; ++s) total_kb += p.seg[s].cblocks;
+    // K blocks of this CTA: all of them, or (MODE 3) the first / second half
+    const int kb_lo = (SPLITK && crank != 0) ? (total_kb + 1) / 2 : 0;
+    const int kb_hi = (SPLITK && crank == 0) ? (total_kb + 1) / 2 : total_kb;
 
     if (warp == IGEMM_EPI_WARPS && lane == 0) {
         prefetch_tmap(&p.tmB);
@@ -244,6 +255,10 @@ __global__ void __launch_bounds__(64 + 32 * EPIW, 1) igemm_kernel(const __grid_c
             mbar_init(tmem_empty_bar(a), TWOSM ? 2 * IGEMM_EPI_WARPS : IGEMM_EPI_WARPS);
         }
         mbar_init(res_full_bar, 1);
+        if constexpr (SPLITK) {
+            mbar_init(xfree_bar, 1);
+            mbar_init(xfull_bar, IGEMM_EPI_WARPS * 32);
+        }
         fence_barrier_init();
     }
     if (warp == IGEMM_EPI_WARPS + 1) {
@@ -257,7 +272,7 @@ __global__ void __launch_bounds__(64 + 32 * EPIW, 1) igemm_kernel(const __grid_c
     }
     tc_fence_before();
     __syncthreads();
-    if constexpr (PAIR) cluster_sync_all();     // the peer's barriers must exist before anything is multicast at them
+    if constexpr (CLUSTER2) cluster_sync_all();     // the peer's barriers must exist before anything is multicast at them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
     pdl_trigger();   // the next kernel may start its own prologue
@@ -288,11 +303,15 @@ __global__ void __launch_bounds__(64 + 32 * EPIW, 1) igemm_kernel(const __grid_c
                     nt = ti.nt; w0 = ti.iw * p.tw; h0 = ti.ih * p.th; n0 = ti.ig * p.tn;
                     ti.next();
                 }
-                int kcol = 0;
+                int kcol = 0, kbi = 0;
                 for (int s = 0; s < p.nseg; ++s) {
                     const IgemmSeg sg = p.seg[s];
                     const void* tm = &p.tmA[sg.map];
                     for (int cb = 0; cb < sg.cblocks; ++cb, kcol += BK) {
+                        if constexpr (SPLITK) {
+                            const int k_ = kbi++;
+                            if (k_ < kb_lo || k_ >= kb_hi) continue;       // the peer's half of the K blocks
+                        }
                         mbar_wait(empty_bar(stage), phase ^ 1);
                         const uint32_t a_dst = smem_base + stage * STAGE_BYTES;
                         if constexpr (TWOSM) {
@@ -329,7 +348,8 @@ __global__ void __launch_bounds__(64 + 32 * EPIW, 1) igemm_kernel(const __grid_c
                 mbar_wait(tmem_empty_bar(as), ((li >> 1) & 1) ^ 1);   // epilogue has drained this accumulator slot
                 tc_fence_after();
                 const uint32_t tacc = tmem_base + as * Cfg::ACC_COLS;
-                for (int kb = 0; kb < total_kb; ++kb) {
+                const int my_kb = kb_hi - kb_lo;
+                for (int kb = 0; kb < my_kb; ++kb) {
                     mbar_wait(full_bar(stage), phase);
                     tc_fence_after();
                     const uint32_t a_addr = smem_base + stage * STAGE_BYTES;
@@ -350,6 +370,10 @@ __global__ void __launch_bounds__(64 + 32 * EPIW, 1) igemm_kernel(const __grid_c
                 // accumulator complete
                 if constexpr (TWOSM) umma_commit_2sm_mc(tmem_full_bar(as), uint16_t(3));
                 else umma_commit(tmem_full_bar(as));
+                if constexpr (SPLITK) {
+                    // rank 0's operand ring is idle from here on: tell rank 1 it may park its partial accumulator there
+                    if (crank == 0) umma_commit_mc(xfree_bar, uint16_t(2));
+                }
             }
         }
         __syncwarp();
@@ -387,7 +411,42 @@ __global__ void __launch_bounds__(64 + 32 * EPIW, 1) igemm_kernel(const __grid_c
             if (nstg == 2 && p.res1 != nullptr && leader && wi0 < num_tiles)
                 load_res(0, ti.nt, ti.iw * p.tw, ti.ih * p.th, ti.ig * p.tn);      // first tile; later ones are prefetched
         }
-        for (int tile = wi0; tile < num_tiles; tile += wstep, ++li) {
+        // MODE 3, rank 1: no epilogue of its own — its slice of the partial accumulator goes, thread for thread, into rank 0's
+        // (idle) operand ring: 16-byte chunk c of epilogue thread t at ((c * threads + t) * 16), so that consecutive threads
+        // write consecutive chunks; rank 0's thread t adds exactly what rank 1's thread t wrote.
+        constexpr int XTHREADS = IGEMM_EPI_WARPS * 32;
+        bool handed_over = false;
+        if constexpr (SPLITK) {
+            if (crank != 0 && wi0 < num_tiles) {
+                constexpr int NCH = BN / 16, NG = IGEMM_COL_GROUPS;
+                constexpr int MAXC = (NCH + NG - 1) / NG;
+                constexpr int CBASE = NCH / NG, CREM = NCH % NG;
+                const int c_begin = half * CBASE + (half < CREM ? half : CREM);
+                const int c_cnt = CBASE + (half < CREM ? 1 : 0);
+                mbar_wait_relaxed(tmem_full_bar(0), 0);
+                tc_fence_after();
+                uint32_t v[MAXC][16];
+                const uint32_t trow = tmem_base + (uint32_t(q * 32) << 16);
+#pragma unroll
+                for (int i = 0; i < MAXC; ++i)
+                    if (i < c_cnt) tmem_ld16(trow + (c_begin + i) * 16, v[i]);
+                tmem_wait_ld();
+                mbar_wait_relaxed(xfree_bar, 0);                 // rank 0's MMAs no longer read its ring
+                const uint32_t xdst = mapa_shared(smem_base, 0) + uint32_t(threadIdx.x) * 16u;
+#pragma unroll
+                for (int i = 0; i < MAXC; ++i) {
+                    if (i < c_cnt) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            st_cluster_v4(xdst + uint32_t((i * 4 + j) * XTHREADS) * 16u, v[i][4 * j], v[i][4 * j + 1], v[i][4 * j + 2],
+                                          v[i][4 * j + 3]);
+                    }
+                }
+                mbar_arrive_cluster(mapa_shared(xfull_bar, 0));  // release.cluster: this thread's stores above are ordered before it
+            }
+            handed_over = crank != 0;
+        }
+        for (int tile = wi0; tile < num_tiles && !handed_over; tile += wstep, ++li) {
             int nt, mt, w0, h0, n0;
             if constexpr (PAIR) {
                 nt = tile % tiles_n;
@@ -470,6 +529,24 @@ __global__ void __launch_bounds__(64 + 32 * EPIW, 1) igemm_kernel(const __grid_c
                 for (int i = 0; i < MAXC; ++i)
                     if (i < c_cnt) tmem_ld16(trow + (c_begin + i) * 16, v[i]);
                 release_acc();
+                if constexpr (SPLITK) {
+                    // the peer's half of the K sum: added in a fixed order (first half + second half) -> deterministic
+                    mbar_wait_cluster(xfull_bar, 0);
+                    const uint8_t* xsrc = smem_raw + (smem_base - smem_u32(smem_raw)) + threadIdx.x * 16;
+#pragma unroll
+                    for (int i = 0; i < MAXC; ++i) {
+                        if (i < c_cnt) {
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const float4 t = *reinterpret_cast<const float4*>(xsrc + static_cast<size_t>((i * 4 + j) * XTHREADS) * 16);
+                                v[i][4 * j + 0] = __float_as_uint(__uint_as_float(v[i][4 * j + 0]) + t.x);
+                                v[i][4 * j + 1] = __float_as_uint(__uint_as_float(v[i][4 * j + 1]) + t.y);
+                                v[i][4 * j + 2] = __float_as_uint(__uint_as_float(v[i][4 * j + 2]) + t.z);
+                                v[i][4 * j + 3] = __float_as_uint(__uint_as_float(v[i][4 * j + 3]) + t.w);
+                            }
+                        }
+                    }
+                }
                 if (p.res1) mbar_wait_relaxed(res_full_bar, li & 1);
                 // fused output statistics: which (image, slot) this warp's 32 rows belong to
                 const bool do_stats = p.stats != nullptr;
@@ -600,7 +677,7 @@ __global__ void __launch_bounds__(64 + 32 * EPIW, 1) igemm_kernel(const __grid_c
 
     tc_fence_before();
     __syncthreads();
-    if constexpr (PAIR) cluster_sync_all();     // no CTA may exit while its peer can still multicast into it
+    if constexpr (CLUSTER2) cluster_sync_all();     // no CTA may exit while its peer can still multicast / write into it
     if (warp == IGEMM_EPI_WARPS + 1) {
         tc_fence_after();
         if constexpr (TWOSM) tmem_dealloc_2sm(tmem_base, Cfg::TMEM_COLS);
@@ -614,7 +691,7 @@ struct Plan {
     int nlaunch;
     dim3 grid;
     int bn;
-    int mode;   // 0 independent CTAs, 1 pair + weight multicast, 2 pair + cta_group::2 UMMA
+    int mode;   // 0 independent CTAs, 1 pair + weight multicast, 2 pair + cta_group::2 UMMA, 3 split-K pair (DSMEM hand-off)
     int epiw;   // epilogue warps of the kernel variant: 8, or 16 for short-K / few-tile launches (mode 0 only)
     int ktot;
     int stats_tiles;    // per-image tile slots of the fused GroupNorm statistics (0 = not supported for this plan)
@@ -751,6 +828,20 @@ static int build_params(const mfb_conv_desc* d, int up_py, int up_px, const void
         const long t_wide = long(tiles_m) * ((d->Cout + bn - 1) / bn);
         if (t_wide * 10 < long(sms) * 7 && d->Cout > bn / 2) bn /= 2;
     }
+    // Split-K CTA pairs (MODE 3, opt-in: env MFB_IGEMM_SPLITK=1 or desc.igemm_mode 4): when even the WIDE tile leaves at least half
+    // of the SMs idle, keep it and give every tile two CTAs, each half of the K blocks (the halved tile is bound by shared-memory
+    // operand bandwidth: 26 KB of operands per 128 x 80 x 64 MMA block against 36 KB per 128 x 160 x 64).
+    bool splitk = false;
+    if (!d->geglu && d->block_n == 0) {
+        static const int env_sk = [] { const char* e = getenv("MFB_IGEMM_SPLITK"); return e ? atoi(e) : 0; }();
+        const int sms = device_sm_count() > 0 ? device_sm_count() : 148;
+        const int bw = d->Cout % 160 == 0 ? 160 : 128;
+        const long t_wide = long(tiles_m) * ((d->Cout + bw - 1) / bw);
+        if ((env_sk == 1 || d->igemm_mode == 4) && 2 * t_wide <= sms && ktot / BK >= 16) {
+            splitk = true;
+            bn = bw;
+        }
+    }
     if (d->block_n == 64 || d->block_n == 80 || d->block_n == 128 || d->block_n == 160) bn = d->block_n;
     MFB_REQUIRE(!d->geglu || bn == 128, "geglu requires block_n 128");
     pl->bn = bn;
@@ -773,6 +864,8 @@ static int build_params(const mfb_conv_desc* d, int up_py, int up_px, const void
         pl->mode = (tiles_m >= 2 && np) ? atoi(np) : 0;
         if (pl->mode < 0 || pl->mode > 2) pl->mode = 0;
         if (d->igemm_mode >= 1 && d->igemm_mode <= 3) pl->mode = tiles_m >= 2 ? d->igemm_mode - 1 : 0;
+        if (d->igemm_mode == 4) pl->mode = 0;        // split-K where the geometry qualifies, independent CTAs otherwise
+        if (splitk) pl->mode = 3;
     }
     {
         // MFB_IGEMM_EPIW = 16: all launches on the 16-epilogue-warp variant; = 1: only short K (<= 2560) and the few-tile 8x8
@@ -837,7 +930,9 @@ static int build_params(const mfb_conv_desc* d, int up_py, int up_px, const void
     }
     {
         const int sms = device_sm_count() > 0 ? device_sm_count() : 148;
-        if (pl->mode != 0) {
+        if (pl->mode == 3) {
+            pl->grid = dim3(unsigned(2 * long(p.tiles_m) * p.tiles_nn), 1, 1);     // one tile per pair (2 * tiles <= SMs)
+        } else if (pl->mode != 0) {
             const long pairs = long((p.tiles_m + 1) / 2) * p.tiles_nn;
             const long maxp = sms / 2;
             pl->grid = dim3(unsigned(2 * (pairs < maxp ? pairs : maxp)), 1, 1);
@@ -922,11 +1017,15 @@ static int run_one(const Plan& pl, const IgemmParams& prm, cudaStream_t st) {
             }
         }
     }
-    switch (pl.bn) {
-        case 160: return launch_igemm<160, MODE>(pl, prm, st);
-        case 128: return launch_igemm<128, MODE>(pl, prm, st);
-        case 80: return launch_igemm<80, MODE>(pl, prm, st);
-        default: return launch_igemm<64, MODE>(pl, prm, st);
+    if constexpr (MODE == 3) {       // split-K pairs exist for the wide tiles only
+        return pl.bn == 160 ? launch_igemm<160, 3>(pl, prm, st) : launch_igemm<128, 3>(pl, prm, st);
+    } else {
+        switch (pl.bn) {
+            case 160: return launch_igemm<160, MODE>(pl, prm, st);
+            case 128: return launch_igemm<128, MODE>(pl, prm, st);
+            case 80: return launch_igemm<80, MODE>(pl, prm, st);
+            default: return launch_igemm<64, MODE>(pl, prm, st);
+        }
     }
 }
 
@@ -943,8 +1042,8 @@ extern "C" int mfb_plan_run(mfb_plan* plan, void* stream) {
         return MFB_OK;
     }
     for (int i = 0; i < pl->nlaunch; ++i) {
-        const int rc = pl->mode == 2 ? run_one<2>(*pl, pl->p[i], st) : pl->mode == 1 ? run_one<1>(*pl, pl->p[i], st)
-                                                                                    : run_one<0>(*pl, pl->p[i], st);
+        const int rc = pl->mode == 3 ? run_one<3>(*pl, pl->p[i], st) : pl->mode == 2 ? run_one<2>(*pl, pl->p[i], st)
+                       : pl->mode == 1 ? run_one<1>(*pl, pl->p[i], st) : run_one<0>(*pl, pl->p[i], st);
         if (rc) return rc;
     }
     return MFB_OK;
@@ -974,6 +1073,8 @@ extern "C" int mfb_plan_destroy(mfb_plan* plan) {
 }
 
 extern "C" double mfb_plan_flops(const mfb_plan* plan) { return plan ? reinterpret_cast<const Plan*>(plan)->flops : 0.0; }
+
+extern "C" int mfb_plan_igemm_mode(const mfb_plan* plan) { return plan ? (reinterpret_cast<const Plan*>(plan)->f32 ? 0 : reinterpret_cast<const Plan*>(plan)->mode) : 0; }
 
 extern "C" int mfb_plan_ktotal(const mfb_plan* plan) {
     if (!plan) return 0;

@@ -190,6 +190,29 @@ __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
     asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+// ---- split-K CTA pair (igemm MODE 3): partial accumulators handed over through distributed shared memory
+// 16-byte store into a peer CTA's shared memory (cluster-shared address from mapa_shared)
+__device__ __forceinline__ void st_cluster_v4(uint32_t cluster_addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(cluster_addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+// mbarrier wait whose acquire covers writes made by the peer CTA before its (release.cluster) arrive; suspend-time hint like
+// mbar_wait_relaxed, bounded like every wait of this library
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+    for (uint32_t spins = 0;; ++spins) {
+        uint32_t ok;
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2, %3;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity), "r"(2000u)
+            : "memory");
+        if (ok) return;
+        if (spins > (1u << 21)) mbar_timeout_trap(bar, parity);      // seconds: a protocol bug traps, never hangs
+    }
+}
 // commit that arrives on the mbarrier at the same offset in every CTA of `mask`
 __device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),

@@ -42,6 +42,7 @@ _SIGS = {
     "mfb_plan_destroy": (i32, [vp]),
     "mfb_plan_flops": (f64, [vp]),
     "mfb_plan_ktotal": (i32, [vp]),
+    "mfb_plan_igemm_mode": (i32, [vp]),
     "mfb_plan_launches": (i32, [vp]),
     "mfb_plan_stats_floats": (i64, [vp]),
     "mfb_plan_stats_tiles": (i32, [vp]),

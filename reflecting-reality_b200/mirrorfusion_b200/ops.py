@@ -198,6 +198,7 @@ class ConvPlan:
         self._keep = (x, w, out, extras, bias, rowbias, alpha, res1, res2)
         self.flops = L.mfb_plan_flops(h)
         self.launches = L.mfb_plan_launches(h)
+        self.mode = L.mfb_plan_igemm_mode(h)      # 0 independent CTAs, 1 / 2 pair modes, 3 split-K pair
         Ho, Wo = (2 * H, 2 * W) if up2x else ((H + stride - 1) // stride, (W + stride - 1) // stride)
         # MMA work actually issued: the sub-pixel upsample plan runs 4 taps per output pixel where `flops` counts the 9 of the
         # reference's conv over the upsampled tensor

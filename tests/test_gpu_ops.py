@@ -167,6 +167,62 @@ def test_igemm_cluster_modes_agree(ops, B, H, W, Cin, Cout):
     assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
 
 
+@pytest.mark.parametrize("B,H,W,Cin,Cout,stride,variant", [
+    (16, 8, 8, 1280, 1280, 1, "plain"), (16, 8, 8, 1280, 1280, 1, "res1+rowbias"), (16, 8, 8, 320, 1280, 1, "odd K blocks"),
+    (16, 16, 16, 1280, 1280, 2, "stride 2"), (16, 8, 8, 1280, 1280, 1, "shortcut segments"), (4, 8, 8, 640, 640, 1, "plain"),
+    (16, 8, 8, 1280, 1280, 1, "up2x"), (3, 8, 8, 128, 256, 1, "ragged M")])
+def test_igemm_split_k_pair(ops, B, H, W, Cin, Cout, stride, variant):
+    """igemm_mode 4: few-tile launches (the 8x8 level: M = 64 * B) on the wide tile with TWO CTAs per tile, each half of the K
+    blocks, rank 1's fp32 partial accumulator handed to rank 0 through distributed shared memory.  Against torch AND against the
+    independent-CTA plan (fp32 sum split in two halves: equal to rounding of the bf16 output)."""
+    x = randn(B, H, W, Cin, seed=1)
+    w = randn(Cout, Cin, 3, 3, seed=2, scale=(9 * Cin) ** -0.5)
+    bias = randn(Cout, seed=3, dtype=torch.float32)
+    Ho, Wo = (2 * H, 2 * W) if variant == "up2x" else (H // stride, W // stride)
+    kw = dict(B=B, H=H, W=W, Cin=Cin, Cout=Cout, ksize=3, bias=bias)
+    ref = None
+    if variant == "up2x":
+        wp = ops.pack_upconv_weight(w.float())
+        kw["up2x"] = True
+        ref = F.conv2d(F.interpolate(nhwc_to_nchw(x), scale_factor=2.0, mode="nearest"), w.float(), bias, padding=1)
+    elif variant == "shortcut segments":
+        xa, xb = randn(B, H, W, 1280, seed=7), randn(B, H, W, 640, seed=8)
+        ws = randn(Cout, 1920, 1, 1, seed=9, scale=1920 ** -0.5)
+        wp = ops.pack_conv_weight(w.float(), extras=[ws.float()[:, :1280, 0, 0], ws.float()[:, 1280:, 0, 0]])
+        kw["extras"] = [xa, xb]
+        ref = F.conv2d(nhwc_to_nchw(x), w.float(), bias, padding=1) + F.conv2d(torch.cat([nhwc_to_nchw(xa), nhwc_to_nchw(xb)], 1), ws.float())
+    else:
+        wp = ops.pack_conv_weight(w.float())
+        kw["stride"] = stride
+        ref = F.conv2d(nhwc_to_nchw(x), w.float(), bias, stride=stride, padding=1)
+    if variant == "res1+rowbias":
+        r1 = randn(B, Ho, Wo, Cout, seed=5)
+        rowbias = randn(B, Cout, seed=4, dtype=torch.float32)
+        kw.update(res1=r1, rowbias=rowbias, rowbias_ld=Cout)
+        ref = ref + rowbias[:, :, None, None] + nhwc_to_nchw(r1)
+    outs = []
+    for mode in (4, 1):
+        o = torch.full((B, Ho, Wo, Cout), float("nan"), device="cuda", dtype=bf16)
+        plan = ops.ConvPlan(x, wp, o, igemm_mode=mode, **kw)
+        assert plan.mode == (3 if mode == 4 else 0), (mode, plan.mode)
+        plan.run()
+        torch.cuda.synchronize()
+        outs.append(o)
+    assert rel(nhwc_to_nchw(outs[0]), ref) < 4e-3
+    assert rel(outs[0].float(), outs[1].float()) < 2e-3          # differ only where the two-half sum rounds to another bf16 value
+    # deterministic: the hand-over adds the halves in a fixed order
+    o2 = torch.full_like(outs[0], float("nan"))
+    ops.ConvPlan(x, wp, o2, igemm_mode=4, **kw).run()
+    assert torch.equal(o2, outs[0])
+
+
+def test_igemm_split_k_falls_back_when_the_tile_count_is_large(ops):
+    x = randn(8, 32, 32, 128, seed=1)                      # 64 M tiles x 2 N tiles: more tiles than CTA pairs
+    wp = ops.pack_conv_weight(randn(320, 128, 3, 3, seed=2, scale=0.03).float())
+    o = torch.empty(8, 32, 32, 320, device="cuda", dtype=bf16)
+    assert ops.ConvPlan(x, wp, o, B=8, H=32, W=32, Cin=128, Cout=320, ksize=3, igemm_mode=4).mode == 0
+
+
 def test_persistent_tile_loop_many_tiles(ops):
     # far more tiles than SMs: every CTA walks several tiles through both TMEM accumulator slots
     M, K, N = 40000, 128, 640
